@@ -1,0 +1,180 @@
+/*
+ * riders_b200 - C ABI of the B200-native RIDERS radar-to-dense-depth hot path.
+ *
+ * Drop-in boundary.  The reference (MMOCKING/RIDERS) is
+ * pure Python: its "FFI" for this path is the set of Python call sites listed
+ * beside each entry point below (paths relative to the reference repo).  A
+ * maintainer binds this library with ctypes and keeps the
+ * Python classes / signatures unchanged.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - all tensors are dense float32 unless stated; layouts are spelled per call;
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous and
+ *     never synchronise; workspaces are caller-owned (size from *_workspace_bytes);
+ *   - return 0 on success, a negative RIDERS_E* code otherwise;
+ *     riders_last_error_string() describes the last failure on this thread;
+ *   - no CPU fallback exists: without an sm_100 device every launch returns
+ *     RIDERS_ENODEVICE / RIDERS_ECUDA.
+ */
+#ifndef RIDERS_B200_H_
+#define RIDERS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RIDERS_OK          0
+#define RIDERS_EINVAL     -1   /* bad argument (shape, null pointer, unsupported size)        */
+#define RIDERS_ECUDA      -2   /* CUDA runtime error at launch                                */
+#define RIDERS_ENODEVICE  -3   /* no sm_100 device / kernel image not loadable                */
+#define RIDERS_EQHULL     -4   /* triangulation impossible (<3 knots or all collinear)        */
+
+#define RIDERS_LAYOUT_NCHW 0
+#define RIDERS_LAYOUT_NHWC 1   /* torch channels_last: logical NCHW, memory N,H,W,C            */
+
+#define RIDERS_MAX_LEVELS 8
+
+const char* riders_last_error_string(void);
+int         riders_abi_version(void);
+/* compute capability major*10+minor of the current device, or <0 */
+int         riders_device_arch(void);
+
+/* ------------------------------------------------------------------------------------------
+ * A1  per-radar-point feature gather  ==  torchvision.ops.roi_pool x n_levels
+ *     replaces RCNet/networks.py:418-433 (5 calls: latent @1/32 + skips @1/2..1/16).
+ *     feat[l]   : (B, C[l], Hl[l], Wl[l]) in `layout`
+ *     rois      : (R, 5) rows (batch_index, x1, y1, x2, y2), RoI order = output order
+ *     out[l]    : (R, C[l], oh[l], ow[l]) in the SAME layout
+ *     argmax[l] : optional int32, same shape/layout as out[l]; flat index h*Wl+w of the
+ *                 selected input element, -1 for an empty bin (needed by the backward)
+ *     max_roi_w/h : upper bound of (x2-x1)/(y2-y1) in image pixels (RC-Net: the patch size);
+ *                 sizes the TMA staging box of the channels-last path.  0 = unknown (generic
+ *                 kernel); RoIs that exceed the bound are still correct (in-kernel direct reads).
+ *     Bit-exact with torchvision's RoIPool (quantised coords, float32 bin edges, first max).
+ * ------------------------------------------------------------------------------------------ */
+int riders_roi_gather_fwd(int n_levels,
+                          const float* const* feat, const int* C, const int* Hl, const int* Wl,
+                          const float* spatial_scale, const int* oh, const int* ow,
+                          int layout, int B,
+                          const float* rois, int R,
+                          int max_roi_w, int max_roi_h,
+                          float* const* out, int32_t* const* argmax,
+                          void* stream);
+
+/* gradient of A1 w.r.t. feat: deterministic (no float atomics); grad_feat must be zero-filled
+ * by the caller.  Used by rcnet_main.train (RCNet/rcnet_main.py:342-358).                    */
+int riders_roi_gather_bwd(int n_levels,
+                          const float* const* grad_out, const int32_t* const* argmax,
+                          const int* C, const int* Hl, const int* Wl, const int* oh, const int* ow,
+                          const float* spatial_scale,
+                          int layout, int B, const float* rois, int R,
+                          float* const* grad_feat, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A2  LinearAttention.forward           RCNet/linear_attention.py:18-45
+ *     q (N,L,H,D), k,v (N,S,H,D), masks (N,L)/(N,S) float or NULL, out (N,L,H,D)
+ * ------------------------------------------------------------------------------------------ */
+int riders_linear_attention_fwd(const float* q, const float* k, const float* v,
+                                const float* q_mask, const float* kv_mask,
+                                int N, int L, int S, int H, int D, float eps,
+                                float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A3  LoFTREncoderLayer.forward         RCNet/linear_attention.py:112-135
+ *     x (N,L,C), src (N,S,C) -> out (N,L,C); all six linears are bias-free, row-major
+ *     (out_features, in_features) exactly as torch stores nn.Linear.weight:
+ *       wq,wk,wv,wm (C,C); w1 (2C,2C); w2 (C,2C); LayerNorm gamma/beta (C).
+ *     impl: RIDERS_LOFTR_SIMT    fp32 FFMA kernels (any C%16==0), bit-for-bit fp32 semantics
+ *           RIDERS_LOFTR_TCGEN05 fused tensor-core layer (C=128, nhead=8, L=S=21 tokens):
+ *                                tcgen05.mma kind::tf32 with a 3-term hi/lo split (fp32-accurate)
+ *     workspace: riders_loftr_workspace_bytes(N, max(L,S), C, impl) bytes, 256-byte aligned.
+ * ------------------------------------------------------------------------------------------ */
+#define RIDERS_LOFTR_SIMT     0
+#define RIDERS_LOFTR_TCGEN05  1
+
+typedef struct {
+    const float* wq; const float* wk; const float* wv; const float* wm;
+    const float* w1; const float* w2;
+    const float* ln1_g; const float* ln1_b; const float* ln2_g; const float* ln2_b;
+} riders_loftr_weights;
+
+size_t riders_loftr_workspace_bytes(int N, int tokens, int d_model, int impl);
+
+int riders_loftr_layer_fwd(const float* x, const float* src, const riders_loftr_weights* w,
+                           int N, int L, int S, int d_model, int nhead,
+                           float attn_eps, float ln_eps, int impl,
+                           float* out, void* workspace, void* stream);
+
+/* A4  LocalFeatureTransformer.forward   RCNet/linear_attention.py:159-184
+ *     layer_kind[i]: 0 = 'self' (f0=layer(f0,f0); f1=layer(f1,f1)), 1 = 'cross'
+ *     (f0=layer(f0,f1); f1=layer(f1,f0_new)).  feat0 (N,L,C), feat1 (N,S,C) are not modified;
+ *     results land in out0/out1 (may alias nothing else).  `layers` is a HOST array.           */
+int riders_loftr_transformer_fwd(const float* feat0, const float* feat1,
+                                 const riders_loftr_weights* layers, const int* layer_kind, int n_layers,
+                                 int N, int L, int S, int d_model, int nhead,
+                                 float attn_eps, float ln_eps, int impl,
+                                 float* out0, float* out1, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A5  thresholded confidence -> quasi-dense depth   RCNet/rcnet_main.py:460-487
+ *     conf (R, ph, pw): per-point correspondence crops; if conf_is_logits != 0 the kernel
+ *                       applies the sigmoid of RCNetModel.forward (rcnet_model.py:123) itself
+ *     pts (R,3): pad-shifted (x, y, z) exactly as forward_output receives them
+ *     frame_offsets (B+1) int32 DEVICE prefix of points per frame (ragged K)
+ *     depth, response (B,H,W) float32; select (B,H,W) int32 = argmax point index within the
+ *     frame (first maximum; 0 where nothing fired), may be NULL.
+ * ------------------------------------------------------------------------------------------ */
+int riders_confidence_reduce(const float* conf, int conf_is_logits,
+                             const float* pts, const int* frame_offsets,
+                             int B, int H, int W, int ph, int pw, float thr,
+                             float* depth, float* response, int32_t* select,
+                             void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A6/A7  compute_scale_and_shift_ls + LeastSquaresEstimator.apply/clamp
+ *        modules/estimator.py:5-29, 108-125
+ *     pred, target (B,H,W) float32; mask (B,H,W) uint8 (numpy/torch bool)
+ *     sums (B,5) double out: a00,a01,a11,b0,b1 (deterministic fp64 tree, may be NULL)
+ *     scale_shift (B,2) double out (0,0 when det <= 0)
+ *     out (B,H,W) float32 or NULL: float32(float32(pred*float32(scale)) + float32(shift)),
+ *     then out[out > clamp_hi] = clamp_hi if (clamp_flags & 1), out[out < clamp_lo] = clamp_lo
+ *     if (clamp_flags & 2); the caller passes clamp_hi = float32(1/clamp_min) and
+ *     clamp_lo = float32(1/clamp_max) (estimator.py:115-125; clamp_min <= 0 clears bit 0).
+ * ------------------------------------------------------------------------------------------ */
+size_t riders_lsq_workspace_bytes(int B, int H, int W);
+int riders_lsq_align(const float* pred, const float* target, const uint8_t* mask,
+                     int B, int H, int W,
+                     double* sums, double* scale_shift,
+                     float* out, float clamp_hi, float clamp_lo, int clamp_flags,
+                     void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A8  Interpolator2D / interpolate_knots(method='linear')   modules/interpolator.py:7-50
+ *     riders_extract_knots: row-major scan of `valid` -> knot_xy (B,max_knots,2) int32 (x,y),
+ *       knot_scale = sparse/pred, knot_shift = sparse-pred (float32), knot_count (B) int32.
+ *     riders_interp_linear: Delaunay triangulation of each frame's knots on the device
+ *       (exact integer predicates) + per-pixel barycentric fill in fp64, `fill` outside the
+ *       convex hull, float32 out (B,H,W).  status (B) int32: 0 ok, RIDERS_EQHULL where SciPy
+ *       would raise QhullError.  Knots of frame b are knot_xy[b*max_knots .. +knot_count[b]).
+ *       If tri_out != NULL it receives the triangles (B, 2*max_knots, 3) int32 (-1 padded) and
+ *       tri_count (B).
+ * ------------------------------------------------------------------------------------------ */
+int riders_extract_knots(const float* pred, const float* sparse, const uint8_t* valid,
+                         int B, int H, int W, int max_knots,
+                         int32_t* knot_xy, float* knot_scale, float* knot_shift, int32_t* knot_count,
+                         void* workspace, void* stream);
+size_t riders_interp_workspace_bytes(int B, int max_knots, int H, int W);
+int riders_interp_linear(const int32_t* knot_xy, const float* knot_val, const int32_t* knot_count,
+                         int B, int max_knots, int H, int W, float fill,
+                         float* out, int32_t* status,
+                         int32_t* tri_out, int32_t* tri_count,
+                         void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIDERS_B200_H_ */

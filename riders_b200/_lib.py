@@ -1,0 +1,72 @@
+"""ctypes binding of ``libriders_b200.so`` (the C ABI declared in include/riders_b200.h).
+
+There is deliberately no fallback: if the shared library has not been built
+(``python -c 'import __graft_entry__ as g; g.build()'`` or ``make -C riders_b200/csrc``)
+every op raises.  PyTorch only supplies device memory and streams.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libriders_b200.so")
+
+RIDERS_OK = 0
+RIDERS_EINVAL, RIDERS_ECUDA, RIDERS_ENODEVICE, RIDERS_EQHULL = -1, -2, -3, -4
+LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
+LOFTR_SIMT, LOFTR_TCGEN05 = 0, 1
+MAX_LEVELS = 8
+
+vp, ci, cf, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+
+
+class LoftrWeights(C.Structure):
+    """riders_loftr_weights (include/riders_b200.h)."""
+    _fields_ = [(n, vp) for n in ("wq", "wk", "wv", "wm", "w1", "w2", "ln1_g", "ln1_b", "ln2_g", "ln2_b")]
+
+
+# name -> (restype, argtypes); must list every symbol of include/riders_b200.h
+SIGNATURES = {
+    "riders_last_error_string": (C.c_char_p, []),
+    "riders_abi_version": (ci, []),
+    "riders_device_arch": (ci, []),
+    "riders_roi_gather_fwd": (ci, [ci, vp, vp, vp, vp, vp, vp, vp, ci, ci, vp, ci, ci, ci, vp, vp, vp]),
+    "riders_roi_gather_bwd": (ci, [ci, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, vp, ci, vp, vp]),
+    "riders_linear_attention_fwd": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp, vp]),
+    "riders_loftr_workspace_bytes": (sz, [ci, ci, ci, ci]),
+    "riders_loftr_layer_fwd": (ci, [vp, vp, C.POINTER(LoftrWeights), ci, ci, ci, ci, ci, cf, cf, ci, vp, vp, vp]),
+    "riders_loftr_transformer_fwd": (ci, [vp, vp, C.POINTER(LoftrWeights), C.POINTER(ci), ci,
+                                          ci, ci, ci, ci, ci, cf, cf, ci, vp, vp, vp, vp]),
+    "riders_confidence_reduce": (ci, [vp, ci, vp, vp, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp]),
+    "riders_lsq_workspace_bytes": (sz, [ci, ci, ci]),
+    "riders_lsq_align": (ci, [vp, vp, vp, ci, ci, ci, vp, vp, vp, cf, cf, ci, vp, vp]),
+}
+
+_lib = None
+
+
+class RidersError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "riders_b200: %s is missing - build the CUDA extension first "
+                "(`make -C riders_b200/csrc` or __graft_entry__.build()); there is no CPU fallback" % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError if the .so is stale
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def last_error():
+    return lib().riders_last_error_string().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc != RIDERS_OK:
+        raise RidersError("%s failed (code %d): %s" % (what, rc, last_error()))

@@ -1,0 +1,27 @@
+// Shared helpers for the riders_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/riders_b200.h"
+
+namespace riders {
+
+void set_error(const char* fmt, ...);
+int  check_launch(const char* what);          // cudaGetLastError -> RIDERS_* code
+int  sm_count();
+
+#define RIDERS_REQUIRE(cond, ...)                         \
+    do { if (!(cond)) { riders::set_error(__VA_ARGS__); return RIDERS_EINVAL; } } while (0)
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float ld_stream(const float* p) {
+    // read-once data: bypass L1 allocation
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+}  // namespace riders

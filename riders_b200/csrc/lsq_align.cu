@@ -1,0 +1,199 @@
+// A6/A7: global scale/shift least squares + apply + clamp (modules/estimator.py:5-29,108-125).
+//
+// Pass 1 (lsq_partial_kernel): every CTA owns a fixed, contiguous PX_PER_CTA-pixel slice of one
+//   frame, reads the mask first and touches pred/target only where the mask is set, accumulates
+//   the five normal-equation sums in fp64 and reduces them with a fixed shuffle/smem tree ->
+//   partial[frame][cta][5].  The slice size does not depend on the SM count, so the result is
+//   bit-reproducible on any device.
+// Pass 2 (lsq_apply_kernel): every CTA re-adds its frame's partials in index order (same value
+//   in every CTA), solves the 2x2 system in fp64 (det > 0 guard, estimator.py:22-27), and
+//   streams out = fl32(fl32(pred*s) + t) with the two clamps.  CTA 0 of each frame publishes
+//   sums / scale / shift.
+//
+// HBM roofline: 9 B/pixel read in pass 1 (mask-gated to >= 1 B/pixel), 4 B read + 4 B written
+// in pass 2 (the re-read of pred is an L2 hit for batches that fit the 126 MB L2).
+#include "common.cuh"
+
+namespace riders {
+
+constexpr int LSQ_THREADS = 256;
+constexpr int PX_PER_THREAD = 16;
+constexpr int PX_PER_CTA = LSQ_THREADS * PX_PER_THREAD;     // 4096
+
+struct Sums5 { double v[5]; };
+
+__device__ __forceinline__ void accumulate(Sums5& s, float pf, float tf) {
+    const double p = (double)pf, t = (double)tf;
+    s.v[0] += p * p;     // a00 = sum m*p*p   (products of two float32 are exact in fp64)
+    s.v[1] += p;         // a01 = sum m*p
+    s.v[2] += 1.0;       // a11 = sum m
+    s.v[3] += p * t;     // b0  = sum m*p*t
+    s.v[4] += t;         // b1  = sum m*t
+}
+
+__device__ __forceinline__ void block_reduce5(Sums5& s, double (*sm)[5]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s.v[q] += __shfl_down_sync(0xffffffffu, s.v[q], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) sm[warp][q] = s.v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double a = 0.0;
+#pragma unroll
+        for (int w = 0; w < LSQ_THREADS / 32; ++w) a += sm[w][threadIdx.x];
+        sm[0][threadIdx.x] = a;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(LSQ_THREADS)
+lsq_partial_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                   const uint8_t* __restrict__ mask, int npx, int ctas_per_frame,
+                   double* __restrict__ partial) {
+    __shared__ double sm[LSQ_THREADS / 32][5];
+    const int frame = blockIdx.y, cta = blockIdx.x;
+    const size_t fo = (size_t)frame * npx;
+    const float* p = pred + fo;
+    const float* t = target + fo;
+    const uint8_t* m = mask + fo;
+    const int begin = cta * PX_PER_CTA;
+    const int end = min(begin + PX_PER_CTA, npx);
+    Sums5 s = {{0, 0, 0, 0, 0}};
+
+    const bool vec_ok = ((npx & 3) == 0) && ((((uintptr_t)m) & 3) == 0) &&
+                        ((((uintptr_t)p) & 15) == 0) && ((((uintptr_t)t) & 15) == 0);
+    if (vec_ok) {
+#pragma unroll
+        for (int it = 0; it < PX_PER_THREAD / 4; ++it) {
+            const int i = begin + (it * LSQ_THREADS + threadIdx.x) * 4;
+            if (i < end) {
+                const uint32_t mm = *reinterpret_cast<const uint32_t*>(m + i);
+                if (mm) {
+                    const float4 pv = *reinterpret_cast<const float4*>(p + i);
+                    const float4 tv = *reinterpret_cast<const float4*>(t + i);
+                    if (mm & 0x000000ffu) accumulate(s, pv.x, tv.x);
+                    if (mm & 0x0000ff00u) accumulate(s, pv.y, tv.y);
+                    if (mm & 0x00ff0000u) accumulate(s, pv.z, tv.z);
+                    if (mm & 0xff000000u) accumulate(s, pv.w, tv.w);
+                }
+            }
+        }
+    } else {
+        // same pixel -> thread assignment as the vector path, so the sums are layout-independent
+        for (int it = 0; it < PX_PER_THREAD / 4; ++it) {
+            const int i = begin + (it * LSQ_THREADS + threadIdx.x) * 4;
+            for (int e = 0; e < 4; ++e)
+                if (i + e < end && m[i + e]) accumulate(s, p[i + e], t[i + e]);
+        }
+    }
+    block_reduce5(s, sm);
+    if (threadIdx.x < 5)
+        partial[((size_t)frame * ctas_per_frame + cta) * 5 + threadIdx.x] = sm[0][threadIdx.x];
+}
+
+__device__ __forceinline__ void solve_frame(const double* __restrict__ partial, int ctas_per_frame,
+                                            double* sm5, double* sm_ss) {
+    // fixed-order sum of the per-CTA partials (identical in every CTA of the frame):
+    // warp q adds sum q; lane l takes CTAs l, l+32, ... in order, then a fixed shuffle tree
+    const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+    if (q < 5) {
+        double a = 0.0;
+        for (int c = lane; c < ctas_per_frame; c += 32) a += partial[(size_t)c * 5 + q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+        if (lane == 0) sm5[q] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double a00 = sm5[0], a01 = sm5[1], a11 = sm5[2], b0 = sm5[3], b1 = sm5[4];
+        const double det = a00 * a11 - a01 * a01;                 // estimator.py:22
+        double x0 = 0.0, x1 = 0.0;
+        if (det > 0.0) {                                           // estimator.py:24
+            x0 = (a11 * b0 - a01 * b1) / det;
+            x1 = (-a01 * b0 + a00 * b1) / det;
+        }
+        sm_ss[0] = x0;
+        sm_ss[1] = x1;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(LSQ_THREADS)
+lsq_apply_kernel(const float* __restrict__ pred, const double* __restrict__ partial,
+                 int npx, int ctas_per_frame,
+                 double* __restrict__ sums, double* __restrict__ scale_shift,
+                 float* __restrict__ out, float clamp_hi, float clamp_lo, int clamp_flags) {
+    __shared__ double sm5[5];
+    __shared__ double sm_ss[2];
+    const int frame = blockIdx.y, cta = blockIdx.x;
+    solve_frame(partial + (size_t)frame * ctas_per_frame * 5, ctas_per_frame, sm5, sm_ss);
+    if (cta == 0) {
+        if (sums && threadIdx.x < 5) sums[frame * 5 + threadIdx.x] = sm5[threadIdx.x];
+        if (scale_shift && threadIdx.x < 2) scale_shift[frame * 2 + threadIdx.x] = sm_ss[threadIdx.x];
+    }
+    if (!out) return;
+    const float s = (float)sm_ss[0], t = (float)sm_ss[1];          // 0-d float32 in the reference
+    const size_t fo = (size_t)frame * npx;
+    const float* p = pred + fo;
+    float* o = out + fo;
+    const int begin = cta * PX_PER_CTA;
+    const int end = min(begin + PX_PER_CTA, npx);
+    const bool hi_on = clamp_flags & 1, lo_on = clamp_flags & 2;
+    auto f = [&](float v) {
+        float r = __fadd_rn(__fmul_rn(v, s), t);                   // two roundings, no FMA (estimator.py:113)
+        if (hi_on && r > clamp_hi) r = clamp_hi;
+        if (lo_on && r < clamp_lo) r = clamp_lo;
+        return r;
+    };
+    const bool vec_ok = ((npx & 3) == 0) && ((((uintptr_t)p) & 15) == 0) && ((((uintptr_t)o) & 15) == 0);
+#pragma unroll
+    for (int it = 0; it < PX_PER_THREAD / 4; ++it) {
+        const int i = begin + (it * LSQ_THREADS + threadIdx.x) * 4;
+        if (vec_ok) {
+            if (i < end) {
+                float4 v = *reinterpret_cast<const float4*>(p + i);
+                v.x = f(v.x); v.y = f(v.y); v.z = f(v.z); v.w = f(v.w);
+                *reinterpret_cast<float4*>(o + i) = v;
+            }
+        } else {
+            for (int e = 0; e < 4; ++e)
+                if (i + e < end) o[i + e] = f(p[i + e]);
+        }
+    }
+}
+
+}  // namespace riders
+
+extern "C" size_t riders_lsq_workspace_bytes(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    const size_t ctas = (size_t)riders::ceil_div(H * W, riders::PX_PER_CTA);
+    return (size_t)B * ctas * 5 * sizeof(double);
+}
+
+extern "C" int riders_lsq_align(const float* pred, const float* target, const uint8_t* mask,
+                                int B, int H, int W, double* sums, double* scale_shift,
+                                float* out, float clamp_hi, float clamp_lo, int clamp_flags,
+                                void* workspace, void* stream) {
+    using namespace riders;
+    RIDERS_REQUIRE(B >= 0 && H > 0 && W > 0, "lsq_align: bad shape B=%d H=%d W=%d", B, H, W);
+    RIDERS_REQUIRE((long long)H * W < (1ll << 30), "lsq_align: frame too large");
+    RIDERS_REQUIRE(B <= 65535, "lsq_align: at most 65535 frames per call");
+    if (B == 0) return RIDERS_OK;
+    RIDERS_REQUIRE(pred && target && mask && workspace, "lsq_align: null pointer");
+    RIDERS_REQUIRE((((uintptr_t)workspace) & 7) == 0, "lsq_align: workspace must be 8-byte aligned");
+    const int npx = H * W;
+    const int ctas = ceil_div(npx, PX_PER_CTA);
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(ctas, B);
+    lsq_partial_kernel<<<grid, LSQ_THREADS, 0, st>>>(pred, target, mask, npx, ctas, (double*)workspace);
+    dim3 grid2(out ? ctas : 1, B);
+    lsq_apply_kernel<<<grid2, LSQ_THREADS, 0, st>>>(pred, (const double*)workspace, npx, ctas, sums, scale_shift,
+                                                    out, clamp_hi, clamp_lo, clamp_flags);
+    return check_launch("lsq_align");
+}

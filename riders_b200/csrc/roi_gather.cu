@@ -1,0 +1,448 @@
+// A1: per-radar-point feature gather == torchvision.ops.roi_pool on every pyramid level
+// (replaces the five calls at RCNet/networks.py:418-433 of the reference).
+//
+// The op is a pure selection (max over a quantised window), so results are bit-exact.
+// Roofline: HBM-write bound - every RoI writes C*oh*ow floats per level (1.39 MB per radar point
+// at patch 240x100) while the feature maps (32.6 MB per frame) are read through L2.
+//
+// Two forward paths:
+//   * roi_gather_tma_kernel  (channels-last maps): one CTA = one RoI x a strip of pooled rows.
+//     The input window of the strip is staged into shared memory by ONE 4-D TMA tile load
+//     (cp.async.bulk.tensor, box = C x BW x BH x 1, out-of-map parts zero-filled and never
+//     read because bins are clipped).  Threads then take the bin maxima as float4 over
+//     channels and stream them out fully coalesced.  Several CTAs per SM overlap load and math.
+//   * roi_gather_generic_kernel (any layout, any RoI size, optional argmax): one thread per
+//     pooled element (NCHW) or per 4 channels (NHWC), reading the window through L1/L2.
+// Backward (training, RCNet/rcnet_main.py:342-358): deterministic gather formulation - one
+// thread per input element visits, in RoI order, the few bins that can contain it and adds
+// the gradients whose argmax points at it.  No float atomics.
+#include "common.cuh"
+#include "roi_bins.cuh"
+#include <cuda.h>
+#include <float.h>
+
+namespace riders {
+
+struct GatherLevel {
+    const float* feat; float* out; int32_t* argmax;
+    int C, H, W, oh, ow;
+    float scale;
+    long long first_item;      // prefix of work items (generic kernel)
+};
+struct GatherParams {
+    GatherLevel lv[RIDERS_MAX_LEVELS];
+    int n_levels;
+    int B, R;
+    const float* rois;
+    long long total_items;
+};
+
+constexpr int GEN_THREADS = 256;
+
+// ---------------------------------------------------------------------------------------------
+// generic kernel
+// ---------------------------------------------------------------------------------------------
+template <bool NHWC>
+__global__ void __launch_bounds__(GEN_THREADS)
+roi_gather_generic_kernel(const GatherParams P) {
+    const long long item = (long long)blockIdx.x * GEN_THREADS + threadIdx.x;
+    if (item >= P.total_items) return;
+    int l = 0;
+#pragma unroll
+    for (int q = 1; q < RIDERS_MAX_LEVELS; ++q)
+        if (q < P.n_levels && item >= P.lv[q].first_item) l = q;
+    const GatherLevel& L = P.lv[l];
+    long long e = item - L.first_item;
+    const int CV = NHWC ? (L.C >> 2) : L.C;          // channel groups
+    int r, c, i, j;
+    if (NHWC) {
+        c = (int)(e % CV); e /= CV;
+        j = (int)(e % L.ow); e /= L.ow;
+        i = (int)(e % L.oh); r = (int)(e / L.oh);
+    } else {
+        j = (int)(e % L.ow); e /= L.ow;
+        i = (int)(e % L.oh); e /= L.oh;
+        c = (int)(e % CV); r = (int)(e / CV);
+    }
+    const float* roi = P.rois + (size_t)r * 5;
+    const int b = (int)roi[0];
+    const RoiAxis ax = roi_axis(roi[1], roi[3], L.scale, L.ow);
+    const RoiAxis ay = roi_axis(roi[2], roi[4], L.scale, L.oh);
+    int w0, w1, h0, h1;
+    roi_bin_range(ax, j, L.W, w0, w1);
+    roi_bin_range(ay, i, L.H, h0, h1);
+    const bool empty = (h1 <= h0) || (w1 <= w0) || b < 0 || b >= P.B;
+
+    if (NHWC) {
+        float4 best = empty ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+        int4 arg = make_int4(-1, -1, -1, -1);
+        if (!empty) {
+            const float* base = L.feat + (size_t)b * L.H * L.W * L.C + (size_t)c * 4;
+            for (int h = h0; h < h1; ++h)
+                for (int w = w0; w < w1; ++w) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(base + ((size_t)h * L.W + w) * L.C));
+                    const int idx = h * L.W + w;
+                    if (v.x > best.x) { best.x = v.x; arg.x = idx; }
+                    if (v.y > best.y) { best.y = v.y; arg.y = idx; }
+                    if (v.z > best.z) { best.z = v.z; arg.z = idx; }
+                    if (v.w > best.w) { best.w = v.w; arg.w = idx; }
+                }
+        }
+        const size_t o = (((size_t)r * L.oh + i) * L.ow + j) * L.C + (size_t)c * 4;
+        __stcs(reinterpret_cast<float4*>(L.out + o), best);
+        if (L.argmax) __stcs(reinterpret_cast<int4*>(L.argmax + o), arg);
+    } else {
+        float best = empty ? 0.f : -FLT_MAX;
+        int arg = -1;
+        if (!empty) {
+            const float* base = L.feat + ((size_t)b * L.C + c) * L.H * L.W;
+            for (int h = h0; h < h1; ++h)
+                for (int w = w0; w < w1; ++w) {
+                    const float v = __ldg(base + (size_t)h * L.W + w);
+                    if (v > best) { best = v; arg = h * L.W + w; }
+                }
+        }
+        const size_t o = (((size_t)r * L.C + c) * L.oh + i) * L.ow + j;
+        __stcs(L.out + o, best);
+        if (L.argmax) __stcs(L.argmax + o, arg);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA-staged channels-last kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int TMA_THREADS = 256;
+
+struct TmaLevel {
+    const float* feat; float* out;
+    int C, H, W, oh, ow;
+    float scale;
+    int TI;          // pooled rows per CTA
+    int BH, BW;      // TMA box rows / cols
+    int B;
+    const float* rois;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+
+__global__ void __launch_bounds__(TMA_THREADS)
+roi_gather_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaLevel L) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ short2 wbin[256];        // per pooled column: [w0, w1) relative to the staged window
+    __shared__ short2 hbin[64];         // per pooled row of this strip
+    __shared__ int s_fallback;
+
+    float* tile = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    const int r = blockIdx.y;
+    const int i0 = blockIdx.x * L.TI;
+    const int ni = min(L.TI, L.oh - i0);
+    const float* roi = L.rois + (size_t)r * 5;
+    const int b = (int)roi[0];
+    const RoiAxis ax = roi_axis(roi[1], roi[3], L.scale, L.ow);
+    const RoiAxis ay = roi_axis(roi[2], roi[4], L.scale, L.oh);
+
+    // unclipped first input row of the strip and first input col of the RoI = window origin
+    const int win_h = (int)floorf(__fmul_rn((float)i0, ay.bin)) + ay.start;
+    const int win_w = ax.start;
+    const int last_h = (int)ceilf(__fmul_rn((float)(i0 + ni), ay.bin)) + ay.start;    // exclusive
+    const int last_w = (int)ceilf(__fmul_rn((float)L.ow, ax.bin)) + ax.start;
+    const bool fits = (last_h - win_h <= L.BH) && (last_w - win_w <= L.BW) && b >= 0 && b < L.B;
+
+    if (threadIdx.x == 0) {
+        s_fallback = fits ? 0 : 1;
+        if (fits) {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            const uint32_t bytes = (uint32_t)L.BH * L.BW * L.C * 4u;
+            mbar_expect_tx(&bar, bytes);
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+                " [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                ::"r"(smem_u32(tile)), "l"(&tmap), "r"(0), "r"(win_w), "r"(win_h), "r"(b), "r"(smem_u32(&bar))
+                : "memory");
+        }
+    }
+    // bin tables (clipped to the map, then made window-relative)
+    for (int j = threadIdx.x; j < L.ow; j += TMA_THREADS) {
+        int w0, w1;
+        roi_bin_range(ax, j, L.W, w0, w1);
+        wbin[j] = make_short2((short)(w0 - win_w), (short)(w1 - win_w));
+    }
+    for (int i = threadIdx.x; i < ni; i += TMA_THREADS) {
+        int h0, h1;
+        roi_bin_range(ay, i0 + i, L.H, h0, h1);
+        hbin[i] = make_short2((short)(h0 - win_h), (short)(h1 - win_h));
+    }
+    __syncthreads();
+
+    const int CV = L.C >> 2;
+    const int n_items = ni * L.ow * CV;
+    float* out_base = L.out + (((size_t)r * L.oh + i0) * L.ow) * L.C;
+
+    if (s_fallback) {
+        // RoI larger than the staged box (or bad batch index): read the map directly
+        const bool bad = b < 0 || b >= L.B;
+        const float* base = L.feat + (size_t)(bad ? 0 : b) * L.H * L.W * L.C;
+        for (int t = threadIdx.x; t < n_items; t += TMA_THREADS) {
+            const int c = t % CV, j = (t / CV) % L.ow, i = t / (CV * L.ow);
+            const short2 hb = hbin[i], wb = wbin[j];
+            const bool empty = hb.y <= hb.x || wb.y <= wb.x || bad;
+            float4 best = empty ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+            if (!empty)
+                for (int h = hb.x + win_h; h < hb.y + win_h; ++h)
+                    for (int w = wb.x + win_w; w < wb.y + win_w; ++w) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(base + ((size_t)h * L.W + w) * L.C + c * 4));
+                        best.x = fmaxf(best.x, v.x); best.y = fmaxf(best.y, v.y);
+                        best.z = fmaxf(best.z, v.z); best.w = fmaxf(best.w, v.w);
+                    }
+            __stcs(reinterpret_cast<float4*>(out_base + (size_t)t * 4), best);
+        }
+        return;
+    }
+
+    mbar_wait(&bar, 0);
+    const int row_stride = L.BW * L.C;            // floats
+    for (int t = threadIdx.x; t < n_items; t += TMA_THREADS) {
+        const int c = t % CV, j = (t / CV) % L.ow, i = t / (CV * L.ow);
+        const short2 hb = hbin[i], wb = wbin[j];
+        const bool empty = hb.y <= hb.x || wb.y <= wb.x;
+        float4 best = empty ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+        if (!empty) {
+            const float* p0 = tile + c * 4;
+            for (int h = hb.x; h < hb.y; ++h) {
+                const float* prow = p0 + h * row_stride;
+                for (int w = wb.x; w < wb.y; ++w) {
+                    const float4 v = *reinterpret_cast<const float4*>(prow + w * L.C);
+                    best.x = fmaxf(best.x, v.x); best.y = fmaxf(best.y, v.y);
+                    best.z = fmaxf(best.z, v.z); best.w = fmaxf(best.w, v.w);
+                }
+            }
+        }
+        __stcs(reinterpret_cast<float4*>(out_base + (size_t)t * 4), best);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// deterministic backward
+// ---------------------------------------------------------------------------------------------
+struct GatherBwdLevel {
+    const float* grad_out; const int32_t* argmax; float* grad_feat;
+    int C, H, W, oh, ow;
+    float scale;
+};
+
+template <bool NHWC>
+__global__ void __launch_bounds__(GEN_THREADS)
+roi_gather_bwd_kernel(const GatherBwdLevel L, const float* __restrict__ rois, int R, int B) {
+    const long long n = (long long)B * L.C * L.H * L.W;
+    const long long e0 = (long long)blockIdx.x * GEN_THREADS + threadIdx.x;
+    if (e0 >= n) return;
+    long long e = e0;
+    int b, c, h, w;
+    if (NHWC) { c = (int)(e % L.C); e /= L.C; w = (int)(e % L.W); e /= L.W; h = (int)(e % L.H); b = (int)(e / L.H); }
+    else      { w = (int)(e % L.W); e /= L.W; h = (int)(e % L.H); e /= L.H; c = (int)(e % L.C); b = (int)(e / L.C); }
+    const int me = h * L.W + w;
+    float acc = 0.f;
+    for (int r = 0; r < R; ++r) {
+        const float* roi = rois + (size_t)r * 5;
+        if ((int)roi[0] != b) continue;
+        const RoiAxis ax = roi_axis(roi[1], roi[3], L.scale, L.ow);
+        const RoiAxis ay = roi_axis(roi[2], roi[4], L.scale, L.oh);
+        const int hr = h - ay.start, wr = w - ax.start;
+        if (hr < 0 || wr < 0 || hr > ay.extent || wr > ax.extent) continue;
+        const int ie = (int)((float)hr / ay.bin), je = (int)((float)wr / ax.bin);
+        for (int i = max(ie - 2, 0); i <= min(ie + 2, L.oh - 1); ++i) {
+            int h0, h1;
+            roi_bin_range(ay, i, L.H, h0, h1);
+            if (h < h0 || h >= h1) continue;
+            for (int j = max(je - 2, 0); j <= min(je + 2, L.ow - 1); ++j) {
+                int w0, w1;
+                roi_bin_range(ax, j, L.W, w0, w1);
+                if (w < w0 || w >= w1) continue;
+                const size_t o = NHWC ? ((((size_t)r * L.oh + i) * L.ow + j) * L.C + c)
+                                      : ((((size_t)r * L.C + c) * L.oh + i) * L.ow + j);
+                if (L.argmax[o] == me) acc += L.grad_out[o];
+            }
+        }
+    }
+    L.grad_feat[e0] += acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+constexpr int TMA_SMEM_BUDGET = 72 * 1024;     // per CTA -> 3 CTAs per SM
+
+// choose strip height / box for one level; returns false if the TMA path cannot be used
+static bool plan_tma_level(TmaLevel& L, int max_roi_w, int max_roi_h) {
+    if (max_roi_w <= 0 || max_roi_h <= 0) return false;
+    if ((L.C & 3) || L.C > 256 || L.ow > 256) return false;
+    const int rw_max = (int)ceilf(max_roi_w * L.scale) + 2;
+    const int rh_max = (int)ceilf(max_roi_h * L.scale) + 2;
+    const float bh_max = (float)rh_max / (float)L.oh;
+    L.BW = rw_max;
+    if (L.BW > 256) return false;
+    int best = 0;
+    for (int ti = 1; ti <= L.oh && ti <= 64; ++ti) {
+        const int bh = (int)(ti * bh_max) + 2;
+        if (bh > 256) break;
+        if ((size_t)bh * L.BW * L.C * 4 + 128 <= (size_t)TMA_SMEM_BUDGET) best = ti;
+    }
+    if (best == 0) return false;
+    // even out the strips
+    const int strips = ceil_div(L.oh, best);
+    L.TI = ceil_div(L.oh, strips);
+    L.BH = (int)(L.TI * bh_max) + 2;
+    return true;
+}
+
+static int launch_tma_level(TmaLevel& L, int R, cudaStream_t st) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("roi_gather: cuTensorMapEncodeTiled unavailable"); return RIDERS_ECUDA; }
+    CUtensorMap tmap;
+    cuuint64_t dims[4] = {(cuuint64_t)L.C, (cuuint64_t)L.W, (cuuint64_t)L.H, (cuuint64_t)L.B};
+    cuuint64_t strides[3] = {(cuuint64_t)L.C * 4, (cuuint64_t)L.W * L.C * 4, (cuuint64_t)L.H * L.W * L.C * 4};
+    cuuint32_t box[4] = {(cuuint32_t)L.C, (cuuint32_t)L.BW, (cuuint32_t)L.BH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)L.feat, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_error("roi_gather: cuTensorMapEncodeTiled failed (%d)", (int)cr); return RIDERS_ECUDA; }
+    const size_t smem = (size_t)L.BH * L.BW * L.C * 4 + 128;
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(roi_gather_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BUDGET) != cudaSuccess)
+            return check_launch("roi_gather: smem attribute");
+        configured = TMA_SMEM_BUDGET;
+    }
+    dim3 grid(ceil_div(L.oh, L.TI), R);
+    roi_gather_tma_kernel<<<grid, TMA_THREADS, smem, st>>>(tmap, L);
+    return RIDERS_OK;
+}
+
+}  // namespace riders
+
+extern "C" int riders_roi_gather_fwd(int n_levels,
+                                     const float* const* feat, const int* C, const int* Hl, const int* Wl,
+                                     const float* spatial_scale, const int* oh, const int* ow,
+                                     int layout, int B, const float* rois, int R,
+                                     int max_roi_w, int max_roi_h,
+                                     float* const* out, int32_t* const* argmax, void* stream) {
+    using namespace riders;
+    RIDERS_REQUIRE(n_levels > 0 && n_levels <= RIDERS_MAX_LEVELS, "roi_gather: n_levels=%d out of range", n_levels);
+    RIDERS_REQUIRE(layout == RIDERS_LAYOUT_NCHW || layout == RIDERS_LAYOUT_NHWC, "roi_gather: bad layout %d", layout);
+    RIDERS_REQUIRE(B > 0 && R >= 0, "roi_gather: bad B=%d R=%d", B, R);
+    RIDERS_REQUIRE(feat && C && Hl && Wl && spatial_scale && oh && ow && out, "roi_gather: null pointer");
+    if (R == 0) return RIDERS_OK;
+    RIDERS_REQUIRE(rois, "roi_gather: null rois");
+    RIDERS_REQUIRE(R <= 65535, "roi_gather: at most 65535 RoIs per call (got %d); chunk the call", R);
+    cudaStream_t st = (cudaStream_t)stream;
+
+    GatherParams P;
+    P.n_levels = 0; P.B = B; P.R = R; P.rois = rois;
+    long long items = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        RIDERS_REQUIRE(feat[l] && out[l], "roi_gather: null map at level %d", l);
+        RIDERS_REQUIRE(C[l] > 0 && Hl[l] > 0 && Wl[l] > 0 && oh[l] > 0 && ow[l] > 0, "roi_gather: bad dims at level %d", l);
+        RIDERS_REQUIRE((long long)Hl[l] * Wl[l] < (1ll << 31), "roi_gather: map too large at level %d", l);
+        const bool want_arg = argmax && argmax[l];
+        if (layout == RIDERS_LAYOUT_NHWC) {
+            RIDERS_REQUIRE((C[l] & 3) == 0 && (((uintptr_t)feat[l]) & 15) == 0 && (((uintptr_t)out[l]) & 15) == 0,
+                           "roi_gather: channels-last path needs C%%4==0 and 16-byte aligned maps (level %d)", l);
+            if (!want_arg) {
+                TmaLevel T;
+                T.feat = feat[l]; T.out = out[l]; T.C = C[l]; T.H = Hl[l]; T.W = Wl[l]; T.oh = oh[l]; T.ow = ow[l];
+                T.scale = spatial_scale[l]; T.B = B; T.rois = rois;
+                if (plan_tma_level(T, max_roi_w, max_roi_h)) {
+                    int rc = launch_tma_level(T, R, st);
+                    if (rc != RIDERS_OK) return rc;
+                    continue;
+                }
+            }
+        }
+        GatherLevel& G = P.lv[P.n_levels++];
+        G.feat = feat[l]; G.out = out[l]; G.argmax = want_arg ? argmax[l] : nullptr;
+        G.C = C[l]; G.H = Hl[l]; G.W = Wl[l]; G.oh = oh[l]; G.ow = ow[l]; G.scale = spatial_scale[l];
+        G.first_item = items;
+        const long long cg = (layout == RIDERS_LAYOUT_NHWC) ? C[l] / 4 : C[l];
+        items += (long long)R * cg * oh[l] * ow[l];
+    }
+    if (P.n_levels > 0) {
+        P.total_items = items;
+        const long long blocks = (items + GEN_THREADS - 1) / GEN_THREADS;
+        RIDERS_REQUIRE(blocks < (1ll << 31), "roi_gather: too many elements for one launch; chunk the RoIs");
+        if (layout == RIDERS_LAYOUT_NHWC)
+            roi_gather_generic_kernel<true><<<(unsigned)blocks, GEN_THREADS, 0, st>>>(P);
+        else
+            roi_gather_generic_kernel<false><<<(unsigned)blocks, GEN_THREADS, 0, st>>>(P);
+    }
+    return check_launch("roi_gather_fwd");
+}
+
+extern "C" int riders_roi_gather_bwd(int n_levels,
+                                     const float* const* grad_out, const int32_t* const* argmax,
+                                     const int* C, const int* Hl, const int* Wl, const int* oh, const int* ow,
+                                     const float* spatial_scale,
+                                     int layout, int B, const float* rois, int R,
+                                     float* const* grad_feat, void* stream) {
+    using namespace riders;
+    RIDERS_REQUIRE(n_levels > 0 && n_levels <= RIDERS_MAX_LEVELS, "roi_gather_bwd: n_levels=%d out of range", n_levels);
+    RIDERS_REQUIRE(layout == RIDERS_LAYOUT_NCHW || layout == RIDERS_LAYOUT_NHWC, "roi_gather_bwd: bad layout %d", layout);
+    RIDERS_REQUIRE(grad_out && argmax && C && Hl && Wl && oh && ow && spatial_scale && grad_feat, "roi_gather_bwd: null pointer");
+    RIDERS_REQUIRE(B > 0 && R >= 0, "roi_gather_bwd: bad B=%d R=%d", B, R);
+    if (R == 0) return RIDERS_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int l = 0; l < n_levels; ++l) {
+        RIDERS_REQUIRE(grad_out[l] && argmax[l] && grad_feat[l], "roi_gather_bwd: null map at level %d", l);
+        GatherBwdLevel L;
+        L.grad_out = grad_out[l]; L.argmax = argmax[l]; L.grad_feat = grad_feat[l];
+        L.C = C[l]; L.H = Hl[l]; L.W = Wl[l]; L.oh = oh[l]; L.ow = ow[l]; L.scale = spatial_scale[l];
+        const long long n = (long long)B * L.C * L.H * L.W;
+        const long long blocks = (n + GEN_THREADS - 1) / GEN_THREADS;
+        RIDERS_REQUIRE(blocks < (1ll << 31), "roi_gather_bwd: map too large");
+        if (layout == RIDERS_LAYOUT_NHWC)
+            roi_gather_bwd_kernel<true><<<(unsigned)blocks, GEN_THREADS, 0, st>>>(L, rois, R, B);
+        else
+            roi_gather_bwd_kernel<false><<<(unsigned)blocks, GEN_THREADS, 0, st>>>(L, rois, R, B);
+    }
+    return check_launch("roi_gather_bwd");
+}

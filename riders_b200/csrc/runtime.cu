@@ -1,0 +1,48 @@
+// Error plumbing + device queries behind the C ABI.
+#include "common.cuh"
+#include <string.h>
+
+namespace riders {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return RIDERS_OK;
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ||
+        e == cudaErrorNoKernelImageForDevice || e == cudaErrorInvalidDeviceFunction)
+        return RIDERS_ENODEVICE;
+    return RIDERS_ECUDA;
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+}  // namespace riders
+
+extern "C" const char* riders_last_error_string(void) { return riders::g_err; }
+extern "C" int riders_abi_version(void) { return 1; }
+extern "C" int riders_device_arch(void) {
+    int dev = 0, major = 0, minor = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { riders::set_error("no CUDA device"); cudaGetLastError(); return RIDERS_ENODEVICE; }
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    return major * 10 + minor;
+}

@@ -1,0 +1,125 @@
+"""Global scale/shift alignment, host side (mirror of the reference's ``modules/estimator.py``).
+
+Same names and call signatures: ``compute_scale_and_shift_ls`` (estimator.py:5-29),
+``LeastSquaresEstimator`` (:90-125) and ``Optimizer`` (:136-185).  NumPy in, NumPy out like the
+reference (one pinned H2D, the kernels, one D2H); torch CUDA tensors are accepted too and then
+stay on the device.  The five normal-equation sums are accumulated in fp64 by a deterministic
+block tree (BASELINE north_star kernel 4), so ``scale``/``shift`` match the reference fed
+float64 inputs to ~1e-15 and the as-shipped float32 reference to its own rounding error.
+The RANSAC variant (estimator.py:32-87) is never called by the scripts and is not provided.
+"""
+import numpy as np
+import torch
+
+from .. import ops
+
+
+def _to_device(a, dtype=None):
+    if torch.is_tensor(a):
+        t = a
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    if not t.is_cuda:
+        t = t.pin_memory().cuda(non_blocking=True) if torch.cuda.is_available() else t.cuda()
+    return t
+
+
+def _as3d(t):
+    return t.unsqueeze(0) if t.dim() == 2 else t
+
+
+def compute_scale_and_shift_ls(prediction, target, mask):
+    """Returns (x_0, x_1) as 0-d float32 arrays (or (B,) arrays for batched (B,H,W) input)."""
+    batched = np.ndim(prediction) == 3
+    p, t, m = _as3d(_to_device(prediction, torch.float32)), _as3d(_to_device(target, torch.float32)), _as3d(_to_device(mask))
+    _, ss, _ = ops.lsq_align(p, t, m, want_out=False)
+    ss = ss.cpu().numpy()
+    if batched:
+        return ss[:, 0].astype(np.float32), ss[:, 1].astype(np.float32)
+    return np.float32(ss[0, 0]).reshape(()), np.float32(ss[0, 1]).reshape(())
+
+
+class LeastSquaresEstimator(object):
+    def __init__(self, estimate, target, valid):
+        self.estimate = estimate
+        self.target = target
+        self.valid = valid
+        # to be computed
+        self.scale = 1.0
+        self.shift = 0.0
+        self.output = None
+        self.scale64 = None       # fp64 solution of the normal equations (extension)
+        self.shift64 = None
+        self._dev = None
+
+    def _device_inputs(self):
+        if self._dev is None:
+            self._dev = (_as3d(_to_device(self.estimate, torch.float32)),
+                         _as3d(_to_device(self.target, torch.float32)),
+                         _as3d(_to_device(self.valid)))
+        return self._dev
+
+    def compute_scale_and_shift(self):
+        # one pass pair on the device: sums -> solve -> unclamped output kept for apply_scale_and_shift()
+        p, t, m = self._device_inputs()
+        _, ss, out = ops.lsq_align(p, t, m, want_out=True)
+        ss = ss.cpu().numpy()
+        self.scale64, self.shift64 = ss[0, 0], ss[0, 1]
+        self.scale = np.float32(ss[0, 0]).reshape(())
+        self.shift = np.float32(ss[0, 1]).reshape(())
+        self._applied = (self.scale, self.shift, out)
+
+    def apply_scale_and_shift(self):
+        cached = getattr(self, '_applied', None)
+        if cached is not None and cached[0] is self.scale and cached[1] is self.shift:
+            out = cached[2]
+        else:
+            # caller overwrote scale/shift by hand: plain elementwise apply (two float32 roundings)
+            p = self._device_inputs()[0]
+            out = p * float(np.float32(self.scale)) + float(np.float32(self.shift))
+        self._store(out.clone())
+
+    def clamp_min_max(self, clamp_min=None, clamp_max=None):
+        """In place on ``self.output`` like the reference (estimator.py:115-125)."""
+        if self.output is None:
+            raise TypeError("apply_scale_and_shift() must run before clamp_min_max()")
+        hi = np.float32(1.0 / clamp_min) if (clamp_min is not None and clamp_min > 0) else None
+        lo = np.float32(1.0 / clamp_max) if clamp_max is not None else None
+        if torch.is_tensor(self.output):
+            if hi is not None:
+                self.output.clamp_(max=float(hi))
+                assert float(self.output.max()) <= hi
+            if lo is not None:
+                self.output.clamp_(min=float(lo))
+            return
+        if hi is not None:
+            self.output[self.output > hi] = hi
+            assert np.max(self.output) <= hi
+        if lo is not None:
+            self.output[self.output < lo] = lo
+
+    def align(self, clamp_min=None, clamp_max=None):
+        """compute + apply + clamp in one device pass (what val_zju.py:147-155 does in 4 calls)."""
+        hi = float(np.float32(1.0 / clamp_min)) if (clamp_min is not None and clamp_min > 0) else None
+        lo = float(np.float32(1.0 / clamp_max)) if clamp_max is not None else None
+        self._apply(hi, lo, solve=True)
+        return self.output
+
+    def _apply(self, hi, lo, solve=True):
+        p, t, m = self._device_inputs()
+        _, ss, out = ops.lsq_align(p, t, m, clamp_hi=hi, clamp_lo=lo, want_out=True)
+        ssh = ss.cpu().numpy()
+        self.scale64, self.shift64 = ssh[0, 0], ssh[0, 1]
+        self.scale = np.float32(ssh[0, 0]).reshape(())
+        self.shift = np.float32(ssh[0, 1]).reshape(())
+        self._store(out)
+
+    def _store(self, out):
+        if torch.is_tensor(self.estimate):
+            self.output = out.reshape(self.estimate.shape)
+            if not self.estimate.is_cuda:
+                self.output = self.output.cpu()
+        else:
+            self.output = out.reshape(np.shape(self.estimate)).cpu().numpy()

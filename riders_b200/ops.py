@@ -1,0 +1,250 @@
+"""Tensor-level wrappers over the C ABI: torch CUDA tensors in, torch CUDA tensors out.
+
+Every function launches on ``torch.cuda.current_stream()`` and never synchronises.
+CPU tensors are rejected - the product has no CPU path (the oracle lives in ``oracle/``
+and is test infrastructure).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import LAYOUT_NCHW, LAYOUT_NHWC, LOFTR_SIMT, LOFTR_TCGEN05  # noqa: F401
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.RidersError("riders_b200 ops need CUDA tensors (no CPU fallback); got device %s" % t.device)
+
+
+def _f32c(t):
+    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _int_array(vals):
+    return (C.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def _ptr_array(tensors):
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() if t is not None else 0 for t in tensors])
+
+
+# --------------------------------------------------------------------------------------------
+# A1 gather
+# --------------------------------------------------------------------------------------------
+def boxes_to_rois(boxes, device):
+    """list[Tensor(K,4)] (batch index = list position) or Tensor(R,5) -> (R,5) float32 on device.
+    Same convention as torchvision's convert_boxes_to_roi_format."""
+    if isinstance(boxes, (list, tuple)):
+        rows = []
+        for b, bx in enumerate(boxes):
+            bx = torch.as_tensor(bx, dtype=torch.float32).reshape(-1, 4).to(device, non_blocking=True)
+            rows.append(torch.cat([torch.full((bx.shape[0], 1), float(b), device=device), bx], dim=1))
+        return torch.cat(rows, dim=0).contiguous() if rows else torch.zeros((0, 5), device=device)
+    rois = torch.as_tensor(boxes, dtype=torch.float32).to(device)
+    if rois.dim() != 2 or rois.shape[1] != 5:
+        raise ValueError("rois must be (R,5) or a list of (K,4) boxes")
+    return rois.contiguous()
+
+
+def _is_channels_last(t):
+    # ambiguous cases (C == 1 or H == W == 1) count as NCHW
+    return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous()
+
+
+def roi_gather(feats, boxes, scales, out_sizes, max_roi=None, want_argmax=False, chunk=32768):
+    """All pyramid levels of torchvision.ops.roi_pool in one call (RCNet/networks.py:418-433).
+
+    feats: list of (B,C,H,W) float32 CUDA maps, all NCHW-contiguous or all channels_last.
+    Returns list of (R,C,oh,ow) tensors in the same memory format (plus argmax list if asked).
+    max_roi=(w,h): upper bound of the RoI size in image pixels (enables the TMA path).
+    """
+    feats = list(feats)
+    _need_cuda(*feats)
+    dev = feats[0].device
+    nhwc = all(_is_channels_last(f) for f in feats)
+    if not nhwc:
+        feats = [_f32c(f) for f in feats]
+    else:
+        feats = [f if f.dtype == torch.float32 else f.float() for f in feats]
+    rois = boxes_to_rois(boxes, dev)
+    R, B = rois.shape[0], feats[0].shape[0]
+    fmt = torch.channels_last if nhwc else torch.contiguous_format
+    outs = [torch.empty((R, f.shape[1], oh, ow), device=dev, dtype=torch.float32, memory_format=fmt)
+            for f, (oh, ow) in zip(feats, out_sizes)]
+    args = [torch.empty(o.shape, device=dev, dtype=torch.int32, memory_format=fmt) for o in outs] if want_argmax else None
+    n = len(feats)
+    Cs = _int_array([f.shape[1] for f in feats])
+    Hs = _int_array([f.shape[2] for f in feats])
+    Ws = _int_array([f.shape[3] for f in feats])
+    ohs = _int_array([o[0] for o in out_sizes])
+    ows = _int_array([o[1] for o in out_sizes])
+    sc = (C.c_float * n)(*[float(s) for s in scales])
+    mw, mh = (int(max_roi[0]), int(max_roi[1])) if max_roi else (0, 0)
+    L = _lib.lib()
+    for r0 in range(0, R, chunk):
+        r1 = min(R, r0 + chunk)
+        o_ptrs = _ptr_array([o[r0:r1] for o in outs])
+        a_ptrs = _ptr_array([a[r0:r1] for a in args]) if want_argmax else None
+        rc = L.riders_roi_gather_fwd(n, _ptr_array(feats), Cs, Hs, Ws, sc, ohs, ows,
+                                     LAYOUT_NHWC if nhwc else LAYOUT_NCHW, B,
+                                     _ptr(rois[r0:r1]), r1 - r0, mw, mh, o_ptrs, a_ptrs, _stream())
+        _lib.check(rc, "riders_roi_gather_fwd")
+    return (outs, args) if want_argmax else outs
+
+
+def roi_gather_bwd(grad_outs, argmaxes, feat_shapes, boxes, scales, nhwc):
+    dev = grad_outs[0].device
+    rois = boxes_to_rois(boxes, dev)
+    fmt = torch.channels_last if nhwc else torch.contiguous_format
+    grad_outs = [g.contiguous(memory_format=fmt).float() for g in grad_outs]
+    grads = [torch.zeros(s, device=dev, dtype=torch.float32).contiguous(memory_format=fmt) for s in feat_shapes]
+    n = len(grads)
+    rc = _lib.lib().riders_roi_gather_bwd(
+        n, _ptr_array(grad_outs), _ptr_array(argmaxes),
+        _int_array([s[1] for s in feat_shapes]), _int_array([s[2] for s in feat_shapes]),
+        _int_array([s[3] for s in feat_shapes]),
+        _int_array([g.shape[2] for g in grad_outs]), _int_array([g.shape[3] for g in grad_outs]),
+        (C.c_float * n)(*[float(s) for s in scales]),
+        LAYOUT_NHWC if nhwc else LAYOUT_NCHW, feat_shapes[0][0], _ptr(rois), rois.shape[0],
+        _ptr_array(grads), _stream())
+    _lib.check(rc, "riders_roi_gather_bwd")
+    return grads
+
+
+def roi_pool(input, boxes, output_size, spatial_scale=1.0):
+    """Drop-in for ``torchvision.ops.roi_pool`` (single level)."""
+    if isinstance(output_size, int):
+        output_size = (output_size, output_size)
+    return roi_gather([input], boxes, [spatial_scale], [tuple(output_size)])[0]
+
+
+# --------------------------------------------------------------------------------------------
+# A2-A4 LoFTR
+# --------------------------------------------------------------------------------------------
+def linear_attention(q, k, v, q_mask=None, kv_mask=None, eps=1e-6):
+    _need_cuda(q, k, v, q_mask, kv_mask)
+    q, k, v = _f32c(q), _f32c(k), _f32c(v)
+    N, Lq, H, D = q.shape
+    S = k.shape[1]
+    qm = _f32c(q_mask) if q_mask is not None else None
+    km = _f32c(kv_mask) if kv_mask is not None else None
+    out = torch.empty_like(q)
+    rc = _lib.lib().riders_linear_attention_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(qm), _ptr(km),
+                                                N, Lq, S, H, D, float(eps), _ptr(out), _stream())
+    _lib.check(rc, "riders_linear_attention_fwd")
+    return out
+
+
+_WEIGHT_ORDER = ("q_proj.weight", "k_proj.weight", "v_proj.weight", "merge.weight", "mlp.0.weight",
+                 "mlp.2.weight", "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias")
+
+
+def _weights_struct(params, keep):
+    """params: dict name->tensor for one LoFTREncoderLayer (reference parameter names)."""
+    w = _lib.LoftrWeights()
+    for field, key in zip([f for f, _ in _lib.LoftrWeights._fields_], _WEIGHT_ORDER):
+        t = _f32c(params[key].detach())
+        _need_cuda(t)
+        keep.append(t)
+        setattr(w, field, t.data_ptr())
+    return w
+
+
+def loftr_layer(x, source, params, nhead=8, impl=LOFTR_SIMT, attn_eps=1e-6, ln_eps=1e-5):
+    _need_cuda(x, source)
+    x, source = _f32c(x), _f32c(source)
+    N, Lx, Cm = x.shape
+    S = source.shape[1]
+    keep = []
+    w = _weights_struct(params, keep)
+    L = _lib.lib()
+    ws = torch.empty(L.riders_loftr_workspace_bytes(N, max(Lx, S), Cm, impl), dtype=torch.uint8, device=x.device)
+    out = torch.empty_like(x)
+    rc = L.riders_loftr_layer_fwd(_ptr(x), _ptr(source), C.byref(w), N, Lx, S, Cm, nhead,
+                                  float(attn_eps), float(ln_eps), impl, _ptr(out), _ptr(ws), _stream())
+    _lib.check(rc, "riders_loftr_layer_fwd")
+    return out
+
+
+def loftr_transformer(feat0, feat1, layer_params, layer_names, nhead=8, impl=LOFTR_SIMT,
+                      attn_eps=1e-6, ln_eps=1e-5):
+    """LocalFeatureTransformer.forward (RCNet/linear_attention.py:159-184) in one C call."""
+    _need_cuda(feat0, feat1)
+    feat0, feat1 = _f32c(feat0), _f32c(feat1)
+    N, L0, Cm = feat0.shape
+    S = feat1.shape[1]
+    keep = []
+    n = len(layer_params)
+    arr = (_lib.LoftrWeights * n)(*[_weights_struct(p, keep) for p in layer_params])
+    kinds = []
+    for name in layer_names:
+        if name not in ("self", "cross"):
+            raise KeyError(name)                      # linear_attention.py:181-182
+        kinds.append(0 if name == "self" else 1)
+    L = _lib.lib()
+    ws = torch.empty(L.riders_loftr_workspace_bytes(N, max(L0, S), Cm, impl), dtype=torch.uint8, device=feat0.device)
+    out0, out1 = torch.empty_like(feat0), torch.empty_like(feat1)
+    rc = L.riders_loftr_transformer_fwd(_ptr(feat0), _ptr(feat1), arr, _int_array(kinds), n,
+                                        N, L0, S, Cm, nhead, float(attn_eps), float(ln_eps), impl,
+                                        _ptr(out0), _ptr(out1), _ptr(ws), _stream())
+    _lib.check(rc, "riders_loftr_transformer_fwd")
+    return out0, out1
+
+
+# --------------------------------------------------------------------------------------------
+# A5 reduce
+# --------------------------------------------------------------------------------------------
+def confidence_reduce(conf, points, frame_offsets, H, W, thr, logits=False, want_select=True):
+    """conf (R,ph,pw) or (R,1,ph,pw); points (R,3) pad-shifted; frame_offsets (B+1) int32 tensor/list.
+    Returns depth (B,H,W), response (B,H,W), select (B,H,W) int32 | None."""
+    _need_cuda(conf, points)
+    if conf.dim() == 4:
+        conf = conf.reshape(conf.shape[0], conf.shape[-2], conf.shape[-1])
+    conf, points = _f32c(conf), _f32c(points)
+    dev = conf.device
+    if not torch.is_tensor(frame_offsets):
+        frame_offsets = torch.tensor(list(frame_offsets), dtype=torch.int32)
+    offs = frame_offsets.to(device=dev, dtype=torch.int32).contiguous()
+    B = offs.numel() - 1
+    ph, pw = conf.shape[-2], conf.shape[-1]
+    depth = torch.empty((B, H, W), device=dev, dtype=torch.float32)
+    resp = torch.empty_like(depth)
+    sel = torch.empty((B, H, W), device=dev, dtype=torch.int32) if want_select else None
+    rc = _lib.lib().riders_confidence_reduce(_ptr(conf), 1 if logits else 0, _ptr(points), _ptr(offs),
+                                             B, H, W, ph, pw, float(thr), _ptr(depth), _ptr(resp), _ptr(sel), _stream())
+    _lib.check(rc, "riders_confidence_reduce")
+    return depth, resp, sel
+
+
+# --------------------------------------------------------------------------------------------
+# A6/A7 alignment
+# --------------------------------------------------------------------------------------------
+def lsq_align(pred, target, mask, clamp_hi=None, clamp_lo=None, want_out=True):
+    """pred/target (B,H,W) float32, mask (B,H,W) bool/uint8 (all CUDA).
+    Returns sums (B,5) f64, scale_shift (B,2) f64, out (B,H,W) f32 | None."""
+    _need_cuda(pred, target, mask)
+    pred, target = _f32c(pred), _f32c(target)
+    mask = mask.contiguous()
+    mask = mask.view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8)
+    B, H, W = pred.shape
+    dev = pred.device
+    L = _lib.lib()
+    ws = torch.empty(max(L.riders_lsq_workspace_bytes(B, H, W), 8), dtype=torch.uint8, device=dev)
+    sums = torch.empty((B, 5), dtype=torch.float64, device=dev)
+    ss = torch.empty((B, 2), dtype=torch.float64, device=dev)
+    out = torch.empty_like(pred) if want_out else None
+    flags = (1 if clamp_hi is not None else 0) | (2 if clamp_lo is not None else 0)
+    rc = L.riders_lsq_align(_ptr(pred), _ptr(target), _ptr(mask), B, H, W, _ptr(sums), _ptr(ss), _ptr(out),
+                            float(clamp_hi or 0.0), float(clamp_lo or 0.0), flags, _ptr(ws), _stream())
+    _lib.check(rc, "riders_lsq_align")
+    return sums, ss, out

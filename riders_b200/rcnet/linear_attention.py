@@ -1,0 +1,123 @@
+"""LoFTR linear-attention modules, host side (mirror of the reference's
+``RCNet/linear_attention.py``; same class names, constructor arguments, parameter names
+``q_proj k_proj v_proj merge mlp.0 mlp.2 norm1 norm2`` and call signatures, so reference
+checkpoints load and ``networks.py`` can import it unchanged).
+
+Forward passes run on the sm_100a kernels:
+  LinearAttention.forward          -> riders_linear_attention_fwd   (linear_attention.py:18-45)
+  LoFTREncoderLayer.forward        -> riders_loftr_layer_fwd        (linear_attention.py:112-135)
+  LocalFeatureTransformer.forward  -> riders_loftr_transformer_fwd  (linear_attention.py:159-184)
+``FullAttention`` (linear_attention.py:49-80) is never constructed by RC-Net
+(attention='linear', networks.py:378) and is not provided.
+"""
+import copy
+import os
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+def default_impl():
+    """RIDERS_LOFTR_IMPL=simt|tcgen05 selects the kernel family (default: tcgen05)."""
+    name = os.environ.get("RIDERS_LOFTR_IMPL", "tcgen05").lower()
+    if name not in ("simt", "tcgen05"):
+        raise ValueError("RIDERS_LOFTR_IMPL must be 'simt' or 'tcgen05'")
+    return ops.LOFTR_SIMT if name == "simt" else ops.LOFTR_TCGEN05
+
+
+class LinearAttention(nn.Module):
+    def __init__(self, eps=1e-6):
+        super().__init__()
+        self.eps = eps
+
+    def forward(self, queries, keys, values, q_mask=None, kv_mask=None):
+        """queries [N,L,H,D], keys/values [N,S,H,D], masks [N,L]/[N,S] -> [N,L,H,D] contiguous."""
+        return ops.linear_attention(queries, keys, values, q_mask, kv_mask, self.eps)
+
+
+class LoFTREncoderLayer(nn.Module):
+    def __init__(self, d_model, nhead, attention='linear'):
+        super().__init__()
+        if attention != 'linear':
+            raise ValueError("only attention='linear' is provided (RC-Net never builds FullAttention)")
+        self.dim = d_model // nhead
+        self.nhead = nhead
+        self.q_proj = nn.Linear(d_model, d_model, bias=False)
+        self.k_proj = nn.Linear(d_model, d_model, bias=False)
+        self.v_proj = nn.Linear(d_model, d_model, bias=False)
+        self.attention = LinearAttention()
+        self.merge = nn.Linear(d_model, d_model, bias=False)
+        self.mlp = nn.Sequential(
+            nn.Linear(d_model * 2, d_model * 2, bias=False),
+            nn.ReLU(True),
+            nn.Linear(d_model * 2, d_model, bias=False),
+        )
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+
+    def kernel_params(self):
+        return dict(self.named_parameters())
+
+    def _supports(self, impl, x, source):
+        if impl == ops.LOFTR_TCGEN05:
+            return x.shape[2] == 128 and self.nhead == 8 and x.shape[1] == 21 and source.shape[1] == 21
+        return True
+
+    def forward(self, x, source, x_mask=None, source_mask=None):
+        """x [N,L,C], source [N,S,C] -> [N,L,C]."""
+        if x_mask is not None or source_mask is not None:
+            # masked call (never issued by RC-Net, networks.py:444): compose from the kernels
+            bs = x.size(0)
+            q = self.q_proj(x).view(bs, -1, self.nhead, self.dim)
+            k = self.k_proj(source).view(bs, -1, self.nhead, self.dim)
+            v = self.v_proj(source).view(bs, -1, self.nhead, self.dim)
+            m = self.attention(q, k, v, q_mask=x_mask, kv_mask=source_mask)
+            m = self.norm1(self.merge(m.view(bs, -1, self.nhead * self.dim)))
+            m = self.norm2(self.mlp(torch.cat([x, m], dim=2)))
+            return x + m
+        impl = default_impl()
+        if not self._supports(impl, x, source):
+            impl = ops.LOFTR_SIMT
+        return ops.loftr_layer(x, source, self.kernel_params(), self.nhead, impl,
+                               self.attention.eps, self.norm1.eps)
+
+
+class LocalFeatureTransformer(nn.Module):
+    """A Local Feature Transformer (LoFTR) module: ['self','cross'] * n_layers."""
+
+    def __init__(self, type, n_layers=1, d_model=256, nhead=8, attention='linear'):
+        super().__init__()
+        self.d_model = d_model
+        self.nhead = nhead
+        self.layer_names = type * n_layers
+        self.attention = attention
+        encoder_layer = LoFTREncoderLayer(self.d_model, self.nhead, self.attention)
+        self.layers = nn.ModuleList([copy.deepcopy(encoder_layer) for _ in range(len(self.layer_names))])
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+    def forward(self, feat0, feat1, mask0=None, mask1=None):
+        assert self.d_model == feat0.size(2), "the feature number of src and transformer must be equal"
+        if mask0 is not None or mask1 is not None:
+            for layer, name in zip(self.layers, self.layer_names):
+                if name == 'self':
+                    feat0 = layer(feat0, feat0, mask0, mask0)
+                    feat1 = layer(feat1, feat1, mask1, mask1)
+                elif name == 'cross':
+                    feat0 = layer(feat0, feat1, mask0, mask1)
+                    feat1 = layer(feat1, feat0, mask1, mask0)
+                else:
+                    raise KeyError
+            return feat0, feat1
+        impl = default_impl()
+        if not self.layers[0]._supports(impl, feat0, feat1):
+            impl = ops.LOFTR_SIMT
+        return ops.loftr_transformer(feat0, feat1, [l.kernel_params() for l in self.layers],
+                                     self.layer_names, self.nhead, impl,
+                                     self.layers[0].attention.eps, self.layers[0].norm1.eps)

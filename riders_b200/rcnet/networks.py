@@ -1,0 +1,281 @@
+"""RC-Net networks, host side (mirror of the reference's ``RCNet/networks.py``).
+
+The CNN backbones stay plain torch modules (BASELINE.json north_star: "the CNN
+backbones ... remain the reference torch modules"); they are re-declared here,
+table-driven, with the reference's attribute names so that reference
+checkpoints (``radarnet_encoder_state_dict`` / ``radarnet_decoder_state_dict``,
+RCNet/rcnet_model.py:211-257) load unchanged:
+
+  ResNetEncoder        <- RCNet/networks.py:10-270   (ResNet-18/34 trunk, skips at 1/2..1/16)
+  FullyConnectedEncoder<- RCNet/networks.py:273-332  (6 FC layers, LeakyReLU 0.2)
+  RCNetEncoder         <- RCNet/networks.py:335-451  (backbone + gather + point MLP + LoFTR)
+  MultiScaleDecoder    <- RCNet/networks.py:458-778  (nearest-up + conv blocks with skips)
+  building blocks      <- utils/net_utils.py:29-569
+
+What is NOT torch here is the hot path inside ``RCNetEncoder.forward``: the five
+``torchvision.ops.roi_pool`` calls (networks.py:418-433) become one launch of the
+sm_100a gather kernel, and the LoFTR transformer (networks.py:444) runs through
+the fused layer kernels.  There is no CPU fallback for those two.
+"""
+import torch
+import torch.nn.functional as F
+
+from .linear_attention import LocalFeatureTransformer
+from .. import ops
+
+_LEAK = 0.20   # utils/net_utils.py:15  LeakyReLU(negative_slope=0.20)
+
+
+def _init_weight(weight, how):
+    # utils/net_utils.py:61-66: torch default (kaiming_uniform a=sqrt(5)) unless named otherwise
+    if how == 'kaiming_normal':
+        torch.nn.init.kaiming_normal_(weight)
+    elif how == 'xavier_normal':
+        torch.nn.init.xavier_normal_(weight)
+    elif how == 'xavier_uniform':
+        torch.nn.init.xavier_uniform_(weight)
+
+
+def _act(name):
+    """utils/net_utils.py:4-26 activation lookup; returns a callable or None."""
+    if name is None or 'linear' in name:
+        return None
+    if 'leaky_relu' in name:
+        return lambda t: F.leaky_relu(t, _LEAK, inplace=True)
+    if 'relu' in name:
+        return torch.relu
+    if 'elu' in name:
+        return F.elu
+    if 'sigmoid' in name:
+        return torch.sigmoid
+    raise ValueError('Unsupported activation function: {}'.format(name))
+
+
+class Conv2d(torch.nn.Module):
+    """conv (no bias) -> optional BatchNorm -> activation; utils/net_utils.py:29-81."""
+
+    def __init__(self, cin, cout, kernel_size=3, stride=1, init='kaiming_uniform',
+                 act='leaky_relu', use_batch_norm=False):
+        super().__init__()
+        self.conv = torch.nn.Conv2d(cin, cout, kernel_size, stride, kernel_size // 2, bias=False)
+        _init_weight(self.conv.weight, init)
+        self.use_batch_norm = use_batch_norm
+        if use_batch_norm:
+            self.batch_norm = torch.nn.BatchNorm2d(cout)
+        self._act = _act(act)
+
+    def forward(self, x):
+        y = self.conv(x)
+        if self.use_batch_norm:
+            y = self.batch_norm(y)
+        return y if self._act is None else self._act(y)
+
+
+class UpConv2d(torch.nn.Module):
+    """nearest resize to ``shape`` then Conv2d; utils/net_utils.py:149-190."""
+
+    def __init__(self, cin, cout, init, act, use_batch_norm):
+        super().__init__()
+        self.conv = Conv2d(cin, cout, 3, 1, init, act, use_batch_norm)
+
+    def forward(self, x, shape):
+        return self.conv(F.interpolate(x, size=shape))
+
+
+class FullyConnected(torch.nn.Module):
+    """Linear (+bias) -> activation; utils/net_utils.py:193-236."""
+
+    def __init__(self, fin, fout, init='kaiming_uniform', act='leaky_relu'):
+        super().__init__()
+        self.fully_connected = torch.nn.Linear(fin, fout)
+        _init_weight(self.fully_connected.weight, init)
+        self._act = _act(act)
+
+    def forward(self, x):
+        y = self.fully_connected(x)
+        return y if self._act is None else self._act(y)
+
+
+class ResNetBlock(torch.nn.Module):
+    """Two 3x3 convs + (1x1 projection when shape/channels change); utils/net_utils.py:242-310."""
+
+    def __init__(self, cin, cout, stride, init, act, use_batch_norm):
+        super().__init__()
+        self.conv1 = Conv2d(cin, cout, 3, stride, init, act, use_batch_norm)
+        self.conv2 = Conv2d(cout, cout, 3, 1, init, act, use_batch_norm)
+        # the reference always owns a projection (it is in every checkpoint) even when unused
+        self.projection = Conv2d(cin, cout, 1, stride, init, None, False)
+        self._needs_projection = stride != 1 or cin != cout
+        self._act = _act(act)
+
+    def forward(self, x):
+        y = self.conv2(self.conv1(x))
+        skip = self.projection(x) if self._needs_projection else x
+        return self._act(y + skip)
+
+
+class DecoderBlock(torch.nn.Module):
+    """up-conv, concat skip, conv; utils/net_utils.py:474-569 (deconv_type 'up' only)."""
+
+    def __init__(self, cin, cskip, cout, init, act, use_batch_norm, deconv_type='up'):
+        super().__init__()
+        if deconv_type != 'up':
+            raise ValueError("only deconv_type='up' is used by RC-Net (rcnet_model.py:94)")
+        self.skip_channels = cskip
+        self.deconv = UpConv2d(cin, cout, init, act, use_batch_norm)
+        self.conv = Conv2d(cskip + cout, cout, 3, 1, init, act, use_batch_norm)
+
+    def forward(self, x, skip=None, shape=None):
+        if skip is not None:
+            shape = skip.shape[2:4]
+        elif shape is None:
+            shape = (2 * x.shape[2], 2 * x.shape[3])
+        y = self.deconv(x, shape=shape)
+        if self.skip_channels > 0:
+            y = torch.cat([y, skip], dim=1)
+        return self.conv(y)
+
+
+class ResNetEncoder(torch.nn.Module):
+    """7x7/2 stem, 3x3/2 max-pool, then ``blocks2..`` stages; RCNet/networks.py:10-270."""
+
+    def __init__(self, n_layer, input_channels=3, n_filters=(32, 64, 128, 256, 256),
+                 weight_initializer='kaiming_uniform', activation_func='leaky_relu',
+                 use_batch_norm=False):
+        super().__init__()
+        depth = {18: [2, 2, 2, 2], 34: [3, 4, 6, 3]}.get(n_layer)
+        if depth is None:
+            raise ValueError('Only supports 18, 34 layer architecture')
+        n_filters = list(n_filters)
+        depth = depth + [depth[-1]] * (len(n_filters) - len(depth) - 1)
+        assert len(n_filters) < 8 and len(n_filters) == len(depth) + 1
+        a, w, bn = activation_func, weight_initializer, use_batch_norm
+        self.conv1 = Conv2d(input_channels, n_filters[0], 7, 2, w, a, bn)
+        self.max_pool = torch.nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+        self._stages = []
+        for s in range(6):                      # blocks2 .. blocks7
+            name = 'blocks%d' % (s + 2)
+            if s + 1 < len(n_filters):
+                cin, cout = n_filters[s], n_filters[s + 1]
+                stride = 1 if s == 0 else 2
+                blocks = [ResNetBlock(cin if n == 0 else cout, cout, stride if n == 0 else 1, w, a, bn)
+                          for n in range(depth[s])]
+                setattr(self, name, torch.nn.Sequential(*blocks))
+                self._stages.append(name)
+            else:
+                setattr(self, name, None)
+
+    def forward(self, x):
+        feats = [self.conv1(x)]
+        y = self.max_pool(feats[0])
+        for name in self._stages:
+            y = getattr(self, name)(y)
+            feats.append(y)
+        return feats[-1], feats[:-1]
+
+
+class FullyConnectedEncoder(torch.nn.Module):
+    """RCNet/networks.py:273-332: in -> n_neurons[0..4] -> latent_size, activation after every layer."""
+
+    def __init__(self, input_channels=3, n_neurons=(32, 64, 96, 128, 256), latent_size=29 * 10,
+                 weight_initializer='kaiming_uniform', activation_func='leaky_relu'):
+        super().__init__()
+        widths = [input_channels] + list(n_neurons[:5]) + [latent_size]
+        self.mlp = torch.nn.Sequential(*[
+            FullyConnected(widths[i], widths[i + 1], weight_initializer, activation_func)
+            for i in range(6)])
+
+    def forward(self, x):
+        return self.mlp(x)
+
+
+class RCNetEncoder(torch.nn.Module):
+    """Radar association encoder; RCNet/networks.py:335-451."""
+
+    def __init__(self, input_channels_image=3, input_channels_depth=3,
+                 input_patch_size_image=(900, 288),
+                 n_filters_encoder_image=(32, 64, 128, 128, 128),
+                 n_neurons_encoder_depth=(32, 64, 128, 128, 128),
+                 latent_size_depth=128 * 29 * 10,
+                 weight_initializer='kaiming_uniform', activation_func='leaky_relu',
+                 use_batch_norm=False):
+        super().__init__()
+        self.n_neuron_latent_depth = n_neurons_encoder_depth[-1]
+        self.encoder_image = ResNetEncoder(18, input_channels_image, n_filters_encoder_image,
+                                           weight_initializer, activation_func, use_batch_norm)
+        self.attention = LocalFeatureTransformer(['self', 'cross'], n_layers=4,
+                                                 d_model=self.n_neuron_latent_depth)
+        self.encoder_depth = FullyConnectedEncoder(input_channels_depth, n_neurons_encoder_depth,
+                                                   latent_size_depth, weight_initializer, activation_func)
+        self.input_patch_size_image = input_patch_size_image
+
+    def pyramid(self, n_skips):
+        """(scale, (oh, ow)) per gathered level, skips first then latent; networks.py:399-412."""
+        ph, pw = self.input_patch_size_image[-2], self.input_patch_size_image[-1]
+        scales = [1 / 2.0, 1 / 4.0, 1 / 8.0, 1 / 16.0, 1 / 32.0, 1 / 64.0, 1 / 128.0]
+        levels = [(s, (int(ph * s), int(pw * s))) for s in scales[:n_skips]]
+        levels.append((1 / 32.0, (int(ph // 32.0), int(pw // 32.0))))
+        return levels
+
+    def forward(self, image, points, b_boxes):
+        """image (B,3,H',W'); points (sum K, 3); b_boxes list[B] of (K,4) -> latent, pooled skips."""
+        latent_image, skips_image = self.encoder_image(image)
+        return self.encode_points(latent_image, skips_image, points, b_boxes)
+
+    def encode_points(self, latent_image, skips_image, points, b_boxes):
+        """Everything after the backbone (networks.py:418-451).  ``b_boxes`` may also be an (R,5)
+        RoI tensor (batch index first), which lets a caller run chunks of points of a big batch."""
+        levels = self.pyramid(len(skips_image))
+        ph, pw = self.input_patch_size_image[-2], self.input_patch_size_image[-1]
+        # one call for all levels (replaces the five roi_pool calls, networks.py:418-433)
+        pooled = ops.roi_gather(list(skips_image) + [latent_image], b_boxes,
+                                [s for s, _ in levels], [o for _, o in levels], max_roi=(pw, ph))
+        skips_pooled, latent_pooled = pooled[:-1], pooled[-1]
+
+        n, c = points.shape[0], self.n_neuron_latent_depth
+        lw = levels[-1][1][1]
+        latent_depth = self.encoder_depth(points).view(n, c, -1, lw)
+        tok_depth = latent_depth.reshape(n, c, -1).permute(0, 2, 1)
+        tok_image = latent_pooled.reshape(n, latent_pooled.shape[1], -1).permute(0, 2, 1)
+        tok_depth, tok_image = self.attention(tok_depth, tok_image)
+        depth_tf = tok_depth.permute(0, 2, 1).reshape(latent_depth.shape)
+        image_tf = tok_image.permute(0, 2, 1).reshape(latent_pooled.shape)
+        return torch.cat([image_tf, depth_tf], dim=1), skips_pooled
+
+
+class MultiScaleDecoder(torch.nn.Module):
+    """RCNet/networks.py:458-778.  RC-Net always builds it with n_resolution=1 and
+    output_func='linear' (rcnet_model.py:83-95); that configuration (and deeper
+    n_filters lists) is what is mirrored - the multi-resolution side outputs are not."""
+
+    def __init__(self, input_channels=256, output_channels=1, n_resolution=1,
+                 n_filters=(256, 128, 64, 32, 16), n_skips=(256, 128, 64, 32, 0),
+                 weight_initializer='kaiming_uniform', activation_func='leaky_relu',
+                 output_func='linear', use_batch_norm=False, deconv_type='up'):
+        super().__init__()
+        if n_resolution != 1 or 'upsample' in output_func:
+            raise ValueError('only the single-resolution decoder used by RC-Net is provided')
+        depth = len(n_filters)
+        assert depth < 8, 'Does not support network depth of 8 or more'
+        self.n_resolution = n_resolution
+        cin = input_channels
+        self._order = []
+        for i in range(depth):                   # deconv{depth-1} ... deconv0
+            name = 'deconv%d' % (depth - 1 - i)
+            setattr(self, name, DecoderBlock(cin, n_skips[i], n_filters[i], weight_initializer,
+                                             activation_func, use_batch_norm, deconv_type))
+            self._order.append(name)
+            cin = n_filters[i]
+        for i in range(depth, 7):
+            setattr(self, 'deconv%d' % i, None)
+        self.output0 = Conv2d(cin, output_channels, 3, 1, weight_initializer, output_func, False)
+
+    def forward(self, x, skips, shape=None):
+        n = len(skips) - 1
+        y = x
+        for name in self._order[:-1]:
+            y = getattr(self, name)(y, skips[n])
+            n -= 1
+        last = getattr(self, self._order[-1])
+        y = last(y, skips[n]) if n == 0 else last(y, shape=tuple(shape[-2:]))
+        return [self.output0(y)]

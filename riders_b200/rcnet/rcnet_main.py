@@ -1,0 +1,83 @@
+"""``forward_output`` (row A5 of SURVEY 8(a)), host side: mirror of
+``RCNet/rcnet_main.py:435-487`` of the reference with the same signature and return values.
+
+Reference flow: edge-pad -> model.forward(sigmoid) -> K zero canvases -> cat -> max/argmax ->
+confidence-weighted mean.  Here: edge-pad -> model.forward(LOGITS) -> one launch of the
+reduce kernel, which applies the sigmoid + threshold on the fly and never materialises the
+(K, H', W') tensor.  ``forward_output_batched`` is the B200 entry point for many frames.
+"""
+import torch
+
+from .. import ops
+
+
+def _pad_edge(image, px, py):
+    # torchvision.transforms.functional.pad(..., padding_mode='edge') == replicate padding
+    return torch.nn.functional.pad(image, (px, px, py, py), mode='replicate')
+
+
+def _model_logits(model, image, radar_points, bounding_boxes_list, chunk_points):
+    """model.forward(return_logits=True), optionally in chunks of points to bound the decoder's
+    activation memory (the gathered skips are 1.39 MB per point)."""
+    n = radar_points.shape[0]
+    if chunk_points is None or n <= chunk_points or len(bounding_boxes_list) != 1:
+        return model.forward(image=image, point=radar_points, bounding_boxes=bounding_boxes_list,
+                             return_logits=True)
+    outs = []
+    boxes = bounding_boxes_list[0]
+    for s in range(0, n, chunk_points):
+        e = min(n, s + chunk_points)
+        outs.append(model.forward(image=image, point=radar_points[s:e], bounding_boxes=[boxes[s:e]],
+                                  return_logits=True))
+    return torch.cat(outs, dim=0)
+
+
+def forward_output(model, image, radar_points, bounding_boxes_list, response_thr=0.5,
+                   device=torch.device('cuda'), return_select=False):
+    """image (1,3,H,W); radar_points (K,3) or (1,K,3), pad-shifted; bounding_boxes_list [Tensor(K,4)].
+    Returns (output_depth (1,H,W), output_response (1,H,W)) like the reference (+ select if asked)."""
+    ph, pw = model.input_patch_size_image
+    px, py = pw // 2, ph // 2
+    H, W = image.shape[-2], image.shape[-1]
+    image = _pad_edge(image, px, py)
+    if radar_points.dim() == 3:
+        radar_points = torch.squeeze(radar_points, dim=0)
+    logits = model.forward(image=image, point=radar_points, bounding_boxes=bounding_boxes_list,
+                           return_logits=True)
+    depth, response, select = ops.confidence_reduce(
+        logits, radar_points, [0, radar_points.shape[0]], H, W, response_thr, logits=True,
+        want_select=return_select)
+    if return_select:
+        return depth, response, select
+    return depth, response
+
+
+def forward_output_batched(model, images, radar_points, frame_offsets, response_thr=0.5,
+                           chunk_points=1024, return_select=False):
+    """Many frames per call (BASELINE config 2/3).
+
+    images (B,3,H,W) unpadded; radar_points (R,3) pad-shifted, frames concatenated;
+    frame_offsets: python list (B+1).  The backbone runs once on the padded batch, the encoder /
+    decoder run per chunk of points (each chunk within one frame), the reduce kernel once.
+    Returns depth (B,H,W), response (B,H,W) [, select]."""
+    ph, pw = model.input_patch_size_image
+    px, py = pw // 2, ph // 2
+    B, _, H, W = images.shape
+    padded = _pad_edge(images, px, py)
+    x, y = radar_points[:, 0:1], radar_points[:, 1:2]
+    boxes = torch.cat([x - px, y - py, x + px, y + py], dim=1)      # run_rcnet_zju.py:227-232
+    enc = model.encoder.module if hasattr(model.encoder, 'module') else model.encoder
+    dec = model.decoder.module if hasattr(model.decoder, 'module') else model.decoder
+    latent_image, skips_image = enc.encoder_image(padded)
+    R = radar_points.shape[0]
+    logits = torch.empty((R, 1, ph, pw), device=images.device, dtype=torch.float32)
+    frame_of = torch.repeat_interleave(
+        torch.arange(B, device=images.device, dtype=torch.float32),
+        torch.tensor([frame_offsets[i + 1] - frame_offsets[i] for i in range(B)], device=images.device))
+    rois = torch.cat([frame_of[:, None], boxes], dim=1).contiguous()
+    for s in range(0, R, chunk_points):
+        e = min(R, s + chunk_points)
+        latent, skips = enc.encode_points(latent_image, skips_image, radar_points[s:e], rois[s:e])
+        logits[s:e] = dec(x=latent, skips=skips, shape=(ph, pw))[-1]
+    return ops.confidence_reduce(logits, radar_points, frame_offsets, H, W, response_thr, logits=True,
+                                 want_select=return_select)[:3 if return_select else 2]

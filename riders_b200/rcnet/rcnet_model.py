@@ -1,0 +1,111 @@
+"""RCNetModel, host side (mirror of the reference's ``RCNet/rcnet_model.py:7-265``).
+
+Same constructor arguments, attributes (``encoder``, ``decoder``, ``input_patch_size_image``,
+``device``) and methods, so ``rcnet_main.train/validate``, ``run_rcnet_zju.py`` and existing
+checkpoints work unchanged.  ``forward`` (rcnet_model.py:101-123) is the A0 dispatcher of the
+hot path: encoder (gather + LoFTR kernels) -> torch decoder -> logits / sigmoid.
+TensorBoard ``log_summary`` (rcnet_model.py:267-476) belongs to the training driver and is out
+of scope.
+"""
+import torch
+
+from . import networks
+
+
+class RCNetModel(object):
+    def __init__(self, input_channels_image, input_channels_depth, input_patch_size_image,
+                 encoder_type, n_filters_encoder_image, n_neurons_encoder_depth,
+                 decoder_type, n_filters_decoder,
+                 weight_initializer='kaiming_uniform', activation_func='leaky_relu',
+                 device=torch.device('cuda')):
+        self.input_patch_size_image = input_patch_size_image
+        self.device = device
+        height, width = input_patch_size_image
+        latent_size_depth = int(height // 32.0) * int(width // 32.0) * n_neurons_encoder_depth[-1]
+
+        if 'rcnet' not in encoder_type:
+            raise ValueError('Encoder type {} not supported.'.format(encoder_type))
+        self.encoder = networks.RCNetEncoder(
+            input_channels_image=input_channels_image,
+            input_channels_depth=input_channels_depth,
+            input_patch_size_image=input_patch_size_image,
+            n_filters_encoder_image=n_filters_encoder_image,
+            n_neurons_encoder_depth=n_neurons_encoder_depth,
+            latent_size_depth=latent_size_depth,
+            weight_initializer=weight_initializer,
+            activation_func=activation_func,
+            use_batch_norm='batch_norm' in encoder_type)
+
+        n_skips = list(n_filters_encoder_image[:-1])[::-1] + [0]
+        latent_channels = n_filters_encoder_image[-1] + n_neurons_encoder_depth[-1]
+        if 'multiscale' not in decoder_type:
+            raise ValueError('Decoder type {} not supported.'.format(decoder_type))
+        self.decoder = networks.MultiScaleDecoder(
+            input_channels=latent_channels, output_channels=1, n_resolution=1,
+            n_filters=n_filters_decoder, n_skips=n_skips,
+            weight_initializer=weight_initializer, activation_func=activation_func,
+            output_func='linear', use_batch_norm='batch_norm' in decoder_type, deconv_type='up')
+        self.to(self.device)
+
+    # -- A0 ---------------------------------------------------------------------------------
+    def forward(self, image, point, bounding_boxes, return_logits=True):
+        """image N x 3 x H x W, point (sum K) x 3, bounding_boxes list[N] of K x 4
+        -> (sum K) x 1 x ph x pw logits (or sigmoid)."""
+        latent, skips = self.encoder(image, point, bounding_boxes)
+        logits = self.decoder(x=latent, skips=skips, shape=self.input_patch_size_image)[-1]
+        return logits if return_logits else torch.sigmoid(logits)
+
+    def compute_loss(self, logits, ground_truth, validity_map, w_positive_class=1.0):
+        """masked BCE-with-logits, rcnet_model.py:125-163."""
+        w = torch.tensor(w_positive_class, device=logits.device)
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(
+            input=logits, target=ground_truth, reduction='none', pos_weight=w)
+        loss = torch.sum(validity_map * loss) / torch.sum(validity_map)
+        return loss, {'loss': loss}
+
+    def parameters(self):
+        return list(self.encoder.parameters()) + list(self.decoder.parameters())
+
+    def train(self):
+        self.encoder.train()
+        self.decoder.train()
+
+    def eval(self):
+        self.encoder.eval()
+        self.decoder.eval()
+
+    def to(self, device):
+        self.encoder.to(device)
+        self.decoder.to(device)
+
+    def channels_last(self):
+        """B200 extension: keep the CNN activations NHWC so the gather kernel takes its TMA path
+        and cuDNN picks tensor-core kernels.  Pure layout change - results are unchanged."""
+        self.encoder.to(memory_format=torch.channels_last)
+        self.decoder.to(memory_format=torch.channels_last)
+        return self
+
+    def save_model(self, checkpoint_path, step, optimizer):
+        torch.save({
+            'train_step': step,
+            'radarnet_optimizer_state_dict': optimizer.state_dict(),
+            'radarnet_encoder_state_dict': self.encoder.state_dict(),
+            'radarnet_decoder_state_dict': self.decoder.state_dict(),
+        }, checkpoint_path)
+
+    def restore_model(self, checkpoint_path, optimizer=None):
+        checkpoint = torch.load(checkpoint_path, map_location=self.device)
+        self.encoder.load_state_dict(checkpoint['radarnet_encoder_state_dict'])
+        self.decoder.load_state_dict(checkpoint['radarnet_decoder_state_dict'])
+        if optimizer is not None:
+            optimizer.load_state_dict(checkpoint['radarnet_optimizer_state_dict'])
+        return checkpoint['train_step'], optimizer
+
+    def data_parallel(self):
+        """The reference wraps encoder/decoder in nn.DataParallel (rcnet_model.py:259-265), which
+        only yields the 'module.' key prefix on a single GPU.  Here scaling is one process per GPU
+        with frame sharding (riders_b200.dist); the wrapper is kept for checkpoint-key parity."""
+        self.encoder = torch.nn.DataParallel(self.encoder, device_ids=[torch.cuda.current_device()]
+                                             if torch.cuda.is_available() else None)
+        self.decoder = torch.nn.DataParallel(self.decoder, device_ids=[torch.cuda.current_device()]
+                                             if torch.cuda.is_available() else None)

@@ -1,0 +1,47 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+class Golden(object):
+    """npz fixture with 'case/name' keys."""
+
+    def __init__(self, fname):
+        self.z = np.load(os.path.join(GOLDEN, fname))
+
+    def case(self, tag):
+        pre = tag + "/"
+        return {k[len(pre):]: self.z[k] for k in self.z.files if k.startswith(pre)}
+
+    def __getitem__(self, k):
+        return self.z[k]
+
+    @property
+    def files(self):
+        return self.z.files
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return Golden
