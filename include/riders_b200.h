@@ -163,16 +163,7 @@ int riders_lsq_align(const float* pred, const float* target, const uint8_t* mask
  *       If tri_out != NULL it receives the triangles (B, 2*max_knots, 3) int32 (-1 padded) and
  *       tri_count (B).
  * ------------------------------------------------------------------------------------------ */
-int riders_extract_knots(const float* pred, const float* sparse, const uint8_t* valid,
-                         int B, int H, int W, int max_knots,
-                         int32_t* knot_xy, float* knot_scale, float* knot_shift, int32_t* knot_count,
-                         void* workspace, void* stream);
-size_t riders_interp_workspace_bytes(int B, int max_knots, int H, int W);
-int riders_interp_linear(const int32_t* knot_xy, const float* knot_val, const int32_t* knot_count,
-                         int B, int max_knots, int H, int W, float fill,
-                         float* out, int32_t* status,
-                         int32_t* tri_out, int32_t* tri_count,
-                         void* workspace, void* stream);
+/* (A8 prototypes land with the triangulation kernel) */
 
 #ifdef __cplusplus
 }

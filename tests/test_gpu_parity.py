@@ -1,0 +1,250 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the reference-generated
+golden fixtures.  Integer / selection work must be bit-exact; floating point within the
+tolerances of BASELINE.json's north_star, written next to each assert."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import (confidence_reduce_ref as cr, estimator_ref as er, linear_attention_ref as lr,
+                    roi_pool_ref as rr, rcnet_ref)
+from riders_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return (t.to(dtype) if dtype else t).to(DEV)
+
+
+# ------------------------------------------------------------------------------------ A1 gather
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_gather_matches_golden_bit_exact(golden, layout):
+    g = golden("roi_pool.npz")
+    ph, pw = [int(v) for v in g["patch"]]
+    feats = [cu(g["feat%d" % l]) for l in range(5)]
+    if layout == "nhwc":
+        feats = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+    boxes = [cu(g["boxes0"]), cu(g["boxes1"])]
+    for max_roi in (None, (pw, ph), (200, 200)):          # generic, TMA with in-kernel fallback, TMA
+        outs = ops.roi_gather(feats, boxes, [float(g["scale%d" % l]) for l in range(5)],
+                              [tuple(int(v) for v in g["osize%d" % l]) for l in range(5)], max_roi=max_roi)
+        for l, o in enumerate(outs):
+            assert o.shape == g["out%d" % l].shape
+            assert np.array_equal(o.cpu().numpy(), g["out%d" % l]), "level %d layout %s max_roi %s" % (l, layout, max_roi)
+
+
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_gather_rcnet_pyramid_vs_torchvision(layout):
+    # the real pyramid shapes, K=24 points incl. the four frame corners
+    rng = np.random.default_rng(3)
+    H, W, patch = 512, 640, (240, 100)
+    pts, boxes = synth.radar_points(3, 24, H, W, patch)
+    corner = np.array([[0, 0], [W - 1, 0], [0, H - 1], [W - 1, H - 1]], np.float32) + [50, 120]
+    boxes[:4] = np.concatenate([corner - [50, 120], corner + [50, 120]], 1)
+    shapes = [(32, 376, 370), (64, 188, 185), (128, 94, 93), (128, 47, 47), (128, 24, 24)]
+    scales, sizes = rr.rcnet_levels(patch)
+    feats_np = [rng.standard_normal((2,) + s).astype(np.float32) for s in shapes]
+    blist = [boxes[:14], boxes[14:]]
+    rois = rr.boxes_list_to_rois(blist)
+    feats = [cu(f) for f in feats_np]
+    if layout == "nhwc":
+        feats = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+    outs, args = ops.roi_gather(feats, [cu(b) for b in blist], scales, sizes, want_argmax=True)
+    fast = ops.roi_gather(feats, [cu(b) for b in blist], scales, sizes, max_roi=(100, 240))
+    for l in range(5):
+        ref = rr.roi_pool_torchvision(feats_np[l], rois, scales[l], sizes[l])
+        assert np.array_equal(outs[l].cpu().numpy(), ref), "level %d" % l
+        assert np.array_equal(fast[l].cpu().numpy(), ref), "level %d (tma)" % l
+        a = args[l].cpu().numpy()
+        flat = feats_np[l].reshape(2, shapes[l][0], -1)
+        b = rois[:, 0].astype(int)
+        picked = np.take_along_axis(flat[b], np.maximum(a, 0).reshape(a.shape[0], a.shape[1], -1), axis=2).reshape(a.shape)
+        assert np.array_equal(np.where(a >= 0, picked, 0), ref)
+
+
+def test_gather_backward_matches_torchvision_autograd():
+    import torchvision
+    rng = np.random.default_rng(5)
+    feat = torch.from_numpy(rng.standard_normal((2, 8, 40, 36)).astype(np.float32))
+    boxes = [torch.tensor([[2., 3., 30., 60.], [10., 0., 50., 70.]]), torch.tensor([[0., 0., 71., 79.]])]
+    f = feat.clone().requires_grad_(True)
+    out = torchvision.ops.roi_pool(f, boxes, output_size=(6, 5), spatial_scale=0.5)
+    gout = torch.from_numpy(rng.standard_normal(tuple(out.shape)).astype(np.float32))
+    out.backward(gout)
+    for nhwc in (False, True):
+        fd = feat.to(DEV).contiguous(memory_format=torch.channels_last) if nhwc else feat.to(DEV)
+        (o,), (a,) = ops.roi_gather([fd], [b.to(DEV) for b in boxes], [0.5], [(6, 5)], want_argmax=True)
+        assert np.array_equal(o.cpu().numpy(), out.detach().numpy())
+        (gf,) = ops.roi_gather_bwd([gout.to(DEV)], [a], [tuple(feat.shape)], [b.to(DEV) for b in boxes], [0.5], nhwc)
+        np.testing.assert_allclose(gf.cpu().numpy(), f.grad.numpy(), rtol=1e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------ A2-A4 LoFTR
+def _layer_params(g, i):
+    pre = "layers.%d." % i
+    return {k[len(pre):]: cu(v) for k, v in g.items() if k.startswith(pre)}
+
+
+@pytest.mark.parametrize("tag", ["small", "rcnet"])
+def test_linear_attention_matches_reference(golden, tag):
+    g = golden("loftr.npz").case(tag)
+    out = ops.linear_attention(cu(g["q"]), cu(g["k"]), cu(g["v"]))
+    np.testing.assert_allclose(out.cpu().numpy(), g["attn"], rtol=1e-5, atol=1e-6)      # fp32 re-association only
+    out = ops.linear_attention(cu(g["q"]), cu(g["k"]), cu(g["v"]), cu(g["qm"]), cu(g["km"]))
+    np.testing.assert_allclose(out.cpu().numpy(), g["attn_masked"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag", ["small", "rcnet"])
+def test_loftr_simt_matches_reference(golden, tag):
+    g = golden("loftr.npz").case(tag)
+    n_layers = int(g["n_layers"])
+    one = ops.loftr_layer(cu(g["f0"]), cu(g["f1"]), _layer_params(g, 0), impl=ops.LOFTR_SIMT)
+    np.testing.assert_allclose(one.cpu().numpy(), g["layer0"], rtol=1e-4, atol=2e-5)
+    o0, o1 = ops.loftr_transformer(cu(g["f0"]), cu(g["f1"]), [_layer_params(g, i) for i in range(2 * n_layers)],
+                                   ["self", "cross"] * n_layers, impl=ops.LOFTR_SIMT)
+    # tolerance: 1e-4 relative (north_star) on the transformer output
+    np.testing.assert_allclose(o0.cpu().numpy(), g["o0"], rtol=1e-4, atol=5e-5)
+    np.testing.assert_allclose(o1.cpu().numpy(), g["o1"], rtol=1e-4, atol=5e-5)
+
+
+# ------------------------------------------------------------------------------------ A5 reduce
+@pytest.mark.parametrize("tag", ["basic", "single", "allbelow", "dups"])
+def test_reduce_matches_golden(golden, tag):
+    g = golden("confidence_reduce.npz").case(tag)
+    H, W = [int(v) for v in g["hw"]]
+    K = g["conf"].shape[0]
+    d, r, s = ops.confidence_reduce(cu(g["conf"]), cu(g["pts"]), [0, K], H, W, float(g["thr"]))
+    assert np.array_equal(r.cpu().numpy(), g["response"])                     # max: exact
+    np.testing.assert_allclose(d.cpu().numpy(), g["depth"], rtol=1e-5, atol=0)  # 1e-4 rel allowed; sums re-associate
+    d0, r0, s0 = cr.confidence_reduce_ref(g["conf"][:, 0], g["pts"], H, W, float(g["thr"]))
+    margin = cr.top2_margin(g["conf"][:, 0], g["pts"], H, W, float(g["thr"]))
+    sel = s.cpu().numpy()[0]
+    assert np.array_equal(sel[margin > 1e-6], s0[margin > 1e-6])             # bit-exact where the margin is clear
+    assert np.array_equal(sel, s0)                                            # and first-max everywhere else
+
+
+def test_reduce_full_size_ragged_batch_and_logits():
+    H, W, patch = 512, 640, (240, 100)
+    Ks = [512, 1, 0, 300]
+    pts, conf = [], []
+    for f, K in enumerate(Ks):
+        p, _ = synth.radar_points(f, max(K, 1), H, W, patch)
+        pts.append(p[:K])
+        conf.append(synth.confidences(f, max(K, 1), patch)[:K])
+    offs = np.concatenate([[0], np.cumsum(Ks)]).tolist()
+    P, Cn = np.concatenate(pts), np.concatenate(conf)
+    d, r, s = ops.confidence_reduce(cu(Cn), cu(P), offs, H, W, 0.1)
+    for f, K in enumerate(Ks):
+        d0, r0, s0 = cr.confidence_reduce_ref(conf[f], pts[f], H, W, 0.1)
+        assert np.array_equal(r[f].cpu().numpy(), r0)
+        np.testing.assert_allclose(d[f].cpu().numpy(), d0, rtol=1e-5, atol=0)
+        assert np.array_equal(s[f].cpu().numpy(), s0)
+    # logits variant == sigmoid then reduce, within 1e-4 relative on the confidences
+    logit = np.log(Cn / (1 - Cn)).astype(np.float32)
+    d2, r2, _ = ops.confidence_reduce(cu(logit), cu(P), offs, H, W, 0.1, logits=True)
+    sig = torch.sigmoid(cu(logit))
+    d3, r3, _ = ops.confidence_reduce(sig, cu(P), offs, H, W, 0.1)
+    rr_, r3_ = r2.cpu().numpy(), r3.cpu().numpy()
+    same = (rr_ > 0) == (r3_ > 0)
+    assert same.mean() > 0.9999
+    np.testing.assert_allclose(rr_[same], r3_[same], rtol=1e-4)
+    # properties: response is in {0} U [thr, 1]; depth within [min z, max z] where it fired
+    rn = r.cpu().numpy()
+    assert ((rn == 0) | (rn >= np.float32(0.1))).all()
+    dn = d.cpu().numpy()
+    assert ((dn[0] == 0) == (rn[0] == 0)).all()
+    fired = rn[0] > 0
+    assert dn[0][fired].min() >= pts[0][:, 2].min() * (1 - 1e-6) and dn[0][fired].max() <= pts[0][:, 2].max() * (1 + 1e-6)
+
+
+# ------------------------------------------------------------------------------------ A6/A7 align
+@pytest.mark.parametrize("tag", ["cfg1", "small", "one", "none"])
+def test_lsq_matches_golden(golden, tag):
+    g = golden("estimator.npz").case(tag)
+    hi, lo = float(np.float32(1.0 / 0.1)), float(np.float32(1.0 / 255.0))
+    sums, ss, out = ops.lsq_align(cu(g["pred"])[None], cu(g["target"])[None], cu(g["mask"])[None], hi, lo)
+    ss = ss.cpu().numpy()[0]
+    if tag in ("one", "none"):
+        assert ss[0] == 0 and ss[1] == 0
+    else:
+        # 1e-6 relative vs the reference fed float64 inputs (north_star)
+        np.testing.assert_allclose(ss[0], g["scale64"], rtol=1e-9)
+        np.testing.assert_allclose(ss[1], g["shift64"], rtol=1e-9)
+    ref_sums = er.normal_equation_sums(g["pred"], g["target"], g["mask"])
+    np.testing.assert_allclose(sums.cpu().numpy()[0], ref_sums, rtol=1e-12, atol=0)
+    exp = er.apply_clamp_ref(g["pred"], ss[0], ss[1], 0.1, 255.0)
+    assert np.array_equal(out.cpu().numpy()[0], exp)                         # apply+clamp is bit-exact
+    if "out_clamped_from64" in g and tag not in ("one", "none"):
+        assert np.array_equal(out.cpu().numpy()[0], g["out_clamped_from64"])
+
+
+def test_lsq_batched_deterministic_and_unaligned():
+    B, H, W = 5, 67, 93                                   # odd sizes: scalar tail path
+    data = [synth.alignment_inputs(s, 40, H, W) for s in range(B)]
+    p, t, m = (np.stack([d[i] for d in data]) for i in range(3))
+    a = ops.lsq_align(cu(p), cu(t), cu(m), 10.0, float(np.float32(1 / 255.0)))
+    b = ops.lsq_align(cu(p), cu(t), cu(m), 10.0, float(np.float32(1 / 255.0)))
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)                          # bit-reproducible
+    for i in range(B):
+        s64, t64 = er.scale_shift_ls_ref(p[i], t[i], m[i])
+        np.testing.assert_allclose(a[1][i].cpu().numpy(), [s64, t64], rtol=1e-9)
+        assert np.array_equal(a[2][i].cpu().numpy(), er.apply_clamp_ref(p[i], s64, t64, 0.1, 255.0))
+    # linearity property: scaling the target scales (scale, shift)
+    _, ss2, _ = ops.lsq_align(cu(p), cu(t * np.float32(2)), cu(m), want_out=False)
+    np.testing.assert_allclose(ss2.cpu().numpy(), 2 * a[1].cpu().numpy(), rtol=1e-12)
+
+
+def test_estimator_class_is_a_drop_in(golden):
+    from riders_b200.modules.estimator import LeastSquaresEstimator, compute_scale_and_shift_ls
+    g = golden("estimator.npz").case("small")
+    e = LeastSquaresEstimator(estimate=g["pred"], target=g["target"], valid=g["mask"])
+    e.compute_scale_and_shift()
+    e.apply_scale_and_shift()
+    e.clamp_min_max(clamp_min=0.1, clamp_max=255.0)
+    assert isinstance(e.output, np.ndarray) and e.output.dtype == np.float32
+    assert e.scale.shape == () and e.scale.dtype == np.float32
+    assert np.array_equal(e.output, g["out_clamped_from64"])
+    np.testing.assert_allclose(e.scale, g["scale32"], rtol=1e-5)             # vs the as-shipped fp32 reference
+    x0, x1 = compute_scale_and_shift_ls(g["pred"], g["target"], g["mask"])
+    np.testing.assert_allclose([x0, x1], [g["scale64"], g["shift64"]], rtol=1e-6)
+    e2 = LeastSquaresEstimator(estimate=g["pred"], target=g["target"], valid=g["mask"])
+    assert np.array_equal(e2.align(clamp_min=0.1, clamp_max=255.0), g["out_clamped_from64"])
+
+
+# ------------------------------------------------------------------------------------ A0 end to end
+def _tiny_model(g, device):
+    from riders_b200.rcnet.rcnet_model import RCNetModel
+    model = RCNetModel(3, 3, [64, 32], ["rcnet", "batch_norm"], [8, 16, 16, 16, 16], [8, 16, 16, 16, 16],
+                       ["multiscale", "batch_norm"], [32, 16, 16, 8, 8], device=torch.device(device))
+    model.encoder.load_state_dict({k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("enc/")})
+    model.decoder.load_state_dict({k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("dec/")})
+    model.eval()
+    return model
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_forward_output_matches_reference_golden(golden, channels_last):
+    from riders_b200.rcnet.rcnet_main import forward_output, forward_output_batched
+    g = golden("rcnet_tiny.npz")
+    torch.backends.cudnn.allow_tf32 = False          # isolate the kernels under test from TF32 convs
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model = _tiny_model(g, DEV)
+    if channels_last:
+        model.channels_last()
+    image, pts, boxes = cu(g["image"]), cu(g["pts"]), [torch.from_numpy(g["boxes"])]   # boxes on the CPU like the reference
+    with torch.no_grad():
+        padded = torch.nn.functional.pad(image, (16, 16, 32, 32), mode="replicate")
+        logits = model.forward(padded, pts, boxes, return_logits=True)
+        np.testing.assert_allclose(logits.cpu().numpy(), g["logits"], rtol=1e-4, atol=2e-5)
+        d, r, s = forward_output(model, image, pts, boxes, response_thr=float(g["thr"]), return_select=True)
+        d2, r2 = forward_output_batched(model, image, pts, [0, pts.shape[0]], float(g["thr"]), chunk_points=2)
+    rn, gn = r.cpu().numpy(), g["response"]
+    agree = (rn > 0) == (gn > 0)                         # threshold flips only for |conf-thr| < 1e-4*thr
+    assert agree.mean() > 0.995
+    np.testing.assert_allclose(rn[agree], gn[agree], rtol=1e-4)              # confidences: 1e-4 relative
+    both = agree & (gn > 0)
+    np.testing.assert_allclose(d.cpu().numpy()[both], g["depth"][both], rtol=2e-3)
+    assert torch.allclose(r2, r, rtol=1e-4, atol=1e-6) and torch.allclose(d2, d, rtol=1e-3, atol=1e-5)

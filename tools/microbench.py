@@ -1,0 +1,120 @@
+"""Per-kernel timings at BASELINE sizes (CUDA events, L2 flushed between iterations).
+Usage: python tools/microbench.py [reduce lsq gather loftr interp]   -> JSON lines on stdout."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from riders_b200 import ops, synth   # noqa: E402
+
+DEV = torch.device("cuda:0")
+PEAKS = {}
+try:
+    PEAKS = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+except Exception:
+    pass
+HBM = float(PEAKS.get("hbm_gbs", 6650.0))
+_flush = None
+
+
+def flush_l2():
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=DEV)
+    _flush.fill_(1)
+
+
+def timeit(fn, iters=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush_l2()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def report(name, ms, best, nbytes=None, flops=None, **kw):
+    rec = {"kernel": name, "ms_median": round(ms, 4), "ms_min": round(best, 4)}
+    if nbytes:
+        rec.update(GBps=round(nbytes / ms / 1e6, 1), frac_hbm=round(nbytes / ms / 1e6 / HBM, 3), bytes=int(nbytes))
+    if flops:
+        rec.update(TFLOPs=round(flops / ms / 1e9, 2), flops=int(flops))
+    rec.update(kw)
+    print(json.dumps(rec), flush=True)
+
+
+def bench_reduce(B=16, K=512, H=512, W=640, patch=(240, 100)):
+    g = torch.Generator(device=DEV).manual_seed(0)
+    conf = torch.sigmoid(torch.randn((B * K,) + patch, device=DEV, generator=g) * 2 - 1.5)
+    pts = torch.cat([torch.from_numpy(synth.radar_points(f, K, H, W, patch)[0]) for f in range(B)]).to(DEV)
+    offs = torch.arange(0, B * K + 1, K, dtype=torch.int32, device=DEV)
+    nbytes = B * (K * patch[0] * patch[1] * 4 + 12 * K + 3 * H * W * 4)
+    for logits in (False, True):
+        ms, best = timeit(lambda: ops.confidence_reduce(conf, pts, offs, H, W, 0.1, logits=logits))
+        report("confidence_reduce" + ("_logits" if logits else ""), ms, best, nbytes, B=B, K=K)
+
+
+def bench_lsq(B=64, H=512, W=640, K=512):
+    data = [synth.alignment_inputs(s, K, H, W) for s in range(4)]
+    p = torch.from_numpy(np.stack([d[0] for d in data])).to(DEV).repeat(B // 4, 1, 1)
+    t = torch.from_numpy(np.stack([d[1] for d in data])).to(DEV).repeat(B // 4, 1, 1)
+    m = torch.from_numpy(np.stack([d[2] for d in data])).to(DEV).repeat(B // 4, 1, 1)
+    nbytes = B * H * W * 13
+    ms, best = timeit(lambda: ops.lsq_align(p, t, m, 10.0, 1 / 255.0))
+    report("lsq_align", ms, best, nbytes, B=B)
+    dense = torch.ones_like(m)
+    ms, best = timeit(lambda: ops.lsq_align(p, t, dense, 10.0, 1 / 255.0))
+    report("lsq_align_dense_mask", ms, best, nbytes, B=B)
+
+
+def bench_gather(B=2, K=512, patch=(240, 100)):
+    shapes = [(32, 376, 370), (64, 188, 185), (128, 94, 93), (128, 47, 47), (128, 24, 24)]
+    scales = [1 / 2., 1 / 4., 1 / 8., 1 / 16., 1 / 32.]
+    sizes = [(120, 50), (60, 25), (30, 12), (15, 6), (7, 3)]
+    g = torch.Generator(device=DEV).manual_seed(0)
+    feats = [torch.randn((B,) + s, device=DEV, generator=g) for s in shapes]
+    boxes = [torch.from_numpy(synth.radar_points(f, K, 512, 640, patch)[1]).to(DEV) for f in range(B)]
+    rois = ops.boxes_to_rois(boxes, DEV)
+    per_point = sum(c * oh * ow for (c, _, _), (oh, ow) in zip(shapes, sizes)) * 4
+    nbytes = B * K * (per_point + 20) + B * sum(c * h * w for c, h, w in shapes) * 4
+    for name, fs, mr in (("nchw_generic", feats, None),
+                         ("nhwc_generic", [f.contiguous(memory_format=torch.channels_last) for f in feats], None),
+                         ("nhwc_tma", [f.contiguous(memory_format=torch.channels_last) for f in feats], (100, 240))):
+        ms, best = timeit(lambda: ops.roi_gather(fs, rois, scales, sizes, max_roi=mr), iters=5)
+        report("roi_gather_" + name, ms, best, nbytes, B=B, K=K)
+
+
+def bench_loftr(N=4096):
+    import oracle  # noqa: F401  (only to keep the import graph explicit: weights are random here)
+    from riders_b200.rcnet.linear_attention import LocalFeatureTransformer
+    torch.manual_seed(0)
+    tf = LocalFeatureTransformer(['self', 'cross'], n_layers=4, d_model=128).to(DEV).eval()
+    f0 = torch.randn(N, 21, 128, device=DEV)
+    f1 = torch.relu(torch.randn(N, 21, 128, device=DEV))
+    flops = N * 112939008
+    params = [l.kernel_params() for l in tf.layers]
+    for impl, name in ((ops.LOFTR_SIMT, "simt"), (ops.LOFTR_TCGEN05, "tcgen05")):
+        try:
+            ms, best = timeit(lambda: ops.loftr_transformer(f0, f1, params, tf.layer_names, 8, impl), iters=5)
+            report("loftr_transformer_" + name, ms, best, flops=flops, N=N)
+        except Exception as e:  # noqa: BLE001
+            print(json.dumps({"kernel": "loftr_transformer_" + name, "error": str(e)[:200]}), flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["reduce", "lsq", "gather", "loftr"]
+    torch.cuda.set_device(DEV)
+    print(json.dumps({"gpu": torch.cuda.get_device_name(0), "hbm_peak_gbs": HBM}), flush=True)
+    with torch.no_grad():
+        for w in which:
+            globals()["bench_" + w]()
