@@ -32,6 +32,7 @@ extern "C" {
 #define RIDERS_ECUDA      -2   /* CUDA runtime error at launch                                */
 #define RIDERS_ENODEVICE  -3   /* no sm_100 device / kernel image not loadable                */
 #define RIDERS_EQHULL     -4   /* triangulation impossible (<3 knots or all collinear)        */
+#define RIDERS_EINTERNAL  -5   /* internal capacity exceeded (reported, never silent)         */
 
 #define RIDERS_LAYOUT_NCHW 0
 #define RIDERS_LAYOUT_NHWC 1   /* torch channels_last: logical NCHW, memory N,H,W,C            */
@@ -155,15 +156,26 @@ int riders_lsq_align(const float* pred, const float* target, const uint8_t* mask
 /* ------------------------------------------------------------------------------------------
  * A8  Interpolator2D / interpolate_knots(method='linear')   modules/interpolator.py:7-50
  *     riders_extract_knots: row-major scan of `valid` -> knot_xy (B,max_knots,2) int32 (x,y),
- *       knot_scale = sparse/pred, knot_shift = sparse-pred (float32), knot_count (B) int32.
+ *       knot_scale = sparse/pred, knot_shift = sparse-pred (float32), knot_count (B) int32 (the
+ *       true count; knots beyond max_knots are dropped - the caller must check).
  *     riders_interp_linear: Delaunay triangulation of each frame's knots on the device
  *       (exact integer predicates) + per-pixel barycentric fill in fp64, `fill` outside the
- *       convex hull, float32 out (B,H,W).  status (B) int32: 0 ok, RIDERS_EQHULL where SciPy
- *       would raise QhullError.  Knots of frame b are knot_xy[b*max_knots .. +knot_count[b]).
+ *       convex hull, float32 out (B,H,W).  Knots must be distinct pixels with 0 <= x,y < 8192.
+ *       status (B) int32: 0 ok, RIDERS_EQHULL where SciPy would raise QhullError (the frame is
+ *       then filled with `fill`), RIDERS_EINTERNAL if the edge pool overflowed.  Knots of frame b are knot_xy[b*max_knots .. +knot_count[b]).
  *       If tri_out != NULL it receives the triangles (B, 2*max_knots, 3) int32 (-1 padded) and
  *       tri_count (B).
  * ------------------------------------------------------------------------------------------ */
-/* (A8 prototypes land with the triangulation kernel) */
+int riders_extract_knots(const float* pred, const float* sparse, const uint8_t* valid,
+                         int B, int H, int W, int max_knots,
+                         int32_t* knot_xy, float* knot_scale, float* knot_shift, int32_t* knot_count,
+                         void* stream);
+size_t riders_interp_workspace_bytes(int B, int max_knots, int H, int W);
+int riders_interp_linear(const int32_t* knot_xy, const float* knot_val, const int32_t* knot_count,
+                         int B, int max_knots, int H, int W, float fill,
+                         float* out, int32_t* status,
+                         int32_t* tri_out, int32_t* tri_count,
+                         void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libriders_b200.so")
 
 RIDERS_OK = 0
-RIDERS_EINVAL, RIDERS_ECUDA, RIDERS_ENODEVICE, RIDERS_EQHULL = -1, -2, -3, -4
+RIDERS_EINVAL, RIDERS_ECUDA, RIDERS_ENODEVICE, RIDERS_EQHULL, RIDERS_EINTERNAL = -1, -2, -3, -4, -5
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 LOFTR_SIMT, LOFTR_TCGEN05 = 0, 1
 MAX_LEVELS = 8
@@ -39,6 +39,9 @@ SIGNATURES = {
     "riders_confidence_reduce": (ci, [vp, ci, vp, vp, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp]),
     "riders_lsq_workspace_bytes": (sz, [ci, ci, ci]),
     "riders_lsq_align": (ci, [vp, vp, vp, ci, ci, ci, vp, vp, vp, cf, cf, ci, vp, vp]),
+    "riders_extract_knots": (ci, [vp, vp, vp, ci, ci, ci, ci, vp, vp, vp, vp, vp]),
+    "riders_interp_workspace_bytes": (sz, [ci, ci, ci, ci]),
+    "riders_interp_linear": (ci, [vp, vp, vp, ci, ci, ci, ci, cf, vp, vp, vp, vp, vp, vp]),
 }
 
 _lib = None

@@ -248,3 +248,47 @@ def lsq_align(pred, target, mask, clamp_hi=None, clamp_lo=None, want_out=True):
                             float(clamp_hi or 0.0), float(clamp_lo or 0.0), flags, _ptr(ws), _stream())
     _lib.check(rc, "riders_lsq_align")
     return sums, ss, out
+
+
+# --------------------------------------------------------------------------------------------
+# A8 interpolation
+# --------------------------------------------------------------------------------------------
+def extract_knots(pred, sparse, valid, max_knots):
+    """(B,H,W) maps -> knot_xy (B,max_knots,2) int32, scales, shifts (B,max_knots) f32, counts (B) int32."""
+    _need_cuda(pred, sparse, valid)
+    pred, sparse = _f32c(pred), _f32c(sparse)
+    valid = valid.contiguous()
+    valid = valid.view(torch.uint8) if valid.dtype == torch.bool else valid.to(torch.uint8)
+    B, H, W = pred.shape
+    dev = pred.device
+    xy = torch.zeros((B, max_knots, 2), dtype=torch.int32, device=dev)
+    sc = torch.zeros((B, max_knots), dtype=torch.float32, device=dev)
+    sh = torch.zeros((B, max_knots), dtype=torch.float32, device=dev)
+    cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
+    rc = _lib.lib().riders_extract_knots(_ptr(pred), _ptr(sparse), _ptr(valid), B, H, W, max_knots,
+                                         _ptr(xy), _ptr(sc), _ptr(sh), _ptr(cnt), _stream())
+    _lib.check(rc, "riders_extract_knots")
+    return xy, sc, sh, cnt
+
+
+def interp_linear(knot_xy, knot_val, knot_count, H, W, fill=1.0, want_triangles=False):
+    """knot_xy (B,max_knots,2) int32 (x,y); knot_val (B,max_knots) f32; knot_count (B) int32.
+    Returns out (B,H,W) f32, status (B) int32 [, triangles (B,2*max_knots,3) int32, tri_count (B)]."""
+    _need_cuda(knot_xy, knot_val, knot_count)
+    knot_xy = knot_xy.to(torch.int32).contiguous()
+    knot_val = _f32c(knot_val)
+    knot_count = knot_count.to(torch.int32).contiguous()
+    B, max_knots = knot_val.shape
+    dev = knot_val.device
+    L = _lib.lib()
+    ws = torch.empty(L.riders_interp_workspace_bytes(B, max_knots, H, W), dtype=torch.uint8, device=dev)
+    out = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    status = torch.zeros((B,), dtype=torch.int32, device=dev)
+    tri = torch.full((B, 2 * max_knots, 3), -1, dtype=torch.int32, device=dev) if want_triangles else None
+    tcount = torch.zeros((B,), dtype=torch.int32, device=dev) if want_triangles else None
+    rc = L.riders_interp_linear(_ptr(knot_xy), _ptr(knot_val), _ptr(knot_count), B, max_knots, H, W, float(fill),
+                                _ptr(out), _ptr(status), _ptr(tri), _ptr(tcount), _ptr(ws), _stream())
+    _lib.check(rc, "riders_interp_linear")
+    if want_triangles:
+        return out, status, tri, tcount
+    return out, status

@@ -248,3 +248,95 @@ def test_forward_output_matches_reference_golden(golden, channels_last):
     both = agree & (gn > 0)
     np.testing.assert_allclose(d.cpu().numpy()[both], g["depth"][both], rtol=2e-3)
     assert torch.allclose(r2, r, rtol=1e-4, atol=1e-6) and torch.allclose(d2, d, rtol=1e-3, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------ A8 interpolation
+def _interp_check(pred, sparse, valid, expected=None):
+    from oracle import interpolator_ref as ir
+    H, W = pred.shape
+    n = int(valid.sum())
+    xy, sc, sh, cnt = ops.extract_knots(cu(pred)[None], cu(sparse)[None], cu(valid)[None], max(n, 1))
+    coords, scales, shifts = ir.extract_knots_ref(pred, sparse, valid)
+    assert int(cnt[0]) == n
+    assert np.array_equal(xy[0, :n].cpu().numpy(), coords.T)                 # row-major scan order, (x, y)
+    assert np.array_equal(sc[0, :n].cpu().numpy(), scales) and np.array_equal(sh[0, :n].cpu().numpy(), shifts)
+    out, status = ops.interp_linear(xy, sc, cnt, H, W, 1.0)
+    assert int(status[0]) == 0
+    got = out[0].cpu().numpy()
+    ref = expected if expected is not None else ir.interpolated_scale_map_ref(pred, sparse, valid)
+    ref64 = ir.interpolate_knots_ref((H, W), coords, scales)
+    outside = np.isclose(ref64, 1.0, rtol=0, atol=0) & (ref == 1.0)
+    degenerate = ir.degenerate_pixel_mask(coords.T, H, W)
+    ok = ~degenerate
+    # exactly fill outside the hull (hull membership is exact: integer predicates)
+    hull_out = ok & (got == 1.0) & (ref == 1.0)
+    inside = ok & ~hull_out
+    np.testing.assert_allclose(got[inside], ref[inside], rtol=1e-5, atol=0)  # 1e-5 relative inside the hull
+    assert np.array_equal(got[ok] == 1.0, ref[ok] == 1.0) or np.abs(got[ok] - ref[ok]).max() < 1e-5
+    # knots reproduce their values exactly
+    assert np.array_equal(got[coords[1], coords[0]], scales.astype(np.float32))
+    return degenerate.mean()
+
+
+@pytest.mark.parametrize("tag", ["n40", "n3", "n200"])
+def test_interp_matches_reference_golden(golden, tag):
+    g = golden("interpolator.npz").case(tag)
+    frac = _interp_check(g["pred"], g["sparse"], g["valid"], g["scale_map"])
+    assert frac < 0.05
+
+
+@pytest.mark.parametrize("K,H,W", [(200, 512, 640), (512, 512, 640), (4096, 1024, 1280)])
+def test_interp_full_size_vs_scipy(K, H, W):
+    pred, target, mask = synth.alignment_inputs(11, K, H, W)
+    pred = (pred * np.float32(0.07) + np.float32(0.002)).astype(np.float32)
+    frac = _interp_check(pred, target, mask)
+    assert frac < 0.02                       # co-circular quads are rare and masked
+
+
+def test_interp_triangulation_is_delaunay_and_batched():
+    from scipy.spatial import Delaunay
+    B, K, H, W = 6, 300, 512, 640
+    xs = []
+    for b in range(B):
+        rng = np.random.default_rng(70 + b)
+        flat = np.sort(rng.choice(H * W, K - 7 * b, replace=False))
+        xs.append(np.stack([flat % W, flat // W], 1).astype(np.int32))
+    xy = np.zeros((B, K, 2), np.int32)
+    val = np.zeros((B, K), np.float32)
+    for b in range(B):
+        xy[b, :len(xs[b])] = xs[b]
+        val[b, :len(xs[b])] = np.random.default_rng(b).uniform(0.5, 2.0, len(xs[b]))
+    cnt = torch.tensor([len(x) for x in xs], dtype=torch.int32)
+    out, status, tri, tcount = ops.interp_linear(cu(xy), cu(val), cnt.to(DEV), H, W, 1.0, want_triangles=True)
+    assert not status.cpu().numpy().any()
+    for b in range(B):
+        mine = set(tuple(sorted(int(v) for v in t)) for t in tri[b, :int(tcount[b])].cpu().numpy())
+        theirs = set(tuple(sorted(int(v) for v in t)) for t in Delaunay(xs[b].astype(np.float64)).simplices)
+        assert len(mine) == len(theirs) and len(mine ^ theirs) <= 6
+    # frames are independent: frame b alone gives the same map bit for bit
+    solo, _ = ops.interp_linear(cu(xy[2:3]), cu(val[2:3]), cnt[2:3].to(DEV), H, W, 1.0)
+    assert torch.equal(solo[0], out[2])
+    again, _ = ops.interp_linear(cu(xy), cu(val), cnt.to(DEV), H, W, 1.0)
+    assert torch.equal(again, out)           # deterministic despite the atomics inside
+
+
+def test_interpolator_class_and_qhull_errors(golden):
+    from riders_b200.modules.interpolator import Interpolator2D, QhullError
+    g = golden("interpolator.npz").case("n40")
+    ip = Interpolator2D(pred_inv=g["pred"], sparse_depth_inv=g["sparse"], valid=g["valid"])
+    assert ip.num_knots == 40 and np.array_equal(ip.knot_coords, g["knot_coords"])
+    assert np.array_equal(ip.knot_scales, g["knot_scales"]) and np.array_equal(ip.knot_shifts, g["knot_shifts"])
+    ip.generate_interpolated_scale_map(interpolate_method="linear", fill_corners=False)
+    m = ip.interpolated_scale_map
+    assert m.dtype == np.float32 and m.shape == g["scale_map"].shape
+    diff = np.abs(m - g["scale_map"]) / np.abs(g["scale_map"])
+    assert np.mean(diff > 1e-5) < 0.05
+    # 2 knots / collinear knots: the reference's SciPy call raises QhullError (SURVEY 8a edge cases)
+    valid = np.zeros((16, 16), bool)
+    valid[3, 4] = valid[9, 2] = True
+    with pytest.raises(QhullError):
+        Interpolator2D(np.ones((16, 16), np.float32), np.ones((16, 16), np.float32), valid).generate_interpolated_scale_map("linear")
+    valid[:] = False
+    valid[5, [1, 4, 8, 12]] = True
+    with pytest.raises(QhullError):
+        Interpolator2D(np.ones((16, 16), np.float32), np.ones((16, 16), np.float32), valid).generate_interpolated_scale_map("linear")

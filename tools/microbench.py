@@ -111,8 +111,26 @@ def bench_loftr(N=4096):
             print(json.dumps({"kernel": "loftr_transformer_" + name, "error": str(e)[:200]}), flush=True)
 
 
+def bench_interp(B=64, K=512, H=512, W=640):
+    xy = np.zeros((B, K, 2), np.int32)
+    for b in range(B):
+        flat = np.sort(np.random.default_rng(b).choice(H * W, K, replace=False))
+        xy[b] = np.stack([flat % W, flat // W], 1)
+    val = torch.rand(B, K, device=DEV) + 0.5
+    xyd = torch.from_numpy(xy).to(DEV)
+    cnt = torch.full((B,), K, dtype=torch.int32, device=DEV)
+    ms, best = timeit(lambda: ops.interp_linear(xyd, val, cnt, H, W, 1.0), iters=5)
+    report("interp_linear(delaunay+fill)", ms, best, B * (H * W * 4 + 12 * K), B=B, K=K)
+    data = [synth.alignment_inputs(s, K, H, W) for s in range(4)]
+    p = torch.from_numpy(np.stack([d[0] for d in data])).to(DEV).repeat(B // 4, 1, 1)
+    t = torch.from_numpy(np.stack([d[1] for d in data])).to(DEV).repeat(B // 4, 1, 1)
+    m = torch.from_numpy(np.stack([d[2] for d in data])).to(DEV).repeat(B // 4, 1, 1)
+    ms, best = timeit(lambda: ops.extract_knots(p, t, m, K), iters=5)
+    report("extract_knots", ms, best, B * H * W * 9, B=B, K=K)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["reduce", "lsq", "gather", "loftr"]
+    which = sys.argv[1:] or ["reduce", "lsq", "gather", "loftr", "interp"]
     torch.cuda.set_device(DEV)
     print(json.dumps({"gpu": torch.cuda.get_device_name(0), "hbm_peak_gbs": HBM}), flush=True)
     with torch.no_grad():
