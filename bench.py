@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""RIDERS radar-to-dense-depth hot path: frames/s on B200 (+ roofline of the dominant kernel,
+CPU baseline, end-to-end figure).  Contract: see the task statement; one JSON line on stdout.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA kernels through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...   the reference's CPU path (oracle port)
+
+Workload (BASELINE.json configs[1] + the SML front-end the metric names): per step and per GPU a
+batch of 16 synthetic 640x512 thermal frames with 512 radar points each goes through
+  RC-Net quasi-dense depth (backbone -> roi gather -> point MLP -> LoFTR -> decoder -> reduce, thr 0.1)
+  -> global scale/shift LSQ alignment of the mono prior -> Delaunay/barycentric scale-map interpolation.
+Frames are independent, so N GPUs = N processes each with its own 16 frames (weak scaling), no
+data-path collective; the one all-reduce is the final metric reduction.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "RC-Net+SML-align frames/s @640x512"
+UNIT = "frames/s"
+H, W, PATCH, K_POINTS, FRAMES_PER_GPU, THR = 512, 640, (240, 100), 512, 16, 0.1
+MODEL_ARGS = dict(input_channels_image=3, input_channels_depth=3, input_patch_size_image=list(PATCH),
+                  encoder_type=["rcnet", "batch_norm"], n_filters_encoder_image=[32, 64, 128, 128, 128],
+                  n_neurons_encoder_depth=[32, 64, 128, 128, 128], decoder_type=["multiscale", "batch_norm"],
+                  n_filters_decoder=[256, 128, 64, 32, 16])          # run_rcnet_zju.py:30-45
+
+# algorithmic work per unit
+GATHER_BYTES_PER_POINT = 1393152 + 20
+GATHER_MAP_BYTES_PER_FRAME = 32612864
+LOFTR_FLOP_PER_POINT = 112939008
+REDUCE_BYTES_PER_POINT = 96000 + 12
+MAP_BYTES = H * W * 4
+
+
+def load_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return {"hbm": float(p["hbm_gbs"]), "tensor": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "source": "measured (MEASURED_PEAKS.json; bf16 sustained)"}
+    except Exception:
+        return {"hbm": 6650.0, "tensor": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def build_model(device, seed=0):
+    from riders_b200.rcnet.rcnet_model import RCNetModel
+    torch.manual_seed(seed)
+    model = RCNetModel(device=torch.device("cpu"), **MODEL_ARGS)      # init on the CPU: same weights on every arm
+    model.eval()
+    if device.type == "cuda":
+        model.device = device
+        model.to(device)
+        model.channels_last()
+    return model
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows),
+                "power_w_max": max(float(r[2]) for r in rows if r[2].replace(".", "").isdigit())}
+
+
+def cpu_frame_rate(seconds_budget, model_cpu=None, max_frames=4):
+    """The oracle port of the reference path on the host cores: frames/s over a bounded sample."""
+    from oracle import chain_ref
+    from riders_b200 import synth
+    model_cpu = model_cpu or build_model(torch.device("cpu"))
+    n, t0 = 0, time.perf_counter()
+    while n < max_frames:
+        chain_ref.chain_frame_ref(model_cpu, synth.chain_frame(n, K_POINTS, H, W, PATCH), THR)
+        n += 1
+        if time.perf_counter() - t0 > seconds_budget:
+            break
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    from oracle import chain_ref
+    from riders_b200 import synth
+    model = build_model(torch.device("cpu"))
+    frames = [synth.chain_frame(i, K_POINTS, H, W, PATCH) for i in range(2)]
+    for i in range(max(args.warmup, 0)):                      # bounded: warm-up on a K=64 slice of a frame
+        chain_ref.chain_frame_ref(model, synth.chain_frame(100 + i, 64, H, W, PATCH), THR)
+    steps = max(1, min(args.steps, 6))                           # one frame per step, <= ~1-2 min of CPU work
+    t0 = time.perf_counter()
+    for i in range(steps):
+        chain_ref.chain_frame_ref(model, frames[i % len(frames)], THR)
+    dt = time.perf_counter() - t0
+    v = steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(1, note="reference arm: one 640x512 frame (K=512) per step on the host cores"),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "%d steps x 1 frame (K=512) of the same synthetic workload; oracle port of "
+                                       "forward_output + LSQ align + griddata-linear (CPU torch/torchvision/NumPy/SciPy)" % steps},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(n_gpus, note=None):
+    c = {"workload": "configs[1] RC-Net inference (run_rcnet_zju path) + SML front-end (LSQ align + scale-map "
+                     "interpolation): synthetic 640x512 thermal frames, 512 radar points/frame, thr 0.1",
+         "frames_per_gpu_per_step": FRAMES_PER_GPU, "radar_points_per_frame": K_POINTS, "patch": list(PATCH),
+         "global_frames_per_step": FRAMES_PER_GPU * n_gpus, "parallelism": "frame-sharded x%d (no data-path collective)" % n_gpus,
+         "l2": "per-step working set (11.4 GB gathered features, 0.8 GB logits) >> 126 MB L2; no flush needed"}
+    if note:
+        c["note"] = note
+    return c
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help=argparse.SUPPRESS)
+    ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a CUDA device: the product has no CPU path")
+    from riders_b200 import dist as rdist, ops, synth
+    from riders_b200.pipeline import RadarDepthPipeline
+    rank, world, local = rdist.init()
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    B = args.frames
+    peaks = load_peaks()
+
+    model = build_model(device)
+    pipe = RadarDepthPipeline(model, response_thr=THR, chunk_points=2048)
+    batch = synth.chain_batch(rank * B, B, K_POINTS, H, W, PATCH)
+    host = {k: torch.from_numpy(batch[k]).pin_memory() for k in ("images", "points", "mono", "sparse")}
+    dev = {k: v.to(device) for k, v in host.items()}
+    offsets = batch["offsets"]
+
+    def step_device():
+        return pipe.run_device(dev["images"], dev["points"], offsets, dev["mono"], dev["sparse"])
+
+    for _ in range(args.warmup):
+        out = step_device()
+    torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- timed region (device-resident inputs)
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = ops.launch_count()
+    rdist.barrier()
+    torch.cuda.synchronize()
+    wall0 = time.time()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ops.StageTimer() as timer:
+        ev0.record()
+        for _ in range(args.steps):
+            out = step_device()
+        ev1.record()
+        torch.cuda.synchronize()
+    rdist.barrier()
+    wall1 = time.time()
+    ms_total = rdist.max_over_ranks(ev0.elapsed_time(ev1))
+    launches = ops.launch_count() - launches0
+    clocks = sampler.stop(wall0, wall1) if sampler else None
+    stages = timer.summary()
+
+    # the final metric reduction (the path's only collective): per-frame means of the three maps
+    sums = torch.stack([out["depth"].double().mean(dim=(1, 2)).sum(), (out["response"] > 0).double().mean(dim=(1, 2)).sum(),
+                        out["int_depth"].double().mean(dim=(1, 2)).sum(), out["scale_map"].double().mean(dim=(1, 2)).sum()])
+    means, n_frames = rdist.reduce_metric_sums(sums, B)
+    assert int(out["interp_status"].abs().sum().item()) == 0, "interpolation reported a failed frame"
+
+    # ---------------------------------------------------------------- end to end (pinned host in / out)
+    for _ in range(2):
+        pipe.run_host(host["images"], host["points"], offsets, host["mono"], host["sparse"], device)
+    torch.cuda.synchronize()
+    rdist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        hout, h2d, d2h = pipe.run_host(host["images"], host["points"], offsets, host["mono"], host["sparse"], device)
+        torch.cuda.current_stream().synchronize()              # the caller reads the host result every step
+    e1.record()
+    torch.cuda.synchronize()
+    rdist.barrier()
+    e2e_ms = rdist.max_over_ranks(e0.elapsed_time(e1))
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel
+    R = B * K_POINTS
+    work = {  # per step on this GPU: (bound, algorithmic bytes or flops)
+        "roi_gather": ("hbm", R * GATHER_BYTES_PER_POINT + B * GATHER_MAP_BYTES_PER_FRAME),
+        "loftr_transformer": ("tensor", R * LOFTR_FLOP_PER_POINT),
+        "confidence_reduce": ("hbm", R * REDUCE_BYTES_PER_POINT + 2 * B * MAP_BYTES),
+        "lsq_align": ("hbm", B * (2 * MAP_BYTES + H * W + MAP_BYTES)),
+        "extract_knots": ("hbm", B * (H * W + 12 * K_POINTS)),
+        "interp_linear": ("hbm", B * (MAP_BYTES + 12 * K_POINTS)),
+    }
+    stage_report = {}
+    for name, (calls, ms) in stages.items():
+        bound, amount = work.get(name, ("hbm", 0))
+        per_call = amount * args.steps / max(calls, 1)
+        avg_ms = ms / max(calls, 1)
+        ach = per_call / (avg_ms * 1e-3) / (1e9 if bound == "hbm" else 1e12) if avg_ms > 0 else 0.0
+        stage_report[name] = {"bound": bound, "calls_per_step": calls / args.steps, "ms_per_step": ms / args.steps,
+                              "achieved": round(ach, 2), "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+                              "frac": round(ach / peaks[bound], 4)}
+    ms_step = ms_total / args.steps
+    dom = max(stage_report, key=lambda k: stage_report[k]["ms_per_step"])
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+    except Exception:
+        pass
+    roofline = {"kernel": dom, "bound": stage_report[dom]["bound"], "achieved": stage_report[dom]["achieved"],
+                "peak": peaks[stage_report[dom]["bound"]], "unit": stage_report[dom]["unit"],
+                "frac": stage_report[dom]["frac"], "traffic": traffic, "peak_source": peaks["source"],
+                "share_of_step": round(stage_report[dom]["ms_per_step"] / ms_step, 4)}
+
+    line = None
+    if rank == 0:
+        line = {"metric": METRIC, "value": world * B * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(world), "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "roofline": roofline, "stages": stage_report,
+                "our_kernels_share_of_step": round(sum(s["ms_per_step"] for s in stage_report.values()) / ms_step, 4),
+                "metrics": {"frames": n_frames, "mean_depth": means[0].item(), "fired_fraction": means[1].item(),
+                            "mean_int_depth": means[2].item(), "mean_scale": means[3].item()},
+                "loftr_impl": os.environ.get("RIDERS_LOFTR_IMPL", "default")}
+        if world == 1 and not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
+            v, n, dt = cpu_frame_rate(12.0)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": "%d frame(s) (K=512) of the same batch through the oracle port, %.1f s" % (n, dt)}
+        print(json.dumps(line), flush=True)
+    rdist.shutdown()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -43,6 +43,8 @@ const char* riders_last_error_string(void);
 int         riders_abi_version(void);
 /* compute capability major*10+minor of the current device, or <0 */
 int         riders_device_arch(void);
+/* number of CUDA kernels this library has launched in this process (all threads, monotonic) */
+unsigned long long riders_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * A1  per-radar-point feature gather  ==  torchvision.ops.roi_pool x n_levels
@@ -104,6 +106,8 @@ typedef struct {
 } riders_loftr_weights;
 
 size_t riders_loftr_workspace_bytes(int N, int tokens, int d_model, int impl);
+/* 1 if `impl` is compiled into this library and covers (d_model, nhead, tokens), else 0 */
+int    riders_loftr_impl_available(int impl, int d_model, int nhead, int tokens);
 
 int riders_loftr_layer_fwd(const float* x, const float* src, const riders_loftr_weights* w,
                            int N, int L, int S, int d_model, int nhead,

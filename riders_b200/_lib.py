@@ -29,10 +29,12 @@ SIGNATURES = {
     "riders_last_error_string": (C.c_char_p, []),
     "riders_abi_version": (ci, []),
     "riders_device_arch": (ci, []),
+    "riders_launch_count": (C.c_ulonglong, []),
     "riders_roi_gather_fwd": (ci, [ci, vp, vp, vp, vp, vp, vp, vp, ci, ci, vp, ci, ci, ci, vp, vp, vp]),
     "riders_roi_gather_bwd": (ci, [ci, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, vp, ci, vp, vp]),
     "riders_linear_attention_fwd": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp, vp]),
     "riders_loftr_workspace_bytes": (sz, [ci, ci, ci, ci]),
+    "riders_loftr_impl_available": (ci, [ci, ci, ci, ci]),
     "riders_loftr_layer_fwd": (ci, [vp, vp, C.POINTER(LoftrWeights), ci, ci, ci, ci, ci, cf, cf, ci, vp, vp, vp]),
     "riders_loftr_transformer_fwd": (ci, [vp, vp, C.POINTER(LoftrWeights), C.POINTER(ci), ci,
                                           ci, ci, ci, ci, ci, cf, cf, ci, vp, vp, vp, vp]),

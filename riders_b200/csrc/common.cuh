@@ -11,6 +11,7 @@ namespace riders {
 void set_error(const char* fmt, ...);
 int  check_launch(const char* what);          // cudaGetLastError -> RIDERS_* code
 int  sm_count();
+void count_launches(int n);                   // feeds riders_launch_count() (bench.py's gpu_launches)
 
 #define RIDERS_REQUIRE(cond, ...)                         \
     do { if (!(cond)) { riders::set_error(__VA_ARGS__); return RIDERS_EINVAL; } } while (0)

@@ -135,6 +135,7 @@ extern "C" int riders_confidence_reduce(const float* conf, int conf_is_logits,
     if (B == 0) return RIDERS_OK;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(ceil_div(W, TILE_W), ceil_div(H, TILE_H), B);
+    count_launches(1);
     if (conf_is_logits)
         confidence_reduce_kernel<true><<<grid, CR_THREADS, 0, st>>>(conf, pts, frame_offsets, H, W, ph, pw, thr, depth, response, select);
     else

@@ -314,6 +314,7 @@ extern "C" int riders_extract_knots(const float* pred, const float* sparse, cons
     RIDERS_REQUIRE((long long)H * W < (1ll << 30), "extract_knots: frame too large");
     if (B == 0) return RIDERS_OK;
     RIDERS_REQUIRE(pred && sparse && valid && knot_xy && knot_scale && knot_shift && knot_count, "extract_knots: null pointer");
+    count_launches(1);
     extract_knots_kernel<<<B, EK_THREADS, 0, (cudaStream_t)stream>>>(pred, sparse, valid, H, W, max_knots,
                                                                      knot_xy, knot_scale, knot_shift, knot_count);
     return check_launch("extract_knots");
@@ -333,6 +334,7 @@ extern "C" int riders_interp_linear(const int32_t* knot_xy, const float* knot_va
     RIDERS_REQUIRE((((uintptr_t)workspace) & 255) == 0, "interp_linear: workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const WsLayout L = ws_layout(max_knots);
+    count_launches(2);
     delaunay_kernel<<<B, DT_THREADS, 0, st>>>(knot_xy, knot_val, knot_count, max_knots, (uint8_t*)workspace, L,
                                               status, tri_out, tri_count);
     dim3 grid(ceil_div(W, FT_W), ceil_div(H, FT_H), B);

@@ -76,6 +76,7 @@ extern "C" int riders_linear_attention_fwd(const float* q, const float* k, const
     if (N == 0) return RIDERS_OK;
     RIDERS_REQUIRE(q && k && v && out, "linear_attention: null pointer");
     RIDERS_REQUIRE((long long)N * H < (1ll << 31), "linear_attention: too many (sample, head) pairs");
+    count_launches(1);
     linear_attention_kernel<<<N * H, LA_THREADS, 0, (cudaStream_t)stream>>>(q, k, v, q_mask, kv_mask, L, S, H, D, eps, out);
     return check_launch("linear_attention_fwd");
 }

@@ -105,6 +105,7 @@ sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
 static void sgemm_nt(const float* A, int lda, const float* Wt, int ldw, float* C, int ldc,
                      int M, int N, int K, bool accumulate, bool relu, cudaStream_t st) {
     dim3 grid(ceil_div(M, BM), ceil_div(N, BN));
+    count_launches(1);
     sgemm_nt_kernel<<<grid, SG_THREADS, 0, st>>>(A, lda, Wt, ldw, C, ldc, M, N, K, accumulate ? 1 : 0, relu ? 1 : 0);
 }
 
@@ -160,6 +161,7 @@ static int loftr_layer_simt(const float* x, const float* src, const riders_loftr
     int rc = riders_linear_attention_fwd(s.q, s.k, s.v, nullptr, nullptr, N, L, S, nhead, C / nhead, attn_eps, s.msg, st);
     if (rc != RIDERS_OK) return rc;
     sgemm_nt(s.msg, C, w.wm, C, s.q, C, Mx, C, C, false, false, st);                 // merge -> q buffer
+    count_launches(2);
     layer_norm_kernel<<<ceil_div(Mx, 8), 256, 0, st>>>(s.q, w.ln1_g, w.ln1_b, nullptr, s.m, Mx, C, ln_eps);
     sgemm_nt(x, C, w.w1, 2 * C, s.h, 2 * C, Mx, 2 * C, C, false, false, st);         // x   * W1[:, :C]^T
     sgemm_nt(s.m, C, w.w1 + C, 2 * C, s.h, 2 * C, Mx, 2 * C, C, true, true, st);     // + m * W1[:, C:]^T, relu
@@ -169,6 +171,7 @@ static int loftr_layer_simt(const float* x, const float* src, const riders_loftr
 }
 
 // implemented in loftr_tcgen05.cu
+bool loftr_tc_built();
 size_t loftr_tc_workspace_bytes(int N, int tokens, int C);
 int loftr_layer_tc(const float* x, const float* src, const riders_loftr_weights& w, int layer_slot,
                    int N, int L, int S, int C, int nhead, float attn_eps, float ln_eps,
@@ -187,6 +190,12 @@ static int validate(const riders_loftr_weights* w, int N, int L, int S, int C, i
 }
 
 }  // namespace riders
+
+extern "C" int riders_loftr_impl_available(int impl, int d_model, int nhead, int tokens) {
+    if (impl == RIDERS_LOFTR_SIMT) return d_model > 0 && nhead > 0 && d_model % nhead == 0 && d_model % 16 == 0 && d_model / nhead <= 64;
+    if (impl == RIDERS_LOFTR_TCGEN05) return riders::loftr_tc_built() && d_model == 128 && nhead == 8 && tokens == 21;
+    return 0;
+}
 
 extern "C" size_t riders_loftr_workspace_bytes(int N, int tokens, int d_model, int impl) {
     if (N <= 0 || tokens <= 0 || d_model <= 0) return 256;

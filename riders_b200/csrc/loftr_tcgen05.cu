@@ -5,6 +5,8 @@
 
 namespace riders {
 
+bool loftr_tc_built() { return false; }
+
 size_t loftr_tc_workspace_bytes(int N, int tokens, int C) {
     return (size_t)N * tokens * C * 4 * sizeof(float) + 256;
 }

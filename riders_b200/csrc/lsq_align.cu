@@ -191,6 +191,7 @@ extern "C" int riders_lsq_align(const float* pred, const float* target, const ui
     const int ctas = ceil_div(npx, PX_PER_CTA);
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(ctas, B);
+    count_launches(2);
     lsq_partial_kernel<<<grid, LSQ_THREADS, 0, st>>>(pred, target, mask, npx, ctas, (double*)workspace);
     dim3 grid2(out ? ctas : 1, B);
     lsq_apply_kernel<<<grid2, LSQ_THREADS, 0, st>>>(pred, (const double*)workspace, npx, ctas, sums, scale_shift,

@@ -355,6 +355,7 @@ static int launch_tma_level(TmaLevel& L, int R, cudaStream_t st) {
         configured = TMA_SMEM_BUDGET;
     }
     dim3 grid(ceil_div(L.oh, L.TI), R);
+    count_launches(1);
     roi_gather_tma_kernel<<<grid, TMA_THREADS, smem, st>>>(tmap, L);
     return RIDERS_OK;
 }
@@ -410,6 +411,7 @@ extern "C" int riders_roi_gather_fwd(int n_levels,
         P.total_items = items;
         const long long blocks = (items + GEN_THREADS - 1) / GEN_THREADS;
         RIDERS_REQUIRE(blocks < (1ll << 31), "roi_gather: too many elements for one launch; chunk the RoIs");
+        count_launches(1);
         if (layout == RIDERS_LAYOUT_NHWC)
             roi_gather_generic_kernel<true><<<(unsigned)blocks, GEN_THREADS, 0, st>>>(P);
         else
@@ -439,6 +441,7 @@ extern "C" int riders_roi_gather_bwd(int n_levels,
         const long long n = (long long)B * L.C * L.H * L.W;
         const long long blocks = (n + GEN_THREADS - 1) / GEN_THREADS;
         RIDERS_REQUIRE(blocks < (1ll << 31), "roi_gather_bwd: map too large");
+        count_launches(1);
         if (layout == RIDERS_LAYOUT_NHWC)
             roi_gather_bwd_kernel<true><<<(unsigned)blocks, GEN_THREADS, 0, st>>>(L, rois, R, B);
         else

@@ -1,10 +1,14 @@
 // Error plumbing + device queries behind the C ABI.
 #include "common.cuh"
 #include <string.h>
+#include <atomic>
 
 namespace riders {
 
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -38,7 +42,8 @@ int sm_count() {
 }  // namespace riders
 
 extern "C" const char* riders_last_error_string(void) { return riders::g_err; }
-extern "C" int riders_abi_version(void) { return 1; }
+extern "C" int riders_abi_version(void) { return 2; }
+extern "C" unsigned long long riders_launch_count(void) { return riders::g_launches.load(std::memory_order_relaxed); }
 extern "C" int riders_device_arch(void) {
     int dev = 0, major = 0, minor = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { riders::set_error("no CUDA device"); cudaGetLastError(); return RIDERS_ENODEVICE; }

@@ -16,6 +16,53 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class StageTimer(object):
+    """Per-stage device timing for bench.py: while installed (``with StageTimer() as t``) every C-ABI
+    call below is bracketed by CUDA events recorded on the launching (current) stream.  Nothing
+    synchronises until ``summary()``; outside the context the wrappers cost one ``is None`` test."""
+
+    def __init__(self):
+        self.spans = {}
+
+    def __enter__(self):
+        global _timer
+        self._prev, _timer = _timer, self
+        return self
+
+    def __exit__(self, *exc):
+        global _timer
+        _timer = self._prev
+
+    def summary(self):
+        """name -> (calls, total_ms); synchronises."""
+        torch.cuda.synchronize()
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.spans.items()}
+
+
+_timer = None
+
+
+class _span(object):
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _timer is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if _timer is not None and exc[0] is None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            _timer.spans.setdefault(self.name, []).append((self.a, b))
+
+
+def launch_count():
+    """Kernels launched by libriders_b200.so in this process so far (bench.py's gpu_launches)."""
+    return int(_lib.lib().riders_launch_count())
+
+
 def _need_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
@@ -95,9 +142,10 @@ def roi_gather(feats, boxes, scales, out_sizes, max_roi=None, want_argmax=False,
         r1 = min(R, r0 + chunk)
         o_ptrs = _ptr_array([o[r0:r1] for o in outs])
         a_ptrs = _ptr_array([a[r0:r1] for a in args]) if want_argmax else None
-        rc = L.riders_roi_gather_fwd(n, _ptr_array(feats), Cs, Hs, Ws, sc, ohs, ows,
-                                     LAYOUT_NHWC if nhwc else LAYOUT_NCHW, B,
-                                     _ptr(rois[r0:r1]), r1 - r0, mw, mh, o_ptrs, a_ptrs, _stream())
+        with _span("roi_gather"):
+            rc = L.riders_roi_gather_fwd(n, _ptr_array(feats), Cs, Hs, Ws, sc, ohs, ows,
+                                         LAYOUT_NHWC if nhwc else LAYOUT_NCHW, B,
+                                         _ptr(rois[r0:r1]), r1 - r0, mw, mh, o_ptrs, a_ptrs, _stream())
         _lib.check(rc, "riders_roi_gather_fwd")
     return (outs, args) if want_argmax else outs
 
@@ -143,6 +191,10 @@ def linear_attention(q, k, v, q_mask=None, kv_mask=None, eps=1e-6):
                                                 N, Lq, S, H, D, float(eps), _ptr(out), _stream())
     _lib.check(rc, "riders_linear_attention_fwd")
     return out
+
+
+def loftr_impl_available(impl, d_model, nhead, tokens):
+    return bool(_lib.lib().riders_loftr_impl_available(int(impl), int(d_model), int(nhead), int(tokens)))
 
 
 _WEIGHT_ORDER = ("q_proj.weight", "k_proj.weight", "v_proj.weight", "merge.weight", "mlp.0.weight",
@@ -194,9 +246,10 @@ def loftr_transformer(feat0, feat1, layer_params, layer_names, nhead=8, impl=LOF
     L = _lib.lib()
     ws = torch.empty(L.riders_loftr_workspace_bytes(N, max(L0, S), Cm, impl), dtype=torch.uint8, device=feat0.device)
     out0, out1 = torch.empty_like(feat0), torch.empty_like(feat1)
-    rc = L.riders_loftr_transformer_fwd(_ptr(feat0), _ptr(feat1), arr, _int_array(kinds), n,
-                                        N, L0, S, Cm, nhead, float(attn_eps), float(ln_eps), impl,
-                                        _ptr(out0), _ptr(out1), _ptr(ws), _stream())
+    with _span("loftr_transformer"):
+        rc = L.riders_loftr_transformer_fwd(_ptr(feat0), _ptr(feat1), arr, _int_array(kinds), n,
+                                            N, L0, S, Cm, nhead, float(attn_eps), float(ln_eps), impl,
+                                            _ptr(out0), _ptr(out1), _ptr(ws), _stream())
     _lib.check(rc, "riders_loftr_transformer_fwd")
     return out0, out1
 
@@ -220,8 +273,9 @@ def confidence_reduce(conf, points, frame_offsets, H, W, thr, logits=False, want
     depth = torch.empty((B, H, W), device=dev, dtype=torch.float32)
     resp = torch.empty_like(depth)
     sel = torch.empty((B, H, W), device=dev, dtype=torch.int32) if want_select else None
-    rc = _lib.lib().riders_confidence_reduce(_ptr(conf), 1 if logits else 0, _ptr(points), _ptr(offs),
-                                             B, H, W, ph, pw, float(thr), _ptr(depth), _ptr(resp), _ptr(sel), _stream())
+    with _span("confidence_reduce"):
+        rc = _lib.lib().riders_confidence_reduce(_ptr(conf), 1 if logits else 0, _ptr(points), _ptr(offs),
+                                                 B, H, W, ph, pw, float(thr), _ptr(depth), _ptr(resp), _ptr(sel), _stream())
     _lib.check(rc, "riders_confidence_reduce")
     return depth, resp, sel
 
@@ -244,8 +298,9 @@ def lsq_align(pred, target, mask, clamp_hi=None, clamp_lo=None, want_out=True):
     ss = torch.empty((B, 2), dtype=torch.float64, device=dev)
     out = torch.empty_like(pred) if want_out else None
     flags = (1 if clamp_hi is not None else 0) | (2 if clamp_lo is not None else 0)
-    rc = L.riders_lsq_align(_ptr(pred), _ptr(target), _ptr(mask), B, H, W, _ptr(sums), _ptr(ss), _ptr(out),
-                            float(clamp_hi or 0.0), float(clamp_lo or 0.0), flags, _ptr(ws), _stream())
+    with _span("lsq_align"):
+        rc = L.riders_lsq_align(_ptr(pred), _ptr(target), _ptr(mask), B, H, W, _ptr(sums), _ptr(ss), _ptr(out),
+                                float(clamp_hi or 0.0), float(clamp_lo or 0.0), flags, _ptr(ws), _stream())
     _lib.check(rc, "riders_lsq_align")
     return sums, ss, out
 
@@ -265,8 +320,9 @@ def extract_knots(pred, sparse, valid, max_knots):
     sc = torch.zeros((B, max_knots), dtype=torch.float32, device=dev)
     sh = torch.zeros((B, max_knots), dtype=torch.float32, device=dev)
     cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
-    rc = _lib.lib().riders_extract_knots(_ptr(pred), _ptr(sparse), _ptr(valid), B, H, W, max_knots,
-                                         _ptr(xy), _ptr(sc), _ptr(sh), _ptr(cnt), _stream())
+    with _span("extract_knots"):
+        rc = _lib.lib().riders_extract_knots(_ptr(pred), _ptr(sparse), _ptr(valid), B, H, W, max_knots,
+                                             _ptr(xy), _ptr(sc), _ptr(sh), _ptr(cnt), _stream())
     _lib.check(rc, "riders_extract_knots")
     return xy, sc, sh, cnt
 
@@ -286,8 +342,9 @@ def interp_linear(knot_xy, knot_val, knot_count, H, W, fill=1.0, want_triangles=
     status = torch.zeros((B,), dtype=torch.int32, device=dev)
     tri = torch.full((B, 2 * max_knots, 3), -1, dtype=torch.int32, device=dev) if want_triangles else None
     tcount = torch.zeros((B,), dtype=torch.int32, device=dev) if want_triangles else None
-    rc = L.riders_interp_linear(_ptr(knot_xy), _ptr(knot_val), _ptr(knot_count), B, max_knots, H, W, float(fill),
-                                _ptr(out), _ptr(status), _ptr(tri), _ptr(tcount), _ptr(ws), _stream())
+    with _span("interp_linear"):
+        rc = L.riders_interp_linear(_ptr(knot_xy), _ptr(knot_val), _ptr(knot_count), B, max_knots, H, W, float(fill),
+                                    _ptr(out), _ptr(status), _ptr(tri), _ptr(tcount), _ptr(ws), _stream())
     _lib.check(rc, "riders_interp_linear")
     if want_triangles:
         return out, status, tri, tcount

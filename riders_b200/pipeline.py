@@ -1,0 +1,84 @@
+"""Batched radar-to-dense-depth chain: the public entry point of the B200 path.
+
+One call = the reference's two-script flow for a batch of frames, without the PNG round trip:
+
+  run_rcnet_zju.py:204-263   RC-Net quasi-dense depth   -> forward_output_batched (A0-A5)
+  val_zju.py:130-133         sparse radar depth -> inverse depth + validity mask
+  val_zju.py:146-155         global scale/shift LSQ alignment of the mono prior (A6/A7)
+  modules/interpolator.py    scale scaffold: knots = target/aligned, Delaunay + barycentric (A8)
+
+``run_device`` takes device tensors; ``run_host`` is the end-to-end form (pinned host buffers in,
+pinned host buffers out, copies on the current stream) that bench.py's ``e2e`` figure times.
+The SML network itself (MidasNet_small_videpth) is not constructible offline (torch.hub encoder,
+modules/midas/blocks.py:44-51) and stays the reference's torch module - any ``nn.Module`` with
+``forward(x, d)`` can be attached by the caller after this front-end.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .rcnet.rcnet_main import forward_output_batched
+
+
+class RadarDepthPipeline(object):
+    def __init__(self, model, response_thr=0.1, min_depth=0.0, max_depth=100.0,
+                 clamp_min=0.1, clamp_max=255.0, chunk_points=2048, max_knots=None):
+        self.model = model
+        self.response_thr = float(response_thr)
+        self.min_depth, self.max_depth = float(min_depth), float(max_depth)
+        self.clamp_hi = float(np.float32(1.0 / clamp_min)) if clamp_min and clamp_min > 0 else None
+        self.clamp_lo = float(np.float32(1.0 / clamp_max)) if clamp_max else None
+        self.chunk_points = chunk_points
+        self.max_knots = max_knots
+        self._pinned = {}
+
+    # ------------------------------------------------------------------------------ device
+    @torch.no_grad()
+    def run_device(self, images, radar_points, frame_offsets, mono_pred, sparse_depth):
+        """images (B,3,H,W) in [0,1]; radar_points (R,3) pad-shifted (x+pw/2, y+ph/2, z), frames
+        concatenated; frame_offsets python list (B+1); mono_pred (B,H,W) relative inverse depth;
+        sparse_depth (B,H,W) metric radar depth, 0 where empty.  Everything on the device."""
+        depth_q, response = forward_output_batched(self.model, images, radar_points, frame_offsets,
+                                                   self.response_thr, chunk_points=self.chunk_points)
+        # val_zju.py:130-133: valid = (d < max) * (d > min); d[~valid] = inf; d = 1/d  (-> 0 at invalid)
+        valid = (sparse_depth < self.max_depth) & (sparse_depth > self.min_depth)
+        sparse_inv = torch.where(valid, 1.0 / sparse_depth, torch.zeros_like(sparse_depth))
+        _, scale_shift, int_depth = ops.lsq_align(mono_pred, sparse_inv, valid,
+                                                  clamp_hi=self.clamp_hi, clamp_lo=self.clamp_lo)
+        counts = [frame_offsets[i + 1] - frame_offsets[i] for i in range(len(frame_offsets) - 1)]
+        cap = self.max_knots or max(max(counts), 1)
+        xy, scales, _, cnt = ops.extract_knots(int_depth, sparse_inv, valid, cap)
+        scale_map, status = ops.interp_linear(xy, scales, cnt, int_depth.shape[-2], int_depth.shape[-1], 1.0)
+        return {"depth": depth_q, "response": response, "int_depth": int_depth, "scale_shift": scale_shift,
+                "scale_map": scale_map, "interp_status": status, "knot_count": cnt}
+
+    # ------------------------------------------------------------------------------ host
+    def _pin(self, name, shape, dtype):
+        t = self._pinned.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(tuple(shape), dtype=dtype).pin_memory()
+            self._pinned[name] = t
+        return t
+
+    @torch.no_grad()
+    def run_host(self, images, radar_points, frame_offsets, mono_pred, sparse_depth, device=None):
+        """Same chain with HOST inputs (numpy arrays or CPU tensors, ideally pinned) and pinned
+        host outputs.  Returns (outputs dict of pinned CPU tensors, h2d_bytes, d2h_bytes).  The
+        copies run on the current stream; the final ``synchronize`` is the caller's read point."""
+        device = device or torch.device("cuda", torch.cuda.current_device())
+        h2d = 0
+        dev = []
+        for a in (images, radar_points, mono_pred, sparse_depth):
+            t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
+            if not t.is_pinned():
+                t = t.pin_memory()
+            h2d += t.numel() * t.element_size()
+            dev.append(t.to(device, non_blocking=True))
+        out = self.run_device(dev[0], dev[1], list(frame_offsets), dev[2], dev[3])
+        host, d2h = {}, 0
+        for k in ("depth", "int_depth", "scale_map", "scale_shift", "interp_status"):
+            h = self._pin(k, out[k].shape, out[k].dtype)
+            h.copy_(out[k], non_blocking=True)
+            d2h += h.numel() * h.element_size()
+            host[k] = h
+        return host, h2d, d2h

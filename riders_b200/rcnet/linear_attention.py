@@ -61,9 +61,10 @@ class LoFTREncoderLayer(nn.Module):
         return dict(self.named_parameters())
 
     def _supports(self, impl, x, source):
-        if impl == ops.LOFTR_TCGEN05:
-            return x.shape[2] == 128 and self.nhead == 8 and x.shape[1] == 21 and source.shape[1] == 21
-        return True
+        # both families are CUDA kernels of this library; the tcgen05 layer is specialised
+        if x.shape[1] != source.shape[1]:
+            return impl == ops.LOFTR_SIMT
+        return ops.loftr_impl_available(impl, x.shape[2], self.nhead, x.shape[1])
 
     def forward(self, x, source, x_mask=None, source_mask=None):
         """x [N,L,C], source [N,S,C] -> [N,L,C]."""

@@ -55,3 +55,35 @@ def alignment_inputs(seed, K, H=512, W=640, s=0.07, t=0.002):
     target = np.zeros((H, W), np.float32)
     target[mask] = ((1.0 / d_true[mask]) * (1 + 0.02 * rng.standard_normal(K))).astype(np.float32)
     return pred, target, mask
+
+
+def chain_frame(seed, K, H=512, W=640, patch=(240, 100), s=0.07, t=0.002):
+    """One frame of the full chain (BASELINE configs 2/3): thermal image, K radar points whose
+    depths are noisy samples of a smooth scene, the sparse radar depth map the SML loader would
+    read (data/UTV_dataset.py:14-17: PNG/256, 0 = empty) and the mono prior (relative inverse
+    depth of the same scene, /256-quantised).  Returns dict of float32 arrays."""
+    rng = np.random.default_rng(32452843 * (seed + 1))
+    pts, boxes = radar_points(seed, K, H, W, patch)
+    px, py = patch[1] // 2, patch[0] // 2
+    yy, xx = np.mgrid[0:H, 0:W]
+    d_true = 25 + 15 * np.sin(xx / 41.0 + seed) + 8 * np.cos(yy / 29.0) + rng.uniform(0, 1.5, (H, W))
+    mono = (np.round(((1.0 / d_true - t) / s) * 256 * 64) / (256 * 64)).astype(np.float32)
+    xs, ys = (pts[:, 0] - px).astype(np.int64), (pts[:, 1] - py).astype(np.int64)
+    z = d_true[ys, xs] * (1 + 0.02 * rng.standard_normal(K))
+    z = (np.floor(np.clip(z, 1.5, 99.0) * 256) / 256).astype(np.float32)      # uint32(z*256) PNG codec
+    pts = pts.copy()
+    pts[:, 2] = z
+    sparse = np.zeros((H, W), np.float32)
+    sparse[ys, xs] = z
+    return {"image": thermal_frame(seed, H, W), "points": pts, "boxes": boxes, "mono": mono, "sparse": sparse}
+
+
+def chain_batch(first_seed, B, K, H=512, W=640, patch=(240, 100)):
+    """B frames stacked: images (B,3,H,W), points (B*K,3), offsets list, mono (B,H,W), sparse (B,H,W)."""
+    fr = [chain_frame(first_seed + b, K, H, W, patch) for b in range(B)]
+    return {"images": np.stack([f["image"] for f in fr]),
+            "points": np.concatenate([f["points"] for f in fr]).astype(np.float32),
+            "offsets": [b * K for b in range(B + 1)],
+            "mono": np.stack([f["mono"] for f in fr]),
+            "sparse": np.stack([f["sparse"] for f in fr]),
+            "boxes": [f["boxes"] for f in fr]}

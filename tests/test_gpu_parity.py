@@ -340,3 +340,81 @@ def test_interpolator_class_and_qhull_errors(golden):
     valid[5, [1, 4, 8, 12]] = True
     with pytest.raises(QhullError):
         Interpolator2D(np.ones((16, 16), np.float32), np.ones((16, 16), np.float32), valid).generate_interpolated_scale_map("linear")
+
+
+# ------------------------------------------------------------------------------------ whole chain
+def _rand_model(device, patch, filt, dec, seed=0):
+    from riders_b200.rcnet.rcnet_model import RCNetModel
+    torch.manual_seed(seed)
+    m = RCNetModel(3, 3, list(patch), ["rcnet", "batch_norm"], filt, filt, ["multiscale", "batch_norm"], dec,
+                   device=torch.device("cpu"))
+    m.eval()
+    return m
+
+
+def _to_cuda(m):
+    import copy
+    g = copy.copy(m)
+    g.encoder, g.decoder = copy.deepcopy(m.encoder).to(DEV), copy.deepcopy(m.decoder).to(DEV)
+    g.device = torch.device(DEV)
+    return g
+
+
+def test_pipeline_matches_oracle_chain():
+    """RadarDepthPipeline (device + host entry points) against oracle.chain_ref frame by frame."""
+    from oracle import chain_ref, interpolator_ref as ir
+    from riders_b200.pipeline import RadarDepthPipeline
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    Hh, Ww, patch, K, B = 96, 128, (64, 32), 14, 3
+    cpu = _rand_model("cpu", patch, [8, 16, 16, 16, 16], [32, 16, 16, 8, 8])
+    gpu = _to_cuda(cpu).channels_last()
+    batch = synth.chain_batch(40, B, K, Hh, Ww, patch)
+    pipe = RadarDepthPipeline(gpu, response_thr=0.45, chunk_points=16)
+    out = pipe.run_device(cu(batch["images"]), cu(batch["points"]), batch["offsets"], cu(batch["mono"]), cu(batch["sparse"]))
+    hout, h2d, d2h = pipe.run_host(batch["images"], batch["points"], batch["offsets"], batch["mono"], batch["sparse"])
+    torch.cuda.synchronize()
+    assert h2d == sum(batch[k].nbytes for k in ("images", "points", "mono", "sparse")) and d2h > 3 * B * Hh * Ww * 4
+    for k in ("depth", "int_depth", "scale_map"):
+        assert np.array_equal(hout[k].numpy(), out[k].cpu().numpy())          # host entry point == device entry point
+    for b in range(B):
+        fr = synth.chain_frame(40 + b, K, Hh, Ww, patch)
+        ref = chain_ref.chain_frame_ref(cpu, fr, 0.45)
+        r, d = out["response"][b].cpu().numpy(), out["depth"][b].cpu().numpy()
+        agree = (r > 0) == (ref["response"] > 0)
+        assert agree.mean() > 0.99                                             # flips only for |conf-thr| < 1e-4
+        np.testing.assert_allclose(r[agree], ref["response"][agree], rtol=1e-4)   # confidences 1e-4 relative
+        both = agree & (ref["response"] > 0)
+        np.testing.assert_allclose(d[both], ref["depth"][both], rtol=2e-3)
+        ss = out["scale_shift"][b].cpu().numpy()
+        np.testing.assert_allclose(ss, [ref["scale"], ref["shift"]], rtol=1e-9)  # alignment 1e-6 relative (fp64 both sides)
+        assert np.array_equal(out["int_depth"][b].cpu().numpy(), ref["int_depth"])
+        coords, _, _ = ir.extract_knots_ref(ref["int_depth"], ref["sparse_inv"], ref["valid"])
+        ok = ~ir.degenerate_pixel_mask(coords.T, Hh, Ww)
+        sm = out["scale_map"][b].cpu().numpy()
+        assert np.array_equal(sm[ok] == 1.0, ref["scale_map"][ok] == 1.0)      # exactly fill outside the hull
+        np.testing.assert_allclose(sm[ok], ref["scale_map"][ok], rtol=1e-5)     # 1e-5 relative inside
+
+
+@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
+def test_full_size_rcnet_forward_vs_oracle(impl, monkeypatch):
+    """The real RC-Net configuration (d_model 128, 21 tokens, patch 240x100, 752x740 padded frame):
+    gather on the real pyramid through the TMA path + the LoFTR kernels, against the CPU oracle."""
+    if impl == "tcgen05" and not ops.loftr_impl_available(ops.LOFTR_TCGEN05, 128, 8, 21):
+        pytest.skip("tcgen05 LoFTR layer not built into this library")
+    monkeypatch.setenv("RIDERS_LOFTR_IMPL", impl)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    patch, K = (240, 100), 9
+    cpu = _rand_model("cpu", patch, [32, 64, 128, 128, 128], [256, 128, 64, 32, 16], seed=1)
+    gpu = _to_cuda(cpu).channels_last()
+    fr = synth.chain_frame(7, K, 512, 640, patch)
+    fr["points"][0, :2] = [50, 120]                       # a corner point: RoI clipped by the map edge
+    fr["boxes"][0] = [0, 0, 100, 240]
+    image = torch.from_numpy(fr["image"])[None]
+    padded = torch.nn.functional.pad(image, (50, 50, 120, 120), mode="replicate")
+    with torch.no_grad():
+        ref = rcnet_ref.model_forward_ref(cpu, padded, torch.from_numpy(fr["points"]), [torch.from_numpy(fr["boxes"])])
+        got = gpu.forward(padded.to(DEV), cu(fr["points"]), [cu(fr["boxes"])], return_logits=True)
+    # logits -> confidences within 1e-4 relative (north_star)
+    np.testing.assert_allclose(torch.sigmoid(got).cpu().numpy(), torch.sigmoid(ref).numpy(), rtol=1e-4, atol=1e-6)
