@@ -181,6 +181,13 @@ int riders_interp_linear(const int32_t* knot_xy, const float* knot_val, const in
                          int32_t* tri_out, int32_t* tri_count,
                          void* workspace, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Diagnostics.  riders_debug_tc_gemm: D (128,128) = A (128,K) * B (128,K)^T on the tcgen05 path
+ * (K = 32 or 64; terms = 1 plain tf32, 3 = hi/lo split) through the same operand staging,
+ * descriptors and TMEM read-back as the fused LoFTR layer - a device self-test of that plumbing.
+ * ------------------------------------------------------------------------------------------ */
+int riders_debug_tc_gemm(const float* a, const float* b, float* d, int K, int terms, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

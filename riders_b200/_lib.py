@@ -43,6 +43,7 @@ SIGNATURES = {
     "riders_lsq_align": (ci, [vp, vp, vp, ci, ci, ci, vp, vp, vp, cf, cf, ci, vp, vp]),
     "riders_extract_knots": (ci, [vp, vp, vp, ci, ci, ci, ci, vp, vp, vp, vp, vp]),
     "riders_interp_workspace_bytes": (sz, [ci, ci, ci, ci]),
+    "riders_debug_tc_gemm": (ci, [vp, vp, vp, ci, ci, vp]),
     "riders_interp_linear": (ci, [vp, vp, vp, ci, ci, ci, ci, cf, vp, vp, vp, vp, vp, vp]),
 }
 

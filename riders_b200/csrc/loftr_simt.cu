@@ -173,9 +173,9 @@ static int loftr_layer_simt(const float* x, const float* src, const riders_loftr
 // implemented in loftr_tcgen05.cu
 bool loftr_tc_built();
 size_t loftr_tc_workspace_bytes(int N, int tokens, int C);
-int loftr_layer_tc(const float* x, const float* src, const riders_loftr_weights& w, int layer_slot,
-                   int N, int L, int S, int C, int nhead, float attn_eps, float ln_eps,
-                   float* out, void* workspace, cudaStream_t st);
+int loftr_tc_pack(const riders_loftr_weights& w, int layer_slot, void* tc_ws, cudaStream_t st);
+int loftr_tc_run(const float* x, const float* src, const riders_loftr_weights& w, int layer_slot,
+                 int N, float attn_eps, float ln_eps, float* out, void* tc_ws, cudaStream_t st);
 
 static int validate(const riders_loftr_weights* w, int N, int L, int S, int C, int nhead, int impl) {
     RIDERS_REQUIRE(N >= 0 && L > 0 && S > 0 && C > 0 && nhead > 0, "loftr: bad shape");
@@ -216,7 +216,9 @@ extern "C" int riders_loftr_layer_fwd(const float* x, const float* src, const ri
     cudaStream_t st = (cudaStream_t)stream;
     if (impl == RIDERS_LOFTR_TCGEN05) {
         const size_t a = (size_t)N * (L > S ? L : S) * d_model;
-        return loftr_layer_tc(x, src, *w, 0, N, L, S, d_model, nhead, attn_eps, ln_eps, out, (float*)workspace + 4 * a, st);
+        void* tc_ws = (float*)workspace + 4 * a;
+        if ((rc = loftr_tc_pack(*w, 0, tc_ws, st)) != RIDERS_OK) return rc;
+        return loftr_tc_run(x, src, *w, 0, N, attn_eps, ln_eps, out, tc_ws, st);
     }
     const SimtScratch s = carve((float*)workspace, N, L > S ? L : S, d_model);
     return loftr_layer_simt(x, src, *w, N, L, S, d_model, nhead, attn_eps, ln_eps, out, s, st);
@@ -248,6 +250,10 @@ extern "C" int riders_loftr_transformer_fwd(const float* feat0, const float* fea
         const size_t a = (size_t)N * tokens * d_model;
         pa0 = ws; pa1 = ws + a; pb0 = ws + 2 * a; pb1 = ws + 3 * a;
         tc_ws = ws + 4 * a;
+        for (int i = 0; i < n_layers; ++i) {                 // split + swizzle every layer's weights once per call
+            int rc = loftr_tc_pack(layers[i], i, tc_ws, st);
+            if (rc != RIDERS_OK) return rc;
+        }
     } else {
         pa0 = s.ping0; pa1 = s.ping1; pb0 = out0; pb1 = out1;     // out buffers double as pair B
     }
@@ -259,7 +265,7 @@ extern "C" int riders_loftr_transformer_fwd(const float* feat0, const float* fea
         float* n1 = (to_end == 0) ? out1 : ((to_end & 1) ? pa1 : pb1);
         auto run = [&](const float* xx, const float* ss, int Lx, int Ss, float* oo) -> int {
             if (impl == RIDERS_LOFTR_TCGEN05)
-                return loftr_layer_tc(xx, ss, layers[i], i, N, Lx, Ss, d_model, nhead, attn_eps, ln_eps, oo, tc_ws, st);
+                return loftr_tc_run(xx, ss, layers[i], i, N, attn_eps, ln_eps, oo, tc_ws, st);
             return loftr_layer_simt(xx, ss, layers[i], N, Lx, Ss, d_model, nhead, attn_eps, ln_eps, oo, s, st);
         };
         int rc;

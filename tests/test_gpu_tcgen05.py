@@ -1,0 +1,92 @@
+"""tcgen05 / TMEM path of the LoFTR fusion (A3/A4): device self-test of the operand staging +
+descriptors, then the fused layer and the 8-layer transformer against the reference-generated
+golden vectors (tests/golden/loftr.npz, case 'rcnet': d_model 128, 8 heads, 21 tokens)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from riders_b200 import _lib, ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def _gemm(a, b, terms):
+    K = a.shape[1]
+    d = torch.empty((128, 128), dtype=torch.float32, device=DEV)
+    rc = _lib.lib().riders_debug_tc_gemm(C.c_void_p(cu(a).data_ptr()), C.c_void_p(cu(b).data_ptr()),
+                                         C.c_void_p(d.data_ptr()), K, terms,
+                                         C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "riders_debug_tc_gemm")
+    torch.cuda.synchronize()
+    return d.cpu().numpy()
+
+
+@pytest.mark.parametrize("K", [32, 64])
+def test_tc_gemm_selftest(K):
+    rng = np.random.default_rng(K)
+    a = rng.standard_normal((128, K)).astype(np.float32)
+    b = rng.standard_normal((128, K)).astype(np.float32)
+    ref = a.astype(np.float64) @ b.astype(np.float64).T
+    scale = np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64).T
+    # integers are exact in tf32: any layout / descriptor mistake shows up as a wrong integer
+    ai = rng.integers(-8, 9, (128, K)).astype(np.float32)
+    bi = rng.integers(-8, 9, (128, K)).astype(np.float32)
+    assert np.array_equal(_gemm(ai, bi, 1), ai @ bi.T)
+    one = _gemm(a, b, 1)
+    assert np.max(np.abs(one - ref) / scale) < 2e-3            # plain tf32: 2^-10 per operand
+    three = _gemm(a, b, 3)
+    assert np.max(np.abs(three - ref) / scale) < 2e-6           # 3-term split: fp32-class
+    assert np.max(np.abs(three - ref) / scale) < 0.01 * np.max(np.abs(one - ref) / scale)
+
+
+def _layer_params(g, i):
+    pre = "layers.%d." % i
+    return {k[len(pre):]: cu(v) for k, v in g.items() if k.startswith(pre)}
+
+
+def test_loftr_tcgen05_layer_and_transformer_match_reference(golden):
+    assert ops.loftr_impl_available(ops.LOFTR_TCGEN05, 128, 8, 21)
+    g = golden("loftr.npz").case("rcnet")
+    n_layers = int(g["n_layers"])
+    f0, f1 = cu(g["f0"]), cu(g["f1"])
+    # self layer (x == source) and cross layer (x != source) against the SIMT kernels and the golden
+    one = ops.loftr_layer(f0, f0, _layer_params(g, 0), impl=ops.LOFTR_TCGEN05)
+    ref_self = ops.loftr_layer(f0, f0, _layer_params(g, 0), impl=ops.LOFTR_SIMT)
+    np.testing.assert_allclose(one.cpu().numpy(), ref_self.cpu().numpy(), rtol=1e-4, atol=2e-5)
+    cross = ops.loftr_layer(f0, f1, _layer_params(g, 0), impl=ops.LOFTR_TCGEN05)
+    np.testing.assert_allclose(cross.cpu().numpy(), g["layer0"], rtol=1e-4, atol=2e-5)
+    o0, o1 = ops.loftr_transformer(f0, f1, [_layer_params(g, i) for i in range(2 * n_layers)],
+                                   ["self", "cross"] * n_layers, impl=ops.LOFTR_TCGEN05)
+    np.testing.assert_allclose(o0.cpu().numpy(), g["o0"], rtol=1e-4, atol=5e-5)      # 1e-4 relative (north_star)
+    np.testing.assert_allclose(o1.cpu().numpy(), g["o1"], rtol=1e-4, atol=5e-5)
+
+
+@pytest.mark.parametrize("N", [1, 5, 6, 7, 149 * 6 + 1])
+def test_loftr_tcgen05_ragged_tiles_vs_simt(N):
+    # tile = 6 points: partial tiles, one tile, many tiles per CTA (> 148 tiles)
+    rng = np.random.default_rng(N)
+    g = torch.Generator(device="cpu").manual_seed(N)
+    params = {}
+    for name, shape in (("q_proj.weight", (128, 128)), ("k_proj.weight", (128, 128)), ("v_proj.weight", (128, 128)),
+                        ("merge.weight", (128, 128)), ("mlp.0.weight", (256, 256)), ("mlp.2.weight", (128, 256))):
+        w = torch.empty(shape)
+        torch.nn.init.xavier_uniform_(w, generator=g)
+        params[name] = w.to(DEV)
+    for name in ("norm1", "norm2"):
+        params[name + ".weight"] = cu(rng.uniform(0.5, 1.5, 128).astype(np.float32))
+        params[name + ".bias"] = cu(rng.uniform(-0.2, 0.2, 128).astype(np.float32))
+    x = cu(rng.standard_normal((N, 21, 128)).astype(np.float32))
+    s = cu(rng.standard_normal((N, 21, 128)).astype(np.float32))
+    for src in (x, s):
+        a = ops.loftr_layer(x, src, params, impl=ops.LOFTR_TCGEN05)
+        b = ops.loftr_layer(x, src, params, impl=ops.LOFTR_SIMT)
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=2e-5)
+    again = ops.loftr_layer(x, s, params, impl=ops.LOFTR_TCGEN05)
+    assert torch.equal(again, ops.loftr_layer(x, s, params, impl=ops.LOFTR_TCGEN05))      # deterministic
