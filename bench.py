@@ -164,10 +164,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--profile", action="store_true", help=argparse.SUPPRESS)   # under ncu: 1 warm-up, no e2e / cpu legs
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    args.warmup = max(args.warmup, 3)
+    args.warmup = 1 if args.profile else max(args.warmup, 3)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl ours) needs a CUDA device: the product has no CPU path")
@@ -220,6 +221,11 @@ def main():
     assert int(out["interp_status"].abs().sum().item()) == 0, "interpolation reported a failed frame"
 
     # ---------------------------------------------------------------- end to end (pinned host in / out)
+    if args.profile:
+        print(json.dumps({"profile_run": True, "ms_per_step": ms_total / args.steps,
+                          "stages": {k: v[1] / args.steps for k, v in stages.items()}}), flush=True)
+        rdist.shutdown()
+        return 0
     for _ in range(2):
         pipe.run_host(host["images"], host["points"], offsets, host["mono"], host["sparse"], device)
     torch.cuda.synchronize()

@@ -158,6 +158,23 @@ int riders_lsq_align(const float* pred, const float* target, const uint8_t* mask
                      void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * N1  Optimizer.optimize_scale + apply_scale + clamp_min_max   modules/estimator.py:129-185
+ *     (the scripts' default alignment, val_zju.py:156-167: global_alignment='s')
+ *     minimises f(x) = sum_valid |x*pred - target| over [lo, hi] with the bounded Brent iteration of
+ *     scipy.optimize.minimize_scalar (xatol, maxiter as SciPy: 1e-5, 500); f is evaluated in fp64 over
+ *     the compacted valid pixels (deterministic).  max_valid >= valid pixels per frame (extra ones are
+ *     dropped - pass H*W to be safe).  scale (B) double out; fval (B) double, nfev (B) int32 optional.
+ *     out (B,H,W) or NULL: float32(pred * float32(scale)) then the clamps as in riders_lsq_align.
+ * ------------------------------------------------------------------------------------------ */
+size_t riders_l1_scale_workspace_bytes(int B, int max_valid);
+int riders_l1_scale_align(const float* pred, const float* target, const uint8_t* mask,
+                          int B, int H, int W, int max_valid,
+                          double lo, double hi, double xatol, int maxiter,
+                          double* scale, double* fval, int32_t* nfev,
+                          float* out, float clamp_hi, float clamp_lo, int clamp_flags,
+                          void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * A8  Interpolator2D / interpolate_knots(method='linear')   modules/interpolator.py:7-50
  *     riders_extract_knots: row-major scan of `valid` -> knot_xy (B,max_knots,2) int32 (x,y),
  *       knot_scale = sparse/pred, knot_shift = sparse-pred (float32), knot_count (B) int32 (the

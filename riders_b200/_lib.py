@@ -41,6 +41,9 @@ SIGNATURES = {
     "riders_confidence_reduce": (ci, [vp, ci, vp, vp, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp]),
     "riders_lsq_workspace_bytes": (sz, [ci, ci, ci]),
     "riders_lsq_align": (ci, [vp, vp, vp, ci, ci, ci, vp, vp, vp, cf, cf, ci, vp, vp]),
+    "riders_l1_scale_workspace_bytes": (sz, [ci, ci]),
+    "riders_l1_scale_align": (ci, [vp, vp, vp, ci, ci, ci, ci, C.c_double, C.c_double, C.c_double, ci,
+                                   vp, vp, vp, vp, cf, cf, ci, vp, vp]),
     "riders_extract_knots": (ci, [vp, vp, vp, ci, ci, ci, ci, vp, vp, vp, vp, vp]),
     "riders_interp_workspace_bytes": (sz, [ci, ci, ci, ci]),
     "riders_debug_tc_gemm": (ci, [vp, vp, vp, ci, ci, vp]),

@@ -123,3 +123,71 @@ class LeastSquaresEstimator(object):
                 self.output = self.output.cpu()
         else:
             self.output = out.reshape(np.shape(self.estimate)).cpu().numpy()
+
+
+def objective_function(x_0, prediction, target, mask):
+    """estimator.py:129-134: masked L1 error of a scale, evaluated on the device (fp64 accumulate)."""
+    p, t, m = _as3d(_to_device(prediction, torch.float32)), _as3d(_to_device(target, torch.float32)), _as3d(_to_device(mask))
+    err = (m.to(torch.float64) * (float(x_0) * p.to(torch.float64) - t.to(torch.float64)).abs()).sum()
+    return float(err.item())
+
+
+class Optimizer(object):
+    """estimator.py:136-185: scale-only alignment by bounded Brent on the masked L1 objective (the
+    scripts' default, val_zju.py:156-167).  One launch group: compaction of the valid pixels, the
+    fminbound iteration (fp64 objective over the compacted pairs), apply + clamp."""
+
+    def __init__(self, estimate, target, valid, depth_type):
+        self.estimate = estimate
+        self.target = target
+        self.valid = valid
+        self.depth_type = depth_type
+        # to be computed
+        self.scale = 1.0
+        self.output = None
+        self.nfev = None
+        self._dev = None
+
+    def _device_inputs(self):
+        if self._dev is None:
+            self._dev = (_as3d(_to_device(self.estimate, torch.float32)),
+                         _as3d(_to_device(self.target, torch.float32)),
+                         _as3d(_to_device(self.valid)))
+        return self._dev
+
+    def _bounds(self):
+        return (0.01, 0.3) if self.depth_type == 'inv' else (0.5, 1.6)      # estimator.py:147-150
+
+    def optimize_scale(self):
+        p, t, m = self._device_inputs()
+        scale, _, nfev, _ = ops.l1_scale_align(p, t, m, bounds=self._bounds(), want_out=False)
+        self.scale = np.float64(scale[0].item())                             # result.x is a NumPy float64
+        self.nfev = int(nfev[0].item())
+
+    def apply_scale(self):
+        p = self._device_inputs()[0]
+        out = p * float(np.float32(self.scale))                              # float32 array * scalar (numpy 1.23 casting)
+        self._store(out)
+
+    def clamp_min_max(self, clamp_min=None, clamp_max=None):
+        LeastSquaresEstimator.clamp_min_max(self, clamp_min, clamp_max)
+
+    def clamp_min_max_pos(self, clamp_min=None, clamp_max=None):
+        """estimator.py:178-185 (positive-depth variant)."""
+        if clamp_min is not None and clamp_min >= 0:
+            self.output[self.output < clamp_min] = clamp_min
+        if clamp_max is not None:
+            self.output[self.output > clamp_max] = clamp_max
+
+    def align(self, clamp_min=None, clamp_max=None):
+        """optimize + apply + clamp in one device call (val_zju.py:157-166 in 4 calls)."""
+        hi = float(np.float32(1.0 / clamp_min)) if (clamp_min is not None and clamp_min > 0) else None
+        lo = float(np.float32(1.0 / clamp_max)) if clamp_max is not None else None
+        p, t, m = self._device_inputs()
+        scale, _, nfev, out = ops.l1_scale_align(p, t, m, bounds=self._bounds(), clamp_hi=hi, clamp_lo=lo)
+        self.scale = np.float64(scale[0].item())
+        self.nfev = int(nfev[0].item())
+        self._store(out)
+        return self.output
+
+    _store = LeastSquaresEstimator._store

@@ -305,6 +305,33 @@ def lsq_align(pred, target, mask, clamp_hi=None, clamp_lo=None, want_out=True):
     return sums, ss, out
 
 
+def l1_scale_align(pred, target, mask, bounds=(0.01, 0.3), clamp_hi=None, clamp_lo=None, want_out=True,
+                   max_valid=None, xatol=1e-5, maxiter=500):
+    """N1: Optimizer.optimize_scale (+ apply_scale + clamp).  Returns scale (B,) f64, fval (B,) f64,
+    nfev (B,) int32, out (B,H,W) f32 | None."""
+    _need_cuda(pred, target, mask)
+    pred, target = _f32c(pred), _f32c(target)
+    mask = mask.contiguous()
+    mask = mask.view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8)
+    B, H, W = pred.shape
+    dev = pred.device
+    cap = int(max_valid) if max_valid else H * W
+    L = _lib.lib()
+    ws = torch.empty(L.riders_l1_scale_workspace_bytes(B, cap), dtype=torch.uint8, device=dev)
+    scale = torch.empty((B,), dtype=torch.float64, device=dev)
+    fval = torch.empty((B,), dtype=torch.float64, device=dev)
+    nfev = torch.empty((B,), dtype=torch.int32, device=dev)
+    out = torch.empty_like(pred) if want_out else None
+    flags = (1 if clamp_hi is not None else 0) | (2 if clamp_lo is not None else 0)
+    with _span("l1_scale_align"):
+        rc = L.riders_l1_scale_align(_ptr(pred), _ptr(target), _ptr(mask), B, H, W, cap,
+                                     float(bounds[0]), float(bounds[1]), float(xatol), int(maxiter),
+                                     _ptr(scale), _ptr(fval), _ptr(nfev), _ptr(out),
+                                     float(clamp_hi or 0.0), float(clamp_lo or 0.0), flags, _ptr(ws), _stream())
+    _lib.check(rc, "riders_l1_scale_align")
+    return scale, fval, nfev, out
+
+
 # --------------------------------------------------------------------------------------------
 # A8 interpolation
 # --------------------------------------------------------------------------------------------

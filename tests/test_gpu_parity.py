@@ -418,3 +418,44 @@ def test_full_size_rcnet_forward_vs_oracle(impl, monkeypatch):
         got = gpu.forward(padded.to(DEV), cu(fr["points"]), [cu(fr["boxes"])], return_logits=True)
     # logits -> confidences within 1e-4 relative (north_star)
     np.testing.assert_allclose(torch.sigmoid(got).cpu().numpy(), torch.sigmoid(ref).numpy(), rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------ N1 L1 scale (Optimizer)
+@pytest.mark.parametrize("depth_type,s_true", [("inv", 0.07), ("inv", 0.2), ("pos", 1.1)])
+def test_l1_scale_matches_scipy_bounded_brent(depth_type, s_true):
+    from scipy.optimize import minimize_scalar
+    B, H, W, K = 3, 120, 160, 200
+    bounds = (0.01, 0.3) if depth_type == "inv" else (0.5, 1.6)
+    P, T, M = [], [], []
+    for b in range(B):
+        pred, target, mask = synth.alignment_inputs(20 + b, K, H, W, s=s_true, t=0.0)
+        P.append(pred); T.append(target); M.append(mask)
+    P, T, M = np.stack(P), np.stack(T), np.stack(M)
+    scale, fval, nfev, out = ops.l1_scale_align(cu(P), cu(T), cu(M), bounds=bounds,
+                                                clamp_hi=10.0, clamp_lo=float(np.float32(1 / 255.0)))
+    for b in range(B):
+        p64, t64, m = P[b].astype(np.float64), T[b].astype(np.float64), M[b]
+        res = minimize_scalar(er.l1_objective_ref, args=(p64, t64, m), bounds=bounds)       # the reference's call, fp64-fed
+        # same algorithm, same fp64 objective up to summation order: 1e-6 relative on the scale (north_star)
+        np.testing.assert_allclose(scale[b].item(), res.x, rtol=1e-6)
+        assert abs(int(nfev[b]) - res.nfev) <= 2
+        np.testing.assert_allclose(fval[b].item(), res.fun, rtol=1e-9)
+        exp = P[b] * np.float32(scale[b].item())
+        exp = np.clip(exp, np.float32(1 / 255.0), np.float32(10.0))
+        assert np.array_equal(out[b].cpu().numpy(), exp)
+        res32 = minimize_scalar(er.l1_objective_ref, args=(P[b], T[b], M[b]), bounds=bounds)  # as shipped (float32 maps)
+        assert abs(scale[b].item() - res32.x) < 2e-5                                         # within Brent's own xatol
+
+
+def test_optimizer_class_is_a_drop_in():
+    from riders_b200.modules.estimator import Optimizer
+    pred, target, mask = synth.alignment_inputs(5, 300, 96, 128, s=0.05, t=0.0)
+    o = Optimizer(estimate=pred, target=target, valid=mask, depth_type="inv")
+    o.optimize_scale()
+    assert isinstance(o.scale, np.float64) and 0.01 <= o.scale <= 0.3
+    o.apply_scale()
+    o.clamp_min_max(clamp_min=0.1, clamp_max=255.0)
+    assert isinstance(o.output, np.ndarray) and o.output.dtype == np.float32 and o.output.shape == pred.shape
+    assert o.output.max() <= np.float32(10.0) and o.output.min() >= np.float32(1 / 255.0)
+    o2 = Optimizer(estimate=pred, target=target, valid=mask, depth_type="inv")
+    assert np.array_equal(o2.align(clamp_min=0.1, clamp_max=255.0), o.output) and o2.scale == o.scale

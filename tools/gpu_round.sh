@@ -1,20 +1,43 @@
 #!/bin/bash
-# One GPU visit: parity tests, smoke, bench, launch list, full ncu capture of our kernels.
-# Usage (from the repo root, under gpurun):  bash tools/gpu_round.sh <tag> [quick]
-TAG=${1:-r01}
+# One GPU visit.  Usage (repo root, under gpurun):  bash tools/gpu_round.sh <tag> <mode>...
+#   modes: tc (tcgen05 self-tests, guarded by a hard timeout)  test (pytest -m gpu + smoke)  bench
+#          micro (tools/microbench.py)  launches (ncu time-only launch list)  full:<regex>:<count> (ncu --set full)
+TAG=${1:-r01}; shift
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/gpu.txt 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/status.txt
-timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/status.txt
-timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" | tee -a $OUT/status.txt
-tail -c 3000 $OUT/bench.json
-if [ "$2" != "quick" ]; then
-  timeout 600 python tools/microbench.py > $OUT/microbench.jsonl 2> $OUT/microbench.err; echo "microbench rc=$?" | tee -a $OUT/status.txt
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches.csv \
-      python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1; echo "ncu-launches rc=$?" | tee -a $OUT/status.txt
-  timeout 900 ncu --set full --clock-control none --import-source on \
-      -k 'regex:roi_gather|confidence_reduce|lsq_|interp_fill|delaunay|extract_knots|loftr' -s 52 -c 40 -o $OUT/prof \
-      python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1; echo "ncu-full rc=$?" | tee -a $OUT/status.txt
-fi
-tail -5 $OUT/pytest_gpu.log; tail -3 $OUT/smoke.log; cat $OUT/status.txt
+for MODE in "$@"; do
+  case $MODE in
+    tc)
+      timeout -s KILL 240 python -m pytest tests/test_gpu_tcgen05.py -m gpu -x -q > $OUT/pytest_tc.log 2>&1; echo "tc rc=$?" | tee -a $OUT/status.txt
+      tail -25 $OUT/pytest_tc.log ;;
+    test)
+      timeout -s KILL 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/status.txt
+      tail -15 $OUT/pytest_gpu.log
+      timeout -s KILL 300 python -c 'import __graft_entry__ as g; g.smoke()' > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/status.txt
+      tail -3 $OUT/smoke.log ;;
+    bench)
+      timeout -s KILL 900 python bench.py --steps 5 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" | tee -a $OUT/status.txt
+      tail -c 4000 $OUT/bench.json; tail -5 $OUT/bench.err ;;
+    benchsimt)
+      RIDERS_LOFTR_IMPL=simt timeout -s KILL 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_simt.json 2> $OUT/bench_simt.err; echo "bench-simt rc=$?" | tee -a $OUT/status.txt
+      tail -c 1500 $OUT/bench_simt.json ;;
+    micro)
+      timeout -s KILL 600 python tools/microbench.py > $OUT/microbench.jsonl 2> $OUT/microbench.err; echo "microbench rc=$?" | tee -a $OUT/status.txt
+      cat $OUT/microbench.jsonl ;;
+    launches)
+      timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches.csv \
+          python bench.py --steps 1 --profile > $OUT/bench_under_ncu.log 2>&1; echo "ncu-launches rc=$?" | tee -a $OUT/status.txt
+      python tools/summarize_launches.py $OUT/launches.csv > $OUT/launches_summary.txt 2>&1; head -40 $OUT/launches_summary.txt
+      gzip -f $OUT/launches.csv ;;
+    full:*)
+      REGEX=$(echo $MODE | cut -d: -f2); COUNT=$(echo $MODE | cut -d: -f3); NAME=$(echo $REGEX | tr -c 'a-zA-Z0-9\n' '_' | cut -c1-40)
+      timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k "regex:$REGEX" -c ${COUNT:-6} -f -o $OUT/prof_$NAME \
+          python bench.py --steps 1 --profile > $OUT/ncu_full_$NAME.log 2>&1; echo "ncu-full $NAME rc=$?" | tee -a $OUT/status.txt
+      ncu -i $OUT/prof_$NAME.ncu-rep --page raw --csv > $OUT/prof_${NAME}_raw.csv 2>/dev/null
+      ncu -i $OUT/prof_$NAME.ncu-rep --page details --csv > $OUT/prof_${NAME}_details.csv 2>/dev/null
+      SZ=$(stat -c %s $OUT/prof_$NAME.ncu-rep 2>/dev/null || echo 0)
+      if [ "$SZ" -gt 12000000 ]; then rm -f $OUT/prof_$NAME.ncu-rep; echo "dropped $NAME.ncu-rep ($SZ bytes)"; fi ;;
+  esac
+done
+du -sh $OUT; cat $OUT/status.txt
