@@ -248,7 +248,8 @@ def main():
         "confidence_reduce": ("hbm", R * REDUCE_BYTES_PER_POINT + 2 * B * MAP_BYTES),
         "lsq_align": ("hbm", B * (2 * MAP_BYTES + H * W + MAP_BYTES)),
         "extract_knots": ("hbm", B * (H * W + 12 * K_POINTS)),
-        "interp_linear": ("hbm", B * (MAP_BYTES + 12 * K_POINTS)),
+        "interp_triangulate": ("hbm", B * (20 * K_POINTS + 2 * K_POINTS * 48)),   # latency bound; bytes = knots in + triangle records out
+        "interp_fill": ("hbm", B * (MAP_BYTES + 2 * K_POINTS * 48)),
     }
     stage_report = {}
     for name, (calls, ms) in stages.items():

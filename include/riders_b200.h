@@ -203,7 +203,16 @@ int riders_interp_linear(const int32_t* knot_xy, const float* knot_val, const in
  * (K = 32 or 64; terms = 1 plain tf32, 3 = hi/lo split) through the same operand staging,
  * descriptors and TMEM read-back as the fused LoFTR layer - a device self-test of that plumbing.
  * ------------------------------------------------------------------------------------------ */
+/* tuning knobs for experiments (not part of the drop-in surface): "gather_smem_kb" = TMA staging budget per CTA */
+int riders_debug_set(const char* key, int value);
 int riders_debug_tc_gemm(const float* a, const float* b, float* d, int K, int terms, void* stream);
+
+/* the two halves of riders_interp_linear, callable (and timeable) separately: the triangulation is
+ * latency bound (pointer chasing), the fill is the HBM kernel.  Same workspace for both.            */
+int riders_interp_triangulate(const int32_t* knot_xy, const float* knot_val, const int32_t* knot_count,
+                              int B, int max_knots, int32_t* status,
+                              int32_t* tri_out, int32_t* tri_count, void* workspace, void* stream);
+int riders_interp_fill(int B, int max_knots, int H, int W, float fill, float* out, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

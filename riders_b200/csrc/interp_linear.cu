@@ -17,6 +17,7 @@
 // (pointer chasing) and only amortises over a batch of frames - reported separately.
 #include "common.cuh"
 #include "delaunay_core.cuh"
+#include "ordered_compact.cuh"
 
 namespace riders {
 
@@ -86,47 +87,16 @@ __device__ inline FrameWs frame_ws(uint8_t* base, const WsLayout& L, int frame) 
 // ---------------------------------------------------------------------------------------------
 // knot extraction
 // ---------------------------------------------------------------------------------------------
-constexpr int EK_THREADS = 1024;
-
-__global__ void __launch_bounds__(EK_THREADS)
+__global__ void __launch_bounds__(OC_THREADS)
 extract_knots_kernel(const float* __restrict__ pred, const float* __restrict__ sparse,
                      const uint8_t* __restrict__ valid, int H, int W, int max_knots,
                      int32_t* __restrict__ knot_xy, float* __restrict__ knot_scale,
                      float* __restrict__ knot_shift, int32_t* __restrict__ knot_count) {
-    __shared__ int warp_sum[EK_THREADS / 32];
-    const int frame = blockIdx.x;
+    const int frame = blockIdx.y;
     const int npx = H * W;
     const size_t fo = (size_t)frame * npx;
-    const uint8_t* v = valid + fo;
-    const int per = ceil_div(npx, EK_THREADS);
-    const int begin = min(threadIdx.x * per, npx), end = min(begin + per, npx);
-    int cnt = 0;
-    for (int i = begin; i < end; ++i) cnt += v[i] ? 1 : 0;
-    // block exclusive scan of cnt
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int inc = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) warp_sum[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        int w = warp_sum[lane];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, w, o);
-            if (lane >= o) w += t;
-        }
-        warp_sum[lane] = w;
-    }
-    __syncthreads();
-    int pos = inc - cnt + (warp > 0 ? warp_sum[warp - 1] : 0);
-    if (threadIdx.x == EK_THREADS - 1) knot_count[frame] = pos + cnt;
     const size_t ko = (size_t)frame * max_knots;
-    for (int i = begin; i < end && cnt > 0; ++i) {
-        if (!v[i]) continue;
+    const int upto = ordered_compact_slice(valid + fo, npx, [&](int pos, int i) {
         if (pos < max_knots) {
             const float p = pred[fo + i], s = sparse[fo + i];
             knot_xy[(ko + pos) * 2 + 0] = i % W;
@@ -134,8 +104,23 @@ extract_knots_kernel(const float* __restrict__ pred, const float* __restrict__ s
             knot_scale[ko + pos] = __fdiv_rn(s, p);          // interpolator.py:31
             knot_shift[ko + pos] = __fsub_rn(s, p);          // interpolator.py:32
         }
-        ++pos;
-    }
+    });
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) knot_count[frame] = upto;
+}
+
+struct SmemMesh { size_t next, org, pts, perm, hulls, total; };
+
+__host__ __device__ inline SmemMesh smem_mesh_layout(int max_knots, const WsLayout& L) {
+    SmemMesh S;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) & ~(size_t)15; return at; };
+    S.next = take(sizeof(int) * 4 * (size_t)L.cap);    // also holds the P sort keys (8 B each, P <= 2 * max_knots)
+    S.org = take(sizeof(int) * 4 * (size_t)L.cap);
+    S.pts = take(sizeof(Pt) * (size_t)(max_knots + 1));
+    S.perm = take(sizeof(int) * (size_t)(max_knots + 1));
+    S.hulls = take(sizeof(Hull) * 4 * (size_t)L.P);
+    S.total = o;
+    return S;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -144,9 +129,23 @@ extract_knots_kernel(const float* __restrict__ pred, const float* __restrict__ s
 __global__ void __launch_bounds__(DT_THREADS)
 delaunay_kernel(const int32_t* __restrict__ knot_xy, const float* __restrict__ knot_val,
                 const int32_t* __restrict__ knot_count, int max_knots, uint8_t* ws_base, WsLayout L,
-                int32_t* __restrict__ status, int32_t* __restrict__ tri_out, int32_t* __restrict__ tri_count) {
+                int32_t* __restrict__ status, int32_t* __restrict__ tri_out, int32_t* __restrict__ tri_count, int mesh_in_smem) {
+    extern __shared__ __align__(16) uint8_t dsm[];
+    __shared__ int s_counters[2];                       // [0] fresh quads, [1] overflow (shared-memory mesh only)
     const int frame = blockIdx.x;
-    const FrameWs w = frame_ws(ws_base, L, frame);
+    FrameWs w = frame_ws(ws_base, L, frame);
+    int* fresh = &w.counters[0];
+    int* overflow = &w.counters[1];
+    if (mesh_in_smem) {
+        // the pointer-chasing structures live in shared memory (~30-cycle instead of L2 latency per hop);
+        // only the triangle records and their count go to the global workspace for the fill kernel
+        const SmemMesh S = smem_mesh_layout(max_knots, L);
+        w.next = (int*)(dsm + S.next); w.org = (int*)(dsm + S.org);
+        w.keys = (unsigned long long*)(dsm + S.next);   // the sort finishes before the mesh is touched
+        w.pts = (Pt*)(dsm + S.pts); w.perm = (int*)(dsm + S.perm); w.hulls = (Hull*)(dsm + S.hulls);
+        fresh = &s_counters[0]; overflow = &s_counters[1];
+        if (threadIdx.x < 2) s_counters[threadIdx.x] = 0;
+    }
     const int n = min(knot_count[frame], max_knots);
     const int tid = threadIdx.x;
     const int32_t* xy = knot_xy + (size_t)frame * max_knots * 2;
@@ -186,7 +185,7 @@ delaunay_kernel(const int32_t* __restrict__ knot_xy, const float* __restrict__ k
 
     // ---- divide and conquer, deepest level first ----------------------------------------------
     Mesh m;
-    m.next = w.next; m.org = w.org; m.fresh = &w.counters[0]; m.capacity = L.cap; m.pts = w.pts; m.overflow = &w.counters[1];
+    m.next = w.next; m.org = w.org; m.fresh = fresh; m.capacity = L.cap; m.pts = w.pts; m.overflow = overflow;
     const int D = dt::tree_depth(n);
     for (int d = D; d >= 0; --d) {
         for (int j = tid; j < (1 << d); j += DT_THREADS) dt::process_node(m, n, d, j, w.hulls);
@@ -194,7 +193,7 @@ delaunay_kernel(const int32_t* __restrict__ knot_xy, const float* __restrict__ k
     }
 
     // ---- triangle records ---------------------------------------------------------------------
-    const int quads = min(w.counters[0], L.cap);
+    const int quads = min(*fresh, L.cap);
     for (int e2 = tid; e2 < 2 * quads; e2 += DT_THREADS) {
         const int e = 4 * (e2 >> 1) + 2 * (e2 & 1);
         int a, b, c;
@@ -219,7 +218,7 @@ delaunay_kernel(const int32_t* __restrict__ knot_xy, const float* __restrict__ k
     __syncthreads();
     if (tid == 0) {
         const int nt = w.counters[2];
-        status[frame] = w.counters[1] ? RIDERS_EINTERNAL : (nt == 0 ? RIDERS_EQHULL : RIDERS_OK);
+        status[frame] = *overflow ? RIDERS_EINTERNAL : (nt == 0 ? RIDERS_EQHULL : RIDERS_OK);
         if (tri_count) tri_count[frame] = nt;
     }
 }
@@ -315,29 +314,59 @@ extern "C" int riders_extract_knots(const float* pred, const float* sparse, cons
     if (B == 0) return RIDERS_OK;
     RIDERS_REQUIRE(pred && sparse && valid && knot_xy && knot_scale && knot_shift && knot_count, "extract_knots: null pointer");
     count_launches(1);
-    extract_knots_kernel<<<B, EK_THREADS, 0, (cudaStream_t)stream>>>(pred, sparse, valid, H, W, max_knots,
+    dim3 grid(ceil_div(H * W, OC_SLICE), B);
+    extract_knots_kernel<<<grid, OC_THREADS, 0, (cudaStream_t)stream>>>(pred, sparse, valid, H, W, max_knots,
                                                                      knot_xy, knot_scale, knot_shift, knot_count);
     return check_launch("extract_knots");
+}
+
+extern "C" int riders_interp_triangulate(const int32_t* knot_xy, const float* knot_val, const int32_t* knot_count,
+                                         int B, int max_knots, int32_t* status,
+                                         int32_t* tri_out, int32_t* tri_count, void* workspace, void* stream) {
+    using namespace riders;
+    RIDERS_REQUIRE(B >= 0, "interp_triangulate: bad shape");
+    RIDERS_REQUIRE(max_knots > 0 && max_knots <= 32768, "interp_triangulate: max_knots=%d out of range (1..32768)", max_knots);
+    RIDERS_REQUIRE(B <= 65535, "interp_triangulate: at most 65535 frames per call");
+    if (B == 0) return RIDERS_OK;
+    RIDERS_REQUIRE(knot_xy && knot_val && knot_count && status && workspace, "interp_triangulate: null pointer");
+    RIDERS_REQUIRE((((uintptr_t)workspace) & 255) == 0, "interp_triangulate: workspace must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const WsLayout L = ws_layout(max_knots);
+    const SmemMesh S = smem_mesh_layout(max_knots, L);
+    const int mesh_in_smem = S.total <= 200 * 1024 ? 1 : 0;               // ~680 knots; larger frames chase pointers in L2
+    if (mesh_in_smem) {
+        static size_t configured = 0;
+        if (S.total > configured) {
+            if (cudaFuncSetAttribute(delaunay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total) != cudaSuccess)
+                return check_launch("interp_triangulate: smem attribute");
+            configured = S.total;
+        }
+    }
+    count_launches(1);
+    delaunay_kernel<<<B, DT_THREADS, mesh_in_smem ? S.total : 0, st>>>(knot_xy, knot_val, knot_count, max_knots, (uint8_t*)workspace, L,
+                                                                       status, tri_out, tri_count, mesh_in_smem);
+    return check_launch("interp_triangulate");
+}
+
+extern "C" int riders_interp_fill(int B, int max_knots, int H, int W, float fill, float* out, void* workspace, void* stream) {
+    using namespace riders;
+    RIDERS_REQUIRE(B >= 0 && H > 0 && W > 0, "interp_fill: bad shape");
+    RIDERS_REQUIRE(H <= 8192 && W <= 8192, "interp_fill: exact predicates need H, W <= 8192");
+    RIDERS_REQUIRE(max_knots > 0 && max_knots <= 32768 && B <= 65535, "interp_fill: max_knots / B out of range");
+    if (B == 0) return RIDERS_OK;
+    RIDERS_REQUIRE(out && workspace, "interp_fill: null pointer");
+    const WsLayout L = ws_layout(max_knots);
+    dim3 grid(ceil_div(W, FT_W), ceil_div(H, FT_H), B);
+    count_launches(1);
+    interp_fill_kernel<<<grid, FILL_THREADS, 0, (cudaStream_t)stream>>>((uint8_t*)workspace, L, max_knots, H, W, fill, out);
+    return check_launch("interp_fill");
 }
 
 extern "C" int riders_interp_linear(const int32_t* knot_xy, const float* knot_val, const int32_t* knot_count,
                                     int B, int max_knots, int H, int W, float fill,
                                     float* out, int32_t* status, int32_t* tri_out, int32_t* tri_count,
                                     void* workspace, void* stream) {
-    using namespace riders;
-    RIDERS_REQUIRE(B >= 0 && H > 0 && W > 0, "interp_linear: bad shape");
-    RIDERS_REQUIRE(H <= 8192 && W <= 8192, "interp_linear: exact predicates need H, W <= 8192");
-    RIDERS_REQUIRE(max_knots > 0 && max_knots <= 32768, "interp_linear: max_knots=%d out of range (1..32768)", max_knots);
-    RIDERS_REQUIRE(B <= 65535, "interp_linear: at most 65535 frames per call");
-    if (B == 0) return RIDERS_OK;
-    RIDERS_REQUIRE(knot_xy && knot_val && knot_count && out && status && workspace, "interp_linear: null pointer");
-    RIDERS_REQUIRE((((uintptr_t)workspace) & 255) == 0, "interp_linear: workspace must be 256-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
-    const WsLayout L = ws_layout(max_knots);
-    count_launches(2);
-    delaunay_kernel<<<B, DT_THREADS, 0, st>>>(knot_xy, knot_val, knot_count, max_knots, (uint8_t*)workspace, L,
-                                              status, tri_out, tri_count);
-    dim3 grid(ceil_div(W, FT_W), ceil_div(H, FT_H), B);
-    interp_fill_kernel<<<grid, FILL_THREADS, 0, st>>>((uint8_t*)workspace, L, max_knots, H, W, fill, out);
-    return check_launch("interp_linear");
+    int rc = riders_interp_triangulate(knot_xy, knot_val, knot_count, B, max_knots, status, tri_out, tri_count, workspace, stream);
+    if (rc != RIDERS_OK) return rc;
+    return riders_interp_fill(B, max_knots, H, W, fill, out, workspace, stream);
 }

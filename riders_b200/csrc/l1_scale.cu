@@ -9,51 +9,23 @@
 //                          objective is a deterministic fp64 block reduction over the compacted pairs
 //   l1_apply_kernel      : out = fl32(pred * fl32(scale)) + the two clamps (estimator.py:161-176)
 #include "common.cuh"
+#include "ordered_compact.cuh"
 
 namespace riders {
 
-constexpr int CV_THREADS = 1024;
 constexpr int BR_THREADS = 256;
 
-__global__ void __launch_bounds__(CV_THREADS)
+__global__ void __launch_bounds__(OC_THREADS)
 compact_valid_kernel(const float* __restrict__ pred, const float* __restrict__ target,
                      const uint8_t* __restrict__ valid, int npx, int cap,
                      float2* __restrict__ pairs, int32_t* __restrict__ count) {
-    __shared__ int warp_sum[CV_THREADS / 32];
-    const int frame = blockIdx.x;
+    const int frame = blockIdx.y;
     const size_t fo = (size_t)frame * npx;
-    const uint8_t* v = valid + fo;
-    const int per = ceil_div(npx, CV_THREADS);
-    const int begin = min((int)threadIdx.x * per, npx), end = min(begin + per, npx);
-    int cnt = 0;
-    for (int i = begin; i < end; ++i) cnt += v[i] ? 1 : 0;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int inc = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) warp_sum[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        int w = warp_sum[lane];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, w, o);
-            if (lane >= o) w += t;
-        }
-        warp_sum[lane] = w;
-    }
-    __syncthreads();
-    int pos = inc - cnt + (warp > 0 ? warp_sum[warp - 1] : 0);
-    if (threadIdx.x == CV_THREADS - 1) count[frame] = pos + cnt;
     float2* dst = pairs + (size_t)frame * cap;
-    for (int i = begin; i < end && cnt > 0; ++i) {
-        if (!v[i]) continue;
+    const int upto = ordered_compact_slice(valid + fo, npx, [&](int pos, int i) {
         if (pos < cap) dst[pos] = make_float2(pred[fo + i], target[fo + i]);
-        ++pos;
-    }
+    });
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) count[frame] = upto;
 }
 
 // deterministic block sum of |x*p - t| over the frame's pairs; every thread returns the same value
@@ -195,7 +167,7 @@ extern "C" int riders_l1_scale_align(const float* pred, const float* target, con
     float2* pairs = (float2*)workspace;
     int32_t* count = (int32_t*)((uint8_t*)workspace + l1_pairs_bytes(B, max_valid));
     count_launches(out ? 3 : 2);
-    compact_valid_kernel<<<B, CV_THREADS, 0, st>>>(pred, target, mask, npx, max_valid, pairs, count);
+    compact_valid_kernel<<<dim3(ceil_div(npx, OC_SLICE), B), OC_THREADS, 0, st>>>(pred, target, mask, npx, max_valid, pairs, count);
     l1_brent_kernel<<<B, BR_THREADS, 0, st>>>(pairs, count, max_valid, lo, hi, xatol, maxiter, scale, fval, nfev);
     if (out) {
         dim3 grid(min(ceil_div(npx, 256 * 4), 1024), B);

@@ -109,9 +109,10 @@ roi_gather_generic_kernel(const GatherParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// TMA-staged channels-last kernel
+// TMA-staged channels-last kernel: ONE launch for every pyramid level
 // ---------------------------------------------------------------------------------------------
 constexpr int TMA_THREADS = 256;
+constexpr int TMA_MAX_LEVELS = RIDERS_MAX_LEVELS;
 
 struct TmaLevel {
     const float* feat; float* out;
@@ -119,7 +120,14 @@ struct TmaLevel {
     float scale;
     int TI;          // pooled rows per CTA
     int BH, BW;      // TMA box rows / cols
-    int B;
+    int cv_shift;    // log2(C / 4); C / 4 is a power of two on this path
+    int strips;      // CTAs per RoI
+    int first_block; // first linear block index of this level
+};
+struct TmaPack {
+    CUtensorMap map[TMA_MAX_LEVELS];
+    TmaLevel lv[TMA_MAX_LEVELS];
+    int n_levels, B;
     const float* rois;
 };
 
@@ -143,19 +151,41 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!done);
 }
 
+__device__ __forceinline__ float4 max4(float4 a, const float4 b) {
+    a.x = fmaxf(a.x, b.x); a.y = fmaxf(a.y, b.y); a.z = fmaxf(a.z, b.z); a.w = fmaxf(a.w, b.w);
+    return a;
+}
+
+// maximum of the window [hb.x, hb.y) x [wb.x, wb.y) (pixels, relative to `base`); empty window -> 0
+__device__ __forceinline__ float4 window_max(const float* base, int row_stride, int C, short2 hb, short2 wb) {
+    if (hb.y <= hb.x || wb.y <= wb.x) return make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 best = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+    for (int h = hb.x; h < hb.y; ++h) {
+        const float* prow = base + h * row_stride;
+        for (int w = wb.x; w < wb.y; ++w) best = max4(best, *reinterpret_cast<const float4*>(prow + w * C));
+    }
+    return best;
+}
+
 __global__ void __launch_bounds__(TMA_THREADS)
-roi_gather_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaLevel L) {
+roi_gather_tma_kernel(const __grid_constant__ TmaPack P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ short2 wbin[256];        // per pooled column: [w0, w1) relative to the staged window
     __shared__ short2 hbin[64];         // per pooled row of this strip
-    __shared__ int s_fallback;
+
+    int l = 0;
+#pragma unroll
+    for (int q = 1; q < TMA_MAX_LEVELS; ++q)
+        if (q < P.n_levels && (int)blockIdx.x >= P.lv[q].first_block) l = q;
+    const TmaLevel& L = P.lv[l];
 
     float* tile = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-    const int r = blockIdx.y;
-    const int i0 = blockIdx.x * L.TI;
+    const int blk = (int)blockIdx.x - L.first_block;
+    const int r = blk / L.strips;
+    const int i0 = (blk - r * L.strips) * L.TI;
     const int ni = min(L.TI, L.oh - i0);
-    const float* roi = L.rois + (size_t)r * 5;
+    const float* roi = P.rois + (size_t)r * 5;
     const int b = (int)roi[0];
     const RoiAxis ax = roi_axis(roi[1], roi[3], L.scale, L.ow);
     const RoiAxis ay = roi_axis(roi[2], roi[4], L.scale, L.oh);
@@ -165,23 +195,21 @@ roi_gather_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaLevel L
     const int win_w = ax.start;
     const int last_h = (int)ceilf(__fmul_rn((float)(i0 + ni), ay.bin)) + ay.start;    // exclusive
     const int last_w = (int)ceilf(__fmul_rn((float)L.ow, ax.bin)) + ax.start;
-    const bool fits = (last_h - win_h <= L.BH) && (last_w - win_w <= L.BW) && b >= 0 && b < L.B;
+    const bool bad = b < 0 || b >= P.B;
+    const bool fits = (last_h - win_h <= L.BH) && (last_w - win_w <= L.BW) && !bad;   // CTA-uniform
 
-    if (threadIdx.x == 0) {
-        s_fallback = fits ? 0 : 1;
-        if (fits) {
-            mbar_init(&bar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            const uint32_t bytes = (uint32_t)L.BH * L.BW * L.C * 4u;
-            mbar_expect_tx(&bar, bytes);
-            asm volatile(
-                "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-                " [%0], [%1, {%2, %3, %4, %5}], [%6];"
-                ::"r"(smem_u32(tile)), "l"(&tmap), "r"(0), "r"(win_w), "r"(win_h), "r"(b), "r"(smem_u32(&bar))
-                : "memory");
-        }
+    if (threadIdx.x == 0 && fits) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t bytes = (uint32_t)L.BH * L.BW * L.C * 4u;
+        mbar_expect_tx(&bar, bytes);
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+            " [%0], [%1, {%2, %3, %4, %5}], [%6];"
+            ::"r"(smem_u32(tile)), "l"(&P.map[l]), "r"(0), "r"(win_w), "r"(win_h), "r"(b), "r"(smem_u32(&bar))
+            : "memory");
     }
-    // bin tables (clipped to the map, then made window-relative)
+    // bin tables (clipped to the map, then made window-relative) while the tile is in flight
     for (int j = threadIdx.x; j < L.ow; j += TMA_THREADS) {
         int w0, w1;
         roi_bin_range(ax, j, L.W, w0, w1);
@@ -194,50 +222,39 @@ roi_gather_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaLevel L
     }
     __syncthreads();
 
-    const int CV = L.C >> 2;
-    const int n_items = ni * L.ow * CV;
-    float* out_base = L.out + (((size_t)r * L.oh + i0) * L.ow) * L.C;
+    // thread -> (channel group c4, pixel); pixels advance by PP per pass, no divisions in the loop
+    const int CV = 1 << L.cv_shift;
+    const int c4 = threadIdx.x & (CV - 1);
+    const int PP = TMA_THREADS >> L.cv_shift;
+    const int npix = ni * L.ow;
+    int p = threadIdx.x >> L.cv_shift;
+    int i = p / L.ow, j = p - i * L.ow;
+    const int di = PP / L.ow, dj = PP - di * L.ow;
+    float4* out_base = reinterpret_cast<float4*>(L.out + (((size_t)r * L.oh + i0) * L.ow) * L.C) + c4;
 
-    if (s_fallback) {
-        // RoI larger than the staged box (or bad batch index): read the map directly
-        const bool bad = b < 0 || b >= L.B;
-        const float* base = L.feat + (size_t)(bad ? 0 : b) * L.H * L.W * L.C;
-        for (int t = threadIdx.x; t < n_items; t += TMA_THREADS) {
-            const int c = t % CV, j = (t / CV) % L.ow, i = t / (CV * L.ow);
-            const short2 hb = hbin[i], wb = wbin[j];
-            const bool empty = hb.y <= hb.x || wb.y <= wb.x || bad;
-            float4 best = empty ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
-            if (!empty)
-                for (int h = hb.x + win_h; h < hb.y + win_h; ++h)
-                    for (int w = wb.x + win_w; w < wb.y + win_w; ++w) {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(base + ((size_t)h * L.W + w) * L.C + c * 4));
-                        best.x = fmaxf(best.x, v.x); best.y = fmaxf(best.y, v.y);
-                        best.z = fmaxf(best.z, v.z); best.w = fmaxf(best.w, v.w);
-                    }
-            __stcs(reinterpret_cast<float4*>(out_base + (size_t)t * 4), best);
-        }
-        return;
+    const float* src;
+    int row_stride;
+    if (fits) {
+        mbar_wait(&bar, 0);
+        src = tile + c4 * 4;
+        row_stride = L.BW * L.C;
+    } else {
+        // RoI larger than the staged box (or bad batch index -> zeros): read the map directly
+        src = L.feat + ((size_t)(bad ? 0 : b) * L.H * L.W + (size_t)win_h * L.W + win_w) * L.C + c4 * 4;
+        row_stride = L.W * L.C;
     }
-
-    mbar_wait(&bar, 0);
-    const int row_stride = L.BW * L.C;            // floats
-    for (int t = threadIdx.x; t < n_items; t += TMA_THREADS) {
-        const int c = t % CV, j = (t / CV) % L.ow, i = t / (CV * L.ow);
-        const short2 hb = hbin[i], wb = wbin[j];
-        const bool empty = hb.y <= hb.x || wb.y <= wb.x;
-        float4 best = empty ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
-        if (!empty) {
-            const float* p0 = tile + c * 4;
-            for (int h = hb.x; h < hb.y; ++h) {
-                const float* prow = p0 + h * row_stride;
-                for (int w = wb.x; w < wb.y; ++w) {
-                    const float4 v = *reinterpret_cast<const float4*>(prow + w * L.C);
-                    best.x = fmaxf(best.x, v.x); best.y = fmaxf(best.y, v.y);
-                    best.z = fmaxf(best.z, v.z); best.w = fmaxf(best.w, v.w);
-                }
-            }
-        }
-        __stcs(reinterpret_cast<float4*>(out_base + (size_t)t * 4), best);
+    for (; p < npix; p += 2 * PP) {
+        const short2 hb0 = hbin[i], wb0 = wbin[j];
+        int i1 = i + di, j1 = j + dj;
+        if (j1 >= L.ow) { j1 -= L.ow; ++i1; }
+        const bool two = p + PP < npix;
+        float4 v0 = bad ? make_float4(0.f, 0.f, 0.f, 0.f) : window_max(src, row_stride, L.C, hb0, wb0);
+        float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (two && !bad) v1 = window_max(src, row_stride, L.C, hbin[i1], wbin[j1]);
+        __stcs(out_base + (size_t)p * CV, v0);
+        if (two) __stcs(out_base + (size_t)(p + PP) * CV, v1);
+        i = i1 + di; j = j1 + dj;
+        if (j >= L.ow) { j -= L.ow; ++i; }
     }
 }
 
@@ -310,12 +327,17 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-constexpr int TMA_SMEM_BUDGET = 72 * 1024;     // per CTA -> 3 CTAs per SM
+static int g_tma_smem_budget = 72 * 1024;     // per CTA -> 3 CTAs per SM (tunable: riders_debug_set("gather_smem_kb", v))
+
+void set_gather_smem_budget(int kb) { if (kb >= 16 && kb <= 200) g_tma_smem_budget = kb * 1024; }
 
 // choose strip height / box for one level; returns false if the TMA path cannot be used
 static bool plan_tma_level(TmaLevel& L, int max_roi_w, int max_roi_h) {
     if (max_roi_w <= 0 || max_roi_h <= 0) return false;
-    if ((L.C & 3) || L.C > 256 || L.ow > 256) return false;
+    const int cv = L.C >> 2;
+    if ((L.C & 3) || cv > TMA_THREADS || (cv & (cv - 1)) || L.C > 256 || L.ow > 256) return false;
+    L.cv_shift = 0;
+    while ((1 << L.cv_shift) < cv) ++L.cv_shift;
     const int rw_max = (int)ceilf(max_roi_w * L.scale) + 2;
     const int rh_max = (int)ceilf(max_roi_h * L.scale) + 2;
     const float bh_max = (float)rh_max / (float)L.oh;
@@ -325,38 +347,52 @@ static bool plan_tma_level(TmaLevel& L, int max_roi_w, int max_roi_h) {
     for (int ti = 1; ti <= L.oh && ti <= 64; ++ti) {
         const int bh = (int)(ti * bh_max) + 2;
         if (bh > 256) break;
-        if ((size_t)bh * L.BW * L.C * 4 + 128 <= (size_t)TMA_SMEM_BUDGET) best = ti;
+        if ((size_t)bh * L.BW * L.C * 4 + 128 <= (size_t)g_tma_smem_budget) best = ti;
     }
     if (best == 0) return false;
     // even out the strips
-    const int strips = ceil_div(L.oh, best);
-    L.TI = ceil_div(L.oh, strips);
+    L.strips = ceil_div(L.oh, best);
+    L.TI = ceil_div(L.oh, L.strips);
+    L.strips = ceil_div(L.oh, L.TI);
     L.BH = (int)(L.TI * bh_max) + 2;
     return true;
 }
 
-static int launch_tma_level(TmaLevel& L, int R, cudaStream_t st) {
+static int encode_level_map(CUtensorMap* tmap, const TmaLevel& L, int B) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("roi_gather: cuTensorMapEncodeTiled unavailable"); return RIDERS_ECUDA; }
-    CUtensorMap tmap;
-    cuuint64_t dims[4] = {(cuuint64_t)L.C, (cuuint64_t)L.W, (cuuint64_t)L.H, (cuuint64_t)L.B};
+    cuuint64_t dims[4] = {(cuuint64_t)L.C, (cuuint64_t)L.W, (cuuint64_t)L.H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)L.C * 4, (cuuint64_t)L.W * L.C * 4, (cuuint64_t)L.H * L.W * L.C * 4};
     cuuint32_t box[4] = {(cuuint32_t)L.C, (cuuint32_t)L.BW, (cuuint32_t)L.BH, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)L.feat, dims, strides, box, estr,
+    CUresult cr = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)L.feat, dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("roi_gather: cuTensorMapEncodeTiled failed (%d)", (int)cr); return RIDERS_ECUDA; }
-    const size_t smem = (size_t)L.BH * L.BW * L.C * 4 + 128;
+    return RIDERS_OK;
+}
+
+static int launch_tma_pack(TmaPack& P, int R, cudaStream_t st) {
+    size_t smem = 0;
+    long long blocks = 0;
+    for (int l = 0; l < P.n_levels; ++l) {
+        TmaLevel& L = P.lv[l];
+        int rc = encode_level_map(&P.map[l], L, P.B);
+        if (rc != RIDERS_OK) return rc;
+        const size_t need = (size_t)L.BH * L.BW * L.C * 4 + 128;
+        if (need > smem) smem = need;
+        L.first_block = (int)blocks;
+        blocks += (long long)R * L.strips;
+    }
+    RIDERS_REQUIRE(blocks < (1ll << 31), "roi_gather: too many CTAs for one launch; chunk the RoIs");
     static size_t configured = 0;
     if (smem > configured) {
-        if (cudaFuncSetAttribute(roi_gather_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BUDGET) != cudaSuccess)
+        if (cudaFuncSetAttribute(roi_gather_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return check_launch("roi_gather: smem attribute");
-        configured = TMA_SMEM_BUDGET;
+        configured = smem;
     }
-    dim3 grid(ceil_div(L.oh, L.TI), R);
     count_launches(1);
-    roi_gather_tma_kernel<<<grid, TMA_THREADS, smem, st>>>(tmap, L);
+    roi_gather_tma_kernel<<<(unsigned)blocks, TMA_THREADS, smem, st>>>(P);
     return RIDERS_OK;
 }
 
@@ -380,6 +416,8 @@ extern "C" int riders_roi_gather_fwd(int n_levels,
 
     GatherParams P;
     P.n_levels = 0; P.B = B; P.R = R; P.rois = rois;
+    static thread_local TmaPack TP;           // 1.5 KB: the levels that take the TMA path, one launch
+    TP.n_levels = 0; TP.B = B; TP.rois = rois;
     long long items = 0;
     for (int l = 0; l < n_levels; ++l) {
         RIDERS_REQUIRE(feat[l] && out[l], "roi_gather: null map at level %d", l);
@@ -390,14 +428,10 @@ extern "C" int riders_roi_gather_fwd(int n_levels,
             RIDERS_REQUIRE((C[l] & 3) == 0 && (((uintptr_t)feat[l]) & 15) == 0 && (((uintptr_t)out[l]) & 15) == 0,
                            "roi_gather: channels-last path needs C%%4==0 and 16-byte aligned maps (level %d)", l);
             if (!want_arg) {
-                TmaLevel T;
+                TmaLevel& T = TP.lv[TP.n_levels];
                 T.feat = feat[l]; T.out = out[l]; T.C = C[l]; T.H = Hl[l]; T.W = Wl[l]; T.oh = oh[l]; T.ow = ow[l];
-                T.scale = spatial_scale[l]; T.B = B; T.rois = rois;
-                if (plan_tma_level(T, max_roi_w, max_roi_h)) {
-                    int rc = launch_tma_level(T, R, st);
-                    if (rc != RIDERS_OK) return rc;
-                    continue;
-                }
+                T.scale = spatial_scale[l];
+                if (plan_tma_level(T, max_roi_w, max_roi_h)) { ++TP.n_levels; continue; }
             }
         }
         GatherLevel& G = P.lv[P.n_levels++];
@@ -406,6 +440,10 @@ extern "C" int riders_roi_gather_fwd(int n_levels,
         G.first_item = items;
         const long long cg = (layout == RIDERS_LAYOUT_NHWC) ? C[l] / 4 : C[l];
         items += (long long)R * cg * oh[l] * ow[l];
+    }
+    if (TP.n_levels > 0) {
+        int rc = launch_tma_pack(TP, R, st);
+        if (rc != RIDERS_OK) return rc;
     }
     if (P.n_levels > 0) {
         P.total_items = items;

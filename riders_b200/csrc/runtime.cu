@@ -44,6 +44,11 @@ int sm_count() {
 extern "C" const char* riders_last_error_string(void) { return riders::g_err; }
 extern "C" int riders_abi_version(void) { return 2; }
 extern "C" unsigned long long riders_launch_count(void) { return riders::g_launches.load(std::memory_order_relaxed); }
+extern "C" int riders_debug_set(const char* key, int value) {
+    if (key && !strcmp(key, "gather_smem_kb")) { riders::set_gather_smem_budget(value); return RIDERS_OK; }
+    riders::set_error("debug_set: unknown key '%s'", key ? key : "(null)");
+    return RIDERS_EINVAL;
+}
 extern "C" int riders_device_arch(void) {
     int dev = 0, major = 0, minor = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { riders::set_error("no CUDA device"); cudaGetLastError(); return RIDERS_ENODEVICE; }

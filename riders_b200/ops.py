@@ -369,10 +369,13 @@ def interp_linear(knot_xy, knot_val, knot_count, H, W, fill=1.0, want_triangles=
     status = torch.zeros((B,), dtype=torch.int32, device=dev)
     tri = torch.full((B, 2 * max_knots, 3), -1, dtype=torch.int32, device=dev) if want_triangles else None
     tcount = torch.zeros((B,), dtype=torch.int32, device=dev) if want_triangles else None
-    with _span("interp_linear"):
-        rc = L.riders_interp_linear(_ptr(knot_xy), _ptr(knot_val), _ptr(knot_count), B, max_knots, H, W, float(fill),
-                                    _ptr(out), _ptr(status), _ptr(tri), _ptr(tcount), _ptr(ws), _stream())
-    _lib.check(rc, "riders_interp_linear")
+    with _span("interp_triangulate"):
+        rc = L.riders_interp_triangulate(_ptr(knot_xy), _ptr(knot_val), _ptr(knot_count), B, max_knots,
+                                         _ptr(status), _ptr(tri), _ptr(tcount), _ptr(ws), _stream())
+    _lib.check(rc, "riders_interp_triangulate")
+    with _span("interp_fill"):
+        rc = L.riders_interp_fill(B, max_knots, H, W, float(fill), _ptr(out), _ptr(ws), _stream())
+    _lib.check(rc, "riders_interp_fill")
     if want_triangles:
         return out, status, tri, tcount
     return out, status

@@ -20,7 +20,8 @@ def cu(a):
 def _gemm(a, b, terms):
     K = a.shape[1]
     d = torch.empty((128, 128), dtype=torch.float32, device=DEV)
-    rc = _lib.lib().riders_debug_tc_gemm(C.c_void_p(cu(a).data_ptr()), C.c_void_p(cu(b).data_ptr()),
+    ta, tb = cu(a), cu(b)                      # keep both alive: the caching allocator would reuse a freed block
+    rc = _lib.lib().riders_debug_tc_gemm(C.c_void_p(ta.data_ptr()), C.c_void_p(tb.data_ptr()),
                                          C.c_void_p(d.data_ptr()), K, terms,
                                          C.c_void_p(torch.cuda.current_stream().cuda_stream))
     _lib.check(rc, "riders_debug_tc_gemm")

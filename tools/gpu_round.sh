@@ -9,8 +9,9 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 for MODE in "$@"; do
   case $MODE in
     tc)
-      timeout -s KILL 240 python -m pytest tests/test_gpu_tcgen05.py -m gpu -x -q > $OUT/pytest_tc.log 2>&1; echo "tc rc=$?" | tee -a $OUT/status.txt
-      tail -25 $OUT/pytest_tc.log ;;
+      timeout -s KILL 240 python -m pytest tests/test_gpu_tcgen05.py -m gpu -q > $OUT/pytest_tc.log 2>&1; RC=$?; echo "tc rc=$RC" | tee -a $OUT/status.txt
+      tail -40 $OUT/pytest_tc.log
+      if [ $RC -ne 0 ]; then export RIDERS_LOFTR_IMPL=simt; echo "tcgen05 tests failed -> remaining modes run with RIDERS_LOFTR_IMPL=simt"; fi ;;
     test)
       timeout -s KILL 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/status.txt
       tail -15 $OUT/pytest_gpu.log
