@@ -60,7 +60,7 @@ def build_model(device, seed=0):
     if device.type == "cuda":
         model.device = device
         model.to(device)
-        model.channels_last()
+        model.optimize_for_inference()
     return model
 
 

@@ -199,12 +199,27 @@ int riders_interp_linear(const int32_t* knot_xy, const float* knot_val, const in
                          void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Decoder glue next to the gather: nearest-neighbour resize of channels-last maps, bit-exact with
+ * torch.nn.functional.interpolate(x, size=(H, W)) (mode 'nearest'); utils/net_utils.py:149-190.
+ *     x (N, C, h, w) / out (N, C, H, W), both in memory order N,H,W,C; C % 4 == 0.
+ * ------------------------------------------------------------------------------------------ */
+int riders_upsample_nearest_nhwc(const float* x, int N, int C, int h, int w, int H, int W,
+                                 float* out, void* stream);
+/* out[p][0:Ca] = leaky_relu(a[p][:], slope) (or a copy if !act_on_a); out[p][Ca:Ca+Cb] = b[p][:] for
+ * `pixels` channels-last pixels: DecoderBlock's activation + torch.cat([y, skip], 1) in one pass
+ * (utils/net_utils.py:474-569).  Ca, Cb multiples of 4; Cb may be 0 (activation only, out of place). */
+int riders_leaky_concat_nhwc(const float* a, int Ca, const float* b, int Cb, long long pixels,
+                             float slope, int act_on_a, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Diagnostics.  riders_debug_tc_gemm: D (128,128) = A (128,K) * B (128,K)^T on the tcgen05 path
  * (K = 32 or 64; terms = 1 plain tf32, 3 = hi/lo split) through the same operand staging,
  * descriptors and TMEM read-back as the fused LoFTR layer - a device self-test of that plumbing.
  * ------------------------------------------------------------------------------------------ */
 /* tuning knobs for experiments (not part of the drop-in surface): "gather_smem_kb" = TMA staging budget per CTA */
 int riders_debug_set(const char* key, int value);
+/* phase timestamps (clock64) of the first tile of two CTAs of the next tcgen05 LoFTR launches; NULL disables */
+int riders_debug_loftr_trace(long long* device_buffer_256);
 int riders_debug_tc_gemm(const float* a, const float* b, float* d, int K, int terms, void* stream);
 
 /* the two halves of riders_interp_linear, callable (and timeable) separately: the triangulation is

@@ -48,7 +48,10 @@ SIGNATURES = {
     "riders_interp_workspace_bytes": (sz, [ci, ci, ci, ci]),
     "riders_interp_triangulate": (ci, [vp, vp, vp, ci, ci, vp, vp, vp, vp, vp]),
     "riders_interp_fill": (ci, [ci, ci, ci, ci, cf, vp, vp, vp]),
+    "riders_upsample_nearest_nhwc": (ci, [vp, ci, ci, ci, ci, ci, ci, vp, vp]),
+    "riders_leaky_concat_nhwc": (ci, [vp, ci, vp, ci, C.c_longlong, cf, ci, vp, vp]),
     "riders_debug_set": (ci, [C.c_char_p, ci]),
+    "riders_debug_loftr_trace": (ci, [vp]),
     "riders_debug_tc_gemm": (ci, [vp, vp, vp, ci, ci, vp]),
     "riders_interp_linear": (ci, [vp, vp, vp, ci, ci, ci, ci, cf, vp, vp, vp, vp, vp, vp]),
 }

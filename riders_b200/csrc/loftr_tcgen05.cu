@@ -167,7 +167,12 @@ struct LayerArgs {
     int n_tiles;
     int is_self;                                // src == x
     float attn_eps, ln_eps;
+    long long* trace;                           // optional phase timestamps (riders_debug_loftr_trace), else null
 };
+
+// trace layout per traced CTA (blockIdx.x == 0 or gridDim.x / 2): 128 slots; [0..63] epilogue thread, [64..127] MMA thread
+#define TRACE_E(k) do { if (P.trace && tr_on && lane == 0 && warp == 2 && tile == (int)blockIdx.x) P.trace[tr_base + (k)] = clock64(); } while (0)
+#define TRACE_M(k) do { if (P.trace && tr_on && tile == (int)blockIdx.x) P.trace[tr_base + 64 + (k)] = clock64(); } while (0)
 
 // ------------------------------------------------------------------------------------ the fused layer
 __global__ void __launch_bounds__(THREADS, 1)
@@ -182,6 +187,8 @@ loftr_layer_tc_kernel(const LayerArgs P) {
     const uint32_t a_ready = smem_u32(bars + 2 * NSTAGE), d_ready = smem_u32(bars + 2 * NSTAGE + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool tr_on = blockIdx.x == 0 || blockIdx.x == gridDim.x / 2;
+    const int tr_base = (blockIdx.x == 0 ? 0 : 128);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(bfull + 8 * s, 1); mbar_init(bempty + 8 * s, 1); }
@@ -231,11 +238,16 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                         default: c_end = 40; break;                      // A = relu(h)[:, C:]  : mlp.2
                     }
                     if (c == c_end) continue;                            // empty segment (self layer, seg 1)
+                    TRACE_M(seg * 4 + 0);
                     mbar_wait(a_ready, aph & 1); ++aph;
                     tc_fence_after();
+                    TRACE_M(seg * 4 + 1);
+                    long long wsum = 0;
                     for (; c < c_end; ++c, ++n) {
                         const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1;
+                        const long long tw = P.trace ? clock64() : 0;
                         mbar_wait(bfull + 8 * s, ph);
+                        if (P.trace) wsum += clock64() - tw;
                         tc_fence_after();
                         const int kc = c & 3;
                         uint32_t dcol, acc0;
@@ -257,6 +269,8 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                         umma_commit(bempty + 8 * s);                     // stage reusable once these MMAs retire
                     }
                     umma_commit(d_ready);
+                    TRACE_M(seg * 4 + 2);
+                    if (P.trace && tr_on && tile == (int)blockIdx.x) P.trace[tr_base + 64 + seg * 4 + 3] = wsum;
                 }
             }
         }
@@ -277,8 +291,10 @@ loftr_layer_tc_kernel(const LayerArgs P) {
             const float* sg = P.src + g_row0 * CH;
 
             // ---- E0: A = x ------------------------------------------------------------------
+            TRACE_E(0);
             load_tile_to_A(a_base, xg, valid_rows, ew, lane);
             publish_A(a_ready);
+            TRACE_E(1);
             if (!P.is_self) {
                 mbar_wait(d_ready, dph & 1); ++dph;      // q done: A is free again
                 tc_fence_after();
@@ -289,6 +305,7 @@ loftr_layer_tc_kernel(const LayerArgs P) {
             // ---- E1: linear attention (linear_attention.py:29-43) ---------------------------
             mbar_wait(d_ready, dph & 1); ++dph;          // q, k, v in D0, D1, D2
             tc_fence_after();
+            TRACE_E(2);
             {
                 // staging inside the (now idle) A region, all fp32:
                 //   Kst [128][64] @0, Vst [128][64] @32K (float4 index XOR (row & 15)), KVs [24][16][16] @64K, Ksum [24][16] @88K
@@ -389,10 +406,12 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                 }
             }
             publish_A(a_ready);
+            TRACE_E(3);
 
             // ---- E2: m = LayerNorm1(merge(msg)) -> A ----------------------------------------
             mbar_wait(d_ready, dph & 1); ++dph;
             tc_fence_after();
+            TRACE_E(4);
             {
                 uint32_t v[128];
                 TMEM_LD32(trow + D0 + 0, (v + 0)); TMEM_LD32(trow + D0 + 32, (v + 32));
@@ -419,18 +438,22 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                 }
             }
             publish_A(a_ready);
+            TRACE_E(5);
 
             // ---- E3: A = x again for mlp.0[:, :C] -------------------------------------------
             mbar_wait(d_ready, dph & 1); ++dph;
             tc_fence_after();
+            TRACE_E(6);
             load_tile_to_A(a_base, xg, valid_rows, ew, lane);
             publish_A(a_ready);
+            TRACE_E(7);
 
             // ---- E4 / E5: A = relu(h) halves for mlp.2 --------------------------------------
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
                 mbar_wait(d_ready, dph & 1); ++dph;
                 tc_fence_after();
+                TRACE_E(8 + 2 * half);
 #pragma unroll
                 for (int part = 0; part < 4; ++part) {
                     uint32_t hr[32];
@@ -443,11 +466,13 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                                                  fmaxf(__uint_as_float(hr[4 * j + 2]), 0.f), fmaxf(__uint_as_float(hr[4 * j + 3]), 0.f)));
                 }
                 publish_A(a_ready);
+                TRACE_E(9 + 2 * half);
             }
 
             // ---- E6: out = x + LayerNorm2(mlp(...)) -----------------------------------------
             mbar_wait(d_ready, dph & 1); ++dph;
             tc_fence_after();
+            TRACE_E(12);
             {
                 uint32_t v[128];
                 TMEM_LD32(trow + D0 + 0, (v + 0)); TMEM_LD32(trow + D0 + 32, (v + 32));
@@ -486,6 +511,7 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                 }
                 __syncwarp();                            // staging reads done before the next tile's split stores
             }
+            TRACE_E(13);
             tc_fence_before();
         }
     }
@@ -586,6 +612,7 @@ tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------ host side
+static long long* g_loftr_trace = nullptr;     // device buffer of 256 int64, set by riders_debug_loftr_trace
 bool loftr_tc_built() { return true; }
 
 size_t loftr_tc_workspace_bytes(int N, int tokens, int C) {
@@ -622,6 +649,7 @@ int loftr_tc_run(const float* x, const float* src, const riders_loftr_weights& w
     P.ln1_g = w.ln1_g; P.ln1_b = w.ln1_b; P.ln2_g = w.ln2_g; P.ln2_b = w.ln2_b;
     P.N = N; P.n_tiles = ceil_div(N, tc::PTS); P.is_self = (x == src) ? 1 : 0;
     P.attn_eps = attn_eps; P.ln_eps = ln_eps;
+    P.trace = g_loftr_trace;
     const int grid = P.n_tiles < sm_count() ? P.n_tiles : sm_count();
     count_launches(1);
     tc::loftr_layer_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(P);
@@ -644,4 +672,9 @@ extern "C" int riders_debug_tc_gemm(const float* a, const float* b, float* d, in
     count_launches(1);
     tc::tc_gemm_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a, b, d, K, terms);
     return check_launch("debug_tc_gemm");
+}
+
+extern "C" int riders_debug_loftr_trace(long long* device_buffer_256) {
+    riders::g_loftr_trace = device_buffer_256;
+    return RIDERS_OK;
 }

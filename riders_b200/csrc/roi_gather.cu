@@ -155,15 +155,28 @@ __device__ __forceinline__ float4 max4(float4 a, const float4 b) {
     a.x = fmaxf(a.x, b.x); a.y = fmaxf(a.y, b.y); a.z = fmaxf(a.z, b.z); a.w = fmaxf(a.w, b.w);
     return a;
 }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 
-// maximum of the window [hb.x, hb.y) x [wb.x, wb.y) (pixels, relative to `base`); empty window -> 0
-__device__ __forceinline__ float4 window_max(const float* base, int row_stride, int C, short2 hb, short2 wb) {
-    if (hb.y <= hb.x || wb.y <= wb.x) return make_float4(0.f, 0.f, 0.f, 0.f);
+// Bin tables of one CTA, in BYTES relative to the staged window: x = offset of the first row / column
+// of the bin (-1: empty bin), y = step to its second row / column (0 if the bin has one), z = count.
+// Maximum over a <= 2 x 2 bin without branches: four loads at {0, dw} x {0, dh} (duplicates are harmless).
+__device__ __forceinline__ float4 bin_max_2x2(uint32_t base, int3 hb, int3 wb) {
+    const uint32_t p = base + (uint32_t)hb.x + (uint32_t)wb.x;
+    const float4 v00 = lds128(p), v01 = lds128(p + wb.y), v10 = lds128(p + hb.y), v11 = lds128(p + hb.y + wb.y);
+    float4 r;
+    r.x = fmaxf(fmaxf(v00.x, v01.x), fmaxf(v10.x, v11.x)); r.y = fmaxf(fmaxf(v00.y, v01.y), fmaxf(v10.y, v11.y));
+    r.z = fmaxf(fmaxf(v00.z, v01.z), fmaxf(v10.z, v11.z)); r.w = fmaxf(fmaxf(v00.w, v01.w), fmaxf(v10.w, v11.w));
+    return r;
+}
+// any bin size (RoIs much larger than the pooled patch)
+__device__ __forceinline__ float4 bin_max_any(uint32_t base, int3 hb, int3 wb, int row_bytes, int px_bytes) {
     float4 best = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
-    for (int h = hb.x; h < hb.y; ++h) {
-        const float* prow = base + h * row_stride;
-        for (int w = wb.x; w < wb.y; ++w) best = max4(best, *reinterpret_cast<const float4*>(prow + w * C));
-    }
+    for (int h = 0; h < hb.z; ++h)
+        for (int w = 0; w < wb.z; ++w) best = max4(best, lds128(base + hb.x + h * row_bytes + wb.x + w * px_bytes));
     return best;
 }
 
@@ -171,8 +184,9 @@ __global__ void __launch_bounds__(TMA_THREADS)
 roi_gather_tma_kernel(const __grid_constant__ TmaPack P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ short2 wbin[256];        // per pooled column: [w0, w1) relative to the staged window
-    __shared__ short2 hbin[64];         // per pooled row of this strip
+    __shared__ int3 wbin[256];          // per pooled column of the RoI
+    __shared__ int3 hbin[64];           // per pooled row of this strip
+    __shared__ int s_big;               // some bin of this CTA is larger than 2 x 2
 
     int l = 0;
 #pragma unroll
@@ -197,30 +211,41 @@ roi_gather_tma_kernel(const __grid_constant__ TmaPack P) {
     const int last_w = (int)ceilf(__fmul_rn((float)L.ow, ax.bin)) + ax.start;
     const bool bad = b < 0 || b >= P.B;
     const bool fits = (last_h - win_h <= L.BH) && (last_w - win_w <= L.BW) && !bad;   // CTA-uniform
+    const int px_bytes = L.C * 4, row_bytes = L.BW * px_bytes;
 
-    if (threadIdx.x == 0 && fits) {
-        mbar_init(&bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t bytes = (uint32_t)L.BH * L.BW * L.C * 4u;
-        mbar_expect_tx(&bar, bytes);
-        asm volatile(
-            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-            " [%0], [%1, {%2, %3, %4, %5}], [%6];"
-            ::"r"(smem_u32(tile)), "l"(&P.map[l]), "r"(0), "r"(win_w), "r"(win_h), "r"(b), "r"(smem_u32(&bar))
-            : "memory");
+    if (threadIdx.x == 0) {
+        s_big = 0;
+        if (fits) {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(&bar, (uint32_t)L.BH * (uint32_t)row_bytes);
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+                " [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                ::"r"(smem_u32(tile)), "l"(&P.map[l]), "r"(0), "r"(win_w), "r"(win_h), "r"(b), "r"(smem_u32(&bar))
+                : "memory");
+        }
     }
+    __syncthreads();
     // bin tables (clipped to the map, then made window-relative) while the tile is in flight
+    bool big = false;
     for (int j = threadIdx.x; j < L.ow; j += TMA_THREADS) {
         int w0, w1;
         roi_bin_range(ax, j, L.W, w0, w1);
-        wbin[j] = make_short2((short)(w0 - win_w), (short)(w1 - win_w));
+        const int n = w1 - w0;
+        wbin[j] = make_int3(n > 0 ? (w0 - win_w) * px_bytes : -1, n > 1 ? px_bytes : 0, n);
+        big |= n > 2;
     }
     for (int i = threadIdx.x; i < ni; i += TMA_THREADS) {
         int h0, h1;
         roi_bin_range(ay, i0 + i, L.H, h0, h1);
-        hbin[i] = make_short2((short)(h0 - win_h), (short)(h1 - win_h));
+        const int n = h1 - h0;
+        hbin[i] = make_int3(n > 0 ? (h0 - win_h) * row_bytes : -1, n > 1 ? row_bytes : 0, n);
+        big |= n > 2;
     }
+    if (big) s_big = 1;
     __syncthreads();
+    const bool any_big = s_big != 0;
 
     // thread -> (channel group c4, pixel); pixels advance by PP per pass, no divisions in the loop
     const int CV = 1 << L.cv_shift;
@@ -231,30 +256,54 @@ roi_gather_tma_kernel(const __grid_constant__ TmaPack P) {
     int i = p / L.ow, j = p - i * L.ow;
     const int di = PP / L.ow, dj = PP - di * L.ow;
     float4* out_base = reinterpret_cast<float4*>(L.out + (((size_t)r * L.oh + i0) * L.ow) * L.C) + c4;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    const float* src;
-    int row_stride;
     if (fits) {
         mbar_wait(&bar, 0);
-        src = tile + c4 * 4;
-        row_stride = L.BW * L.C;
+        const uint32_t base = smem_u32(tile) + (uint32_t)c4 * 16u;
+        if (!any_big) {
+            // hot path (RC-Net: RoI extent = pooled size + 1, every bin is 1 or 2 wide): two pixels per pass
+            for (; p < npix; p += 2 * PP) {
+                int i1 = i + di, j1 = j + dj;
+                if (j1 >= L.ow) { j1 -= L.ow; ++i1; }
+                const bool two = p + PP < npix;
+                const int3 hb0 = hbin[i], wb0 = wbin[j];
+                const int3 hb1 = two ? hbin[i1] : hb0, wb1 = two ? wbin[j1] : wb0;
+                const bool e0 = (hb0.x | wb0.x) < 0, e1 = (hb1.x | wb1.x) < 0;
+                float4 v0 = bin_max_2x2(base, e0 ? make_int3(0, 0, 0) : hb0, e0 ? make_int3(0, 0, 0) : wb0);
+                float4 v1 = bin_max_2x2(base, e1 ? make_int3(0, 0, 0) : hb1, e1 ? make_int3(0, 0, 0) : wb1);
+                __stcs(out_base + (size_t)p * CV, e0 ? zero : v0);
+                if (two) __stcs(out_base + (size_t)(p + PP) * CV, e1 ? zero : v1);
+                i = i1 + di; j = j1 + dj;
+                if (j >= L.ow) { j -= L.ow; ++i; }
+            }
+        } else {
+            for (; p < npix; p += PP) {
+                const int3 hb = hbin[i], wb = wbin[j];
+                const bool e = (hb.x | wb.x) < 0;
+                __stcs(out_base + (size_t)p * CV, e ? zero : bin_max_any(base, hb, wb, row_bytes, px_bytes));
+                i += di; j += dj;
+                if (j >= L.ow) { j -= L.ow; ++i; }
+            }
+        }
     } else {
         // RoI larger than the staged box (or bad batch index -> zeros): read the map directly
-        src = L.feat + ((size_t)(bad ? 0 : b) * L.H * L.W + (size_t)win_h * L.W + win_w) * L.C + c4 * 4;
-        row_stride = L.W * L.C;
-    }
-    for (; p < npix; p += 2 * PP) {
-        const short2 hb0 = hbin[i], wb0 = wbin[j];
-        int i1 = i + di, j1 = j + dj;
-        if (j1 >= L.ow) { j1 -= L.ow; ++i1; }
-        const bool two = p + PP < npix;
-        float4 v0 = bad ? make_float4(0.f, 0.f, 0.f, 0.f) : window_max(src, row_stride, L.C, hb0, wb0);
-        float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (two && !bad) v1 = window_max(src, row_stride, L.C, hbin[i1], wbin[j1]);
-        __stcs(out_base + (size_t)p * CV, v0);
-        if (two) __stcs(out_base + (size_t)(p + PP) * CV, v1);
-        i = i1 + di; j = j1 + dj;
-        if (j >= L.ow) { j -= L.ow; ++i; }
+        const int g_row = L.W * L.C;                                   // floats
+        const float* src = L.feat + (size_t)(bad ? 0 : b) * L.H * g_row + c4 * 4;
+        for (; p < npix; p += PP) {
+            const int3 hb = hbin[i], wb = wbin[j];
+            float4 best = zero;
+            if (!bad && (hb.x | wb.x) >= 0) {
+                best = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+                const int h0 = hb.x / row_bytes + win_h, w0 = wb.x / px_bytes + win_w;
+                for (int h = h0; h < h0 + hb.z; ++h)
+                    for (int w = w0; w < w0 + wb.z; ++w)
+                        best = max4(best, __ldg(reinterpret_cast<const float4*>(src + (size_t)h * g_row + (size_t)w * L.C)));
+            }
+            __stcs(out_base + (size_t)p * CV, best);
+            i += di; j += dj;
+            if (j >= L.ow) { j -= L.ow; ++i; }
+        }
     }
 }
 

@@ -176,6 +176,36 @@ def roi_pool(input, boxes, output_size, spatial_scale=1.0):
     return roi_gather([input], boxes, [spatial_scale], [tuple(output_size)])[0]
 
 
+def upsample_nearest(x, size):
+    """F.interpolate(x, size=size) (nearest) for channels-last float32 CUDA maps, bit-exact."""
+    _need_cuda(x)
+    if not (_is_channels_last(x) and x.dtype == torch.float32 and x.shape[1] % 4 == 0):
+        raise _lib.RidersError("upsample_nearest needs a channels_last float32 map with C % 4 == 0")
+    N, Cc, h, w = x.shape
+    H, W = int(size[0]), int(size[1])
+    out = torch.empty((N, Cc, H, W), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+    with _span("upsample_nearest"):
+        rc = _lib.lib().riders_upsample_nearest_nhwc(_ptr(x), N, Cc, h, w, H, W, _ptr(out), _stream())
+    _lib.check(rc, "riders_upsample_nearest_nhwc")
+    return out
+
+
+def leaky_concat(a, b, slope=0.2, act_on_a=True):
+    """cat([leaky_relu(a), b], dim=1) for channels-last float32 CUDA maps in one pass (bit-exact)."""
+    _need_cuda(a, b)
+    for t in (a, b):
+        if not (_is_channels_last(t) and t.dtype == torch.float32 and t.shape[1] % 4 == 0):
+            raise _lib.RidersError("leaky_concat needs channels_last float32 maps with C % 4 == 0")
+    N, Ca, H, W = a.shape
+    Cb = b.shape[1]
+    out = torch.empty((N, Ca + Cb, H, W), device=a.device, dtype=torch.float32, memory_format=torch.channels_last)
+    with _span("leaky_concat"):
+        rc = _lib.lib().riders_leaky_concat_nhwc(_ptr(a), Ca, _ptr(b), Cb, N * H * W, float(slope),
+                                                 1 if act_on_a else 0, _ptr(out), _stream())
+    _lib.check(rc, "riders_leaky_concat_nhwc")
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # A2-A4 LoFTR
 # --------------------------------------------------------------------------------------------

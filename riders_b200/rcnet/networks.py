@@ -70,6 +70,16 @@ class Conv2d(torch.nn.Module):
             y = self.batch_norm(y)
         return y if self._act is None else self._act(y)
 
+    def fold_batch_norm_(self):
+        """Inference only: fold the (eval-mode) BatchNorm affine into the convolution's weights and bias
+        (torch.nn.utils.fusion).  Same function up to float32 rounding; removes one full pass over the
+        activations per convolution.  The state_dict no longer matches the reference's after this."""
+        if self.use_batch_norm:
+            self.conv = torch.nn.utils.fusion.fuse_conv_bn_eval(self.conv.eval(), self.batch_norm.eval())
+            self.use_batch_norm = False
+            del self.batch_norm
+        return self
+
 
 class UpConv2d(torch.nn.Module):
     """nearest resize to ``shape`` then Conv2d; utils/net_utils.py:149-190."""
@@ -79,6 +89,9 @@ class UpConv2d(torch.nn.Module):
         self.conv = Conv2d(cin, cout, 3, 1, init, act, use_batch_norm)
 
     def forward(self, x, shape):
+        if x.is_cuda and x.dtype == torch.float32 and x.shape[1] % 4 == 0 and ops._is_channels_last(x) \
+                and not torch.is_grad_enabled():
+            return self.conv(ops.upsample_nearest(x, shape))      # same values, streaming NHWC kernel
         return self.conv(F.interpolate(x, size=shape))
 
 
@@ -122,6 +135,7 @@ class DecoderBlock(torch.nn.Module):
         if deconv_type != 'up':
             raise ValueError("only deconv_type='up' is used by RC-Net (rcnet_model.py:94)")
         self.skip_channels = cskip
+        self._leaky = act is not None and 'leaky_relu' in act
         self.deconv = UpConv2d(cin, cout, init, act, use_batch_norm)
         self.conv = Conv2d(cskip + cout, cout, 3, 1, init, act, use_batch_norm)
 
@@ -130,6 +144,13 @@ class DecoderBlock(torch.nn.Module):
             shape = skip.shape[2:4]
         elif shape is None:
             shape = (2 * x.shape[2], 2 * x.shape[3])
+        up = self.deconv.conv
+        if (self.skip_channels > 0 and self._leaky and not up.use_batch_norm and not torch.is_grad_enabled()
+                and x.is_cuda and x.dtype == torch.float32 and ops._is_channels_last(x) and ops._is_channels_last(skip)
+                and x.shape[1] % 4 == 0 and up.conv.out_channels % 4 == 0 and skip.shape[1] % 4 == 0):
+            # inference fast path (BatchNorm folded): resize -> conv(+bias) -> [LeakyReLU | skip] in one pass -> conv
+            y = up.conv(ops.upsample_nearest(x, shape))
+            return self.conv(ops.leaky_concat(y, skip, _LEAK))
         y = self.deconv(x, shape=shape)
         if self.skip_channels > 0:
             y = torch.cat([y, skip], dim=1)

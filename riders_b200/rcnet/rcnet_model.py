@@ -85,6 +85,16 @@ class RCNetModel(object):
         self.decoder.to(memory_format=torch.channels_last)
         return self
 
+    def optimize_for_inference(self):
+        """B200 extension, inference only: channels_last + BatchNorm folded into the convolutions.
+        Results stay within the 1e-4 tolerance on confidences (float32 re-association only)."""
+        self.eval()
+        for net in (self.encoder, self.decoder):
+            for mod in net.modules():
+                if isinstance(mod, networks.Conv2d):
+                    mod.fold_batch_norm_()
+        return self.channels_last()
+
     def save_model(self, checkpoint_path, step, optimizer):
         torch.save({
             'train_step': step,

@@ -459,3 +459,47 @@ def test_optimizer_class_is_a_drop_in():
     assert o.output.max() <= np.float32(10.0) and o.output.min() >= np.float32(1 / 255.0)
     o2 = Optimizer(estimate=pred, target=target, valid=mask, depth_type="inv")
     assert np.array_equal(o2.align(clamp_min=0.1, clamp_max=255.0), o.output) and o2.scale == o.scale
+
+
+# ------------------------------------------------------------------------------------ decoder glue
+@pytest.mark.parametrize("shape,size", [((3, 32, 120, 50), (240, 100)), ((2, 256, 7, 3), (15, 6)), ((2, 128, 30, 12), (60, 25)),
+                                        ((1, 8, 13, 5), (5, 13)), ((2, 4, 1, 1), (7, 9))])
+def test_upsample_nearest_is_bit_exact_with_torch(shape, size):
+    x = torch.randn(shape, device=DEV).contiguous(memory_format=torch.channels_last)
+    got = ops.upsample_nearest(x, size)
+    ref = torch.nn.functional.interpolate(x, size=size)
+    assert got.shape == ref.shape and got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(got, ref)
+
+
+def test_optimize_for_inference_keeps_the_tolerance():
+    """BatchNorm folding + channels_last + the upsample kernel: confidences stay within 1e-4 of the oracle."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    patch, K = (64, 32), 10
+    cpu = _rand_model("cpu", patch, [8, 16, 16, 16, 16], [32, 16, 16, 8, 8], seed=3)
+    with torch.no_grad():                                  # non-trivial running statistics so that folding matters
+        for net in (cpu.encoder, cpu.decoder):
+            for m in net.modules():
+                if isinstance(m, torch.nn.BatchNorm2d):
+                    m.running_mean.uniform_(-0.3, 0.3)
+                    m.running_var.uniform_(0.5, 1.5)
+                    m.weight.uniform_(0.7, 1.3)
+                    m.bias.uniform_(-0.2, 0.2)
+    gpu = _to_cuda(cpu).optimize_for_inference()
+    assert not any(isinstance(m, torch.nn.BatchNorm2d) for m in gpu.decoder.modules())
+    fr = synth.chain_frame(9, K, 96, 128, patch)
+    padded = torch.nn.functional.pad(torch.from_numpy(fr["image"])[None], (16, 16, 32, 32), mode="replicate")
+    with torch.no_grad():
+        ref = rcnet_ref.model_forward_ref(cpu, padded, torch.from_numpy(fr["points"]), [torch.from_numpy(fr["boxes"])])
+        got = gpu.forward(padded.to(DEV), cu(fr["points"]), [cu(fr["boxes"])], return_logits=True)
+    np.testing.assert_allclose(torch.sigmoid(got).cpu().numpy(), torch.sigmoid(ref).numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_leaky_concat_is_bit_exact_with_torch():
+    a = torch.randn((5, 32, 30, 12), device=DEV).contiguous(memory_format=torch.channels_last)
+    b = torch.randn((5, 64, 30, 12), device=DEV).contiguous(memory_format=torch.channels_last)
+    got = ops.leaky_concat(a, b, 0.2)
+    ref = torch.cat([torch.nn.functional.leaky_relu(a, 0.2), b], dim=1)
+    assert got.is_contiguous(memory_format=torch.channels_last) and torch.equal(got, ref)
+    assert torch.equal(ops.leaky_concat(a, b, 0.2, act_on_a=False), torch.cat([a, b], dim=1))
