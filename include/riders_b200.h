@@ -210,6 +210,13 @@ int riders_upsample_nearest_nhwc(const float* x, int N, int C, int h, int w, int
  * (utils/net_utils.py:474-569).  Ca, Cb multiples of 4; Cb may be 0 (activation only, out of place). */
 int riders_leaky_concat_nhwc(const float* a, int Ca, const float* b, int Cb, long long pixels,
                              float slope, int act_on_a, float* out, void* stream);
+/* the same with the (BatchNorm-folded) convolution bias added first: out[p][0:Ca] = leaky(a[p][:] + bias[:]) */
+int riders_bias_leaky_concat_nhwc(const float* a, const float* bias, int Ca, const float* b, int Cb,
+                                  long long pixels, float slope, float* out, void* stream);
+/* out = act(x + bias[c]) over `pixels` channels-last pixels of C channels (in place when out == x);
+ * slope 0.2 = LeakyReLU of utils/net_utils.py:15, 0 = ReLU, 1 = identity; bias may be NULL.          */
+int riders_bias_act_nhwc(const float* x, const float* bias, int C, long long pixels, float slope,
+                         float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Diagnostics.  riders_debug_tc_gemm: D (128,128) = A (128,K) * B (128,K)^T on the tcgen05 path

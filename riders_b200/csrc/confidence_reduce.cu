@@ -28,24 +28,39 @@ template <bool LOGITS>
 __device__ __forceinline__ float conf_value(float v, float thr) {
     // torch.sigmoid (rcnet_model.py:123): 1 / (1 + exp(-v)) with the SFU exp2 / reciprocal (relative
     // error ~2e-7, far inside the 1e-4 tolerance on confidences); strict < (rcnet_main.py:462)
-    if (LOGITS) v = __frcp_rn(1.0f + __expf(-v));
+    if (LOGITS) v = __fdividef(1.0f, 1.0f + __expf(-v));
     return (v < thr) ? 0.0f : v;
 }
 
-// the 4 vertically stacked confidences of candidate q under this thread (0 where the crop does not cover)
-template <bool LOGITS>
-__device__ __forceinline__ void load_candidate(const float* __restrict__ conf, const Cand& q, bool on, int first_point,
-                                               size_t crop, int col, int row, int ph, int pw, float thr,
-                                               float (&v)[ROWS_PER_THREAD]) {
+// predicated streaming load (no branch around it, so the 8 loads of an iteration issue back to back)
+__device__ __forceinline__ float ld_stream_if(const float* p, bool on) {
+    float v;
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.b32 q, %2, 0;\n"
+        "mov.f32 %0, 0f00000000;\n"
+        "@q ld.global.nc.L1::no_allocate.f32 %0, [%1];\n"
+        "}\n" : "=f"(v) : "l"(p), "r"((int)on));
+    return v;
+}
+
+// raw values of the 4 vertically stacked crop pixels of candidate q under this thread + their coverage mask
+__device__ __forceinline__ unsigned load_candidate(const float* __restrict__ conf, const Cand& q, bool on, int first_point,
+                                                   size_t crop, int col, int row, int ph, int pw,
+                                                   float (&v)[ROWS_PER_THREAD]) {
     const int j = col - q.c0;
     const int i0 = row - q.r0;
     const bool in_col = on && (unsigned)j < (unsigned)pw;
     const float* src = conf + (size_t)(first_point + q.k) * crop + (ptrdiff_t)i0 * pw + j;
+    unsigned mask = 0;
 #pragma unroll
     for (int m = 0; m < ROWS_PER_THREAD; ++m) {
         const bool in = in_col && (unsigned)(i0 + m) < (unsigned)ph;
-        v[m] = in ? conf_value<LOGITS>(ld_stream(src + m * pw), thr) : 0.0f;
+        v[m] = ld_stream_if(src + m * pw, in);
+        mask |= in ? (1u << m) : 0u;
     }
+    return mask;
 }
 
 template <bool LOGITS>
@@ -107,8 +122,14 @@ confidence_reduce_kernel(const float* __restrict__ conf, const float* __restrict
             const Cand q0 = cand[i];                   // smem broadcast
             const Cand q1 = cand[has1 ? i + 1 : i];
             float v0[ROWS_PER_THREAD], v1[ROWS_PER_THREAD];
-            load_candidate<LOGITS>(conf, q0, true, first_point, crop, col, row, ph, pw, thr, v0);
-            load_candidate<LOGITS>(conf, q1, has1, first_point, crop, col, row, ph, pw, thr, v1);
+            const unsigned m0 = load_candidate(conf, q0, true, first_point, crop, col, row, ph, pw, v0);
+            const unsigned m1 = load_candidate(conf, q1, has1, first_point, crop, col, row, ph, pw, v1);
+#pragma unroll
+            for (int m = 0; m < ROWS_PER_THREAD; ++m) {
+                const float c0 = conf_value<LOGITS>(v0[m], thr), c1 = conf_value<LOGITS>(v1[m], thr);   // branch-free
+                v0[m] = (m0 >> m) & 1u ? c0 : 0.0f;
+                v1[m] = (m1 >> m) & 1u ? c1 : 0.0f;
+            }
 #pragma unroll
             for (int m = 0; m < ROWS_PER_THREAD; ++m) {
                 if (v0[m] > best[m]) { best[m] = v0[m]; arg[m] = q0.k; }   // first max wins

@@ -34,8 +34,9 @@ constexpr int NSTAGE = 3;
 constexpr int NCHUNK = 40;
 constexpr int LAYER_PACK_BYTES = NCHUNK * CHUNK;               // 1.25 MB per layer
 constexpr int MAX_LAYERS = 16;
-constexpr int THREADS = 192;
-constexpr int SMEM_BYTES = 1024 + A_BYTES + NSTAGE * CHUNK + 128;
+constexpr int THREADS = 320;                                   // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int TAIL_BYTES = 128 + 2048;                         // barriers + TMEM slot | LayerNorm partials (4 x 128 floats)
+constexpr int SMEM_BYTES = A_BYTES + NSTAGE * CHUNK + TAIL_BYTES;      // 231552 of the 232448 available; base must be 1024-aligned
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t D0 = 0, D1 = 128, D2 = 256, D3 = 256;
 // instruction descriptor: D fp32, A/B tf32, both K-major, N = 128, M = 128
@@ -115,7 +116,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
 
 // ------------------------------------------------------------------------------------ operand staging
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
@@ -134,23 +135,40 @@ __device__ __forceinline__ void split_store4(uint8_t* a_base, int row, int col, 
     *reinterpret_cast<float4*>(a_base + 4 * SLAB + off) = lo;
 }
 
-// coalesced: epilogue warp `ew` loads rows ew*32.. of a (rows x 128) fp32 tile and splits them into A
+// coalesced: epilogue warp `ew` (0..7) loads rows ew*16.. of a (rows x 128) fp32 tile and splits them into A
 __device__ __forceinline__ void load_tile_to_A(uint8_t* a_base, const float* __restrict__ g, int valid_rows, int ew, int lane) {
 #pragma unroll 1
-    for (int r0 = 0; r0 < 32; r0 += 8) {
+    for (int r0 = 0; r0 < 16; r0 += 8) {
         float4 v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int row = ew * 32 + r0 + i;
+            const int row = ew * 16 + r0 + i;
             v[i] = (row < valid_rows) ? __ldg(reinterpret_cast<const float4*>(g + (size_t)row * CH) + lane)
                                       : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) split_store4(a_base, ew * 32 + r0 + i, lane * 4, v[i]);
+        for (int i = 0; i < 8; ++i) split_store4(a_base, ew * 16 + r0 + i, lane * 4, v[i]);
     }
 }
 
-__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x + 1.0f : expf(x); }   // elu(x) + 1
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x + 1.0f : __expf(x); }   // elu(x) + 1 (SFU exp2, ~2 ulp)
+
+// LayerNorm statistics of a 128-wide row held as 64 + 64 values by the two threads (column halves) of the row:
+// partial sums go through shared memory and are added in a fixed order, so both threads get identical bits.
+__device__ __forceinline__ void row_stats(const uint32_t (&v)[64], int row, int half, float* red, float eps, float& mean, float& rstd) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) s += __uint_as_float(v[i]);
+    red[half * 128 + row] = s;
+    epi_bar();
+    mean = (red[row] + red[128 + row]) * (1.0f / CH);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) { const float d = __uint_as_float(v[i]) - mean; q = fmaf(d, d, q); }
+    red[256 + half * 128 + row] = q;
+    epi_bar();
+    rstd = 1.0f / sqrtf((red[256 + row] + red[384 + row]) * (1.0f / CH) + eps);
+}
 
 // signal "A operand (and my TMEM reads) done" to the MMA warp
 __device__ __forceinline__ void publish_A(uint32_t a_ready) {
@@ -171,18 +189,20 @@ struct LayerArgs {
 };
 
 // trace layout per traced CTA (blockIdx.x == 0 or gridDim.x / 2): 128 slots; [0..63] epilogue thread, [64..127] MMA thread
-#define TRACE_E(k) do { if (P.trace && tr_on && lane == 0 && warp == 2 && tile == (int)blockIdx.x) P.trace[tr_base + (k)] = clock64(); } while (0)
+#define TRACE_E(k) do { if (P.trace && tr_on && lane == 0 && warp == 4 && tile == (int)blockIdx.x) P.trace[tr_base + (k)] = clock64(); } while (0)
 #define TRACE_M(k) do { if (P.trace && tr_on && tile == (int)blockIdx.x) P.trace[tr_base + 64 + (k)] = clock64(); } while (0)
 
 // ------------------------------------------------------------------------------------ the fused layer
 __global__ void __launch_bounds__(THREADS, 1)
 loftr_layer_tc_kernel(const LayerArgs P) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;                                 // SWIZZLE_128B slabs need a 1024-byte aligned base
+    if (smem_u32(smem) & 1023u) __trap();
     uint8_t* a_base = smem;                                   // A hi[4] | lo[4]
     uint8_t* b_base = smem + A_BYTES;                         // NSTAGE x (hi | lo)
     uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + NSTAGE * CHUNK);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);
     const uint32_t bfull = smem_u32(bars), bempty = smem_u32(bars + NSTAGE);
     const uint32_t a_ready = smem_u32(bars + 2 * NSTAGE), d_ready = smem_u32(bars + 2 * NSTAGE + 1);
 
@@ -192,7 +212,7 @@ loftr_layer_tc_kernel(const LayerArgs P) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(bfull + 8 * s, 1); mbar_init(bempty + 8 * s, 1); }
-        mbar_init(a_ready, 128);
+        mbar_init(a_ready, 256);
         mbar_init(d_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -275,10 +295,12 @@ loftr_layer_tc_kernel(const LayerArgs P) {
             }
         }
     } else {
-        // ===================== epilogue warps: thread = token row =====================
+        // ===================== epilogue warps: (thread pair) = token row, each thread 64 of its 128 columns =====
+        const int ew = warp - 2;                         // 0..7
         const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
-        const int ew = quad;                             // row block of this warp
+        const int half = ew >> 2;                        // column half: warps 2..5 -> [0,64), warps 6..9 -> [64,128)
         const int row = quad * 32 + lane;
+        const int col0 = half * 64;
         const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
         uint32_t dph = 0;
         float* stage_f = reinterpret_cast<float*>(a_base);
@@ -303,9 +325,12 @@ loftr_layer_tc_kernel(const LayerArgs P) {
             }
 
             // ---- E1: linear attention (linear_attention.py:29-43) ---------------------------
+            // The reference divides V by S and multiplies the message by S (fp16 range safety,
+            // linear_attention.py:39-43); in fp32 the two cancel to rounding, so neither is applied.
             mbar_wait(d_ready, dph & 1); ++dph;          // q, k, v in D0, D1, D2
             tc_fence_after();
             TRACE_E(2);
+            float msg[2][2][16];                         // [head half hh][head e][v]: heads hh*4 + half*2 + e
             {
                 // staging inside the (now idle) A region, all fp32:
                 //   Kst [128][64] @0, Vst [128][64] @32K (float4 index XOR (row & 15)), KVs [24][16][16] @64K, Ksum [24][16] @88K
@@ -314,47 +339,56 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                 float* KVs = stage_f + 16384;
                 float* Ksum = stage_f + 16384 + 6144;
                 const int p_row = min(row / TOK, PTS - 1);
-#pragma unroll 1
-                for (int hh = 0; hh < 2; ++hh) {
-                    // (1) K' = elu(k)+1 and V/S of heads 4hh..4hh+3 -> smem
 #pragma unroll
-                    for (int part = 0; part < 2; ++part) {
+                for (int hh = 0; hh < 2; ++hh) {
+                    // (1) K' = elu(k)+1 and V of heads 4hh..4hh+3 -> smem (this thread: 32 of the 64 columns)
+                    {
                         uint32_t kr[32], vr[32];
-                        TMEM_LD32(trow + D1 + hh * 64 + part * 32, kr);
-                        TMEM_LD32(trow + D2 + hh * 64 + part * 32, vr);
+                        TMEM_LD32(trow + D1 + hh * 64 + half * 32, kr);
+                        TMEM_LD32(trow + D2 + hh * 64 + half * 32, vr);
                         tmem_wait_ld();
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             float4 kk, vv;
                             kk.x = elu1(__uint_as_float(kr[4 * j + 0])); kk.y = elu1(__uint_as_float(kr[4 * j + 1]));
                             kk.z = elu1(__uint_as_float(kr[4 * j + 2])); kk.w = elu1(__uint_as_float(kr[4 * j + 3]));
-                            vv.x = __fdiv_rn(__uint_as_float(vr[4 * j + 0]), (float)TOK); vv.y = __fdiv_rn(__uint_as_float(vr[4 * j + 1]), (float)TOK);
-                            vv.z = __fdiv_rn(__uint_as_float(vr[4 * j + 2]), (float)TOK); vv.w = __fdiv_rn(__uint_as_float(vr[4 * j + 3]), (float)TOK);
-                            const int f4 = (part * 8 + j) ^ (row & 15);
+                            vv.x = __uint_as_float(vr[4 * j + 0]); vv.y = __uint_as_float(vr[4 * j + 1]);
+                            vv.z = __uint_as_float(vr[4 * j + 2]); vv.w = __uint_as_float(vr[4 * j + 3]);
+                            const int f4 = (half * 8 + j) ^ (row & 15);
                             reinterpret_cast<float4*>(Kst + row * 64)[f4] = kk;
                             reinterpret_cast<float4*>(Vst + row * 64)[f4] = vv;
                         }
                     }
                     epi_bar();
-                    // (2) KV[p][h] = K'^T V, Ksum[p][h] = sum_s K'   (24 (point, head) pairs, 6 per warp)
+                    // (2) KV[p][h] = K'^T V, Ksum[p][h] = sum_s K'   (24 (point, head) pairs, 3 per warp;
+                    //     lane -> (d, 8 consecutive v); 7 tokens per batch so 21 loads are in flight)
 #pragma unroll 1
-                    for (int q6 = 0; q6 < 6; ++q6) {
-                        const int pair = ew * 6 + q6, p = pair >> 2, hl = pair & 3;
+                    for (int q3 = 0; q3 < 3; ++q3) {
+                        const int pair = ew * 3 + q3, p = pair >> 2, hl = pair & 3;
                         const int d = lane >> 1, v0 = (lane & 1) * 8;
                         float acc[8], ks = 0.f;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
                         if (p < pts) {
-                            for (int s = 0; s < TOK; ++s) {
-                                const int r = p * TOK + s, sw = r & 15;
-                                const float kk = Kst[r * 64 + (((hl * 4 + (d >> 2)) ^ sw) << 2) + (d & 3)];
-                                const float4 va = reinterpret_cast<const float4*>(Vst + r * 64)[(hl * 4 + (v0 >> 2)) ^ sw];
-                                const float4 vb = reinterpret_cast<const float4*>(Vst + r * 64)[(hl * 4 + (v0 >> 2) + 1) ^ sw];
-                                ks += kk;
-                                acc[0] = fmaf(kk, va.x, acc[0]); acc[1] = fmaf(kk, va.y, acc[1]);
-                                acc[2] = fmaf(kk, va.z, acc[2]); acc[3] = fmaf(kk, va.w, acc[3]);
-                                acc[4] = fmaf(kk, vb.x, acc[4]); acc[5] = fmaf(kk, vb.y, acc[5]);
-                                acc[6] = fmaf(kk, vb.z, acc[6]); acc[7] = fmaf(kk, vb.w, acc[7]);
+#pragma unroll 1
+                            for (int s0 = 0; s0 < TOK; s0 += 7) {
+                                float kk[7];
+                                float4 va[7], vb[7];
+#pragma unroll
+                                for (int u = 0; u < 7; ++u) {
+                                    const int r = p * TOK + s0 + u, sw = r & 15;
+                                    kk[u] = Kst[r * 64 + (((hl * 4 + (d >> 2)) ^ sw) << 2) + (d & 3)];
+                                    va[u] = reinterpret_cast<const float4*>(Vst + r * 64)[(hl * 4 + (v0 >> 2)) ^ sw];
+                                    vb[u] = reinterpret_cast<const float4*>(Vst + r * 64)[(hl * 4 + (v0 >> 2) + 1) ^ sw];
+                                }
+#pragma unroll
+                                for (int u = 0; u < 7; ++u) {
+                                    ks += kk[u];
+                                    acc[0] = fmaf(kk[u], va[u].x, acc[0]); acc[1] = fmaf(kk[u], va[u].y, acc[1]);
+                                    acc[2] = fmaf(kk[u], va[u].z, acc[2]); acc[3] = fmaf(kk[u], va[u].w, acc[3]);
+                                    acc[4] = fmaf(kk[u], vb[u].x, acc[4]); acc[5] = fmaf(kk[u], vb[u].y, acc[5]);
+                                    acc[6] = fmaf(kk[u], vb[u].z, acc[6]); acc[7] = fmaf(kk[u], vb[u].w, acc[7]);
+                                }
                             }
                         }
                         float4* dst = reinterpret_cast<float4*>(KVs + pair * 256 + d * 16 + v0);
@@ -363,47 +397,44 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                         if ((lane & 1) == 0) Ksum[pair * 16 + d] = ks;
                     }
                     epi_bar();
-                    // (3) message rows of these 4 heads -> TMEM scratch (k's columns, already consumed)
-#pragma unroll 1
-                    for (int hl = 0; hl < 4; ++hl) {
+                    // (3) message rows of heads hh*4 + half*2 + {0,1} -> registers
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int hl = half * 2 + e;
                         uint32_t qr[16];
                         TMEM_LD16(trow + D0 + (hh * 4 + hl) * 16, qr);
                         tmem_wait_ld();
                         const int pair = p_row * 4 + hl;
-                        float Q[16], den = 0.f, num[16];
+                        float Q[16], den = 0.f;
 #pragma unroll
-                        for (int dd = 0; dd < 16; ++dd) { Q[dd] = elu1(__uint_as_float(qr[dd])); den = fmaf(Q[dd], Ksum[pair * 16 + dd], den); num[dd] = 0.f; }
+                        for (int dd = 0; dd < 16; ++dd) { Q[dd] = elu1(__uint_as_float(qr[dd])); den = fmaf(Q[dd], Ksum[pair * 16 + dd], den); }
+#pragma unroll
+                        for (int v = 0; v < 16; ++v) msg[hh][e][v] = 0.f;
 #pragma unroll
                         for (int dd = 0; dd < 16; ++dd) {
                             const float4* kv = reinterpret_cast<const float4*>(KVs + pair * 256 + dd * 16);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const float4 t = kv[j];
-                                num[4 * j + 0] = fmaf(Q[dd], t.x, num[4 * j + 0]); num[4 * j + 1] = fmaf(Q[dd], t.y, num[4 * j + 1]);
-                                num[4 * j + 2] = fmaf(Q[dd], t.z, num[4 * j + 2]); num[4 * j + 3] = fmaf(Q[dd], t.w, num[4 * j + 3]);
+                                msg[hh][e][4 * j + 0] = fmaf(Q[dd], t.x, msg[hh][e][4 * j + 0]); msg[hh][e][4 * j + 1] = fmaf(Q[dd], t.y, msg[hh][e][4 * j + 1]);
+                                msg[hh][e][4 * j + 2] = fmaf(Q[dd], t.z, msg[hh][e][4 * j + 2]); msg[hh][e][4 * j + 3] = fmaf(Q[dd], t.w, msg[hh][e][4 * j + 3]);
                             }
                         }
-                        const float z = __fdiv_rn(1.0f, den + P.attn_eps);
-                        uint32_t mr[16];
+                        const float z = __fdividef(1.0f, den + P.attn_eps);
 #pragma unroll
-                        for (int dd = 0; dd < 16; ++dd) mr[dd] = __float_as_uint(num[dd] * z * (float)TOK);
-                        TMEM_ST16(trow + D1 + (hh * 4 + hl) * 16, mr);
+                        for (int v = 0; v < 16; ++v) msg[hh][e][v] *= z;
                     }
-                    tmem_wait_st();
                     // the barrier after the next half's stage (1) orders (3) before the next (2)
                 }
                 epi_bar();                               // staging dead: A may be overwritten
 #pragma unroll
-                for (int part = 0; part < 4; ++part) {
-                    uint32_t mr[32];
-                    TMEM_LD32(trow + D1 + part * 32, mr);
-                    tmem_wait_ld();
+                for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        split_store4(a_base, row, part * 32 + j * 4,
-                                     make_float4(__uint_as_float(mr[4 * j]), __uint_as_float(mr[4 * j + 1]),
-                                                 __uint_as_float(mr[4 * j + 2]), __uint_as_float(mr[4 * j + 3])));
-                }
+                    for (int e = 0; e < 2; ++e)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            split_store4(a_base, row, (hh * 4 + half * 2 + e) * 16 + j * 4,
+                                         make_float4(msg[hh][e][4 * j], msg[hh][e][4 * j + 1], msg[hh][e][4 * j + 2], msg[hh][e][4 * j + 3]));
             }
             publish_A(a_ready);
             TRACE_E(3);
@@ -413,28 +444,21 @@ loftr_layer_tc_kernel(const LayerArgs P) {
             tc_fence_after();
             TRACE_E(4);
             {
-                uint32_t v[128];
-                TMEM_LD32(trow + D0 + 0, (v + 0)); TMEM_LD32(trow + D0 + 32, (v + 32));
-                TMEM_LD32(trow + D0 + 64, (v + 64)); TMEM_LD32(trow + D0 + 96, (v + 96));
+                uint32_t v[64];
+                TMEM_LD32(trow + D0 + col0, (v + 0)); TMEM_LD32(trow + D0 + col0 + 32, (v + 32));
                 tmem_wait_ld();
-                float mean = 0.f;
+                float mean, rstd;
+                row_stats(v, row, half, red, P.ln_eps, mean, rstd);
 #pragma unroll
-                for (int i = 0; i < 128; ++i) mean += __uint_as_float(v[i]);
-                mean *= (1.0f / CH);
-                float var = 0.f;
-#pragma unroll
-                for (int i = 0; i < 128; ++i) { const float dlt = __uint_as_float(v[i]) - mean; var = fmaf(dlt, dlt, var); }
-                const float rstd = 1.0f / sqrtf(var * (1.0f / CH) + P.ln_eps);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float4 g = __ldg(reinterpret_cast<const float4*>(P.ln1_g) + j);
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(P.ln1_b) + j);
+                for (int j = 0; j < 16; ++j) {
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(P.ln1_g + col0) + j);
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(P.ln1_b + col0) + j);
                     float4 y;
                     y.x = (__uint_as_float(v[4 * j + 0]) - mean) * rstd * g.x + b.x;
                     y.y = (__uint_as_float(v[4 * j + 1]) - mean) * rstd * g.y + b.y;
                     y.z = (__uint_as_float(v[4 * j + 2]) - mean) * rstd * g.z + b.z;
                     y.w = (__uint_as_float(v[4 * j + 3]) - mean) * rstd * g.w + b.w;
-                    split_store4(a_base, row, j * 4, y);
+                    split_store4(a_base, row, col0 + j * 4, y);
                 }
             }
             publish_A(a_ready);
@@ -450,23 +474,23 @@ loftr_layer_tc_kernel(const LayerArgs P) {
 
             // ---- E4 / E5: A = relu(h) halves for mlp.2 --------------------------------------
 #pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
+            for (int hf = 0; hf < 2; ++hf) {
                 mbar_wait(d_ready, dph & 1); ++dph;
                 tc_fence_after();
-                TRACE_E(8 + 2 * half);
+                TRACE_E(8 + 2 * hf);
 #pragma unroll
-                for (int part = 0; part < 4; ++part) {
+                for (int part = 0; part < 2; ++part) {
                     uint32_t hr[32];
-                    TMEM_LD32(trow + D3 + half * 128 + part * 32, hr);
+                    TMEM_LD32(trow + D3 + hf * 128 + col0 + part * 32, hr);
                     tmem_wait_ld();
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        split_store4(a_base, row, part * 32 + j * 4,
+                        split_store4(a_base, row, col0 + part * 32 + j * 4,
                                      make_float4(fmaxf(__uint_as_float(hr[4 * j]), 0.f), fmaxf(__uint_as_float(hr[4 * j + 1]), 0.f),
                                                  fmaxf(__uint_as_float(hr[4 * j + 2]), 0.f), fmaxf(__uint_as_float(hr[4 * j + 3]), 0.f)));
                 }
                 publish_A(a_ready);
-                TRACE_E(9 + 2 * half);
+                TRACE_E(9 + 2 * hf);
             }
 
             // ---- E6: out = x + LayerNorm2(mlp(...)) -----------------------------------------
@@ -474,42 +498,35 @@ loftr_layer_tc_kernel(const LayerArgs P) {
             tc_fence_after();
             TRACE_E(12);
             {
-                uint32_t v[128];
-                TMEM_LD32(trow + D0 + 0, (v + 0)); TMEM_LD32(trow + D0 + 32, (v + 32));
-                TMEM_LD32(trow + D0 + 64, (v + 64)); TMEM_LD32(trow + D0 + 96, (v + 96));
+                uint32_t v[64];
+                TMEM_LD32(trow + D0 + col0, (v + 0)); TMEM_LD32(trow + D0 + col0 + 32, (v + 32));
                 tmem_wait_ld();
-                float mean = 0.f;
-#pragma unroll
-                for (int i = 0; i < 128; ++i) mean += __uint_as_float(v[i]);
-                mean *= (1.0f / CH);
-                float var = 0.f;
-#pragma unroll
-                for (int i = 0; i < 128; ++i) { const float dlt = __uint_as_float(v[i]) - mean; var = fmaf(dlt, dlt, var); }
-                const float rstd = 1.0f / sqrtf(var * (1.0f / CH) + P.ln_eps);
+                float mean, rstd;
+                row_stats(v, row, half, red, P.ln_eps, mean, rstd);
                 // stage the normalised row (float4 index XOR (row & 31)) so the global traffic is coalesced
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float4 g = __ldg(reinterpret_cast<const float4*>(P.ln2_g) + j);
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(P.ln2_b) + j);
+                for (int j = 0; j < 16; ++j) {
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(P.ln2_g + col0) + j);
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(P.ln2_b + col0) + j);
                     float4 y;
                     y.x = (__uint_as_float(v[4 * j + 0]) - mean) * rstd * g.x + b.x;
                     y.y = (__uint_as_float(v[4 * j + 1]) - mean) * rstd * g.y + b.y;
                     y.z = (__uint_as_float(v[4 * j + 2]) - mean) * rstd * g.z + b.z;
                     y.w = (__uint_as_float(v[4 * j + 3]) - mean) * rstd * g.w + b.w;
-                    reinterpret_cast<float4*>(stage_f + row * CH)[j ^ (row & 31)] = y;
+                    reinterpret_cast<float4*>(stage_f + row * CH)[(half * 16 + j) ^ (row & 31)] = y;
                 }
-                __syncwarp();                            // each warp re-reads only its own 32 rows
+                epi_bar();
                 float* og = P.out + g_row0 * CH;
 #pragma unroll 4
-                for (int i = 0; i < 32; ++i) {
-                    const int r = ew * 32 + i;
+                for (int i = 0; i < 16; ++i) {
+                    const int r = ew * 16 + i;
                     if (r < valid_rows) {
                         const float4 y = reinterpret_cast<const float4*>(stage_f + r * CH)[lane ^ (r & 31)];
                         const float4 xv = __ldg(reinterpret_cast<const float4*>(xg + (size_t)r * CH) + lane);
                         reinterpret_cast<float4*>(og + (size_t)r * CH)[lane] = make_float4(xv.x + y.x, xv.y + y.y, xv.z + y.z, xv.w + y.w);
                     }
                 }
-                __syncwarp();                            // staging reads done before the next tile's split stores
+                epi_bar();                               // staging reads done before the next tile's split stores
             }
             TRACE_E(13);
             tc_fence_before();

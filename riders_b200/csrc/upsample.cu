@@ -97,3 +97,102 @@ extern "C" int riders_leaky_concat_nhwc(const float* a, int Ca, const float* b, 
         Ca / 4, Cb / 4, pixels, slope, act_on_a);
     return check_launch("leaky_concat_nhwc");
 }
+
+// ---------------------------------------------------------------------------------------------
+// y = act(x + bias[c]) in one pass over a channels-last map (in place when out == x): the bias of a
+// convolution whose eval-mode BatchNorm was folded into it, plus utils/net_utils.py's activation
+// (LeakyReLU 0.2 everywhere in RC-Net).  ATen would run a broadcast add and then leaky_relu_.
+// slope: 0.2 leaky, 0 relu, 1 identity.  bias may be NULL.
+// ---------------------------------------------------------------------------------------------
+namespace riders {
+
+__global__ void __launch_bounds__(256)
+bias_act_nhwc_kernel(const float4* __restrict__ x, const float* __restrict__ bias, float4* __restrict__ out,
+                     int C4, long long total4, float slope) {
+    // blockDim (256) and the grid stride are multiples of C4 (a power of two <= 256): the channel group is fixed per thread
+    const int c = threadIdx.x & (C4 - 1);
+    const float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total4; e += (long long)gridDim.x * 256) {
+        float4 v = x[e];
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+        v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+        out[e] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bias_act_generic_kernel(const float* __restrict__ x, const float* __restrict__ bias, float* __restrict__ out,
+                        int C, long long total, float slope) {
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        float v = x[e] + (bias ? bias[e % C] : 0.f);
+        out[e] = v > 0.f ? v : v * slope;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bias_leaky_concat_nhwc_kernel(const float4* __restrict__ a, const float* __restrict__ bias, const float4* __restrict__ b,
+                              float4* __restrict__ out, int Ca4, int Cb4, long long pixels, float slope) {
+    const int Ct4 = Ca4 + Cb4;
+    const long long total = pixels * Ct4;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const long long p = e / Ct4;
+        const int c = (int)(e - p * Ct4);
+        float4 v;
+        if (c < Ca4) {
+            v = __ldcs(a + p * Ca4 + c);
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + c);
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+            v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+            v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+        } else {
+            v = __ldcs(b + p * Cb4 + (c - Ca4));
+        }
+        out[e] = v;
+    }
+}
+
+}  // namespace riders
+
+extern "C" int riders_bias_act_nhwc(const float* x, const float* bias, int C, long long pixels, float slope,
+                                    float* out, void* stream) {
+    using namespace riders;
+    RIDERS_REQUIRE(C > 0 && pixels >= 0, "bias_act: bad shape");
+    if (pixels == 0) return RIDERS_OK;
+    RIDERS_REQUIRE(x && out, "bias_act: null pointer");
+    const long long cap = (long long)sm_count() * 16;
+    count_launches(1);
+    const int C4 = C / 4;
+    if ((C & 3) == 0 && C4 <= 256 && (C4 & (C4 - 1)) == 0 && ((((uintptr_t)x) | ((uintptr_t)out) | ((uintptr_t)bias)) & 15) == 0) {
+        const long long total4 = pixels * C4;
+        long long blocks = (total4 + 255) / 256;
+        if (blocks > cap) blocks = cap;
+        bias_act_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4*>(x), bias, reinterpret_cast<float4*>(out), C4, total4, slope);
+    } else {
+        const long long total = pixels * C;
+        long long blocks = (total + 255) / 256;
+        if (blocks > cap) blocks = cap;
+        bias_act_generic_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, bias, out, C, total, slope);
+    }
+    return check_launch("bias_act_nhwc");
+}
+
+extern "C" int riders_bias_leaky_concat_nhwc(const float* a, const float* bias, int Ca, const float* b, int Cb,
+                                             long long pixels, float slope, float* out, void* stream) {
+    using namespace riders;
+    RIDERS_REQUIRE(Ca > 0 && Cb >= 0 && pixels >= 0, "bias_leaky_concat: bad shape");
+    RIDERS_REQUIRE((Ca & 3) == 0 && (Cb & 3) == 0, "bias_leaky_concat: channel counts must be multiples of 4 (%d, %d)", Ca, Cb);
+    if (pixels == 0) return RIDERS_OK;
+    RIDERS_REQUIRE(a && bias && out && (b || Cb == 0), "bias_leaky_concat: null pointer");
+    RIDERS_REQUIRE(((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)out) | ((uintptr_t)bias)) & 15) == 0, "bias_leaky_concat: 16-byte alignment");
+    const long long total = pixels * ((Ca + Cb) / 4);
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    count_launches(1);
+    bias_leaky_concat_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(a), bias, reinterpret_cast<const float4*>(b), reinterpret_cast<float4*>(out),
+        Ca / 4, Cb / 4, pixels, slope);
+    return check_launch("bias_leaky_concat_nhwc");
+}

@@ -190,8 +190,32 @@ def upsample_nearest(x, size):
     return out
 
 
-def leaky_concat(a, b, slope=0.2, act_on_a=True):
-    """cat([leaky_relu(a), b], dim=1) for channels-last float32 CUDA maps in one pass (bit-exact)."""
+def bias_act_(x, bias, slope):
+    """In place x = act(x + bias[c]) for a channels-last (or C == 1) float32 CUDA map; slope 0.2 leaky, 0 relu, 1 none."""
+    _need_cuda(x, bias)
+    N, Cc, H, W = x.shape
+    if not (x.dtype == torch.float32 and (x.is_contiguous(memory_format=torch.channels_last) or (Cc == 1 and x.is_contiguous()))):
+        raise _lib.RidersError("bias_act_ needs a channels_last float32 map")
+    b = _f32c(bias) if bias is not None else None
+    with _span("bias_act"):
+        rc = _lib.lib().riders_bias_act_nhwc(_ptr(x), _ptr(b), Cc, N * H * W, float(slope), _ptr(x), _stream())
+    _lib.check(rc, "riders_bias_act_nhwc")
+    return x
+
+
+def leaky_concat(a, b, slope=0.2, act_on_a=True, bias=None):
+    """cat([leaky_relu(a [+ bias]), b], dim=1) for channels-last float32 CUDA maps in one pass (bit-exact)."""
+    if bias is not None:
+        _need_cuda(a, b, bias)
+        N, Ca, H, W = a.shape
+        Cb = b.shape[1]
+        out = torch.empty((N, Ca + Cb, H, W), device=a.device, dtype=torch.float32, memory_format=torch.channels_last)
+        bias = _f32c(bias)
+        with _span("leaky_concat"):
+            rc = _lib.lib().riders_bias_leaky_concat_nhwc(_ptr(a), _ptr(bias), Ca, _ptr(b), Cb, N * H * W, float(slope),
+                                                          _ptr(out), _stream())
+        _lib.check(rc, "riders_bias_leaky_concat_nhwc")
+        return out
     _need_cuda(a, b)
     for t in (a, b):
         if not (_is_channels_last(t) and t.dtype == torch.float32 and t.shape[1] % 4 == 0):

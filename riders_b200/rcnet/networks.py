@@ -63,8 +63,22 @@ class Conv2d(torch.nn.Module):
         if use_batch_norm:
             self.batch_norm = torch.nn.BatchNorm2d(cout)
         self._act = _act(act)
+        self._act_name = None if (act is None or 'linear' in act) else ('leaky_relu' if 'leaky_relu' in act else
+                                                                        ('relu' if 'relu' in act else act))
+        self._fused_slope = None                  # set by fold_batch_norm_(): bias + activation run in one kernel
 
     def forward(self, x):
+        if self._fused_slope is not None and x.is_cuda and not torch.is_grad_enabled() and x.dtype == torch.float32 \
+                and (ops._is_channels_last(x) or x.shape[1] == 1):
+            # inference fast path after fold_batch_norm_(): conv without bias, then bias + activation in ONE pass
+            c = self.conv
+            y = F.conv2d(x, c.weight, None, c.stride, c.padding, c.dilation, c.groups)
+            if c.bias is None and self._fused_slope == 1.0:
+                return y
+            if ops._is_channels_last(y) or (y.shape[1] == 1 and y.is_contiguous()):
+                return ops.bias_act_(y, c.bias, self._fused_slope)
+            y = y if c.bias is None else y + c.bias.view(1, -1, 1, 1)
+            return y if self._act is None else self._act(y)
         y = self.conv(x)
         if self.use_batch_norm:
             y = self.batch_norm(y)
@@ -78,6 +92,7 @@ class Conv2d(torch.nn.Module):
             self.conv = torch.nn.utils.fusion.fuse_conv_bn_eval(self.conv.eval(), self.batch_norm.eval())
             self.use_batch_norm = False
             del self.batch_norm
+        self._fused_slope = {'leaky_relu': _LEAK, 'relu': 0.0, None: 1.0}.get(self._act_name)
         return self
 
 
@@ -149,8 +164,9 @@ class DecoderBlock(torch.nn.Module):
                 and x.is_cuda and x.dtype == torch.float32 and ops._is_channels_last(x) and ops._is_channels_last(skip)
                 and x.shape[1] % 4 == 0 and up.conv.out_channels % 4 == 0 and skip.shape[1] % 4 == 0):
             # inference fast path (BatchNorm folded): resize -> conv(+bias) -> [LeakyReLU | skip] in one pass -> conv
-            y = up.conv(ops.upsample_nearest(x, shape))
-            return self.conv(ops.leaky_concat(y, skip, _LEAK))
+            c = up.conv
+            y = F.conv2d(ops.upsample_nearest(x, shape), c.weight, None, c.stride, c.padding, c.dilation, c.groups)
+            return self.conv(ops.leaky_concat(y, skip, _LEAK, bias=c.bias))
         y = self.deconv(x, shape=shape)
         if self.skip_channels > 0:
             y = torch.cat([y, skip], dim=1)

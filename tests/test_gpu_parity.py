@@ -463,7 +463,7 @@ def test_optimizer_class_is_a_drop_in():
 
 # ------------------------------------------------------------------------------------ decoder glue
 @pytest.mark.parametrize("shape,size", [((3, 32, 120, 50), (240, 100)), ((2, 256, 7, 3), (15, 6)), ((2, 128, 30, 12), (60, 25)),
-                                        ((1, 8, 13, 5), (5, 13)), ((2, 4, 1, 1), (7, 9))])
+                                        ((1, 8, 13, 5), (5, 13)), ((2, 4, 2, 1), (7, 9))])
 def test_upsample_nearest_is_bit_exact_with_torch(shape, size):
     x = torch.randn(shape, device=DEV).contiguous(memory_format=torch.channels_last)
     got = ops.upsample_nearest(x, size)
@@ -503,3 +503,18 @@ def test_leaky_concat_is_bit_exact_with_torch():
     ref = torch.cat([torch.nn.functional.leaky_relu(a, 0.2), b], dim=1)
     assert got.is_contiguous(memory_format=torch.channels_last) and torch.equal(got, ref)
     assert torch.equal(ops.leaky_concat(a, b, 0.2, act_on_a=False), torch.cat([a, b], dim=1))
+
+
+def test_bias_act_and_biased_concat_match_torch():
+    x = torch.randn((3, 16, 20, 10), device=DEV).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(16, device=DEV)
+    ref = torch.nn.functional.leaky_relu(x + bias.view(1, -1, 1, 1), 0.2)
+    got = ops.bias_act_(x.clone(memory_format=torch.channels_last), bias, 0.2)
+    assert torch.equal(got, ref)
+    assert torch.equal(ops.bias_act_(x.clone(memory_format=torch.channels_last), None, 1.0), x)
+    assert torch.equal(ops.bias_act_(x.clone(memory_format=torch.channels_last), bias, 0.0), torch.relu(x + bias.view(1, -1, 1, 1)))
+    one = torch.randn((2, 1, 9, 7), device=DEV)                               # C == 1 (output head): scalar path
+    assert torch.equal(ops.bias_act_(one.clone(), torch.tensor([0.5], device=DEV), 0.2),
+                       torch.nn.functional.leaky_relu(one + 0.5, 0.2))
+    skip = torch.randn((3, 32, 20, 10), device=DEV).contiguous(memory_format=torch.channels_last)
+    assert torch.equal(ops.leaky_concat(x, skip, 0.2, bias=bias), torch.cat([ref, skip], dim=1))

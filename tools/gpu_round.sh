@@ -23,6 +23,9 @@ for MODE in "$@"; do
     benchsimt)
       RIDERS_LOFTR_IMPL=simt timeout -s KILL 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_simt.json 2> $OUT/bench_simt.err; echo "bench-simt rc=$?" | tee -a $OUT/status.txt
       tail -c 1500 $OUT/bench_simt.json ;;
+    trace)
+      timeout -s KILL 300 python tools/loftr_trace.py 2048 > $OUT/loftr_trace.txt 2>&1; echo "trace rc=$?" | tee -a $OUT/status.txt
+      cat $OUT/loftr_trace.txt ;;
     micro)
       timeout -s KILL 600 python tools/microbench.py > $OUT/microbench.jsonl 2> $OUT/microbench.err; echo "microbench rc=$?" | tee -a $OUT/status.txt
       cat $OUT/microbench.jsonl ;;
