@@ -61,6 +61,7 @@ def build_model(device, seed=0):
         model.device = device
         model.to(device)
         model.optimize_for_inference()
+        torch.backends.cudnn.benchmark = os.environ.get("RIDERS_CUDNN_BENCHMARK", "1") == "1"   # autotune the torch convs
     return model
 
 

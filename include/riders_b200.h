@@ -213,6 +213,13 @@ int riders_leaky_concat_nhwc(const float* a, int Ca, const float* b, int Cb, lon
 /* the same with the (BatchNorm-folded) convolution bias added first: out[p][0:Ca] = leaky(a[p][:] + bias[:]) */
 int riders_bias_leaky_concat_nhwc(const float* a, const float* bias, int Ca, const float* b, int Cb,
                                   long long pixels, float slope, float* out, void* stream);
+/* Decoder head in front of riders_confidence_reduce: logits (N,H,W) = conv3x3(act(x + bias)), zero padding,
+ * x (N,H,W,C=16) channels-last RAW output of the last decoder convolution, weight_host (1,C,3,3) and
+ * bias_host (C, or NULL) in HOST memory (they become kernel parameters).  MultiScaleDecoder.output0,
+ * RCNet/networks.py:678-779.                                                                          */
+int riders_conv3x3_head_nhwc(const float* x, int N, int C, int H, int W,
+                             const float* bias_host, float slope, const float* weight_host,
+                             float* out, void* stream);
 /* out = act(x + bias[c]) over `pixels` channels-last pixels of C channels (in place when out == x);
  * slope 0.2 = LeakyReLU of utils/net_utils.py:15, 0 = ReLU, 1 = identity; bias may be NULL.          */
 int riders_bias_act_nhwc(const float* x, const float* bias, int C, long long pixels, float slope,

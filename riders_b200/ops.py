@@ -203,6 +203,37 @@ def bias_act_(x, bias, slope):
     return x
 
 
+_HOST_CACHE = {}
+
+
+def _host_floats(t):
+    """Small parameter tensor -> cached contiguous float32 host copy (one D2H per parameter version)."""
+    if t is None:
+        return None
+    key = (t.data_ptr(), t._version, tuple(t.shape))
+    h = _HOST_CACHE.get(key)
+    if h is None:
+        if len(_HOST_CACHE) > 64:
+            _HOST_CACHE.clear()
+        h = t.detach().to("cpu", torch.float32).contiguous()
+        _HOST_CACHE[key] = h
+    return h
+
+
+def conv3x3_head(x_raw, bias, slope, weight):
+    """logits (N,1,H,W) = conv2d(act(x_raw + bias), weight (1,C,3,3), padding=1) for a channels-last C=16 map."""
+    _need_cuda(x_raw)
+    if not (_is_channels_last(x_raw) and x_raw.dtype == torch.float32):
+        raise _lib.RidersError("conv3x3_head needs a channels_last float32 map")
+    N, Cc, H, W = x_raw.shape
+    hb, hw = _host_floats(bias), _host_floats(weight)
+    out = torch.empty((N, 1, H, W), device=x_raw.device, dtype=torch.float32)
+    with _span("conv3x3_head"):
+        rc = _lib.lib().riders_conv3x3_head_nhwc(_ptr(x_raw), N, Cc, H, W, _ptr(hb), float(slope), _ptr(hw), _ptr(out), _stream())
+    _lib.check(rc, "riders_conv3x3_head_nhwc")
+    return out
+
+
 def leaky_concat(a, b, slope=0.2, act_on_a=True, bias=None):
     """cat([leaky_relu(a [+ bias]), b], dim=1) for channels-last float32 CUDA maps in one pass (bit-exact)."""
     if bias is not None:

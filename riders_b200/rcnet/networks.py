@@ -84,6 +84,15 @@ class Conv2d(torch.nn.Module):
             y = self.batch_norm(y)
         return y if self._act is None else self._act(y)
 
+    def fast_ok(self, x):
+        return (self._fused_slope is not None and x.is_cuda and not torch.is_grad_enabled() and x.dtype == torch.float32
+                and ops._is_channels_last(x))
+
+    def raw(self, x):
+        """Convolution only; the caller fuses (bias, slope) into its own kernel.  Needs ``fast_ok(x)``."""
+        c = self.conv
+        return F.conv2d(x, c.weight, None, c.stride, c.padding, c.dilation, c.groups), c.bias, self._fused_slope
+
     def fold_batch_norm_(self):
         """Inference only: fold the (eval-mode) BatchNorm affine into the convolution's weights and bias
         (torch.nn.utils.fusion).  Same function up to float32 rounding; removes one full pass over the
@@ -154,11 +163,15 @@ class DecoderBlock(torch.nn.Module):
         self.deconv = UpConv2d(cin, cout, init, act, use_batch_norm)
         self.conv = Conv2d(cskip + cout, cout, 3, 1, init, act, use_batch_norm)
 
-    def forward(self, x, skip=None, shape=None):
+    def forward(self, x, skip=None, shape=None, raw=False):
+        """``raw=True`` (inference fast path only): return (conv output without bias/activation, bias, slope)
+        of the block's last convolution so that the decoder head can fuse them."""
         if skip is not None:
             shape = skip.shape[2:4]
         elif shape is None:
             shape = (2 * x.shape[2], 2 * x.shape[3])
+        if raw:
+            return self.conv.raw(self.deconv(x, shape=shape))
         up = self.deconv.conv
         if (self.skip_channels > 0 and self._leaky and not up.use_batch_norm and not torch.is_grad_enabled()
                 and x.is_cuda and x.dtype == torch.float32 and ops._is_channels_last(x) and ops._is_channels_last(skip)
@@ -259,6 +272,28 @@ class RCNetEncoder(torch.nn.Module):
         latent_image, skips_image = self.encoder_image(image)
         return self.encode_points(latent_image, skips_image, points, b_boxes)
 
+    def encode_latent(self, latent_image, points, b_boxes):
+        """Latent half of ``encode_points``: gather of the 1/32 level, point MLP, LoFTR fusion, concat
+        (networks.py:418-419, 438-450).  Cheap per point, so a whole batch goes through in one call."""
+        scale, osize = self.pyramid(0)[-1]
+        ph, pw = self.input_patch_size_image[-2], self.input_patch_size_image[-1]
+        latent_pooled = ops.roi_gather([latent_image], b_boxes, [scale], [osize], max_roi=(pw, ph))[0]
+        n, c = points.shape[0], self.n_neuron_latent_depth
+        latent_depth = self.encoder_depth(points).view(n, c, -1, osize[1])
+        tok_depth = latent_depth.reshape(n, c, -1).permute(0, 2, 1)
+        tok_image = latent_pooled.reshape(n, latent_pooled.shape[1], -1).permute(0, 2, 1)
+        tok_depth, tok_image = self.attention(tok_depth, tok_image)
+        depth_tf = tok_depth.permute(0, 2, 1).reshape(latent_depth.shape)
+        image_tf = tok_image.permute(0, 2, 1).reshape(latent_pooled.shape)
+        return torch.cat([image_tf, depth_tf], dim=1)
+
+    def gather_skips(self, skips_image, b_boxes):
+        """Skip half of ``encode_points``: the four pooled skip levels (networks.py:421-433); 1.38 MB per
+        point, so callers chunk the points to bound the decoder's activation memory."""
+        levels = self.pyramid(len(skips_image))[:-1]
+        ph, pw = self.input_patch_size_image[-2], self.input_patch_size_image[-1]
+        return ops.roi_gather(list(skips_image), b_boxes, [s for s, _ in levels], [o for _, o in levels], max_roi=(pw, ph))
+
     def encode_points(self, latent_image, skips_image, points, b_boxes):
         """Everything after the backbone (networks.py:418-451).  ``b_boxes`` may also be an (R,5)
         RoI tensor (batch index first), which lets a caller run chunks of points of a big batch."""
@@ -314,5 +349,15 @@ class MultiScaleDecoder(torch.nn.Module):
             y = getattr(self, name)(y, skips[n])
             n -= 1
         last = getattr(self, self._order[-1])
+        head = self.output0.conv
+        if (n != 0 and last.skip_channels == 0 and last.conv.fast_ok(y) and self.output0._act is None
+                and not self.output0.use_batch_norm and head.bias is None and head.kernel_size == (3, 3)
+                and head.out_channels == 1 and head.in_channels == 16 and head.stride == (1, 1) and head.padding == (1, 1)):
+            # inference fast path: last conv raw -> [bias + LeakyReLU + 3x3 head] in one kernel -> logits
+            y_raw, bias, slope = last(y, shape=tuple(shape[-2:]), raw=True)
+            if ops._is_channels_last(y_raw):
+                return [ops.conv3x3_head(y_raw, bias, slope, head.weight)]
+            y = ops.bias_act_(y_raw, bias, slope) if bias is not None or slope != 1.0 else y_raw
+            return [self.output0(y)]
         y = last(y, skips[n]) if n == 0 else last(y, shape=tuple(shape[-2:]))
         return [self.output0(y)]

@@ -75,9 +75,12 @@ def forward_output_batched(model, images, radar_points, frame_offsets, response_
         torch.arange(B, device=images.device, dtype=torch.float32),
         torch.tensor([frame_offsets[i + 1] - frame_offsets[i] for i in range(B)], device=images.device))
     rois = torch.cat([frame_of[:, None], boxes], dim=1).contiguous()
+    # latent path (1/32-level gather + point MLP + LoFTR) for every point of the batch at once: 1366 tiles of
+    # 6 points fill the 148 SMs in ~9 full waves; the skip gather + decoder run per chunk of points.
+    latent = enc.encode_latent(latent_image, radar_points, rois)
     for s in range(0, R, chunk_points):
         e = min(R, s + chunk_points)
-        latent, skips = enc.encode_points(latent_image, skips_image, radar_points[s:e], rois[s:e])
-        logits[s:e] = dec(x=latent, skips=skips, shape=(ph, pw))[-1]
+        skips = enc.gather_skips(skips_image, rois[s:e])
+        logits[s:e] = dec(x=latent[s:e], skips=skips, shape=(ph, pw))[-1]
     return ops.confidence_reduce(logits, radar_points, frame_offsets, H, W, response_thr, logits=True,
                                  want_select=return_select)[:3 if return_select else 2]

@@ -396,8 +396,8 @@ def test_pipeline_matches_oracle_chain():
         np.testing.assert_allclose(sm[ok], ref["scale_map"][ok], rtol=1e-5)     # 1e-5 relative inside
 
 
-@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
-def test_full_size_rcnet_forward_vs_oracle(impl, monkeypatch):
+@pytest.mark.parametrize("impl,optimized", [("simt", False), ("tcgen05", False), ("tcgen05", True)])
+def test_full_size_rcnet_forward_vs_oracle(impl, optimized, monkeypatch):
     """The real RC-Net configuration (d_model 128, 21 tokens, patch 240x100, 752x740 padded frame):
     gather on the real pyramid through the TMA path + the LoFTR kernels, against the CPU oracle."""
     if impl == "tcgen05" and not ops.loftr_impl_available(ops.LOFTR_TCGEN05, 128, 8, 21):
@@ -407,7 +407,8 @@ def test_full_size_rcnet_forward_vs_oracle(impl, monkeypatch):
     torch.backends.cuda.matmul.allow_tf32 = False
     patch, K = (240, 100), 9
     cpu = _rand_model("cpu", patch, [32, 64, 128, 128, 128], [256, 128, 64, 32, 16], seed=1)
-    gpu = _to_cuda(cpu).channels_last()
+    gpu = _to_cuda(cpu)
+    gpu = gpu.optimize_for_inference() if optimized else gpu.channels_last()   # optimized: folded BN + fused decoder glue + head
     fr = synth.chain_frame(7, K, 512, 640, patch)
     fr["points"][0, :2] = [50, 120]                       # a corner point: RoI clipped by the map edge
     fr["boxes"][0] = [0, 0, 100, 240]
@@ -518,3 +519,21 @@ def test_bias_act_and_biased_concat_match_torch():
                        torch.nn.functional.leaky_relu(one + 0.5, 0.2))
     skip = torch.randn((3, 32, 20, 10), device=DEV).contiguous(memory_format=torch.channels_last)
     assert torch.equal(ops.leaky_concat(x, skip, 0.2, bias=bias), torch.cat([ref, skip], dim=1))
+
+
+def test_conv3x3_head_matches_torch():
+    torch.backends.cudnn.allow_tf32 = False
+    x = torch.randn((5, 16, 37, 53), device=DEV).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(16, device=DEV)
+    w = torch.randn((1, 16, 3, 3), device=DEV) * 0.2
+    got = ops.conv3x3_head(x, bias, 0.2, w)
+    ref = torch.nn.functional.conv2d(torch.nn.functional.leaky_relu(x + bias.view(1, -1, 1, 1), 0.2), w, padding=1)
+    assert got.shape == ref.shape
+    np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    got2 = ops.conv3x3_head(x, None, 1.0, w)                                   # no bias, identity activation
+    ref2 = torch.nn.functional.conv2d(x, w, padding=1)
+    np.testing.assert_allclose(got2.cpu().numpy(), ref2.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    big = torch.randn((3, 16, 240, 100), device=DEV).contiguous(memory_format=torch.channels_last)   # the RC-Net patch
+    np.testing.assert_allclose(ops.conv3x3_head(big, bias, 0.2, w).cpu().numpy(),
+                               torch.nn.functional.conv2d(torch.nn.functional.leaky_relu(big + bias.view(1, -1, 1, 1), 0.2), w, padding=1).cpu().numpy(),
+                               rtol=1e-5, atol=1e-5)
