@@ -242,25 +242,18 @@ def main():
     e2e_ms = rdist.max_over_ranks(e0.elapsed_time(e1))
 
     # ---------------------------------------------------------------- roofline of the dominant kernel
-    R = B * K_POINTS
-    work = {  # per step on this GPU: (bound, algorithmic bytes or flops)
-        "roi_gather": ("hbm", R * GATHER_BYTES_PER_POINT + B * GATHER_MAP_BYTES_PER_FRAME),
-        "loftr_transformer": ("tensor", R * LOFTR_FLOP_PER_POINT),
-        "confidence_reduce": ("hbm", R * REDUCE_BYTES_PER_POINT + 2 * B * MAP_BYTES),
-        "lsq_align": ("hbm", B * (2 * MAP_BYTES + H * W + MAP_BYTES)),
-        "extract_knots": ("hbm", B * (H * W + 12 * K_POINTS)),
-        "interp_triangulate": ("hbm", B * (20 * K_POINTS + 2 * K_POINTS * 48)),   # latency bound; bytes = knots in + triangle records out
-        "interp_fill": ("hbm", B * (MAP_BYTES + 2 * K_POINTS * 48)),
-    }
+    # Every ops.* wrapper reports the algorithmic bytes (flops for LoFTR) of its call next to the CUDA events that
+    # bracket it.  The gather additionally reads each frame's feature maps once.
+    TENSOR = {"loftr_transformer"}
     stage_report = {}
-    for name, (calls, ms) in stages.items():
-        bound, amount = work.get(name, ("hbm", 0))
-        per_call = amount * args.steps / max(calls, 1)
-        avg_ms = ms / max(calls, 1)
-        ach = per_call / (avg_ms * 1e-3) / (1e9 if bound == "hbm" else 1e12) if avg_ms > 0 else 0.0
+    for name, (calls, ms, amount) in stages.items():
+        bound = "tensor" if name in TENSOR else "hbm"
+        if name == "roi_gather":
+            amount += args.steps * B * GATHER_MAP_BYTES_PER_FRAME
+        ach = amount / (ms * 1e-3) / (1e12 if bound == "tensor" else 1e9) if ms > 0 else 0.0
         stage_report[name] = {"bound": bound, "calls_per_step": calls / args.steps, "ms_per_step": ms / args.steps,
-                              "achieved": round(ach, 2), "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
-                              "frac": round(ach / peaks[bound], 4)}
+                              "work_per_step": amount / args.steps, "achieved": round(ach, 2),
+                              "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac": round(ach / peaks[bound], 4)}
     ms_step = ms_total / args.steps
     dom = max(stage_report, key=lambda k: stage_report[k]["ms_per_step"])
     traffic = None
@@ -268,10 +261,11 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
     except Exception:
         pass
-    roofline = {"kernel": dom, "bound": stage_report[dom]["bound"], "achieved": stage_report[dom]["achieved"],
-                "peak": peaks[stage_report[dom]["bound"]], "unit": stage_report[dom]["unit"],
-                "frac": stage_report[dom]["frac"], "traffic": traffic, "peak_source": peaks["source"],
-                "share_of_step": round(stage_report[dom]["ms_per_step"] / ms_step, 4)}
+    d = stage_report[dom]
+    roofline = {"kernel": dom, "bound": d["bound"], "achieved": d["achieved"], "peak": peaks[d["bound"]], "unit": d["unit"],
+                "frac": d["frac"], "traffic": traffic, "peak_source": peaks["source"],
+                "launches_per_step": d["calls_per_step"], "algorithmic_work_per_launch": d["work_per_step"] / max(d["calls_per_step"], 1),
+                "avg_launch_ms": d["ms_per_step"] / max(d["calls_per_step"], 1), "share_of_step": round(d["ms_per_step"] / ms_step, 4)}
 
     line = None
     if rank == 0:

@@ -175,6 +175,26 @@ int riders_l1_scale_align(const float* pred, const float* target, const uint8_t*
                           void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * N2/N3  scale scaffold (val_zju.py:135-138,171-179) with the RC-Net -> SML PNG hand-off in memory
+ *     int_depth (aligned prior), rcnet_depth (quasi-dense METRIC depth from A5, or NULL),
+ *     sparse_inv / sparse_valid (radar inverse depth and mask), all (B,H,W).
+ *     png_quantize != 0 applies the 16-bit PNG codec of data/data_utils.py:94-143 (uint32(z*256)/256).
+ *     int_scales (B,H,W) out = normalize_unit_range(scales); minmax (B,2) float32 optional;
+ *     status (B) optional: 1 where max-min <= eps (the reference raises ValueError; scales left raw).
+ * N4  riders_depth_metrics: per-frame MAE, RMSE, iMAE, iRMSE, AbsRel, SqRel, delta1, n  (B,8) double
+ *     utils/eval_utils.py:17-117 as called from val_zju.py:212-231 (mask: gt > 0, min_val < gt < max_val).
+ *     workspace: riders_glue_workspace_bytes(B, H, W), 8-byte aligned.
+ * ------------------------------------------------------------------------------------------ */
+size_t riders_glue_workspace_bytes(int B, int H, int W);
+int riders_scale_scaffold(const float* int_depth, const float* rcnet_depth,
+                          const float* sparse_inv, const uint8_t* sparse_valid,
+                          int B, int H, int W, float min_depth, float max_depth, int png_quantize,
+                          float* int_scales, float* minmax, int32_t* status,
+                          void* workspace, void* stream);
+int riders_depth_metrics(const float* pred, const float* gt, int B, int H, int W,
+                         float min_val, float max_val, double* metrics, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * A8  Interpolator2D / interpolate_knots(method='linear')   modules/interpolator.py:7-50
  *     riders_extract_knots: row-major scan of `valid` -> knot_xy (B,max_knots,2) int32 (x,y),
  *       knot_scale = sparse/pred, knot_shift = sparse-pred (float32), knot_count (B) int32 (the

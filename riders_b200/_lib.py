@@ -44,6 +44,9 @@ SIGNATURES = {
     "riders_l1_scale_workspace_bytes": (sz, [ci, ci]),
     "riders_l1_scale_align": (ci, [vp, vp, vp, ci, ci, ci, ci, C.c_double, C.c_double, C.c_double, ci,
                                    vp, vp, vp, vp, cf, cf, ci, vp, vp]),
+    "riders_glue_workspace_bytes": (sz, [ci, ci, ci]),
+    "riders_scale_scaffold": (ci, [vp, vp, vp, vp, ci, ci, ci, cf, cf, ci, vp, vp, vp, vp, vp]),
+    "riders_depth_metrics": (ci, [vp, vp, ci, ci, ci, cf, cf, vp, vp, vp]),
     "riders_extract_knots": (ci, [vp, vp, vp, ci, ci, ci, ci, vp, vp, vp, vp, vp]),
     "riders_interp_workspace_bytes": (sz, [ci, ci, ci, ci]),
     "riders_interp_triangulate": (ci, [vp, vp, vp, ci, ci, vp, vp, vp, vp, vp]),

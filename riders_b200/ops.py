@@ -34,17 +34,20 @@ class StageTimer(object):
         _timer = self._prev
 
     def summary(self):
-        """name -> (calls, total_ms); synchronises."""
+        """name -> (calls, total_ms, total algorithmic bytes or flops reported by the wrappers); synchronises."""
         torch.cuda.synchronize()
-        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.spans.items()}
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b, _ in v), sum(w for _, _, w in v)) for k, v in self.spans.items()}
 
 
 _timer = None
 
 
 class _span(object):
-    def __init__(self, name):
+    """``work`` = algorithmic bytes (HBM kernels) or flops (LoFTR) of the call, for bench.py's roofline."""
+
+    def __init__(self, name, work=0):
         self.name = name
+        self.work = work
 
     def __enter__(self):
         if _timer is not None:
@@ -55,7 +58,7 @@ class _span(object):
         if _timer is not None and exc[0] is None:
             b = torch.cuda.Event(enable_timing=True)
             b.record()
-            _timer.spans.setdefault(self.name, []).append((self.a, b))
+            _timer.spans.setdefault(self.name, []).append((self.a, b, self.work))
 
 
 def launch_count():
@@ -142,7 +145,8 @@ def roi_gather(feats, boxes, scales, out_sizes, max_roi=None, want_argmax=False,
         r1 = min(R, r0 + chunk)
         o_ptrs = _ptr_array([o[r0:r1] for o in outs])
         a_ptrs = _ptr_array([a[r0:r1] for a in args]) if want_argmax else None
-        with _span("roi_gather"):
+        nb = sum(o[r0:r1].numel() for o in outs) * 4 + (r1 - r0) * 20          # written patches + RoIs (maps: see bench.py)
+        with _span("roi_gather", nb):
             rc = L.riders_roi_gather_fwd(n, _ptr_array(feats), Cs, Hs, Ws, sc, ohs, ows,
                                          LAYOUT_NHWC if nhwc else LAYOUT_NCHW, B,
                                          _ptr(rois[r0:r1]), r1 - r0, mw, mh, o_ptrs, a_ptrs, _stream())
@@ -184,7 +188,7 @@ def upsample_nearest(x, size):
     N, Cc, h, w = x.shape
     H, W = int(size[0]), int(size[1])
     out = torch.empty((N, Cc, H, W), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
-    with _span("upsample_nearest"):
+    with _span("upsample_nearest", (x.numel() + out.numel()) * 4):
         rc = _lib.lib().riders_upsample_nearest_nhwc(_ptr(x), N, Cc, h, w, H, W, _ptr(out), _stream())
     _lib.check(rc, "riders_upsample_nearest_nhwc")
     return out
@@ -197,7 +201,7 @@ def bias_act_(x, bias, slope):
     if not (x.dtype == torch.float32 and (x.is_contiguous(memory_format=torch.channels_last) or (Cc == 1 and x.is_contiguous()))):
         raise _lib.RidersError("bias_act_ needs a channels_last float32 map")
     b = _f32c(bias) if bias is not None else None
-    with _span("bias_act"):
+    with _span("bias_act", 2 * x.numel() * 4):
         rc = _lib.lib().riders_bias_act_nhwc(_ptr(x), _ptr(b), Cc, N * H * W, float(slope), _ptr(x), _stream())
     _lib.check(rc, "riders_bias_act_nhwc")
     return x
@@ -228,7 +232,7 @@ def conv3x3_head(x_raw, bias, slope, weight):
     N, Cc, H, W = x_raw.shape
     hb, hw = _host_floats(bias), _host_floats(weight)
     out = torch.empty((N, 1, H, W), device=x_raw.device, dtype=torch.float32)
-    with _span("conv3x3_head"):
+    with _span("conv3x3_head", (x_raw.numel() + out.numel()) * 4):
         rc = _lib.lib().riders_conv3x3_head_nhwc(_ptr(x_raw), N, Cc, H, W, _ptr(hb), float(slope), _ptr(hw), _ptr(out), _stream())
     _lib.check(rc, "riders_conv3x3_head_nhwc")
     return out
@@ -242,7 +246,7 @@ def leaky_concat(a, b, slope=0.2, act_on_a=True, bias=None):
         Cb = b.shape[1]
         out = torch.empty((N, Ca + Cb, H, W), device=a.device, dtype=torch.float32, memory_format=torch.channels_last)
         bias = _f32c(bias)
-        with _span("leaky_concat"):
+        with _span("leaky_concat", 2 * out.numel() * 4):
             rc = _lib.lib().riders_bias_leaky_concat_nhwc(_ptr(a), _ptr(bias), Ca, _ptr(b), Cb, N * H * W, float(slope),
                                                           _ptr(out), _stream())
         _lib.check(rc, "riders_bias_leaky_concat_nhwc")
@@ -254,7 +258,7 @@ def leaky_concat(a, b, slope=0.2, act_on_a=True, bias=None):
     N, Ca, H, W = a.shape
     Cb = b.shape[1]
     out = torch.empty((N, Ca + Cb, H, W), device=a.device, dtype=torch.float32, memory_format=torch.channels_last)
-    with _span("leaky_concat"):
+    with _span("leaky_concat", 2 * out.numel() * 4):
         rc = _lib.lib().riders_leaky_concat_nhwc(_ptr(a), Ca, _ptr(b), Cb, N * H * W, float(slope),
                                                  1 if act_on_a else 0, _ptr(out), _stream())
     _lib.check(rc, "riders_leaky_concat_nhwc")
@@ -331,7 +335,8 @@ def loftr_transformer(feat0, feat1, layer_params, layer_names, nhead=8, impl=LOF
     L = _lib.lib()
     ws = torch.empty(L.riders_loftr_workspace_bytes(N, max(L0, S), Cm, impl), dtype=torch.uint8, device=feat0.device)
     out0, out1 = torch.empty_like(feat0), torch.empty_like(feat1)
-    with _span("loftr_transformer"):
+    # 7 058 688 flop per point per layer call, two calls per layer
+    with _span("loftr_transformer", 2 * n * N * 7058688):
         rc = L.riders_loftr_transformer_fwd(_ptr(feat0), _ptr(feat1), arr, _int_array(kinds), n,
                                             N, L0, S, Cm, nhead, float(attn_eps), float(ln_eps), impl,
                                             _ptr(out0), _ptr(out1), _ptr(ws), _stream())
@@ -358,7 +363,7 @@ def confidence_reduce(conf, points, frame_offsets, H, W, thr, logits=False, want
     depth = torch.empty((B, H, W), device=dev, dtype=torch.float32)
     resp = torch.empty_like(depth)
     sel = torch.empty((B, H, W), device=dev, dtype=torch.int32) if want_select else None
-    with _span("confidence_reduce"):
+    with _span("confidence_reduce", conf.numel() * 4 + points.numel() * 4 + (3 if want_select else 2) * B * H * W * 4):
         rc = _lib.lib().riders_confidence_reduce(_ptr(conf), 1 if logits else 0, _ptr(points), _ptr(offs),
                                                  B, H, W, ph, pw, float(thr), _ptr(depth), _ptr(resp), _ptr(sel), _stream())
     _lib.check(rc, "riders_confidence_reduce")
@@ -383,7 +388,7 @@ def lsq_align(pred, target, mask, clamp_hi=None, clamp_lo=None, want_out=True):
     ss = torch.empty((B, 2), dtype=torch.float64, device=dev)
     out = torch.empty_like(pred) if want_out else None
     flags = (1 if clamp_hi is not None else 0) | (2 if clamp_lo is not None else 0)
-    with _span("lsq_align"):
+    with _span("lsq_align", B * H * W * (9 + (4 + 4 if want_out else 0))):
         rc = L.riders_lsq_align(_ptr(pred), _ptr(target), _ptr(mask), B, H, W, _ptr(sums), _ptr(ss), _ptr(out),
                                 float(clamp_hi or 0.0), float(clamp_lo or 0.0), flags, _ptr(ws), _stream())
     _lib.check(rc, "riders_lsq_align")
@@ -408,13 +413,53 @@ def l1_scale_align(pred, target, mask, bounds=(0.01, 0.3), clamp_hi=None, clamp_
     nfev = torch.empty((B,), dtype=torch.int32, device=dev)
     out = torch.empty_like(pred) if want_out else None
     flags = (1 if clamp_hi is not None else 0) | (2 if clamp_lo is not None else 0)
-    with _span("l1_scale_align"):
+    with _span("l1_scale_align", B * H * W * (9 + (8 if want_out else 0))):
         rc = L.riders_l1_scale_align(_ptr(pred), _ptr(target), _ptr(mask), B, H, W, cap,
                                      float(bounds[0]), float(bounds[1]), float(xatol), int(maxiter),
                                      _ptr(scale), _ptr(fval), _ptr(nfev), _ptr(out),
                                      float(clamp_hi or 0.0), float(clamp_lo or 0.0), flags, _ptr(ws), _stream())
     _lib.check(rc, "riders_l1_scale_align")
     return scale, fval, nfev, out
+
+
+# --------------------------------------------------------------------------------------------
+# N2/N3 scaffold, N4 metrics
+# --------------------------------------------------------------------------------------------
+def scale_scaffold(int_depth, rcnet_depth, sparse_inv, sparse_valid, min_depth=0.0, max_depth=100.0, png_quantize=True):
+    """Scale scaffold of val_zju.py:171-179 (+ the PNG codec of the RC-Net -> SML hand-off).
+    Returns int_scales (B,H,W) f32 in [0,1], minmax (B,2) f32, status (B,) int32 (1 = zero range)."""
+    _need_cuda(int_depth, rcnet_depth, sparse_inv, sparse_valid)
+    int_depth, sparse_inv = _f32c(int_depth), _f32c(sparse_inv)
+    rc = _f32c(rcnet_depth) if rcnet_depth is not None else None
+    sv = sparse_valid.contiguous()
+    sv = sv.view(torch.uint8) if sv.dtype == torch.bool else sv.to(torch.uint8)
+    B, H, W = int_depth.shape
+    dev = int_depth.device
+    L = _lib.lib()
+    ws = torch.empty(L.riders_glue_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev)
+    out = torch.empty_like(int_depth)
+    minmax = torch.empty((B, 2), dtype=torch.float32, device=dev)
+    status = torch.zeros((B,), dtype=torch.int32, device=dev)
+    with _span("scale_scaffold", B * H * W * (4 + (4 if rc is not None else 0) + 4 + 1 + 4 + 8)):
+        rc_ = L.riders_scale_scaffold(_ptr(int_depth), _ptr(rc), _ptr(sparse_inv), _ptr(sv), B, H, W, float(min_depth),
+                                      float(max_depth), 1 if png_quantize else 0, _ptr(out), _ptr(minmax), _ptr(status),
+                                      _ptr(ws), _stream())
+    _lib.check(rc_, "riders_scale_scaffold")
+    return out, minmax, status
+
+
+def depth_metrics(pred, gt, min_val=0.0, max_val=50.0):
+    """Per-frame [MAE, RMSE, iMAE, iRMSE, AbsRel, SqRel, delta1, n] (B,8) float64 (val_zju.py:212-231)."""
+    _need_cuda(pred, gt)
+    pred, gt = _f32c(pred), _f32c(gt)
+    B, H, W = pred.shape
+    L = _lib.lib()
+    ws = torch.empty(L.riders_glue_workspace_bytes(B, H, W), dtype=torch.uint8, device=pred.device)
+    out = torch.empty((B, 8), dtype=torch.float64, device=pred.device)
+    with _span("depth_metrics", B * H * W * 8):
+        rc = L.riders_depth_metrics(_ptr(pred), _ptr(gt), B, H, W, float(min_val), float(max_val), _ptr(out), _ptr(ws), _stream())
+    _lib.check(rc, "riders_depth_metrics")
+    return out
 
 
 # --------------------------------------------------------------------------------------------
@@ -432,7 +477,7 @@ def extract_knots(pred, sparse, valid, max_knots):
     sc = torch.zeros((B, max_knots), dtype=torch.float32, device=dev)
     sh = torch.zeros((B, max_knots), dtype=torch.float32, device=dev)
     cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
-    with _span("extract_knots"):
+    with _span("extract_knots", B * H * W + 20 * B * max_knots):
         rc = _lib.lib().riders_extract_knots(_ptr(pred), _ptr(sparse), _ptr(valid), B, H, W, max_knots,
                                              _ptr(xy), _ptr(sc), _ptr(sh), _ptr(cnt), _stream())
     _lib.check(rc, "riders_extract_knots")
@@ -454,11 +499,11 @@ def interp_linear(knot_xy, knot_val, knot_count, H, W, fill=1.0, want_triangles=
     status = torch.zeros((B,), dtype=torch.int32, device=dev)
     tri = torch.full((B, 2 * max_knots, 3), -1, dtype=torch.int32, device=dev) if want_triangles else None
     tcount = torch.zeros((B,), dtype=torch.int32, device=dev) if want_triangles else None
-    with _span("interp_triangulate"):
+    with _span("interp_triangulate", B * max_knots * (12 + 2 * 48)):
         rc = L.riders_interp_triangulate(_ptr(knot_xy), _ptr(knot_val), _ptr(knot_count), B, max_knots,
                                          _ptr(status), _ptr(tri), _ptr(tcount), _ptr(ws), _stream())
     _lib.check(rc, "riders_interp_triangulate")
-    with _span("interp_fill"):
+    with _span("interp_fill", B * H * W * 4 + B * 2 * max_knots * 48):
         rc = L.riders_interp_fill(B, max_knots, H, W, float(fill), _ptr(out), _ptr(ws), _stream())
     _lib.check(rc, "riders_interp_fill")
     if want_triangles:

@@ -49,8 +49,13 @@ class RadarDepthPipeline(object):
         cap = self.max_knots or max(max(counts), 1)
         xy, scales, _, cnt = ops.extract_knots(int_depth, sparse_inv, valid, cap)
         scale_map, status = ops.interp_linear(xy, scales, cnt, int_depth.shape[-2], int_depth.shape[-1], 1.0)
+        # val_zju.py:171-179 (interp='rcnet_*'): the scaffold the scripts actually feed to the SML network, with the
+        # 16-bit PNG hand-off between run_rcnet_zju.py and val_zju.py applied in memory
+        int_scales, _, scaffold_status = ops.scale_scaffold(int_depth, depth_q, sparse_inv, valid,
+                                                            self.min_depth, self.max_depth, png_quantize=True)
         return {"depth": depth_q, "response": response, "int_depth": int_depth, "scale_shift": scale_shift,
-                "scale_map": scale_map, "interp_status": status, "knot_count": cnt}
+                "scale_map": scale_map, "interp_status": status, "knot_count": cnt,
+                "int_scales": int_scales, "scaffold_status": scaffold_status}
 
     # ------------------------------------------------------------------------------ host
     def _pin(self, name, shape, dtype):
@@ -76,7 +81,7 @@ class RadarDepthPipeline(object):
             dev.append(t.to(device, non_blocking=True))
         out = self.run_device(dev[0], dev[1], list(frame_offsets), dev[2], dev[3])
         host, d2h = {}, 0
-        for k in ("depth", "int_depth", "scale_map", "scale_shift", "interp_status"):
+        for k in ("depth", "int_depth", "scale_map", "int_scales", "scale_shift", "interp_status"):
             h = self._pin(k, out[k].shape, out[k].dtype)
             h.copy_(out[k], non_blocking=True)
             d2h += h.numel() * h.element_size()

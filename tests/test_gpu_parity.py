@@ -394,6 +394,9 @@ def test_pipeline_matches_oracle_chain():
         sm = out["scale_map"][b].cpu().numpy()
         assert np.array_equal(sm[ok] == 1.0, ref["scale_map"][ok] == 1.0)      # exactly fill outside the hull
         np.testing.assert_allclose(sm[ok], ref["scale_map"][ok], rtol=1e-5)     # 1e-5 relative inside
+        from oracle import sml_glue_ref as gr                                   # scaffold of the GPU's own quasi-dense depth
+        assert np.array_equal(out["int_scales"][b].cpu().numpy(),
+                              gr.scale_scaffold_ref(ref["int_depth"], d, ref["sparse_inv"], ref["valid"]))
 
 
 @pytest.mark.parametrize("impl,optimized", [("simt", False), ("tcgen05", False), ("tcgen05", True)])
@@ -537,3 +540,46 @@ def test_conv3x3_head_matches_torch():
     np.testing.assert_allclose(ops.conv3x3_head(big, bias, 0.2, w).cpu().numpy(),
                                torch.nn.functional.conv2d(torch.nn.functional.leaky_relu(big + bias.view(1, -1, 1, 1), 0.2), w, padding=1).cpu().numpy(),
                                rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------ N2/N3 scaffold, N4 metrics
+def test_scale_scaffold_is_bit_exact_with_the_reference_statements():
+    from oracle import sml_glue_ref as gr
+    B, H, W = 3, 96, 128
+    ID, RC, SI, SV = [], [], [], []
+    for b in range(B):
+        rng = np.random.default_rng(300 + b)
+        pred, target, mask = synth.alignment_inputs(30 + b, 60, H, W)
+        int_depth = er.apply_clamp_ref(pred, 0.07, 0.002, 0.1, 255.0)
+        rc = rng.uniform(0.0, 120.0, (H, W)).astype(np.float32)              # some beyond max_depth, dense like A5's output
+        rc[rng.uniform(size=(H, W)) < 0.3] = 0.0                               # uncovered pixels
+        ID.append(int_depth); RC.append(rc); SI.append(target); SV.append(mask)
+    ID, RC, SI, SV = (np.stack(a) for a in (ID, RC, SI, SV))
+    out, minmax, status = ops.scale_scaffold(cu(ID), cu(RC), cu(SI), cu(SV))
+    assert not status.cpu().numpy().any()
+    for b in range(B):
+        ref = gr.scale_scaffold_ref(ID[b], RC[b], SI[b], SV[b])
+        assert np.array_equal(out[b].cpu().numpy(), ref)                       # float32 statements in the same order
+    assert np.array_equal(gr.png_roundtrip_ref(RC[0]), np.floor(RC[0] * 256) / 256)
+    # no RC-Net map (interp without 'rcnet', val_zju.py:175-178) and the zero-range error case
+    out2, _, _ = ops.scale_scaffold(cu(ID), None, cu(SI), cu(SV))
+    assert np.array_equal(out2[1].cpu().numpy(), gr.scale_scaffold_ref(ID[1], None, SI[1], SV[1]))
+    _, _, st = ops.scale_scaffold(cu(ID), None, cu(SI), cu(np.zeros_like(SV)))
+    assert st.cpu().numpy().all()                                              # all ones -> the reference raises ValueError
+
+
+def test_depth_metrics_match_eval_utils():
+    from oracle import sml_glue_ref as gr
+    B, H, W = 4, 120, 160
+    rng = np.random.default_rng(9)
+    gt = rng.uniform(0.5, 80.0, (B, H, W)).astype(np.float32)
+    gt[rng.uniform(size=gt.shape) < 0.9] = 0.0                                  # sparse lidar ground truth
+    pred = (gt * rng.uniform(0.8, 1.3, gt.shape) + rng.uniform(0.1, 1.0, gt.shape)).astype(np.float32)
+    pred[gt == 0] = rng.uniform(1, 50, (gt == 0).sum()).astype(np.float32)
+    got = ops.depth_metrics(cu(pred), cu(gt), 0.0, 50.0).cpu().numpy()
+    for b in range(B):
+        ref = gr.depth_metrics_ref(pred[b], gt[b], 0.0, 50.0)
+        assert got[b, 7] == ref[7]
+        np.testing.assert_allclose(got[b, :7], ref[:7], rtol=2e-6)              # float32 pairwise mean vs fp64 tree
+    again = ops.depth_metrics(cu(pred), cu(gt), 0.0, 50.0)
+    assert torch.equal(again, ops.depth_metrics(cu(pred), cu(gt), 0.0, 50.0))   # deterministic
