@@ -191,12 +191,12 @@ def main():
     def step_device():
         return pipe.run_device(dev["images"], dev["points"], offsets, dev["mono"], dev["sparse"])
 
+    sampler = ClockSampler(local) if rank == 0 else None        # started early: nvidia-smi needs ~0.5 s to deliver samples
     for _ in range(args.warmup):
         out = step_device()
     torch.cuda.synchronize()
 
     # ---------------------------------------------------------------- timed region (device-resident inputs)
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = ops.launch_count()
     rdist.barrier()
     torch.cuda.synchronize()

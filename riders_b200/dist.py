@@ -27,6 +27,7 @@ def init(backend=None):
     Returns (rank, world_size, local_rank).  A 1-process run never creates a group."""
     rank, world, local = env_rank()
     if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout (bench.py prints one JSON line)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         if backend is None:
