@@ -233,6 +233,11 @@ int riders_leaky_concat_nhwc(const float* a, int Ca, const float* b, int Cb, lon
 /* the same with the (BatchNorm-folded) convolution bias added first: out[p][0:Ca] = leaky(a[p][:] + bias[:]) */
 int riders_bias_leaky_concat_nhwc(const float* a, const float* bias, int Ca, const float* b, int Cb,
                                   long long pixels, float slope, float* out, void* stream);
+/* Sub-pixel form of "nearest 2x resize -> 3x3 convolution": y4 (N, 4*Ca, h, w) is the low-resolution convolution
+ * with phase-major output channels ((2a+b)*Ca + c, see DecoderBlock.fold_upsample_); this writes
+ * out (N, Ca+Cb, 2h, 2w): out[n][2i+a][2j+b][0:Ca] = act(y4[n][i][j][(2a+b)*Ca + :] + bias), [Ca:] = skip.   */
+int riders_d2s_bias_act_concat_nhwc(const float* y4, const float* bias, int Ca, const float* skip, int Cb,
+                                    int N, int h, int w, float slope, float* out, void* stream);
 /* Decoder head in front of riders_confidence_reduce: logits (N,H,W) = conv3x3(act(x + bias)), zero padding,
  * x (N,H,W,C=16) channels-last RAW output of the last decoder convolution, weight_host (1,C,3,3) and
  * bias_host (C, or NULL) in HOST memory (they become kernel parameters).  MultiScaleDecoder.output0,

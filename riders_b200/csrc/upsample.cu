@@ -196,3 +196,65 @@ extern "C" int riders_bias_leaky_concat_nhwc(const float* a, const float* bias, 
         Ca / 4, Cb / 4, pixels, slope);
     return check_launch("bias_leaky_concat_nhwc");
 }
+
+// ---------------------------------------------------------------------------------------------
+// Sub-pixel form of "nearest 2x resize -> 3x3 convolution" (decoder blocks whose target size is exactly
+// twice the input: 15x6 -> 30x12, 60x25 -> 120x50, 120x50 -> 240x100 in RC-Net).  With U[r][c] = x[r>>1][c>>1]
+// the 3x3 convolution of U at output pixel (2i+a, 2j+b) only touches x rows {i-1, i, i+1}: it equals a 3x3
+// convolution of x itself with the row taps [W0, W1+W2, 0] (a = 0) or [0, W0+W1, W2] (a = 1), same for columns.
+// So ONE convolution of the low-resolution map with 4*Cout phase-major output channels (built once by
+// DecoderBlock.fold_upsample_) replaces resize + convolution: the 4x larger resized map is never written or read.
+// This kernel is the consumer: out[n][2i+a][2j+b][0:Ca] = act(y4[n][i][j][(2a+b)*Ca + c] + bias[c]), then the skip
+// channels (if any) are appended - depth-to-space + bias + LeakyReLU + concat in one pass.
+// ---------------------------------------------------------------------------------------------
+namespace riders {
+
+__global__ void __launch_bounds__(128)
+d2s_bias_act_concat_kernel(const float4* __restrict__ y4, const float* __restrict__ bias, const float4* __restrict__ skip,
+                           float4* __restrict__ out, int Ca4, int Cb4, int h, int w, float slope, long long rows) {
+    const int Ct4 = Ca4 + Cb4, W2 = 2 * w, H2 = 2 * h;
+    const int len = W2 * Ct4;
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {          // row = n * H2 + Y
+        const int Y = (int)(row % H2);
+        const long long n = row / H2;
+        const int i = Y >> 1, a = Y & 1;
+        const float4* src = y4 + ((size_t)n * h + i) * (size_t)w * (4 * Ca4) + (size_t)(2 * a) * Ca4;
+        const float4* sk = skip ? skip + (size_t)row * W2 * Cb4 : nullptr;
+        float4* dst = out + (size_t)row * len;
+        for (int e = threadIdx.x; e < len; e += 128) {
+            const int X = e / Ct4, c = e - X * Ct4;
+            float4 v;
+            if (c < Ca4) {
+                v = __ldcs(src + (size_t)(X >> 1) * (4 * Ca4) + (X & 1) * Ca4 + c);
+                if (bias) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + c);
+                    v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                }
+                v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+                v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+            } else {
+                v = __ldcs(sk + (size_t)X * Cb4 + (c - Ca4));
+            }
+            dst[e] = v;
+        }
+    }
+}
+
+}  // namespace riders
+
+extern "C" int riders_d2s_bias_act_concat_nhwc(const float* y4, const float* bias, int Ca, const float* skip, int Cb,
+                                               int N, int h, int w, float slope, float* out, void* stream) {
+    using namespace riders;
+    RIDERS_REQUIRE(N >= 0 && Ca > 0 && Cb >= 0 && h > 0 && w > 0, "d2s_bias_act_concat: bad shape");
+    RIDERS_REQUIRE((Ca & 3) == 0 && (Cb & 3) == 0, "d2s_bias_act_concat: channel counts must be multiples of 4 (%d, %d)", Ca, Cb);
+    if (N == 0) return RIDERS_OK;
+    RIDERS_REQUIRE(y4 && out && (skip || Cb == 0), "d2s_bias_act_concat: null pointer");
+    RIDERS_REQUIRE(((((uintptr_t)y4) | ((uintptr_t)skip) | ((uintptr_t)out) | ((uintptr_t)bias)) & 15) == 0, "d2s_bias_act_concat: 16-byte alignment");
+    const long long rows = (long long)N * 2 * h;
+    const long long cap = (long long)sm_count() * 64;
+    count_launches(1);
+    d2s_bias_act_concat_kernel<<<(unsigned)(rows < cap ? rows : cap), 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(y4), bias, reinterpret_cast<const float4*>(skip), reinterpret_cast<float4*>(out),
+        Ca / 4, Cb / 4, h, w, slope, rows);
+    return check_launch("d2s_bias_act_concat_nhwc");
+}

@@ -207,6 +207,27 @@ def bias_act_(x, bias, slope):
     return x
 
 
+def d2s_bias_act_concat(y4, bias, skip, slope=0.2):
+    """Depth-to-space (2x2, phase-major channels) + bias + LeakyReLU (+ concat of ``skip``) in one pass.
+    y4 (N, 4*Ca, h, w) channels_last -> (N, Ca [+ Cb], 2h, 2w) channels_last."""
+    _need_cuda(y4, bias, skip)
+    N, C4, h, w = y4.shape
+    Ca = C4 // 4
+    Cb = skip.shape[1] if skip is not None else 0
+    for t in (y4, skip):
+        if t is not None and not (_is_channels_last(t) and t.dtype == torch.float32 and t.shape[1] % 4 == 0):
+            raise _lib.RidersError("d2s_bias_act_concat needs channels_last float32 maps with C % 4 == 0")
+    if skip is not None and tuple(skip.shape[2:]) != (2 * h, 2 * w):
+        raise ValueError("skip must be (N, Cb, 2h, 2w)")
+    out = torch.empty((N, Ca + Cb, 2 * h, 2 * w), device=y4.device, dtype=torch.float32, memory_format=torch.channels_last)
+    b = _f32c(bias) if bias is not None else None
+    with _span("d2s_bias_act_concat", (y4.numel() + (skip.numel() if skip is not None else 0) + out.numel()) * 4):
+        rc = _lib.lib().riders_d2s_bias_act_concat_nhwc(_ptr(y4), _ptr(b), Ca, _ptr(skip), Cb, N, h, w, float(slope),
+                                                        _ptr(out), _stream())
+    _lib.check(rc, "riders_d2s_bias_act_concat_nhwc")
+    return out
+
+
 _HOST_CACHE = {}
 
 

@@ -159,9 +159,24 @@ class DecoderBlock(torch.nn.Module):
         if deconv_type != 'up':
             raise ValueError("only deconv_type='up' is used by RC-Net (rcnet_model.py:94)")
         self.skip_channels = cskip
+        self._w4 = None                            # sub-pixel weights, built by fold_upsample_()
         self._leaky = act is not None and 'leaky_relu' in act
         self.deconv = UpConv2d(cin, cout, init, act, use_batch_norm)
         self.conv = Conv2d(cskip + cout, cout, 3, 1, init, act, use_batch_norm)
+
+    def fold_upsample_(self):
+        """Inference only, after the BatchNorm fold: weights of the sub-pixel form of 'nearest 2x resize -> 3x3 conv'.
+        Output pixel (2i+a, 2j+b) of conv3x3(resize2x(x)) reads x rows {i-1, i, i+1} with taps [W0, W1+W2, 0] (a = 0) or
+        [0, W0+W1, W2] (a = 1), likewise for columns; the four phases become 4*Cout output channels, phase-major."""
+        c = self.deconv.conv
+        if c.use_batch_norm or not self._leaky or c.conv.kernel_size != (3, 3) or c.conv.out_channels % 4:
+            return self
+        w = c.conv.weight.detach()
+        t = [torch.tensor([[1., 0., 0.], [0., 1., 1.], [0., 0., 0.]], device=w.device, dtype=w.dtype),
+             torch.tensor([[0., 0., 0.], [1., 1., 0.], [0., 0., 1.]], device=w.device, dtype=w.dtype)]
+        w4 = torch.cat([torch.einsum('sk,oikl,tl->oist', t[a], w, t[b]) for a in (0, 1) for b in (0, 1)], dim=0)
+        self._w4 = w4.contiguous(memory_format=torch.channels_last)
+        return self
 
     def forward(self, x, skip=None, shape=None, raw=False):
         """``raw=True`` (inference fast path only): return (conv output without bias/activation, bias, slope)
@@ -170,9 +185,16 @@ class DecoderBlock(torch.nn.Module):
             shape = skip.shape[2:4]
         elif shape is None:
             shape = (2 * x.shape[2], 2 * x.shape[3])
+        up = self.deconv.conv
+        if (self._w4 is not None and tuple(shape) == (2 * x.shape[2], 2 * x.shape[3]) and up.fast_ok(x)
+                and (skip is None or (ops._is_channels_last(skip) and skip.shape[1] % 4 == 0))):
+            # exact 2x block: sub-pixel convolution on the low-resolution map (the resized map never exists),
+            # then depth-to-space + bias + LeakyReLU (+ skip concat) in one pass
+            y4 = F.conv2d(x, self._w4, None, 1, 1)
+            z = ops.d2s_bias_act_concat(y4, up.conv.bias, skip if self.skip_channels > 0 else None, _LEAK)
+            return self.conv.raw(z) if raw else self.conv(z)
         if raw:
             return self.conv.raw(self.deconv(x, shape=shape))
-        up = self.deconv.conv
         if (self.skip_channels > 0 and self._leaky and not up.use_batch_norm and not torch.is_grad_enabled()
                 and x.is_cuda and x.dtype == torch.float32 and ops._is_channels_last(x) and ops._is_channels_last(skip)
                 and x.shape[1] % 4 == 0 and up.conv.out_channels % 4 == 0 and skip.shape[1] % 4 == 0):

@@ -93,7 +93,11 @@ class RCNetModel(object):
             for mod in net.modules():
                 if isinstance(mod, networks.Conv2d):
                     mod.fold_batch_norm_()
-        return self.channels_last()
+        self.channels_last()
+        for mod in self.decoder.modules():
+            if isinstance(mod, networks.DecoderBlock):
+                mod.fold_upsample_()
+        return self
 
     def save_model(self, checkpoint_path, step, optimizer):
         torch.save({

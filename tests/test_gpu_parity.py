@@ -583,3 +583,39 @@ def test_depth_metrics_match_eval_utils():
         np.testing.assert_allclose(got[b, :7], ref[:7], rtol=2e-6)              # float32 pairwise mean vs fp64 tree
     again = ops.depth_metrics(cu(pred), cu(gt), 0.0, 50.0)
     assert torch.equal(again, ops.depth_metrics(cu(pred), cu(gt), 0.0, 50.0))   # deterministic
+
+
+def test_d2s_bias_act_concat_matches_torch():
+    N, Ca, Cb, h, w = 3, 8, 12, 5, 7
+    y4 = torch.randn((N, 4 * Ca, h, w), device=DEV).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(Ca, device=DEV)
+    skip = torch.randn((N, Cb, 2 * h, 2 * w), device=DEV).contiguous(memory_format=torch.channels_last)
+    y = y4.view(N, 2, 2, Ca, h, w).permute(0, 3, 4, 1, 5, 2).reshape(N, Ca, 2 * h, 2 * w)     # channel (2a+b)*Ca + c -> pixel (2i+a, 2j+b)
+    ref = torch.cat([torch.nn.functional.leaky_relu(y + bias.view(1, -1, 1, 1), 0.2), skip], dim=1)
+    got = ops.d2s_bias_act_concat(y4, bias, skip, 0.2)
+    assert got.is_contiguous(memory_format=torch.channels_last) and torch.equal(got, ref)
+    assert torch.equal(ops.d2s_bias_act_concat(y4, bias, None, 0.2), ref[:, :Ca])
+
+
+def test_subpixel_decoder_block_equals_resize_then_conv():
+    """DecoderBlock fast path (exact 2x): sub-pixel convolution == nearest resize + 3x3 convolution (fp32 rounding only)."""
+    from riders_b200.rcnet import networks
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(4)
+    blk = networks.DecoderBlock(32, 16, 16, 'kaiming_uniform', 'leaky_relu', True).to(DEV).eval()
+    with torch.no_grad():
+        for m in blk.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.uniform_(-0.3, 0.3); m.running_var.uniform_(0.5, 1.5); m.weight.uniform_(0.7, 1.3); m.bias.uniform_(-0.2, 0.2)
+    x = torch.randn((4, 32, 15, 6), device=DEV).contiguous(memory_format=torch.channels_last)
+    skip = torch.randn((4, 16, 30, 12), device=DEV).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        ref = blk(x, skip)                                           # reference order: interpolate, conv, BN, act, cat, conv, BN, act
+        for m in blk.modules():
+            if isinstance(m, networks.Conv2d):
+                m.fold_batch_norm_()
+        blk.to(memory_format=torch.channels_last)
+        blk.fold_upsample_()
+        assert blk._w4 is not None and tuple(blk._w4.shape) == (64, 32, 3, 3)
+        got = blk(x, skip)
+    np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=1e-5)
