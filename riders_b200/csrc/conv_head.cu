@@ -40,21 +40,29 @@ conv3x3_head_kernel(const float4* __restrict__ x, float* __restrict__ out, const
     float* o = out + (size_t)n * H * W;
 
     float acc_prev = 0.f, acc_cur = 0.f;                             // sums of output rows h-1 and h
+    // software pipeline: the 64 B of row h+1 are in flight while row h is activated and accumulated
+    float4 nxt[HEAD_C / 4];
+    auto fetch = [&](int h) {
+        const bool ok = col_ok && h >= 0 && h < H;
+        const float4* p = xin + ((size_t)(ok ? h : 0) * W + (ok ? col : 0)) * (HEAD_C / 4);
+#pragma unroll
+        for (int q = 0; q < HEAD_C / 4; ++q) nxt[q] = ok ? __ldcs(p + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        return ok;
+    };
+    bool ok_nxt = fetch(r0 - 1);
     for (int h = r0 - 1; h <= r1; ++h) {
         float a[HEAD_C];
-        if (col_ok && h >= 0 && h < H) {
-            const float4* p = xin + ((size_t)h * W + col) * (HEAD_C / 4);
+        const bool ok = ok_nxt;
 #pragma unroll
-            for (int q = 0; q < HEAD_C / 4; ++q) {
-                const float4 v = __ldcs(p + q);
-                a[4 * q + 0] = v.x + P.bias[4 * q + 0]; a[4 * q + 1] = v.y + P.bias[4 * q + 1];
-                a[4 * q + 2] = v.z + P.bias[4 * q + 2]; a[4 * q + 3] = v.w + P.bias[4 * q + 3];
-            }
+        for (int q = 0; q < HEAD_C / 4; ++q) {
+            a[4 * q + 0] = nxt[q].x + P.bias[4 * q + 0]; a[4 * q + 1] = nxt[q].y + P.bias[4 * q + 1];
+            a[4 * q + 2] = nxt[q].z + P.bias[4 * q + 2]; a[4 * q + 3] = nxt[q].w + P.bias[4 * q + 3];
+        }
+        if (h < r1) ok_nxt = fetch(h + 1);
 #pragma unroll
-            for (int c = 0; c < HEAD_C; ++c) a[c] = a[c] > 0.f ? a[c] : a[c] * P.slope;
-        } else {
-#pragma unroll
-            for (int c = 0; c < HEAD_C; ++c) a[c] = 0.f;             // zero padding of the ACTIVATED map
+        for (int c = 0; c < HEAD_C; ++c) {
+            const float v = a[c] > 0.f ? a[c] : a[c] * P.slope;
+            a[c] = ok ? v : 0.f;                                     // zero padding of the ACTIVATED map
         }
         float t0 = 0.f, t1 = 0.f, t2 = 0.f;                          // contributions to rows h+1 (ky=0), h (ky=1), h-1 (ky=2)
 #pragma unroll

@@ -209,34 +209,46 @@ extern "C" int riders_bias_leaky_concat_nhwc(const float* a, const float* bias, 
 // ---------------------------------------------------------------------------------------------
 namespace riders {
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 d2s_bias_act_concat_kernel(const float4* __restrict__ y4, const float* __restrict__ bias, const float4* __restrict__ skip,
-                           float4* __restrict__ out, int Ca4, int Cb4, int h, int w, float slope, long long rows) {
+                           float4* __restrict__ out, int Ca4, int Cb4, int ct_shift, int h, int w, float slope,
+                           long long rows, int rows_per_block) {
+    // a block streams `rows_per_block` consecutive output rows as one flat run of float4s: (row, position) advance
+    // incrementally, the channel split uses a shift when Ct4 is a power of two (RC-Net: 4, 16, 64)
     const int Ct4 = Ca4 + Cb4, W2 = 2 * w, H2 = 2 * h;
     const int len = W2 * Ct4;
-    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {          // row = n * H2 + Y
-        const int Y = (int)(row % H2);
-        const long long n = row / H2;
-        const int i = Y >> 1, a = Y & 1;
-        const float4* src = y4 + ((size_t)n * h + i) * (size_t)w * (4 * Ca4) + (size_t)(2 * a) * Ca4;
-        const float4* sk = skip ? skip + (size_t)row * W2 * Cb4 : nullptr;
-        float4* dst = out + (size_t)row * len;
-        for (int e = threadIdx.x; e < len; e += 128) {
-            const int X = e / Ct4, c = e - X * Ct4;
-            float4 v;
-            if (c < Ca4) {
-                v = __ldcs(src + (size_t)(X >> 1) * (4 * Ca4) + (X & 1) * Ca4 + c);
-                if (bias) {
-                    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + c);
-                    v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-                }
-                v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
-                v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
-            } else {
-                v = __ldcs(sk + (size_t)X * Cb4 + (c - Ca4));
-            }
-            dst[e] = v;
+    const long long row0 = (long long)blockIdx.x * rows_per_block;
+    const int nrows = (int)min((long long)rows_per_block, rows - row0);
+    int r = 0, pos = threadIdx.x;
+    while (pos >= len) { pos -= len; ++r; }
+    int r_cached = -1;
+    const float4* src = nullptr; const float4* sk = nullptr; float4* dst = nullptr;
+    while (r < nrows) {
+        if (r != r_cached) {                                                  // per-row bases (32-bit row index: rows < 2^31)
+            const unsigned row = (unsigned)(row0 + r);                        // row = n * H2 + Y
+            const unsigned n = row / (unsigned)H2, Y = row - n * (unsigned)H2;
+            src = y4 + (((size_t)n * h + (Y >> 1)) * (size_t)w) * (4 * Ca4) + (2 * (Y & 1)) * Ca4;
+            sk = skip + (size_t)row * W2 * Cb4;
+            dst = out + (size_t)row * len;
+            r_cached = r;
         }
+        const int X = ct_shift >= 0 ? (pos >> ct_shift) : (pos / Ct4);
+        const int c = pos - X * Ct4;
+        float4 v;
+        if (c < Ca4) {
+            v = __ldcs(src + (size_t)(X >> 1) * (4 * Ca4) + (X & 1) * Ca4 + c);
+            if (bias) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + c);
+                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+            }
+            v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+            v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+        } else {
+            v = __ldcs(sk + (size_t)X * Cb4 + (c - Ca4));
+        }
+        dst[pos] = v;
+        pos += 256;
+        while (pos >= len) { pos -= len; ++r; }
     }
 }
 
@@ -251,10 +263,15 @@ extern "C" int riders_d2s_bias_act_concat_nhwc(const float* y4, const float* bia
     RIDERS_REQUIRE(y4 && out && (skip || Cb == 0), "d2s_bias_act_concat: null pointer");
     RIDERS_REQUIRE(((((uintptr_t)y4) | ((uintptr_t)skip) | ((uintptr_t)out) | ((uintptr_t)bias)) & 15) == 0, "d2s_bias_act_concat: 16-byte alignment");
     const long long rows = (long long)N * 2 * h;
-    const long long cap = (long long)sm_count() * 64;
+    const int Ct4 = (Ca + Cb) / 4, len = 2 * w * Ct4;
+    int ct_shift = -1;
+    if ((Ct4 & (Ct4 - 1)) == 0) { ct_shift = 0; while ((1 << ct_shift) < Ct4) ++ct_shift; }
+    const int rows_per_block = len >= 8192 ? 1 : (8192 + len - 1) / len;
+    const long long blocks = (rows + rows_per_block - 1) / rows_per_block;
+    RIDERS_REQUIRE(rows < (1ll << 31), "d2s_bias_act_concat: too many rows for one launch");
     count_launches(1);
-    d2s_bias_act_concat_kernel<<<(unsigned)(rows < cap ? rows : cap), 128, 0, (cudaStream_t)stream>>>(
+    d2s_bias_act_concat_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(y4), bias, reinterpret_cast<const float4*>(skip), reinterpret_cast<float4*>(out),
-        Ca / 4, Cb / 4, h, w, slope, rows);
+        Ca / 4, Cb / 4, ct_shift, h, w, slope, rows, rows_per_block);
     return check_launch("d2s_bias_act_concat_nhwc");
 }

@@ -32,7 +32,7 @@ for MODE in "$@"; do
     launches)
       timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches.csv \
           python bench.py --steps 1 --profile > $OUT/bench_under_ncu.log 2>&1; echo "ncu-launches rc=$?" | tee -a $OUT/status.txt
-      python tools/summarize_launches.py $OUT/launches.csv > $OUT/launches_summary.txt 2>&1; head -40 $OUT/launches_summary.txt
+      python tools/summarize_launches.py $OUT/launches.csv replication_pad > $OUT/launches_summary.txt 2>&1; head -40 $OUT/launches_summary.txt
       gzip -f $OUT/launches.csv ;;
     full:*)
       REGEX=$(echo $MODE | cut -d: -f2); COUNT=$(echo $MODE | cut -d: -f3); NAME=$(echo $REGEX | tr -c 'a-zA-Z0-9\n' '_' | cut -c1-40)

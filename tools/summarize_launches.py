@@ -14,6 +14,12 @@ for r in csv.DictReader(lines):
     unit = r.get("Metric Unit", "ns")
     v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(unit, 1e-3)
     rows.append((r["Kernel Name"], v))
+# optional: keep only the launches from the LAST occurrence of a marker kernel on (e.g. the start of the last step)
+if len(sys.argv) > 2:
+    marks = [i for i, (n, _) in enumerate(rows) if sys.argv[2] in n]
+    if marks:
+        rows = rows[marks[-1]:]
+        print("(from the last '%s' launch on: one step)" % sys.argv[2])
 agg = collections.OrderedDict()
 for name, us in rows:
     short = name.split("(")[0][:90]
