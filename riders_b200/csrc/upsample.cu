@@ -219,36 +219,45 @@ d2s_bias_act_concat_kernel(const float4* __restrict__ y4, const float* __restric
     const int len = W2 * Ct4;
     const long long row0 = (long long)blockIdx.x * rows_per_block;
     const int nrows = (int)min((long long)rows_per_block, rows - row0);
+    // four elements per thread and iteration: all loads are issued before the first store (latency bound otherwise)
     int r = 0, pos = threadIdx.x;
     while (pos >= len) { pos -= len; ++r; }
-    int r_cached = -1;
-    const float4* src = nullptr; const float4* sk = nullptr; float4* dst = nullptr;
     while (r < nrows) {
-        if (r != r_cached) {                                                  // per-row bases (32-bit row index: rows < 2^31)
-            const unsigned row = (unsigned)(row0 + r);                        // row = n * H2 + Y
-            const unsigned n = row / (unsigned)H2, Y = row - n * (unsigned)H2;
-            src = y4 + (((size_t)n * h + (Y >> 1)) * (size_t)w) * (4 * Ca4) + (2 * (Y & 1)) * Ca4;
-            sk = skip + (size_t)row * W2 * Cb4;
-            dst = out + (size_t)row * len;
-            r_cached = r;
-        }
-        const int X = ct_shift >= 0 ? (pos >> ct_shift) : (pos / Ct4);
-        const int c = pos - X * Ct4;
-        float4 v;
-        if (c < Ca4) {
-            v = __ldcs(src + (size_t)(X >> 1) * (4 * Ca4) + (X & 1) * Ca4 + c);
-            if (bias) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + c);
-                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+        float4 v[4];
+        float4* dstp[4];
+        bool act[4];
+        int cc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            dstp[u] = nullptr;
+            if (r < nrows) {
+                const unsigned row = (unsigned)(row0 + r);                    // row = n * H2 + Y (rows < 2^31)
+                const unsigned n = row / (unsigned)H2, Y = row - n * (unsigned)H2;
+                const int X = ct_shift >= 0 ? (pos >> ct_shift) : (pos / Ct4);
+                const int c = pos - X * Ct4;
+                act[u] = c < Ca4;
+                cc[u] = c;
+                v[u] = act[u] ? __ldcs(y4 + (((size_t)n * h + (Y >> 1)) * (size_t)w + (X >> 1)) * (4 * Ca4) + (2 * (Y & 1) + (X & 1)) * Ca4 + c)
+                              : __ldcs(skip + ((size_t)row * W2 + X) * Cb4 + (c - Ca4));
+                dstp[u] = out + (size_t)row * len + pos;
+                pos += 256;
+                while (pos >= len) { pos -= len; ++r; }
             }
-            v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
-            v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
-        } else {
-            v = __ldcs(sk + (size_t)X * Cb4 + (c - Ca4));
         }
-        dst[pos] = v;
-        pos += 256;
-        while (pos >= len) { pos -= len; ++r; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (!dstp[u]) continue;
+            float4 t = v[u];
+            if (act[u]) {
+                if (bias) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + cc[u]);
+                    t.x += bb.x; t.y += bb.y; t.z += bb.z; t.w += bb.w;
+                }
+                t.x = t.x > 0.f ? t.x : t.x * slope; t.y = t.y > 0.f ? t.y : t.y * slope;
+                t.z = t.z > 0.f ? t.z : t.z * slope; t.w = t.w > 0.f ? t.w : t.w * slope;
+            }
+            *dstp[u] = t;
+        }
     }
 }
 

@@ -26,6 +26,10 @@ for MODE in "$@"; do
     trace)
       timeout -s KILL 300 python tools/loftr_trace.py 2048 > $OUT/loftr_trace.txt 2>&1; echo "trace rc=$?" | tee -a $OUT/status.txt
       cat $OUT/loftr_trace.txt ;;
+    micro:*)
+      WHICH=$(echo $MODE | cut -d: -f2 | tr ',' ' ')
+      timeout -s KILL 600 python tools/microbench.py $WHICH > $OUT/microbench_part.jsonl 2> $OUT/microbench_part.err; echo "microbench($WHICH) rc=$?" | tee -a $OUT/status.txt
+      cat $OUT/microbench_part.jsonl ;;
     micro)
       timeout -s KILL 600 python tools/microbench.py > $OUT/microbench.jsonl 2> $OUT/microbench.err; echo "microbench rc=$?" | tee -a $OUT/status.txt
       cat $OUT/microbench.jsonl ;;

@@ -92,6 +92,31 @@ def bench_gather(B=2, K=512, patch=(240, 100)):
                          ("nhwc_tma", [f.contiguous(memory_format=torch.channels_last) for f in feats], (100, 240))):
         ms, best = timeit(lambda: ops.roi_gather(fs, rois, scales, sizes, max_roi=mr), iters=5)
         report("roi_gather_" + name, ms, best, nbytes, B=B, K=K)
+    # staging budget sweep of the TMA path (riders_debug_set knob): smaller strips -> more CTAs per SM
+    from riders_b200 import _lib
+    fs = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+    for kb in (24, 36, 48, 56, 72, 100):
+        _lib.lib().riders_debug_set(b"gather_smem_kb", kb)
+        ms, best = timeit(lambda: ops.roi_gather(fs, rois, scales, sizes, max_roi=(100, 240)), iters=5)
+        report("roi_gather_nhwc_tma_smem%dk" % kb, ms, best, nbytes, B=B, K=K)
+    _lib.lib().riders_debug_set(b"gather_smem_kb", 72)
+
+
+def bench_glue(R=2048):
+    """Decoder glue kernels at RC-Net's largest shapes (per chunk of 2048 points)."""
+    x = torch.randn((R, 32, 120, 50), device=DEV).contiguous(memory_format=torch.channels_last)
+    ms, best = timeit(lambda: ops.upsample_nearest(x, (240, 100)), iters=5)
+    report("upsample_nearest_32ch_240x100", ms, best, x.numel() * 4 * 5, R=R)
+    y4 = torch.randn((R, 64, 120, 50), device=DEV).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(16, device=DEV)
+    ms, best = timeit(lambda: ops.d2s_bias_act_concat(y4, bias, None, 0.2), iters=5)
+    report("d2s_bias_act_16ch_240x100", ms, best, y4.numel() * 4 * 2, R=R)
+    z = torch.randn((R, 16, 240, 100), device=DEV).contiguous(memory_format=torch.channels_last)
+    w = torch.randn((1, 16, 3, 3), device=DEV) * 0.1
+    ms, best = timeit(lambda: ops.conv3x3_head(z, bias, 0.2, w), iters=5)
+    report("conv3x3_head_16ch_240x100", ms, best, z.numel() * 4 + R * 24000 * 4, R=R)
+    ms, best = timeit(lambda: ops.bias_act_(z, bias, 0.2), iters=5)
+    report("bias_act_16ch_240x100", ms, best, z.numel() * 8, R=R)
 
 
 def bench_loftr(N=4096):
@@ -130,7 +155,7 @@ def bench_interp(B=64, K=512, H=512, W=640):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["reduce", "lsq", "gather", "loftr", "interp"]
+    which = sys.argv[1:] or ["reduce", "lsq", "gather", "loftr", "interp", "glue"]
     torch.cuda.set_device(DEV)
     print(json.dumps({"gpu": torch.cuda.get_device_name(0), "hbm_peak_gbs": HBM}), flush=True)
     with torch.no_grad():
