@@ -376,7 +376,7 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-static int g_tma_smem_budget = 72 * 1024;     // per CTA -> 3 CTAs per SM (tunable: riders_debug_set("gather_smem_kb", v))
+static int g_tma_smem_budget = 48 * 1024;     // per CTA -> 4 CTAs per SM; measured best of {24..100} KB (tunable: riders_debug_set("gather_smem_kb", v))
 
 void set_gather_smem_budget(int kb) { if (kb >= 16 && kb <= 200) g_tma_smem_budget = kb * 1024; }
 

@@ -99,7 +99,7 @@ def bench_gather(B=2, K=512, patch=(240, 100)):
         _lib.lib().riders_debug_set(b"gather_smem_kb", kb)
         ms, best = timeit(lambda: ops.roi_gather(fs, rois, scales, sizes, max_roi=(100, 240)), iters=5)
         report("roi_gather_nhwc_tma_smem%dk" % kb, ms, best, nbytes, B=B, K=K)
-    _lib.lib().riders_debug_set(b"gather_smem_kb", 72)
+    _lib.lib().riders_debug_set(b"gather_smem_kb", 48)
 
 
 def bench_glue(R=2048):
