@@ -173,6 +173,31 @@ def roi_gather_bwd(grad_outs, argmaxes, feat_shapes, boxes, scales, nhwc):
     return grads
 
 
+class RoiGatherFunction(torch.autograd.Function):
+    """Differentiable multi-level gather for RC-Net training (rcnet_main.py:342-358): forward records the
+    argmax of every bin, backward is the deterministic (atomic-free) scatter of riders_roi_gather_bwd."""
+
+    @staticmethod
+    def forward(ctx, rois, scales, out_sizes, *feats):
+        outs, args = roi_gather(list(feats), rois, scales, out_sizes, want_argmax=True)
+        ctx.save_for_backward(rois, *args)
+        ctx.meta = (tuple(scales), [tuple(f.shape) for f in feats], all(_is_channels_last(f) for f in feats))
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grad_outs):
+        rois, args = ctx.saved_tensors[0], list(ctx.saved_tensors[1:])
+        scales, shapes, nhwc = ctx.meta
+        grads = roi_gather_bwd(list(grad_outs), args, shapes, rois, scales, nhwc)
+        return (None, None, None) + tuple(grads)
+
+
+def roi_gather_autograd(feats, boxes, scales, out_sizes):
+    """roi_gather with gradients w.r.t. the feature maps (training path)."""
+    rois = boxes_to_rois(boxes, feats[0].device)
+    return list(RoiGatherFunction.apply(rois, tuple(float(s) for s in scales), tuple(tuple(o) for o in out_sizes), *feats))
+
+
 def roi_pool(input, boxes, output_size, spatial_scale=1.0):
     """Drop-in for ``torchvision.ops.roi_pool`` (single level)."""
     if isinstance(output_size, int):

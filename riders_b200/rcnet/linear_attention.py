@@ -66,8 +66,28 @@ class LoFTREncoderLayer(nn.Module):
             return impl == ops.LOFTR_SIMT
         return ops.loftr_impl_available(impl, x.shape[2], self.nhead, x.shape[1])
 
+    def _forward_autograd(self, x, source):
+        """Training path (rcnet_main.py:342-358 needs gradients): the layer as differentiable torch ops on the
+        device, statement for statement linear_attention.py:112-135 / 18-45.  The fused kernels are inference-only."""
+        bs = x.size(0)
+        q = self.q_proj(x).view(bs, -1, self.nhead, self.dim)
+        k = self.k_proj(source).view(bs, -1, self.nhead, self.dim)
+        v = self.v_proj(source).view(bs, -1, self.nhead, self.dim)
+        Q, K = torch.nn.functional.elu(q) + 1, torch.nn.functional.elu(k) + 1
+        v_length = v.size(1)
+        v = v / v_length
+        KV = torch.einsum("nshd,nshv->nhdv", K, v)
+        Z = 1 / (torch.einsum("nlhd,nhd->nlh", Q, K.sum(dim=1)) + self.attention.eps)
+        message = (torch.einsum("nlhd,nhdv,nlh->nlhv", Q, KV, Z) * v_length).contiguous()
+        message = self.norm1(self.merge(message.view(bs, -1, self.nhead * self.dim)))
+        message = self.norm2(self.mlp(torch.cat([x, message], dim=2)))
+        return x + message
+
     def forward(self, x, source, x_mask=None, source_mask=None):
         """x [N,L,C], source [N,S,C] -> [N,L,C]."""
+        if torch.is_grad_enabled() and x_mask is None and source_mask is None and \
+                (x.requires_grad or source.requires_grad or self.q_proj.weight.requires_grad):
+            return self._forward_autograd(x, source)
         if x_mask is not None or source_mask is not None:
             # masked call (never issued by RC-Net, networks.py:444): compose from the kernels
             bs = x.size(0)
@@ -113,6 +133,18 @@ class LocalFeatureTransformer(nn.Module):
                 elif name == 'cross':
                     feat0 = layer(feat0, feat1, mask0, mask1)
                     feat1 = layer(feat1, feat0, mask1, mask0)
+                else:
+                    raise KeyError
+            return feat0, feat1
+        if torch.is_grad_enabled() and (feat0.requires_grad or feat1.requires_grad or
+                                        self.layers[0].q_proj.weight.requires_grad):
+            for layer, name in zip(self.layers, self.layer_names):            # training: differentiable torch ops
+                if name == 'self':
+                    feat0 = layer(feat0, feat0)
+                    feat1 = layer(feat1, feat1)
+                elif name == 'cross':
+                    feat0 = layer(feat0, feat1)
+                    feat1 = layer(feat1, feat0)
                 else:
                     raise KeyError
             return feat0, feat1

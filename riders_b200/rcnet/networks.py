@@ -322,8 +322,11 @@ class RCNetEncoder(torch.nn.Module):
         levels = self.pyramid(len(skips_image))
         ph, pw = self.input_patch_size_image[-2], self.input_patch_size_image[-1]
         # one call for all levels (replaces the five roi_pool calls, networks.py:418-433)
-        pooled = ops.roi_gather(list(skips_image) + [latent_image], b_boxes,
-                                [s for s, _ in levels], [o for _, o in levels], max_roi=(pw, ph))
+        feats = list(skips_image) + [latent_image]
+        if torch.is_grad_enabled() and any(f.requires_grad for f in feats):
+            pooled = ops.roi_gather_autograd(feats, b_boxes, [s for s, _ in levels], [o for _, o in levels])   # training
+        else:
+            pooled = ops.roi_gather(feats, b_boxes, [s for s, _ in levels], [o for _, o in levels], max_roi=(pw, ph))
         skips_pooled, latent_pooled = pooled[:-1], pooled[-1]
 
         n, c = points.shape[0], self.n_neuron_latent_depth

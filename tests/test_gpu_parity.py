@@ -619,3 +619,40 @@ def test_subpixel_decoder_block_equals_resize_then_conv():
         assert blk._w4 is not None and tuple(blk._w4.shape) == (64, 32, 3, 3)
         got = blk(x, skip)
     np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------ config 4: training step
+def test_training_step_gradients_match_the_reference_path():
+    """rcnet_main.train's inner step (forward with logits, masked BCE, backward) through the mirror on the GPU
+    (deterministic gather backward + differentiable LoFTR) against the oracle path (torchvision roi_pool) on the CPU."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    patch, K = (64, 32), 8
+    cpu = _rand_model("cpu", patch, [8, 16, 16, 16, 16], [32, 16, 16, 8, 8], seed=5)
+    gpu = _to_cuda(cpu)
+    cpu.train(); gpu.train()
+    fr = synth.chain_frame(11, K, 96, 128, patch)
+    padded = torch.nn.functional.pad(torch.from_numpy(fr["image"])[None], (16, 16, 32, 32), mode="replicate")
+    pts, boxes = torch.from_numpy(fr["points"]), torch.from_numpy(fr["boxes"])
+    rng = np.random.default_rng(0)
+    gt = torch.from_numpy((rng.uniform(size=(K, 1) + patch) > 0.6).astype(np.float32))
+    valid = torch.from_numpy((rng.uniform(size=(K, 1) + patch) > 0.2).astype(np.float32))
+    # reference path on the CPU with autograd (oracle functions without their no_grad decorators)
+    latent, skips = rcnet_ref.encoder_forward_ref.__wrapped__(cpu.encoder, padded, pts, [boxes])
+    logits_ref = cpu.decoder(x=latent, skips=skips, shape=cpu.input_patch_size_image)[-1]
+    loss_ref, _ = cpu.compute_loss(logits_ref, gt, valid, w_positive_class=2.5)
+    loss_ref.backward()
+    logits = gpu.forward(padded.to(DEV), pts.to(DEV), [boxes.to(DEV)], return_logits=True)
+    loss, _ = gpu.compute_loss(logits, gt.to(DEV), valid.to(DEV), w_positive_class=2.5)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), loss_ref.item(), rtol=1e-5)
+    checked = 0
+    for (name, pc), pg in zip(list(cpu.encoder.named_parameters()) + list(cpu.decoder.named_parameters()),
+                              list(gpu.encoder.parameters()) + list(gpu.decoder.parameters())):
+        if pc.grad is None:
+            assert pg.grad is None or float(pg.grad.abs().max()) == 0.0, name
+            continue
+        scale = float(pc.grad.abs().max()) + 1e-12
+        assert float((pg.grad.cpu() - pc.grad).abs().max()) <= 2e-4 * scale + 1e-7, name
+        checked += 1
+    assert checked > 50
