@@ -21,6 +21,7 @@ constexpr int TILE_H = 32;
 constexpr int ROWS_PER_THREAD = 4;
 constexpr int CR_THREADS = 256;
 constexpr int CHUNK = 256;                 // candidate points examined per round
+constexpr int NC = 4;                      // candidates gathered per inner iteration (16 loads in flight per thread)
 
 struct Cand { int r0; int c0; float z; int k; };
 
@@ -115,32 +116,28 @@ confidence_reduce_kernel(const float* __restrict__ conf, const float* __restrict
         __syncthreads();
         const int n = n_cand;
 
-        // ---- gather: two candidates per iteration -> 8 independent loads in flight per thread ----
+        // ---- gather: NC candidates per iteration -> NC * 4 independent loads in flight per thread ----
         // A pixel the crop does not cover contributes v = 0, which leaves max / sums bit-identical.
-        for (int i = 0; i < n; i += 2) {
-            const bool has1 = i + 1 < n;
-            const Cand q0 = cand[i];                   // smem broadcast
-            const Cand q1 = cand[has1 ? i + 1 : i];
-            float v0[ROWS_PER_THREAD], v1[ROWS_PER_THREAD];
-            const unsigned m0 = load_candidate(conf, q0, true, first_point, crop, col, row, ph, pw, v0);
-            const unsigned m1 = load_candidate(conf, q1, has1, first_point, crop, col, row, ph, pw, v1);
+        for (int i = 0; i < n; i += NC) {
+            Cand q[NC];
+            float v[NC][ROWS_PER_THREAD];
+            unsigned msk[NC];
 #pragma unroll
-            for (int m = 0; m < ROWS_PER_THREAD; ++m) {
-                const float c0 = conf_value<LOGITS>(v0[m], thr), c1 = conf_value<LOGITS>(v1[m], thr);   // branch-free
-                v0[m] = (m0 >> m) & 1u ? c0 : 0.0f;
-                v1[m] = (m1 >> m) & 1u ? c1 : 0.0f;
+            for (int u = 0; u < NC; ++u) {
+                const bool on = i + u < n;
+                q[u] = cand[on ? i + u : i];           // smem broadcast
+                msk[u] = load_candidate(conf, q[u], on, first_point, crop, col, row, ph, pw, v[u]);
             }
 #pragma unroll
-            for (int m = 0; m < ROWS_PER_THREAD; ++m) {
-                if (v0[m] > best[m]) { best[m] = v0[m]; arg[m] = q0.k; }   // first max wins
-                sc[m] = __fadd_rn(sc[m], v0[m]);
-                scz[m] = __fadd_rn(scz[m], __fmul_rn(v0[m], q0.z));       // (tile*z) then sum, rcnet_main.py:478
-            }
+            for (int u = 0; u < NC; ++u) {             // in candidate (= point) order: float sums as in the reference
 #pragma unroll
-            for (int m = 0; m < ROWS_PER_THREAD; ++m) {
-                if (v1[m] > best[m]) { best[m] = v1[m]; arg[m] = q1.k; }
-                sc[m] = __fadd_rn(sc[m], v1[m]);
-                scz[m] = __fadd_rn(scz[m], __fmul_rn(v1[m], q1.z));
+                for (int m = 0; m < ROWS_PER_THREAD; ++m) {
+                    const float c = conf_value<LOGITS>(v[u][m], thr);          // branch-free
+                    const float x = (msk[u] >> m) & 1u ? c : 0.0f;
+                    if (x > best[m]) { best[m] = x; arg[m] = q[u].k; }          // first max wins
+                    sc[m] = __fadd_rn(sc[m], x);
+                    scz[m] = __fadd_rn(scz[m], __fmul_rn(x, q[u].z));           // (tile*z) then sum, rcnet_main.py:478
+                }
             }
         }
     }

@@ -23,6 +23,9 @@ for MODE in "$@"; do
     benchsimt)
       RIDERS_LOFTR_IMPL=simt timeout -s KILL 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_simt.json 2> $OUT/bench_simt.err; echo "bench-simt rc=$?" | tee -a $OUT/status.txt
       tail -c 1500 $OUT/bench_simt.json ;;
+    stress)
+      timeout -s KILL 600 python tools/stress_sweep.py > $OUT/stress_sweep.jsonl 2> $OUT/stress_sweep.err; echo "stress rc=$?" | tee -a $OUT/status.txt
+      cat $OUT/stress_sweep.jsonl; tail -3 $OUT/stress_sweep.err ;;
     trace)
       timeout -s KILL 300 python tools/loftr_trace.py 2048 > $OUT/loftr_trace.txt 2>&1; echo "trace rc=$?" | tee -a $OUT/status.txt
       cat $OUT/loftr_trace.txt ;;
