@@ -17,60 +17,54 @@
 namespace riders {
 
 constexpr int TILE_W = 32;
-constexpr int TILE_H = 32;
-constexpr int ROWS_PER_THREAD = 4;
 constexpr int CR_THREADS = 256;
 constexpr int CHUNK = 256;                 // candidate points examined per round
-constexpr int NC = 2;                      // candidates gathered per inner iteration (8 loads in flight per thread; 4 measured slower)
+constexpr int NC = 2;                      // candidates gathered per inner iteration (4 measured slower)
 
-struct Cand { int r0; int c0; float z; int k; };
+// base = address of crop pixel (0, 0) shifted so that base + row * pw + col addresses the crop pixel under frame
+// pixel (row, col): one 64-bit add per candidate and thread instead of re-deriving (i, j) offsets
+struct Cand { const float* base; int r0; int c0; float z; int k; };
 
 template <bool LOGITS>
 __device__ __forceinline__ float conf_value(float v, float thr) {
     // torch.sigmoid (rcnet_model.py:123): 1 / (1 + exp(-v)) with the SFU exp2 / reciprocal (relative
-    // error ~2e-7, far inside the 1e-4 tolerance on confidences); strict < (rcnet_main.py:462)
+    // error ~2e-7, far inside the 1e-4 tolerance on confidences); strict < (rcnet_main.py:462).
+    // A pixel the crop does not cover is loaded as 0 (confidences) / -inf (logits) -> contributes exactly 0.
     if (LOGITS) v = __fdividef(1.0f, 1.0f + __expf(-v));
     return (v < thr) ? 0.0f : v;
 }
 
-// predicated streaming load (no branch around it, so the 8 loads of an iteration issue back to back)
+// predicated streaming load (no branch around it, so the loads of an iteration issue back to back)
+template <bool LOGITS>
 __device__ __forceinline__ float ld_stream_if(const float* p, bool on) {
     float v;
-    asm volatile(
-        "{\n"
-        ".reg .pred q;\n"
-        "setp.ne.b32 q, %2, 0;\n"
-        "mov.f32 %0, 0f00000000;\n"
-        "@q ld.global.nc.L1::no_allocate.f32 %0, [%1];\n"
-        "}\n" : "=f"(v) : "l"(p), "r"((int)on));
+    if (LOGITS)
+        asm volatile(
+            "{\n"
+            ".reg .pred q;\n"
+            "setp.ne.b32 q, %2, 0;\n"
+            "mov.f32 %0, 0fFF800000;\n"
+            "@q ld.global.nc.L1::no_allocate.f32 %0, [%1];\n"
+            "}\n" : "=f"(v) : "l"(p), "r"((int)on));
+    else
+        asm volatile(
+            "{\n"
+            ".reg .pred q;\n"
+            "setp.ne.b32 q, %2, 0;\n"
+            "mov.f32 %0, 0f00000000;\n"
+            "@q ld.global.nc.L1::no_allocate.f32 %0, [%1];\n"
+            "}\n" : "=f"(v) : "l"(p), "r"((int)on));
     return v;
 }
 
-// raw values of the 4 vertically stacked crop pixels of candidate q under this thread + their coverage mask
-__device__ __forceinline__ unsigned load_candidate(const float* __restrict__ conf, const Cand& q, bool on, int first_point,
-                                                   size_t crop, int col, int row, int ph, int pw,
-                                                   float (&v)[ROWS_PER_THREAD]) {
-    const int j = col - q.c0;
-    const int i0 = row - q.r0;
-    const bool in_col = on && (unsigned)j < (unsigned)pw;
-    const float* src = conf + (size_t)(first_point + q.k) * crop + (ptrdiff_t)i0 * pw + j;
-    unsigned mask = 0;
-#pragma unroll
-    for (int m = 0; m < ROWS_PER_THREAD; ++m) {
-        const bool in = in_col && (unsigned)(i0 + m) < (unsigned)ph;
-        v[m] = ld_stream_if(src + m * pw, in);
-        mask |= in ? (1u << m) : 0u;
-    }
-    return mask;
-}
-
-template <bool LOGITS>
+template <bool LOGITS, int ROWS>
 __global__ void __launch_bounds__(CR_THREADS)
 confidence_reduce_kernel(const float* __restrict__ conf, const float* __restrict__ pts,
                          const int* __restrict__ frame_offsets,
                          int H, int W, int ph, int pw, float thr,
                          float* __restrict__ depth, float* __restrict__ response,
                          int32_t* __restrict__ select) {
+    constexpr int TILE_H = (CR_THREADS / 32) * ROWS;
     __shared__ Cand cand[CHUNK];
     __shared__ int warp_count[CR_THREADS / 32];
     __shared__ int n_cand;
@@ -82,12 +76,13 @@ confidence_reduce_kernel(const float* __restrict__ conf, const float* __restrict
     const size_t frame_px = (size_t)frame * H * W;
     const int tile_c = blockIdx.x * TILE_W, tile_r = blockIdx.y * TILE_H;
     const int col = tile_c + lane;
-    const int row = tile_r + warp * ROWS_PER_THREAD;
+    const int row = tile_r + warp * ROWS;
+    const ptrdiff_t thr_off = (ptrdiff_t)row * pw + col;
 
-    float best[ROWS_PER_THREAD], sc[ROWS_PER_THREAD], scz[ROWS_PER_THREAD];
-    int arg[ROWS_PER_THREAD];
+    float best[ROWS], sc[ROWS], scz[ROWS];
+    int arg[ROWS];
 #pragma unroll
-    for (int m = 0; m < ROWS_PER_THREAD; ++m) { best[m] = 0.f; sc[m] = 0.f; scz[m] = 0.f; arg[m] = 0; }
+    for (int m = 0; m < ROWS; ++m) { best[m] = 0.f; sc[m] = 0.f; scz[m] = 0.f; arg[m] = 0; }
 
     const size_t crop = (size_t)ph * pw;
 
@@ -102,6 +97,7 @@ confidence_reduce_kernel(const float* __restrict__ conf, const float* __restrict
             c.r0 = (int)p[1] - ph;
             c.z = p[2];
             c.k = k;
+            c.base = conf + (size_t)(first_point + k) * crop - ((ptrdiff_t)c.r0 * pw + c.c0);
             hit = (c.r0 < tile_r + TILE_H) && (c.r0 + ph > tile_r) &&
                   (c.c0 < tile_c + TILE_W) && (c.c0 + pw > tile_c);
         }
@@ -116,24 +112,34 @@ confidence_reduce_kernel(const float* __restrict__ conf, const float* __restrict
         __syncthreads();
         const int n = n_cand;
 
-        // ---- gather: NC candidates per iteration -> NC * 4 independent loads in flight per thread ----
-        // A pixel the crop does not cover contributes v = 0, which leaves max / sums bit-identical.
+        // ---- gather: NC candidates per iteration, in point order (float sums as in the reference) ----
         for (int i = 0; i < n; i += NC) {
             Cand q[NC];
-            float v[NC][ROWS_PER_THREAD];
-            unsigned msk[NC];
+            float v[NC][ROWS];
+            bool any[NC];
 #pragma unroll
             for (int u = 0; u < NC; ++u) {
                 const bool on = i + u < n;
                 q[u] = cand[on ? i + u : i];           // smem broadcast
-                msk[u] = load_candidate(conf, q[u], on, first_point, crop, col, row, ph, pw, v[u]);
+                const int i0 = row - q[u].r0;          // warp-uniform
+                const bool in_col = on && (unsigned)(col - q[u].c0) < (unsigned)pw;
+                const float* src = q[u].base + thr_off;
+                any[u] = on && i0 + ROWS > 0 && i0 < ph;
+                if (i0 >= 0 && i0 + ROWS <= ph) {      // the usual case: all ROWS rows inside the 240-row crop
+#pragma unroll
+                    for (int m = 0; m < ROWS; ++m) v[u][m] = ld_stream_if<LOGITS>(src + m * pw, in_col);
+                } else {
+#pragma unroll
+                    for (int m = 0; m < ROWS; ++m)
+                        v[u][m] = ld_stream_if<LOGITS>(src + m * pw, in_col && (unsigned)(i0 + m) < (unsigned)ph);
+                }
             }
 #pragma unroll
-            for (int u = 0; u < NC; ++u) {             // in candidate (= point) order: float sums as in the reference
+            for (int u = 0; u < NC; ++u) {
+                if (!any[u]) continue;                 // warp-uniform: this warp's rows miss the crop
 #pragma unroll
-                for (int m = 0; m < ROWS_PER_THREAD; ++m) {
-                    const float c = conf_value<LOGITS>(v[u][m], thr);          // branch-free
-                    const float x = (msk[u] >> m) & 1u ? c : 0.0f;
+                for (int m = 0; m < ROWS; ++m) {
+                    const float x = conf_value<LOGITS>(v[u][m], thr);
                     if (x > best[m]) { best[m] = x; arg[m] = q[u].k; }          // first max wins
                     sc[m] = __fadd_rn(sc[m], x);
                     scz[m] = __fadd_rn(scz[m], __fmul_rn(x, q[u].z));           // (tile*z) then sum, rcnet_main.py:478
@@ -144,7 +150,7 @@ confidence_reduce_kernel(const float* __restrict__ conf, const float* __restrict
 
     if (col < W) {
 #pragma unroll
-        for (int m = 0; m < ROWS_PER_THREAD; ++m) {
+        for (int m = 0; m < ROWS; ++m) {
             const int r = row + m;
             if (r < H) {
                 const size_t o = frame_px + (size_t)r * W + col;
@@ -154,6 +160,16 @@ confidence_reduce_kernel(const float* __restrict__ conf, const float* __restrict
             }
         }
     }
+}
+
+static int g_reduce_rows = 4;
+void set_reduce_rows(int rows) { if (rows == 4 || rows == 8) g_reduce_rows = rows; }
+
+template <bool LOGITS, int ROWS>
+static void launch_reduce(const float* conf, const float* pts, const int* frame_offsets, int B, int H, int W, int ph, int pw,
+                          float thr, float* depth, float* response, int32_t* select, cudaStream_t st) {
+    dim3 grid(ceil_div(W, TILE_W), ceil_div(H, (CR_THREADS / 32) * ROWS), B);
+    confidence_reduce_kernel<LOGITS, ROWS><<<grid, CR_THREADS, 0, st>>>(conf, pts, frame_offsets, H, W, ph, pw, thr, depth, response, select);
 }
 
 }  // namespace riders
@@ -170,11 +186,13 @@ extern "C" int riders_confidence_reduce(const float* conf, int conf_is_logits,
     RIDERS_REQUIRE((ph % 2 == 0) && (pw % 2 == 0), "confidence_reduce: patch size must be even (got %dx%d)", ph, pw);
     if (B == 0) return RIDERS_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid(ceil_div(W, TILE_W), ceil_div(H, TILE_H), B);
     count_launches(1);
-    if (conf_is_logits)
-        confidence_reduce_kernel<true><<<grid, CR_THREADS, 0, st>>>(conf, pts, frame_offsets, H, W, ph, pw, thr, depth, response, select);
-    else
-        confidence_reduce_kernel<false><<<grid, CR_THREADS, 0, st>>>(conf, pts, frame_offsets, H, W, ph, pw, thr, depth, response, select);
+    if (g_reduce_rows == 8) {
+        if (conf_is_logits) launch_reduce<true, 8>(conf, pts, frame_offsets, B, H, W, ph, pw, thr, depth, response, select, st);
+        else launch_reduce<false, 8>(conf, pts, frame_offsets, B, H, W, ph, pw, thr, depth, response, select, st);
+    } else {
+        if (conf_is_logits) launch_reduce<true, 4>(conf, pts, frame_offsets, B, H, W, ph, pw, thr, depth, response, select, st);
+        else launch_reduce<false, 4>(conf, pts, frame_offsets, B, H, W, ph, pw, thr, depth, response, select, st);
+    }
     return check_launch("confidence_reduce");
 }

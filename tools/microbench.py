@@ -59,9 +59,13 @@ def bench_reduce(B=16, K=512, H=512, W=640, patch=(240, 100)):
     pts = torch.cat([torch.from_numpy(synth.radar_points(f, K, H, W, patch)[0]) for f in range(B)]).to(DEV)
     offs = torch.arange(0, B * K + 1, K, dtype=torch.int32, device=DEV)
     nbytes = B * (K * patch[0] * patch[1] * 4 + 12 * K + 3 * H * W * 4)
-    for logits in (False, True):
-        ms, best = timeit(lambda: ops.confidence_reduce(conf, pts, offs, H, W, 0.1, logits=logits))
-        report("confidence_reduce" + ("_logits" if logits else ""), ms, best, nbytes, B=B, K=K)
+    from riders_b200 import _lib
+    for rows in (4, 8):
+        _lib.lib().riders_debug_set(b"reduce_rows", rows)
+        for logits in (False, True):
+            ms, best = timeit(lambda: ops.confidence_reduce(conf, pts, offs, H, W, 0.1, logits=logits))
+            report("confidence_reduce" + ("_logits" if logits else "") + "_rows%d" % rows, ms, best, nbytes, B=B, K=K)
+    _lib.lib().riders_debug_set(b"reduce_rows", 4)
 
 
 def bench_lsq(B=64, H=512, W=640, K=512):
