@@ -93,7 +93,7 @@ int riders_linear_attention_fwd(const float* q, const float* k, const float* v,
  *       wq,wk,wv,wm (C,C); w1 (2C,2C); w2 (C,2C); LayerNorm gamma/beta (C).
  *     impl: RIDERS_LOFTR_SIMT    fp32 FFMA kernels (any C%16==0), bit-for-bit fp32 semantics
  *           RIDERS_LOFTR_TCGEN05 fused tensor-core layer (C=128, nhead=8, L=S=21 tokens):
- *                                tcgen05.mma kind::tf32 with a 3-term hi/lo split (fp32-accurate)
+ *                                tcgen05.mma kind::f16 with a 2-term fp16 hi/lo operand split, 3 MMAs (fp32-accurate)
  *     workspace: riders_loftr_workspace_bytes(N, max(L,S), C, impl) bytes, 256-byte aligned.
  * ------------------------------------------------------------------------------------------ */
 #define RIDERS_LOFTR_SIMT     0
@@ -252,7 +252,7 @@ int riders_bias_act_nhwc(const float* x, const float* bias, int C, long long pix
 
 /* ------------------------------------------------------------------------------------------
  * Diagnostics.  riders_debug_tc_gemm: D (128,128) = A (128,K) * B (128,K)^T on the tcgen05 path
- * (K = 32 or 64; terms = 1 plain tf32, 3 = hi/lo split) through the same operand staging,
+ * (K = 64 or 128; terms = 1 plain fp16, 3 = hi/lo split) through the same operand staging,
  * descriptors and TMEM read-back as the fused LoFTR layer - a device self-test of that plumbing.
  * ------------------------------------------------------------------------------------------ */
 /* tuning knobs for experiments (not part of the drop-in surface): "gather_smem_kb" = TMA staging budget per CTA */
@@ -260,6 +260,8 @@ int riders_debug_set(const char* key, int value);
 /* phase timestamps (clock64) of the first tile of two CTAs of the next tcgen05 LoFTR launches; NULL disables */
 int riders_debug_loftr_trace(long long* device_buffer_256);
 int riders_debug_tc_gemm(const float* a, const float* b, float* d, int K, int terms, void* stream);
+/* MMA issue-rate probe (tools/mma_rate.py): mode = N code | accumulators << 4 | tf32 << 8; cycles per CTA. */
+int riders_debug_tc_mma_rate(int mode, int count, int ctas, long long* device_cycles, void* stream);
 
 /* the two halves of riders_interp_linear, callable (and timeable) separately: the triangulation is
  * latency bound (pointer chasing), the fill is the HBM kernel.  Same workspace for both.            */

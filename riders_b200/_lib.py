@@ -60,6 +60,7 @@ SIGNATURES = {
     "riders_debug_set": (ci, [C.c_char_p, ci]),
     "riders_debug_loftr_trace": (ci, [vp]),
     "riders_debug_tc_gemm": (ci, [vp, vp, vp, ci, ci, vp]),
+    "riders_debug_tc_mma_rate": (ci, [ci, ci, ci, vp, vp]),
     "riders_interp_linear": (ci, [vp, vp, vp, ci, ci, ci, ci, cf, vp, vp, vp, vp, vp, vp]),
 }
 

@@ -4,43 +4,59 @@
 // Specialised for RC-Net's transformer: d_model 128, 8 heads of 16, 21 tokens per radar point
 // (networks.py:378, :441).  One CTA per SM, persistent over tiles of 6 points (126 token rows
 // padded to the UMMA M of 128).  Every dense contraction of the layer - q/k/v projections,
-// merge, the 256->256->128 MLP - is a tcgen05.mma kind::tf32 with both operands in shared
-// memory (K-major, 128-byte swizzle) and the fp32 accumulator in tensor memory.  fp32 accuracy
-// comes from the 3-term split  a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo  with hi = the top 19
-// bits (exactly representable in tf32) and lo = a - hi, all three accumulated in TMEM.
+// merge, the 256->256->128 MLP - is a tcgen05.mma kind::f16 (fp16 operands, fp32 accumulate)
+// with both operands in shared memory (K-major, 128-byte swizzle) and the accumulator in tensor
+// memory.  fp32 accuracy comes from the 2-term operand split  a = a_hi + a_lo  with
+// a_hi = fp16(a), a_lo = fp16(a - a_hi)  (22-23 significant bits; products of fp16 values are
+// exact in the fp32 accumulator) and the 3 MMAs  a_lo*b_hi + a_hi*b_lo + a_hi*b_hi.  Compared with
+// a 3xTF32 split this halves the tensor-pipe time (K = 16 per instruction instead of 8) and the
+// operand bytes, which is what lets x stay resident next to the working operand.  Weights are
+// pre-scaled by 2^8 when packed (exact; keeps the lo halves of small weights out of the fp16
+// subnormal range) and every accumulator read-back multiplies by 2^-8.  Activations must stay
+// inside the fp16 range (|a| < 65504), the same constraint the reference's V/S scaling exists for.
 //
-// Roles (192 threads): warp 0 streams the pre-split, pre-swizzled weight chunks (32 KB: hi|lo
-// of a 128 x 32 block) from L2 with cp.async.bulk through a 3-stage mbarrier ring; lane 0 of
-// warp 1 issues the MMAs and commits their completion to mbarriers; warps 2..5 own one TMEM lane
-// quadrant each (thread = token row) and run every epilogue: elu+1, the per-(point, head) KV /
-// normaliser contraction (2.5 % of the layer's FLOPs, CUDA cores), LayerNorms, ReLU, residual,
-// and the hi/lo re-split of the next A operand straight into the swizzled layout.
+// Roles (576 threads): warp 0 streams the pre-split, pre-swizzled weight chunks (16 KB: hi|lo of
+// a 64 x 64 block) from L2 with cp.async.bulk through a 4-stage mbarrier ring; lane 0 of warp 1
+// issues the MMAs and commits their completion to mbarriers; warps 2..17 are the epilogue: four
+// warps per TMEM lane quadrant, thread = (token row, 32 of its 128 columns): elu+1, the
+// per-(point, head) KV / normaliser contraction (2.5 % of the layer's FLOPs, CUDA cores),
+// LayerNorms, ReLU, residual, and the hi/lo re-split of the next A operand straight into the
+// swizzled layout.
 //
-// TMEM columns (512 allocated): D0 [0,128) q -> merge -> mlp.2 | D1 [128,256) k -> msg scratch
-//                               D2 [256,384) v | D3 [256,512) mlp.0 (after v is consumed)
-// Shared memory: A operand hi[4]|lo[4] slabs of 128 x 128 B (128 KB, also the attention / output
-// staging) + 3 weight stages of 32 KB.
+// TMEM columns (512): D0 [0,128) q -> merge -> mlp.2 | D1 [128,256) k | D2 [256,384) v -> h[:,128:]
+//                     D3 [384,512) h[:, :128]
+// The x half of mlp.0 (cat([x, message]) @ W1^T, linear_attention.py:132) does not depend on the
+// attention: its first 128 outputs are issued right behind q/k/v, the second 128 as soon as the
+// epilogue has drained v out of D2 - both run under the attention epilogue.
+// Shared memory: X operand (hi[2] | lo[2] slabs of 128 rows x 128 B) 64 KB, resident x (later
+// relu(h[:,128:]), LayerNorm partials) | A operand 64 KB (src / msg / m / relu(h[:, :128]), also
+// the attention and output staging) | 4 weight stages of 16 KB | 26 KB KV / Ksum staging.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace riders {
 namespace tc {
 
 constexpr int TOK = 21, CH = 128, NHEAD = 8, HD = 16;
 constexpr int TILE_M = 128, PTS = 6, ROWS = PTS * TOK;        // 126 valid rows per tile
-constexpr int SLAB = 128 * 128;                                // bytes: 128 rows x 32 fp32
-constexpr int A_BYTES = 8 * SLAB;
-constexpr int CHUNK = 2 * SLAB;                                // hi + lo of one 128 x 32 weight block
-constexpr int NSTAGE = 3;
-constexpr int NCHUNK = 40;
-constexpr int LAYER_PACK_BYTES = NCHUNK * CHUNK;               // 1.25 MB per layer
+constexpr int SLAB = 128 * 128;                                // bytes: 128 rows x 64 fp16
+constexpr int OPER_BYTES = 4 * SLAB;                           // hi[2] | lo[2] of a 128 x 128 operand
+constexpr int CHUNK = SLAB;                                    // hi (8 KB) | lo (8 KB) of one 64 x 64 weight block
+constexpr int NSTAGE = 4;
+constexpr int NBLOCK = 10;                                     // 128 x 128 weight blocks per layer, in issue order
+constexpr int NCHUNK = NBLOCK * 4;
+constexpr int LAYER_PACK_BYTES = NCHUNK * CHUNK;               // 640 KB per layer
 constexpr int MAX_LAYERS = 16;
-constexpr int THREADS = 320;                                   // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
-constexpr int TAIL_BYTES = 128 + 2048;                         // barriers + TMEM slot | LayerNorm partials (4 x 128 floats)
-constexpr int SMEM_BYTES = A_BYTES + NSTAGE * CHUNK + TAIL_BYTES;      // 231552 of the 232448 available; base must be 1024-aligned
+constexpr int EPI_WARPS = 16;
+constexpr int THREADS = 64 + EPI_WARPS * 32;                   // warp 0 producer, warp 1 MMA, warps 2..17 epilogue
+constexpr int KV_BYTES = 24 * 256 * 4 + 24 * 16 * 4;           // KV[24][16][16] + Ksum[24][16]
+constexpr int TAIL_BYTES = 128;                                // barriers + TMEM slot
+constexpr int SMEM_BYTES = 2 * OPER_BYTES + NSTAGE * CHUNK + KV_BYTES + TAIL_BYTES;   // 222848; base must be 1024-aligned
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t D0 = 0, D1 = 128, D2 = 256, D3 = 256;
-// instruction descriptor: D fp32, A/B tf32, both K-major, N = 128, M = 128
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t D0 = 0, D1 = 128, D2 = 256, D3 = 384;
+constexpr float W_SCALE = 256.0f, W_UNSCALE = 1.0f / 256.0f;
+// instruction descriptor: D fp32, A/B fp16 (format 0), both K-major, M = 128; N in bits 17..22
+constexpr uint32_t idesc_f16(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
 
 // ------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -73,18 +89,18 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// K-major, 128-byte-swizzled operand slab (rows x 32 fp32): 8-row groups 1024 B apart
+// K-major, 128-byte-swizzled operand slab (rows x 64 fp16): 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
@@ -107,79 +123,80 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),     \
                    "=r"(r[15])                                                                                  \
                  : "r"(taddr))
-#define TMEM_ST16(taddr, r)                                                                                     \
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                                \
-                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"                                    \
-                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),     \
-                   "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), \
-                   "r"(r[15]) : "memory")
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the 16 epilogue warps
 
 // ------------------------------------------------------------------------------------ operand staging
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
-
 // byte offset of 16-byte segment `seg` (0..7) of row `row` inside one swizzled slab
 __device__ __forceinline__ uint32_t sw128(int row, int seg) {
     return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((seg ^ (row & 7)) << 4));
 }
-// split 4 consecutive K elements (col % 4 == 0) of row `row` into the hi / lo A slabs
-__device__ __forceinline__ void split_store4(uint8_t* a_base, int row, int col, float4 v) {
-    const uint32_t off = (uint32_t)(col >> 5) * SLAB + sw128(row, (col & 31) >> 2);
-    float4 hi, lo;
-    hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
-    lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
-    *reinterpret_cast<float4*>(a_base + off) = hi;
-    *reinterpret_cast<float4*>(a_base + 4 * SLAB + off) = lo;
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// split 8 consecutive K elements (col % 8 == 0) of row `row` into the hi / lo slabs of the operand at `base`
+__device__ __forceinline__ void split_store8(uint8_t* base, int row, int col, float4 a, float4 b) {
+    const uint32_t off = (uint32_t)(col >> 6) * SLAB + sw128(row, (col & 63) >> 3);
+    uint4 hi, lo;
+    split2(a.x, a.y, hi.x, lo.x); split2(a.z, a.w, hi.y, lo.y);
+    split2(b.x, b.y, hi.z, lo.z); split2(b.z, b.w, hi.w, lo.w);
+    *reinterpret_cast<uint4*>(base + off) = hi;
+    *reinterpret_cast<uint4*>(base + 2 * SLAB + off) = lo;
 }
 
-// coalesced: epilogue warp `ew` (0..7) loads rows ew*16.. of a (rows x 128) fp32 tile and splits them into A
-__device__ __forceinline__ void load_tile_to_A(uint8_t* a_base, const float* __restrict__ g, int valid_rows, int ew, int lane) {
-#pragma unroll 1
-    for (int r0 = 0; r0 < 16; r0 += 8) {
-        float4 v[8];
+// coalesced: epilogue warp `ew` (0..15) loads rows ew*8.. of a (rows x 128) fp32 tile and splits them into the operand
+__device__ __forceinline__ void load_tile_to_oper(uint8_t* base, const float* __restrict__ g, int valid_rows, int ew, int lane) {
+    float4 v[8];
+    const int c8 = (lane & 15) * 8;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int row = ew * 16 + r0 + i;
-            v[i] = (row < valid_rows) ? __ldg(reinterpret_cast<const float4*>(g + (size_t)row * CH) + lane)
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 4; ++i) {
+        const int row = ew * 8 + i * 2 + (lane >> 4);
+        if (row < valid_rows) {
+            const float4* src = reinterpret_cast<const float4*>(g + (size_t)row * CH + c8);
+            v[2 * i] = __ldg(src); v[2 * i + 1] = __ldg(src + 1);
+        } else {
+            v[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f); v[2 * i + 1] = v[2 * i];
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) split_store4(a_base, ew * 16 + r0 + i, lane * 4, v[i]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_store8(base, ew * 8 + i * 2 + (lane >> 4), c8, v[2 * i], v[2 * i + 1]);
 }
 
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x + 1.0f : __expf(x); }   // elu(x) + 1 (SFU exp2, ~2 ulp)
+__device__ __forceinline__ float acc_f(uint32_t r) { return __uint_as_float(r) * W_UNSCALE; }  // accumulator read-back
 
-// LayerNorm statistics of a 128-wide row held as 64 + 64 values by the two threads (column halves) of the row:
-// partial sums go through shared memory and are added in a fixed order, so both threads get identical bits.
-__device__ __forceinline__ void row_stats(const uint32_t (&v)[64], int row, int half, float* red, float eps, float& mean, float& rstd) {
+// LayerNorm statistics of a 128-wide row held as 4 x 32 values by the four threads (column quarters) of the row:
+// partial sums go through shared memory and are added in a fixed order, so all four threads get identical bits.
+__device__ __forceinline__ void row_stats(const float (&v)[32], int row, int colq, float* red, float eps, float& mean, float& rstd) {
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 64; ++i) s += __uint_as_float(v[i]);
-    red[half * 128 + row] = s;
+    for (int i = 0; i < 32; ++i) s += v[i];
+    red[colq * 128 + row] = s;
     epi_bar();
-    mean = (red[row] + red[128 + row]) * (1.0f / CH);
+    mean = ((red[row] + red[128 + row]) + (red[256 + row] + red[384 + row])) * (1.0f / CH);
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < 64; ++i) { const float d = __uint_as_float(v[i]) - mean; q = fmaf(d, d, q); }
-    red[256 + half * 128 + row] = q;
+    for (int i = 0; i < 32; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    red[512 + colq * 128 + row] = q;
     epi_bar();
-    rstd = 1.0f / sqrtf((red[256 + row] + red[384 + row]) * (1.0f / CH) + eps);
+    rstd = 1.0f / sqrtf(((red[512 + row] + red[640 + row]) + (red[768 + row] + red[896 + row])) * (1.0f / CH) + eps);
 }
 
-// signal "A operand (and my TMEM reads) done" to the MMA warp
-__device__ __forceinline__ void publish_A(uint32_t a_ready) {
+// signal "operand written (and my TMEM reads done)" to the MMA warp
+__device__ __forceinline__ void publish(uint32_t bar) {
     fence_async_smem();
     tc_fence_before();
-    mbar_arrive(a_ready);
+    mbar_arrive(bar);
 }
 
 struct LayerArgs {
     const float* x; const float* src; float* out;
-    const uint8_t* wpack;                       // NCHUNK x 32 KB, pre-split + pre-swizzled
+    const uint8_t* wpack;                       // NCHUNK x 16 KB, pre-split + pre-swizzled
     const float* ln1_g; const float* ln1_b; const float* ln2_g; const float* ln2_b;
     int N;                                      // radar points
     int n_tiles;
@@ -198,13 +215,16 @@ loftr_layer_tc_kernel(const LayerArgs P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;                                 // SWIZZLE_128B slabs need a 1024-byte aligned base
     if (smem_u32(smem) & 1023u) __trap();
-    uint8_t* a_base = smem;                                   // A hi[4] | lo[4]
-    uint8_t* b_base = smem + A_BYTES;                         // NSTAGE x (hi | lo)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + NSTAGE * CHUNK);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-    float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);
+    uint8_t* x_base = smem;                                   // X operand: hi[2] | lo[2]
+    uint8_t* a_base = smem + OPER_BYTES;                      // A operand: hi[2] | lo[2]
+    uint8_t* b_base = smem + 2 * OPER_BYTES;                  // NSTAGE x (hi | lo)
+    float* KVs = reinterpret_cast<float*>(b_base + NSTAGE * CHUNK);
+    float* Ksum = KVs + 24 * 256;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(KVs) + KV_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
     const uint32_t bfull = smem_u32(bars), bempty = smem_u32(bars + NSTAGE);
     const uint32_t a_ready = smem_u32(bars + 2 * NSTAGE), d_ready = smem_u32(bars + 2 * NSTAGE + 1);
+    const uint32_t v_free = smem_u32(bars + 2 * NSTAGE + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool tr_on = blockIdx.x == 0 || blockIdx.x == gridDim.x / 2;
@@ -212,8 +232,9 @@ loftr_layer_tc_kernel(const LayerArgs P) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(bfull + 8 * s, 1); mbar_init(bempty + 8 * s, 1); }
-        mbar_init(a_ready, 256);
+        mbar_init(a_ready, EPI_WARPS * 32);
         mbar_init(d_ready, 1);
+        mbar_init(v_free, EPI_WARPS * 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -240,70 +261,97 @@ loftr_layer_tc_kernel(const LayerArgs P) {
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            uint32_t n = 0, aph = 0;
-            const uint32_t a_hi = smem_u32(a_base), a_lo = a_hi + 4 * SLAB, b0 = smem_u32(b_base);
-            // segment ends (exclusive chunk index): after each the accumulators are committed to d_ready
-            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-                int c = 0;
+            uint32_t n = 0, aph = 0, vph = 0;
+            const uint32_t xo = smem_u32(x_base), ao = smem_u32(a_base), b0 = smem_u32(b_base);
+            const uint32_t kv_src = P.is_self ? xo : ao;
+            constexpr uint32_t IDESC = idesc_f16(64);
+            long long wsum = 0;
+            // one 128 x 128 weight block = 4 chunks (N half, K half): D[:, dcol + 64 nh ..] (+)= oper[:, 64 kb ..] W^T
+            auto issue_block = [&](uint32_t oper, uint32_t dcol, uint32_t acc_in) {
 #pragma unroll 1
-                for (int seg = 0; seg < 7; ++seg) {
-                    int c_end;
-                    switch (seg) {
-                        case 0: c_end = P.is_self ? 12 : 4; break;      // A = x   : q (+ k, v when self)
-                        case 1: c_end = 12; break;                       // A = src : k, v (cross only)
-                        case 2: c_end = 16; break;                       // A = msg : merge
-                        case 3: c_end = 24; break;                       // A = m   : mlp.0[:, C:]
-                        case 4: c_end = 32; break;                       // A = x   : mlp.0[:, :C]
-                        case 5: c_end = 36; break;                       // A = relu(h)[:, :C]  : mlp.2
-                        default: c_end = 40; break;                      // A = relu(h)[:, C:]  : mlp.2
-                    }
-                    if (c == c_end) continue;                            // empty segment (self layer, seg 1)
-                    TRACE_M(seg * 4 + 0);
-                    mbar_wait(a_ready, aph & 1); ++aph;
+                for (int j = 0; j < 4; ++j, ++n) {
+                    const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1;
+                    const long long tw = P.trace ? clock64() : 0;
+                    mbar_wait(bfull + 8 * s, ph);
+                    if (P.trace) wsum += clock64() - tw;
                     tc_fence_after();
-                    TRACE_M(seg * 4 + 1);
-                    long long wsum = 0;
-                    for (; c < c_end; ++c, ++n) {
-                        const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1;
-                        const long long tw = P.trace ? clock64() : 0;
-                        mbar_wait(bfull + 8 * s, ph);
-                        if (P.trace) wsum += clock64() - tw;
-                        tc_fence_after();
-                        const int kc = c & 3;
-                        uint32_t dcol, acc0;
-                        if (c < 12)      { dcol = (uint32_t)(c >> 2) * 128; acc0 = kc > 0; }
-                        else if (c < 16) { dcol = D0; acc0 = kc > 0; }
-                        else if (c < 24) { dcol = D3 + (uint32_t)((c - 16) >> 2) * 128; acc0 = kc > 0; }
-                        else if (c < 32) { dcol = D3 + (uint32_t)((c - 24) >> 2) * 128; acc0 = 1; }
-                        else if (c < 36) { dcol = D0; acc0 = kc > 0; }
-                        else             { dcol = D0; acc0 = 1; }
-                        const uint64_t ah = smem_desc(a_hi + kc * SLAB), al = smem_desc(a_lo + kc * SLAB);
-                        const uint64_t bh = smem_desc(b0 + s * CHUNK), bl = smem_desc(b0 + s * CHUNK + SLAB);
+                    const uint32_t nh = (uint32_t)j >> 1, kb = (uint32_t)j & 1;
+                    const uint32_t d = tmem + dcol + nh * 64;
+                    const uint64_t ah = smem_desc(oper + kb * SLAB), al = smem_desc(oper + (2 + kb) * SLAB);
+                    const uint64_t bh = smem_desc(b0 + s * CHUNK), bl = smem_desc(b0 + s * CHUNK + CHUNK / 2);
 #pragma unroll
-                        for (int k8 = 0; k8 < 4; ++k8) {                 // 8 tf32 = 32 bytes per MMA along K
-                            const uint64_t adv = (uint64_t)(k8 * 2);
-                            umma_tf32(tmem + dcol, al + adv, bh + adv, acc0 | (k8 > 0));
-                            umma_tf32(tmem + dcol, ah + adv, bl + adv, 1);
-                            umma_tf32(tmem + dcol, ah + adv, bh + adv, 1);
-                        }
-                        umma_commit(bempty + 8 * s);                     // stage reusable once these MMAs retire
+                    for (int k16 = 0; k16 < 4; ++k16) {              // 16 fp16 = 32 bytes per MMA along K
+                        const uint64_t adv = (uint64_t)(k16 * 2);
+                        umma_f16(d, al + adv, bh + adv, IDESC, acc_in | kb | (k16 > 0));
+                        umma_f16(d, ah + adv, bl + adv, IDESC, 1);
+                        umma_f16(d, ah + adv, bh + adv, IDESC, 1);
                     }
-                    umma_commit(d_ready);
-                    TRACE_M(seg * 4 + 2);
-                    if (P.trace && tr_on && tile == (int)blockIdx.x) P.trace[tr_base + 64 + seg * 4 + 3] = wsum;
+                    umma_commit(bempty + 8 * s);                     // stage reusable once these MMAs retire
                 }
+            };
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+                // seg 0: q, k, v (-> attention can start), then mlp.0[: C, :C] on x
+                TRACE_M(0);
+                mbar_wait(a_ready, aph & 1); ++aph;
+                tc_fence_after();
+                TRACE_M(1); wsum = 0;
+                issue_block(xo, D0, 0);
+                issue_block(kv_src, D1, 0);
+                issue_block(kv_src, D2, 0);
+                umma_commit(d_ready);
+                issue_block(xo, D3, 0);
+                TRACE_M(2);
+                if (P.trace && tr_on && tile == (int)blockIdx.x) P.trace[tr_base + 64 + 3] = wsum;
+                // seg 1: v drained from D2 -> mlp.0[C :, :C] on x
+                TRACE_M(4);
+                mbar_wait(v_free, vph & 1); ++vph;
+                tc_fence_after();
+                TRACE_M(5); wsum = 0;
+                issue_block(xo, D2, 0);
+                TRACE_M(6);
+                if (P.trace && tr_on && tile == (int)blockIdx.x) P.trace[tr_base + 64 + 7] = wsum;
+                // seg 2: merge(msg)
+                TRACE_M(8);
+                mbar_wait(a_ready, aph & 1); ++aph;
+                tc_fence_after();
+                TRACE_M(9); wsum = 0;
+                issue_block(ao, D0, 0);
+                umma_commit(d_ready);
+                TRACE_M(10);
+                if (P.trace && tr_on && tile == (int)blockIdx.x) P.trace[tr_base + 64 + 11] = wsum;
+                // seg 3: mlp.0[:, C:] on m, accumulated onto the x halves
+                TRACE_M(12);
+                mbar_wait(a_ready, aph & 1); ++aph;
+                tc_fence_after();
+                TRACE_M(13); wsum = 0;
+                issue_block(ao, D3, 1);
+                issue_block(ao, D2, 1);
+                umma_commit(d_ready);
+                TRACE_M(14);
+                if (P.trace && tr_on && tile == (int)blockIdx.x) P.trace[tr_base + 64 + 15] = wsum;
+                // seg 4: mlp.2 on relu(h): [:, :C] from A, [:, C:] from X
+                TRACE_M(16);
+                mbar_wait(a_ready, aph & 1); ++aph;
+                tc_fence_after();
+                TRACE_M(17); wsum = 0;
+                issue_block(ao, D0, 0);
+                issue_block(xo, D0, 1);
+                umma_commit(d_ready);
+                TRACE_M(18);
+                if (P.trace && tr_on && tile == (int)blockIdx.x) P.trace[tr_base + 64 + 19] = wsum;
             }
         }
     } else {
-        // ===================== epilogue warps: (thread pair) = token row, each thread 64 of its 128 columns =====
-        const int ew = warp - 2;                         // 0..7
+        // ===================== epilogue warps: thread = (token row, column quarter) =====================
+        const int ew = warp - 2;                         // 0..15
         const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
-        const int half = ew >> 2;                        // column half: warps 2..5 -> [0,64), warps 6..9 -> [64,128)
+        const int colq = ew >> 2;                        // column quarter: 32 columns = heads 2 colq, 2 colq + 1
         const int row = quad * 32 + lane;
-        const int col0 = half * 64;
+        const int col0 = colq * 32;
         const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
         uint32_t dph = 0;
         float* stage_f = reinterpret_cast<float*>(a_base);
+        float* red = reinterpret_cast<float*>(x_base);   // LayerNorm partials (X is dead whenever a LayerNorm runs)
 
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
             const int pts = min(PTS, P.N - tile * PTS);
@@ -312,17 +360,12 @@ loftr_layer_tc_kernel(const LayerArgs P) {
             const float* xg = P.x + g_row0 * CH;
             const float* sg = P.src + g_row0 * CH;
 
-            // ---- E0: A = x ------------------------------------------------------------------
+            // ---- E0: X = x, A = src (cross) ---------------------------------------------------
             TRACE_E(0);
-            load_tile_to_A(a_base, xg, valid_rows, ew, lane);
-            publish_A(a_ready);
+            load_tile_to_oper(x_base, xg, valid_rows, ew, lane);
+            if (!P.is_self) load_tile_to_oper(a_base, sg, valid_rows, ew, lane);
+            publish(a_ready);
             TRACE_E(1);
-            if (!P.is_self) {
-                mbar_wait(d_ready, dph & 1); ++dph;      // q done: A is free again
-                tc_fence_after();
-                load_tile_to_A(a_base, sg, valid_rows, ew, lane);
-                publish_A(a_ready);
-            }
 
             // ---- E1: linear attention (linear_attention.py:29-43) ---------------------------
             // The reference divides V by S and multiplies the message by S (fp16 range safety,
@@ -330,205 +373,197 @@ loftr_layer_tc_kernel(const LayerArgs P) {
             mbar_wait(d_ready, dph & 1); ++dph;          // q, k, v in D0, D1, D2
             tc_fence_after();
             TRACE_E(2);
-            float msg[2][2][16];                         // [head half hh][head e][v]: heads hh*4 + half*2 + e
+            float msg[2][16];                            // [head half hh][v]: head hh*4 + colq
             {
-                // staging inside the (now idle) A region, all fp32:
-                //   Kst [128][64] @0, Vst [128][64] @32K (float4 index XOR (row & 15)), KVs [24][16][16] @64K, Ksum [24][16] @88K
+                // staging inside the A operand (idle until msg is written), fp32:
+                //   Kst [128][64] @0, Vst [128][64] @32K (float4 index XOR (row & 15)); KVs / Ksum have their own region
                 float* Kst = stage_f;
                 float* Vst = stage_f + 8192;
-                float* KVs = stage_f + 16384;
-                float* Ksum = stage_f + 16384 + 6144;
                 const int p_row = min(row / TOK, PTS - 1);
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
-                    // (1) K' = elu(k)+1 and V of heads 4hh..4hh+3 -> smem (this thread: 32 of the 64 columns)
+                    // (1) K' = elu(k)+1 and V of heads 4hh..4hh+3 -> smem (this thread: 16 of the 64 columns)
                     {
-                        uint32_t kr[32], vr[32];
-                        TMEM_LD32(trow + D1 + hh * 64 + half * 32, kr);
-                        TMEM_LD32(trow + D2 + hh * 64 + half * 32, vr);
+                        uint32_t kr[16], vr[16];
+                        TMEM_LD16(trow + D1 + hh * 64 + colq * 16, kr);
+                        TMEM_LD16(trow + D2 + hh * 64 + colq * 16, vr);
                         tmem_wait_ld();
+                        if (hh == 1) { tc_fence_before(); mbar_arrive(v_free); }    // D2 is free: mlp.0[C:, :C] may go
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
+                        for (int j = 0; j < 4; ++j) {
                             float4 kk, vv;
-                            kk.x = elu1(__uint_as_float(kr[4 * j + 0])); kk.y = elu1(__uint_as_float(kr[4 * j + 1]));
-                            kk.z = elu1(__uint_as_float(kr[4 * j + 2])); kk.w = elu1(__uint_as_float(kr[4 * j + 3]));
-                            vv.x = __uint_as_float(vr[4 * j + 0]); vv.y = __uint_as_float(vr[4 * j + 1]);
-                            vv.z = __uint_as_float(vr[4 * j + 2]); vv.w = __uint_as_float(vr[4 * j + 3]);
-                            const int f4 = (half * 8 + j) ^ (row & 15);
+                            kk.x = elu1(acc_f(kr[4 * j + 0])); kk.y = elu1(acc_f(kr[4 * j + 1]));
+                            kk.z = elu1(acc_f(kr[4 * j + 2])); kk.w = elu1(acc_f(kr[4 * j + 3]));
+                            vv.x = acc_f(vr[4 * j + 0]); vv.y = acc_f(vr[4 * j + 1]);
+                            vv.z = acc_f(vr[4 * j + 2]); vv.w = acc_f(vr[4 * j + 3]);
+                            const int f4 = (colq * 4 + j) ^ (row & 15);
                             reinterpret_cast<float4*>(Kst + row * 64)[f4] = kk;
                             reinterpret_cast<float4*>(Vst + row * 64)[f4] = vv;
                         }
                     }
                     epi_bar();
-                    // (2) KV[p][h] = K'^T V, Ksum[p][h] = sum_s K'   (24 (point, head) pairs, 3 per warp;
-                    //     lane -> (d, 8 consecutive v); 7 tokens per batch so 21 loads are in flight)
+                    // (2) KV[p][h] = K'^T V, Ksum[p][h] = sum_s K'   (24 (point, head) pairs x 2 v halves = 48 warp
+                    //     tasks, 3 per warp; lane -> (d, 4 consecutive v); 7 tokens per batch so 14 loads are in flight)
 #pragma unroll 1
                     for (int q3 = 0; q3 < 3; ++q3) {
-                        const int pair = ew * 3 + q3, p = pair >> 2, hl = pair & 3;
-                        const int d = lane >> 1, v0 = (lane & 1) * 8;
-                        float acc[8], ks = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+                        const int task = ew * 3 + q3, pair = task >> 1, p = pair >> 2, hl = pair & 3;
+                        const int d = lane >> 1, v0 = (task & 1) * 8 + (lane & 1) * 4;
+                        float acc[4] = {0.f, 0.f, 0.f, 0.f}, ks = 0.f;
                         if (p < pts) {
-#pragma unroll 1
+#pragma unroll
                             for (int s0 = 0; s0 < TOK; s0 += 7) {
                                 float kk[7];
-                                float4 va[7], vb[7];
+                                float4 va[7];
 #pragma unroll
                                 for (int u = 0; u < 7; ++u) {
                                     const int r = p * TOK + s0 + u, sw = r & 15;
                                     kk[u] = Kst[r * 64 + (((hl * 4 + (d >> 2)) ^ sw) << 2) + (d & 3)];
                                     va[u] = reinterpret_cast<const float4*>(Vst + r * 64)[(hl * 4 + (v0 >> 2)) ^ sw];
-                                    vb[u] = reinterpret_cast<const float4*>(Vst + r * 64)[(hl * 4 + (v0 >> 2) + 1) ^ sw];
                                 }
 #pragma unroll
                                 for (int u = 0; u < 7; ++u) {
                                     ks += kk[u];
                                     acc[0] = fmaf(kk[u], va[u].x, acc[0]); acc[1] = fmaf(kk[u], va[u].y, acc[1]);
                                     acc[2] = fmaf(kk[u], va[u].z, acc[2]); acc[3] = fmaf(kk[u], va[u].w, acc[3]);
-                                    acc[4] = fmaf(kk[u], vb[u].x, acc[4]); acc[5] = fmaf(kk[u], vb[u].y, acc[5]);
-                                    acc[6] = fmaf(kk[u], vb[u].z, acc[6]); acc[7] = fmaf(kk[u], vb[u].w, acc[7]);
                                 }
                             }
                         }
-                        float4* dst = reinterpret_cast<float4*>(KVs + pair * 256 + d * 16 + v0);
-                        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-                        if ((lane & 1) == 0) Ksum[pair * 16 + d] = ks;
+                        *reinterpret_cast<float4*>(KVs + pair * 256 + d * 16 + v0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                        if ((lane & 1) == 0 && (task & 1) == 0) Ksum[pair * 16 + d] = ks;
                     }
                     epi_bar();
-                    // (3) message rows of heads hh*4 + half*2 + {0,1} -> registers
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int hl = half * 2 + e;
+                    // (3) message row of head hh*4 + colq -> registers
+                    {
                         uint32_t qr[16];
-                        TMEM_LD16(trow + D0 + (hh * 4 + hl) * 16, qr);
+                        TMEM_LD16(trow + D0 + (hh * 4 + colq) * 16, qr);
                         tmem_wait_ld();
-                        const int pair = p_row * 4 + hl;
+                        const int pair = p_row * 4 + colq;
                         float Q[16], den = 0.f;
 #pragma unroll
-                        for (int dd = 0; dd < 16; ++dd) { Q[dd] = elu1(__uint_as_float(qr[dd])); den = fmaf(Q[dd], Ksum[pair * 16 + dd], den); }
+                        for (int dd = 0; dd < 16; ++dd) { Q[dd] = elu1(acc_f(qr[dd])); den = fmaf(Q[dd], Ksum[pair * 16 + dd], den); }
 #pragma unroll
-                        for (int v = 0; v < 16; ++v) msg[hh][e][v] = 0.f;
+                        for (int v = 0; v < 16; ++v) msg[hh][v] = 0.f;
 #pragma unroll
                         for (int dd = 0; dd < 16; ++dd) {
                             const float4* kv = reinterpret_cast<const float4*>(KVs + pair * 256 + dd * 16);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const float4 t = kv[j];
-                                msg[hh][e][4 * j + 0] = fmaf(Q[dd], t.x, msg[hh][e][4 * j + 0]); msg[hh][e][4 * j + 1] = fmaf(Q[dd], t.y, msg[hh][e][4 * j + 1]);
-                                msg[hh][e][4 * j + 2] = fmaf(Q[dd], t.z, msg[hh][e][4 * j + 2]); msg[hh][e][4 * j + 3] = fmaf(Q[dd], t.w, msg[hh][e][4 * j + 3]);
+                                msg[hh][4 * j + 0] = fmaf(Q[dd], t.x, msg[hh][4 * j + 0]); msg[hh][4 * j + 1] = fmaf(Q[dd], t.y, msg[hh][4 * j + 1]);
+                                msg[hh][4 * j + 2] = fmaf(Q[dd], t.z, msg[hh][4 * j + 2]); msg[hh][4 * j + 3] = fmaf(Q[dd], t.w, msg[hh][4 * j + 3]);
                             }
                         }
                         const float z = __fdividef(1.0f, den + P.attn_eps);
 #pragma unroll
-                        for (int v = 0; v < 16; ++v) msg[hh][e][v] *= z;
+                        for (int v = 0; v < 16; ++v) msg[hh][v] *= z;
                     }
-                    // the barrier after the next half's stage (1) orders (3) before the next (2)
+                    if (hh == 0) TRACE_E(3);
+                    // the barrier after the next half's stage (1) orders (3) before the next (2); stage (1) of the
+                    // next half overwrites Kst / Vst, which stage (2) finished reading before the barrier above
                 }
                 epi_bar();                               // staging dead: A may be overwritten
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            split_store4(a_base, row, (hh * 4 + half * 2 + e) * 16 + j * 4,
-                                         make_float4(msg[hh][e][4 * j], msg[hh][e][4 * j + 1], msg[hh][e][4 * j + 2], msg[hh][e][4 * j + 3]));
+                    for (int j = 0; j < 2; ++j)
+                        split_store8(a_base, row, (hh * 4 + colq) * 16 + j * 8,
+                                     make_float4(msg[hh][8 * j], msg[hh][8 * j + 1], msg[hh][8 * j + 2], msg[hh][8 * j + 3]),
+                                     make_float4(msg[hh][8 * j + 4], msg[hh][8 * j + 5], msg[hh][8 * j + 6], msg[hh][8 * j + 7]));
             }
-            publish_A(a_ready);
-            TRACE_E(3);
+            publish(a_ready);
+            TRACE_E(4);
 
             // ---- E2: m = LayerNorm1(merge(msg)) -> A ----------------------------------------
-            mbar_wait(d_ready, dph & 1); ++dph;
+            mbar_wait(d_ready, dph & 1); ++dph;          // merge done (and with it both x halves of mlp.0: X is dead)
             tc_fence_after();
-            TRACE_E(4);
-            {
-                uint32_t v[64];
-                TMEM_LD32(trow + D0 + col0, (v + 0)); TMEM_LD32(trow + D0 + col0 + 32, (v + 32));
-                tmem_wait_ld();
-                float mean, rstd;
-                row_stats(v, row, half, red, P.ln_eps, mean, rstd);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float4 g = __ldg(reinterpret_cast<const float4*>(P.ln1_g + col0) + j);
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(P.ln1_b + col0) + j);
-                    float4 y;
-                    y.x = (__uint_as_float(v[4 * j + 0]) - mean) * rstd * g.x + b.x;
-                    y.y = (__uint_as_float(v[4 * j + 1]) - mean) * rstd * g.y + b.y;
-                    y.z = (__uint_as_float(v[4 * j + 2]) - mean) * rstd * g.z + b.z;
-                    y.w = (__uint_as_float(v[4 * j + 3]) - mean) * rstd * g.w + b.w;
-                    split_store4(a_base, row, col0 + j * 4, y);
-                }
-            }
-            publish_A(a_ready);
             TRACE_E(5);
-
-            // ---- E3: A = x again for mlp.0[:, :C] -------------------------------------------
-            mbar_wait(d_ready, dph & 1); ++dph;
-            tc_fence_after();
-            TRACE_E(6);
-            load_tile_to_A(a_base, xg, valid_rows, ew, lane);
-            publish_A(a_ready);
-            TRACE_E(7);
-
-            // ---- E4 / E5: A = relu(h) halves for mlp.2 --------------------------------------
-#pragma unroll 1
-            for (int hf = 0; hf < 2; ++hf) {
-                mbar_wait(d_ready, dph & 1); ++dph;
-                tc_fence_after();
-                TRACE_E(8 + 2 * hf);
-#pragma unroll
-                for (int part = 0; part < 2; ++part) {
-                    uint32_t hr[32];
-                    TMEM_LD32(trow + D3 + hf * 128 + col0 + part * 32, hr);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        split_store4(a_base, row, col0 + part * 32 + j * 4,
-                                     make_float4(fmaxf(__uint_as_float(hr[4 * j]), 0.f), fmaxf(__uint_as_float(hr[4 * j + 1]), 0.f),
-                                                 fmaxf(__uint_as_float(hr[4 * j + 2]), 0.f), fmaxf(__uint_as_float(hr[4 * j + 3]), 0.f)));
-                }
-                publish_A(a_ready);
-                TRACE_E(9 + 2 * hf);
-            }
-
-            // ---- E6: out = x + LayerNorm2(mlp(...)) -----------------------------------------
-            mbar_wait(d_ready, dph & 1); ++dph;
-            tc_fence_after();
-            TRACE_E(12);
             {
-                uint32_t v[64];
-                TMEM_LD32(trow + D0 + col0, (v + 0)); TMEM_LD32(trow + D0 + col0 + 32, (v + 32));
+                uint32_t r[32];
+                float v[32];
+                TMEM_LD32(trow + D0 + col0, r);
                 tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = acc_f(r[i]);
                 float mean, rstd;
-                row_stats(v, row, half, red, P.ln_eps, mean, rstd);
+                row_stats(v, row, colq, red, P.ln_eps, mean, rstd);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float y[8];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float4 g = __ldg(reinterpret_cast<const float4*>(P.ln1_g + col0) + 2 * j + e);
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(P.ln1_b + col0) + 2 * j + e);
+                        y[4 * e + 0] = (v[8 * j + 4 * e + 0] - mean) * rstd * g.x + b.x;
+                        y[4 * e + 1] = (v[8 * j + 4 * e + 1] - mean) * rstd * g.y + b.y;
+                        y[4 * e + 2] = (v[8 * j + 4 * e + 2] - mean) * rstd * g.z + b.z;
+                        y[4 * e + 3] = (v[8 * j + 4 * e + 3] - mean) * rstd * g.w + b.w;
+                    }
+                    split_store8(a_base, row, col0 + j * 8, make_float4(y[0], y[1], y[2], y[3]), make_float4(y[4], y[5], y[6], y[7]));
+                }
+            }
+            publish(a_ready);
+            TRACE_E(6);
+
+            // ---- E3: relu(h[:, :C]) -> A, relu(h[:, C:]) -> X for mlp.2 -----------------------
+            mbar_wait(d_ready, dph & 1); ++dph;
+            tc_fence_after();
+            TRACE_E(7);
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t hr[32];
+                TMEM_LD32(trow + (hf ? D2 : D3) + col0, hr);
+                tmem_wait_ld();
+                uint8_t* dst = hf ? x_base : a_base;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    split_store8(dst, row, col0 + j * 8,
+                                 make_float4(fmaxf(acc_f(hr[8 * j]), 0.f), fmaxf(acc_f(hr[8 * j + 1]), 0.f),
+                                             fmaxf(acc_f(hr[8 * j + 2]), 0.f), fmaxf(acc_f(hr[8 * j + 3]), 0.f)),
+                                 make_float4(fmaxf(acc_f(hr[8 * j + 4]), 0.f), fmaxf(acc_f(hr[8 * j + 5]), 0.f),
+                                             fmaxf(acc_f(hr[8 * j + 6]), 0.f), fmaxf(acc_f(hr[8 * j + 7]), 0.f)));
+            }
+            publish(a_ready);
+            TRACE_E(8);
+
+            // ---- E4: out = x + LayerNorm2(mlp(...)) -----------------------------------------
+            mbar_wait(d_ready, dph & 1); ++dph;
+            tc_fence_after();
+            TRACE_E(9);
+            {
+                uint32_t r[32];
+                float v[32];
+                TMEM_LD32(trow + D0 + col0, r);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = acc_f(r[i]);
+                float mean, rstd;
+                row_stats(v, row, colq, red, P.ln_eps, mean, rstd);
                 // stage the normalised row (float4 index XOR (row & 31)) so the global traffic is coalesced
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
+                for (int j = 0; j < 8; ++j) {
                     const float4 g = __ldg(reinterpret_cast<const float4*>(P.ln2_g + col0) + j);
                     const float4 b = __ldg(reinterpret_cast<const float4*>(P.ln2_b + col0) + j);
                     float4 y;
-                    y.x = (__uint_as_float(v[4 * j + 0]) - mean) * rstd * g.x + b.x;
-                    y.y = (__uint_as_float(v[4 * j + 1]) - mean) * rstd * g.y + b.y;
-                    y.z = (__uint_as_float(v[4 * j + 2]) - mean) * rstd * g.z + b.z;
-                    y.w = (__uint_as_float(v[4 * j + 3]) - mean) * rstd * g.w + b.w;
-                    reinterpret_cast<float4*>(stage_f + row * CH)[(half * 16 + j) ^ (row & 31)] = y;
+                    y.x = (v[4 * j + 0] - mean) * rstd * g.x + b.x;
+                    y.y = (v[4 * j + 1] - mean) * rstd * g.y + b.y;
+                    y.z = (v[4 * j + 2] - mean) * rstd * g.z + b.z;
+                    y.w = (v[4 * j + 3] - mean) * rstd * g.w + b.w;
+                    reinterpret_cast<float4*>(stage_f + row * CH)[(colq * 8 + j) ^ (row & 31)] = y;
                 }
                 epi_bar();
                 float* og = P.out + g_row0 * CH;
-#pragma unroll 4
-                for (int i = 0; i < 16; ++i) {
-                    const int r = ew * 16 + i;
-                    if (r < valid_rows) {
-                        const float4 y = reinterpret_cast<const float4*>(stage_f + r * CH)[lane ^ (r & 31)];
-                        const float4 xv = __ldg(reinterpret_cast<const float4*>(xg + (size_t)r * CH) + lane);
-                        reinterpret_cast<float4*>(og + (size_t)r * CH)[lane] = make_float4(xv.x + y.x, xv.y + y.y, xv.z + y.z, xv.w + y.w);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r2 = ew * 8 + i;
+                    if (r2 < valid_rows) {
+                        const float4 y = reinterpret_cast<const float4*>(stage_f + r2 * CH)[lane ^ (r2 & 31)];
+                        const float4 xv = __ldg(reinterpret_cast<const float4*>(xg + (size_t)r2 * CH) + lane);
+                        reinterpret_cast<float4*>(og + (size_t)r2 * CH)[lane] = make_float4(xv.x + y.x, xv.y + y.y, xv.z + y.z, xv.w + y.w);
                     }
                 }
-                epi_bar();                               // staging reads done before the next tile's split stores
+                epi_bar();                               // staging / partials reads done before the next tile's split stores
             }
-            TRACE_E(13);
+            TRACE_E(10);
             tc_fence_before();
         }
     }
@@ -541,7 +576,7 @@ loftr_layer_tc_kernel(const LayerArgs P) {
 }
 
 // ------------------------------------------------------------------------------------ weight packing
-// chunk c -> (matrix, first row, first column, leading dimension); see the file header for the order
+// block b (issue order) -> (matrix, first row, first column, leading dimension); chunk = block * 4 + (N half * 2 + K half)
 struct PackArgs {
     const float* wq; const float* wk; const float* wv; const float* wm; const float* w1; const float* w2;
     uint8_t* dst;
@@ -549,47 +584,56 @@ struct PackArgs {
 
 __global__ void __launch_bounds__(256)
 loftr_pack_weights_kernel(const PackArgs P) {
-    const int t = blockIdx.x * 256 + threadIdx.x;                // one 16-byte segment each
-    if (t >= NCHUNK * 128 * 8) return;
-    const int seg = t & 7, row = (t >> 3) & 127, c = t >> 10, kc = c & 3;
-    const float* W; int r0 = 0, c0 = kc * 32, ld = CH;
-    if (c < 4) W = P.wq;
-    else if (c < 8) W = P.wk;
-    else if (c < 12) W = P.wv;
-    else if (c < 16) W = P.wm;
-    else if (c < 24) { W = P.w1; ld = 2 * CH; r0 = ((c - 16) >> 2) * 128; c0 = CH + kc * 32; }
-    else if (c < 32) { W = P.w1; ld = 2 * CH; r0 = ((c - 24) >> 2) * 128; }
-    else if (c < 36) { W = P.w2; ld = 2 * CH; }
-    else { W = P.w2; ld = 2 * CH; c0 = CH + kc * 32; }
-    const float4 v = __ldg(reinterpret_cast<const float4*>(W + (size_t)(r0 + row) * ld + c0 + seg * 4));
-    float4 hi, lo;
-    hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
-    lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+    const int t = blockIdx.x * 256 + threadIdx.x;                // one 16-byte segment (8 fp16) each
+    if (t >= NCHUNK * 64 * 8) return;
+    const int seg = t & 7, row = (t >> 3) & 63, c = t >> 9, blk = c >> 2, nh = (c >> 1) & 1, kb = c & 1;
+    const float* W; int r0 = 0, c0 = 0, ld = CH;
+    switch (blk) {
+        case 0: W = P.wq; break;
+        case 1: W = P.wk; break;
+        case 2: W = P.wv; break;
+        case 3: W = P.w1; ld = 2 * CH; break;                    // mlp.0[:C, :C]   (x half of cat([x, message]))
+        case 4: W = P.w1; ld = 2 * CH; r0 = CH; break;           // mlp.0[C:, :C]
+        case 5: W = P.wm; break;
+        case 6: W = P.w1; ld = 2 * CH; c0 = CH; break;           // mlp.0[:C, C:]   (message half)
+        case 7: W = P.w1; ld = 2 * CH; r0 = CH; c0 = CH; break;  // mlp.0[C:, C:]
+        case 8: W = P.w2; ld = 2 * CH; break;                    // mlp.2[:, :C]
+        default: W = P.w2; ld = 2 * CH; c0 = CH; break;          // mlp.2[:, C:]
+    }
+    const float4* src = reinterpret_cast<const float4*>(W + (size_t)(r0 + nh * 64 + row) * ld + c0 + kb * 64 + seg * 8);
+    float4 a = __ldg(src), b = __ldg(src + 1);
+    a.x *= W_SCALE; a.y *= W_SCALE; a.z *= W_SCALE; a.w *= W_SCALE;
+    b.x *= W_SCALE; b.y *= W_SCALE; b.z *= W_SCALE; b.w *= W_SCALE;
+    uint4 hi, lo;
+    split2(a.x, a.y, hi.x, lo.x); split2(a.z, a.w, hi.y, lo.y);
+    split2(b.x, b.y, hi.z, lo.z); split2(b.z, b.w, hi.w, lo.w);
     uint8_t* d = P.dst + (size_t)c * CHUNK + sw128(row, seg);
-    *reinterpret_cast<float4*>(d) = hi;
-    *reinterpret_cast<float4*>(d + SLAB) = lo;
+    *reinterpret_cast<uint4*>(d) = hi;
+    *reinterpret_cast<uint4*>(d + CHUNK / 2) = lo;
 }
 
 // ------------------------------------------------------------------------------------ self-test GEMM
-// D (128 x 128) = A (128 x K) * B (128 x K)^T, K in {32, 64}, through exactly the staging /
-// descriptor / TMEM helpers of the layer kernel.  terms = 1: plain tf32; terms = 3: hi/lo split.
+// D (128 x 128) = A (128 x K) * B (128 x K)^T, K in {64, 128}, through exactly the staging /
+// descriptor / TMEM helpers of the layer kernel (two N = 64 halves).  terms = 1: plain fp16; terms = 3: hi/lo split.
 __global__ void __launch_bounds__(128, 1)
 tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int K, int terms) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* a_base = smem;
-    uint8_t* b_base = smem + 2 * SLAB;                        // B: hi in slabs 2,3 / lo in slabs 6,7 of the same region
+    uint8_t* b_base = smem + OPER_BYTES;
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_slot;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, row = threadIdx.x;
+    const int warp = threadIdx.x >> 5, row = threadIdx.x;
     if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(128u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int c = 0; c < K; c += 4) {
-        split_store4(a_base, row, c, *reinterpret_cast<const float4*>(A + (size_t)row * K + c));
-        split_store4(b_base, row, c, *reinterpret_cast<const float4*>(B + (size_t)row * K + c));
+    for (int c = 0; c < K; c += 8) {
+        const float4* pa = reinterpret_cast<const float4*>(A + (size_t)row * K + c);
+        const float4* pb = reinterpret_cast<const float4*>(B + (size_t)row * K + c);
+        split_store8(a_base, row, c, pa[0], pa[1]);
+        split_store8(b_base, row, c, pb[0], pb[1]);
     }
     fence_async_smem();
     tc_fence_before();
@@ -597,17 +641,21 @@ tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     if (threadIdx.x == 0) {
-        const uint32_t a_hi = smem_u32(a_base), a_lo = a_hi + 4 * SLAB, b_hi = smem_u32(b_base), b_lo = b_hi + 4 * SLAB;
-        uint32_t acc = 0;
-        for (int kc = 0; kc < K / 32; ++kc)
-            for (int k8 = 0; k8 < 4; ++k8) {
-                const uint64_t adv = (uint64_t)(k8 * 2);
-                if (terms == 3) {
-                    umma_tf32(tmem, smem_desc(a_lo + kc * SLAB) + adv, smem_desc(b_hi + kc * SLAB) + adv, acc); acc = 1;
-                    umma_tf32(tmem, smem_desc(a_hi + kc * SLAB) + adv, smem_desc(b_lo + kc * SLAB) + adv, 1);
+        const uint32_t a_hi = smem_u32(a_base), a_lo = a_hi + 2 * SLAB, b_hi = smem_u32(b_base), b_lo = b_hi + 2 * SLAB;
+        constexpr uint32_t IDESC = idesc_f16(64);
+        for (int nh = 0; nh < 2; ++nh) {
+            uint32_t acc = 0;
+            const uint32_t boff = (uint32_t)nh * 64 * 128;           // rows 64.. of the B slab
+            for (int kb = 0; kb < K / 64; ++kb)
+                for (int k16 = 0; k16 < 4; ++k16) {
+                    const uint64_t adv = (uint64_t)(k16 * 2);
+                    if (terms == 3) {
+                        umma_f16(tmem + nh * 64, smem_desc(a_lo + kb * SLAB) + adv, smem_desc(b_hi + kb * SLAB + boff) + adv, IDESC, acc); acc = 1;
+                        umma_f16(tmem + nh * 64, smem_desc(a_hi + kb * SLAB) + adv, smem_desc(b_lo + kb * SLAB + boff) + adv, IDESC, 1);
+                    }
+                    umma_f16(tmem + nh * 64, smem_desc(a_hi + kb * SLAB) + adv, smem_desc(b_hi + kb * SLAB + boff) + adv, IDESC, acc); acc = 1;
                 }
-                umma_tf32(tmem, smem_desc(a_hi + kc * SLAB) + adv, smem_desc(b_hi + kc * SLAB) + adv, acc); acc = 1;
-            }
+        }
         umma_commit(smem_u32(&bar));
     }
     mbar_wait(smem_u32(&bar), 0);
@@ -619,11 +667,59 @@ tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B
         tmem_wait_ld();
         for (int j = 0; j < 32; ++j) D[(size_t)row * 128 + part * 32 + j] = __uint_as_float(r[j]);
     }
-    (void)lane;
     tc_fence_before();
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+}
+
+// ------------------------------------------------------------------------------------ MMA rate probe
+// Times `count` back-to-back tcgen05.mma (M = 128, K = 32 bytes) issued by one thread against zeroed shared-memory
+// operands: mode bits 0..1 = N (0: 64, 1: 128, 2: 256), bits 4..7 = number of accumulators rotated over (1..4),
+// bit 8 = kind::tf32 instead of kind::f16.  cycles[blockIdx.x] = clock64 delta from first issue to commit arrival.
+__global__ void __launch_bounds__(128, 1)
+tc_mma_rate_kernel(int mode, int count, long long* __restrict__ cycles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 6 * SLAB / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t n = 64u << (mode & 3), nacc = (uint32_t)((mode >> 4) & 15), tf32 = (mode >> 8) & 1;
+    long long t0 = 0;
+    if (threadIdx.x == 0) {
+        const uint32_t a = smem_u32(smem), b = a + 2 * SLAB;
+        const uint32_t idesc = tf32 ? ((1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24)) : idesc_f16(n);
+        t0 = clock64();
+        for (int i = 0; i < count; ++i) {
+            const uint32_t d = tmem + (uint32_t)(i % nacc) * n;
+            const uint64_t ad = smem_desc(a + (i & 1) * SLAB) + (uint64_t)((i >> 1) & 3) * 2;
+            const uint64_t bd = smem_desc(b + (i & 1) * SLAB) + (uint64_t)((i >> 1) & 3) * 2;
+            if (tf32)
+                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                             ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+            else
+                umma_f16(d, ad, bd, idesc, 1);
+        }
+        umma_commit(smem_u32(&bar));
+    }
+    mbar_wait(smem_u32(&bar), 0);
+    if (threadIdx.x == 0) cycles[blockIdx.x] = clock64() - t0;
+    tc_fence_after();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
 }  // namespace tc
@@ -647,7 +743,7 @@ int loftr_tc_pack(const riders_loftr_weights& w, int layer_slot, void* tc_ws, cu
     P.wq = w.wq; P.wk = w.wk; P.wv = w.wv; P.wm = w.wm; P.w1 = w.w1; P.w2 = w.w2;
     P.dst = pack_base(tc_ws) + (size_t)layer_slot * tc::LAYER_PACK_BYTES;
     count_launches(1);
-    tc::loftr_pack_weights_kernel<<<ceil_div(tc::NCHUNK * 128 * 8, 256), 256, 0, st>>>(P);
+    tc::loftr_pack_weights_kernel<<<ceil_div(tc::NCHUNK * 64 * 8, 256), 256, 0, st>>>(P);
     return check_launch("loftr_pack_weights");
 }
 
@@ -678,8 +774,8 @@ int loftr_tc_run(const float* x, const float* src, const riders_loftr_weights& w
 extern "C" int riders_debug_tc_gemm(const float* a, const float* b, float* d, int K, int terms, void* stream) {
     using namespace riders;
     RIDERS_REQUIRE(a && b && d, "debug_tc_gemm: null pointer");
-    RIDERS_REQUIRE((K == 32 || K == 64) && (terms == 1 || terms == 3), "debug_tc_gemm: K=%d terms=%d unsupported", K, terms);
-    const int smem = 1024 + tc::A_BYTES;
+    RIDERS_REQUIRE((K == 64 || K == 128) && (terms == 1 || terms == 3), "debug_tc_gemm: K=%d terms=%d unsupported", K, terms);
+    const int smem = 1024 + 2 * tc::OPER_BYTES;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(tc::tc_gemm_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
@@ -694,4 +790,21 @@ extern "C" int riders_debug_tc_gemm(const float* a, const float* b, float* d, in
 extern "C" int riders_debug_loftr_trace(long long* device_buffer_256) {
     riders::g_loftr_trace = device_buffer_256;
     return RIDERS_OK;
+}
+
+extern "C" int riders_debug_tc_mma_rate(int mode, int count, int ctas, long long* device_cycles, void* stream) {
+    using namespace riders;
+    RIDERS_REQUIRE(device_cycles && count > 0 && ctas > 0, "debug_tc_mma_rate: bad arguments");
+    const int nacc = (mode >> 4) & 15, n = 64 << (mode & 3);
+    RIDERS_REQUIRE((mode & 3) < 3 && nacc >= 1 && nacc * n <= 512, "debug_tc_mma_rate: mode %d unsupported", mode);
+    const int smem = 1024 + 6 * tc::SLAB;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(tc::tc_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return check_launch("debug_tc_mma_rate: shared memory attribute");
+        configured = true;
+    }
+    count_launches(1);
+    tc::tc_mma_rate_kernel<<<ctas, 128, smem, (cudaStream_t)stream>>>(mode, count, device_cycles);
+    return check_launch("debug_tc_mma_rate");
 }

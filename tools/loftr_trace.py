@@ -29,9 +29,8 @@ try:
     mhz = float(subprocess.check_output(["nvidia-smi", "--query-gpu=clocks.max.sm", "--format=csv,noheader,nounits"]).split()[0])
 except Exception:
     mhz = 1965.0
-E_NAMES = ["E0 start", "E0 x split done", "q/k/v ready", "attention+msg split done", "merge ready", "LN1 split done",
-           "mlp0[m] done (A free)", "x re-split done", "h ready", "relu(h0) split done", "mlp2 half ready",
-           "relu(h1) split done", "mlp2 ready", "LN2+store done"]
+E_NAMES = ["E0 start", "x (src) split done", "q/k/v ready", "attention half 0 done", "attention+msg split done", "merge ready",
+           "LN1 split done", "h ready", "relu(h) split done", "mlp2 ready", "LN2+store done"]
 for label, src in (("self", x), ("cross", s)):
     for _ in range(2):
         ops.loftr_layer(x, src, params, impl=ops.LOFTR_TCGEN05)
@@ -56,7 +55,7 @@ for label, src in (("self", x), ("cross", s)):
             print("   %-28s t=%8.2f  (+%6.2f)" % (name, (e[k] - t0) / mhz, (e[k] - prev) / mhz))
             prev = e[k]
         print(" %s MMA thread: segment [wait A, issue, of which waiting for weights]" % cta)
-        for seg in range(7):
+        for seg in range(5):
             w0, w1, w2, ws = m[seg * 4:seg * 4 + 4]
             if w1 == 0:
                 continue
