@@ -89,6 +89,12 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// one lane of a converged warp (the pattern ptxas recognises: no per-MMA election loop in the SASS)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
@@ -207,7 +213,8 @@ struct LayerArgs {
 
 // trace layout per traced CTA (blockIdx.x == 0 or gridDim.x / 2): 128 slots; [0..63] epilogue thread, [64..127] MMA thread
 #define TRACE_E(k) do { if (P.trace && tr_on && lane == 0 && warp == 4 && tile == (int)blockIdx.x) P.trace[tr_base + (k)] = clock64(); } while (0)
-#define TRACE_M(k) do { if (P.trace && tr_on && tile == (int)blockIdx.x) P.trace[tr_base + 64 + (k)] = clock64(); } while (0)
+#define TRACE_M(k) do { if (P.trace && tr_on && lane == 0 && tile == (int)blockIdx.x) P.trace[tr_base + 64 + (k)] = clock64(); } while (0)
+#define TRACE_W(k) do { if (P.trace && tr_on && lane == 0 && tile == (int)blockIdx.x) P.trace[tr_base + 64 + (k)] = wsum; } while (0)
 
 // ------------------------------------------------------------------------------------ the fused layer
 __global__ void __launch_bounds__(THREADS, 1)
@@ -259,16 +266,16 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                 }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+        {
             uint32_t n = 0, aph = 0, vph = 0;
             const uint32_t xo = smem_u32(x_base), ao = smem_u32(a_base), b0 = smem_u32(b_base);
             const uint32_t kv_src = P.is_self ? xo : ao;
             constexpr uint32_t IDESC = idesc_f16(64);
             long long wsum = 0;
             // one 128 x 128 weight block = 4 chunks (N half, K half): D[:, dcol + 64 nh ..] (+)= oper[:, 64 kb ..] W^T
-            auto issue_block = [&](uint32_t oper, uint32_t dcol, uint32_t acc_in) {
-#pragma unroll 1
+            auto issue_block = [&](uint32_t oper, uint32_t dcol, uint32_t acc_in, uint32_t commit_bar) {
+#pragma unroll
                 for (int j = 0; j < 4; ++j, ++n) {
                     const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1;
                     const long long tw = P.trace ? clock64() : 0;
@@ -279,14 +286,18 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                     const uint32_t d = tmem + dcol + nh * 64;
                     const uint64_t ah = smem_desc(oper + kb * SLAB), al = smem_desc(oper + (2 + kb) * SLAB);
                     const uint64_t bh = smem_desc(b0 + s * CHUNK), bl = smem_desc(b0 + s * CHUNK + CHUNK / 2);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k16 = 0; k16 < 4; ++k16) {              // 16 fp16 = 32 bytes per MMA along K
-                        const uint64_t adv = (uint64_t)(k16 * 2);
-                        umma_f16(d, al + adv, bh + adv, IDESC, acc_in | kb | (k16 > 0));
-                        umma_f16(d, ah + adv, bl + adv, IDESC, 1);
-                        umma_f16(d, ah + adv, bh + adv, IDESC, 1);
+                        for (int k16 = 0; k16 < 4; ++k16) {          // 16 fp16 = 32 bytes per MMA along K
+                            const uint64_t adv = (uint64_t)(k16 * 2);
+                            umma_f16(d, al + adv, bh + adv, IDESC, acc_in | kb | (k16 > 0));
+                            umma_f16(d, ah + adv, bl + adv, IDESC, 1);
+                            umma_f16(d, ah + adv, bh + adv, IDESC, 1);
+                        }
+                        umma_commit(bempty + 8 * s);                 // stage reusable once these MMAs retire
+                        if (j == 3 && commit_bar) umma_commit(commit_bar);
                     }
-                    umma_commit(bempty + 8 * s);                     // stage reusable once these MMAs retire
+                    __syncwarp();
                 }
             };
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
@@ -295,50 +306,46 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                 mbar_wait(a_ready, aph & 1); ++aph;
                 tc_fence_after();
                 TRACE_M(1); wsum = 0;
-                issue_block(xo, D0, 0);
-                issue_block(kv_src, D1, 0);
-                issue_block(kv_src, D2, 0);
-                umma_commit(d_ready);
-                issue_block(xo, D3, 0);
+                issue_block(xo, D0, 0, 0);
+                issue_block(kv_src, D1, 0, 0);
+                issue_block(kv_src, D2, 0, d_ready);
+                issue_block(xo, D3, 0, 0);
                 TRACE_M(2);
-                if (P.trace && tr_on && tile == (int)blockIdx.x) P.trace[tr_base + 64 + 3] = wsum;
+                TRACE_W(3);
                 // seg 1: v drained from D2 -> mlp.0[C :, :C] on x
                 TRACE_M(4);
                 mbar_wait(v_free, vph & 1); ++vph;
                 tc_fence_after();
                 TRACE_M(5); wsum = 0;
-                issue_block(xo, D2, 0);
+                issue_block(xo, D2, 0, 0);
                 TRACE_M(6);
-                if (P.trace && tr_on && tile == (int)blockIdx.x) P.trace[tr_base + 64 + 7] = wsum;
+                TRACE_W(7);
                 // seg 2: merge(msg)
                 TRACE_M(8);
                 mbar_wait(a_ready, aph & 1); ++aph;
                 tc_fence_after();
                 TRACE_M(9); wsum = 0;
-                issue_block(ao, D0, 0);
-                umma_commit(d_ready);
+                issue_block(ao, D0, 0, d_ready);
                 TRACE_M(10);
-                if (P.trace && tr_on && tile == (int)blockIdx.x) P.trace[tr_base + 64 + 11] = wsum;
+                TRACE_W(11);
                 // seg 3: mlp.0[:, C:] on m, accumulated onto the x halves
                 TRACE_M(12);
                 mbar_wait(a_ready, aph & 1); ++aph;
                 tc_fence_after();
                 TRACE_M(13); wsum = 0;
-                issue_block(ao, D3, 1);
-                issue_block(ao, D2, 1);
-                umma_commit(d_ready);
+                issue_block(ao, D3, 1, 0);
+                issue_block(ao, D2, 1, d_ready);
                 TRACE_M(14);
-                if (P.trace && tr_on && tile == (int)blockIdx.x) P.trace[tr_base + 64 + 15] = wsum;
+                TRACE_W(15);
                 // seg 4: mlp.2 on relu(h): [:, :C] from A, [:, C:] from X
                 TRACE_M(16);
                 mbar_wait(a_ready, aph & 1); ++aph;
                 tc_fence_after();
                 TRACE_M(17); wsum = 0;
-                issue_block(ao, D0, 0);
-                issue_block(xo, D0, 1);
-                umma_commit(d_ready);
+                issue_block(ao, D0, 0, 0);
+                issue_block(xo, D0, 1, d_ready);
                 TRACE_M(18);
-                if (P.trace && tr_on && tile == (int)blockIdx.x) P.trace[tr_base + 64 + 19] = wsum;
+                TRACE_W(19);
             }
         }
     } else {
@@ -697,21 +704,32 @@ tc_mma_rate_kernel(int mode, int count, long long* __restrict__ cycles) {
     const uint32_t tmem = tmem_slot;
     const uint32_t n = 64u << (mode & 3), nacc = (uint32_t)((mode >> 4) & 15), tf32 = (mode >> 8) & 1;
     long long t0 = 0;
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
         const uint32_t a = smem_u32(smem), b = a + 2 * SLAB;
         const uint32_t idesc = tf32 ? ((1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24)) : idesc_f16(n);
-        t0 = clock64();
-        for (int i = 0; i < count; ++i) {
-            const uint32_t d = tmem + (uint32_t)(i % nacc) * n;
-            const uint64_t ad = smem_desc(a + (i & 1) * SLAB) + (uint64_t)((i >> 1) & 3) * 2;
-            const uint64_t bd = smem_desc(b + (i & 1) * SLAB) + (uint64_t)((i >> 1) & 3) * 2;
-            if (tf32)
-                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
-                             ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(1u) : "memory");
-            else
-                umma_f16(d, ad, bd, idesc, 1);
+        uint32_t dd[8];
+        uint64_t ad[8], bd[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            dd[u] = tmem + ((uint32_t)u % nacc) * n;
+            ad[u] = smem_desc(a + (u & 1) * SLAB) + (uint64_t)((u >> 1) & 3) * 2;
+            bd[u] = smem_desc(b + (u & 1) * SLAB) + (uint64_t)((u >> 1) & 3) * 2;
         }
-        umma_commit(smem_u32(&bar));
+        t0 = clock64();
+        if (elect_one()) {
+            for (int i = 0; i < count; i += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (tf32)
+                        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                                     ::"r"(dd[u]), "l"(ad[u]), "l"(bd[u]), "r"(idesc), "r"(1u) : "memory");
+                    else
+                        umma_f16(dd[u], ad[u], bd[u], idesc, 1);
+                }
+            }
+            umma_commit(smem_u32(&bar));
+        }
+        __syncwarp();
     }
     mbar_wait(smem_u32(&bar), 0);
     if (threadIdx.x == 0) cycles[blockIdx.x] = clock64() - t0;
