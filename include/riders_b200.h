@@ -68,6 +68,19 @@ int riders_roi_gather_fwd(int n_levels,
                           float* const* out, int32_t* const* argmax,
                           void* stream);
 
+/* The same with a per-level output pixel stride (channels-last only): out[l] points at channel c0 of a wider
+ * (R, oh, ow, ld) map, ld = out_pixel_stride[l] floats >= C[l], so the gathered skip lands directly inside the
+ * decoder's concat buffer [upconv | skip] (utils/net_utils.py:474-569 torch.cat) and is never copied again.
+ * out_pixel_stride NULL or 0 entries = dense.  argmax[l] (if any) stays dense.                             */
+int riders_roi_gather_fwd_placed(int n_levels,
+                                 const float* const* feat, const int* C, const int* Hl, const int* Wl,
+                                 const float* spatial_scale, const int* oh, const int* ow,
+                                 int layout, int B,
+                                 const float* rois, int R,
+                                 int max_roi_w, int max_roi_h,
+                                 float* const* out, const int* out_pixel_stride, int32_t* const* argmax,
+                                 void* stream);
+
 /* gradient of A1 w.r.t. feat: deterministic (no float atomics); grad_feat must be zero-filled
  * by the caller.  Used by rcnet_main.train (RCNet/rcnet_main.py:342-358).                    */
 int riders_roi_gather_bwd(int n_levels,
@@ -233,11 +246,18 @@ int riders_leaky_concat_nhwc(const float* a, int Ca, const float* b, int Cb, lon
 /* the same with the (BatchNorm-folded) convolution bias added first: out[p][0:Ca] = leaky(a[p][:] + bias[:]) */
 int riders_bias_leaky_concat_nhwc(const float* a, const float* bias, int Ca, const float* b, int Cb,
                                   long long pixels, float slope, float* out, void* stream);
+/* ... into a map of out_pixel_stride >= Ca + Cb floats per pixel: with Cb = 0 and the skip channels already
+ * in place behind channel Ca (riders_roi_gather_fwd_placed) only the Ca produced channels are written.   */
+int riders_bias_leaky_place_nhwc(const float* a, const float* bias, int Ca, const float* b, int Cb,
+                                 long long pixels, float slope, float* out, int out_pixel_stride, void* stream);
 /* Sub-pixel form of "nearest 2x resize -> 3x3 convolution": y4 (N, 4*Ca, h, w) is the low-resolution convolution
  * with phase-major output channels ((2a+b)*Ca + c, see DecoderBlock.fold_upsample_); this writes
  * out (N, Ca+Cb, 2h, 2w): out[n][2i+a][2j+b][0:Ca] = act(y4[n][i][j][(2a+b)*Ca + :] + bias), [Ca:] = skip.   */
 int riders_d2s_bias_act_concat_nhwc(const float* y4, const float* bias, int Ca, const float* skip, int Cb,
                                     int N, int h, int w, float slope, float* out, void* stream);
+/* ... into a map of out_pixel_stride >= Ca + Cb floats per pixel (skip already in place: Cb = 0, skip = NULL) */
+int riders_d2s_bias_act_place_nhwc(const float* y4, const float* bias, int Ca, const float* skip, int Cb,
+                                   int N, int h, int w, float slope, float* out, int out_pixel_stride, void* stream);
 /* Decoder head in front of riders_confidence_reduce: logits (N,H,W) = conv3x3(act(x + bias)), zero padding,
  * x (N,H,W,C=16) channels-last RAW output of the last decoder convolution, weight_host (1,C,3,3) and
  * bias_host (C, or NULL) in HOST memory (they become kernel parameters).  MultiScaleDecoder.output0,

@@ -31,6 +31,7 @@ SIGNATURES = {
     "riders_device_arch": (ci, []),
     "riders_launch_count": (C.c_ulonglong, []),
     "riders_roi_gather_fwd": (ci, [ci, vp, vp, vp, vp, vp, vp, vp, ci, ci, vp, ci, ci, ci, vp, vp, vp]),
+    "riders_roi_gather_fwd_placed": (ci, [ci, vp, vp, vp, vp, vp, vp, vp, ci, ci, vp, ci, ci, ci, vp, vp, vp, vp]),
     "riders_roi_gather_bwd": (ci, [ci, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, vp, ci, vp, vp]),
     "riders_linear_attention_fwd": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp, vp]),
     "riders_loftr_workspace_bytes": (sz, [ci, ci, ci, ci]),
@@ -54,9 +55,11 @@ SIGNATURES = {
     "riders_upsample_nearest_nhwc": (ci, [vp, ci, ci, ci, ci, ci, ci, vp, vp]),
     "riders_leaky_concat_nhwc": (ci, [vp, ci, vp, ci, C.c_longlong, cf, ci, vp, vp]),
     "riders_bias_leaky_concat_nhwc": (ci, [vp, vp, ci, vp, ci, C.c_longlong, cf, vp, vp]),
+    "riders_bias_leaky_place_nhwc": (ci, [vp, vp, ci, vp, ci, C.c_longlong, cf, vp, ci, vp]),
     "riders_bias_act_nhwc": (ci, [vp, vp, ci, C.c_longlong, cf, vp, vp]),
     "riders_conv3x3_head_nhwc": (ci, [vp, ci, ci, ci, ci, vp, cf, vp, vp, vp]),
     "riders_d2s_bias_act_concat_nhwc": (ci, [vp, vp, ci, vp, ci, ci, ci, ci, cf, vp, vp]),
+    "riders_d2s_bias_act_place_nhwc": (ci, [vp, vp, ci, vp, ci, ci, ci, ci, cf, vp, ci, vp]),
     "riders_debug_set": (ci, [C.c_char_p, ci]),
     "riders_debug_loftr_trace": (ci, [vp]),
     "riders_debug_tc_gemm": (ci, [vp, vp, vp, ci, ci, vp]),

@@ -26,6 +26,7 @@ namespace riders {
 struct GatherLevel {
     const float* feat; float* out; int32_t* argmax;
     int C, H, W, oh, ow;
+    int ld;                    // floats per output pixel (channels-last only; C unless the output is a channel slice)
     float scale;
     long long first_item;      // prefix of work items (generic kernel)
 };
@@ -88,9 +89,9 @@ roi_gather_generic_kernel(const GatherParams P) {
                     if (v.w > best.w) { best.w = v.w; arg.w = idx; }
                 }
         }
-        const size_t o = (((size_t)r * L.oh + i) * L.ow + j) * L.C + (size_t)c * 4;
-        __stcs(reinterpret_cast<float4*>(L.out + o), best);
-        if (L.argmax) __stcs(reinterpret_cast<int4*>(L.argmax + o), arg);
+        const size_t px = ((size_t)r * L.oh + i) * L.ow + j;
+        __stcs(reinterpret_cast<float4*>(L.out + px * L.ld + (size_t)c * 4), best);
+        if (L.argmax) __stcs(reinterpret_cast<int4*>(L.argmax + px * L.C + (size_t)c * 4), arg);
     } else {
         float best = empty ? 0.f : -FLT_MAX;
         int arg = -1;
@@ -117,6 +118,7 @@ constexpr int TMA_MAX_LEVELS = RIDERS_MAX_LEVELS;
 struct TmaLevel {
     const float* feat; float* out;
     int C, H, W, oh, ow;
+    int ld;          // floats per output pixel (C, or more when out[l] is a channel slice of a wider map)
     float scale;
     int TI;          // pooled rows per CTA
     int BH, BW;      // TMA box rows / cols
@@ -255,7 +257,8 @@ roi_gather_tma_kernel(const __grid_constant__ TmaPack P) {
     int p = threadIdx.x >> L.cv_shift;
     int i = p / L.ow, j = p - i * L.ow;
     const int di = PP / L.ow, dj = PP - di * L.ow;
-    float4* out_base = reinterpret_cast<float4*>(L.out + (((size_t)r * L.oh + i0) * L.ow) * L.C) + c4;
+    float4* out_base = reinterpret_cast<float4*>(L.out + (((size_t)r * L.oh + i0) * L.ow) * L.ld) + c4;
+    const int LD4 = L.ld >> 2;                                       // float4s per output pixel
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 
     if (fits) {
@@ -272,8 +275,8 @@ roi_gather_tma_kernel(const __grid_constant__ TmaPack P) {
                 const bool e0 = (hb0.x | wb0.x) < 0, e1 = (hb1.x | wb1.x) < 0;
                 float4 v0 = bin_max_2x2(base, e0 ? make_int3(0, 0, 0) : hb0, e0 ? make_int3(0, 0, 0) : wb0);
                 float4 v1 = bin_max_2x2(base, e1 ? make_int3(0, 0, 0) : hb1, e1 ? make_int3(0, 0, 0) : wb1);
-                __stcs(out_base + (size_t)p * CV, e0 ? zero : v0);
-                if (two) __stcs(out_base + (size_t)(p + PP) * CV, e1 ? zero : v1);
+                __stcs(out_base + (size_t)p * LD4, e0 ? zero : v0);
+                if (two) __stcs(out_base + (size_t)(p + PP) * LD4, e1 ? zero : v1);
                 i = i1 + di; j = j1 + dj;
                 if (j >= L.ow) { j -= L.ow; ++i; }
             }
@@ -281,7 +284,7 @@ roi_gather_tma_kernel(const __grid_constant__ TmaPack P) {
             for (; p < npix; p += PP) {
                 const int3 hb = hbin[i], wb = wbin[j];
                 const bool e = (hb.x | wb.x) < 0;
-                __stcs(out_base + (size_t)p * CV, e ? zero : bin_max_any(base, hb, wb, row_bytes, px_bytes));
+                __stcs(out_base + (size_t)p * LD4, e ? zero : bin_max_any(base, hb, wb, row_bytes, px_bytes));
                 i += di; j += dj;
                 if (j >= L.ow) { j -= L.ow; ++i; }
             }
@@ -300,7 +303,7 @@ roi_gather_tma_kernel(const __grid_constant__ TmaPack P) {
                     for (int w = w0; w < w0 + wb.z; ++w)
                         best = max4(best, __ldg(reinterpret_cast<const float4*>(src + (size_t)h * g_row + (size_t)w * L.C)));
             }
-            __stcs(out_base + (size_t)p * CV, best);
+            __stcs(out_base + (size_t)p * LD4, best);
             i += di; j += dj;
             if (j >= L.ow) { j -= L.ow; ++i; }
         }
@@ -453,6 +456,17 @@ extern "C" int riders_roi_gather_fwd(int n_levels,
                                      int layout, int B, const float* rois, int R,
                                      int max_roi_w, int max_roi_h,
                                      float* const* out, int32_t* const* argmax, void* stream) {
+    return riders_roi_gather_fwd_placed(n_levels, feat, C, Hl, Wl, spatial_scale, oh, ow, layout, B, rois, R,
+                                        max_roi_w, max_roi_h, out, nullptr, argmax, stream);
+}
+
+extern "C" int riders_roi_gather_fwd_placed(int n_levels,
+                                            const float* const* feat, const int* C, const int* Hl, const int* Wl,
+                                            const float* spatial_scale, const int* oh, const int* ow,
+                                            int layout, int B, const float* rois, int R,
+                                            int max_roi_w, int max_roi_h,
+                                            float* const* out, const int* out_pixel_stride, int32_t* const* argmax,
+                                            void* stream) {
     using namespace riders;
     RIDERS_REQUIRE(n_levels > 0 && n_levels <= RIDERS_MAX_LEVELS, "roi_gather: n_levels=%d out of range", n_levels);
     RIDERS_REQUIRE(layout == RIDERS_LAYOUT_NCHW || layout == RIDERS_LAYOUT_NHWC, "roi_gather: bad layout %d", layout);
@@ -473,19 +487,22 @@ extern "C" int riders_roi_gather_fwd(int n_levels,
         RIDERS_REQUIRE(C[l] > 0 && Hl[l] > 0 && Wl[l] > 0 && oh[l] > 0 && ow[l] > 0, "roi_gather: bad dims at level %d", l);
         RIDERS_REQUIRE((long long)Hl[l] * Wl[l] < (1ll << 31), "roi_gather: map too large at level %d", l);
         const bool want_arg = argmax && argmax[l];
+        const int ld = (out_pixel_stride && out_pixel_stride[l] > 0) ? out_pixel_stride[l] : C[l];
+        RIDERS_REQUIRE(ld == C[l] || (layout == RIDERS_LAYOUT_NHWC && ld > C[l] && (ld & 3) == 0),
+                       "roi_gather: out_pixel_stride[%d]=%d needs the channels-last layout, >= C and %%4==0", l, ld);
         if (layout == RIDERS_LAYOUT_NHWC) {
             RIDERS_REQUIRE((C[l] & 3) == 0 && (((uintptr_t)feat[l]) & 15) == 0 && (((uintptr_t)out[l]) & 15) == 0,
                            "roi_gather: channels-last path needs C%%4==0 and 16-byte aligned maps (level %d)", l);
             if (!want_arg) {
                 TmaLevel& T = TP.lv[TP.n_levels];
-                T.feat = feat[l]; T.out = out[l]; T.C = C[l]; T.H = Hl[l]; T.W = Wl[l]; T.oh = oh[l]; T.ow = ow[l];
+                T.feat = feat[l]; T.out = out[l]; T.C = C[l]; T.H = Hl[l]; T.W = Wl[l]; T.oh = oh[l]; T.ow = ow[l]; T.ld = ld;
                 T.scale = spatial_scale[l];
                 if (plan_tma_level(T, max_roi_w, max_roi_h)) { ++TP.n_levels; continue; }
             }
         }
         GatherLevel& G = P.lv[P.n_levels++];
         G.feat = feat[l]; G.out = out[l]; G.argmax = want_arg ? argmax[l] : nullptr;
-        G.C = C[l]; G.H = Hl[l]; G.W = Wl[l]; G.oh = oh[l]; G.ow = ow[l]; G.scale = spatial_scale[l];
+        G.C = C[l]; G.H = Hl[l]; G.W = Wl[l]; G.oh = oh[l]; G.ow = ow[l]; G.ld = ld; G.scale = spatial_scale[l];
         G.first_item = items;
         const long long cg = (layout == RIDERS_LAYOUT_NHWC) ? C[l] / 4 : C[l];
         items += (long long)R * cg * oh[l] * ow[l];

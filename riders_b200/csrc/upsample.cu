@@ -132,7 +132,7 @@ bias_act_generic_kernel(const float* __restrict__ x, const float* __restrict__ b
 
 __global__ void __launch_bounds__(256)
 bias_leaky_concat_nhwc_kernel(const float4* __restrict__ a, const float* __restrict__ bias, const float4* __restrict__ b,
-                              float4* __restrict__ out, int Ca4, int Cb4, long long pixels, float slope) {
+                              float4* __restrict__ out, int Ca4, int Cb4, int ld4, long long pixels, float slope) {
     const int Ct4 = Ca4 + Cb4;
     const long long total = pixels * Ct4;
     for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
@@ -148,7 +148,7 @@ bias_leaky_concat_nhwc_kernel(const float4* __restrict__ a, const float* __restr
         } else {
             v = __ldcs(b + p * Cb4 + (c - Ca4));
         }
-        out[e] = v;
+        out[p * ld4 + c] = v;                       // ld4 == Ct4: dense; larger: the skip channels are already in place
     }
 }
 
@@ -180,7 +180,13 @@ extern "C" int riders_bias_act_nhwc(const float* x, const float* bias, int C, lo
 
 extern "C" int riders_bias_leaky_concat_nhwc(const float* a, const float* bias, int Ca, const float* b, int Cb,
                                              long long pixels, float slope, float* out, void* stream) {
+    return riders_bias_leaky_place_nhwc(a, bias, Ca, b, Cb, pixels, slope, out, Ca + Cb, stream);
+}
+
+extern "C" int riders_bias_leaky_place_nhwc(const float* a, const float* bias, int Ca, const float* b, int Cb,
+                                            long long pixels, float slope, float* out, int out_pixel_stride, void* stream) {
     using namespace riders;
+    RIDERS_REQUIRE(out_pixel_stride >= Ca + Cb && (out_pixel_stride & 3) == 0, "bias_leaky_place: out_pixel_stride=%d < %d channels or not %%4", out_pixel_stride, Ca + Cb);
     RIDERS_REQUIRE(Ca > 0 && Cb >= 0 && pixels >= 0, "bias_leaky_concat: bad shape");
     RIDERS_REQUIRE((Ca & 3) == 0 && (Cb & 3) == 0, "bias_leaky_concat: channel counts must be multiples of 4 (%d, %d)", Ca, Cb);
     if (pixels == 0) return RIDERS_OK;
@@ -193,7 +199,7 @@ extern "C" int riders_bias_leaky_concat_nhwc(const float* a, const float* bias, 
     count_launches(1);
     bias_leaky_concat_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(a), bias, reinterpret_cast<const float4*>(b), reinterpret_cast<float4*>(out),
-        Ca / 4, Cb / 4, pixels, slope);
+        Ca / 4, Cb / 4, out_pixel_stride / 4, pixels, slope);
     return check_launch("bias_leaky_concat_nhwc");
 }
 
@@ -211,7 +217,7 @@ namespace riders {
 
 __global__ void __launch_bounds__(256)
 d2s_bias_act_concat_kernel(const float4* __restrict__ y4, const float* __restrict__ bias, const float4* __restrict__ skip,
-                           float4* __restrict__ out, int Ca4, int Cb4, int ct_shift, int h, int w, float slope,
+                           float4* __restrict__ out, int Ca4, int Cb4, int ld4, int ct_shift, int h, int w, float slope,
                            long long rows, int rows_per_block) {
     // a block streams `rows_per_block` consecutive output rows as one flat run of float4s: (row, position) advance
     // incrementally, the channel split uses a shift when Ct4 is a power of two (RC-Net: 4, 16, 64)
@@ -239,7 +245,7 @@ d2s_bias_act_concat_kernel(const float4* __restrict__ y4, const float* __restric
                 cc[u] = c;
                 v[u] = act[u] ? __ldcs(y4 + (((size_t)n * h + (Y >> 1)) * (size_t)w + (X >> 1)) * (4 * Ca4) + (2 * (Y & 1) + (X & 1)) * Ca4 + c)
                               : __ldcs(skip + ((size_t)row * W2 + X) * Cb4 + (c - Ca4));
-                dstp[u] = out + (size_t)row * len + pos;
+                dstp[u] = out + ((size_t)row * W2 + X) * ld4 + c;      // ld4 == Ct4: dense; larger: the skip channels are already in place
                 pos += 256;
                 while (pos >= len) { pos -= len; ++r; }
             }
@@ -265,7 +271,13 @@ d2s_bias_act_concat_kernel(const float4* __restrict__ y4, const float* __restric
 
 extern "C" int riders_d2s_bias_act_concat_nhwc(const float* y4, const float* bias, int Ca, const float* skip, int Cb,
                                                int N, int h, int w, float slope, float* out, void* stream) {
+    return riders_d2s_bias_act_place_nhwc(y4, bias, Ca, skip, Cb, N, h, w, slope, out, Ca + Cb, stream);
+}
+
+extern "C" int riders_d2s_bias_act_place_nhwc(const float* y4, const float* bias, int Ca, const float* skip, int Cb,
+                                              int N, int h, int w, float slope, float* out, int out_pixel_stride, void* stream) {
     using namespace riders;
+    RIDERS_REQUIRE(out_pixel_stride >= Ca + Cb && (out_pixel_stride & 3) == 0, "d2s_bias_act_place: out_pixel_stride=%d < %d channels or not %%4", out_pixel_stride, Ca + Cb);
     RIDERS_REQUIRE(N >= 0 && Ca > 0 && Cb >= 0 && h > 0 && w > 0, "d2s_bias_act_concat: bad shape");
     RIDERS_REQUIRE((Ca & 3) == 0 && (Cb & 3) == 0, "d2s_bias_act_concat: channel counts must be multiples of 4 (%d, %d)", Ca, Cb);
     if (N == 0) return RIDERS_OK;
@@ -281,6 +293,6 @@ extern "C" int riders_d2s_bias_act_concat_nhwc(const float* y4, const float* bia
     count_launches(1);
     d2s_bias_act_concat_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(y4), bias, reinterpret_cast<const float4*>(skip), reinterpret_cast<float4*>(out),
-        Ca / 4, Cb / 4, ct_shift, h, w, slope, rows, rows_per_block);
+        Ca / 4, Cb / 4, out_pixel_stride / 4, ct_shift, h, w, slope, rows, rows_per_block);
     return check_launch("d2s_bias_act_concat_nhwc");
 }

@@ -111,12 +111,40 @@ def _is_channels_last(t):
     return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous()
 
 
-def roi_gather(feats, boxes, scales, out_sizes, max_roi=None, want_argmax=False, chunk=32768):
+def placed_skip_buffers(R, lead_channels, skip_channels, out_sizes, device):
+    """Concat buffers of the decoder, allocated BEFORE the gather: buffer l is (R, lead + C, oh, ow) channels_last
+    and the returned view ``buf[:, lead:]`` is where roi_gather writes the pooled skip of level l.  The decoder
+    block later finds the buffer behind the view (``placed_parent``) and writes its own ``lead`` channels in
+    front - the torch.cat of utils/net_utils.py:474-569 without ever copying the skip."""
+    views = []
+    for lead, c, (oh, ow) in zip(lead_channels, skip_channels, out_sizes):
+        buf = torch.empty((R, oh, ow, lead + c), device=device, dtype=torch.float32).permute(0, 3, 1, 2)
+        views.append(buf[:, lead:])
+    return views
+
+
+def placed_parent(skip, lead):
+    """If ``skip`` (N,C,H,W) is the trailing-channel view made by ``placed_skip_buffers`` with ``lead`` channels in
+    front, return the full (N, lead + C, H, W) channels_last buffer (same storage), else None."""
+    if skip is None or skip.dim() != 4 or lead <= 0 or lead % 4 or skip.dtype != torch.float32 or not skip.is_cuda:
+        return None
+    N, Cs, H, W = skip.shape
+    ld = lead + Cs
+    if skip.stride() != (H * W * ld, 1, W * ld, ld) or skip.storage_offset() < lead:
+        return None
+    if (skip.storage_offset() - lead) % 4 or skip.untyped_storage().nbytes() < ((skip.storage_offset() - lead) + N * H * W * ld) * 4:
+        return None
+    return torch.as_strided(skip, (N, ld, H, W), (H * W * ld, 1, W * ld, ld), skip.storage_offset() - lead)
+
+
+def roi_gather(feats, boxes, scales, out_sizes, max_roi=None, want_argmax=False, chunk=32768, outs=None):
     """All pyramid levels of torchvision.ops.roi_pool in one call (RCNet/networks.py:418-433).
 
     feats: list of (B,C,H,W) float32 CUDA maps, all NCHW-contiguous or all channels_last.
     Returns list of (R,C,oh,ow) tensors in the same memory format (plus argmax list if asked).
     max_roi=(w,h): upper bound of the RoI size in image pixels (enables the TMA path).
+    outs: optional pre-allocated destinations (channels_last inputs only): (R,C,oh,ow) views with channel stride 1
+    and any pixel stride >= C, e.g. from ``placed_skip_buffers``.
     """
     feats = list(feats)
     _need_cuda(*feats)
@@ -129,9 +157,24 @@ def roi_gather(feats, boxes, scales, out_sizes, max_roi=None, want_argmax=False,
     rois = boxes_to_rois(boxes, dev)
     R, B = rois.shape[0], feats[0].shape[0]
     fmt = torch.channels_last if nhwc else torch.contiguous_format
-    outs = [torch.empty((R, f.shape[1], oh, ow), device=dev, dtype=torch.float32, memory_format=fmt)
-            for f, (oh, ow) in zip(feats, out_sizes)]
+    lds = None
+    if outs is not None:
+        if not nhwc or want_argmax:
+            raise _lib.RidersError("roi_gather(outs=...) needs channels_last maps and no argmax")
+        lds = []
+        for o, f, (oh, ow) in zip(outs, feats, out_sizes):
+            ld = o.stride(3)
+            if (tuple(o.shape) != (R, f.shape[1], oh, ow) or o.dtype != torch.float32 or o.device != dev or o.stride(1) != 1
+                    or o.stride(2) != ow * ld or o.stride(0) != oh * ow * ld or ld < f.shape[1] or ld % 4 or o.data_ptr() % 16):
+                raise _lib.RidersError("roi_gather(outs=...): destination %s / strides %s do not describe a channel slice of a "
+                                       "channels-last map" % (tuple(o.shape), o.stride()))
+            lds.append(ld)
+        outs = list(outs)
+    else:
+        outs = [torch.empty((R, f.shape[1], oh, ow), device=dev, dtype=torch.float32, memory_format=fmt)
+                for f, (oh, ow) in zip(feats, out_sizes)]
     args = [torch.empty(o.shape, device=dev, dtype=torch.int32, memory_format=fmt) for o in outs] if want_argmax else None
+    ld_arr = _int_array(lds) if lds is not None else None
     n = len(feats)
     Cs = _int_array([f.shape[1] for f in feats])
     Hs = _int_array([f.shape[2] for f in feats])
@@ -147,10 +190,10 @@ def roi_gather(feats, boxes, scales, out_sizes, max_roi=None, want_argmax=False,
         a_ptrs = _ptr_array([a[r0:r1] for a in args]) if want_argmax else None
         nb = sum(o[r0:r1].numel() for o in outs) * 4 + (r1 - r0) * 20          # written patches + RoIs (maps: see bench.py)
         with _span("roi_gather", nb):
-            rc = L.riders_roi_gather_fwd(n, _ptr_array(feats), Cs, Hs, Ws, sc, ohs, ows,
-                                         LAYOUT_NHWC if nhwc else LAYOUT_NCHW, B,
-                                         _ptr(rois[r0:r1]), r1 - r0, mw, mh, o_ptrs, a_ptrs, _stream())
-        _lib.check(rc, "riders_roi_gather_fwd")
+            rc = L.riders_roi_gather_fwd_placed(n, _ptr_array(feats), Cs, Hs, Ws, sc, ohs, ows,
+                                                LAYOUT_NHWC if nhwc else LAYOUT_NCHW, B,
+                                                _ptr(rois[r0:r1]), r1 - r0, mw, mh, o_ptrs, ld_arr, a_ptrs, _stream())
+        _lib.check(rc, "riders_roi_gather_fwd_placed")
     return (outs, args) if want_argmax else outs
 
 
@@ -234,10 +277,22 @@ def bias_act_(x, bias, slope):
 
 def d2s_bias_act_concat(y4, bias, skip, slope=0.2):
     """Depth-to-space (2x2, phase-major channels) + bias + LeakyReLU (+ concat of ``skip``) in one pass.
-    y4 (N, 4*Ca, h, w) channels_last -> (N, Ca [+ Cb], 2h, 2w) channels_last."""
+    y4 (N, 4*Ca, h, w) channels_last -> (N, Ca [+ Cb], 2h, 2w) channels_last.  A ``skip`` that already sits behind
+    Ca free channels of a wider buffer (``placed_skip_buffers``) is not copied: only the Ca channels are written."""
     _need_cuda(y4, bias, skip)
     N, C4, h, w = y4.shape
     Ca = C4 // 4
+    parent = placed_parent(skip, Ca)
+    if parent is not None:
+        if not (_is_channels_last(y4) and y4.dtype == torch.float32 and Ca % 4 == 0) or tuple(skip.shape[2:]) != (2 * h, 2 * w) \
+                or skip.shape[0] != N:
+            raise _lib.RidersError("d2s_bias_act_concat (placed skip): shape / layout mismatch")
+        b = _f32c(bias) if bias is not None else None
+        with _span("d2s_bias_act_concat", 2 * y4.numel() * 4):
+            rc = _lib.lib().riders_d2s_bias_act_place_nhwc(_ptr(y4), _ptr(b), Ca, None, 0, N, h, w, float(slope),
+                                                           _ptr(parent), parent.shape[1], _stream())
+        _lib.check(rc, "riders_d2s_bias_act_place_nhwc")
+        return parent
     Cb = skip.shape[1] if skip is not None else 0
     for t in (y4, skip):
         if t is not None and not (_is_channels_last(t) and t.dtype == torch.float32 and t.shape[1] % 4 == 0):
@@ -289,6 +344,14 @@ def leaky_concat(a, b, slope=0.2, act_on_a=True, bias=None):
     if bias is not None:
         _need_cuda(a, b, bias)
         N, Ca, H, W = a.shape
+        parent = placed_parent(b, Ca)
+        if parent is not None and tuple(b.shape[2:]) == (H, W) and b.shape[0] == N and _is_channels_last(a) and Ca % 4 == 0:
+            bias = _f32c(bias)
+            with _span("leaky_concat", 2 * a.numel() * 4):
+                rc = _lib.lib().riders_bias_leaky_place_nhwc(_ptr(a), _ptr(bias), Ca, None, 0, N * H * W, float(slope),
+                                                             _ptr(parent), parent.shape[1], _stream())
+            _lib.check(rc, "riders_bias_leaky_place_nhwc")
+            return parent
         Cb = b.shape[1]
         out = torch.empty((N, Ca + Cb, H, W), device=a.device, dtype=torch.float32, memory_format=torch.channels_last)
         bias = _f32c(bias)

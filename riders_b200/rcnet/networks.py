@@ -186,8 +186,10 @@ class DecoderBlock(torch.nn.Module):
         elif shape is None:
             shape = (2 * x.shape[2], 2 * x.shape[3])
         up = self.deconv.conv
+        # a skip gathered straight into this block's concat buffer (ops.placed_skip_buffers) counts as channels-last
+        skip_cl = skip is not None and (ops._is_channels_last(skip) or ops.placed_parent(skip, up.conv.out_channels) is not None)
         if (self._w4 is not None and tuple(shape) == (2 * x.shape[2], 2 * x.shape[3]) and up.fast_ok(x)
-                and (skip is None or (ops._is_channels_last(skip) and skip.shape[1] % 4 == 0))):
+                and (skip is None or (skip_cl and skip.shape[1] % 4 == 0))):
             # exact 2x block: sub-pixel convolution on the low-resolution map (the resized map never exists),
             # then depth-to-space + bias + LeakyReLU (+ skip concat) in one pass
             y4 = F.conv2d(x, self._w4, None, 1, 1)
@@ -196,7 +198,7 @@ class DecoderBlock(torch.nn.Module):
         if raw:
             return self.conv.raw(self.deconv(x, shape=shape))
         if (self.skip_channels > 0 and self._leaky and not up.use_batch_norm and not torch.is_grad_enabled()
-                and x.is_cuda and x.dtype == torch.float32 and ops._is_channels_last(x) and ops._is_channels_last(skip)
+                and x.is_cuda and x.dtype == torch.float32 and ops._is_channels_last(x) and skip_cl
                 and x.shape[1] % 4 == 0 and up.conv.out_channels % 4 == 0 and skip.shape[1] % 4 == 0):
             # inference fast path (BatchNorm folded): resize -> conv(+bias) -> [LeakyReLU | skip] in one pass -> conv
             c = up.conv
@@ -309,12 +311,20 @@ class RCNetEncoder(torch.nn.Module):
         image_tf = tok_image.permute(0, 2, 1).reshape(latent_pooled.shape)
         return torch.cat([image_tf, depth_tf], dim=1)
 
-    def gather_skips(self, skips_image, b_boxes):
+    def gather_skips(self, skips_image, b_boxes, lead_channels=None):
         """Skip half of ``encode_points``: the four pooled skip levels (networks.py:421-433); 1.38 MB per
-        point, so callers chunk the points to bound the decoder's activation memory."""
+        point, so callers chunk the points to bound the decoder's activation memory.  ``lead_channels`` (one per
+        level, from ``MultiScaleDecoder.skip_lead_channels``): gather each level straight into the concat buffer of
+        the decoder block that consumes it, behind that many free channels (channels-last maps only)."""
         levels = self.pyramid(len(skips_image))[:-1]
         ph, pw = self.input_patch_size_image[-2], self.input_patch_size_image[-1]
-        return ops.roi_gather(list(skips_image), b_boxes, [s for s, _ in levels], [o for _, o in levels], max_roi=(pw, ph))
+        outs = None
+        if (lead_channels is not None and all(ops._is_channels_last(f) for f in skips_image)
+                and all(l > 0 and l % 4 == 0 for l in lead_channels) and torch.is_tensor(b_boxes)):
+            outs = ops.placed_skip_buffers(b_boxes.shape[0], lead_channels, [f.shape[1] for f in skips_image],
+                                           [o for _, o in levels], skips_image[0].device)
+        return ops.roi_gather(list(skips_image), b_boxes, [s for s, _ in levels], [o for _, o in levels], max_roi=(pw, ph),
+                              outs=outs)
 
     def encode_points(self, latent_image, skips_image, points, b_boxes):
         """Everything after the backbone (networks.py:418-451).  ``b_boxes`` may also be an (R,5)
@@ -366,6 +376,11 @@ class MultiScaleDecoder(torch.nn.Module):
         for i in range(depth, 7):
             setattr(self, 'deconv%d' % i, None)
         self.output0 = Conv2d(cin, output_channels, 3, 1, weight_initializer, output_func, False)
+
+    def skip_lead_channels(self, n_skips):
+        """Output channels of the up-convolution in front of each skip (skips[i] feeds block ``_order[n_skips-1-i]``,
+        see ``forward``): the number of channels a placed skip must leave free in its concat buffer."""
+        return [getattr(self, self._order[n_skips - 1 - i]).deconv.conv.conv.out_channels for i in range(n_skips)]
 
     def forward(self, x, skips, shape=None):
         n = len(skips) - 1

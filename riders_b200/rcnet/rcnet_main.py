@@ -78,9 +78,11 @@ def forward_output_batched(model, images, radar_points, frame_offsets, response_
     # latent path (1/32-level gather + point MLP + LoFTR) for every point of the batch at once: 1366 tiles of
     # 6 points fill the 148 SMs in ~9 full waves; the skip gather + decoder run per chunk of points.
     latent = enc.encode_latent(latent_image, radar_points, rois)
+    # each pooled skip is gathered straight into the concat buffer of the decoder block that consumes it
+    lead = dec.skip_lead_channels(len(skips_image)) if hasattr(dec, 'skip_lead_channels') else None
     for s in range(0, R, chunk_points):
         e = min(R, s + chunk_points)
-        skips = enc.gather_skips(skips_image, rois[s:e])
+        skips = enc.gather_skips(skips_image, rois[s:e], lead_channels=lead)
         logits[s:e] = dec(x=latent[s:e], skips=skips, shape=(ph, pw))[-1]
     return ops.confidence_reduce(logits, radar_points, frame_offsets, H, W, response_thr, logits=True,
                                  want_select=return_select)[:3 if return_select else 2]

@@ -656,3 +656,45 @@ def test_training_step_gradients_match_the_reference_path():
         assert float((pg.grad.cpu() - pc.grad).abs().max()) <= 2e-3 * scale + 1e-7, name      # train-mode BatchNorm amplifies fp32 re-association
         checked += 1
     assert checked > 50
+
+
+def test_gather_into_placed_concat_buffers_is_bit_exact_and_never_copied():
+    """Skips gathered straight into the decoder's concat buffers (riders_roi_gather_fwd_placed) + the d2s / bias-leaky
+    kernels that fill the leading channels == dense gather followed by the concat kernels, bit for bit."""
+    rng = np.random.default_rng(11)
+    H, W, patch = 512, 640, (240, 100)
+    pts, boxes = synth.radar_points(5, 20, H, W, patch)
+    corner = np.array([[0, 0], [W - 1, H - 1]], np.float32) + [50, 120]
+    boxes[:2] = np.concatenate([corner - [50, 120], corner + [50, 120]], 1)
+    shapes = [(32, 376, 370), (64, 188, 185), (128, 94, 93), (128, 47, 47)]
+    scales, sizes = rr.rcnet_levels(patch)
+    scales, sizes = scales[:4], sizes[:4]
+    feats = [cu(rng.standard_normal((2,) + s).astype(np.float32)).contiguous(memory_format=torch.channels_last) for s in shapes]
+    rois = cu(rr.boxes_list_to_rois([boxes[:9], boxes[9:]]))
+    dense = ops.roi_gather(feats, rois, scales, sizes, max_roi=(100, 240))
+    lead = [32, 64, 128, 128]
+    views = ops.placed_skip_buffers(rois.shape[0], lead, [s[0] for s in shapes], sizes, feats[0].device)
+    for v in views:
+        ops.placed_parent(v, v.stride(3) - v.shape[1]).fill_(float("nan"))
+    placed = ops.roi_gather(feats, rois, scales, sizes, max_roi=(100, 240), outs=views)
+    for l in range(4):
+        assert placed[l].data_ptr() == views[l].data_ptr() and torch.equal(placed[l], dense[l]), "level %d" % l
+        parent = ops.placed_parent(placed[l], lead[l])
+        assert parent is not None and parent.shape[1] == lead[l] + shapes[l][0] and torch.isnan(parent[:, :lead[l]]).all()
+        assert ops.placed_parent(placed[l], lead[l] + 4) is None and ops.placed_parent(dense[l], lead[l]) is None
+    # generic kernel (no max_roi) honours the pixel stride too
+    views2 = ops.placed_skip_buffers(rois.shape[0], lead, [s[0] for s in shapes], sizes, feats[0].device)
+    for a, b in zip(ops.roi_gather(feats, rois, scales, sizes, outs=views2), dense):
+        assert torch.equal(a, b)
+    # exact-2x block (level 1/2: 60x25 -> 120x50): depth-to-space into the leading channels
+    R, Ca = rois.shape[0], lead[0]
+    y4 = torch.randn((R, 4 * Ca, 60, 25), device=DEV).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(Ca, device=DEV)
+    ref = ops.d2s_bias_act_concat(y4, bias, dense[0], 0.2)
+    got = ops.d2s_bias_act_concat(y4, bias, placed[0], 0.2)
+    assert got.data_ptr() == ops.placed_parent(placed[0], Ca).data_ptr() and got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(got, ref)
+    # non-2x block (level 1/4: 60x25): bias + LeakyReLU into the leading channels
+    y = torch.randn((R, lead[1], 60, 25), device=DEV).contiguous(memory_format=torch.channels_last)
+    b1 = torch.randn(lead[1], device=DEV)
+    assert torch.equal(ops.leaky_concat(y, placed[1], 0.2, bias=b1), ops.leaky_concat(y, dense[1], 0.2, bias=b1))
