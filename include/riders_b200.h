@@ -188,6 +188,27 @@ int riders_l1_scale_align(const float* pred, const float* target, const uint8_t*
                           void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * N4  RC-Net input prologue: run_rcnet_zju.py:214-240 (shift points by the pads, box = shifted point -/+ pads),
+ *     RCNet/rcnet_transforms.py:100-103 (max > 1 -> Tensor.int(), decided per frame) and :258-261 (/ 255.0),
+ *     RCNet/rcnet_main.py:441-444 (edge pad by (pw//2, ph//2)).
+ *     image (B,C,H,W) NCHW float32; points (R,3) UNSHIFTED (x, y, z), frames concatenated;
+ *     frame_offsets (B+1) int32 DEVICE; padded (B,C,H+2*pad_y,W+2*pad_x) in out_layout;
+ *     points_shifted (R,3); rois (R,5) = (frame, x1, y1, x2, y2) for riders_roi_gather_fwd;
+ *     frame_flags (B) int32 workspace (1 where the frame held a value > 1).
+ * N2  SML input assembly: val_zju.py:181-196 + modules/midas/transforms.py (Resize with cv2.INTER_NEAREST on
+ *     every item, NormalizeIntermediate, PrepareForNet): x (B,3,out_h,out_w) = [(int_depth-mean)/std |
+ *     (int_scales-mean)/std | 0.299 r + 0.587 g + 0.114 b], d (B,1,out_h,out_w) = resized int_depth.
+ *     image: (B,H,W,3) if image_hwc (the reference's sample layout) else (B,3,H,W).
+ * ------------------------------------------------------------------------------------------ */
+int riders_rcnet_prologue(const float* image, int B, int C, int H, int W, int pad_x, int pad_y, int out_layout,
+                          const float* points, const int32_t* frame_offsets, int R,
+                          float* padded, float* points_shifted, float* rois, int32_t* frame_flags, void* stream);
+int riders_sml_input_assemble(const float* int_depth, const float* int_scales, const float* image, int image_hwc,
+                              int B, int H, int W, int out_h, int out_w,
+                              float depth_mean, float depth_std, float scales_mean, float scales_std,
+                              float* x, float* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * N2/N3  scale scaffold (val_zju.py:135-138,171-179) with the RC-Net -> SML PNG hand-off in memory
  *     int_depth (aligned prior), rcnet_depth (quasi-dense METRIC depth from A5, or NULL),
  *     sparse_inv / sparse_valid (radar inverse depth and mask), all (B,H,W).

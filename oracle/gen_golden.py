@@ -238,10 +238,87 @@ def gen_rcnet(ref):
     np.savez_compressed(os.path.join(OUT, "rcnet_tiny.npz"), **out)
 
 
+def sml_input_case(tag, H, W):
+    """Inputs of the SML-input golden cases, regenerated (not stored) by the tests.  'zju' is a full-size frame whose
+    pixels encode their own coordinates (pins cv2's nearest index tables at 640x512 -> 352x288 and compresses well);
+    'small' is random data (pins the float32 arithmetic)."""
+    if tag == "zju":
+        yy, xx = np.mgrid[0:H, 0:W]
+        code = ((yy * W + xx) / float(1 << 19)).astype(np.float32)                     # exact in float32
+        image = np.stack([code, (xx / 1024.0).astype(np.float32), (yy / 1024.0).astype(np.float32)], -1)
+        return image, code + np.float32(0.25), (np.float32(1.0) - code).astype(np.float32)
+    rng = np.random.default_rng(H * 1000 + W)
+    return (rng.uniform(0, 1, (H, W, 3)).astype(np.float32), rng.uniform(0.004, 1.2, (H, W)).astype(np.float32),
+            rng.uniform(0, 1, (H, W)).astype(np.float32))
+
+
+def gen_sml_glue(ref):
+    """N2 / N4 rows and the sml_glue statements: the reference's own transforms, utils and eval functions."""
+    import torchvision
+    import rcnet_transforms
+    from modules.midas import transforms as midas_transforms, utils as midas_utils
+    from utils import eval_utils
+    rng = np.random.default_rng(77)
+    out = {}
+    # --- SML input assembly: val_zju.py:181-196 executed literally around the reference's transform pipeline
+    for tag, (H, W) in (("zju", (512, 640)), ("small", (96, 200))):
+        tf = midas_transforms.get_transforms(288, 288, depth_predictor='midas_small')
+        image, int_depth, int_scales = sml_input_case(tag, H, W)
+        sample = tf({'image': image.copy(), 'int_depth': int_depth.copy(), 'int_scales': int_scales.copy(),
+                     'int_depth_no_tf': int_depth.copy()})
+        x = torch.cat([sample['int_depth'], sample['int_scales']], 0)
+        image_gray = sample['image'][0] * 0.299 + sample['image'][1] * 0.587 + sample['image'][2] * 0.114
+        x = torch.cat([x, image_gray.unsqueeze(0)], 0)
+        xs = x.numpy() if tag != "zju" else x.numpy()[:, ::4, ::4]       # full-size case: d in full (index tables), x subsampled
+        out.update({"sml_input_%s/shape" % tag: np.array([H, W]), "sml_input_%s/x" % tag: xs,
+                    "sml_input_%s/d" % tag: sample['int_depth_no_tf'].numpy()})
+    # --- RC-Net prologue: run_rcnet_zju.py:214-240 + Transforms + the pad of rcnet_main.forward_output
+    for tag, hi in (("u8", 255.0), ("unit", 1.0)):
+        H, W, ph, pw, K = 40, 56, 24, 10, 7
+        image = torch.from_numpy(rng.uniform(0, hi, (1, 3, H, W)).astype(np.float32))
+        pts0 = np.stack([rng.integers(0, W, K), rng.integers(0, H, K), rng.uniform(1.5, 100, K)], 1).astype(np.float32)
+        radar_points = torch.from_numpy(pts0.copy())
+        pad_size_x, pad_size_y = pw // 2, ph // 2
+        bounding_boxes_list = []
+        for i in range(radar_points.shape[0]):
+            radar_points[i, 0] = radar_points[i, 0] + pad_size_x
+            radar_points[i, 1] = radar_points[i, 1] + pad_size_y
+            bounding_box = torch.zeros(4)
+            bounding_box[0] = radar_points[i, 0] - pad_size_x
+            bounding_box[1] = radar_points[i, 1] - pad_size_y
+            bounding_box[2] = radar_points[i, 0] + pad_size_x
+            bounding_box[3] = radar_points[i, 1] + pad_size_y
+            bounding_boxes_list.append(bounding_box)
+        bounding_boxes_list = [torch.stack(bounding_boxes_list, dim=0)]
+        tr = rcnet_transforms.Transforms(normalized_image_range=[0, 1])
+        [img_t], [pts_t], [bb_t] = tr.transform(images_arr=[image.clone()], points_arr=[radar_points],
+                                                bounding_boxes_arr=[bounding_boxes_list], random_transform_probability=0.0)
+        padded = torchvision.transforms.functional.pad(img_t, (pad_size_x, pad_size_y, pad_size_x, pad_size_y), padding_mode='edge')
+        out.update({"prologue_%s/image" % tag: image.numpy(), "prologue_%s/points" % tag: pts0,
+                    "prologue_%s/patch" % tag: np.array([ph, pw]), "prologue_%s/padded" % tag: padded.numpy(),
+                    "prologue_%s/points_shifted" % tag: pts_t.numpy(), "prologue_%s/boxes" % tag: bb_t[0].numpy()})
+    # --- pins for the statements sml_glue_ref restates: normalize_unit_range, eval_utils
+    sc = rng.uniform(0.3, 2.5, (48, 64)).astype(np.float32)
+    out["normalize/in"], out["normalize/out"] = sc, midas_utils.normalize_unit_range(sc.copy())
+    gt = (rng.uniform(0, 60, (48, 64)) * (rng.uniform(0, 1, (48, 64)) < 0.4)).astype(np.float32)
+    pred = (np.abs(gt + rng.normal(0, 2, gt.shape)) + 0.5).astype(np.float32)
+    mask = np.where(np.logical_and(gt > 0, np.logical_and(gt > 0.0, gt < 50.0)))       # val_zju.py:212-218
+    p, g = pred[mask], gt[mask]
+    out["metrics/pred"], out["metrics/gt"] = pred, gt
+    out["metrics/values"] = np.array([eval_utils.mean_abs_err(1000.0 * p, 1000.0 * g), eval_utils.root_mean_sq_err(1000.0 * p, 1000.0 * g),
+                                      eval_utils.inv_mean_abs_err(0.001 * p, 0.001 * g), eval_utils.inv_root_mean_sq_err(0.001 * p, 0.001 * g),
+                                      eval_utils.mean_abs_rel_err(1000.0 * p, 1000.0 * g), eval_utils.mean_sq_rel_err(1000.0 * p, 1000.0 * g),
+                                      eval_utils.thr_acc(p, g), float(p.size)], np.float64)
+    np.savez_compressed(os.path.join(OUT, "sml_glue.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = import_reference()
-    for fn in (gen_roi_pool, gen_loftr, gen_reduce, gen_estimator, gen_interpolator, gen_rcnet):
+    only = set(sys.argv[1:])                     # e.g. `python -m oracle.gen_golden gen_sml_glue` regenerates one file
+    for fn in (gen_roi_pool, gen_loftr, gen_reduce, gen_estimator, gen_interpolator, gen_rcnet, gen_sml_glue):
+        if only and fn.__name__ not in only:
+            continue
         fn(ref)
         print("wrote", fn.__name__)
 

@@ -6,6 +6,8 @@ and is test infrastructure).
 """
 import ctypes as C
 
+import numpy as np
+
 import torch
 
 from . import _lib
@@ -618,3 +620,66 @@ def interp_linear(knot_xy, knot_val, knot_count, H, W, fill=1.0, want_triangles=
     if want_triangles:
         return out, status, tri, tcount
     return out, status
+
+
+# --------------------------------------------------------------------------------------------
+# N4 prologue / N2 SML input assembly
+# --------------------------------------------------------------------------------------------
+def rcnet_prologue(images, points, frame_offsets, patch, channels_last=True):
+    """run_rcnet_zju.py:214-240 + rcnet_transforms normalisation + rcnet_main.py:441-444 edge pad, one pass.
+    images (B,C,H,W) float32 as loaded ([0,255] or [0,1]); points (R,3) UNSHIFTED; patch (ph, pw).
+    Returns padded normalised images (B,C,H+ph,W+pw) [channels_last], pad-shifted points (R,3), rois (R,5)."""
+    _need_cuda(images, points)
+    images, points = _f32c(images), _f32c(points)
+    dev = images.device
+    B, Cc, H, W = images.shape
+    ph, pw = int(patch[0]), int(patch[1])
+    px, py = pw // 2, ph // 2
+    if not torch.is_tensor(frame_offsets):
+        frame_offsets = torch.tensor(list(frame_offsets), dtype=torch.int32)
+    offs = frame_offsets.to(device=dev, dtype=torch.int32).contiguous()
+    R = points.shape[0]
+    fmt = torch.channels_last if channels_last else torch.contiguous_format
+    padded = torch.empty((B, Cc, H + 2 * py, W + 2 * px), device=dev, dtype=torch.float32, memory_format=fmt)
+    shifted = torch.empty((R, 3), device=dev, dtype=torch.float32)
+    rois = torch.empty((R, 5), device=dev, dtype=torch.float32)
+    flags = torch.empty(B, device=dev, dtype=torch.int32)
+    with _span("rcnet_prologue", (images.numel() * 2 + padded.numel() + R * 11) * 4):
+        rc = _lib.lib().riders_rcnet_prologue(_ptr(images), B, Cc, H, W, px, py, LAYOUT_NHWC if channels_last else LAYOUT_NCHW,
+                                              _ptr(points), _ptr(offs), R, _ptr(padded), _ptr(shifted), _ptr(rois),
+                                              _ptr(flags), _stream())
+    _lib.check(rc, "riders_rcnet_prologue")
+    return padded, shifted, rois
+
+
+def sml_resize_size(width, height, net_w=288, net_h=288, multiple_of=32):
+    """modules/midas/transforms.py Resize.get_size with keep_aspect_ratio=True, resize_method='minimal' (:70-125)."""
+    scale_h, scale_w = net_h / height, net_w / width
+    if abs(1 - scale_w) < abs(1 - scale_h):
+        scale_h = scale_w
+    else:
+        scale_w = scale_h
+    new_h = int(np.round(scale_h * height / multiple_of) * multiple_of)
+    new_w = int(np.round(scale_w * width / multiple_of) * multiple_of)
+    return new_w, new_h
+
+
+SML_MEAN = {"int_depth": 0.729, "int_scales": 0.404}          # modules/midas/transforms.py:333-334
+SML_STD = {"int_depth": 0.210, "int_scales": 0.117}
+
+
+def sml_input_assemble(int_depth, int_scales, image, image_hwc=False, net=(288, 288)):
+    """val_zju.py:181-196: the SML network's inputs x (B,3,oh,ow) and d (B,1,oh,ow) from the aligned prior
+    (B,H,W), the scale scaffold (B,H,W) and the frame ((B,3,H,W), or (B,H,W,3) with image_hwc)."""
+    _need_cuda(int_depth, int_scales, image)
+    int_depth, int_scales, image = _f32c(int_depth), _f32c(int_scales), _f32c(image)
+    B, H, W = int_depth.shape
+    ow, oh = sml_resize_size(W, H, net[0], net[1])
+    x = torch.empty((B, 3, oh, ow), device=int_depth.device, dtype=torch.float32)
+    d = torch.empty((B, 1, oh, ow), device=int_depth.device, dtype=torch.float32)
+    with _span("sml_input_assemble", B * oh * ow * 9 * 4):
+        rc = _lib.lib().riders_sml_input_assemble(_ptr(int_depth), _ptr(int_scales), _ptr(image), 1 if image_hwc else 0,
+                                                  B, H, W, oh, ow, SML_MEAN["int_depth"], SML_STD["int_depth"],
+                                                  SML_MEAN["int_scales"], SML_STD["int_scales"], _ptr(x), _ptr(d), _stream())
+    _lib.check(rc, "riders_sml_input_assemble")
+    return x, d

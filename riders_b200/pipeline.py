@@ -22,7 +22,13 @@ from .rcnet.rcnet_main import forward_output_batched
 
 class RadarDepthPipeline(object):
     def __init__(self, model, response_thr=0.1, min_depth=0.0, max_depth=100.0,
-                 clamp_min=0.1, clamp_max=255.0, chunk_points=2048, max_knots=None):
+                 clamp_min=0.1, clamp_max=255.0, chunk_points=2048, max_knots=None,
+                 raw_inputs=False, retry_empty=False, sml_input=False):
+        """raw_inputs: frames as loaded ([0,255]) and radar points in frame coordinates (the prologue kernel does the
+        shift / boxes / normalisation / pad of run_rcnet_zju.py:214-240); retry_empty: the script's threshold-lowering
+        retry for frames where nothing fires (:254-265); sml_input: also assemble the SML network's inputs (x, d) of
+        val_zju.py:181-196 (resize to 288-multiple-of-32, normalise, gray channel)."""
+        self.raw_inputs, self.retry_empty, self.sml_input = bool(raw_inputs), bool(retry_empty), bool(sml_input)
         self.model = model
         self.response_thr = float(response_thr)
         self.min_depth, self.max_depth = float(min_depth), float(max_depth)
@@ -34,12 +40,15 @@ class RadarDepthPipeline(object):
 
     # ------------------------------------------------------------------------------ device
     @torch.no_grad()
-    def run_device(self, images, radar_points, frame_offsets, mono_pred, sparse_depth):
+    def run_device(self, images, radar_points, frame_offsets, mono_pred, sparse_depth, sml_image=None):
         """images (B,3,H,W) in [0,1]; radar_points (R,3) pad-shifted (x+pw/2, y+ph/2, z), frames
-        concatenated; frame_offsets python list (B+1); mono_pred (B,H,W) relative inverse depth;
-        sparse_depth (B,H,W) metric radar depth, 0 where empty.  Everything on the device."""
+        concatenated (with ``raw_inputs``: [0,255] frames and unshifted points); frame_offsets python list (B+1);
+        mono_pred (B,H,W) relative inverse depth; sparse_depth (B,H,W) metric radar depth, 0 where empty;
+        sml_image: the frame the SML network sees ((B,3,H,W) or (B,H,W,3) in [0,1]; default: the normalised ``images``).
+        Everything on the device."""
         depth_q, response = forward_output_batched(self.model, images, radar_points, frame_offsets,
-                                                   self.response_thr, chunk_points=self.chunk_points)
+                                                   self.response_thr, chunk_points=self.chunk_points,
+                                                   raw_inputs=self.raw_inputs, retry_empty=self.retry_empty)
         # val_zju.py:130-133: valid = (d < max) * (d > min); d[~valid] = inf; d = 1/d  (-> 0 at invalid)
         valid = (sparse_depth < self.max_depth) & (sparse_depth > self.min_depth)
         sparse_inv = torch.where(valid, 1.0 / sparse_depth, torch.zeros_like(sparse_depth))
@@ -53,9 +62,15 @@ class RadarDepthPipeline(object):
         # 16-bit PNG hand-off between run_rcnet_zju.py and val_zju.py applied in memory
         int_scales, _, scaffold_status = ops.scale_scaffold(int_depth, depth_q, sparse_inv, valid,
                                                             self.min_depth, self.max_depth, png_quantize=True)
-        return {"depth": depth_q, "response": response, "int_depth": int_depth, "scale_shift": scale_shift,
-                "scale_map": scale_map, "interp_status": status, "knot_count": cnt,
-                "int_scales": int_scales, "scaffold_status": scaffold_status}
+        out = {"depth": depth_q, "response": response, "int_depth": int_depth, "scale_shift": scale_shift,
+               "scale_map": scale_map, "interp_status": status, "knot_count": cnt,
+               "int_scales": int_scales, "scaffold_status": scaffold_status}
+        if self.sml_input:
+            # val_zju.py:181-196: what ScaleMapLearner.forward(x, d) is fed
+            img = sml_image if sml_image is not None else (images / 255.0 if self.raw_inputs else images)
+            hwc = img.dim() == 4 and img.shape[-1] == 3 and img.shape[1] != 3
+            out["sml_x"], out["sml_d"] = ops.sml_input_assemble(int_depth, int_scales, img, image_hwc=hwc)
+        return out
 
     # ------------------------------------------------------------------------------ host
     def _pin(self, name, shape, dtype):
@@ -81,7 +96,8 @@ class RadarDepthPipeline(object):
             dev.append(t.to(device, non_blocking=True))
         out = self.run_device(dev[0], dev[1], list(frame_offsets), dev[2], dev[3])
         host, d2h = {}, 0
-        for k in ("depth", "int_depth", "scale_map", "int_scales", "scale_shift", "interp_status"):
+        for k in ("depth", "int_depth", "scale_map", "int_scales", "scale_shift", "interp_status") + \
+                ((("sml_x", "sml_d")) if self.sml_input else ()):
             h = self._pin(k, out[k].shape, out[k].dtype)
             h.copy_(out[k], non_blocking=True)
             d2h += h.numel() * h.element_size()

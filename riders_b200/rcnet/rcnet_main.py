@@ -53,28 +53,37 @@ def forward_output(model, image, radar_points, bounding_boxes_list, response_thr
 
 
 def forward_output_batched(model, images, radar_points, frame_offsets, response_thr=0.5,
-                           chunk_points=1024, return_select=False):
+                           chunk_points=1024, return_select=False, raw_inputs=False, retry_empty=False):
     """Many frames per call (BASELINE config 2/3).
 
-    images (B,3,H,W) unpadded; radar_points (R,3) pad-shifted, frames concatenated;
-    frame_offsets: python list (B+1).  The backbone runs once on the padded batch, the encoder /
-    decoder run per chunk of points (each chunk within one frame), the reduce kernel once.
-    Returns depth (B,H,W), response (B,H,W) [, select]."""
+    images (B,3,H,W) unpadded; radar_points (R,3), frames concatenated; frame_offsets: python list (B+1).
+    ``raw_inputs=False``: images already normalised to [0,1] and points pad-shifted (what ``forward_output`` takes).
+    ``raw_inputs=True``: images as loaded ([0,255]) and points in frame coordinates - the prologue of
+    run_rcnet_zju.py:214-240 (shift, boxes, int()/255 normalisation, edge pad) runs as one kernel.
+    ``retry_empty``: the caller's retry loop of run_rcnet_zju.py:254-265 - a frame whose depth map is all zero is reduced
+    again with the threshold lowered by 0.05 until something fires (one tiny D2H per call; the logits are reused).
+    The backbone runs once on the padded batch, the encoder / decoder run per chunk of points (each chunk within one
+    frame), the reduce kernel once.  Returns depth (B,H,W), response (B,H,W) [, select]."""
     ph, pw = model.input_patch_size_image
     px, py = pw // 2, ph // 2
     B, _, H, W = images.shape
-    padded = _pad_edge(images, px, py)
-    x, y = radar_points[:, 0:1], radar_points[:, 1:2]
-    boxes = torch.cat([x - px, y - py, x + px, y + py], dim=1)      # run_rcnet_zju.py:227-232
     enc = model.encoder.module if hasattr(model.encoder, 'module') else model.encoder
     dec = model.decoder.module if hasattr(model.decoder, 'module') else model.decoder
+    if raw_inputs:
+        cl = next(enc.encoder_image.parameters()).is_contiguous(memory_format=torch.channels_last) and \
+            next(enc.encoder_image.parameters()).dim() == 4 and not next(enc.encoder_image.parameters()).is_contiguous()
+        padded, radar_points, rois = ops.rcnet_prologue(images, radar_points, frame_offsets, (ph, pw), channels_last=cl)
+    else:
+        padded = _pad_edge(images, px, py)
+        x, y = radar_points[:, 0:1], radar_points[:, 1:2]
+        boxes = torch.cat([x - px, y - py, x + px, y + py], dim=1)      # run_rcnet_zju.py:227-232
+        frame_of = torch.repeat_interleave(
+            torch.arange(B, device=images.device, dtype=torch.float32),
+            torch.tensor([frame_offsets[i + 1] - frame_offsets[i] for i in range(B)], device=images.device))
+        rois = torch.cat([frame_of[:, None], boxes], dim=1).contiguous()
     latent_image, skips_image = enc.encoder_image(padded)
     R = radar_points.shape[0]
     logits = torch.empty((R, 1, ph, pw), device=images.device, dtype=torch.float32)
-    frame_of = torch.repeat_interleave(
-        torch.arange(B, device=images.device, dtype=torch.float32),
-        torch.tensor([frame_offsets[i + 1] - frame_offsets[i] for i in range(B)], device=images.device))
-    rois = torch.cat([frame_of[:, None], boxes], dim=1).contiguous()
     # latent path (1/32-level gather + point MLP + LoFTR) for every point of the batch at once: 1366 tiles of
     # 6 points fill the 148 SMs in ~9 full waves; the skip gather + decoder run per chunk of points.
     latent = enc.encode_latent(latent_image, radar_points, rois)
@@ -84,5 +93,21 @@ def forward_output_batched(model, images, radar_points, frame_offsets, response_
         e = min(R, s + chunk_points)
         skips = enc.gather_skips(skips_image, rois[s:e], lead_channels=lead)
         logits[s:e] = dec(x=latent[s:e], skips=skips, shape=(ph, pw))[-1]
-    return ops.confidence_reduce(logits, radar_points, frame_offsets, H, W, response_thr, logits=True,
-                                 want_select=return_select)[:3 if return_select else 2]
+    out = list(ops.confidence_reduce(logits, radar_points, frame_offsets, H, W, response_thr, logits=True,
+                                     want_select=return_select))
+    if retry_empty:
+        thr = float(response_thr)
+        empty = (out[0].flatten(1).amax(dim=1) == 0).nonzero().flatten().tolist()          # D2H: the caller's np.sum(...) == 0
+        while empty and thr > -1.0:
+            thr -= 0.05
+            for b in empty:
+                s, e = frame_offsets[b], frame_offsets[b + 1]
+                if e == s:
+                    continue
+                again = ops.confidence_reduce(logits[s:e], radar_points[s:e], [0, e - s], H, W, thr, logits=True,
+                                              want_select=return_select)
+                for o, a in zip(out, again):
+                    if o is not None:
+                        o[b] = a[0]
+            empty = [b for b in empty if frame_offsets[b + 1] > frame_offsets[b] and float(out[0][b].amax()) == 0.0]
+    return tuple(out[:3 if return_select else 2])

@@ -7,6 +7,7 @@ import torch
 
 from oracle import (confidence_reduce_ref as cr, estimator_ref as er, linear_attention_ref as lr,
                     roi_pool_ref as rr, rcnet_ref)
+from oracle import sml_glue_ref as sg
 from riders_b200 import ops, synth
 
 pytestmark = pytest.mark.gpu
@@ -698,3 +699,82 @@ def test_gather_into_placed_concat_buffers_is_bit_exact_and_never_copied():
     y = torch.randn((R, lead[1], 60, 25), device=DEV).contiguous(memory_format=torch.channels_last)
     b1 = torch.randn(lead[1], device=DEV)
     assert torch.equal(ops.leaky_concat(y, placed[1], 0.2, bias=b1), ops.leaky_concat(y, dense[1], 0.2, bias=b1))
+
+
+@pytest.mark.parametrize("tag", ["u8", "unit"])
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_rcnet_prologue_matches_the_reference_statements(golden, tag, channels_last):
+    """N4: shift / boxes / int()-and-/255 normalisation / edge pad against fixtures made by the reference's own
+    Transforms + torchvision pad + the script's box loop (oracle/gen_golden.py gen_sml_glue)."""
+    g = golden("sml_glue.npz").case("prologue_" + tag)
+    patch = tuple(int(v) for v in g["patch"])
+    # two frames: the golden one and a [0,1]-valued one (the max > 1 decision is per frame)
+    other = np.random.default_rng(3).uniform(0, 1, g["image"].shape).astype(np.float32)
+    images = np.concatenate([g["image"], other], 0)
+    pts = np.concatenate([g["points"], g["points"][:3]], 0)
+    K = g["points"].shape[0]
+    padded, shifted, rois = ops.rcnet_prologue(cu(images), cu(pts), [0, K, K + 3], patch, channels_last=channels_last)
+    assert padded.is_contiguous(memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+    assert np.array_equal(padded[0:1].cpu().numpy(), g["padded"])
+    ref_other, _, _ = sg.rcnet_prologue_ref(other, pts[:1], patch)
+    assert np.array_equal(padded[1:2].cpu().numpy(), ref_other)
+    assert np.array_equal(shifted[:K].cpu().numpy(), g["points_shifted"])
+    r = rois.cpu().numpy()
+    assert np.array_equal(r[:K, 1:], g["boxes"]) and np.all(r[:K, 0] == 0) and np.all(r[K:, 0] == 1)
+    assert np.array_equal(r[K:, 1:], g["boxes"][:3])
+
+
+def test_sml_input_assemble_matches_the_reference_transform_pipeline(golden):
+    """N2: val_zju.py:181-196 (Resize INTER_NEAREST + NormalizeIntermediate + gray) against the reference's transform
+    pipeline (golden) and the oracle at full size, both image layouts, bit for bit."""
+    from oracle.gen_golden import sml_input_case
+    for tag in ("zju", "small"):
+        g = golden("sml_glue.npz").case("sml_input_" + tag)
+        H, W = (int(v) for v in g["shape"])
+        image, int_depth, int_scales = sml_input_case(tag, H, W)
+        x, d = ops.sml_input_assemble(cu(int_depth[None]), cu(int_scales[None]), cu(image[None]), image_hwc=True)
+        assert np.array_equal(d[0].cpu().numpy(), g["d"])
+        xs = x[0].cpu().numpy()
+        assert np.array_equal(xs if tag != "zju" else xs[:, ::4, ::4], g["x"])
+    rng = np.random.default_rng(8)
+    B, H, W = 3, 512, 640
+    img = rng.uniform(0, 1, (B, H, W, 3)).astype(np.float32)
+    dep = rng.uniform(0.004, 10, (B, H, W)).astype(np.float32)
+    sc = rng.uniform(0, 1, (B, H, W)).astype(np.float32)
+    x, d = ops.sml_input_assemble(cu(dep), cu(sc), cu(np.ascontiguousarray(img.transpose(0, 3, 1, 2))))
+    assert tuple(x.shape) == (B, 3, 288, 352) and tuple(d.shape) == (B, 1, 288, 352)
+    for b in range(B):
+        rx, rd = sg.sml_input_ref(img[b], dep[b], sc[b])
+        assert np.array_equal(x[b].cpu().numpy(), rx) and np.array_equal(d[b].cpu().numpy(), rd)
+
+
+def test_pipeline_raw_inputs_retry_and_sml_input():
+    """The pipeline fed 'as loaded' inputs ([0,255] frames, unshifted points) == the pipeline fed the transformed ones;
+    the threshold-lowering retry of run_rcnet_zju.py:254-265; SML inputs against the oracle."""
+    from riders_b200.pipeline import RadarDepthPipeline
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    Hh, Ww, patch, K, B = 96, 128, (64, 32), 14, 3
+    gpu = _to_cuda(_rand_model("cpu", patch, [8, 16, 16, 16, 16], [32, 16, 16, 8, 8])).channels_last()
+    batch = synth.chain_batch(60, B, K, Hh, Ww, patch)
+    args = (batch["offsets"], cu(batch["mono"]), cu(batch["sparse"]))
+    base = RadarDepthPipeline(gpu, response_thr=0.45, chunk_points=16).run_device(cu(batch["images"]), cu(batch["points"]), *args)
+    raw_images = np.rint(batch["images"] * 255.0).astype(np.float32)
+    raw_points = batch["points"] - np.array([patch[1] // 2, patch[0] // 2, 0], np.float32)
+    pipe = RadarDepthPipeline(gpu, response_thr=0.45, chunk_points=16, raw_inputs=True, retry_empty=True, sml_input=True)
+    out = pipe.run_device(cu(raw_images), cu(raw_points), *args)
+    for k in ("depth", "response", "int_depth", "scale_map", "int_scales"):
+        assert torch.equal(out[k], base[k]), k
+    for b in range(B):
+        rx, rd = sg.sml_input_ref(batch["images"][b].transpose(1, 2, 0), out["int_depth"][b].cpu().numpy(), out["int_scales"][b].cpu().numpy())
+        x = out["sml_x"][b].cpu().numpy()
+        assert np.array_equal(x[:2], rx[:2]) and np.array_equal(out["sml_d"][b].cpu().numpy(), rd)
+        np.testing.assert_allclose(x[2], rx[2], rtol=1e-6)            # raw / 255 on the device vs the loader's uint8 / 255
+    # nothing fires at thr = 0.99 with random weights (sigmoid ~ 0.5): the retry walks the threshold down until it does
+    from riders_b200.rcnet.rcnet_main import forward_output_batched
+    with torch.no_grad():
+        d0, r0 = forward_output_batched(gpu, cu(batch["images"]), cu(batch["points"]), batch["offsets"], 0.99, chunk_points=16)
+        d1, r1 = forward_output_batched(gpu, cu(batch["images"]), cu(batch["points"]), batch["offsets"], 0.99, chunk_points=16,
+                                        retry_empty=True)
+    assert float(d0.abs().sum()) == 0.0
+    assert all(float(d1[b].amax()) > 0 for b in range(B))

@@ -125,3 +125,46 @@ def test_rcnet_oracle_matches_reference_end_to_end(golden):
         agree = (r.numpy() > 0) == (g["response"] > 0)
         np.testing.assert_allclose(d.numpy()[agree], g["depth"][agree], rtol=1e-4, atol=1e-5)
         assert agree.mean() > 0.999
+
+
+# ---------------------------------------------------------------------------------------------
+# N2 / N4 rows: oracle.sml_glue_ref against the reference's own transforms / utils
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["zju", "small"])
+def test_sml_input_oracle_matches_the_reference_transform_pipeline(golden, tag):
+    from oracle import sml_glue_ref as sg
+    from oracle.gen_golden import sml_input_case
+    g = golden("sml_glue.npz").case("sml_input_" + tag)
+    H, W = (int(v) for v in g["shape"])
+    image, int_depth, int_scales = sml_input_case(tag, H, W)
+    x, d = sg.sml_input_ref(image, int_depth, int_scales)
+    assert d.shape == g["d"].shape and np.array_equal(d, g["d"])              # cv2.INTER_NEAREST index tables
+    ref_x = g["x"]
+    assert np.array_equal(x if tag != "zju" else x[:, ::4, ::4], ref_x)       # float32 statements, bit for bit
+    assert sg.sml_resize_size_ref(640, 512) == (352, 288)
+
+
+def test_sml_nearest_indices_equal_cv2():
+    cv2 = pytest.importorskip("cv2")
+    from oracle import sml_glue_ref as sg
+    for src, dst in ((640, 352), (512, 288), (1280, 352), (200, 608), (96, 288), (37, 64)):
+        ramp = np.arange(src, dtype=np.float32)[None, :].repeat(2, 0)
+        got = cv2.resize(ramp, (dst, 2), interpolation=cv2.INTER_NEAREST)[0].astype(np.int64)
+        assert np.array_equal(sg.nearest_indices_ref(dst, src), got), (src, dst)
+
+
+@pytest.mark.parametrize("tag", ["u8", "unit"])
+def test_rcnet_prologue_oracle_matches_the_reference_statements(golden, tag):
+    from oracle import sml_glue_ref as sg
+    g = golden("sml_glue.npz").case("prologue_" + tag)
+    padded, pts, boxes = sg.rcnet_prologue_ref(g["image"], g["points"], g["patch"])
+    assert np.array_equal(padded, g["padded"]) and np.array_equal(pts, g["points_shifted"]) and np.array_equal(boxes, g["boxes"])
+
+
+def test_sml_glue_statements_are_pinned_by_the_reference_utils(golden):
+    from oracle import sml_glue_ref as sg
+    z = golden("sml_glue.npz")
+    n = z.case("normalize")
+    assert np.array_equal(sg.normalize_unit_range_ref(n["in"].copy()), n["out"])
+    m = z.case("metrics")
+    np.testing.assert_allclose(sg.depth_metrics_ref(m["pred"], m["gt"], 0.0, 50.0), m["values"], rtol=1e-12)
