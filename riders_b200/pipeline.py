@@ -13,6 +13,8 @@ The SML network itself (MidasNet_small_videpth) is not constructible offline (to
 modules/midas/blocks.py:44-51) and stays the reference's torch module - any ``nn.Module`` with
 ``forward(x, d)`` can be attached by the caller after this front-end.
 """
+import contextlib
+
 import numpy as np
 import torch
 
@@ -23,12 +25,14 @@ from .rcnet.rcnet_main import forward_output_batched
 class RadarDepthPipeline(object):
     def __init__(self, model, response_thr=0.1, min_depth=0.0, max_depth=100.0,
                  clamp_min=0.1, clamp_max=255.0, chunk_points=2048, max_knots=None,
-                 raw_inputs=False, retry_empty=False, sml_input=False):
+                 raw_inputs=False, retry_empty=False, sml_input=False, overlap_front_end=True):
         """raw_inputs: frames as loaded ([0,255]) and radar points in frame coordinates (the prologue kernel does the
         shift / boxes / normalisation / pad of run_rcnet_zju.py:214-240); retry_empty: the script's threshold-lowering
         retry for frames where nothing fires (:254-265); sml_input: also assemble the SML network's inputs (x, d) of
         val_zju.py:181-196 (resize to 288-multiple-of-32, normalise, gray channel)."""
         self.raw_inputs, self.retry_empty, self.sml_input = bool(raw_inputs), bool(retry_empty), bool(sml_input)
+        self.overlap_front_end = bool(overlap_front_end)
+        self._side = None
         self.model = model
         self.response_thr = float(response_thr)
         self.min_depth, self.max_depth = float(min_depth), float(max_depth)
@@ -46,18 +50,39 @@ class RadarDepthPipeline(object):
         mono_pred (B,H,W) relative inverse depth; sparse_depth (B,H,W) metric radar depth, 0 where empty;
         sml_image: the frame the SML network sees ((B,3,H,W) or (B,H,W,3) in [0,1]; default: the normalised ``images``).
         Everything on the device."""
+        # The alignment / interpolation half of the front-end depends only on the mono prior and the radar map, not on
+        # RC-Net: it runs on a side stream underneath the RC-Net forward (the triangulation is one CTA per frame and
+        # would otherwise leave most of the 148 SMs idle for ~0.6 ms).  The scale scaffold joins the two.
+        main = torch.cuda.current_stream()
+        if self.overlap_front_end:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=images.device)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            self._side.wait_event(fork)
+            ctx = torch.cuda.stream(self._side)
+        else:
+            ctx = contextlib.nullcontext()
+        with ctx:
+            # val_zju.py:130-133: valid = (d < max) * (d > min); d[~valid] = inf; d = 1/d  (-> 0 at invalid)
+            valid = (sparse_depth < self.max_depth) & (sparse_depth > self.min_depth)
+            sparse_inv = torch.where(valid, 1.0 / sparse_depth, torch.zeros_like(sparse_depth))
+            _, scale_shift, int_depth = ops.lsq_align(mono_pred, sparse_inv, valid,
+                                                      clamp_hi=self.clamp_hi, clamp_lo=self.clamp_lo)
+            counts = [frame_offsets[i + 1] - frame_offsets[i] for i in range(len(frame_offsets) - 1)]
+            cap = self.max_knots or max(max(counts), 1)
+            xy, scales, _, cnt = ops.extract_knots(int_depth, sparse_inv, valid, cap)
+            scale_map, status = ops.interp_linear(xy, scales, cnt, int_depth.shape[-2], int_depth.shape[-1], 1.0)
+            if self.overlap_front_end:
+                join = torch.cuda.Event()
+                join.record(self._side)
+                for t in (valid, sparse_inv, scale_shift, int_depth, cnt, scale_map, status):
+                    t.record_stream(main)
         depth_q, response = forward_output_batched(self.model, images, radar_points, frame_offsets,
                                                    self.response_thr, chunk_points=self.chunk_points,
                                                    raw_inputs=self.raw_inputs, retry_empty=self.retry_empty)
-        # val_zju.py:130-133: valid = (d < max) * (d > min); d[~valid] = inf; d = 1/d  (-> 0 at invalid)
-        valid = (sparse_depth < self.max_depth) & (sparse_depth > self.min_depth)
-        sparse_inv = torch.where(valid, 1.0 / sparse_depth, torch.zeros_like(sparse_depth))
-        _, scale_shift, int_depth = ops.lsq_align(mono_pred, sparse_inv, valid,
-                                                  clamp_hi=self.clamp_hi, clamp_lo=self.clamp_lo)
-        counts = [frame_offsets[i + 1] - frame_offsets[i] for i in range(len(frame_offsets) - 1)]
-        cap = self.max_knots or max(max(counts), 1)
-        xy, scales, _, cnt = ops.extract_knots(int_depth, sparse_inv, valid, cap)
-        scale_map, status = ops.interp_linear(xy, scales, cnt, int_depth.shape[-2], int_depth.shape[-1], 1.0)
+        if self.overlap_front_end:
+            main.wait_event(join)
         # val_zju.py:171-179 (interp='rcnet_*'): the scaffold the scripts actually feed to the SML network, with the
         # 16-bit PNG hand-off between run_rcnet_zju.py and val_zju.py applied in memory (SURVEY 8(f) N2/N3)
         int_scales, _, scaffold_status = ops.scale_scaffold(int_depth, depth_q, sparse_inv, valid,
