@@ -15,9 +15,10 @@
 // subnormal range) and every accumulator read-back multiplies by 2^-8.  Activations must stay
 // inside the fp16 range (|a| < 65504), the same constraint the reference's V/S scaling exists for.
 //
-// Roles (576 threads): warp 0 streams the pre-split, pre-swizzled weight chunks (16 KB: hi|lo of
-// a 64 x 64 block) from L2 with cp.async.bulk through a 4-stage mbarrier ring; lane 0 of warp 1
-// issues the MMAs and commits their completion to mbarriers; warps 2..17 are the epilogue: four
+// Roles (576 threads): warp 0 streams the pre-split, pre-swizzled weight chunks (32 KB: hi|lo of
+// a 128 x 64 block) from L2 with cp.async.bulk through a 3-stage mbarrier ring; one elected lane of
+// warp 1 issues the MMAs (N = 128: an SS-mode MMA costs ~43 + N/2 cycles on this part, tools/mma_rate.py,
+// so wide instructions matter) and commits their completion to mbarriers; warps 2..17 are the epilogue: four
 // warps per TMEM lane quadrant, thread = (token row, 32 of its 128 columns): elu+1, the
 // per-(point, head) KV / normaliser contraction (2.5 % of the layer's FLOPs, CUDA cores),
 // LayerNorms, ReLU, residual, and the hi/lo re-split of the next A operand straight into the
@@ -30,7 +31,7 @@
 // epilogue has drained v out of D2 - both run under the attention epilogue.
 // Shared memory: X operand (hi[2] | lo[2] slabs of 128 rows x 128 B) 64 KB, resident x (later
 // relu(h[:,128:]), LayerNorm partials) | A operand 64 KB (src / msg / m / relu(h[:, :128]), also
-// the attention and output staging) | 4 weight stages of 16 KB | 26 KB KV / Ksum staging.
+// the attention staging - one quarter = 2 heads at a time - and the output staging) | 3 weight stages of 32 KB.
 #include "common.cuh"
 #include <cuda_fp16.h>
 
@@ -41,17 +42,16 @@ constexpr int TOK = 21, CH = 128, NHEAD = 8, HD = 16;
 constexpr int TILE_M = 128, PTS = 6, ROWS = PTS * TOK;        // 126 valid rows per tile
 constexpr int SLAB = 128 * 128;                                // bytes: 128 rows x 64 fp16
 constexpr int OPER_BYTES = 4 * SLAB;                           // hi[2] | lo[2] of a 128 x 128 operand
-constexpr int CHUNK = SLAB;                                    // hi (8 KB) | lo (8 KB) of one 64 x 64 weight block
-constexpr int NSTAGE = 4;
+constexpr int CHUNK = 2 * SLAB;                                // hi (16 KB) | lo (16 KB) of one 128 x 64 weight block
+constexpr int NSTAGE = 3;
 constexpr int NBLOCK = 10;                                     // 128 x 128 weight blocks per layer, in issue order
-constexpr int NCHUNK = NBLOCK * 4;
+constexpr int NCHUNK = NBLOCK * 2;
 constexpr int LAYER_PACK_BYTES = NCHUNK * CHUNK;               // 640 KB per layer
 constexpr int MAX_LAYERS = 16;
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = 64 + EPI_WARPS * 32;                   // warp 0 producer, warp 1 MMA, warps 2..17 epilogue
-constexpr int KV_BYTES = 24 * 256 * 4 + 24 * 16 * 4;           // KV[24][16][16] + Ksum[24][16]
 constexpr int TAIL_BYTES = 128;                                // barriers + TMEM slot
-constexpr int SMEM_BYTES = 2 * OPER_BYTES + NSTAGE * CHUNK + KV_BYTES + TAIL_BYTES;   // 222848; base must be 1024-aligned
+constexpr int SMEM_BYTES = 2 * OPER_BYTES + NSTAGE * CHUNK + TAIL_BYTES;   // 229504 of 232448; base must be 1024-aligned
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t D0 = 0, D1 = 128, D2 = 256, D3 = 384;
 constexpr float W_SCALE = 256.0f, W_UNSCALE = 1.0f / 256.0f;
@@ -129,6 +129,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),     \
                    "=r"(r[15])                                                                                  \
                  : "r"(taddr))
+#define TMEM_LD8(taddr, r)                                                                                      \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                       \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])    \
+                 : "r"(taddr))
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the 16 epilogue warps
@@ -153,6 +157,15 @@ __device__ __forceinline__ void split_store8(uint8_t* base, int row, int col, fl
     split2(b.x, b.y, hi.z, lo.z); split2(b.z, b.w, hi.w, lo.w);
     *reinterpret_cast<uint4*>(base + off) = hi;
     *reinterpret_cast<uint4*>(base + 2 * SLAB + off) = lo;
+}
+
+// the same for 4 consecutive K elements (col % 4 == 0): 8-byte stores
+__device__ __forceinline__ void split_store4(uint8_t* base, int row, int col, float4 a) {
+    const uint32_t off = (uint32_t)(col >> 6) * SLAB + sw128(row, (col & 63) >> 3) + (uint32_t)((col & 7) >> 2) * 8u;
+    uint2 hi, lo;
+    split2(a.x, a.y, hi.x, lo.x); split2(a.z, a.w, hi.y, lo.y);
+    *reinterpret_cast<uint2*>(base + off) = hi;
+    *reinterpret_cast<uint2*>(base + 2 * SLAB + off) = lo;
 }
 
 // coalesced: epilogue warp `ew` (0..15) loads rows ew*8.. of a (rows x 128) fp32 tile and splits them into the operand
@@ -225,9 +238,7 @@ loftr_layer_tc_kernel(const LayerArgs P) {
     uint8_t* x_base = smem;                                   // X operand: hi[2] | lo[2]
     uint8_t* a_base = smem + OPER_BYTES;                      // A operand: hi[2] | lo[2]
     uint8_t* b_base = smem + 2 * OPER_BYTES;                  // NSTAGE x (hi | lo)
-    float* KVs = reinterpret_cast<float*>(b_base + NSTAGE * CHUNK);
-    float* Ksum = KVs + 24 * 256;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(KVs) + KV_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + NSTAGE * CHUNK);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
     const uint32_t bfull = smem_u32(bars), bempty = smem_u32(bars + NSTAGE);
     const uint32_t a_ready = smem_u32(bars + 2 * NSTAGE), d_ready = smem_u32(bars + 2 * NSTAGE + 1);
@@ -271,31 +282,30 @@ loftr_layer_tc_kernel(const LayerArgs P) {
             uint32_t n = 0, aph = 0, vph = 0;
             const uint32_t xo = smem_u32(x_base), ao = smem_u32(a_base), b0 = smem_u32(b_base);
             const uint32_t kv_src = P.is_self ? xo : ao;
-            constexpr uint32_t IDESC = idesc_f16(64);
+            constexpr uint32_t IDESC = idesc_f16(128);
             long long wsum = 0;
-            // one 128 x 128 weight block = 4 chunks (N half, K half): D[:, dcol + 64 nh ..] (+)= oper[:, 64 kb ..] W^T
+            // one 128 x 128 weight block = 2 chunks (K halves): D[:, dcol .. dcol + 128) (+)= oper W^T
             auto issue_block = [&](uint32_t oper, uint32_t dcol, uint32_t acc_in, uint32_t commit_bar) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j, ++n) {
+                for (int kb = 0; kb < 2; ++kb, ++n) {
                     const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1;
                     const long long tw = P.trace ? clock64() : 0;
                     mbar_wait(bfull + 8 * s, ph);
                     if (P.trace) wsum += clock64() - tw;
                     tc_fence_after();
-                    const uint32_t nh = (uint32_t)j >> 1, kb = (uint32_t)j & 1;
-                    const uint32_t d = tmem + dcol + nh * 64;
+                    const uint32_t d = tmem + dcol;
                     const uint64_t ah = smem_desc(oper + kb * SLAB), al = smem_desc(oper + (2 + kb) * SLAB);
-                    const uint64_t bh = smem_desc(b0 + s * CHUNK), bl = smem_desc(b0 + s * CHUNK + CHUNK / 2);
+                    const uint64_t bh = smem_desc(b0 + s * CHUNK), bl = smem_desc(b0 + s * CHUNK + SLAB);
                     if (elect_one()) {
 #pragma unroll
                         for (int k16 = 0; k16 < 4; ++k16) {          // 16 fp16 = 32 bytes per MMA along K
                             const uint64_t adv = (uint64_t)(k16 * 2);
-                            umma_f16(d, al + adv, bh + adv, IDESC, acc_in | kb | (k16 > 0));
+                            umma_f16(d, al + adv, bh + adv, IDESC, acc_in | (uint32_t)kb | (k16 > 0));
                             umma_f16(d, ah + adv, bl + adv, IDESC, 1);
                             umma_f16(d, ah + adv, bh + adv, IDESC, 1);
                         }
                         umma_commit(bempty + 8 * s);                 // stage reusable once these MMAs retire
-                        if (j == 3 && commit_bar) umma_commit(commit_bar);
+                        if (kb == 1 && commit_bar) umma_commit(commit_bar);
                     }
                     __syncwarp();
                 }
@@ -380,102 +390,114 @@ loftr_layer_tc_kernel(const LayerArgs P) {
             mbar_wait(d_ready, dph & 1); ++dph;          // q, k, v in D0, D1, D2
             tc_fence_after();
             TRACE_E(2);
-            float msg[2][16];                            // [head half hh][v]: head hh*4 + colq
             {
-                // staging inside the A operand (idle until msg is written), fp32:
-                //   Kst [128][64] @0, Vst [128][64] @32K (float4 index XOR (row & 15)); KVs / Ksum have their own region
-                float* Kst = stage_f;
+                // One quarter (heads 2hq, 2hq+1 = 32 columns) at a time, staged in the idle A operand, fp32:
+                //   Qst | Kst | Vst [128][32] @0 / 16K / 32K (float4 index XOR (row & 7)), KVs [12][16][16] @48K, Ksum [12][16] @60K
+                // (1) every thread moves 8 columns of q, k, v of its row from TMEM (elu+1 on q and k);
+                // (2) warp w < 12 owns the (point, head) pair w: KV = K'^T V and Ksum, lane = (2 d, 4 v);
+                // (3) the same warp computes the 21 x 16 message block of its pair as a register-tiled product
+                //     Q' KV (lane = (3 rows, 4 v)): 4 shared-memory wavefronts per d instead of one KV broadcast per row.
+                float* Qst = stage_f;
+                float* Kst = stage_f + 4096;
                 float* Vst = stage_f + 8192;
-                const int p_row = min(row / TOK, PTS - 1);
+                float* KVs = stage_f + 12288;
+                float* Ksum = stage_f + 15360;
+                float4 m[4][3];                          // [quarter][row of the lane's row group]: 4 v values each
+                const int pair = ew, p = pair >> 1, hl = pair & 1;
+                const int rg = lane >> 2, vq = lane & 3;
+                const bool worker = ew < 12;
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    // (1) K' = elu(k)+1 and V of heads 4hh..4hh+3 -> smem (this thread: 16 of the 64 columns)
+                for (int hq = 0; hq < 4; ++hq) {
                     {
-                        uint32_t kr[16], vr[16];
-                        TMEM_LD16(trow + D1 + hh * 64 + colq * 16, kr);
-                        TMEM_LD16(trow + D2 + hh * 64 + colq * 16, vr);
+                        uint32_t qr[8], kr[8], vr[8];
+                        TMEM_LD8(trow + D0 + hq * 32 + colq * 8, qr);
+                        TMEM_LD8(trow + D1 + hq * 32 + colq * 8, kr);
+                        TMEM_LD8(trow + D2 + hq * 32 + colq * 8, vr);
                         tmem_wait_ld();
-                        if (hh == 1) { tc_fence_before(); mbar_arrive(v_free); }    // D2 is free: mlp.0[C:, :C] may go
+                        if (hq == 3) { tc_fence_before(); mbar_arrive(v_free); }    // D2 is free: mlp.0[C:, :C] may go
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float4 kk, vv;
+                        for (int j = 0; j < 2; ++j) {
+                            float4 qq, kk, vv;
+                            qq.x = elu1(acc_f(qr[4 * j + 0])); qq.y = elu1(acc_f(qr[4 * j + 1]));
+                            qq.z = elu1(acc_f(qr[4 * j + 2])); qq.w = elu1(acc_f(qr[4 * j + 3]));
                             kk.x = elu1(acc_f(kr[4 * j + 0])); kk.y = elu1(acc_f(kr[4 * j + 1]));
                             kk.z = elu1(acc_f(kr[4 * j + 2])); kk.w = elu1(acc_f(kr[4 * j + 3]));
                             vv.x = acc_f(vr[4 * j + 0]); vv.y = acc_f(vr[4 * j + 1]);
                             vv.z = acc_f(vr[4 * j + 2]); vv.w = acc_f(vr[4 * j + 3]);
-                            const int f4 = (colq * 4 + j) ^ (row & 15);
-                            reinterpret_cast<float4*>(Kst + row * 64)[f4] = kk;
-                            reinterpret_cast<float4*>(Vst + row * 64)[f4] = vv;
+                            const int f4 = (colq * 2 + j) ^ (row & 7);
+                            reinterpret_cast<float4*>(Qst + row * 32)[f4] = qq;
+                            reinterpret_cast<float4*>(Kst + row * 32)[f4] = kk;
+                            reinterpret_cast<float4*>(Vst + row * 32)[f4] = vv;
                         }
                     }
                     epi_bar();
-                    // (2) KV[p][h] = K'^T V, Ksum[p][h] = sum_s K'   (24 (point, head) pairs x 2 v halves = 48 warp
-                    //     tasks, 3 per warp; lane -> (d, 4 consecutive v); 7 tokens per batch so 14 loads are in flight)
-#pragma unroll 1
-                    for (int q3 = 0; q3 < 3; ++q3) {
-                        const int task = ew * 3 + q3, pair = task >> 1, p = pair >> 2, hl = pair & 3;
-                        const int d = lane >> 1, v0 = (task & 1) * 8 + (lane & 1) * 4;
-                        float acc[4] = {0.f, 0.f, 0.f, 0.f}, ks = 0.f;
+                    if (worker) {
+                        // (2) lane -> d = 2 dp, 2 dp + 1 and v = 4 vq .. 4 vq + 3
+                        const int dp = rg;
+                        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+                        float ks0 = 0.f, ks1 = 0.f;
                         if (p < pts) {
+#pragma unroll 7
+                            for (int u = 0; u < TOK; ++u) {
+                                const int r = p * TOK + u, sw = r & 7;
+                                const float2 kk = *reinterpret_cast<const float2*>(Kst + r * 32 + (((hl * 4 + (dp >> 1)) ^ sw) << 2) + (dp & 1) * 2);
+                                const float4 vv = reinterpret_cast<const float4*>(Vst + r * 32)[(hl * 4 + vq) ^ sw];
+                                ks0 += kk.x; ks1 += kk.y;
+                                a0.x = fmaf(kk.x, vv.x, a0.x); a0.y = fmaf(kk.x, vv.y, a0.y);
+                                a0.z = fmaf(kk.x, vv.z, a0.z); a0.w = fmaf(kk.x, vv.w, a0.w);
+                                a1.x = fmaf(kk.y, vv.x, a1.x); a1.y = fmaf(kk.y, vv.y, a1.y);
+                                a1.z = fmaf(kk.y, vv.z, a1.z); a1.w = fmaf(kk.y, vv.w, a1.w);
+                            }
+                        }
+                        *reinterpret_cast<float4*>(KVs + pair * 256 + (2 * dp) * 16 + 4 * vq) = a0;
+                        *reinterpret_cast<float4*>(KVs + pair * 256 + (2 * dp + 1) * 16 + 4 * vq) = a1;
+                        if (vq == 0) *reinterpret_cast<float2*>(Ksum + pair * 16 + 2 * dp) = make_float2(ks0, ks1);
+                        __syncwarp();
+                        // (3) lane -> rows 3 rg .. 3 rg + 2 of the point (rg < 7) and v = 4 vq .. 4 vq + 3
+                        float4 acc[3];
+                        float den[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-                            for (int s0 = 0; s0 < TOK; s0 += 7) {
-                                float kk[7];
-                                float4 va[7];
+                        for (int i = 0; i < 3; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int r0 = p * TOK + min(rg, 6) * 3;
 #pragma unroll
-                                for (int u = 0; u < 7; ++u) {
-                                    const int r = p * TOK + s0 + u, sw = r & 15;
-                                    kk[u] = Kst[r * 64 + (((hl * 4 + (d >> 2)) ^ sw) << 2) + (d & 3)];
-                                    va[u] = reinterpret_cast<const float4*>(Vst + r * 64)[(hl * 4 + (v0 >> 2)) ^ sw];
-                                }
+                        for (int dq = 0; dq < 4; ++dq) {
+                            const float4 ksum = *reinterpret_cast<const float4*>(Ksum + pair * 16 + 4 * dq);
+                            float4 qv[3];
 #pragma unroll
-                                for (int u = 0; u < 7; ++u) {
-                                    ks += kk[u];
-                                    acc[0] = fmaf(kk[u], va[u].x, acc[0]); acc[1] = fmaf(kk[u], va[u].y, acc[1]);
-                                    acc[2] = fmaf(kk[u], va[u].z, acc[2]); acc[3] = fmaf(kk[u], va[u].w, acc[3]);
+                            for (int i = 0; i < 3; ++i) {
+                                const int r = r0 + i;
+                                qv[i] = reinterpret_cast<const float4*>(Qst + r * 32)[(hl * 4 + dq) ^ (r & 7)];
+                                den[i] = fmaf(qv[i].x, ksum.x, den[i]); den[i] = fmaf(qv[i].y, ksum.y, den[i]);
+                                den[i] = fmaf(qv[i].z, ksum.z, den[i]); den[i] = fmaf(qv[i].w, ksum.w, den[i]);
+                            }
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float4 kv = *reinterpret_cast<const float4*>(KVs + pair * 256 + (4 * dq + e) * 16 + 4 * vq);
+#pragma unroll
+                                for (int i = 0; i < 3; ++i) {
+                                    const float q1 = e == 0 ? qv[i].x : e == 1 ? qv[i].y : e == 2 ? qv[i].z : qv[i].w;
+                                    acc[i].x = fmaf(q1, kv.x, acc[i].x); acc[i].y = fmaf(q1, kv.y, acc[i].y);
+                                    acc[i].z = fmaf(q1, kv.z, acc[i].z); acc[i].w = fmaf(q1, kv.w, acc[i].w);
                                 }
                             }
                         }
-                        *reinterpret_cast<float4*>(KVs + pair * 256 + d * 16 + v0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                        if ((lane & 1) == 0 && (task & 1) == 0) Ksum[pair * 16 + d] = ks;
-                    }
-                    epi_bar();
-                    // (3) message row of head hh*4 + colq -> registers
-                    {
-                        uint32_t qr[16];
-                        TMEM_LD16(trow + D0 + (hh * 4 + colq) * 16, qr);
-                        tmem_wait_ld();
-                        const int pair = p_row * 4 + colq;
-                        float Q[16], den = 0.f;
 #pragma unroll
-                        for (int dd = 0; dd < 16; ++dd) { Q[dd] = elu1(acc_f(qr[dd])); den = fmaf(Q[dd], Ksum[pair * 16 + dd], den); }
-#pragma unroll
-                        for (int v = 0; v < 16; ++v) msg[hh][v] = 0.f;
-#pragma unroll
-                        for (int dd = 0; dd < 16; ++dd) {
-                            const float4* kv = reinterpret_cast<const float4*>(KVs + pair * 256 + dd * 16);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float4 t = kv[j];
-                                msg[hh][4 * j + 0] = fmaf(Q[dd], t.x, msg[hh][4 * j + 0]); msg[hh][4 * j + 1] = fmaf(Q[dd], t.y, msg[hh][4 * j + 1]);
-                                msg[hh][4 * j + 2] = fmaf(Q[dd], t.z, msg[hh][4 * j + 2]); msg[hh][4 * j + 3] = fmaf(Q[dd], t.w, msg[hh][4 * j + 3]);
-                            }
+                        for (int i = 0; i < 3; ++i) {
+                            const float z = __fdividef(1.0f, den[i] + P.attn_eps);
+                            m[hq][i] = make_float4(acc[i].x * z, acc[i].y * z, acc[i].z * z, acc[i].w * z);
                         }
-                        const float z = __fdividef(1.0f, den + P.attn_eps);
-#pragma unroll
-                        for (int v = 0; v < 16; ++v) msg[hh][v] *= z;
                     }
-                    if (hh == 0) TRACE_E(3);
-                    // the barrier after the next half's stage (1) orders (3) before the next (2); stage (1) of the
-                    // next half overwrites Kst / Vst, which stage (2) finished reading before the barrier above
+                    if (hq == 0) TRACE_E(3);
+                    epi_bar();                           // (2), (3) done reading: the next quarter may overwrite the staging
                 }
-                epi_bar();                               // staging dead: A may be overwritten
+                // staging dead (barrier above): msg -> A operand, rows of point p, columns of head 2 hq + hl
+                if (worker && rg < 7) {
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh)
+                    for (int hq = 0; hq < 4; ++hq)
 #pragma unroll
-                    for (int j = 0; j < 2; ++j)
-                        split_store8(a_base, row, (hh * 4 + colq) * 16 + j * 8,
-                                     make_float4(msg[hh][8 * j], msg[hh][8 * j + 1], msg[hh][8 * j + 2], msg[hh][8 * j + 3]),
-                                     make_float4(msg[hh][8 * j + 4], msg[hh][8 * j + 5], msg[hh][8 * j + 6], msg[hh][8 * j + 7]));
+                        for (int i = 0; i < 3; ++i)
+                            split_store4(a_base, p * TOK + rg * 3 + i, (2 * hq + hl) * 16 + 4 * vq, m[hq][i]);
+                }
             }
             publish(a_ready);
             TRACE_E(4);
@@ -583,7 +605,7 @@ loftr_layer_tc_kernel(const LayerArgs P) {
 }
 
 // ------------------------------------------------------------------------------------ weight packing
-// block b (issue order) -> (matrix, first row, first column, leading dimension); chunk = block * 4 + (N half * 2 + K half)
+// block b (issue order) -> (matrix, first row, first column, leading dimension); chunk = block * 2 + K half
 struct PackArgs {
     const float* wq; const float* wk; const float* wv; const float* wm; const float* w1; const float* w2;
     uint8_t* dst;
@@ -592,8 +614,8 @@ struct PackArgs {
 __global__ void __launch_bounds__(256)
 loftr_pack_weights_kernel(const PackArgs P) {
     const int t = blockIdx.x * 256 + threadIdx.x;                // one 16-byte segment (8 fp16) each
-    if (t >= NCHUNK * 64 * 8) return;
-    const int seg = t & 7, row = (t >> 3) & 63, c = t >> 9, blk = c >> 2, nh = (c >> 1) & 1, kb = c & 1;
+    if (t >= NCHUNK * 128 * 8) return;
+    const int seg = t & 7, row = (t >> 3) & 127, c = t >> 10, blk = c >> 1, kb = c & 1;
     const float* W; int r0 = 0, c0 = 0, ld = CH;
     switch (blk) {
         case 0: W = P.wq; break;
@@ -607,7 +629,7 @@ loftr_pack_weights_kernel(const PackArgs P) {
         case 8: W = P.w2; ld = 2 * CH; break;                    // mlp.2[:, :C]
         default: W = P.w2; ld = 2 * CH; c0 = CH; break;          // mlp.2[:, C:]
     }
-    const float4* src = reinterpret_cast<const float4*>(W + (size_t)(r0 + nh * 64 + row) * ld + c0 + kb * 64 + seg * 8);
+    const float4* src = reinterpret_cast<const float4*>(W + (size_t)(r0 + row) * ld + c0 + kb * 64 + seg * 8);
     float4 a = __ldg(src), b = __ldg(src + 1);
     a.x *= W_SCALE; a.y *= W_SCALE; a.z *= W_SCALE; a.w *= W_SCALE;
     b.x *= W_SCALE; b.y *= W_SCALE; b.z *= W_SCALE; b.w *= W_SCALE;
@@ -616,12 +638,12 @@ loftr_pack_weights_kernel(const PackArgs P) {
     split2(b.x, b.y, hi.z, lo.z); split2(b.z, b.w, hi.w, lo.w);
     uint8_t* d = P.dst + (size_t)c * CHUNK + sw128(row, seg);
     *reinterpret_cast<uint4*>(d) = hi;
-    *reinterpret_cast<uint4*>(d + CHUNK / 2) = lo;
+    *reinterpret_cast<uint4*>(d + SLAB) = lo;
 }
 
 // ------------------------------------------------------------------------------------ self-test GEMM
 // D (128 x 128) = A (128 x K) * B (128 x K)^T, K in {64, 128}, through exactly the staging /
-// descriptor / TMEM helpers of the layer kernel (two N = 64 halves).  terms = 1: plain fp16; terms = 3: hi/lo split.
+// descriptor / TMEM helpers of the layer kernel.  terms = 1: plain fp16; terms = 3: hi/lo split.
 __global__ void __launch_bounds__(128, 1)
 tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int K, int terms) {
     extern __shared__ uint8_t smem_raw[];
@@ -649,20 +671,17 @@ tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B
     const uint32_t tmem = tmem_slot;
     if (threadIdx.x == 0) {
         const uint32_t a_hi = smem_u32(a_base), a_lo = a_hi + 2 * SLAB, b_hi = smem_u32(b_base), b_lo = b_hi + 2 * SLAB;
-        constexpr uint32_t IDESC = idesc_f16(64);
-        for (int nh = 0; nh < 2; ++nh) {
-            uint32_t acc = 0;
-            const uint32_t boff = (uint32_t)nh * 64 * 128;           // rows 64.. of the B slab
-            for (int kb = 0; kb < K / 64; ++kb)
-                for (int k16 = 0; k16 < 4; ++k16) {
-                    const uint64_t adv = (uint64_t)(k16 * 2);
-                    if (terms == 3) {
-                        umma_f16(tmem + nh * 64, smem_desc(a_lo + kb * SLAB) + adv, smem_desc(b_hi + kb * SLAB + boff) + adv, IDESC, acc); acc = 1;
-                        umma_f16(tmem + nh * 64, smem_desc(a_hi + kb * SLAB) + adv, smem_desc(b_lo + kb * SLAB + boff) + adv, IDESC, 1);
-                    }
-                    umma_f16(tmem + nh * 64, smem_desc(a_hi + kb * SLAB) + adv, smem_desc(b_hi + kb * SLAB + boff) + adv, IDESC, acc); acc = 1;
+        constexpr uint32_t IDESC = idesc_f16(128);
+        uint32_t acc = 0;
+        for (int kb = 0; kb < K / 64; ++kb)
+            for (int k16 = 0; k16 < 4; ++k16) {
+                const uint64_t adv = (uint64_t)(k16 * 2);
+                if (terms == 3) {
+                    umma_f16(tmem, smem_desc(a_lo + kb * SLAB) + adv, smem_desc(b_hi + kb * SLAB) + adv, IDESC, acc); acc = 1;
+                    umma_f16(tmem, smem_desc(a_hi + kb * SLAB) + adv, smem_desc(b_lo + kb * SLAB) + adv, IDESC, 1);
                 }
-        }
+                umma_f16(tmem, smem_desc(a_hi + kb * SLAB) + adv, smem_desc(b_hi + kb * SLAB) + adv, IDESC, acc); acc = 1;
+            }
         umma_commit(smem_u32(&bar));
     }
     mbar_wait(smem_u32(&bar), 0);
@@ -761,7 +780,7 @@ int loftr_tc_pack(const riders_loftr_weights& w, int layer_slot, void* tc_ws, cu
     P.wq = w.wq; P.wk = w.wk; P.wv = w.wv; P.wm = w.wm; P.w1 = w.w1; P.w2 = w.w2;
     P.dst = pack_base(tc_ws) + (size_t)layer_slot * tc::LAYER_PACK_BYTES;
     count_launches(1);
-    tc::loftr_pack_weights_kernel<<<ceil_div(tc::NCHUNK * 64 * 8, 256), 256, 0, st>>>(P);
+    tc::loftr_pack_weights_kernel<<<ceil_div(tc::NCHUNK * 128 * 8, 256), 256, 0, st>>>(P);
     return check_launch("loftr_pack_weights");
 }
 
