@@ -158,6 +158,21 @@ def bench_interp(B=64, K=512, H=512, W=640):
     report("extract_knots", ms, best, B * H * W * 9, B=B, K=K)
 
 
+def bench_membw(nbytes=4 << 30):
+    """Direction-specific HBM rooflines on this box (library kernels, for reference next to MEASURED_PEAKS' copy figure):
+    write-only (fill_), read-only (sum), copy."""
+    a = torch.empty(nbytes // 4, dtype=torch.float32, device=DEV)
+    b = torch.empty_like(a)
+    ms, best = timeit(lambda: a.fill_(1.0), iters=8)
+    report("hbm_write_only_fill", ms, best, nbytes)
+    ms, best = timeit(lambda: a.zero_(), iters=8)
+    report("hbm_write_only_memset", ms, best, nbytes)
+    ms, best = timeit(lambda: a.sum(), iters=8)
+    report("hbm_read_only_sum", ms, best, nbytes)
+    ms, best = timeit(lambda: b.copy_(a), iters=8)
+    report("hbm_copy", ms, best, 2 * nbytes)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["reduce", "lsq", "gather", "loftr", "interp", "glue"]
     torch.cuda.set_device(DEV)
