@@ -286,6 +286,11 @@ int riders_d2s_bias_act_place_nhwc(const float* y4, const float* bias, int Ca, c
 int riders_conv3x3_head_nhwc(const float* x, int N, int C, int H, int W,
                              const float* bias_host, float slope, const float* weight_host,
                              float* out, void* stream);
+/* the same with torch.sigmoid fused (apply_sigmoid != 0): writes the CONFIDENCES RCNetModel.forward returns with
+ * return_logits=False (RCNet/rcnet_model.py:123), same SFU formula as riders_confidence_reduce's logits mode.  */
+int riders_conv3x3_head_sigmoid_nhwc(const float* x, int N, int C, int H, int W,
+                                     const float* bias_host, float slope, const float* weight_host,
+                                     int apply_sigmoid, float* out, void* stream);
 /* out = act(x + bias[c]) over `pixels` channels-last pixels of C channels (in place when out == x);
  * slope 0.2 = LeakyReLU of utils/net_utils.py:15, 0 = ReLU, 1 = identity; bias may be NULL.          */
 int riders_bias_act_nhwc(const float* x, const float* bias, int C, long long pixels, float slope,

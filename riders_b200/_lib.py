@@ -58,6 +58,7 @@ SIGNATURES = {
     "riders_bias_leaky_place_nhwc": (ci, [vp, vp, ci, vp, ci, C.c_longlong, cf, vp, ci, vp]),
     "riders_bias_act_nhwc": (ci, [vp, vp, ci, C.c_longlong, cf, vp, vp]),
     "riders_conv3x3_head_nhwc": (ci, [vp, ci, ci, ci, ci, vp, cf, vp, vp, vp]),
+    "riders_conv3x3_head_sigmoid_nhwc": (ci, [vp, ci, ci, ci, ci, vp, cf, vp, ci, vp, vp]),
     "riders_d2s_bias_act_concat_nhwc": (ci, [vp, vp, ci, vp, ci, ci, ci, ci, cf, vp, vp]),
     "riders_d2s_bias_act_place_nhwc": (ci, [vp, vp, ci, vp, ci, ci, ci, ci, cf, vp, ci, vp]),
     "riders_debug_set": (ci, [C.c_char_p, ci]),

@@ -57,13 +57,43 @@ __device__ __forceinline__ float ld_stream_if(const float* p, bool on) {
     return v;
 }
 
-template <bool LOGITS, int ROWS>
+// four vertically stacked crop pixels under ONE predicate, row stride known at compile time (immediate offsets):
+// 1 setp + 4 mov + 4 predicated loads instead of 4 x (setp + mov + 64-bit add + load)
+template <bool LOGITS, int PW>
+__device__ __forceinline__ void ld4_stream_if(const float* p, bool on, float (&v)[4]) {
+    if (LOGITS)
+        asm volatile(
+            "{\n"
+            ".reg .pred q;\n"
+            "setp.ne.b32 q, %5, 0;\n"
+            "mov.f32 %0, 0fFF800000;\n mov.f32 %1, 0fFF800000;\n mov.f32 %2, 0fFF800000;\n mov.f32 %3, 0fFF800000;\n"
+            "@q ld.global.nc.L1::no_allocate.f32 %0, [%4];\n"
+            "@q ld.global.nc.L1::no_allocate.f32 %1, [%4+%6];\n"
+            "@q ld.global.nc.L1::no_allocate.f32 %2, [%4+%7];\n"
+            "@q ld.global.nc.L1::no_allocate.f32 %3, [%4+%8];\n"
+            "}\n" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p), "r"((int)on), "n"(PW * 4), "n"(PW * 8), "n"(PW * 12));
+    else
+        asm volatile(
+            "{\n"
+            ".reg .pred q;\n"
+            "setp.ne.b32 q, %5, 0;\n"
+            "mov.f32 %0, 0f00000000;\n mov.f32 %1, 0f00000000;\n mov.f32 %2, 0f00000000;\n mov.f32 %3, 0f00000000;\n"
+            "@q ld.global.nc.L1::no_allocate.f32 %0, [%4];\n"
+            "@q ld.global.nc.L1::no_allocate.f32 %1, [%4+%6];\n"
+            "@q ld.global.nc.L1::no_allocate.f32 %2, [%4+%7];\n"
+            "@q ld.global.nc.L1::no_allocate.f32 %3, [%4+%8];\n"
+            "}\n" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p), "r"((int)on), "n"(PW * 4), "n"(PW * 8), "n"(PW * 12));
+}
+
+// PW > 0: crop width fixed at compile time (RC-Net's 100): immediate row offsets, constant address math
+template <bool LOGITS, int ROWS, int PW>
 __global__ void __launch_bounds__(CR_THREADS)
 confidence_reduce_kernel(const float* __restrict__ conf, const float* __restrict__ pts,
                          const int* __restrict__ frame_offsets,
-                         int H, int W, int ph, int pw, float thr,
+                         int H, int W, int ph, int pw_rt, float thr,
                          float* __restrict__ depth, float* __restrict__ response,
                          int32_t* __restrict__ select) {
+    const int pw = PW > 0 ? PW : pw_rt;
     constexpr int TILE_H = (CR_THREADS / 32) * ROWS;
     __shared__ Cand cand[CHUNK];
     __shared__ int warp_count[CR_THREADS / 32];
@@ -126,8 +156,12 @@ confidence_reduce_kernel(const float* __restrict__ conf, const float* __restrict
                 const float* src = q[u].base + thr_off;
                 any[u] = on && i0 + ROWS > 0 && i0 < ph;
                 if (i0 >= 0 && i0 + ROWS <= ph) {      // the usual case: all ROWS rows inside the 240-row crop
+                    if constexpr (PW > 0 && ROWS == 4) {
+                        ld4_stream_if<LOGITS, PW>(src, in_col, v[u]);
+                    } else {
 #pragma unroll
-                    for (int m = 0; m < ROWS; ++m) v[u][m] = ld_stream_if<LOGITS>(src + m * pw, in_col);
+                        for (int m = 0; m < ROWS; ++m) v[u][m] = ld_stream_if<LOGITS>(src + m * pw, in_col);
+                    }
                 } else {
 #pragma unroll
                     for (int m = 0; m < ROWS; ++m)
@@ -169,7 +203,10 @@ template <bool LOGITS, int ROWS>
 static void launch_reduce(const float* conf, const float* pts, const int* frame_offsets, int B, int H, int W, int ph, int pw,
                           float thr, float* depth, float* response, int32_t* select, cudaStream_t st) {
     dim3 grid(ceil_div(W, TILE_W), ceil_div(H, (CR_THREADS / 32) * ROWS), B);
-    confidence_reduce_kernel<LOGITS, ROWS><<<grid, CR_THREADS, 0, st>>>(conf, pts, frame_offsets, H, W, ph, pw, thr, depth, response, select);
+    if (ROWS == 4 && pw == 100)                 // RC-Net's patch width (run_rcnet_zju.py:30)
+        confidence_reduce_kernel<LOGITS, ROWS, 100><<<grid, CR_THREADS, 0, st>>>(conf, pts, frame_offsets, H, W, ph, pw, thr, depth, response, select);
+    else
+        confidence_reduce_kernel<LOGITS, ROWS, 0><<<grid, CR_THREADS, 0, st>>>(conf, pts, frame_offsets, H, W, ph, pw, thr, depth, response, select);
 }
 
 }  // namespace riders

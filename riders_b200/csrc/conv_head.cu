@@ -21,6 +21,7 @@ struct HeadParams {
     float w[3][3][HEAD_C];      // [ky][kx][c]
     float bias[HEAD_C];
     float slope;
+    int sigmoid;                // write torch.sigmoid(logit) (rcnet_model.py:123) instead of the logit
 };
 
 __global__ void __launch_bounds__(HEAD_WARPS * 32)
@@ -83,7 +84,8 @@ conv3x3_head_kernel(const float4* __restrict__ x, float* __restrict__ out, const
         const float t1 = __shfl_up_sync(0xffffffffu, d[1][0], 1) + d[1][1] + __shfl_down_sync(0xffffffffu, d[1][2], 1);   // -> row h
         const float t2 = __shfl_up_sync(0xffffffffu, d[2][0], 1) + d[2][1] + __shfl_down_sync(0xffffffffu, d[2][2], 1);   // -> row h-1
         acc_prev += t2;
-        if (writes && h - 1 >= r0 && h - 1 < r1) __stcs(o + (size_t)(h - 1) * W + col, acc_prev);
+        if (writes && h - 1 >= r0 && h - 1 < r1)
+            __stcs(o + (size_t)(h - 1) * W + col, P.sigmoid ? __fdividef(1.0f, 1.0f + __expf(-acc_prev)) : acc_prev);
         acc_prev = acc_cur + t1;
         acc_cur = t0;
     }
@@ -94,6 +96,12 @@ conv3x3_head_kernel(const float4* __restrict__ x, float* __restrict__ out, const
 extern "C" int riders_conv3x3_head_nhwc(const float* x, int N, int C, int H, int W,
                                         const float* bias_host, float slope, const float* weight_host,
                                         float* out, void* stream) {
+    return riders_conv3x3_head_sigmoid_nhwc(x, N, C, H, W, bias_host, slope, weight_host, 0, out, stream);
+}
+
+extern "C" int riders_conv3x3_head_sigmoid_nhwc(const float* x, int N, int C, int H, int W,
+                                                const float* bias_host, float slope, const float* weight_host,
+                                                int apply_sigmoid, float* out, void* stream) {
     using namespace riders;
     RIDERS_REQUIRE(N >= 0 && H > 0 && W > 0, "conv3x3_head: bad shape");
     RIDERS_REQUIRE(C == HEAD_C, "conv3x3_head: built for %d input channels (got %d)", HEAD_C, C);
@@ -107,6 +115,7 @@ extern "C" int riders_conv3x3_head_nhwc(const float* x, int N, int C, int H, int
             for (int kx = 0; kx < 3; ++kx) P.w[ky][kx][c] = weight_host[(c * 3 + ky) * 3 + kx];    // torch (1, C, 3, 3)
     }
     P.slope = slope;
+    P.sigmoid = apply_sigmoid ? 1 : 0;
     const int strips = ceil_div(W, 30);
     const int S = ceil_div(W, strips);
     const int segs = ceil_div(H, 64);

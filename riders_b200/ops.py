@@ -327,8 +327,9 @@ def _host_floats(t):
     return h
 
 
-def conv3x3_head(x_raw, bias, slope, weight):
-    """logits (N,1,H,W) = conv2d(act(x_raw + bias), weight (1,C,3,3), padding=1) for a channels-last C=16 map."""
+def conv3x3_head(x_raw, bias, slope, weight, sigmoid=False):
+    """logits (N,1,H,W) = conv2d(act(x_raw + bias), weight (1,C,3,3), padding=1) for a channels-last C=16 map;
+    ``sigmoid=True`` writes torch.sigmoid(logits), the confidences of RCNetModel.forward(return_logits=False)."""
     _need_cuda(x_raw)
     if not (_is_channels_last(x_raw) and x_raw.dtype == torch.float32):
         raise _lib.RidersError("conv3x3_head needs a channels_last float32 map")
@@ -336,8 +337,9 @@ def conv3x3_head(x_raw, bias, slope, weight):
     hb, hw = _host_floats(bias), _host_floats(weight)
     out = torch.empty((N, 1, H, W), device=x_raw.device, dtype=torch.float32)
     with _span("conv3x3_head", (x_raw.numel() + out.numel()) * 4):
-        rc = _lib.lib().riders_conv3x3_head_nhwc(_ptr(x_raw), N, Cc, H, W, _ptr(hb), float(slope), _ptr(hw), _ptr(out), _stream())
-    _lib.check(rc, "riders_conv3x3_head_nhwc")
+        rc = _lib.lib().riders_conv3x3_head_sigmoid_nhwc(_ptr(x_raw), N, Cc, H, W, _ptr(hb), float(slope), _ptr(hw),
+                                                         1 if sigmoid else 0, _ptr(out), _stream())
+    _lib.check(rc, "riders_conv3x3_head_sigmoid_nhwc")
     return out
 
 

@@ -382,7 +382,10 @@ class MultiScaleDecoder(torch.nn.Module):
         see ``forward``): the number of channels a placed skip must leave free in its concat buffer."""
         return [getattr(self, self._order[n_skips - 1 - i]).deconv.conv.conv.out_channels for i in range(n_skips)]
 
-    def forward(self, x, skips, shape=None):
+    def forward(self, x, skips, shape=None, head_sigmoid=False):
+        """``head_sigmoid`` (inference fast path only; ignored otherwise - check ``self.last_head_sigmoid``): let the fused
+        head kernel write torch.sigmoid(logits), so that the reduce kernel streams confidences."""
+        self.last_head_sigmoid = False
         n = len(skips) - 1
         y = x
         for name in self._order[:-1]:
@@ -396,7 +399,8 @@ class MultiScaleDecoder(torch.nn.Module):
             # inference fast path: last conv raw -> [bias + LeakyReLU + 3x3 head] in one kernel -> logits
             y_raw, bias, slope = last(y, shape=tuple(shape[-2:]), raw=True)
             if ops._is_channels_last(y_raw):
-                return [ops.conv3x3_head(y_raw, bias, slope, head.weight)]
+                self.last_head_sigmoid = bool(head_sigmoid)
+                return [ops.conv3x3_head(y_raw, bias, slope, head.weight, sigmoid=head_sigmoid)]
             y = ops.bias_act_(y_raw, bias, slope) if bias is not None or slope != 1.0 else y_raw
             return [self.output0(y)]
         y = last(y, skips[n]) if n == 0 else last(y, shape=tuple(shape[-2:]))

@@ -9,6 +9,7 @@ reduce kernel, which applies the sigmoid + threshold on the fly and never materi
 import torch
 
 from .. import ops
+from . import networks
 
 
 def _pad_edge(image, px, py):
@@ -89,11 +90,23 @@ def forward_output_batched(model, images, radar_points, frame_offsets, response_
     latent = enc.encode_latent(latent_image, radar_points, rois)
     # each pooled skip is gathered straight into the concat buffer of the decoder block that consumes it
     lead = dec.skip_lead_channels(len(skips_image)) if hasattr(dec, 'skip_lead_channels') else None
+    sigmoid_in_head = None if isinstance(dec, networks.MultiScaleDecoder) else False
     for s in range(0, R, chunk_points):
         e = min(R, s + chunk_points)
         skips = enc.gather_skips(skips_image, rois[s:e], lead_channels=lead)
-        logits[s:e] = dec(x=latent[s:e], skips=skips, shape=(ph, pw))[-1]
-    out = list(ops.confidence_reduce(logits, radar_points, frame_offsets, H, W, response_thr, logits=True,
+        # the fused head kernel writes sigmoid(logit) directly when it runs (SFU work under an HBM-bound kernel), so the
+        # reduce streams confidences; otherwise the reduce applies the sigmoid itself
+        if sigmoid_in_head is None or sigmoid_in_head:
+            logits[s:e] = dec(x=latent[s:e], skips=skips, shape=(ph, pw), head_sigmoid=True)[-1]
+            done = bool(getattr(dec, 'last_head_sigmoid', False))
+            if sigmoid_in_head is None:
+                sigmoid_in_head = done
+            elif not done:
+                logits[s:e] = torch.sigmoid(logits[s:e])
+        else:
+            logits[s:e] = dec(x=latent[s:e], skips=skips, shape=(ph, pw))[-1]
+    is_logits = not sigmoid_in_head
+    out = list(ops.confidence_reduce(logits, radar_points, frame_offsets, H, W, response_thr, logits=is_logits,
                                      want_select=return_select))
     if retry_empty:
         thr = float(response_thr)
@@ -104,7 +117,7 @@ def forward_output_batched(model, images, radar_points, frame_offsets, response_
                 s, e = frame_offsets[b], frame_offsets[b + 1]
                 if e == s:
                     continue
-                again = ops.confidence_reduce(logits[s:e], radar_points[s:e], [0, e - s], H, W, thr, logits=True,
+                again = ops.confidence_reduce(logits[s:e], radar_points[s:e], [0, e - s], H, W, thr, logits=is_logits,
                                               want_select=return_select)
                 for o, a in zip(out, again):
                     if o is not None:

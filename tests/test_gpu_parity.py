@@ -541,6 +541,10 @@ def test_conv3x3_head_matches_torch():
     np.testing.assert_allclose(ops.conv3x3_head(big, bias, 0.2, w).cpu().numpy(),
                                torch.nn.functional.conv2d(torch.nn.functional.leaky_relu(big + bias.view(1, -1, 1, 1), 0.2), w, padding=1).cpu().numpy(),
                                rtol=1e-5, atol=1e-5)
+    # fused sigmoid (what forward_output_batched feeds the reduce kernel): torch.sigmoid of the SAME logits, 1e-6
+    logit = ops.conv3x3_head(big, bias, 0.2, w)
+    np.testing.assert_allclose(ops.conv3x3_head(big, bias, 0.2, w, sigmoid=True).cpu().numpy(), torch.sigmoid(logit).cpu().numpy(),
+                               rtol=2e-6, atol=1e-7)
 
 
 # ------------------------------------------------------------------------------------ N2/N3 scaffold, N4 metrics
