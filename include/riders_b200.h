@@ -279,6 +279,13 @@ int riders_d2s_bias_act_concat_nhwc(const float* y4, const float* bias, int Ca, 
 /* ... into a map of out_pixel_stride >= Ca + Cb floats per pixel (skip already in place: Cb = 0, skip = NULL) */
 int riders_d2s_bias_act_place_nhwc(const float* y4, const float* bias, int Ca, const float* skip, int Cb,
                                    int N, int h, int w, float slope, float* out, int out_pixel_stride, void* stream);
+/* Sub-pixel form for blocks whose target is 2n+1 along ONE axis (torch nearest: source max(j-1,0)>>1; RC-Net 30x12 -> 60x25,
+ * 7x3 -> 15x6): y4 (N,4*Ca,hp,wp) = phase convolution of x replicate-padded by one on the left (sx) / top (sy); yfirst =
+ * 3x1 / 1x3 phase convolution of x's first column (N,2*Ca,h,1) / row (N,2*Ca,1,w); out (N, ld, 2hp-sy, 2wp-sx), channels
+ * [0,Ca) = act(. + bias) with pixel stride ld = out_pixel_stride (the skip, if any, is already in place behind them).    */
+int riders_d2s_shift_bias_act_place_nhwc(const float* y4, const float* yfirst, const float* bias, int Ca,
+                                         int N, int hp, int wp, int sy, int sx, float slope,
+                                         float* out, int out_pixel_stride, void* stream);
 /* Decoder head in front of riders_confidence_reduce: logits (N,H,W) = conv3x3(act(x + bias)), zero padding,
  * x (N,H,W,C=16) channels-last RAW output of the last decoder convolution, weight_host (1,C,3,3) and
  * bias_host (C, or NULL) in HOST memory (they become kernel parameters).  MultiScaleDecoder.output0,

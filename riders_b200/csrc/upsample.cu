@@ -296,3 +296,70 @@ extern "C" int riders_d2s_bias_act_place_nhwc(const float* y4, const float* bias
         Ca / 4, Cb / 4, out_pixel_stride / 4, ct_shift, h, w, slope, rows, rows_per_block);
     return check_launch("d2s_bias_act_concat_nhwc");
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// The same sub-pixel trick for decoder blocks whose target is 2n + 1 along ONE axis (RC-Net: 30x12 -> 60x25 and
+// 7x3 -> 15x6).  torch's nearest resize to 2n + 1 picks source index max(j - 1, 0) >> 1: the resized map is the exact
+// 2x upsampling of x' = replicate-pad(x, 1 on the left / top) without its first column / row.  So for X >= 1 (Y >= 1)
+// the 3x3 convolution of the resized map is the phase convolution of x' read one output pixel further (k = X + 1);
+// only the first column (row), whose left (top) neighbour is the zero padding instead of another copy of x[0], differs:
+// it comes from a 3x1 (1x3) phase convolution of x's first column (row) with the kx (ky) in {1, 2} taps pre-summed.
+//   y4     (N, 4*Ca, hp, wp)  phase convolution of x' (hp = h + sy, wp = w + sx), channel (2a+b)*Ca + c
+//   yfirst sx: (N, 2*Ca, h, 1) channel a*Ca + c  |  sy: (N, 2*Ca, 1, w) channel b*Ca + c
+//   out    (N, ld, 2*hp - sy, 2*wp - sx): channels [0, Ca) = act(. + bias), pixel stride ld (skip already in place)
+// ---------------------------------------------------------------------------------------------
+namespace riders {
+
+__global__ void __launch_bounds__(256)
+d2s_shift_bias_act_kernel(const float4* __restrict__ y4, const float4* __restrict__ yfirst, const float* __restrict__ bias,
+                          float4* __restrict__ out, int Ca4, int ld4, int hp, int wp, int sy, int sx, float slope,
+                          long long total) {
+    const int H = 2 * hp - sy, W = 2 * wp - sx;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const int c = (int)(e % Ca4);
+        long long t = e / Ca4;
+        const int X = (int)(t % W); t /= W;
+        const int Y = (int)(t % H);
+        const long long n = t / H;
+        float4 v;
+        if (sx && X == 0) {
+            v = __ldcs(yfirst + (n * (hp - sy) + (Y >> 1)) * (2 * Ca4) + (Y & 1) * Ca4 + c);
+        } else if (sy && Y == 0) {
+            v = __ldcs(yfirst + (n * (wp - sx) + (X >> 1)) * (2 * Ca4) + (X & 1) * Ca4 + c);
+        } else {
+            const int ky = Y + sy, kx = X + sx;
+            v = __ldcs(y4 + ((n * hp + (ky >> 1)) * (long long)wp + (kx >> 1)) * (4 * Ca4) + (2 * (ky & 1) + (kx & 1)) * Ca4 + c);
+        }
+        if (bias) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + c);
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+        }
+        v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+        v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+        out[((n * H + Y) * (long long)W + X) * ld4 + c] = v;
+    }
+}
+
+}  // namespace riders
+
+extern "C" int riders_d2s_shift_bias_act_place_nhwc(const float* y4, const float* yfirst, const float* bias, int Ca,
+                                                    int N, int hp, int wp, int sy, int sx, float slope,
+                                                    float* out, int out_pixel_stride, void* stream) {
+    using namespace riders;
+    RIDERS_REQUIRE(N >= 0 && Ca > 0 && (Ca & 3) == 0 && hp > 1 && wp > 1, "d2s_shift: bad shape");
+    RIDERS_REQUIRE((sy == 0 || sy == 1) && (sx == 0 || sx == 1) && sy + sx == 1, "d2s_shift: exactly one of sy, sx must be 1");
+    RIDERS_REQUIRE(out_pixel_stride >= Ca && (out_pixel_stride & 3) == 0, "d2s_shift: out_pixel_stride=%d < %d channels or not %%4", out_pixel_stride, Ca);
+    if (N == 0) return RIDERS_OK;
+    RIDERS_REQUIRE(y4 && yfirst && out, "d2s_shift: null pointer");
+    RIDERS_REQUIRE(((((uintptr_t)y4) | ((uintptr_t)yfirst) | ((uintptr_t)out) | ((uintptr_t)bias)) & 15) == 0, "d2s_shift: 16-byte alignment");
+    const long long total = (long long)N * (2 * hp - sy) * (2 * wp - sx) * (Ca / 4);
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    count_launches(1);
+    d2s_shift_bias_act_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(y4), reinterpret_cast<const float4*>(yfirst), bias, reinterpret_cast<float4*>(out),
+        Ca / 4, out_pixel_stride / 4, hp, wp, sy, sx, slope, total);
+    return check_launch("d2s_shift_bias_act_place_nhwc");
+}

@@ -310,6 +310,32 @@ def d2s_bias_act_concat(y4, bias, skip, slope=0.2):
     return out
 
 
+def d2s_shift_bias_act_concat(y4, yfirst, bias, skip, sy, sx, slope=0.2):
+    """Sub-pixel consumer for a 2n+1 target along one axis (see upsample.cu): y4 (N,4Ca,hp,wp), yfirst (N,2Ca,h,1) [sx] or
+    (N,2Ca,1,w) [sy] -> (N, Ca [+ Cb], 2hp-sy, 2wp-sx) channels_last with ``skip`` concatenated (a placed skip is not copied)."""
+    _need_cuda(y4, yfirst, bias, skip)
+    N, C4, hp, wp = y4.shape
+    Ca = C4 // 4
+    H, W = 2 * hp - sy, 2 * wp - sx
+    for t in (y4, yfirst):
+        if not (t.dtype == torch.float32 and t.is_contiguous(memory_format=torch.channels_last)):
+            raise _lib.RidersError("d2s_shift needs channels_last float32 maps")
+    parent = placed_parent(skip, Ca) if skip is not None else None
+    if skip is not None and (tuple(skip.shape[2:]) != (H, W) or skip.shape[0] != N):
+        raise ValueError("skip must be (N, Cb, %d, %d)" % (H, W))
+    if parent is None:
+        Cb = skip.shape[1] if skip is not None else 0
+        parent = torch.empty((N, H, W, Ca + Cb), device=y4.device, dtype=torch.float32).permute(0, 3, 1, 2)
+        if skip is not None:
+            parent[:, Ca:] = skip
+    b = _f32c(bias) if bias is not None else None
+    with _span("d2s_bias_act_concat", (y4.numel() + N * H * W * Ca) * 4):
+        rc = _lib.lib().riders_d2s_shift_bias_act_place_nhwc(_ptr(y4), _ptr(yfirst), _ptr(b), Ca, N, hp, wp, int(sy), int(sx),
+                                                             float(slope), _ptr(parent), parent.shape[1], _stream())
+    _lib.check(rc, "riders_d2s_shift_bias_act_place_nhwc")
+    return parent
+
+
 _HOST_CACHE = {}
 
 

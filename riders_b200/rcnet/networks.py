@@ -159,7 +159,7 @@ class DecoderBlock(torch.nn.Module):
         if deconv_type != 'up':
             raise ValueError("only deconv_type='up' is used by RC-Net (rcnet_model.py:94)")
         self.skip_channels = cskip
-        self._w4 = None                            # sub-pixel weights, built by fold_upsample_()
+        self._w4 = self._wcol = self._wrow = None   # sub-pixel weights, built by fold_upsample_()
         self._leaky = act is not None and 'leaky_relu' in act
         self.deconv = UpConv2d(cin, cout, init, act, use_batch_norm)
         self.conv = Conv2d(cskip + cout, cout, 3, 1, init, act, use_batch_norm)
@@ -176,6 +176,11 @@ class DecoderBlock(torch.nn.Module):
              torch.tensor([[0., 0., 0.], [1., 1., 0.], [0., 0., 1.]], device=w.device, dtype=w.dtype)]
         w4 = torch.cat([torch.einsum('sk,oikl,tl->oist', t[a], w, t[b]) for a in (0, 1) for b in (0, 1)], dim=0)
         self._w4 = w4.contiguous(memory_format=torch.channels_last)
+        # 2n+1 targets (torch nearest picks source max(j-1, 0) >> 1, see upsample.cu): the first output column (row) sees the
+        # zero padding on its left (top), so its kx (ky) in {1, 2} taps are pre-summed into a 3x1 (1x3) phase kernel
+        wc, wr = w[:, :, :, 1] + w[:, :, :, 2], w[:, :, 1, :] + w[:, :, 2, :]
+        self._wcol = torch.cat([torch.einsum('sk,oik->ois', t[a], wc) for a in (0, 1)], dim=0).unsqueeze(-1).contiguous()
+        self._wrow = torch.cat([torch.einsum('tl,oil->oit', t[b], wr) for b in (0, 1)], dim=0).unsqueeze(2).contiguous()
         return self
 
     def forward(self, x, skip=None, shape=None, raw=False):
@@ -194,6 +199,20 @@ class DecoderBlock(torch.nn.Module):
             # then depth-to-space + bias + LeakyReLU (+ skip concat) in one pass
             y4 = F.conv2d(x, self._w4, None, 1, 1)
             z = ops.d2s_bias_act_concat(y4, up.conv.bias, skip if self.skip_channels > 0 else None, _LEAK)
+            return self.conv.raw(z) if raw else self.conv(z)
+        sy, sx = int(shape[0] == 2 * x.shape[2] + 1), int(shape[1] == 2 * x.shape[3] + 1)
+        if (self._w4 is not None and sy + sx == 1 and shape[0] == 2 * x.shape[2] + sy and shape[1] == 2 * x.shape[3] + sx
+                and up.fast_ok(x) and x.shape[2] > 1 and x.shape[3] > 1 and (skip is None or (skip_cl and skip.shape[1] % 4 == 0))):
+            # 2n+1 along one axis: the same sub-pixel convolution on x replicate-padded by one, read one pixel further, plus a
+            # 3x1 / 1x3 phase convolution of the first column / row (the resized map never exists here either)
+            xp = F.pad(x, (sx, 0, sy, 0), mode='replicate').contiguous(memory_format=torch.channels_last)
+            y4 = F.conv2d(xp, self._w4, None, 1, 1)
+            if sx:
+                yfirst = F.conv2d(x[:, :, :, 0:1].contiguous(memory_format=torch.channels_last), self._wcol, None, 1, (1, 0))
+            else:
+                yfirst = F.conv2d(x[:, :, 0:1, :].contiguous(memory_format=torch.channels_last), self._wrow, None, 1, (0, 1))
+            yfirst = yfirst.contiguous(memory_format=torch.channels_last)
+            z = ops.d2s_shift_bias_act_concat(y4, yfirst, up.conv.bias, skip if self.skip_channels > 0 else None, sy, sx, _LEAK)
             return self.conv.raw(z) if raw else self.conv(z)
         if raw:
             return self.conv.raw(self.deconv(x, shape=shape))

@@ -626,6 +626,40 @@ def test_subpixel_decoder_block_equals_resize_then_conv():
     np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("hw,target", [((30, 12), (60, 25)), ((7, 3), (15, 6)), ((5, 4), (10, 9))])
+@pytest.mark.parametrize("placed", [False, True])
+def test_subpixel_decoder_block_odd_targets(hw, target, placed, monkeypatch):
+    """DecoderBlock fast path for 2n+1 targets along one axis (RC-Net: 30x12 -> 60x25, 7x3 -> 15x6): the shifted sub-pixel
+    convolution + first-column / first-row phase convolution == F.interpolate(nearest) + 3x3 convolution (fp32 rounding only),
+    and the resized map is never produced."""
+    from riders_b200.rcnet import networks
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(7)
+    blk = networks.DecoderBlock(32, 16, 24, 'kaiming_uniform', 'leaky_relu', True).to(DEV).eval()
+    with torch.no_grad():
+        for m in blk.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.uniform_(-0.3, 0.3); m.running_var.uniform_(0.5, 1.5); m.weight.uniform_(0.7, 1.3); m.bias.uniform_(-0.2, 0.2)
+    x = torch.randn((3, 32) + hw, device=DEV).contiguous(memory_format=torch.channels_last)
+    skip = torch.randn((3, 16) + target, device=DEV).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        ref = blk(x, skip)
+        for m in blk.modules():
+            if isinstance(m, networks.Conv2d):
+                m.fold_batch_norm_()
+        blk.to(memory_format=torch.channels_last)
+        blk.fold_upsample_()
+        if placed:
+            view = ops.placed_skip_buffers(3, [24], [16], [target], x.device)[0]
+            view.copy_(skip)
+            skip = view
+        def no_resize(*a, **k):
+            raise AssertionError("the resized map must not be materialised on this path")
+        monkeypatch.setattr(ops, "upsample_nearest", no_resize)
+        got = blk(x, skip)
+    np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
 # ------------------------------------------------------------------------------------ config 4: training step
 def test_training_step_gradients_match_the_reference_path():
     """rcnet_main.train's inner step (forward with logits, masked BCE, backward) through the mirror on the GPU
