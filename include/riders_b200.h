@@ -286,6 +286,18 @@ int riders_d2s_bias_act_place_nhwc(const float* y4, const float* bias, int Ca, c
 int riders_d2s_shift_bias_act_place_nhwc(const float* y4, const float* yfirst, const float* bias, int Ca,
                                          int N, int hp, int wp, int sy, int sx, float slope,
                                          float* out, int out_pixel_stride, void* stream);
+/* The two consumers above for either form of the phase convolution.  taps = 3: y4 from the 3x3 phase kernels, (N,4*Ca,h,w)
+ * [shift: (N,4*Ca,hp,wp)].  taps = 2: y4 from the equivalent 2x2 phase kernels with padding 1 (4/9 of the multiply-adds:
+ * rows [W0, W1+W2] / [W0+W1, W2]), (N,4*Ca,h+1,w+1) [shift: (N,4*Ca,hp+1,wp+1)], phase (a,b) of pixel (i,j) at (i+a, j+b). */
+int riders_subpixel_d2s_place_nhwc(const float* y4, int taps, const float* bias, int Ca, const float* skip, int Cb,
+                                   int N, int h, int w, float slope, float* out, int out_pixel_stride, void* stream);
+int riders_subpixel_d2s_shift_place_nhwc(const float* y4, int taps, const float* yfirst, const float* bias, int Ca,
+                                         int N, int hp, int wp, int sy, int sx, float slope,
+                                         float* out, int out_pixel_stride, void* stream);
+/* out (N, C, h+sy, w+sx) channels-last = act(x + bias) replicate-padded by one column on the left (sx = 1) / one row on top
+ * (sy = 1): the operand of the 2n+1 sub-pixel block, written by the pass that applies bias + LeakyReLU anyway.  Out of place. */
+int riders_bias_act_pad_nhwc(const float* x, const float* bias, int C, int N, int h, int w, int sy, int sx,
+                             float slope, float* out, void* stream);
 /* Decoder head in front of riders_confidence_reduce: logits (N,H,W) = conv3x3(act(x + bias)), zero padding,
  * x (N,H,W,C=16) channels-last RAW output of the last decoder convolution, weight_host (1,C,3,3) and
  * bias_host (C, or NULL) in HOST memory (they become kernel parameters).  MultiScaleDecoder.output0,

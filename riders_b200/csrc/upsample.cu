@@ -217,8 +217,10 @@ namespace riders {
 
 __global__ void __launch_bounds__(256)
 d2s_bias_act_concat_kernel(const float4* __restrict__ y4, const float* __restrict__ bias, const float4* __restrict__ skip,
-                           float4* __restrict__ out, int Ca4, int Cb4, int ld4, int ct_shift, int h, int w, float slope,
+                           float4* __restrict__ out, int Ca4, int Cb4, int ld4, int ct_shift, int h, int w, int t, float slope,
                            long long rows, int rows_per_block) {
+    // t = 0: y4 is (N, h, w, 4*Ca) from the 3x3 phase kernels; t = 1: (N, h+1, w+1, 4*Ca) from the 2x2 phase kernels with
+    // padding 1, where phase (a, b) of low-resolution pixel (i, j) sits at (i + a, j + b)
     // a block streams `rows_per_block` consecutive output rows as one flat run of float4s: (row, position) advance
     // incrementally, the channel split uses a shift when Ct4 is a power of two (RC-Net: 4, 16, 64)
     const int Ct4 = Ca4 + Cb4, W2 = 2 * w, H2 = 2 * h;
@@ -243,7 +245,8 @@ d2s_bias_act_concat_kernel(const float4* __restrict__ y4, const float* __restric
                 const int c = pos - X * Ct4;
                 act[u] = c < Ca4;
                 cc[u] = c;
-                v[u] = act[u] ? __ldcs(y4 + (((size_t)n * h + (Y >> 1)) * (size_t)w + (X >> 1)) * (4 * Ca4) + (2 * (Y & 1) + (X & 1)) * Ca4 + c)
+                v[u] = act[u] ? __ldcs(y4 + (((size_t)n * (h + t) + (Y >> 1) + (Y & 1) * t) * (size_t)(w + t) + (X >> 1) + (X & 1) * t) * (4 * Ca4)
+                                          + (2 * (Y & 1) + (X & 1)) * Ca4 + c)
                               : __ldcs(skip + ((size_t)row * W2 + X) * Cb4 + (c - Ca4));
                 dstp[u] = out + ((size_t)row * W2 + X) * ld4 + c;      // ld4 == Ct4: dense; larger: the skip channels are already in place
                 pos += 256;
@@ -276,7 +279,13 @@ extern "C" int riders_d2s_bias_act_concat_nhwc(const float* y4, const float* bia
 
 extern "C" int riders_d2s_bias_act_place_nhwc(const float* y4, const float* bias, int Ca, const float* skip, int Cb,
                                               int N, int h, int w, float slope, float* out, int out_pixel_stride, void* stream) {
+    return riders_subpixel_d2s_place_nhwc(y4, 3, bias, Ca, skip, Cb, N, h, w, slope, out, out_pixel_stride, stream);
+}
+
+extern "C" int riders_subpixel_d2s_place_nhwc(const float* y4, int taps, const float* bias, int Ca, const float* skip, int Cb,
+                                              int N, int h, int w, float slope, float* out, int out_pixel_stride, void* stream) {
     using namespace riders;
+    RIDERS_REQUIRE(taps == 2 || taps == 3, "subpixel_d2s: taps must be 2 or 3 (got %d)", taps);
     RIDERS_REQUIRE(out_pixel_stride >= Ca + Cb && (out_pixel_stride & 3) == 0, "d2s_bias_act_place: out_pixel_stride=%d < %d channels or not %%4", out_pixel_stride, Ca + Cb);
     RIDERS_REQUIRE(N >= 0 && Ca > 0 && Cb >= 0 && h > 0 && w > 0, "d2s_bias_act_concat: bad shape");
     RIDERS_REQUIRE((Ca & 3) == 0 && (Cb & 3) == 0, "d2s_bias_act_concat: channel counts must be multiples of 4 (%d, %d)", Ca, Cb);
@@ -293,7 +302,7 @@ extern "C" int riders_d2s_bias_act_place_nhwc(const float* y4, const float* bias
     count_launches(1);
     d2s_bias_act_concat_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(y4), bias, reinterpret_cast<const float4*>(skip), reinterpret_cast<float4*>(out),
-        Ca / 4, Cb / 4, out_pixel_stride / 4, ct_shift, h, w, slope, rows, rows_per_block);
+        Ca / 4, Cb / 4, out_pixel_stride / 4, ct_shift, h, w, taps == 2 ? 1 : 0, slope, rows, rows_per_block);
     return check_launch("d2s_bias_act_concat_nhwc");
 }
 
@@ -313,7 +322,7 @@ namespace riders {
 
 __global__ void __launch_bounds__(256)
 d2s_shift_bias_act_kernel(const float4* __restrict__ y4, const float4* __restrict__ yfirst, const float* __restrict__ bias,
-                          float4* __restrict__ out, int Ca4, int ld4, int hp, int wp, int sy, int sx, float slope,
+                          float4* __restrict__ out, int Ca4, int ld4, int hp, int wp, int sy, int sx, int tp, float slope,
                           long long total) {
     const int H = 2 * hp - sy, W = 2 * wp - sx;
     for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
@@ -329,7 +338,8 @@ d2s_shift_bias_act_kernel(const float4* __restrict__ y4, const float4* __restric
             v = __ldcs(yfirst + (n * (wp - sx) + (X >> 1)) * (2 * Ca4) + (X & 1) * Ca4 + c);
         } else {
             const int ky = Y + sy, kx = X + sx;
-            v = __ldcs(y4 + ((n * hp + (ky >> 1)) * (long long)wp + (kx >> 1)) * (4 * Ca4) + (2 * (ky & 1) + (kx & 1)) * Ca4 + c);
+            v = __ldcs(y4 + ((n * (hp + tp) + (ky >> 1) + (ky & 1) * tp) * (long long)(wp + tp) + (kx >> 1) + (kx & 1) * tp) * (4 * Ca4)
+                       + (2 * (ky & 1) + (kx & 1)) * Ca4 + c);
         }
         if (bias) {
             const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + c);
@@ -346,7 +356,14 @@ d2s_shift_bias_act_kernel(const float4* __restrict__ y4, const float4* __restric
 extern "C" int riders_d2s_shift_bias_act_place_nhwc(const float* y4, const float* yfirst, const float* bias, int Ca,
                                                     int N, int hp, int wp, int sy, int sx, float slope,
                                                     float* out, int out_pixel_stride, void* stream) {
+    return riders_subpixel_d2s_shift_place_nhwc(y4, 3, yfirst, bias, Ca, N, hp, wp, sy, sx, slope, out, out_pixel_stride, stream);
+}
+
+extern "C" int riders_subpixel_d2s_shift_place_nhwc(const float* y4, int taps, const float* yfirst, const float* bias, int Ca,
+                                                    int N, int hp, int wp, int sy, int sx, float slope,
+                                                    float* out, int out_pixel_stride, void* stream) {
     using namespace riders;
+    RIDERS_REQUIRE(taps == 2 || taps == 3, "subpixel_d2s_shift: taps must be 2 or 3 (got %d)", taps);
     RIDERS_REQUIRE(N >= 0 && Ca > 0 && (Ca & 3) == 0 && hp > 1 && wp > 1, "d2s_shift: bad shape");
     RIDERS_REQUIRE((sy == 0 || sy == 1) && (sx == 0 || sx == 1) && sy + sx == 1, "d2s_shift: exactly one of sy, sx must be 1");
     RIDERS_REQUIRE(out_pixel_stride >= Ca && (out_pixel_stride & 3) == 0, "d2s_shift: out_pixel_stride=%d < %d channels or not %%4", out_pixel_stride, Ca);
@@ -360,6 +377,56 @@ extern "C" int riders_d2s_shift_bias_act_place_nhwc(const float* y4, const float
     count_launches(1);
     d2s_shift_bias_act_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(y4), reinterpret_cast<const float4*>(yfirst), bias, reinterpret_cast<float4*>(out),
-        Ca / 4, out_pixel_stride / 4, hp, wp, sy, sx, slope, total);
+        Ca / 4, out_pixel_stride / 4, hp, wp, sy, sx, taps == 2 ? 1 : 0, slope, total);
     return check_launch("d2s_shift_bias_act_place_nhwc");
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// act(x + bias) written into a map that is replicate-padded by one column on the left (sx) or one row on top (sy): the
+// operand x' of the 2n+1 sub-pixel block above, produced by the pass that applies the previous convolution's bias and
+// LeakyReLU anyway (instead of F.pad + a layout copy of the activated map: two more passes over it).
+//   x (N, h, w, C) channels-last raw convolution output -> out (N, h + sy, w + sx, C); out[:, sy:, sx:] is act(x + bias).
+// ---------------------------------------------------------------------------------------------
+namespace riders {
+
+__global__ void __launch_bounds__(256)
+bias_act_pad_nhwc_kernel(const float4* __restrict__ x, const float* __restrict__ bias, float4* __restrict__ out,
+                         int C4, int h, int w, int sy, int sx, float slope, long long total) {
+    const int H = h + sy, W = w + sx;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const int c = (int)(e % C4);
+        long long t = e / C4;
+        const int X = (int)(t % W); t /= W;
+        const int Y = (int)(t % H);
+        const long long n = t / H;
+        float4 v = __ldg(x + ((n * h + max(Y - sy, 0)) * (long long)w + max(X - sx, 0)) * C4 + c);
+        if (bias) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + c);
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+        }
+        v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+        v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+        out[e] = v;
+    }
+}
+
+}  // namespace riders
+
+extern "C" int riders_bias_act_pad_nhwc(const float* x, const float* bias, int C, int N, int h, int w, int sy, int sx,
+                                        float slope, float* out, void* stream) {
+    using namespace riders;
+    RIDERS_REQUIRE(N >= 0 && C > 0 && (C & 3) == 0 && h > 0 && w > 0, "bias_act_pad: bad shape");
+    RIDERS_REQUIRE((sy == 0 || sy == 1) && (sx == 0 || sx == 1), "bias_act_pad: sy, sx must be 0 or 1");
+    if (N == 0) return RIDERS_OK;
+    RIDERS_REQUIRE(x && out && x != out, "bias_act_pad: null pointer or in-place call");
+    RIDERS_REQUIRE(((((uintptr_t)x) | ((uintptr_t)out) | ((uintptr_t)bias)) & 15) == 0, "bias_act_pad: 16-byte alignment");
+    const long long total = (long long)N * (h + sy) * (w + sx) * (C / 4);
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    count_launches(1);
+    bias_act_pad_nhwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(x), bias, reinterpret_cast<float4*>(out), C / 4, h, w, sy, sx, slope, total);
+    return check_launch("bias_act_pad_nhwc");
 }

@@ -277,48 +277,67 @@ def bias_act_(x, bias, slope):
     return x
 
 
-def d2s_bias_act_concat(y4, bias, skip, slope=0.2):
-    """Depth-to-space (2x2, phase-major channels) + bias + LeakyReLU (+ concat of ``skip``) in one pass.
-    y4 (N, 4*Ca, h, w) channels_last -> (N, Ca [+ Cb], 2h, 2w) channels_last.  A ``skip`` that already sits behind
-    Ca free channels of a wider buffer (``placed_skip_buffers``) is not copied: only the Ca channels are written."""
-    _need_cuda(y4, bias, skip)
-    N, C4, h, w = y4.shape
-    Ca = C4 // 4
-    parent = placed_parent(skip, Ca)
-    if parent is not None:
-        if not (_is_channels_last(y4) and y4.dtype == torch.float32 and Ca % 4 == 0) or tuple(skip.shape[2:]) != (2 * h, 2 * w) \
-                or skip.shape[0] != N:
-            raise _lib.RidersError("d2s_bias_act_concat (placed skip): shape / layout mismatch")
-        b = _f32c(bias) if bias is not None else None
-        with _span("d2s_bias_act_concat", 2 * y4.numel() * 4):
-            rc = _lib.lib().riders_d2s_bias_act_place_nhwc(_ptr(y4), _ptr(b), Ca, None, 0, N, h, w, float(slope),
-                                                           _ptr(parent), parent.shape[1], _stream())
-        _lib.check(rc, "riders_d2s_bias_act_place_nhwc")
-        return parent
-    Cb = skip.shape[1] if skip is not None else 0
-    for t in (y4, skip):
-        if t is not None and not (_is_channels_last(t) and t.dtype == torch.float32 and t.shape[1] % 4 == 0):
-            raise _lib.RidersError("d2s_bias_act_concat needs channels_last float32 maps with C % 4 == 0")
-    if skip is not None and tuple(skip.shape[2:]) != (2 * h, 2 * w):
-        raise ValueError("skip must be (N, Cb, 2h, 2w)")
-    out = torch.empty((N, Ca + Cb, 2 * h, 2 * w), device=y4.device, dtype=torch.float32, memory_format=torch.channels_last)
+def bias_act_pad(x, bias, slope, sy, sx):
+    """act(x + bias[c]) written into a fresh map replicate-padded by one row on top (sy) / one column on the left (sx):
+    (N, C, h, w) channels_last raw convolution output -> (N, C, h+sy, w+sx) channels_last; ``out[:, :, sy:, sx:]`` is the
+    activated map itself.  Same bytes as ``bias_act_`` plus the duplicated row / column."""
+    _need_cuda(x, bias)
+    N, Cc, h, w = x.shape
+    if not (x.dtype == torch.float32 and _is_channels_last(x) and Cc % 4 == 0):
+        raise _lib.RidersError("bias_act_pad needs a channels_last float32 map with C % 4 == 0")
+    out = torch.empty((N, Cc, h + sy, w + sx), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
     b = _f32c(bias) if bias is not None else None
-    with _span("d2s_bias_act_concat", (y4.numel() + (skip.numel() if skip is not None else 0) + out.numel()) * 4):
-        rc = _lib.lib().riders_d2s_bias_act_concat_nhwc(_ptr(y4), _ptr(b), Ca, _ptr(skip), Cb, N, h, w, float(slope),
-                                                        _ptr(out), _stream())
-    _lib.check(rc, "riders_d2s_bias_act_concat_nhwc")
+    with _span("bias_act", (x.numel() + out.numel()) * 4):
+        rc = _lib.lib().riders_bias_act_pad_nhwc(_ptr(x), _ptr(b), Cc, N, h, w, int(sy), int(sx), float(slope), _ptr(out), _stream())
+    _lib.check(rc, "riders_bias_act_pad_nhwc")
     return out
 
 
-def d2s_shift_bias_act_concat(y4, yfirst, bias, skip, sy, sx, slope=0.2):
-    """Sub-pixel consumer for a 2n+1 target along one axis (see upsample.cu): y4 (N,4Ca,hp,wp), yfirst (N,2Ca,h,1) [sx] or
-    (N,2Ca,1,w) [sy] -> (N, Ca [+ Cb], 2hp-sy, 2wp-sx) channels_last with ``skip`` concatenated (a placed skip is not copied)."""
+def d2s_bias_act_concat(y4, bias, skip, slope=0.2, taps=3):
+    """Depth-to-space (2x2, phase-major channels) + bias + LeakyReLU (+ concat of ``skip``) in one pass.
+    y4 (N, 4*Ca, h, w) channels_last [``taps=2``: (N, 4*Ca, h+1, w+1), the 2x2 phase kernels with padding 1]
+    -> (N, Ca [+ Cb], 2h, 2w) channels_last.  A ``skip`` that already sits behind Ca free channels of a wider buffer
+    (``placed_skip_buffers``) is not copied: only the Ca channels are written."""
+    _need_cuda(y4, bias, skip)
+    t = 1 if taps == 2 else 0
+    N, C4 = y4.shape[:2]
+    h, w = y4.shape[2] - t, y4.shape[3] - t
+    Ca = C4 // 4
+    if not (_is_channels_last(y4) and y4.dtype == torch.float32 and Ca % 4 == 0 and h > 0 and w > 0):
+        raise _lib.RidersError("d2s_bias_act_concat needs a channels_last float32 y4 with Ca % 4 == 0")
+    if skip is not None and (tuple(skip.shape[2:]) != (2 * h, 2 * w) or skip.shape[0] != N):
+        raise ValueError("skip must be (N, Cb, 2h, 2w)")
+    b = _f32c(bias) if bias is not None else None
+    parent = placed_parent(skip, Ca)
+    if parent is not None:
+        with _span("d2s_bias_act_concat", (y4.numel() + N * 4 * h * w * Ca) * 4):
+            rc = _lib.lib().riders_subpixel_d2s_place_nhwc(_ptr(y4), int(taps), _ptr(b), Ca, None, 0, N, h, w, float(slope),
+                                                           _ptr(parent), parent.shape[1], _stream())
+        _lib.check(rc, "riders_subpixel_d2s_place_nhwc")
+        return parent
+    Cb = skip.shape[1] if skip is not None else 0
+    if skip is not None and not (_is_channels_last(skip) and skip.dtype == torch.float32 and Cb % 4 == 0):
+        raise _lib.RidersError("d2s_bias_act_concat needs channels_last float32 maps with C % 4 == 0")
+    out = torch.empty((N, Ca + Cb, 2 * h, 2 * w), device=y4.device, dtype=torch.float32, memory_format=torch.channels_last)
+    with _span("d2s_bias_act_concat", (y4.numel() + (skip.numel() if skip is not None else 0) + out.numel()) * 4):
+        rc = _lib.lib().riders_subpixel_d2s_place_nhwc(_ptr(y4), int(taps), _ptr(b), Ca, _ptr(skip), Cb, N, h, w, float(slope),
+                                                       _ptr(out), Ca + Cb, _stream())
+    _lib.check(rc, "riders_subpixel_d2s_place_nhwc")
+    return out
+
+
+def d2s_shift_bias_act_concat(y4, yfirst, bias, skip, sy, sx, slope=0.2, taps=3):
+    """Sub-pixel consumer for a 2n+1 target along one axis (see upsample.cu): y4 (N,4Ca,hp,wp) [``taps=2``: (N,4Ca,hp+1,wp+1)],
+    yfirst (N,2Ca,h,1) [sx] or (N,2Ca,1,w) [sy] -> (N, Ca [+ Cb], 2hp-sy, 2wp-sx) channels_last with ``skip`` concatenated
+    (a placed skip is not copied)."""
     _need_cuda(y4, yfirst, bias, skip)
-    N, C4, hp, wp = y4.shape
+    t = 1 if taps == 2 else 0
+    N, C4 = y4.shape[:2]
+    hp, wp = y4.shape[2] - t, y4.shape[3] - t
     Ca = C4 // 4
     H, W = 2 * hp - sy, 2 * wp - sx
-    for t in (y4, yfirst):
-        if not (t.dtype == torch.float32 and t.is_contiguous(memory_format=torch.channels_last)):
+    for m in (y4, yfirst):
+        if not (m.dtype == torch.float32 and m.is_contiguous(memory_format=torch.channels_last)):
             raise _lib.RidersError("d2s_shift needs channels_last float32 maps")
     parent = placed_parent(skip, Ca) if skip is not None else None
     if skip is not None and (tuple(skip.shape[2:]) != (H, W) or skip.shape[0] != N):
@@ -330,9 +349,9 @@ def d2s_shift_bias_act_concat(y4, yfirst, bias, skip, sy, sx, slope=0.2):
             parent[:, Ca:] = skip
     b = _f32c(bias) if bias is not None else None
     with _span("d2s_bias_act_concat", (y4.numel() + N * H * W * Ca) * 4):
-        rc = _lib.lib().riders_d2s_shift_bias_act_place_nhwc(_ptr(y4), _ptr(yfirst), _ptr(b), Ca, N, hp, wp, int(sy), int(sx),
+        rc = _lib.lib().riders_subpixel_d2s_shift_place_nhwc(_ptr(y4), int(taps), _ptr(yfirst), _ptr(b), Ca, N, hp, wp, int(sy), int(sx),
                                                              float(slope), _ptr(parent), parent.shape[1], _stream())
-    _lib.check(rc, "riders_d2s_shift_bias_act_place_nhwc")
+    _lib.check(rc, "riders_subpixel_d2s_shift_place_nhwc")
     return parent
 
 

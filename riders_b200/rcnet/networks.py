@@ -17,6 +17,8 @@ What is NOT torch here is the hot path inside ``RCNetEncoder.forward``: the five
 sm_100a gather kernel, and the LoFTR transformer (networks.py:444) runs through
 the fused layer kernels.  There is no CPU fallback for those two.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -24,6 +26,9 @@ from .linear_attention import LocalFeatureTransformer
 from .. import ops
 
 _LEAK = 0.20   # utils/net_utils.py:15  LeakyReLU(negative_slope=0.20)
+# form of the sub-pixel phase convolution of the exact-2x / 2n+1 decoder blocks (DecoderBlock.fold_upsample_): 3 = 3x3 phase
+# kernels with their zero taps, 2 = 2x2 phase kernels (same sums, 4/9 of the multiply-adds)
+SUBPIXEL_TAPS = int(os.environ.get('RIDERS_SUBPIXEL_TAPS', '2'))
 
 
 def _init_weight(weight, how):
@@ -83,6 +88,14 @@ class Conv2d(torch.nn.Module):
         if self.use_batch_norm:
             y = self.batch_norm(y)
         return y if self._act is None else self._act(y)
+
+    def forward_padded(self, x, sy, sx):
+        """Inference fast path only (needs ``fast_ok(x)``): act(conv(x) + bias) replicate-padded by one row on top (sy) /
+        one column on the left (sx), written by the bias + activation pass itself.  Returns the padded map; the
+        activated map is ``out[:, :, sy:, sx:]``."""
+        c = self.conv
+        y = F.conv2d(x, c.weight, None, c.stride, c.padding, c.dilation, c.groups)
+        return ops.bias_act_pad(y, c.bias, self._fused_slope, sy, sx)
 
     def fast_ok(self, x):
         return (self._fused_slope is not None and x.is_cuda and not torch.is_grad_enabled() and x.dtype == torch.float32
@@ -159,7 +172,8 @@ class DecoderBlock(torch.nn.Module):
         if deconv_type != 'up':
             raise ValueError("only deconv_type='up' is used by RC-Net (rcnet_model.py:94)")
         self.skip_channels = cskip
-        self._w4 = self._wcol = self._wrow = None   # sub-pixel weights, built by fold_upsample_()
+        self._w4 = self._w2 = self._wcol = self._wrow = None   # sub-pixel weights, built by fold_upsample_()
+        self.subpixel_taps = SUBPIXEL_TAPS          # 3: 3x3 phase kernels; 2: the equivalent 2x2 phase kernels (4/9 of the MACs)
         self._leaky = act is not None and 'leaky_relu' in act
         self.deconv = UpConv2d(cin, cout, init, act, use_batch_norm)
         self.conv = Conv2d(cskip + cout, cout, 3, 1, init, act, use_batch_norm)
@@ -176,6 +190,12 @@ class DecoderBlock(torch.nn.Module):
              torch.tensor([[0., 0., 0.], [1., 1., 0.], [0., 0., 1.]], device=w.device, dtype=w.dtype)]
         w4 = torch.cat([torch.einsum('sk,oikl,tl->oist', t[a], w, t[b]) for a in (0, 1) for b in (0, 1)], dim=0)
         self._w4 = w4.contiguous(memory_format=torch.channels_last)
+        # the zero taps dropped: phase a reads rows {i-1+a, i+a} with [W0, W1+W2] (a = 0) / [W0+W1, W2] (a = 1); as ONE 2x2
+        # convolution with padding 1 the phase (a, b) of pixel (i, j) is output pixel (i+a, j+b) of an (h+1, w+1) map
+        t2 = [torch.tensor([[1., 0., 0.], [0., 1., 1.]], device=w.device, dtype=w.dtype),
+              torch.tensor([[1., 1., 0.], [0., 0., 1.]], device=w.device, dtype=w.dtype)]
+        w2 = torch.cat([torch.einsum('sk,oikl,tl->oist', t2[a], w, t2[b]) for a in (0, 1) for b in (0, 1)], dim=0)
+        self._w2 = w2.contiguous(memory_format=torch.channels_last)
         # 2n+1 targets (torch nearest picks source max(j-1, 0) >> 1, see upsample.cu): the first output column (row) sees the
         # zero padding on its left (top), so its kx (ky) in {1, 2} taps are pre-summed into a 3x1 (1x3) phase kernel
         wc, wr = w[:, :, :, 1] + w[:, :, :, 2], w[:, :, 1, :] + w[:, :, 2, :]
@@ -183,37 +203,54 @@ class DecoderBlock(torch.nn.Module):
         self._wrow = torch.cat([torch.einsum('tl,oil->oit', t[b], wr) for b in (0, 1)], dim=0).unsqueeze(2).contiguous()
         return self
 
-    def forward(self, x, skip=None, shape=None, raw=False):
+    def _tail(self, z, raw, pad_out):
+        if raw:
+            return self.conv.raw(z)
+        if pad_out is not None and self.conv.fast_ok(z) and self.conv.conv.out_channels % 4 == 0:
+            yp = self.conv.forward_padded(z, pad_out[0], pad_out[1])
+            return yp[:, :, pad_out[0]:, pad_out[1]:], yp
+        return self.conv(z)
+
+    def forward(self, x, skip=None, shape=None, raw=False, xp=None, pad_out=None):
         """``raw=True`` (inference fast path only): return (conv output without bias/activation, bias, slope)
-        of the block's last convolution so that the decoder head can fuse them."""
+        of the block's last convolution so that the decoder head can fuse them.
+        ``pad_out=(sy, sx)`` (fast path only, ignored otherwise): the NEXT block's target is 2n+1 along one axis, so return
+        ``(y, y_padded)`` with ``y = y_padded[:, :, sy:, sx:]``; ``xp``: that padded map handed to the next block."""
         if skip is not None:
             shape = skip.shape[2:4]
         elif shape is None:
             shape = (2 * x.shape[2], 2 * x.shape[3])
         up = self.deconv.conv
+        taps = 2 if (self.subpixel_taps == 2 and self._w2 is not None) else 3
+        wsub = self._w2 if taps == 2 else self._w4
         # a skip gathered straight into this block's concat buffer (ops.placed_skip_buffers) counts as channels-last
         skip_cl = skip is not None and (ops._is_channels_last(skip) or ops.placed_parent(skip, up.conv.out_channels) is not None)
         if (self._w4 is not None and tuple(shape) == (2 * x.shape[2], 2 * x.shape[3]) and up.fast_ok(x)
                 and (skip is None or (skip_cl and skip.shape[1] % 4 == 0))):
             # exact 2x block: sub-pixel convolution on the low-resolution map (the resized map never exists),
             # then depth-to-space + bias + LeakyReLU (+ skip concat) in one pass
-            y4 = F.conv2d(x, self._w4, None, 1, 1)
-            z = ops.d2s_bias_act_concat(y4, up.conv.bias, skip if self.skip_channels > 0 else None, _LEAK)
-            return self.conv.raw(z) if raw else self.conv(z)
+            y4 = F.conv2d(x, wsub, None, 1, 1)
+            z = ops.d2s_bias_act_concat(y4, up.conv.bias, skip if self.skip_channels > 0 else None, _LEAK, taps=taps)
+            return self._tail(z, raw, pad_out)
         sy, sx = int(shape[0] == 2 * x.shape[2] + 1), int(shape[1] == 2 * x.shape[3] + 1)
         if (self._w4 is not None and sy + sx == 1 and shape[0] == 2 * x.shape[2] + sy and shape[1] == 2 * x.shape[3] + sx
-                and up.fast_ok(x) and x.shape[2] > 1 and x.shape[3] > 1 and (skip is None or (skip_cl and skip.shape[1] % 4 == 0))):
+                and up.fast_ok(x if xp is None else xp) and x.shape[2] > 1 and x.shape[3] > 1
+                and (skip is None or (skip_cl and skip.shape[1] % 4 == 0))):
             # 2n+1 along one axis: the same sub-pixel convolution on x replicate-padded by one, read one pixel further, plus a
             # 3x1 / 1x3 phase convolution of the first column / row (the resized map never exists here either)
-            xp = F.pad(x, (sx, 0, sy, 0), mode='replicate').contiguous(memory_format=torch.channels_last)
-            y4 = F.conv2d(xp, self._w4, None, 1, 1)
+            if xp is None or tuple(xp.shape[2:]) != (x.shape[2] + sy, x.shape[3] + sx):
+                xp = F.pad(x, (sx, 0, sy, 0), mode='replicate').contiguous(memory_format=torch.channels_last)
+            y4 = F.conv2d(xp, wsub, None, 1, 1)
             if sx:
                 yfirst = F.conv2d(x[:, :, :, 0:1].contiguous(memory_format=torch.channels_last), self._wcol, None, 1, (1, 0))
             else:
                 yfirst = F.conv2d(x[:, :, 0:1, :].contiguous(memory_format=torch.channels_last), self._wrow, None, 1, (0, 1))
             yfirst = yfirst.contiguous(memory_format=torch.channels_last)
-            z = ops.d2s_shift_bias_act_concat(y4, yfirst, up.conv.bias, skip if self.skip_channels > 0 else None, sy, sx, _LEAK)
-            return self.conv.raw(z) if raw else self.conv(z)
+            z = ops.d2s_shift_bias_act_concat(y4, yfirst, up.conv.bias, skip if self.skip_channels > 0 else None, sy, sx, _LEAK,
+                                              taps=taps)
+            return self._tail(z, raw, pad_out)
+        if xp is not None:
+            x = x.contiguous(memory_format=torch.channels_last)
         if raw:
             return self.conv.raw(self.deconv(x, shape=shape))
         if (self.skip_channels > 0 and self._leaky and not up.use_batch_norm and not torch.is_grad_enabled()
@@ -406,9 +443,20 @@ class MultiScaleDecoder(torch.nn.Module):
         head kernel write torch.sigmoid(logits), so that the reduce kernel streams confidences."""
         self.last_head_sigmoid = False
         n = len(skips) - 1
-        y = x
-        for name in self._order[:-1]:
-            y = getattr(self, name)(y, skips[n])
+        y, yp = x, None
+        for i, name in enumerate(self._order[:-1]):
+            # target of the NEXT block: when it is 2n+1 along one axis, this block's bias + activation pass writes the
+            # replicate-padded operand of that block's sub-pixel convolution directly (DecoderBlock.forward, pad_out)
+            nxt = getattr(self, self._order[i + 1])
+            tgt = skips[n - 1].shape[2:4] if n >= 1 else (tuple(shape[-2:]) if shape is not None else None)
+            cur = skips[n].shape[2:4]
+            pad_out = None
+            if tgt is not None and nxt._w4 is not None and not torch.is_grad_enabled():
+                sy, sx = int(tgt[0] == 2 * cur[0] + 1), int(tgt[1] == 2 * cur[1] + 1)
+                if sy + sx == 1 and tgt[0] == 2 * cur[0] + sy and tgt[1] == 2 * cur[1] + sx:
+                    pad_out = (sy, sx)
+            out = getattr(self, name)(y, skips[n], xp=yp, pad_out=pad_out)
+            y, yp = out if isinstance(out, tuple) else (out, None)
             n -= 1
         last = getattr(self, self._order[-1])
         head = self.output0.conv
@@ -416,11 +464,11 @@ class MultiScaleDecoder(torch.nn.Module):
                 and not self.output0.use_batch_norm and head.bias is None and head.kernel_size == (3, 3)
                 and head.out_channels == 1 and head.in_channels == 16 and head.stride == (1, 1) and head.padding == (1, 1)):
             # inference fast path: last conv raw -> [bias + LeakyReLU + 3x3 head] in one kernel -> logits
-            y_raw, bias, slope = last(y, shape=tuple(shape[-2:]), raw=True)
+            y_raw, bias, slope = last(y, shape=tuple(shape[-2:]), raw=True, xp=yp)
             if ops._is_channels_last(y_raw):
                 self.last_head_sigmoid = bool(head_sigmoid)
                 return [ops.conv3x3_head(y_raw, bias, slope, head.weight, sigmoid=head_sigmoid)]
             y = ops.bias_act_(y_raw, bias, slope) if bias is not None or slope != 1.0 else y_raw
             return [self.output0(y)]
-        y = last(y, skips[n]) if n == 0 else last(y, shape=tuple(shape[-2:]))
+        y = last(y, skips[n], xp=yp) if n == 0 else last(y, shape=tuple(shape[-2:]), xp=yp)
         return [self.output0(y)]

@@ -600,9 +600,29 @@ def test_d2s_bias_act_concat_matches_torch():
     got = ops.d2s_bias_act_concat(y4, bias, skip, 0.2)
     assert got.is_contiguous(memory_format=torch.channels_last) and torch.equal(got, ref)
     assert torch.equal(ops.d2s_bias_act_concat(y4, bias, None, 0.2), ref[:, :Ca])
+    # 2x2-tap form: phase (a, b) of pixel (i, j) sits at (i + a, j + b) of an (h+1, w+1) map
+    y2 = torch.randn((N, 4 * Ca, h + 1, w + 1), device=DEV).contiguous(memory_format=torch.channels_last)
+    ref2 = torch.empty((N, Ca, 2 * h, 2 * w), device=DEV)
+    for a in (0, 1):
+        for b in (0, 1):
+            ref2[:, :, a::2, b::2] = y2[:, (2 * a + b) * Ca:(2 * a + b + 1) * Ca, a:a + h, b:b + w]
+    ref2 = torch.cat([torch.nn.functional.leaky_relu(ref2 + bias.view(1, -1, 1, 1), 0.2), skip], dim=1)
+    assert torch.equal(ops.d2s_bias_act_concat(y2, bias, skip, 0.2, taps=2), ref2)
 
 
-def test_subpixel_decoder_block_equals_resize_then_conv():
+@pytest.mark.parametrize("sy,sx", [(0, 1), (1, 0), (0, 0)])
+def test_bias_act_pad_is_bit_exact_with_torch(sy, sx):
+    x = torch.randn((3, 32, 9, 7), device=DEV).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(32, device=DEV)
+    act = torch.nn.functional.leaky_relu(x + bias.view(1, -1, 1, 1), 0.2)
+    ref = torch.nn.functional.pad(act, (sx, 0, sy, 0), mode="replicate")
+    got = ops.bias_act_pad(x, bias, 0.2, sy, sx)
+    assert got.is_contiguous(memory_format=torch.channels_last) and torch.equal(got, ref)
+    assert torch.equal(got[:, :, sy:, sx:], act)
+
+
+@pytest.mark.parametrize("taps", [2, 3])
+def test_subpixel_decoder_block_equals_resize_then_conv(taps):
     """DecoderBlock fast path (exact 2x): sub-pixel convolution == nearest resize + 3x3 convolution (fp32 rounding only)."""
     from riders_b200.rcnet import networks
     torch.backends.cudnn.allow_tf32 = False
@@ -621,14 +641,16 @@ def test_subpixel_decoder_block_equals_resize_then_conv():
                 m.fold_batch_norm_()
         blk.to(memory_format=torch.channels_last)
         blk.fold_upsample_()
-        assert blk._w4 is not None and tuple(blk._w4.shape) == (64, 32, 3, 3)
+        assert blk._w4 is not None and tuple(blk._w4.shape) == (64, 32, 3, 3) and tuple(blk._w2.shape) == (64, 32, 2, 2)
+        blk.subpixel_taps = taps
         got = blk(x, skip)
     np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=1e-5)
 
 
 @pytest.mark.parametrize("hw,target", [((30, 12), (60, 25)), ((7, 3), (15, 6)), ((5, 4), (10, 9))])
 @pytest.mark.parametrize("placed", [False, True])
-def test_subpixel_decoder_block_odd_targets(hw, target, placed, monkeypatch):
+@pytest.mark.parametrize("taps", [2, 3])
+def test_subpixel_decoder_block_odd_targets(hw, target, placed, taps, monkeypatch):
     """DecoderBlock fast path for 2n+1 targets along one axis (RC-Net: 30x12 -> 60x25, 7x3 -> 15x6): the shifted sub-pixel
     convolution + first-column / first-row phase convolution == F.interpolate(nearest) + 3x3 convolution (fp32 rounding only),
     and the resized map is never produced."""
@@ -656,8 +678,46 @@ def test_subpixel_decoder_block_odd_targets(hw, target, placed, monkeypatch):
         def no_resize(*a, **k):
             raise AssertionError("the resized map must not be materialised on this path")
         monkeypatch.setattr(ops, "upsample_nearest", no_resize)
+        blk.subpixel_taps = taps
         got = blk(x, skip)
+        # the padded operand handed over by the previous block's bias + activation pass (MultiScaleDecoder.forward)
+        sy, sx = int(target[0] == 2 * hw[0] + 1), int(target[1] == 2 * hw[1] + 1)
+        xp = torch.nn.functional.pad(x, (sx, 0, sy, 0), mode="replicate").contiguous(memory_format=torch.channels_last)
+        got2 = blk(xp[:, :, sy:, sx:], skip, xp=xp)
     np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    assert torch.equal(got, got2)
+
+
+def test_decoder_hands_padded_maps_to_odd_blocks(monkeypatch):
+    """MultiScaleDecoder at RC-Net's sizes (7x3 -> 15x6 -> 30x12 -> 60x25 -> 120x50 -> 240x100): the block in front of the
+    60x25 one returns its output replicate-padded (bias_act_pad), nothing calls F.pad on a big map, same logits."""
+    from riders_b200.rcnet import networks
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(11)
+    dec = networks.MultiScaleDecoder(64, 1, 1, [32, 32, 16, 16, 16], [32, 32, 16, 8, 0], 'kaiming_uniform', 'leaky_relu', 'linear',
+                                     True, 'up').to(DEV).eval()
+    N = 3
+    x = torch.randn((N, 64, 7, 3), device=DEV)
+    skips = [torch.randn((N, c) + hw, device=DEV) for c, hw in ((8, (120, 50)), (16, (60, 25)), (32, (30, 12)), (32, (15, 6)))]
+    with torch.no_grad():
+        ref = dec(x, skips, shape=(240, 100))[-1]
+        for m in dec.modules():
+            if isinstance(m, networks.Conv2d):
+                m.fold_batch_norm_()
+        dec.to(memory_format=torch.channels_last)
+        for m in dec.modules():
+            if isinstance(m, networks.DecoderBlock):
+                m.fold_upsample_()
+        xc = x.contiguous(memory_format=torch.channels_last)
+        sc = [t.contiguous(memory_format=torch.channels_last) for t in skips]
+        calls = []
+        real_pad, real_bap = torch.nn.functional.pad, ops.bias_act_pad
+        monkeypatch.setattr(networks.F, "pad", lambda t, *a, **k: (calls.append(("pad", tuple(t.shape))), real_pad(t, *a, **k))[1])
+        monkeypatch.setattr(ops, "bias_act_pad", lambda t, *a, **k: (calls.append(("bap", tuple(t.shape))), real_bap(t, *a, **k))[1])
+        got = dec(xc, sc, shape=(240, 100))[-1]
+    assert ("bap", (N, 32, 30, 12)) in calls, calls
+    assert [c for c in calls if c[0] == "pad"] == [("pad", (N, 64, 7, 3))], calls          # only the tiny latent is padded by torch
+    np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=2e-4, atol=2e-5)
 
 
 # ------------------------------------------------------------------------------------ config 4: training step
