@@ -310,6 +310,20 @@ int riders_conv3x3_head_nhwc(const float* x, int N, int C, int H, int W,
 int riders_conv3x3_head_sigmoid_nhwc(const float* x, int N, int C, int H, int W,
                                      const float* bias_host, float slope, const float* weight_host,
                                      int apply_sigmoid, float* out, void* stream);
+/* Fused tail of the decoder in front of riders_confidence_reduce (TF32 path: the host selects it only where the
+ * reference flow runs the convolution in TF32 too, torch.backends.cudnn.allow_tf32):
+ *   y = act(depth_to_space(y4) + bias_a); z = act(conv3x3(y; Wb) + bias_b); out = conv3x3(z; Wh) [sigmoid]
+ * = last DecoderBlock (deconv0: up-convolution in sub-pixel form, then its 16 -> 16 convolution) + output0 of
+ * MultiScaleDecoder (RCNet/networks.py:678-779, utils/net_utils.py:474-569).  y4 (N, 64, h(+1), w(+1)) channels-last
+ * phase convolution output (taps as in riders_subpixel_d2s_place_nhwc); wb_frag: DEVICE, Wb (16,16,3,3) in
+ * mma.m16n8k8 B-fragment order [K step = (ky*3+kx)*2 + ci/8][lane][N half][2], TF32-rounded (ops.decoder_tail builds it);
+ * bias_a_host / bias_b_host (16, or NULL) and wh_host (1,16,3,3) in HOST memory; out (N, 2h, 2w).          */
+int riders_decoder_tail_nhwc(const float* y4, int taps, int N, int h, int w,
+                             const float* bias_a_host, const float* wb_frag, const float* bias_b_host,
+                             const float* wh_host, float slope, int apply_sigmoid,
+                             float* out, void* stream);
+/* issue-rate probe of mma.sync.m16n8k8.tf32 (cycles for iters x 8 MMAs per warp, per CTA) */
+int riders_debug_mma_sync_rate(int warps, int iters, int ctas, long long* device_cycles, float* device_sink, void* stream);
 /* out = act(x + bias[c]) over `pixels` channels-last pixels of C channels (in place when out == x);
  * slope 0.2 = LeakyReLU of utils/net_utils.py:15, 0 = ReLU, 1 = identity; bias may be NULL.          */
 int riders_bias_act_nhwc(const float* x, const float* bias, int C, long long pixels, float slope,

@@ -39,10 +39,10 @@ constexpr int ZH = TH + 2, ZW = TW + 2;
 constexpr int YP = 20;                               // floats per y-tile pixel
 constexpr int NZ = ZH * ZW;                          // 728 z positions
 constexpr int MT = (NZ + 15) / 16;                   // 46 M-tiles
-constexpr int UP = MT * 16 + 8;                      // u plane stride: == 8 mod 32 -> the quad's 4 taps hit distinct banks
+constexpr int UP = MT * 16 + 4;                      // u plane stride: == 4 mod 32 -> taps 2t (+1) of the 4 quad lanes hit distinct banks
 constexpr int WARPS = 6, THREADS = WARPS * 32;
 constexpr int KSTEPS = 18;                           // 9 taps x 2 halves of the 16 input channels
-constexpr int SMEM_BYTES = (YH * YW * YP + 9 * UP) * 4;      // 69120 + 26784 = 95904
+constexpr int SMEM_BYTES = (YH * YW * YP + 9 * UP) * 4;      // 69120 + 26640 = 95760
 
 struct Params {
     float bias_a[C];
@@ -53,10 +53,22 @@ struct Params {
     int t;                   // 0: y4 from the 3x3 phase kernels (h, w); 1: from the 2x2 phase kernels, (h + 1, w + 1)
 };
 
-__device__ __forceinline__ uint32_t to_tf32(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return r;
+// cvt.rna.tf32.f32 (round to nearest, ties away) for finite values in ONE integer add: the MMA ignores the low 13
+// mantissa bits, so adding half a TF32 ulp to the magnitude bits and letting the hardware truncate is the same rounding.
+// (ptxas expands the cvt itself into an |x| < inf test plus this add: ~5 instructions per value.)
+__device__ __forceinline__ uint32_t to_tf32(float v) { return __float_as_uint(v) + 0x1000u; }
+
+// 16-byte streaming load under a predicate (no branch: the loads of a batch issue back to back), zeros when off
+__device__ __forceinline__ float4 ldg128_if(const float4* p, bool on) {
+    float4 v;
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.b32 q, %5, 0;\n"
+        "mov.f32 %0, 0f00000000;\n mov.f32 %1, 0f00000000;\n mov.f32 %2, 0f00000000;\n mov.f32 %3, 0f00000000;\n"
+        "@q ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+        "}\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "r"((int)on));
+    return v;
 }
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&a)[4]) {
@@ -71,7 +83,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 }
 
 __global__ void __launch_bounds__(THREADS, 2)
-decoder_tail_kernel(const float4* __restrict__ y4, const float2* __restrict__ wb_frag, float* __restrict__ out,
+decoder_tail_kernel(const float4* __restrict__ y4, const float4* __restrict__ wb_frag, float* __restrict__ out,
                     const __grid_constant__ Params P, int h, int w, int tiles_x, int tiles_y) {
     extern __shared__ __align__(16) float smem[];
     float* ys = smem;                                 // [YH][YW][YP]
@@ -84,116 +96,169 @@ decoder_tail_kernel(const float4* __restrict__ y4, const float2* __restrict__ wb
     const int ty = tile % tiles_y;
     const long long n = tile / tiles_y;
     const int R0 = ty * TH, C0 = tx * TW;
+    const float slope = P.slope;
 
-    // Wb fragments (constant over the whole kernel): b0 = B[k = t][n = g], b1 = B[k = t + 4][n = g] per (K step, N half)
+    // ---- 1. y tile: depth-to-space + bias_a + LeakyReLU + TF32 rounding, zero outside the patch (the convolution's zero
+    //         padding applies to the ACTIVATED map).  Warp w owns tile rows w, w + 6, w + 12; a pass covers 8 pixels x 4
+    //         quarters of a row, lane = (quarter, pixel): the 8 lanes of a 128-bit store phase hit 8 pixels (80 B apart:
+    //         distinct bank groups).  Row part of the address once per row, column part once per thread (C0 and the 8-pixel
+    //         pass are even, so the column phase is fixed per lane and a pass advances 4 low-resolution pixels): every
+    //         load / store is base + immediate.  All loads are issued before the first store.
+    {
+        constexpr int PASSES = (YW + 7) / 8;                          // 7 (the last one covers 6 pixels)
+        constexpr int ROWS_PER_WARP = (YH + WARPS - 1) / WARPS;       // 3
+        static_assert((TW & 1) == 0, "column phase per lane needs an even tile origin");
+        const int q = lane >> 3, l8 = lane & 7;
+        const float4 ba = make_float4(P.bias_a[4 * q + 0], P.bias_a[4 * q + 1], P.bias_a[4 * q + 2], P.bias_a[4 * q + 3]);
+        const int hq = h + P.t, wq = w + P.t, pt = P.t;
+        const int X0 = C0 - 2 + l8;                                   // column of pass 0; X0 + 8 p for pass p
+        const int bcol = X0 & 1;
+        // float4 offset of (Y, X) = [((Y >> 1) + a pt) wq + (X >> 1) + b pt] * 16 + (2 a + b) * 4 + q
+        const float4* src = y4 + (size_t)n * hq * wq * (4 * C / 4) + q + ((X0 >> 1) + bcol * pt) * (4 * C / 4) + bcol * (C / 4);
+        float4 v[ROWS_PER_WARP][PASSES];
+        bool in[ROWS_PER_WARP][PASSES];
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_WARP; ++r) {
+            const int Y = R0 - 2 + warp + r * WARPS, a = Y & 1;
+            const bool row_ok = warp + r * WARPS < YH && (unsigned)Y < (unsigned)H;
+            const float4* rp = src + (row_ok ? (((Y >> 1) + a * pt) * wq) * (4 * C / 4) + a * (2 * C / 4) : 0);
+#pragma unroll
+            for (int p = 0; p < PASSES; ++p) {
+                in[r][p] = row_ok && (unsigned)(X0 + 8 * p) < (unsigned)W && l8 + 8 * p < YW;
+                v[r][p] = __ldcs(in[r][p] ? rp + p * 4 * (4 * C / 4) : y4);       // always a valid address: no branch
+            }
+        }
+        float* dstp = ys + ((warp * YW + l8) * YP + 4 * q);
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_WARP; ++r) {
+#pragma unroll
+            for (int p = 0; p < PASSES; ++p) {
+                float4 x = v[r][p];
+                x.x += ba.x; x.y += ba.y; x.z += ba.z; x.w += ba.w;
+                x.x = fmaxf(x.x, x.x * slope); x.y = fmaxf(x.y, x.y * slope);          // LeakyReLU, 0 <= slope <= 1
+                x.z = fmaxf(x.z, x.z * slope); x.w = fmaxf(x.w, x.w * slope);
+                uint4 o;
+                o.x = in[r][p] ? to_tf32(x.x) : 0u; o.y = in[r][p] ? to_tf32(x.y) : 0u;
+                o.z = in[r][p] ? to_tf32(x.z) : 0u; o.w = in[r][p] ? to_tf32(x.w) : 0u;
+                if (warp + r * WARPS < YH && l8 + 8 * p < YW)
+                    *reinterpret_cast<uint4*>(dstp + (r * WARPS * YW + 8 * p) * YP) = o;
+            }
+        }
+    }
+
+    // Wb fragments (constant over the whole kernel, TF32-rounded by the host): per K step s one float4 per lane =
+    // {b0, b1 of N half 0, b0, b1 of N half 1}, b0 = B[k = t][n = g], b1 = B[k = t + 4][n = g]
     uint32_t bf[KSTEPS][2][2];
 #pragma unroll
-    for (int s = 0; s < KSTEPS; ++s)
+    for (int s = 0; s < KSTEPS; ++s) {
+        const float4 v = __ldg(wb_frag + s * 32 + lane);
+        bf[s][0][0] = __float_as_uint(v.x); bf[s][0][1] = __float_as_uint(v.y);
+        bf[s][1][0] = __float_as_uint(v.z); bf[s][1][1] = __float_as_uint(v.w);
+    }
+    // head: u[pos][tap] = sum_c z[pos][c] Wh[tap][c] as a second MMA whose A operand IS the accumulator fragment of the
+    // first one (K slot t <-> channel 2t, slot t + 4 <-> channel 2t + 1 of each 8-channel half: the K order is free as
+    // long as B uses the same one), N = taps 0..7 | 8 (+ 7 zero columns)
+    uint32_t hb[2][2][2];                                     // [channel half][tap half][b0, b1]
+    float bbr[2][2];
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-            const float2 v = __ldg(wb_frag + (s * 2 + nt) * 32 + lane);
-            bf[s][nt][0] = to_tf32(v.x);
-            bf[s][nt][1] = to_tf32(v.y);
-        }
-
-    // ---- 1. y tile: depth-to-space + bias + LeakyReLU + TF32 rounding, zero outside the patch --------------------
-    {
-        const int hq = h + P.t, wq = w + P.t;
-        const float4* src = y4 + (size_t)n * hq * wq * (4 * C / 4);
-#pragma unroll 6
-        for (int idx = tid; idx < YH * YW * 4; idx += THREADS) {
-            const int pix = idx >> 2, q = idx & 3;
-            const int yy = pix / YW, yx = pix - yy * YW;
-            const int Y = R0 - 2 + yy, X = C0 - 2 + yx;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if ((unsigned)Y < (unsigned)H && (unsigned)X < (unsigned)W) {
-                const int a = Y & 1, b = X & 1;
-                v = __ldcs(src + ((size_t)((Y >> 1) + a * P.t) * wq + (X >> 1) + b * P.t) * (4 * C / 4) + (2 * a + b) * (C / 4) + q);
-                v.x += P.bias_a[4 * q + 0]; v.y += P.bias_a[4 * q + 1]; v.z += P.bias_a[4 * q + 2]; v.w += P.bias_a[4 * q + 3];
-                v.x = v.x > 0.f ? v.x : v.x * P.slope; v.y = v.y > 0.f ? v.y : v.y * P.slope;
-                v.z = v.z > 0.f ? v.z : v.z * P.slope; v.w = v.w > 0.f ? v.w : v.w * P.slope;
-                v.x = __uint_as_float(to_tf32(v.x)); v.y = __uint_as_float(to_tf32(v.y));
-                v.z = __uint_as_float(to_tf32(v.z)); v.w = __uint_as_float(to_tf32(v.w));
-            }
-            *reinterpret_cast<float4*>(ys + pix * YP + 4 * q) = v;
+    for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            bbr[nt][e] = P.bias_b[nt * 8 + 2 * t + e];
+            hb[nt][0][e] = to_tf32(P.wh[g][nt * 8 + 2 * t + e]);
+            hb[nt][1][e] = g == 0 ? to_tf32(P.wh[8][nt * 8 + 2 * t + e]) : 0u;
         }
     }
     __syncthreads();
 
-    // ---- 2 + 3. z = conv3x3(y) on the tensor cores, then bias / activation / head partial products in registers ----
+    // ---- 2 + 3. z = conv3x3(y) on the tensor cores; bias_b, LeakyReLU, zero outside the patch (the head's zero padding),
+    //             TF32; head per-tap products by MMA straight from the accumulator registers -> u[tap][position] ----
     const uint32_t ys_addr = (uint32_t)__cvta_generic_to_shared(ys);
     const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8;     // ldmatrix: this lane supplies row lrow of the 16-row tile ...
     const int lk = (lane >> 4) * 4;                           // ... at channel offset 0 (matrices 0, 1) or 4 (matrices 2, 3)
-    float whr[9][4];                                          // the head weights of this lane's four channels
-    float bbr[4];
+    // two M-tiles per iteration: four independent accumulator chains per warp keep the tensor pipe fed
+    for (int mp = warp; mp < (MT + 1) / 2; mp += WARPS) {
+        uint32_t base[2];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const int co = (e >> 1) * 8 + 2 * t + (e & 1);
-        bbr[e] = P.bias_b[co];
+        for (int i = 0; i < 2; ++i) {
+            const int l = min(16 * (2 * mp + i) + lrow, NZ - 1);
+            const int zy = l / ZW, zx = l - zy * ZW;
+            base[i] = ys_addr + (uint32_t)(((zy * YW + zx) * YP + lk) * 4);
+        }
+        float acc[2][2][4];
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) whr[tap][e] = P.wh[tap][co];
-    }
-    for (int m = warp; m < MT; m += WARPS) {
-        const int l = min(16 * m + lrow, NZ - 1);
-        const int zy = l / ZW, zx = l - zy * ZW;
-        const uint32_t base = ys_addr + (uint32_t)(((zy * YW + zx) * YP + lk) * 4);
-        float acc[2][4];
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
+            for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+                for (int e = 0; e < 4; ++e) acc[i][nt][e] = bbr[nt][e & 1];       // bias_b rides in the accumulator
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
             const int dy = tap / 3, dx = tap - dy * 3;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                uint32_t a[4];
-                ldmatrix_x4(base + (uint32_t)(((dy * YW + dx) * YP + 8 * j) * 4), a);
-                mma_tf32(acc[0], a, bf[tap * 2 + j][0][0], bf[tap * 2 + j][0][1]);
-                mma_tf32(acc[1], a, bf[tap * 2 + j][1][0], bf[tap * 2 + j][1][1]);
+                uint32_t a0[4], a1[4];
+                ldmatrix_x4(base[0] + (uint32_t)(((dy * YW + dx) * YP + 8 * j) * 4), a0);
+                ldmatrix_x4(base[1] + (uint32_t)(((dy * YW + dx) * YP + 8 * j) * 4), a1);
+                mma_tf32(acc[0][0], a0, bf[tap * 2 + j][0][0], bf[tap * 2 + j][0][1]);
+                mma_tf32(acc[1][0], a1, bf[tap * 2 + j][0][0], bf[tap * 2 + j][0][1]);
+                mma_tf32(acc[0][1], a0, bf[tap * 2 + j][1][0], bf[tap * 2 + j][1][1]);
+                mma_tf32(acc[1][1], a1, bf[tap * 2 + j][1][0], bf[tap * 2 + j][1][1]);
             }
         }
-        // accumulator layout: acc[nt][0..1] -> position 16 m + g, channels nt * 8 + 2 t (+1); acc[nt][2..3] -> position + 8
+        // accumulator layout: acc[.][nt][0..1] -> position 16 m + g, channels nt * 8 + 2 t (+1); acc[.][nt][2..3] -> position + 8
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int pos = 16 * m + g + 8 * half;
-            const int py = pos / ZW, px = pos - py * ZW;
-            const bool inside = pos < NZ && (unsigned)(R0 - 1 + py) < (unsigned)H && (unsigned)(C0 - 1 + px) < (unsigned)W;
-            float z[4];
+        for (int i = 0; i < 2; ++i) {
+            const int pos0 = 16 * (2 * mp + i) + g;
+            bool inside[2];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float v = acc[e >> 1][2 * half + (e & 1)] + bbr[e];
-                v = v > 0.f ? v : v * P.slope;
-                z[e] = inside ? v : 0.f;                      // zero padding of the ACTIVATED map for the head
+            for (int half = 0; half < 2; ++half) {
+                const int pos = pos0 + 8 * half;
+                const int py = pos / ZW, px = pos - py * ZW;
+                inside[half] = pos < NZ && (unsigned)(R0 - 1 + py) < (unsigned)H && (unsigned)(C0 - 1 + px) < (unsigned)W;
             }
-            float u[9];
+            float u[2][4];
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-                float s = whr[tap][0] * z[0];
-                s = fmaf(whr[tap][1], z[1], s); s = fmaf(whr[tap][2], z[2], s); s = fmaf(whr[tap][3], z[3], s);
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                u[tap] = s;
+            for (int nh = 0; nh < 2; ++nh)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) u[nh][e] = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                uint32_t za[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float v = fmaxf(acc[i][nt][e], acc[i][nt][e] * slope);
+                    za[e] = inside[e >> 1] ? to_tf32(v) : 0u;
+                }
+                const uint32_t afrag[4] = {za[0], za[2], za[1], za[3]};      // (g, k=t) (g+8, k=t) (g, k=t+4) (g+8, k=t+4)
+                mma_tf32(u[0], afrag, hb[nt][0][0], hb[nt][0][1]);
+                mma_tf32(u[1], afrag, hb[nt][1][0], hb[nt][1][1]);
             }
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap)
-                if ((tap & 3) == t) us[tap * UP + pos] = u[tap];          // pos < MT * 16 <= UP
+            // u[0][0..1]: position pos0, taps 2t, 2t+1; u[0][2..3]: position pos0 + 8; u[1][0], u[1][2]: tap 8 on the t == 0 lanes
+            us[(2 * t) * UP + pos0] = u[0][0];
+            us[(2 * t + 1) * UP + pos0] = u[0][1];
+            us[(2 * t) * UP + pos0 + 8] = u[0][2];
+            us[(2 * t + 1) * UP + pos0 + 8] = u[0][3];
+            if (t == 0) { us[8 * UP + pos0] = u[1][0]; us[8 * UP + pos0 + 8] = u[1][2]; }
         }
     }
     __syncthreads();
 
     // ---- 4. logits = sum over the head's taps of the per-tap products of the neighbouring z positions -----------
     float* o = out + (size_t)n * H * W;
-    for (int idx = tid; idx < TH * TW; idx += THREADS) {
-        const int oy = idx / TW, ox = idx - oy * TW;
-        if (R0 + oy < H && C0 + ox < W) {
-            float s = 0.f;
+    {
+        int oy = tid / TW, ox = tid - oy * TW;
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-                const int dy = tap / 3, dx = tap - dy * 3;
-                s += us[tap * UP + (oy + dy) * ZW + ox + dx];
+        for (int k = 0; k < (TH * TW + THREADS - 1) / THREADS; ++k) {
+            if (oy < TH && R0 + oy < H && C0 + ox < W) {
+                const float* up = us + oy * ZW + ox;
+                float s = 0.f;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) s += up[tap * UP + (tap / 3) * ZW + (tap % 3)];
+                __stcs(o + (size_t)(R0 + oy) * W + C0 + ox, P.sigmoid ? __fdividef(1.0f, 1.0f + __expf(-s)) : s);
             }
-            __stcs(o + (size_t)(R0 + oy) * W + C0 + ox, P.sigmoid ? __fdividef(1.0f, 1.0f + __expf(-s)) : s);
+            ox += THREADS % TW; oy += THREADS / TW;
+            if (ox >= TW) { ox -= TW; ++oy; }
         }
     }
 }
@@ -233,6 +298,7 @@ extern "C" int riders_decoder_tail_nhwc(const float* y4, int taps, int N, int h,
     using namespace riders;
     RIDERS_REQUIRE(N >= 0 && h > 0 && w > 0, "decoder_tail: bad shape");
     RIDERS_REQUIRE(taps == 2 || taps == 3, "decoder_tail: taps must be 2 or 3 (got %d)", taps);
+    RIDERS_REQUIRE(slope >= 0.f && slope <= 1.f, "decoder_tail: LeakyReLU slope must be in [0, 1] (got %g)", (double)slope);
     if (N == 0) return RIDERS_OK;
     RIDERS_REQUIRE(y4 && wb_frag && wh_host && out, "decoder_tail: null pointer");
     RIDERS_REQUIRE(((((uintptr_t)y4) | ((uintptr_t)wb_frag)) & 15) == 0, "decoder_tail: y4 / wb_frag must be 16-byte aligned");
@@ -256,7 +322,7 @@ extern "C" int riders_decoder_tail_nhwc(const float* y4, int taps, int N, int h,
     }
     count_launches(1);
     tail::decoder_tail_kernel<<<(unsigned)blocks, tail::THREADS, tail::SMEM_BYTES, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(y4), reinterpret_cast<const float2*>(wb_frag), out, P, h, w, tiles_x, tiles_y);
+        reinterpret_cast<const float4*>(y4), reinterpret_cast<const float4*>(wb_frag), out, P, h, w, tiles_x, tiles_y);
     return check_launch("decoder_tail_nhwc");
 }
 

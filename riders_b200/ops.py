@@ -8,6 +8,8 @@ import ctypes as C
 
 import numpy as np
 
+import weakref
+
 import torch
 
 from . import _lib
@@ -362,14 +364,20 @@ def _host_floats(t):
     """Small parameter tensor -> cached contiguous float32 host copy (one D2H per parameter version)."""
     if t is None:
         return None
-    key = (t.data_ptr(), t._version, tuple(t.shape))
-    h = _HOST_CACHE.get(key)
-    if h is None:
-        if len(_HOST_CACHE) > 64:
-            _HOST_CACHE.clear()
-        h = t.detach().to("cpu", torch.float32).contiguous()
-        _HOST_CACHE[key] = h
-    return h
+    return _cached(_HOST_CACHE, t, lambda: t.detach().to("cpu", torch.float32).contiguous())
+
+
+def _cached(cache, t, make):
+    """Value derived from tensor ``t``, rebuilt when ``t`` is another tensor object (a recycled address does not count) or
+    was modified in place (``_version``)."""
+    ent = cache.get(id(t))
+    if ent is not None and ent[0]() is t and ent[1] == t._version and ent[2] == t.data_ptr():
+        return ent[3]
+    if len(cache) > 64:
+        cache.clear()
+    val = make()
+    cache[id(t)] = (weakref.ref(t), t._version, t.data_ptr(), val)
+    return val
 
 
 def conv3x3_head(x_raw, bias, slope, weight, sigmoid=False):
@@ -385,6 +393,45 @@ def conv3x3_head(x_raw, bias, slope, weight, sigmoid=False):
         rc = _lib.lib().riders_conv3x3_head_sigmoid_nhwc(_ptr(x_raw), N, Cc, H, W, _ptr(hb), float(slope), _ptr(hw),
                                                          1 if sigmoid else 0, _ptr(out), _stream())
     _lib.check(rc, "riders_conv3x3_head_sigmoid_nhwc")
+    return out
+
+
+_FRAG_CACHE = {}
+
+
+def _tail_weight_fragments(weight):
+    """(16,16,3,3) convolution weight -> mma.m16n8k8 B fragments [K step][lane][N half][2] on the device, rounded to TF32
+    (cvt.rna), cached per parameter version: b0 = W[co = 8 nt + g][ci = 8 j + t][ky][kx], b1 the same at ci + 4,
+    lane = 4 g + t, K step = (ky * 3 + kx) * 2 + j."""
+    def make():
+        dev = weight.device
+        s = torch.arange(18, device=dev).view(18, 1, 1, 1)
+        lane = torch.arange(32, device=dev).view(1, 32, 1, 1)
+        nt = torch.arange(2, device=dev).view(1, 1, 2, 1)
+        e = torch.arange(2, device=dev).view(1, 1, 1, 2)
+        tap, j = s // 2, s % 2
+        f = weight.detach().float()[nt * 8 + lane // 4, 8 * j + lane % 4 + 4 * e, tap // 3, tap % 3].contiguous()
+        return ((f.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    return _cached(_FRAG_CACHE, weight, make)
+
+
+def decoder_tail(y4, bias_a, weight_b, bias_b, weight_head, slope=0.2, taps=3, sigmoid=False):
+    """Fused last decoder block + head (TF32): logits (N,1,2h,2w) = conv3x3(act(conv3x3(act(d2s(y4) + bias_a); weight_b)
+    + bias_b); weight_head).  y4 (N,64,h,w) [taps=2: (N,64,h+1,w+1)] channels_last phase-convolution output."""
+    _need_cuda(y4, weight_b)
+    t = 1 if taps == 2 else 0
+    N, C4 = y4.shape[:2]
+    h, w = y4.shape[2] - t, y4.shape[3] - t
+    if not (_is_channels_last(y4) and y4.dtype == torch.float32 and C4 == 64 and tuple(weight_b.shape) == (16, 16, 3, 3)
+            and tuple(weight_head.shape) == (1, 16, 3, 3) and h > 0 and w > 0):
+        raise _lib.RidersError("decoder_tail: needs a channels_last float32 (N,64,h,w) map, a (16,16,3,3) and a (1,16,3,3) weight")
+    frag = _tail_weight_fragments(weight_b)
+    ha, hb, hh = _host_floats(bias_a), _host_floats(bias_b), _host_floats(weight_head)
+    out = torch.empty((N, 1, 2 * h, 2 * w), device=y4.device, dtype=torch.float32)
+    with _span("decoder_tail", (y4.numel() + out.numel()) * 4):
+        rc = _lib.lib().riders_decoder_tail_nhwc(_ptr(y4), int(taps), N, h, w, _ptr(ha), _ptr(frag), _ptr(hb), _ptr(hh),
+                                                 float(slope), 1 if sigmoid else 0, _ptr(out), _stream())
+    _lib.check(rc, "riders_decoder_tail_nhwc")
     return out
 
 

@@ -432,6 +432,19 @@ class MultiScaleDecoder(torch.nn.Module):
         for i in range(depth, 7):
             setattr(self, 'deconv%d' % i, None)
         self.output0 = Conv2d(cin, output_channels, 3, 1, weight_initializer, output_func, False)
+        self.fused_tail = os.environ.get('RIDERS_FUSED_TAIL', '1') != '0'      # ops.decoder_tail where TF32 is allowed
+
+    def _tail_ok(self, last, y, yp, shape):
+        """Can ``ops.decoder_tail`` take over from the last block's sub-pixel convolution on?  (inference fast path, exact 2x,
+        16 -> 16 -> 1 channels, LeakyReLU, BatchNorm folded, no skip)"""
+        head, up, cv = self.output0.conv, last.deconv.conv, last.conv
+        return (shape is not None and yp is None and last._w4 is not None and last.skip_channels == 0
+                and tuple(shape[-2:]) == (2 * y.shape[2], 2 * y.shape[3]) and up.fast_ok(y)
+                and up._fused_slope == _LEAK and cv._fused_slope == _LEAK and not cv.use_batch_norm
+                and up.conv.out_channels == 16 and tuple(cv.conv.weight.shape) == (16, 16, 3, 3)
+                and cv.conv.stride == (1, 1) and cv.conv.padding == (1, 1)
+                and self.output0._act is None and not self.output0.use_batch_norm and head.bias is None
+                and tuple(head.weight.shape) == (1, 16, 3, 3) and head.stride == (1, 1) and head.padding == (1, 1))
 
     def skip_lead_channels(self, n_skips):
         """Output channels of the up-convolution in front of each skip (skips[i] feeds block ``_order[n_skips-1-i]``,
@@ -460,6 +473,14 @@ class MultiScaleDecoder(torch.nn.Module):
             n -= 1
         last = getattr(self, self._order[-1])
         head = self.output0.conv
+        if (n != 0 and self.fused_tail and torch.backends.cudnn.allow_tf32 and self._tail_ok(last, y, yp, shape)):
+            # TF32 flow (torch's default): the whole tail - depth-to-space + bias + LeakyReLU, the block's 16 -> 16
+            # convolution, bias + LeakyReLU, the 16 -> 1 head - in ONE kernel fed by the sub-pixel phase convolution
+            taps = 2 if (last.subpixel_taps == 2 and last._w2 is not None) else 3
+            y4 = F.conv2d(y, last._w2 if taps == 2 else last._w4, None, 1, 1)
+            self.last_head_sigmoid = bool(head_sigmoid)
+            return [ops.decoder_tail(y4, last.deconv.conv.conv.bias, last.conv.conv.weight, last.conv.conv.bias, head.weight,
+                                     _LEAK, taps=taps, sigmoid=head_sigmoid)]
         if (n != 0 and last.skip_channels == 0 and last.conv.fast_ok(y) and self.output0._act is None
                 and not self.output0.use_batch_norm and head.bias is None and head.kernel_size == (3, 3)
                 and head.out_channels == 1 and head.in_channels == 16 and head.stride == (1, 1) and head.padding == (1, 1)):

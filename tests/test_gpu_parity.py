@@ -720,6 +720,81 @@ def test_decoder_hands_padded_maps_to_odd_blocks(monkeypatch):
     np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=2e-4, atol=2e-5)
 
 
+def _tf32_rna(x):
+    """cvt.rna.tf32.f32 in torch: round the magnitude to 10 mantissa bits, ties away from zero."""
+    return ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("taps", [2, 3])
+@pytest.mark.parametrize("hw", [(120, 50), (7, 9), (13, 30)])
+def test_decoder_tail_matches_the_three_passes(hw, taps):
+    """ops.decoder_tail (d2s + bias + act -> 16->16 conv on TF32 tensor cores -> bias + act -> 16->1 head, TF32 too) against
+    torch: against fp32 convolutions of the TF32-ROUNDED operands (same rounding points as the kernel) the mean error is at
+    fp32 level and only values whose z sits on a TF32 rounding boundary move (by one TF32 ulp of a product); against the
+    pure fp32 passes it is within TF32 accuracy (2e-3 of the logit scale)."""
+    F = torch.nn.functional
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device=DEV).manual_seed(hw[0] * 7 + taps)
+    N, (h, w), t = 3, hw, (1 if taps == 2 else 0)
+    y4 = torch.randn((N, 64, h + t, w + t), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    ba, bb = torch.randn(16, device=DEV, generator=g) * 0.3, torch.randn(16, device=DEV, generator=g) * 0.3
+    wb = torch.randn((16, 16, 3, 3), device=DEV, generator=g) * 0.15
+    wh = torch.randn((1, 16, 3, 3), device=DEV, generator=g) * 0.2
+    y = ops.d2s_bias_act_concat(y4, ba, None, 0.2, taps=taps).contiguous()           # bit-exact pass (tested above)
+    z32 = F.leaky_relu(F.conv2d(y, wb, bb, 1, 1), 0.2)
+    ref32 = F.conv2d(z32, wh, None, 1, 1)
+    zt = F.leaky_relu(F.conv2d(_tf32_rna(y), _tf32_rna(wb), None, 1, 1) + bb.view(1, -1, 1, 1), 0.2)
+    reft = F.conv2d(_tf32_rna(zt), _tf32_rna(wh), None, 1, 1)               # the head runs on the tensor cores too
+    got = ops.decoder_tail(y4, ba, wb, bb, wh, 0.2, taps=taps)
+    assert got.shape == ref32.shape
+    scale = float(ref32.abs().max())
+    err = (got - reft).abs()
+    assert float(err.mean()) < 2e-6 * scale and float(err.max()) < 5e-4 * scale
+    assert float((err > 2e-5 * scale).float().mean()) < 0.02
+    assert float((got - ref32).abs().max()) < 2e-3 * scale
+    sg = ops.decoder_tail(y4, ba, wb, bb, wh, 0.2, taps=taps, sigmoid=True)
+    np.testing.assert_allclose(sg.cpu().numpy(), torch.sigmoid(got).cpu().numpy(), rtol=2e-6, atol=1e-7)
+
+
+def test_decoder_uses_the_fused_tail_only_where_tf32_is_allowed(monkeypatch):
+    """MultiScaleDecoder: with torch.backends.cudnn.allow_tf32 the tail runs in ops.decoder_tail and agrees with the cuDNN
+    TF32 passes to TF32 accuracy; without it the fp32 passes run (the 1e-4 parity tests above are untouched)."""
+    from riders_b200.rcnet import networks
+    torch.manual_seed(12)
+    dec = networks.MultiScaleDecoder(64, 1, 1, [32, 32, 16, 16, 16], [32, 32, 16, 8, 0], 'kaiming_uniform', 'leaky_relu', 'linear',
+                                     True, 'up').to(DEV).eval()
+    N = 3
+    x = torch.randn((N, 64, 7, 3), device=DEV).contiguous(memory_format=torch.channels_last)
+    skips = [torch.randn((N, c) + hw, device=DEV).contiguous(memory_format=torch.channels_last)
+             for c, hw in ((8, (120, 50)), (16, (60, 25)), (32, (30, 12)), (32, (15, 6)))]
+    with torch.no_grad():
+        for m in dec.modules():
+            if isinstance(m, networks.Conv2d):
+                m.fold_batch_norm_()
+        dec.to(memory_format=torch.channels_last)
+        for m in dec.modules():
+            if isinstance(m, networks.DecoderBlock):
+                m.fold_upsample_()
+        calls = []
+        real = ops.decoder_tail
+        monkeypatch.setattr(ops, "decoder_tail", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+        torch.backends.cudnn.allow_tf32 = False
+        ref = dec(x, skips, shape=(240, 100))[-1]
+        assert not calls
+        torch.backends.cudnn.allow_tf32 = True
+        try:
+            got = dec(x, skips, shape=(240, 100))[-1]
+            assert len(calls) == 1
+            dec.fused_tail = False
+            sep = dec(x, skips, shape=(240, 100))[-1]
+            assert len(calls) == 1
+        finally:
+            torch.backends.cudnn.allow_tf32 = False
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) < 5e-3 * scale and float((sep - ref).abs().max()) < 5e-3 * scale
+    assert float((got - sep).abs().max()) < 5e-3 * scale
+
+
 # ------------------------------------------------------------------------------------ config 4: training step
 def test_training_step_gradients_match_the_reference_path():
     """rcnet_main.train's inner step (forward with logits, masked BCE, backward) through the mirror on the GPU

@@ -123,6 +123,46 @@ def bench_glue(R=2048):
     report("bias_act_16ch_240x100", ms, best, z.numel() * 8, R=R)
 
 
+def bench_tail(R=2048):
+    """Fused decoder tail (d2s + 16->16 conv + head) against the three passes it replaces (d2s kernel, cuDNN TF32, head kernel)."""
+    import torch.nn.functional as F
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    g = torch.Generator(device=DEV).manual_seed(0)
+    ba, bb = torch.randn(16, device=DEV, generator=g) * 0.1, torch.randn(16, device=DEV, generator=g) * 0.1
+    wb = (torch.randn((16, 16, 3, 3), device=DEV, generator=g) * 0.1).contiguous(memory_format=torch.channels_last)
+    wh = torch.randn((1, 16, 3, 3), device=DEV, generator=g) * 0.1
+    flops = R * 24000 * 16 * 16 * 9 * 2
+    for taps in (3, 2):
+        t = 1 if taps == 2 else 0
+        y4 = torch.randn((R, 64, 120 + t, 50 + t), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+        nbytes = (y4.numel() + R * 24000) * 4
+        ms, best = timeit(lambda: ops.decoder_tail(y4, ba, wb, bb, wh, 0.2, taps=taps, sigmoid=True), iters=5)
+        report("decoder_tail_taps%d" % taps, ms, best, nbytes, flops=flops, R=R)
+
+        def separate():
+            z = ops.d2s_bias_act_concat(y4, ba, None, 0.2, taps=taps)
+            return ops.conv3x3_head(F.conv2d(z, wb, None, 1, 1), bb, 0.2, wh, sigmoid=True)
+        ms, best = timeit(separate, iters=5)
+        report("separate_d2s_cudnn_head_taps%d" % taps, ms, best, nbytes, flops=flops, R=R)
+
+
+def bench_mmasync():
+    """Issue rate of mma.sync.m16n8k8.tf32 (registers only): cycles per MMA per SM for 4..16 warps per SM."""
+    from riders_b200 import _lib
+    cyc = torch.zeros(148, dtype=torch.int64, device=DEV)
+    sink = torch.zeros(4, device=DEV)
+    iters = 4096
+    for warps in (4, 8, 12, 16):
+        for ctas in (1, 148):
+            _lib.check(_lib.lib().riders_debug_mma_sync_rate(warps, iters, ctas, cyc.data_ptr(), sink.data_ptr(), None), "mma_sync_rate")
+            torch.cuda.synchronize()
+            c = float(cyc[:ctas].double().mean())
+            per_sm = c / (iters * 8 * warps)
+            print(json.dumps({"kernel": "mma_sync_m16n8k8_tf32", "warps": warps, "ctas": ctas, "cycles_per_mma_per_sm": round(per_sm, 3),
+                              "mac_per_cycle_per_sm": round(1024 / per_sm, 1)}), flush=True)
+
+
 def bench_loftr(N=4096):
     import oracle  # noqa: F401  (only to keep the import graph explicit: weights are random here)
     from riders_b200.rcnet.linear_attention import LocalFeatureTransformer
