@@ -13,7 +13,6 @@ int  check_launch(const char* what);          // cudaGetLastError -> RIDERS_* co
 int  sm_count();
 void set_reduce_rows(int rows);              // confidence_reduce.cu tuning knob (4 or 8 rows per thread)
 void set_gather_smem_budget(int kb);         // roi_gather.cu tuning knob (riders_debug_set)
-void set_tail_impl(int v);                    // decoder_tail.cu: 1 warp-specialised persistent (default), 0 one CTA per tile
 void count_launches(int n);                   // feeds riders_launch_count() (bench.py's gpu_launches)
 
 #define RIDERS_REQUIRE(cond, ...)                         \

@@ -19,6 +19,13 @@
 // tools/mma_rate.py: ~43 + N/2), i.e. ~270 MAC/cycle/SM; the warp-level m16n8k8 keeps Wb in registers (72 per thread)
 // and re-uses every A fragment for both 8-wide halves of N, so shared memory supplies 256 B per 2 x 1024 MACs.
 //
+// Measured (B200, 2048 points, profiles/r01_ncu_summary_v6_decoder_tail.txt): 2.9 ms against 3.25 ms for the three passes;
+// tensor pipe 38 % busy, L1/shared data pipe 57 %, issue slots 34 %: with only 16 output channels there are ~5 scalar
+// instructions (activation, rounding, masks, addressing) per MMA and the kernel is bound by their issue / latency, not by
+// a pipe.  A warp-specialised persistent variant (loader + mma warps, double-buffered tiles, vertically shared A
+// fragments) and deeper ldmatrix prefetch were built and measured at the same 2.9 - 3.0 ms (git history), so the simple
+// form stays.
+//
 // CTA = 12 x 50 output pixels of one point (6 warps, 2 CTAs / SM):
 //   1. y tile (16 x 54, halo 2) <- y4 + bias_a, LeakyReLU, cvt.rna.tf32; 20 floats per pixel so that the 8 rows of an
 //      ldmatrix 8 x 16 B tile fall into distinct bank groups;
@@ -77,7 +84,7 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&a)[4]) {
 }
 
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -263,274 +270,6 @@ decoder_tail_kernel(const float4* __restrict__ y4, const float4* __restrict__ wb
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Warp-specialised persistent form of the same computation (the default): one CTA per SM, tiles round-robin.
-//   warps 0..3   "loader": y4 window -> registers -> bias_a / LeakyReLU / TF32 -> y tile (double buffered), and the final
-//                logits of the PREVIOUS tile from its u planes (double buffered) - all the non-tensor work;
-//   warps 4..15  "mma": Wb fragments resident in registers for the whole kernel; per tile 23 pair-iterations:
-//                21 vertical pairs (16 columns x rows 2r, 2r+1: the two M-tiles share two of their three tap rows, so
-//                24 ldmatrix.x4 feed 72 MMAs instead of 36) + 2 linear pairs over the 4-column remainder strip.
-// Hand-off through named barriers (bar.arrive on the producing side, bar.sync on the consuming side, 512 participants):
-// FULL_Y / EMPTY_Y for the y tile, FULL_U / EMPTY_U for the u planes, one pair per buffer.
-// ---------------------------------------------------------------------------------------------
-namespace ws {
-
-constexpr int L_WARPS = 8, M_WARPS = 8, NTHREADS = (L_WARPS + M_WARPS) * 32;
-constexpr int LROWS = YH / L_WARPS;                                // tile rows per loader warp: one batch of LROWS x 7 loads
-constexpr int YBUF = YH * YW * YP, UBUF = 9 * UP;                 // floats
-constexpr int SMEM_BYTES = 2 * (YBUF + UBUF) * 4;                  // 191520
-constexpr int NCB = ZW / 16, STRIP = ZW - NCB * 16;                // 3 column blocks of 16 + a 4-column strip
-constexpr int NVERT = NCB * (ZH / 2);                              // 21 vertical pairs
-constexpr int STRIP_TILES = (STRIP * ZH + 15) / 16;                // 4 (3.5)
-constexpr int NIT = NVERT + (STRIP_TILES + 1) / 2;                 // 23 pair-iterations per tile
-static_assert(ZH % 2 == 0 && STRIP == 4 && YH == LROWS * L_WARPS, "tile decomposition");
-enum { BAR_FULL_Y = 1, BAR_EMPTY_Y = 3, BAR_FULL_U = 5, BAR_EMPTY_U = 7 };
-
-__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(NTHREADS) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "n"(NTHREADS) : "memory"); }
-
-struct TileCoord { long long n; int R0, C0; };
-__device__ __forceinline__ TileCoord decode_tile(int tile, int tiles_x, int tiles_y) {
-    TileCoord c;
-    const int tx = tile % tiles_x; tile /= tiles_x;
-    const int ty = tile % tiles_y;
-    c.n = tile / tiles_y; c.R0 = ty * TH; c.C0 = tx * TW;
-    return c;
-}
-
-__global__ void __launch_bounds__(NTHREADS, 1)
-decoder_tail_ws_kernel(const float4* __restrict__ y4, const float4* __restrict__ wb_frag, float* __restrict__ out,
-                       const __grid_constant__ Params P, int h, int w, int tiles_x, int tiles_y, int n_tiles) {
-    extern __shared__ __align__(16) float smem[];
-    float* ys = smem;                                  // [2][YH][YW][YP]
-    float* us = smem + 2 * YBUF;                       // [2][9][UP]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int H = 2 * h, W = 2 * w;
-    const float slope = P.slope;
-
-    if (warp < L_WARPS) {
-        // =============================== loader / finisher ===============================
-        constexpr int PASSES = (YW + 7) / 8;                          // 7 (the last one covers 6 pixels)
-        const int q = lane >> 3, l8 = lane & 7;
-        const float4 ba = make_float4(P.bias_a[4 * q + 0], P.bias_a[4 * q + 1], P.bias_a[4 * q + 2], P.bias_a[4 * q + 3]);
-        const int hq = h + P.t, wq = w + P.t, pt = P.t;
-        const size_t point_stride = (size_t)hq * wq * (4 * C / 4);
-        float4 v[LROWS][PASSES];
-        bool in[LROWS][PASSES];
-        // rows warp + L_WARPS * r of the tile at `c`: all loads in flight together
-        auto issue = [&](const TileCoord& c) {
-            const int X0 = c.C0 - 2 + l8, bcol = X0 & 1;
-            const float4* src = y4 + c.n * point_stride + q + ((X0 >> 1) + bcol * pt) * (4 * C / 4) + bcol * (C / 4);
-#pragma unroll
-            for (int r = 0; r < LROWS; ++r) {
-                const int Y = c.R0 - 2 + warp + L_WARPS * r, a = Y & 1;
-                const bool row_ok = (unsigned)Y < (unsigned)H;
-                const float4* rp = src + (row_ok ? (((Y >> 1) + a * pt) * wq) * (4 * C / 4) + a * (2 * C / 4) : 0);
-#pragma unroll
-                for (int p = 0; p < PASSES; ++p) {
-                    in[r][p] = row_ok && (unsigned)(X0 + 8 * p) < (unsigned)W && l8 + 8 * p < YW;
-                    v[r][p] = __ldcs(in[r][p] ? rp + p * 4 * (4 * C / 4) : y4);          // always a valid address: no branch
-                }
-            }
-        };
-        auto stash = [&](float* ybuf) {
-            float* dstp = ybuf + ((warp * YW + l8) * YP + 4 * q);
-#pragma unroll
-            for (int r = 0; r < LROWS; ++r)
-#pragma unroll
-                for (int p = 0; p < PASSES; ++p) {
-                    float4 x = v[r][p];
-                    x.x += ba.x; x.y += ba.y; x.z += ba.z; x.w += ba.w;
-                    x.x = fmaxf(x.x, x.x * slope); x.y = fmaxf(x.y, x.y * slope);          // LeakyReLU, 0 <= slope <= 1
-                    x.z = fmaxf(x.z, x.z * slope); x.w = fmaxf(x.w, x.w * slope);
-                    uint4 o;
-                    o.x = in[r][p] ? to_tf32(x.x) : 0u; o.y = in[r][p] ? to_tf32(x.y) : 0u;
-                    o.z = in[r][p] ? to_tf32(x.z) : 0u; o.w = in[r][p] ? to_tf32(x.w) : 0u;
-                    if (l8 + 8 * p < YW) *reinterpret_cast<uint4*>(dstp + (r * L_WARPS * YW + 8 * p) * YP) = o;
-                }
-        };
-        // logits of a finished tile: sum over the head's taps of the per-tap products of the neighbouring z positions
-        auto finish = [&](const TileCoord& c, const float* ub) {
-            float* o = out + (size_t)c.n * H * W;
-            int oy = tid / TW, ox = tid - oy * TW;
-#pragma unroll
-            for (int k = 0; k < (TH * TW + L_WARPS * 32 - 1) / (L_WARPS * 32); ++k) {
-                if (oy < TH && c.R0 + oy < H && c.C0 + ox < W) {
-                    const float* up = ub + oy * ZW + ox;
-                    float s = 0.f;
-#pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) s += up[tap * UP + (tap / 3) * ZW + (tap % 3)];
-                    __stcs(o + (size_t)(c.R0 + oy) * W + c.C0 + ox, P.sigmoid ? __fdividef(1.0f, 1.0f + __expf(-s)) : s);
-                }
-                ox += (L_WARPS * 32) % TW; oy += (L_WARPS * 32) / TW;
-                if (ox >= TW) { ox -= TW; ++oy; }
-            }
-        };
-        int k = 0;
-        TileCoord cur = decode_tile(min((int)blockIdx.x, n_tiles - 1), tiles_x, tiles_y), prev = cur;
-        if ((int)blockIdx.x < n_tiles) issue(cur);
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
-            const int b = k & 1;
-            if (k >= 2) bar_sync(BAR_EMPTY_Y + b);                  // the mma warps are done with tile k - 2 in this buffer
-            stash(ys + b * YBUF);
-            bar_arrive(BAR_FULL_Y + b);
-            const TileCoord done = prev;
-            prev = cur;
-            if (tile + (int)gridDim.x < n_tiles) {                  // next tile's first batch flies during the finish below
-                cur = decode_tile(tile + gridDim.x, tiles_x, tiles_y);
-                issue(cur);
-            }
-            if (k >= 1) {
-                bar_sync(BAR_FULL_U + (b ^ 1));
-                finish(done, us + (b ^ 1) * UBUF);
-                bar_arrive(BAR_EMPTY_U + (b ^ 1));
-            }
-        }
-        if (k >= 1) {
-            const int b = (k - 1) & 1;
-            bar_sync(BAR_FULL_U + b);
-            finish(prev, us + b * UBUF);
-        }
-    } else {
-        // =============================== mma warps ===============================
-        const int mw = warp - L_WARPS;
-        const int g = lane >> 2, t = lane & 3;
-        uint32_t bf[KSTEPS][2][2];
-#pragma unroll
-        for (int s = 0; s < KSTEPS; ++s) {
-            const float4 x = __ldg(wb_frag + s * 32 + lane);
-            bf[s][0][0] = __float_as_uint(x.x); bf[s][0][1] = __float_as_uint(x.y);
-            bf[s][1][0] = __float_as_uint(x.z); bf[s][1][1] = __float_as_uint(x.w);
-        }
-        uint32_t hb[2][2][2];                                     // head B fragments, see decoder_tail_kernel
-        float bbr[2][2];
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                bbr[nt][e] = P.bias_b[nt * 8 + 2 * t + e];
-                hb[nt][0][e] = to_tf32(P.wh[g][nt * 8 + 2 * t + e]);
-                hb[nt][1][e] = g == 0 ? to_tf32(P.wh[8][nt * 8 + 2 * t + e]) : 0u;
-            }
-        const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8;
-        const int lk = (lane >> 4) * 4;
-        const uint32_t ys_addr = (uint32_t)__cvta_generic_to_shared(ys);
-
-        int k = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
-            const int b = k & 1;
-            const TileCoord c = decode_tile(tile, tiles_x, tiles_y);
-            float* ub = us + b * UBUF;
-            const uint32_t yb = ys_addr + (uint32_t)(b * YBUF * 4);
-            // z-position (zy, zx) -> inside the patch?  (the head's zero padding applies to the ACTIVATED z)
-            auto inside = [&](int zy, int zx) { return (unsigned)(c.R0 - 1 + zy) < (unsigned)H && (unsigned)(c.C0 - 1 + zx) < (unsigned)W; };
-            // bias_b rode in the accumulator; LeakyReLU, mask, TF32; head MMA from the accumulator fragment; u planes
-            auto epilogue = [&](const float (&acc)[2][4], int pos_lo, int pos_hi, bool in_lo, bool in_hi, bool st_lo, bool st_hi) {
-                float u[2][4];
-#pragma unroll
-                for (int nh = 0; nh < 2; ++nh)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) u[nh][e] = 0.f;
-#pragma unroll
-                for (int nt = 0; nt < 2; ++nt) {
-                    uint32_t za[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float x = fmaxf(acc[nt][e], acc[nt][e] * slope);
-                        za[e] = ((e >> 1) ? in_hi : in_lo) ? to_tf32(x) : 0u;
-                    }
-                    const uint32_t afrag[4] = {za[0], za[2], za[1], za[3]};
-                    mma_tf32(u[0], afrag, hb[nt][0][0], hb[nt][0][1]);
-                    mma_tf32(u[1], afrag, hb[nt][1][0], hb[nt][1][1]);
-                }
-                if (st_lo) {
-                    ub[(2 * t) * UP + pos_lo] = u[0][0];
-                    ub[(2 * t + 1) * UP + pos_lo] = u[0][1];
-                    if (t == 0) ub[8 * UP + pos_lo] = u[1][0];
-                }
-                if (st_hi) {
-                    ub[(2 * t) * UP + pos_hi] = u[0][2];
-                    ub[(2 * t + 1) * UP + pos_hi] = u[0][3];
-                    if (t == 0) ub[8 * UP + pos_hi] = u[1][2];
-                }
-            };
-
-            bar_sync(BAR_FULL_Y + b);
-            if (k >= 2) bar_sync(BAR_EMPTY_U + b);                  // the loader has read tile k - 2's u planes
-            for (int it = mw; it < NIT; it += M_WARPS) {
-                float acc[2][2][4];
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                    for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) acc[i][nt][e] = bbr[nt][e & 1];
-                if (it < NVERT) {
-                    const int rp = it / NCB, cb = it - rp * NCB;
-                    const uint32_t base = yb + (uint32_t)((((2 * rp) * YW + 16 * cb + lrow) * YP + lk) * 4);
-                    // 24 steps (tap row d of the 4 shared y rows, dx, channel half j); the A fragments are fetched two steps
-                    // ahead of the MMAs that use them (asm volatile keeps program order, so the distance is explicit)
-                    auto step_off = [](int s) { return (uint32_t)(((((s / 6) * YW) + (s % 6) / 2) * YP + 8 * (s & 1)) * 4); };
-                    uint32_t a[3][4];
-                    ldmatrix_x4(base + step_off(0), a[0]);
-                    ldmatrix_x4(base + step_off(1), a[1]);
-#pragma unroll
-                    for (int s = 0; s < 24; ++s) {
-                        if (s + 2 < 24) ldmatrix_x4(base + step_off(s + 2), a[(s + 2) % 3]);
-                        const int d = s / 6, dx = (s % 6) / 2, j = s & 1;
-                        if (d <= 2) {
-                            mma_tf32(acc[0][0], a[s % 3], bf[(d * 3 + dx) * 2 + j][0][0], bf[(d * 3 + dx) * 2 + j][0][1]);
-                            mma_tf32(acc[0][1], a[s % 3], bf[(d * 3 + dx) * 2 + j][1][0], bf[(d * 3 + dx) * 2 + j][1][1]);
-                        }
-                        if (d >= 1) {
-                            mma_tf32(acc[1][0], a[s % 3], bf[((d - 1) * 3 + dx) * 2 + j][0][0], bf[((d - 1) * 3 + dx) * 2 + j][0][1]);
-                            mma_tf32(acc[1][1], a[s % 3], bf[((d - 1) * 3 + dx) * 2 + j][1][0], bf[((d - 1) * 3 + dx) * 2 + j][1][1]);
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int zy = 2 * rp + i, zx = 16 * cb + g;
-                        epilogue(acc[i], zy * ZW + zx, zy * ZW + zx + 8, inside(zy, zx), inside(zy, zx + 8), true, true);
-                    }
-                } else {
-                    // remainder strip (columns 48..51, 14 rows = 56 positions, 4 per row): two 16-position tiles per iteration
-                    const int m0 = 2 * (it - NVERT);
-                    uint32_t base[2];
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int l = min(16 * (m0 + i) + lrow, STRIP * ZH - 1);
-                        base[i] = yb + (uint32_t)((((l / STRIP) * YW + NCB * 16 + (l % STRIP)) * YP + lk) * 4);
-                    }
-#pragma unroll
-                    for (int tap = 0; tap < 9; ++tap)
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            uint32_t a0[4], a1[4];
-                            const uint32_t off = (uint32_t)((((tap / 3) * YW + tap % 3) * YP + 8 * j) * 4);
-                            ldmatrix_x4(base[0] + off, a0);
-                            ldmatrix_x4(base[1] + off, a1);
-                            mma_tf32(acc[0][0], a0, bf[tap * 2 + j][0][0], bf[tap * 2 + j][0][1]);
-                            mma_tf32(acc[1][0], a1, bf[tap * 2 + j][0][0], bf[tap * 2 + j][0][1]);
-                            mma_tf32(acc[0][1], a0, bf[tap * 2 + j][1][0], bf[tap * 2 + j][1][1]);
-                            mma_tf32(acc[1][1], a1, bf[tap * 2 + j][1][0], bf[tap * 2 + j][1][1]);
-                        }
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int l_lo = 16 * (m0 + i) + g, l_hi = l_lo + 8;
-                        const bool v_lo = l_lo < STRIP * ZH, v_hi = l_hi < STRIP * ZH;
-                        const int zy_lo = l_lo / STRIP, zx_lo = NCB * 16 + l_lo % STRIP, zy_hi = l_hi / STRIP, zx_hi = NCB * 16 + l_hi % STRIP;
-                        epilogue(acc[i], zy_lo * ZW + zx_lo, zy_hi * ZW + zx_hi, v_lo && inside(zy_lo, zx_lo), v_hi && inside(zy_hi, zx_hi), v_lo, v_hi);
-                    }
-                }
-            }
-            bar_arrive(BAR_EMPTY_Y + b);
-            bar_arrive(BAR_FULL_U + b);
-        }
-    }
-}
-
-}  // namespace ws
-
 // issue-rate probe for the warp-level TF32 MMA (riders_debug_mma_sync_rate): `warps` warps per CTA, one CTA per SM,
 // 8 independent accumulators per warp, registers only
 __global__ void __launch_bounds__(1024, 1)
@@ -557,9 +296,6 @@ mma_sync_rate_kernel(int iters, long long* cycles, float* sink) {
 }
 
 }  // namespace tail
-
-static int g_tail_impl = 1;                  // 1: warp-specialised persistent kernel, 0: one CTA per tile
-void set_tail_impl(int v) { g_tail_impl = v ? 1 : 0; }
 
 }  // namespace riders
 
@@ -588,20 +324,13 @@ extern "C" int riders_decoder_tail_nhwc(const float* y4, int taps, int N, int h,
     RIDERS_REQUIRE(blocks < (1ll << 31), "decoder_tail: too many tiles for one launch");
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(tail::decoder_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tail::SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(tail::ws::decoder_tail_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tail::ws::SMEM_BYTES) != cudaSuccess)
+        if (cudaFuncSetAttribute(tail::decoder_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tail::SMEM_BYTES) != cudaSuccess)
             return check_launch("decoder_tail: shared memory attribute");
         configured = true;
     }
     count_launches(1);
-    if (g_tail_impl == 1) {
-        const int grid = blocks < sm_count() ? (int)blocks : sm_count();
-        tail::ws::decoder_tail_ws_kernel<<<grid, tail::ws::NTHREADS, tail::ws::SMEM_BYTES, (cudaStream_t)stream>>>(
-            reinterpret_cast<const float4*>(y4), reinterpret_cast<const float4*>(wb_frag), out, P, h, w, tiles_x, tiles_y, (int)blocks);
-    } else {
-        tail::decoder_tail_kernel<<<(unsigned)blocks, tail::THREADS, tail::SMEM_BYTES, (cudaStream_t)stream>>>(
-            reinterpret_cast<const float4*>(y4), reinterpret_cast<const float4*>(wb_frag), out, P, h, w, tiles_x, tiles_y);
-    }
+    tail::decoder_tail_kernel<<<(unsigned)blocks, tail::THREADS, tail::SMEM_BYTES, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(y4), reinterpret_cast<const float4*>(wb_frag), out, P, h, w, tiles_x, tiles_y);
     return check_launch("decoder_tail_nhwc");
 }
 

@@ -428,7 +428,8 @@ def decoder_tail(y4, bias_a, weight_b, bias_b, weight_head, slope=0.2, taps=3, s
     frag = _tail_weight_fragments(weight_b)
     ha, hb, hh = _host_floats(bias_a), _host_floats(bias_b), _host_floats(weight_head)
     out = torch.empty((N, 1, 2 * h, 2 * w), device=y4.device, dtype=torch.float32)
-    with _span("decoder_tail", (y4.numel() + out.numel()) * 4):
+    # tensor-bound stage: the span carries FLOPs (16 -> 16 and 16 -> 1 3x3 convolutions); HBM bytes are y4 + out
+    with _span("decoder_tail", N * 4 * h * w * (16 * 16 * 9 + 16 * 9) * 2):
         rc = _lib.lib().riders_decoder_tail_nhwc(_ptr(y4), int(taps), N, h, w, _ptr(ha), _ptr(frag), _ptr(hb), _ptr(hh),
                                                  float(slope), 1 if sigmoid else 0, _ptr(out), _stream())
     _lib.check(rc, "riders_decoder_tail_nhwc")

@@ -20,6 +20,9 @@ for MODE in "$@"; do
     bench)
       timeout -s KILL 900 python bench.py --steps 5 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" | tee -a $OUT/status.txt
       tail -c 4000 $OUT/bench.json; tail -5 $OUT/bench.err ;;
+    benchnotail)
+      RIDERS_FUSED_TAIL=0 timeout -s KILL 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_notail.json 2> $OUT/bench_notail.err; echo "bench-notail rc=$?" | tee -a $OUT/status.txt
+      tail -c 1500 $OUT/bench_notail.json ;;
     bench3)
       RIDERS_SUBPIXEL_TAPS=3 timeout -s KILL 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_taps3.json 2> $OUT/bench_taps3.err; echo "bench-taps3 rc=$?" | tee -a $OUT/status.txt
       tail -c 1500 $OUT/bench_taps3.json ;;

@@ -137,12 +137,8 @@ def bench_tail(R=2048):
         t = 1 if taps == 2 else 0
         y4 = torch.randn((R, 64, 120 + t, 50 + t), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
         nbytes = (y4.numel() + R * 24000) * 4
-        from riders_b200 import _lib
-        for impl, name in ((1, "ws"), (0, "cta_per_tile")):
-            _lib.lib().riders_debug_set(b"tail_impl", impl)
-            ms, best = timeit(lambda: ops.decoder_tail(y4, ba, wb, bb, wh, 0.2, taps=taps, sigmoid=True), iters=5)
-            report("decoder_tail_%s_taps%d" % (name, taps), ms, best, nbytes, flops=flops, R=R)
-        _lib.lib().riders_debug_set(b"tail_impl", 1)
+        ms, best = timeit(lambda: ops.decoder_tail(y4, ba, wb, bb, wh, 0.2, taps=taps, sigmoid=True), iters=5)
+        report("decoder_tail_taps%d" % taps, ms, best, nbytes, flops=flops, R=R)
 
         def separate():
             z = ops.d2s_bias_act_concat(y4, ba, None, 0.2, taps=taps)
