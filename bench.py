@@ -250,7 +250,7 @@ def main():
     # ---------------------------------------------------------------- roofline of the dominant kernel
     # Every ops.* wrapper reports the algorithmic bytes (flops for LoFTR) of its call next to the CUDA events that
     # bracket it.  The gather additionally reads each frame's feature maps once.
-    TENSOR = {"loftr_transformer", "decoder_tail"}
+    TENSOR = {"loftr_transformer", "decoder_tail", "subpixel_conv"}
     stage_report = {}
     for name, (calls, ms, amount) in stages.items():
         bound = "tensor" if name in TENSOR else "hbm"

@@ -322,6 +322,14 @@ int riders_decoder_tail_nhwc(const float* y4, int taps, int N, int h, int w,
                              const float* bias_a_host, const float* wb_frag, const float* bias_b_host,
                              const float* wh_host, float slope, int apply_sigmoid,
                              float* out, void* stream);
+/* Sub-pixel phase convolution of the last decoder block in its 2x2-tap form (32 -> 4 x 16 channels), TF32, with the bias
+ * + LeakyReLU of the convolution that produced x fused into the operand load (deconv1.conv -> deconv0.deconv of
+ * MultiScaleDecoder, RCNet/networks.py:678-779): y4 (N, 64, h+1, w+1) = conv2x2(act(x + bias), W2, padding 1), x (N, 32, h, w)
+ * raw convolution output, both channels-last; bias_host (32, or NULL) in HOST memory; w_frag: DEVICE, W2 (64,32,2,2) in
+ * mma.m16n8k8 B-fragment order [K step = (u*2+v)*4 + c/8][N tile pair][lane][4], TF32-rounded (ops.subpixel_conv_act). */
+int riders_subpixel_conv_act_nhwc(const float* x, const float* bias_host, float slope, const float* w_frag,
+                                  int N, int h, int w, float* y4, void* stream);
+size_t riders_subpixel_conv_smem_bytes(int w);
 /* issue-rate probe of mma.sync.m16n8k8.tf32 (cycles for iters x 8 MMAs per warp, per CTA) */
 int riders_debug_mma_sync_rate(int warps, int iters, int ctas, long long* device_cycles, float* device_sink, void* stream);
 /* out = act(x + bias[c]) over `pixels` channels-last pixels of C channels (in place when out == x);

@@ -415,6 +415,38 @@ def _tail_weight_fragments(weight):
     return _cached(_FRAG_CACHE, weight, make)
 
 
+def _subpixel_weight_fragments(w2):
+    """(64,32,2,2) 2x2-tap phase kernels -> mma.m16n8k8 B fragments [K step][N tile pair][lane][4] = {b0, b1 of N tile 2 np,
+    b0, b1 of N tile 2 np + 1}, b0 = W2[n = 8 nt + g][c = 8 (ks % 4) + t][u][v], b1 the same at c + 4, tap (u, v) = ks // 4,
+    TF32-rounded; cached per parameter version."""
+    def make():
+        dev = w2.device
+        ks = torch.arange(16, device=dev).view(16, 1, 1, 1)
+        npair = torch.arange(4, device=dev).view(1, 4, 1, 1)
+        lane = torch.arange(32, device=dev).view(1, 1, 32, 1)
+        e = torch.arange(4, device=dev).view(1, 1, 1, 4)
+        tap = ks // 4
+        f = w2.detach().float()[(2 * npair + e // 2) * 8 + lane // 4, (ks % 4) * 8 + lane % 4 + 4 * (e % 2), tap // 2, tap % 2].contiguous()
+        return ((f.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    return _cached(_FRAG_CACHE, w2, make)
+
+
+def subpixel_conv_act(x_raw, bias, slope, w2):
+    """y4 (N,64,h+1,w+1) channels_last = conv2d(act(x_raw + bias), w2 (64,32,2,2), padding=1) on the TF32 tensor cores, the
+    bias + LeakyReLU(slope) of the convolution that produced ``x_raw`` (N,32,h,w) fused into the operand load."""
+    _need_cuda(x_raw, w2)
+    N, Cc, h, w = x_raw.shape
+    if not (_is_channels_last(x_raw) and x_raw.dtype == torch.float32 and Cc == 32 and tuple(w2.shape) == (64, 32, 2, 2)):
+        raise _lib.RidersError("subpixel_conv_act: needs a channels_last float32 (N,32,h,w) map and (64,32,2,2) kernels")
+    frag = _subpixel_weight_fragments(w2)
+    hb = _host_floats(bias)
+    y4 = torch.empty((N, 64, h + 1, w + 1), device=x_raw.device, dtype=torch.float32, memory_format=torch.channels_last)
+    with _span("subpixel_conv", N * (h + 1) * (w + 1) * 128 * 64 * 2):
+        rc = _lib.lib().riders_subpixel_conv_act_nhwc(_ptr(x_raw), _ptr(hb), float(slope), _ptr(frag), N, h, w, _ptr(y4), _stream())
+    _lib.check(rc, "riders_subpixel_conv_act_nhwc")
+    return y4
+
+
 def decoder_tail(y4, bias_a, weight_b, bias_b, weight_head, slope=0.2, taps=3, sigmoid=False):
     """Fused last decoder block + head (TF32): logits (N,1,2h,2w) = conv3x3(act(conv3x3(act(d2s(y4) + bias_a); weight_b)
     + bias_b); weight_head).  y4 (N,64,h,w) [taps=2: (N,64,h+1,w+1)] channels_last phase-convolution output."""

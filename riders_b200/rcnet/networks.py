@@ -239,7 +239,10 @@ class DecoderBlock(torch.nn.Module):
             # 2n+1 along one axis: the same sub-pixel convolution on x replicate-padded by one, read one pixel further, plus a
             # 3x1 / 1x3 phase convolution of the first column / row (the resized map never exists here either)
             if xp is None or tuple(xp.shape[2:]) != (x.shape[2] + sy, x.shape[3] + sx):
-                xp = F.pad(x, (sx, 0, sy, 0), mode='replicate').contiguous(memory_format=torch.channels_last)
+                if ops._is_channels_last(x) and x.shape[1] % 4 == 0:
+                    xp = ops.bias_act_pad(x, None, 1.0, sy, sx)        # identity pass = replicate pad, one streaming kernel
+                else:
+                    xp = F.pad(x, (sx, 0, sy, 0), mode='replicate').contiguous(memory_format=torch.channels_last)
             y4 = F.conv2d(xp, wsub, None, 1, 1)
             if sx:
                 yfirst = F.conv2d(x[:, :, :, 0:1].contiguous(memory_format=torch.channels_last), self._wcol, None, 1, (1, 0))
@@ -433,6 +436,7 @@ class MultiScaleDecoder(torch.nn.Module):
             setattr(self, 'deconv%d' % i, None)
         self.output0 = Conv2d(cin, output_channels, 3, 1, weight_initializer, output_func, False)
         self.fused_tail = os.environ.get('RIDERS_FUSED_TAIL', '1') != '0'      # ops.decoder_tail where TF32 is allowed
+        self.fused_sub = os.environ.get('RIDERS_FUSED_SUBCONV', '0') != '0'    # ops.subpixel_conv_act in front of it: opt-in, measured no faster than bias_act + cuDNN
 
     def _tail_ok(self, last, y, yp, shape):
         """Can ``ops.decoder_tail`` take over from the last block's sub-pixel convolution on?  (inference fast path, exact 2x,
@@ -446,6 +450,13 @@ class MultiScaleDecoder(torch.nn.Module):
                 and self.output0._act is None and not self.output0.use_batch_norm and head.bias is None
                 and tuple(head.weight.shape) == (1, 16, 3, 3) and head.stride == (1, 1) and head.padding == (1, 1))
 
+    def _sub_ok(self, last, shape):
+        """May the block in front of the last one hand over its raw convolution output (own TF32 phase-convolution kernel
+        with that block's bias + LeakyReLU fused in)?  Only on the fused-tail path with the 2x2-tap 32 -> 4 x 16 kernels."""
+        return (self.fused_sub and self.fused_tail and torch.backends.cudnn.allow_tf32 and not torch.is_grad_enabled()
+                and shape is not None and last.subpixel_taps == 2 and last._w2 is not None
+                and tuple(last._w2.shape) == (64, 32, 2, 2) and last.skip_channels == 0)
+
     def skip_lead_channels(self, n_skips):
         """Output channels of the up-convolution in front of each skip (skips[i] feeds block ``_order[n_skips-1-i]``,
         see ``forward``): the number of channels a placed skip must leave free in its concat buffer."""
@@ -457,6 +468,7 @@ class MultiScaleDecoder(torch.nn.Module):
         self.last_head_sigmoid = False
         n = len(skips) - 1
         y, yp = x, None
+        raw_bias = raw_slope = None                    # set when y is a RAW convolution output (see want_raw below)
         for i, name in enumerate(self._order[:-1]):
             # target of the NEXT block: when it is 2n+1 along one axis, this block's bias + activation pass writes the
             # replicate-padded operand of that block's sub-pixel convolution directly (DecoderBlock.forward, pad_out)
@@ -468,16 +480,34 @@ class MultiScaleDecoder(torch.nn.Module):
                 sy, sx = int(tgt[0] == 2 * cur[0] + 1), int(tgt[1] == 2 * cur[1] + 1)
                 if sy + sx == 1 and tgt[0] == 2 * cur[0] + sy and tgt[1] == 2 * cur[1] + sx:
                     pad_out = (sy, sx)
-            out = getattr(self, name)(y, skips[n], xp=yp, pad_out=pad_out)
-            y, yp = out if isinstance(out, tuple) else (out, None)
+            # the block in front of the fused tail hands over its RAW convolution output: its bias + LeakyReLU are applied
+            # by the tail's own phase-convolution kernel while it stages its operand (ops.subpixel_conv_act)
+            want_raw = (i == len(self._order) - 2 and pad_out is None and getattr(self, name).conv._fused_slope is not None
+                        and self._sub_ok(getattr(self, self._order[-1]), shape))
+            out = getattr(self, name)(y, skips[n], xp=yp, pad_out=pad_out, raw=want_raw)
+            if want_raw:
+                y, raw_bias, raw_slope = out
+                yp = None
+            else:
+                y, yp = out if isinstance(out, tuple) else (out, None)
             n -= 1
         last = getattr(self, self._order[-1])
         head = self.output0.conv
+        if raw_slope is not None and not (n != 0 and self._tail_ok(last, y, yp, shape) and raw_slope is not None
+                                          and 0.0 <= raw_slope <= 1.0 and y.shape[1] == 32):
+            if ops._is_channels_last(y):                                                   # not fusable after all
+                y = ops.bias_act_(y, raw_bias, raw_slope) if (raw_bias is not None or raw_slope != 1.0) else y
+            else:
+                y = F.leaky_relu(y if raw_bias is None else y + raw_bias.view(1, -1, 1, 1), raw_slope)
+            raw_bias = raw_slope = None
         if (n != 0 and self.fused_tail and torch.backends.cudnn.allow_tf32 and self._tail_ok(last, y, yp, shape)):
             # TF32 flow (torch's default): the whole tail - depth-to-space + bias + LeakyReLU, the block's 16 -> 16
             # convolution, bias + LeakyReLU, the 16 -> 1 head - in ONE kernel fed by the sub-pixel phase convolution
             taps = 2 if (last.subpixel_taps == 2 and last._w2 is not None) else 3
-            y4 = F.conv2d(y, last._w2 if taps == 2 else last._w4, None, 1, 1)
+            if raw_slope is not None:
+                y4 = ops.subpixel_conv_act(y, raw_bias, raw_slope, last._w2)          # previous block's bias + LeakyReLU fused in
+            else:
+                y4 = F.conv2d(y, last._w2 if taps == 2 else last._w4, None, 1, 1)
             self.last_head_sigmoid = bool(head_sigmoid)
             return [ops.decoder_tail(y4, last.deconv.conv.conv.bias, last.conv.conv.weight, last.conv.conv.bias, head.weight,
                                      _LEAK, taps=taps, sigmoid=head_sigmoid)]

@@ -690,7 +690,7 @@ def test_subpixel_decoder_block_odd_targets(hw, target, placed, taps, monkeypatc
 
 def test_decoder_hands_padded_maps_to_odd_blocks(monkeypatch):
     """MultiScaleDecoder at RC-Net's sizes (7x3 -> 15x6 -> 30x12 -> 60x25 -> 120x50 -> 240x100): the block in front of the
-    60x25 one returns its output replicate-padded (bias_act_pad), nothing calls F.pad on a big map, same logits."""
+    60x25 one returns its output replicate-padded (bias_act_pad), nothing calls F.pad, same logits."""
     from riders_b200.rcnet import networks
     torch.backends.cudnn.allow_tf32 = False
     torch.manual_seed(11)
@@ -716,7 +716,8 @@ def test_decoder_hands_padded_maps_to_odd_blocks(monkeypatch):
         monkeypatch.setattr(ops, "bias_act_pad", lambda t, *a, **k: (calls.append(("bap", tuple(t.shape))), real_bap(t, *a, **k))[1])
         got = dec(xc, sc, shape=(240, 100))[-1]
     assert ("bap", (N, 32, 30, 12)) in calls, calls
-    assert [c for c in calls if c[0] == "pad"] == [("pad", (N, 64, 7, 3))], calls          # only the tiny latent is padded by torch
+    assert not [c for c in calls if c[0] == "pad"], calls                                   # torch's pad kernel is never used
+    assert ("bap", (N, 64, 7, 3)) in calls, calls                                          # the latent: identity bias_act_pad
     np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=2e-4, atol=2e-5)
 
 
@@ -756,12 +757,35 @@ def test_decoder_tail_matches_the_three_passes(hw, taps):
     np.testing.assert_allclose(sg.cpu().numpy(), torch.sigmoid(got).cpu().numpy(), rtol=2e-6, atol=1e-7)
 
 
+@pytest.mark.parametrize("hw", [(120, 50), (7, 9), (13, 30)])
+def test_subpixel_conv_act_matches_torch(hw):
+    """ops.subpixel_conv_act: conv2x2(act(x + bias), W2, padding 1) on the TF32 tensor cores == fp32 convolution of the
+    TF32-rounded operands (one rounding point: 1e-5 of the scale), and within TF32 accuracy of the pure fp32 result."""
+    F = torch.nn.functional
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device=DEV).manual_seed(hw[0])
+    N, (h, w) = 3, hw
+    x = torch.randn((N, 32, h, w), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    b = torch.randn(32, device=DEV, generator=g) * 0.3
+    w2 = torch.randn((64, 32, 2, 2), device=DEV, generator=g) * 0.1
+    xa = F.leaky_relu(x + b.view(1, -1, 1, 1), 0.2)
+    ref32 = F.conv2d(xa, w2, None, 1, 1)
+    reft = F.conv2d(_tf32_rna(xa), _tf32_rna(w2), None, 1, 1)
+    got = ops.subpixel_conv_act(x, b, 0.2, w2)
+    assert got.shape == ref32.shape == (N, 64, h + 1, w + 1) and got.is_contiguous(memory_format=torch.channels_last)
+    scale = float(ref32.abs().max())
+    np.testing.assert_allclose(got.cpu().numpy(), reft.cpu().numpy(), rtol=1e-4, atol=1e-5 * scale)
+    assert float((got - ref32).abs().max()) < 2e-3 * scale
+    got1 = ops.subpixel_conv_act(xa, None, 1.0, w2)                      # already activated input: identity "activation"
+    np.testing.assert_allclose(got1.cpu().numpy(), reft.cpu().numpy(), rtol=1e-4, atol=1e-5 * scale)
+
+
 def test_decoder_uses_the_fused_tail_only_where_tf32_is_allowed(monkeypatch):
     """MultiScaleDecoder: with torch.backends.cudnn.allow_tf32 the tail runs in ops.decoder_tail and agrees with the cuDNN
     TF32 passes to TF32 accuracy; without it the fp32 passes run (the 1e-4 parity tests above are untouched)."""
     from riders_b200.rcnet import networks
     torch.manual_seed(12)
-    dec = networks.MultiScaleDecoder(64, 1, 1, [32, 32, 16, 16, 16], [32, 32, 16, 8, 0], 'kaiming_uniform', 'leaky_relu', 'linear',
+    dec = networks.MultiScaleDecoder(64, 1, 1, [32, 32, 16, 32, 16], [32, 32, 16, 8, 0], 'kaiming_uniform', 'leaky_relu', 'linear',
                                      True, 'up').to(DEV).eval()
     N = 3
     x = torch.randn((N, 64, 7, 3), device=DEV).contiguous(memory_format=torch.channels_last)
@@ -775,23 +799,29 @@ def test_decoder_uses_the_fused_tail_only_where_tf32_is_allowed(monkeypatch):
         for m in dec.modules():
             if isinstance(m, networks.DecoderBlock):
                 m.fold_upsample_()
-        calls = []
-        real = ops.decoder_tail
+        calls, subs = [], []
+        real, real_sub = ops.decoder_tail, ops.subpixel_conv_act
         monkeypatch.setattr(ops, "decoder_tail", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+        monkeypatch.setattr(ops, "subpixel_conv_act", lambda *a, **k: (subs.append(1), real_sub(*a, **k))[1])
         torch.backends.cudnn.allow_tf32 = False
         ref = dec(x, skips, shape=(240, 100))[-1]
-        assert not calls
+        assert not calls and not subs
         torch.backends.cudnn.allow_tf32 = True
         try:
-            got = dec(x, skips, shape=(240, 100))[-1]
-            assert len(calls) == 1
+            dec.fused_sub = True                                      # opt-in (RIDERS_FUSED_SUBCONV=1)
+            got = dec(x, skips, shape=(240, 100))[-1]                 # own phase convolution (+ fused activation) + tail
+            assert len(calls) == 1 and len(subs) == 1
+            dec.fused_sub = False
+            got2 = dec(x, skips, shape=(240, 100))[-1]                # cuDNN phase convolution + tail
+            assert len(calls) == 2 and len(subs) == 1
             dec.fused_tail = False
-            sep = dec(x, skips, shape=(240, 100))[-1]
-            assert len(calls) == 1
+            sep = dec(x, skips, shape=(240, 100))[-1]                 # the separate passes
+            assert len(calls) == 2 and len(subs) == 1
         finally:
             torch.backends.cudnn.allow_tf32 = False
     scale = float(ref.abs().max())
-    assert float((got - ref).abs().max()) < 5e-3 * scale and float((sep - ref).abs().max()) < 5e-3 * scale
+    for t in (got, got2, sep):
+        assert float((t - ref).abs().max()) < 5e-3 * scale
     assert float((got - sep).abs().max()) < 5e-3 * scale
 
 

@@ -23,6 +23,9 @@ for MODE in "$@"; do
     benchnotail)
       RIDERS_FUSED_TAIL=0 timeout -s KILL 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_notail.json 2> $OUT/bench_notail.err; echo "bench-notail rc=$?" | tee -a $OUT/status.txt
       tail -c 1500 $OUT/bench_notail.json ;;
+    benchsub)
+      RIDERS_FUSED_SUBCONV=1 timeout -s KILL 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_sub.json 2> $OUT/bench_sub.err; echo "bench-sub rc=$?" | tee -a $OUT/status.txt
+      tail -c 1500 $OUT/bench_sub.json ;;
     bench3)
       RIDERS_SUBPIXEL_TAPS=3 timeout -s KILL 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_taps3.json 2> $OUT/bench_taps3.err; echo "bench-taps3 rc=$?" | tee -a $OUT/status.txt
       tail -c 1500 $OUT/bench_taps3.json ;;

@@ -147,6 +147,24 @@ def bench_tail(R=2048):
         report("separate_d2s_cudnn_head_taps%d" % taps, ms, best, nbytes, flops=flops, R=R)
 
 
+def bench_subconv(R=2048):
+    """Own TF32 phase convolution (bias + LeakyReLU of the producer fused in) against bias_act_ + cuDNN's 2x2 convolution."""
+    import torch.nn.functional as F
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    g = torch.Generator(device=DEV).manual_seed(0)
+    x = torch.randn((R, 32, 120, 50), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    b = torch.randn(32, device=DEV, generator=g) * 0.1
+    w2 = (torch.randn((64, 32, 2, 2), device=DEV, generator=g) * 0.1).contiguous(memory_format=torch.channels_last)
+    flops = R * 121 * 51 * 128 * 64 * 2
+    nbytes = (x.numel() + R * 64 * 121 * 51) * 4
+    ms, best = timeit(lambda: ops.subpixel_conv_act(x, b, 0.2, w2), iters=5)
+    report("subpixel_conv_act", ms, best, nbytes, flops=flops, R=R)
+    xc = x.clone(memory_format=torch.channels_last)
+    ms, best = timeit(lambda: F.conv2d(ops.bias_act_(xc, b, 0.2), w2, None, 1, 1), iters=5)
+    report("bias_act_plus_cudnn_conv2x2", ms, best, nbytes + 2 * x.numel() * 4, flops=flops, R=R)
+
+
 def bench_mmasync():
     """Issue rate of mma.sync.m16n8k8.tf32 (registers only): cycles per MMA per SM for 4..16 warps per SM."""
     from riders_b200 import _lib
