@@ -244,25 +244,39 @@ decoder_tail_kernel(const float4* __restrict__ y4, const float4* __restrict__ wb
 
 // issue-rate probe for the warp-level TF32 MMA (riders_debug_mma_sync_rate): `warps` warps per CTA, one CTA per SM,
 // 8 independent accumulators per warp, registers only
+// MODE 0: all MMAs share one A and one B fragment (operand registers re-used back to back); MODE 1: every MMA of an
+// iteration has its own A and B registers, as in a real kernel.  CHAINS independent accumulators per warp.
+template <int CHAINS, int MODE>
 __global__ void __launch_bounds__(1024, 1)
 mma_sync_rate_kernel(int iters, long long* cycles, float* sink) {
-    float acc[8][4];
+    float acc[CHAINS][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < CHAINS; ++i)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
-    uint32_t a[4] = {0x3f800000u + threadIdx.x, 0x3f800000u, 0x3f000000u, 0x3f800000u};
-    const uint32_t b0 = 0x3f800000u, b1 = 0x3f000000u + threadIdx.x;
+    uint32_t a[8][4], b[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) a[i][e] = 0x3f800000u + threadIdx.x * 8 + (MODE ? i * 4 + e : e) + iters;
+        b[i][0] = 0x3f000000u + threadIdx.x + (MODE ? i : 0) + iters;
+        b[i][1] = 0x3f400000u + threadIdx.x * 3 + (MODE ? i : 0) + iters;
+    }
     __syncthreads();
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mma_tf32(acc[i], a, b0, b1);
+        for (int r = 0; r < 8 / CHAINS; ++r)
+#pragma unroll
+            for (int i = 0; i < CHAINS; ++i) {
+                const int o = MODE ? r * CHAINS + i : 0;
+                mma_tf32(acc[i], a[o], b[o][0], b[o][1]);
+            }
     }
     const long long t1 = clock64();
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += acc[i][0] + acc[i][1] + acc[i][2] + acc[i][3];
+    for (int i = 0; i < CHAINS; ++i) s += acc[i][0] + acc[i][1] + acc[i][2] + acc[i][3];
     if (s == 12345.678f) sink[0] = s;
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
@@ -308,8 +322,17 @@ extern "C" int riders_decoder_tail_nhwc(const float* y4, int taps, int N, int h,
 
 extern "C" int riders_debug_mma_sync_rate(int warps, int iters, int ctas, long long* device_cycles, float* device_sink, void* stream) {
     using namespace riders;
+    // warps: bits 0..7 warps per CTA; bits 8..11 independent accumulators per warp (1, 2, 4, 8; 0 = 8); bit 12: distinct
+    // operand registers per MMA
+    const int chains = (warps >> 8) & 15 ? (warps >> 8) & 15 : 8, mode = (warps >> 12) & 1;
+    warps &= 255;
     RIDERS_REQUIRE(warps >= 1 && warps <= 32 && iters > 0 && ctas > 0 && device_cycles && device_sink, "debug_mma_sync_rate: bad arguments");
+    RIDERS_REQUIRE(chains == 1 || chains == 2 || chains == 4 || chains == 8, "debug_mma_sync_rate: chains must be 1, 2, 4 or 8");
     count_launches(1);
-    tail::mma_sync_rate_kernel<<<ctas, warps * 32, 0, (cudaStream_t)stream>>>(iters, device_cycles, device_sink);
+    cudaStream_t st = (cudaStream_t)stream;
+#define RIDERS_RATE(C_, M_) tail::mma_sync_rate_kernel<C_, M_><<<ctas, warps * 32, 0, st>>>(iters, device_cycles, device_sink)
+    if (mode) { if (chains == 1) RIDERS_RATE(1, 1); else if (chains == 2) RIDERS_RATE(2, 1); else if (chains == 4) RIDERS_RATE(4, 1); else RIDERS_RATE(8, 1); }
+    else      { if (chains == 1) RIDERS_RATE(1, 0); else if (chains == 2) RIDERS_RATE(2, 0); else if (chains == 4) RIDERS_RATE(4, 0); else RIDERS_RATE(8, 0); }
+#undef RIDERS_RATE
     return check_launch("debug_mma_sync_rate");
 }

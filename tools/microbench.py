@@ -166,19 +166,22 @@ def bench_subconv(R=2048):
 
 
 def bench_mmasync():
-    """Issue rate of mma.sync.m16n8k8.tf32 (registers only): cycles per MMA per SM for 4..16 warps per SM."""
+    """Issue rate / latency of mma.sync.m16n8k8.tf32 (registers only): chains = independent accumulators per warp; mode 1 gives
+    every MMA its own operand registers (a real kernel), mode 0 re-uses one A / B fragment."""
     from riders_b200 import _lib
     cyc = torch.zeros(148, dtype=torch.int64, device=DEV)
     sink = torch.zeros(4, device=DEV)
     iters = 4096
-    for warps in (4, 8, 12, 16):
-        for ctas in (1, 148):
-            _lib.check(_lib.lib().riders_debug_mma_sync_rate(warps, iters, ctas, cyc.data_ptr(), sink.data_ptr(), None), "mma_sync_rate")
-            torch.cuda.synchronize()
-            c = float(cyc[:ctas].double().mean())
-            per_sm = c / (iters * 8 * warps)
-            print(json.dumps({"kernel": "mma_sync_m16n8k8_tf32", "warps": warps, "ctas": ctas, "cycles_per_mma_per_sm": round(per_sm, 3),
-                              "mac_per_cycle_per_sm": round(1024 / per_sm, 1)}), flush=True)
+    for mode in (0, 1):
+        for chains in (1, 4, 8):
+            for warps in (4, 8, 16):
+                _lib.check(_lib.lib().riders_debug_mma_sync_rate(warps | (chains << 8) | (mode << 12), iters, 148, cyc.data_ptr(), sink.data_ptr(), None), "mma_sync_rate")
+                torch.cuda.synchronize()
+                c = float(cyc.double().mean())
+                per_sm = c / (iters * 8 * warps)
+                print(json.dumps({"kernel": "mma_sync_m16n8k8_tf32", "distinct_operands": mode, "chains_per_warp": chains, "warps": warps,
+                                  "cycles_per_mma_per_sm": round(per_sm, 3), "cycles_per_mma_per_warp": round(c / (iters * 8), 2),
+                                  "mac_per_cycle_per_sm": round(1024 / per_sm, 1)}), flush=True)
 
 
 def bench_loftr(N=4096):
