@@ -330,6 +330,11 @@ int riders_decoder_tail_nhwc(const float* y4, int taps, int N, int h, int w,
 int riders_subpixel_conv_act_nhwc(const float* x, const float* bias_host, float slope, const float* w_frag,
                                   int N, int h, int w, float* y4, void* stream);
 size_t riders_subpixel_conv_smem_bytes(int w);
+/* The phase convolution itself on the 5th-generation tensor cores (TMA -> tcgen05.mma kind::tf32 -> TMEM), for an ALREADY
+ * ACTIVATED input: y4 (N, 64, h+1, w+1) = conv2x2(x, W2, padding 1), x (N, 32, h, w), both channels-last, w <= 55.
+ * w_pack: DEVICE, W2 (64,32,2,2) as four K-major SWIZZLE_128B B slabs [tap = u*2+v][n = 64 rows][c = 32 tf32], TF32-rounded
+ * (ops.subpixel_conv_tc builds it).  Replaces cuDNN's generic implicit GEMM for this K = 128, N = 64 shape.            */
+int riders_subpixel_conv_tc_nhwc(const float* x, const float* w_pack, int N, int h, int w, float* y4, void* stream);
 /* issue-rate probe of mma.sync.m16n8k8.tf32 (cycles for iters x 8 MMAs per warp, per CTA) */
 int riders_debug_mma_sync_rate(int warps, int iters, int ctas, long long* device_cycles, float* device_sink, void* stream);
 /* out = act(x + bias[c]) over `pixels` channels-last pixels of C channels (in place when out == x);

@@ -67,6 +67,7 @@ SIGNATURES = {
     "riders_bias_act_pad_nhwc": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, cf, vp, vp]),
     "riders_decoder_tail_nhwc": (ci, [vp, ci, ci, ci, ci, vp, vp, vp, vp, cf, ci, vp, vp]),
     "riders_subpixel_conv_act_nhwc": (ci, [vp, vp, cf, vp, ci, ci, ci, vp, vp]),
+    "riders_subpixel_conv_tc_nhwc": (ci, [vp, vp, ci, ci, ci, vp, vp]),
     "riders_subpixel_conv_smem_bytes": (C.c_size_t, [ci]),
     "riders_debug_mma_sync_rate": (ci, [ci, ci, ci, vp, vp, vp]),
     "riders_debug_set": (ci, [C.c_char_p, ci]),

@@ -431,18 +431,52 @@ def _subpixel_weight_fragments(w2):
     return _cached(_FRAG_CACHE, w2, make)
 
 
+_PACK_CACHE = {}
+
+
+def _subpixel_tc_weights(w2):
+    """(64,32,2,2) phase kernels -> four K-major SWIZZLE_128B B slabs for tcgen05 [tap = u*2+v][n][c]: 128-byte rows (32 tf32),
+    8-row groups of 1024 B, 16-byte chunk index XOR (n & 7); TF32-rounded; cached per parameter version."""
+    def make():
+        dev = w2.device
+        tap = torch.arange(4, device=dev).view(4, 1, 1)
+        n = torch.arange(64, device=dev).view(1, 64, 1)
+        k = torch.arange(32, device=dev).view(1, 1, 32)
+        val = w2.detach().float()[n, k, tap // 2, tap % 2]
+        val = ((val.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+        off = tap * 2048 + (n >> 3) * 256 + (n & 7) * 32 + (((k >> 2) ^ (n & 7)) << 2) + (k & 3)        # in floats
+        out = torch.empty(4 * 64 * 32, device=dev, dtype=torch.float32)
+        out[off.reshape(-1)] = val.reshape(-1)
+        return out
+    return _cached(_PACK_CACHE, w2, make)
+
+
+def subpixel_conv_tc(x, w2):
+    """y4 (N,64,h+1,w+1) channels_last = conv2d(x, w2 (64,32,2,2), padding=1) in TF32 on the 5th-generation tensor cores
+    (TMA-fed tcgen05.mma, accumulator in TMEM); x (N,32,h,w) channels_last, already activated, w <= 54."""
+    _need_cuda(x, w2)
+    N, Cc, h, w = x.shape
+    if not (_is_channels_last(x) and x.dtype == torch.float32 and Cc == 32 and tuple(w2.shape) == (64, 32, 2, 2) and w <= 54):
+        raise _lib.RidersError("subpixel_conv_tc: needs a channels_last float32 (N,32,h,w<=54) map and (64,32,2,2) kernels")
+    y4 = torch.empty((N, 64, h + 1, w + 1), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+    with _span("subpixel_conv", N * (h + 1) * (w + 1) * 128 * 64 * 2):
+        rc = _lib.lib().riders_subpixel_conv_tc_nhwc(_ptr(x), _ptr(_subpixel_tc_weights(w2)), N, h, w, _ptr(y4), _stream())
+    _lib.check(rc, "riders_subpixel_conv_tc_nhwc")
+    return y4
+
+
 def subpixel_conv_act(x_raw, bias, slope, w2):
-    """y4 (N,64,h+1,w+1) channels_last = conv2d(act(x_raw + bias), w2 (64,32,2,2), padding=1) on the TF32 tensor cores, the
-    bias + LeakyReLU(slope) of the convolution that produced ``x_raw`` (N,32,h,w) fused into the operand load."""
+    """y4 (N,64,h+1,w+1) channels_last = conv2d(act(x_raw + bias), w2 (64,32,2,2), padding=1) in TF32 (warp-level mma.sync),
+    the bias + LeakyReLU(slope) of the convolution that produced ``x_raw`` (N,32,h,w) fused into the operand load."""
     _need_cuda(x_raw, w2)
     N, Cc, h, w = x_raw.shape
     if not (_is_channels_last(x_raw) and x_raw.dtype == torch.float32 and Cc == 32 and tuple(w2.shape) == (64, 32, 2, 2)):
         raise _lib.RidersError("subpixel_conv_act: needs a channels_last float32 (N,32,h,w) map and (64,32,2,2) kernels")
-    frag = _subpixel_weight_fragments(w2)
     hb = _host_floats(bias)
     y4 = torch.empty((N, 64, h + 1, w + 1), device=x_raw.device, dtype=torch.float32, memory_format=torch.channels_last)
     with _span("subpixel_conv", N * (h + 1) * (w + 1) * 128 * 64 * 2):
-        rc = _lib.lib().riders_subpixel_conv_act_nhwc(_ptr(x_raw), _ptr(hb), float(slope), _ptr(frag), N, h, w, _ptr(y4), _stream())
+        rc = _lib.lib().riders_subpixel_conv_act_nhwc(_ptr(x_raw), _ptr(hb), float(slope), _ptr(_subpixel_weight_fragments(w2)),
+                                                      N, h, w, _ptr(y4), _stream())
     _lib.check(rc, "riders_subpixel_conv_act_nhwc")
     return y4
 

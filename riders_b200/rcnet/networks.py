@@ -299,6 +299,13 @@ class ResNetEncoder(torch.nn.Module):
                 setattr(self, name, None)
 
     def forward(self, x):
+        pad = getattr(self, 'stem_pad_channels', 0)            # set by RCNetModel.optimize_for_inference()
+        if pad and x.shape[1] + pad == self.conv1.conv.in_channels:
+            xp = torch.empty((x.shape[0], x.shape[1] + pad) + tuple(x.shape[2:]), device=x.device, dtype=x.dtype,
+                             memory_format=torch.channels_last)
+            xp[:, :x.shape[1]].copy_(x)
+            xp[:, x.shape[1]:].zero_()
+            x = xp
         feats = [self.conv1(x)]
         y = self.max_pool(feats[0])
         for name in self._stages:
@@ -436,6 +443,7 @@ class MultiScaleDecoder(torch.nn.Module):
             setattr(self, 'deconv%d' % i, None)
         self.output0 = Conv2d(cin, output_channels, 3, 1, weight_initializer, output_func, False)
         self.fused_tail = os.environ.get('RIDERS_FUSED_TAIL', '1') != '0'      # ops.decoder_tail where TF32 is allowed
+        self.subconv_tc = os.environ.get('RIDERS_SUBCONV_TC', '0') != '0'      # ops.subpixel_conv_tc instead of cuDNN's 2x2 convolution: opt-in (both sit at the HBM bound of this write-heavy shape, cuDNN 10-15 % ahead)
         self.fused_sub = os.environ.get('RIDERS_FUSED_SUBCONV', '0') != '0'    # ops.subpixel_conv_act in front of it: opt-in, measured no faster than bias_act + cuDNN
 
     def _tail_ok(self, last, y, yp, shape):
@@ -506,6 +514,9 @@ class MultiScaleDecoder(torch.nn.Module):
             taps = 2 if (last.subpixel_taps == 2 and last._w2 is not None) else 3
             if raw_slope is not None:
                 y4 = ops.subpixel_conv_act(y, raw_bias, raw_slope, last._w2)          # previous block's bias + LeakyReLU fused in
+            elif (self.subconv_tc and taps == 2 and tuple(last._w2.shape) == (64, 32, 2, 2) and y.shape[3] <= 54
+                  and ops._is_channels_last(y)):
+                y4 = ops.subpixel_conv_tc(y, last._w2)                                # TMA -> tcgen05 -> TMEM phase convolution
             else:
                 y4 = F.conv2d(y, last._w2 if taps == 2 else last._w4, None, 1, 1)
             self.last_head_sigmoid = bool(head_sigmoid)

@@ -759,8 +759,8 @@ def test_decoder_tail_matches_the_three_passes(hw, taps):
 
 @pytest.mark.parametrize("hw", [(120, 50), (7, 9), (13, 30)])
 def test_subpixel_conv_act_matches_torch(hw):
-    """ops.subpixel_conv_act: conv2x2(act(x + bias), W2, padding 1) on the TF32 tensor cores == fp32 convolution of the
-    TF32-rounded operands (one rounding point: 1e-5 of the scale), and within TF32 accuracy of the pure fp32 result."""
+    """ops.subpixel_conv_act (mma.sync): conv2x2(act(x + bias), W2, padding 1) on the TF32 tensor cores == fp32 convolution
+    of the TF32-rounded operands (one rounding point: 1e-5 of the scale), and within TF32 accuracy of the pure fp32 result."""
     F = torch.nn.functional
     torch.backends.cudnn.allow_tf32 = False
     g = torch.Generator(device=DEV).manual_seed(hw[0])
@@ -778,6 +778,28 @@ def test_subpixel_conv_act_matches_torch(hw):
     assert float((got - ref32).abs().max()) < 2e-3 * scale
     got1 = ops.subpixel_conv_act(xa, None, 1.0, w2)                      # already activated input: identity "activation"
     np.testing.assert_allclose(got1.cpu().numpy(), reft.cpu().numpy(), rtol=1e-4, atol=1e-5 * scale)
+
+
+@pytest.mark.parametrize("hw,N", [((120, 50), 3), ((7, 9), 2), ((13, 30), 5), ((120, 50), 40)])
+def test_subpixel_conv_tc_matches_torch(hw, N):
+    """ops.subpixel_conv_tc (TMA -> tcgen05.mma kind::tf32 -> TMEM): conv2x2(x, W2, padding 1).  The tensor core truncates
+    the fp32 activations to TF32 (W2 is rounded when packed): exactly the fp32 convolution of those operands (1e-5 of the
+    scale) and within TF32 accuracy of the pure fp32 result; several tiles per persistent CTA in the N = 40 case."""
+    F = torch.nn.functional
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device=DEV).manual_seed(hw[0] + N)
+    h, w = hw
+    x = torch.randn((N, 32, h, w), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    w2 = torch.randn((64, 32, 2, 2), device=DEV, generator=g) * 0.1
+    ref32 = F.conv2d(x, w2, None, 1, 1)
+    x_trunc = (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+    reft = F.conv2d(x_trunc, _tf32_rna(w2), None, 1, 1)
+    got = ops.subpixel_conv_tc(x, w2)
+    assert got.shape == ref32.shape == (N, 64, h + 1, w + 1) and got.is_contiguous(memory_format=torch.channels_last)
+    scale = float(ref32.abs().max())
+    np.testing.assert_allclose(got.cpu().numpy(), reft.cpu().numpy(), rtol=1e-4, atol=1e-5 * scale)
+    assert float((got - ref32).abs().max()) < 3e-3 * scale
+    assert torch.equal(got, ops.subpixel_conv_tc(x, w2))                 # deterministic
 
 
 def test_decoder_uses_the_fused_tail_only_where_tf32_is_allowed(monkeypatch):
@@ -799,8 +821,9 @@ def test_decoder_uses_the_fused_tail_only_where_tf32_is_allowed(monkeypatch):
         for m in dec.modules():
             if isinstance(m, networks.DecoderBlock):
                 m.fold_upsample_()
-        calls, subs = [], []
-        real, real_sub = ops.decoder_tail, ops.subpixel_conv_act
+        calls, subs, tcs = [], [], []
+        real, real_sub, real_tc = ops.decoder_tail, ops.subpixel_conv_act, ops.subpixel_conv_tc
+        monkeypatch.setattr(ops, "subpixel_conv_tc", lambda *a, **k: (tcs.append(1), real_tc(*a, **k))[1])
         monkeypatch.setattr(ops, "decoder_tail", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
         monkeypatch.setattr(ops, "subpixel_conv_act", lambda *a, **k: (subs.append(1), real_sub(*a, **k))[1])
         torch.backends.cudnn.allow_tf32 = False
@@ -809,18 +832,23 @@ def test_decoder_uses_the_fused_tail_only_where_tf32_is_allowed(monkeypatch):
         torch.backends.cudnn.allow_tf32 = True
         try:
             dec.fused_sub = True                                      # opt-in (RIDERS_FUSED_SUBCONV=1)
-            got = dec(x, skips, shape=(240, 100))[-1]                 # own phase convolution (+ fused activation) + tail
-            assert len(calls) == 1 and len(subs) == 1
+            got = dec(x, skips, shape=(240, 100))[-1]                 # mma.sync phase convolution (+ fused activation) + tail
+            assert len(calls) == 1 and len(subs) == 1 and not tcs
             dec.fused_sub = False
-            got2 = dec(x, skips, shape=(240, 100))[-1]                # cuDNN phase convolution + tail
-            assert len(calls) == 2 and len(subs) == 1
+            dec.subconv_tc = True                                     # opt-in (RIDERS_SUBCONV_TC=1)
+            got2 = dec(x, skips, shape=(240, 100))[-1]                # tcgen05 phase convolution + tail
+            assert len(calls) == 2 and len(subs) == 1 and len(tcs) == 1
+            dec.subconv_tc = False
+            got3 = dec(x, skips, shape=(240, 100))[-1]                # cuDNN phase convolution + tail
+            assert len(calls) == 3 and len(subs) == 1 and len(tcs) == 1
+            calls.pop()
             dec.fused_tail = False
             sep = dec(x, skips, shape=(240, 100))[-1]                 # the separate passes
             assert len(calls) == 2 and len(subs) == 1
         finally:
             torch.backends.cudnn.allow_tf32 = False
     scale = float(ref.abs().max())
-    for t in (got, got2, sep):
+    for t in (got, got2, got3, sep):
         assert float((t - ref).abs().max()) < 5e-3 * scale
     assert float((got - sep).abs().max()) < 5e-3 * scale
 

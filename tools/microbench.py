@@ -158,8 +158,12 @@ def bench_subconv(R=2048):
     w2 = (torch.randn((64, 32, 2, 2), device=DEV, generator=g) * 0.1).contiguous(memory_format=torch.channels_last)
     flops = R * 121 * 51 * 128 * 64 * 2
     nbytes = (x.numel() + R * 64 * 121 * 51) * 4
+    ms, best = timeit(lambda: ops.subpixel_conv_tc(x, w2), iters=5)
+    report("subpixel_conv_tc (conv only)", ms, best, nbytes, flops=flops, R=R)
+    ms, best = timeit(lambda: F.conv2d(x, w2, None, 1, 1), iters=5)
+    report("cudnn_conv2x2 (conv only)", ms, best, nbytes, flops=flops, R=R)
     ms, best = timeit(lambda: ops.subpixel_conv_act(x, b, 0.2, w2), iters=5)
-    report("subpixel_conv_act", ms, best, nbytes, flops=flops, R=R)
+    report("subpixel_conv_act_mma (bias+act fused)", ms, best, nbytes, flops=flops, R=R)
     xc = x.clone(memory_format=torch.channels_last)
     ms, best = timeit(lambda: F.conv2d(ops.bias_act_(xc, b, 0.2), w2, None, 1, 1), iters=5)
     report("bias_act_plus_cudnn_conv2x2", ms, best, nbytes + 2 * x.numel() * 4, flops=flops, R=R)

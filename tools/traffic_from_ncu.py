@@ -27,7 +27,7 @@ for r in csv.DictReader(lines):
     mul = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1, "ms": 1e3}.get(unit, 1)
     d[r["Metric Name"]] = v * mul
 launches = list(rows.values())
-marker = sys.argv[2] if len(sys.argv) > 2 else "replication_pad"
+marker = sys.argv[2] if len(sys.argv) > 2 else "prologue_flag"
 marks = [i for i, l in enumerate(launches) if marker in l["name"]]
 if marks:
     launches = launches[marks[-1]:]
