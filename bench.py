@@ -233,15 +233,23 @@ def main():
                           "stages": {k: v[1] / args.steps for k, v in stages.items()}}), flush=True)
         rdist.shutdown()
         return 0
+    # The public call a user makes: RadarDepthPipeline.submit_host (pinned host buffers in, pinned host buffers out).  Two
+    # steps are in flight: the copies of step k + 1 / k - 1 ride on copy streams under the compute of step k, and the
+    # caller reads step k - 1's host result (handle.wait()) every step.  Every step's H2D and D2H are inside the timed region.
     for _ in range(2):
-        pipe.run_host(host["images"], host["points"], offsets, host["mono"], host["sparse"], device)
+        pipe.submit_host(host["images"], host["points"], offsets, host["mono"], host["sparse"], device).wait()
     torch.cuda.synchronize()
     rdist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    pending = None
     for _ in range(args.steps):
-        hout, h2d, d2h = pipe.run_host(host["images"], host["points"], offsets, host["mono"], host["sparse"], device)
-        torch.cuda.current_stream().synchronize()              # the caller reads the host result every step
+        handle = pipe.submit_host(host["images"], host["points"], offsets, host["mono"], host["sparse"], device)
+        if pending is not None:
+            hout, h2d, d2h = pending.wait()                    # the caller reads the host result of the previous step
+        pending = handle
+    hout, h2d, d2h = pending.wait()
+    torch.cuda.current_stream().wait_event(pending.done)
     e1.record()
     torch.cuda.synchronize()
     rdist.barrier()

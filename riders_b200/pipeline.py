@@ -41,6 +41,8 @@ class RadarDepthPipeline(object):
         self.chunk_points = chunk_points
         self.max_knots = max_knots
         self._pinned = {}
+        self._copy_streams = None
+        self._slot = 0
 
     # ------------------------------------------------------------------------------ device
     @torch.no_grad()
@@ -128,3 +130,52 @@ class RadarDepthPipeline(object):
             d2h += h.numel() * h.element_size()
             host[k] = h
         return host, h2d, d2h
+
+    @torch.no_grad()
+    def submit_host(self, images, radar_points, frame_offsets, mono_pred, sparse_depth, device=None):
+        """Pipelined form of ``run_host``: the host->device copies run on a copy stream, the chain on the current stream, the
+        device->host copies on a second copy stream into one of two sets of pinned buffers, so that the copies of step k + 1 /
+        step k - 1 overlap the compute of step k.  Returns a handle; ``handle.wait()`` blocks until this step's results are in
+        pinned host memory and returns ``(outputs, h2d_bytes, d2h_bytes)`` like ``run_host``.  The host inputs must stay
+        untouched until then; at most two steps may be in flight (the result buffers alternate)."""
+        device = device or torch.device("cuda", torch.cuda.current_device())
+        main = torch.cuda.current_stream(device)
+        if self._copy_streams is None:
+            self._copy_streams = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+        s_in, s_out = self._copy_streams
+        self._slot ^= 1
+        h2d, dev = 0, []
+        s_in.wait_stream(main)                                   # buffers recycled by the allocator were last used on main
+        with torch.cuda.stream(s_in):
+            for a in (images, radar_points, mono_pred, sparse_depth):
+                t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
+                if not t.is_pinned():
+                    t = t.pin_memory()
+                h2d += t.numel() * t.element_size()
+                d = t.to(device, non_blocking=True)
+                d.record_stream(main)
+                dev.append(d)
+        main.wait_stream(s_in)
+        out = self.run_device(dev[0], dev[1], list(frame_offsets), dev[2], dev[3])
+        s_out.wait_stream(main)
+        host, d2h = {}, 0
+        with torch.cuda.stream(s_out):
+            for k in ("depth", "int_depth", "scale_map", "int_scales", "scale_shift", "interp_status") + \
+                    ((("sml_x", "sml_d")) if self.sml_input else ()):
+                h = self._pin("%s#%d" % (k, self._slot), out[k].shape, out[k].dtype)
+                out[k].record_stream(s_out)
+                h.copy_(out[k], non_blocking=True)
+                d2h += h.numel() * h.element_size()
+                host[k] = h
+            done = torch.cuda.Event()
+            done.record(s_out)
+        return _HostResult(host, h2d, d2h, done)
+
+
+class _HostResult(object):
+    def __init__(self, host, h2d, d2h, done):
+        self.host, self.h2d, self.d2h, self.done = host, h2d, d2h, done
+
+    def wait(self):
+        self.done.synchronize()
+        return self.host, self.h2d, self.d2h

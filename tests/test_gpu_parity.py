@@ -378,6 +378,15 @@ def test_pipeline_matches_oracle_chain():
     assert h2d == sum(batch[k].nbytes for k in ("images", "points", "mono", "sparse")) and d2h > 3 * B * Hh * Ww * 4
     for k in ("depth", "int_depth", "scale_map"):
         assert np.array_equal(hout[k].numpy(), out[k].cpu().numpy())          # host entry point == device entry point
+    # pipelined host entry point: two steps in flight (copies on their own streams, alternating pinned result buffers)
+    batch2 = synth.chain_batch(77, B, K, Hh, Ww, patch)
+    ref2 = pipe.run_device(cu(batch2["images"]), cu(batch2["points"]), batch2["offsets"], cu(batch2["mono"]), cu(batch2["sparse"]))
+    h1 = pipe.submit_host(batch["images"], batch["points"], batch["offsets"], batch["mono"], batch["sparse"])
+    h2 = pipe.submit_host(batch2["images"], batch2["points"], batch2["offsets"], batch2["mono"], batch2["sparse"])
+    (o1, b_in, b_out), (o2, _, _) = h1.wait(), h2.wait()
+    assert (b_in, b_out) == (h2d, d2h)
+    for k in ("depth", "int_depth", "scale_map", "int_scales"):
+        assert np.array_equal(o1[k].numpy(), out[k].cpu().numpy()) and np.array_equal(o2[k].numpy(), ref2[k].cpu().numpy())
     for b in range(B):
         fr = synth.chain_frame(40 + b, K, Hh, Ww, patch)
         ref = chain_ref.chain_frame_ref(cpu, fr, 0.45)
