@@ -198,6 +198,13 @@ def main():
         return pipe.run_device(dev["images"], dev["points"], offsets, dev["mono"], dev["sparse"])
 
     sampler = ClockSampler(local) if rank == 0 else None        # started early: nvidia-smi needs ~0.5 s to deliver samples
+    # cuDNN picks its convolution algorithms by timing them in the first call: run that one (untimed, not counted in W)
+    # without the side stream so that the alignment / interpolation kernels do not perturb the measurements it is based on
+    if not args.profile:
+        pipe.overlap_front_end = False
+        out = step_device()
+        torch.cuda.synchronize()
+        pipe.overlap_front_end = True
     for _ in range(args.warmup):
         out = step_device()
     torch.cuda.synchronize()
@@ -236,20 +243,23 @@ def main():
     # The public call a user makes: RadarDepthPipeline.submit_host (pinned host buffers in, pinned host buffers out).  Two
     # steps are in flight: the copies of step k + 1 / k - 1 ride on copy streams under the compute of step k, and the
     # caller reads step k - 1's host result (handle.wait()) every step.  Every step's H2D and D2H are inside the timed region.
-    for _ in range(2):
-        pipe.submit_host(host["images"], host["points"], offsets, host["mono"], host["sparse"], device).wait()
+    def e2e_steps(n):
+        pending = None
+        for _ in range(n):
+            handle = pipe.submit_host(host["images"], host["points"], offsets, host["mono"], host["sparse"], device)
+            if pending is not None:
+                pending.wait()                                 # the caller reads the host result of the previous step
+            pending = handle
+        res = pending.wait()
+        torch.cuda.current_stream().wait_event(pending.done)
+        return res
+
+    e2e_steps(max(args.warmup, 3))                             # warm-up in the same two-in-flight pattern (allocator steady state)
     torch.cuda.synchronize()
     rdist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    pending = None
-    for _ in range(args.steps):
-        handle = pipe.submit_host(host["images"], host["points"], offsets, host["mono"], host["sparse"], device)
-        if pending is not None:
-            hout, h2d, d2h = pending.wait()                    # the caller reads the host result of the previous step
-        pending = handle
-    hout, h2d, d2h = pending.wait()
-    torch.cuda.current_stream().wait_event(pending.done)
+    hout, h2d, d2h = e2e_steps(args.steps)
     e1.record()
     torch.cuda.synchronize()
     rdist.barrier()

@@ -134,42 +134,63 @@ class RadarDepthPipeline(object):
     @torch.no_grad()
     def submit_host(self, images, radar_points, frame_offsets, mono_pred, sparse_depth, device=None):
         """Pipelined form of ``run_host``: the host->device copies run on a copy stream, the chain on the current stream, the
-        device->host copies on a second copy stream into one of two sets of pinned buffers, so that the copies of step k + 1 /
-        step k - 1 overlap the compute of step k.  Returns a handle; ``handle.wait()`` blocks until this step's results are in
-        pinned host memory and returns ``(outputs, h2d_bytes, d2h_bytes)`` like ``run_host``.  The host inputs must stay
-        untouched until then; at most two steps may be in flight (the result buffers alternate)."""
+        device->host copies on a second copy stream, each through one of two sets of persistent device / pinned buffers, so
+        that the copies of step k + 1 / step k - 1 overlap the compute of step k.  Returns a handle; ``handle.wait()`` blocks
+        until this step's results are in pinned host memory and returns ``(outputs, h2d_bytes, d2h_bytes)`` like
+        ``run_host``.  The host inputs must stay untouched until then; at most two steps may be in flight (the buffers
+        alternate).  No allocator interplay: every cross-stream buffer is persistent and guarded by events."""
         device = device or torch.device("cuda", torch.cuda.current_device())
         main = torch.cuda.current_stream(device)
         if self._copy_streams is None:
             self._copy_streams = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+            self._slots = [dict(inp={}, stage={}, computed=None, drained=None) for _ in range(2)]
         s_in, s_out = self._copy_streams
         self._slot ^= 1
+        slot = self._slots[self._slot]
+        # ---- host -> device into this slot's persistent input buffers (free once the step that last used them has run)
         h2d, dev = 0, []
-        s_in.wait_stream(main)                                   # buffers recycled by the allocator were last used on main
+        if slot["computed"] is not None:
+            s_in.wait_event(slot["computed"])
         with torch.cuda.stream(s_in):
-            for a in (images, radar_points, mono_pred, sparse_depth):
+            for name, a in (("images", images), ("points", radar_points), ("mono", mono_pred), ("sparse", sparse_depth)):
                 t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
                 if not t.is_pinned():
                     t = t.pin_memory()
+                d = slot["inp"].get(name)
+                if d is None or d.shape != t.shape or d.dtype != t.dtype:
+                    d = torch.empty(t.shape, dtype=t.dtype, device=device)
+                    slot["inp"][name] = d
+                d.copy_(t, non_blocking=True)
                 h2d += t.numel() * t.element_size()
-                d = t.to(device, non_blocking=True)
-                d.record_stream(main)
                 dev.append(d)
-        main.wait_stream(s_in)
+            loaded = torch.cuda.Event()
+            loaded.record(s_in)
+        main.wait_event(loaded)
         out = self.run_device(dev[0], dev[1], list(frame_offsets), dev[2], dev[3])
-        s_out.wait_stream(main)
+        # ---- results -> this slot's device staging buffers (on the compute stream), then device -> host on the copy stream
+        keys = ("depth", "int_depth", "scale_map", "int_scales", "scale_shift", "interp_status") + \
+            ((("sml_x", "sml_d")) if self.sml_input else ())
+        if slot["drained"] is not None:
+            main.wait_event(slot["drained"])                     # the copy-out of the step that last used the staging buffers
+        for k in keys:
+            g = slot["stage"].get(k)
+            if g is None or g.shape != out[k].shape or g.dtype != out[k].dtype:
+                g = torch.empty_like(out[k], memory_format=torch.contiguous_format)
+                slot["stage"][k] = g
+            g.copy_(out[k])
+        slot["computed"] = torch.cuda.Event()
+        slot["computed"].record(main)
+        s_out.wait_event(slot["computed"])
         host, d2h = {}, 0
         with torch.cuda.stream(s_out):
-            for k in ("depth", "int_depth", "scale_map", "int_scales", "scale_shift", "interp_status") + \
-                    ((("sml_x", "sml_d")) if self.sml_input else ()):
-                h = self._pin("%s#%d" % (k, self._slot), out[k].shape, out[k].dtype)
-                out[k].record_stream(s_out)
-                h.copy_(out[k], non_blocking=True)
+            for k in keys:
+                h = self._pin("%s#%d" % (k, self._slot), slot["stage"][k].shape, slot["stage"][k].dtype)
+                h.copy_(slot["stage"][k], non_blocking=True)
                 d2h += h.numel() * h.element_size()
                 host[k] = h
-            done = torch.cuda.Event()
-            done.record(s_out)
-        return _HostResult(host, h2d, d2h, done)
+            slot["drained"] = torch.cuda.Event()
+            slot["drained"].record(s_out)
+        return _HostResult(host, h2d, d2h, slot["drained"])
 
 
 class _HostResult(object):
