@@ -392,16 +392,18 @@ loftr_layer_tc_kernel(const LayerArgs P) {
             TRACE_E(2);
             {
                 // One quarter (heads 2hq, 2hq+1 = 32 columns) at a time, staged in the idle A operand, fp32:
-                //   Qst | Kst | Vst [128][32] @0 / 16K / 32K (float4 index XOR (row & 7)), KVs [12][16][16] @48K, Ksum [12][16] @60K
+                //   Qst | Kst | Vst [128][ST] with ST = 36 floats per row (144 B: the 8 lanes of a 128-bit store phase, one row
+                //   each, fall into distinct bank groups, so no XOR swizzle and every address below is base + immediate);
+                //   KV (16 x 16) and Ksum (16) of a (point, head) pair overwrite rows 0..15 / 16 of that pair's own K block
+                //   (21 rows x 16 columns) once its warp has consumed it.
                 // (1) every thread moves 8 columns of q, k, v of its row from TMEM (elu+1 on q and k);
                 // (2) warp w < 12 owns the (point, head) pair w: KV = K'^T V and Ksum, lane = (2 d, 4 v);
                 // (3) the same warp computes the 21 x 16 message block of its pair as a register-tiled product
                 //     Q' KV (lane = (3 rows, 4 v)): 4 shared-memory wavefronts per d instead of one KV broadcast per row.
+                constexpr int ST = 36;
                 float* Qst = stage_f;
-                float* Kst = stage_f + 4096;
-                float* Vst = stage_f + 8192;
-                float* KVs = stage_f + 12288;
-                float* Ksum = stage_f + 15360;
+                float* Kst = stage_f + 128 * ST;
+                float* Vst = stage_f + 2 * 128 * ST;
                 float4 m[4][3];                          // [quarter][row of the lane's row group]: 4 v values each
                 const int pair = ew, p = pair >> 1, hl = pair & 1;
                 const int rg = lane >> 2, vq = lane & 3;
@@ -414,6 +416,7 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                         TMEM_LD8(trow + D1 + hq * 32 + colq * 8, kr);
                         TMEM_LD8(trow + D2 + hq * 32 + colq * 8, vr);
                         tmem_wait_ld();
+                        if (hq == 1) TRACE_E(20);
                         if (hq == 3) { tc_fence_before(); mbar_arrive(v_free); }    // D2 is free: mlp.0[C:, :C] may go
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
@@ -424,24 +427,28 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                             kk.z = elu1(acc_f(kr[4 * j + 2])); kk.w = elu1(acc_f(kr[4 * j + 3]));
                             vv.x = acc_f(vr[4 * j + 0]); vv.y = acc_f(vr[4 * j + 1]);
                             vv.z = acc_f(vr[4 * j + 2]); vv.w = acc_f(vr[4 * j + 3]);
-                            const int f4 = (colq * 2 + j) ^ (row & 7);
-                            reinterpret_cast<float4*>(Qst + row * 32)[f4] = qq;
-                            reinterpret_cast<float4*>(Kst + row * 32)[f4] = kk;
-                            reinterpret_cast<float4*>(Vst + row * 32)[f4] = vv;
+                            const int f4 = colq * 2 + j;
+                            reinterpret_cast<float4*>(Qst + row * ST)[f4] = qq;
+                            reinterpret_cast<float4*>(Kst + row * ST)[f4] = kk;
+                            reinterpret_cast<float4*>(Vst + row * ST)[f4] = vv;
                         }
                     }
+                    if (hq == 1) TRACE_E(21);
                     epi_bar();
+                    if (hq == 1) TRACE_E(22);
                     if (worker) {
                         // (2) lane -> d = 2 dp, 2 dp + 1 and v = 4 vq .. 4 vq + 3
                         const int dp = rg;
                         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
                         float ks0 = 0.f, ks1 = 0.f;
+                        float* kblk = Kst + p * TOK * ST + hl * 16;               // this pair's K block: rows p*21 .. +20, 16 columns
                         if (p < pts) {
-#pragma unroll 7
+                            const float* kp = kblk + 2 * dp;
+                            const float* vp = Vst + p * TOK * ST + hl * 16 + 4 * vq;
+#pragma unroll
                             for (int u = 0; u < TOK; ++u) {
-                                const int r = p * TOK + u, sw = r & 7;
-                                const float2 kk = *reinterpret_cast<const float2*>(Kst + r * 32 + (((hl * 4 + (dp >> 1)) ^ sw) << 2) + (dp & 1) * 2);
-                                const float4 vv = reinterpret_cast<const float4*>(Vst + r * 32)[(hl * 4 + vq) ^ sw];
+                                const float2 kk = *reinterpret_cast<const float2*>(kp + u * ST);
+                                const float4 vv = *reinterpret_cast<const float4*>(vp + u * ST);
                                 ks0 += kk.x; ks1 += kk.y;
                                 a0.x = fmaf(kk.x, vv.x, a0.x); a0.y = fmaf(kk.x, vv.y, a0.y);
                                 a0.z = fmaf(kk.x, vv.z, a0.z); a0.w = fmaf(kk.x, vv.w, a0.w);
@@ -449,30 +456,31 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                                 a1.z = fmaf(kk.y, vv.z, a1.z); a1.w = fmaf(kk.y, vv.w, a1.w);
                             }
                         }
-                        *reinterpret_cast<float4*>(KVs + pair * 256 + (2 * dp) * 16 + 4 * vq) = a0;
-                        *reinterpret_cast<float4*>(KVs + pair * 256 + (2 * dp + 1) * 16 + 4 * vq) = a1;
-                        if (vq == 0) *reinterpret_cast<float2*>(Ksum + pair * 16 + 2 * dp) = make_float2(ks0, ks1);
+                        __syncwarp();                                             // every lane is done reading the K block
+                        *reinterpret_cast<float4*>(kblk + (2 * dp) * ST + 4 * vq) = a0;           // KV[d][v] -> row d of the block
+                        *reinterpret_cast<float4*>(kblk + (2 * dp + 1) * ST + 4 * vq) = a1;
+                        if (vq == 0) *reinterpret_cast<float2*>(kblk + 16 * ST + 2 * dp) = make_float2(ks0, ks1);   // Ksum -> row 16
                         __syncwarp();
+                        if (hq == 1) TRACE_E(23);
                         // (3) lane -> rows 3 rg .. 3 rg + 2 of the point (rg < 7) and v = 4 vq .. 4 vq + 3
                         float4 acc[3];
                         float den[3] = {0.f, 0.f, 0.f};
 #pragma unroll
                         for (int i = 0; i < 3; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        const int r0 = p * TOK + min(rg, 6) * 3;
+                        const float* qp = Qst + (p * TOK + min(rg, 6) * 3) * ST + hl * 16;
 #pragma unroll
                         for (int dq = 0; dq < 4; ++dq) {
-                            const float4 ksum = *reinterpret_cast<const float4*>(Ksum + pair * 16 + 4 * dq);
+                            const float4 ksum = *reinterpret_cast<const float4*>(kblk + 16 * ST + 4 * dq);
                             float4 qv[3];
 #pragma unroll
                             for (int i = 0; i < 3; ++i) {
-                                const int r = r0 + i;
-                                qv[i] = reinterpret_cast<const float4*>(Qst + r * 32)[(hl * 4 + dq) ^ (r & 7)];
+                                qv[i] = *reinterpret_cast<const float4*>(qp + i * ST + 4 * dq);
                                 den[i] = fmaf(qv[i].x, ksum.x, den[i]); den[i] = fmaf(qv[i].y, ksum.y, den[i]);
                                 den[i] = fmaf(qv[i].z, ksum.z, den[i]); den[i] = fmaf(qv[i].w, ksum.w, den[i]);
                             }
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                const float4 kv = *reinterpret_cast<const float4*>(KVs + pair * 256 + (4 * dq + e) * 16 + 4 * vq);
+                                const float4 kv = *reinterpret_cast<const float4*>(kblk + (4 * dq + e) * ST + 4 * vq);
 #pragma unroll
                                 for (int i = 0; i < 3; ++i) {
                                     const float q1 = e == 0 ? qv[i].x : e == 1 ? qv[i].y : e == 2 ? qv[i].z : qv[i].w;
@@ -488,7 +496,9 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                         }
                     }
                     if (hq == 0) TRACE_E(3);
+                    if (hq == 1) TRACE_E(24);
                     epi_bar();                           // (2), (3) done reading: the next quarter may overwrite the staging
+                    if (hq == 1) TRACE_E(25);
                 }
                 // staging dead (barrier above): msg -> A operand, rows of point p, columns of head 2 hq + hl
                 if (worker && rg < 7) {

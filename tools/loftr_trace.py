@@ -54,6 +54,10 @@ for label, src in (("self", x), ("cross", s)):
                 continue
             print("   %-28s t=%8.2f  (+%6.2f)" % (name, (e[k] - t0) / mhz, (e[k] - prev) / mhz))
             prev = e[k]
+        q = e[20:26]
+        if q[0]:
+            names = ["TMEM loads of q, k, v landed", "elu + staging stores", "barrier (all 16 warps staged)", "(2) KV + Ksum", "(3) Q.KV message", "barrier (staging free)"]
+            print(" %s attention quarter 1 (us):  " % cta + "; ".join("%s %.2f" % (nm, (q[i] - (e[3] if i == 0 else q[i - 1])) / mhz) for i, nm in enumerate(names)))
         print(" %s MMA thread: segment [wait A, issue, of which waiting for weights]" % cta)
         for seg in range(5):
             w0, w1, w2, ws = m[seg * 4:seg * 4 + 4]
