@@ -1,0 +1,111 @@
+"""Host-side weight preparation of the decoder fast paths (CPU only, no kernels): the sub-pixel phase kernels, the
+mma.m16n8k8 B-fragment orders and the tcgen05 K-major SWIZZLE_128B slab image are pure index algebra in torch."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from riders_b200 import ops
+from riders_b200.rcnet import networks
+
+
+def _tf32_rna(x):
+    return ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def _block(cin=8, cskip=4, cout=4):
+    torch.manual_seed(3)
+    blk = networks.DecoderBlock(cin, cskip, cout, 'kaiming_uniform', 'leaky_relu', False).eval()
+    for m in blk.modules():
+        if isinstance(m, networks.Conv2d):
+            m.fold_batch_norm_()
+    return blk.fold_upsample_()
+
+
+def test_subpixel_phase_kernels_equal_resize_then_conv():
+    """DecoderBlock.fold_upsample_: both forms of the phase kernels reproduce conv3x3(nearest 2x resize(x)) (the kernels are float32 pre-sums of the taps, evaluated in fp64)."""
+    blk = _block()
+    w = blk.deconv.conv.conv.weight.detach().double()
+    x = torch.randn(2, 8, 5, 7, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2), w, None, 1, 1)
+    co = w.shape[0]
+    y3 = F.conv2d(x, blk._w4.double(), None, 1, 1)                        # (N, 4 co, h, w), phase-major channels
+    y2 = F.conv2d(x, blk._w2.double(), None, 1, 1)                        # (N, 4 co, h + 1, w + 1): phase (a, b) at (i + a, j + b)
+    assert tuple(blk._w4.shape) == (4 * co, 8, 3, 3) and tuple(blk._w2.shape) == (4 * co, 8, 2, 2)
+    out3, out2 = torch.empty_like(ref), torch.empty_like(ref)
+    for a in (0, 1):
+        for b in (0, 1):
+            ph = slice((2 * a + b) * co, (2 * a + b + 1) * co)
+            out3[:, :, a::2, b::2] = y3[:, ph]
+            out2[:, :, a::2, b::2] = y2[:, ph, a:a + 5, b:b + 7]
+    np.testing.assert_allclose(out3.numpy(), ref.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out2.numpy(), ref.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_odd_target_first_column_and_row_kernels():
+    """2n+1 targets: torch's nearest resize picks source max(j - 1, 0) >> 1; the first output column (row) comes from the
+    3x1 (1x3) phase kernels, everything else from the phase kernels on the replicate-padded map read one pixel further."""
+    blk = _block()
+    w = blk.deconv.conv.conv.weight.detach().double()
+    co = w.shape[0]
+    x = torch.randn(2, 8, 5, 4, dtype=torch.float64)
+    for sy, sx in ((0, 1), (1, 0)):
+        H, W = 2 * 5 + sy, 2 * 4 + sx
+        ref = F.conv2d(F.interpolate(x, size=(H, W)), w, None, 1, 1)
+        xp = F.pad(x, (sx, 0, sy, 0), mode='replicate')
+        y2 = F.conv2d(xp, blk._w2.double(), None, 1, 1)
+        out = torch.empty_like(ref)
+        for Y in range(H):
+            for X in range(W):
+                if (sx and X == 0) or (sy and Y == 0):
+                    continue
+                ky, kx = Y + sy, X + sx
+                ph = 2 * (ky & 1) + (kx & 1)
+                out[:, :, Y, X] = y2[:, ph * co:(ph + 1) * co, (ky >> 1) + (ky & 1), (kx >> 1) + (kx & 1)]
+        if sx:
+            yf = F.conv2d(x[:, :, :, 0:1], blk._wcol.double(), None, 1, (1, 0))          # (N, 2 co, h, 1): channel a * co + c
+            for Y in range(H):
+                out[:, :, Y, 0] = yf[:, (Y & 1) * co:((Y & 1) + 1) * co, Y >> 1, 0]
+        else:
+            yf = F.conv2d(x[:, :, 0:1, :], blk._wrow.double(), None, 1, (0, 1))          # (N, 2 co, 1, w): channel b * co + c
+            for X in range(W):
+                out[:, :, 0, X] = yf[:, (X & 1) * co:((X & 1) + 1) * co, 0, X >> 1]
+        np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_tail_weight_fragments_follow_the_mma_layout():
+    """ops._tail_weight_fragments: [K step][lane][N half][2] with b0 = W[8 nt + g][8 j + t][ky][kx], b1 at ci + 4,
+    lane = 4 g + t, K step = (ky * 3 + kx) * 2 + j; TF32-rounded."""
+    torch.manual_seed(0)
+    w = torch.randn(16, 16, 3, 3)
+    f = ops._tail_weight_fragments(w)
+    assert tuple(f.shape) == (18, 32, 2, 2)
+    wr = _tf32_rna(w)
+    for s, lane, nt, e in ((0, 0, 0, 0), (5, 13, 1, 1), (17, 31, 1, 0), (8, 6, 0, 1)):
+        tap, j, g, t = s // 2, s % 2, lane // 4, lane % 4
+        assert f[s, lane, nt, e] == wr[nt * 8 + g, 8 * j + t + 4 * e, tap // 3, tap % 3]
+    assert ops._tail_weight_fragments(w) is f                             # cached per tensor object and version
+    w.mul_(2.0)
+    assert ops._tail_weight_fragments(w) is not f                         # in-place update -> rebuilt
+    assert ops._tail_weight_fragments(w.clone()) is not ops._tail_weight_fragments(w)
+
+
+def test_subpixel_fragments_and_tcgen05_slabs():
+    torch.manual_seed(1)
+    w2 = torch.randn(64, 32, 2, 2)
+    wr = _tf32_rna(w2)
+    f = ops._subpixel_weight_fragments(w2)                                # [K step][N tile pair][lane][4]
+    assert tuple(f.shape) == (16, 4, 32, 4)
+    for ks, npair, lane, e in ((0, 0, 0, 0), (7, 3, 21, 3), (15, 1, 31, 2), (9, 2, 5, 1)):
+        tap, g, t = ks // 4, lane // 4, lane % 4
+        assert f[ks, npair, lane, e] == wr[(2 * npair + e // 2) * 8 + g, (ks % 4) * 8 + t + 4 * (e % 2), tap // 2, tap % 2]
+    p = ops._subpixel_tc_weights(w2)                                      # four K-major SWIZZLE_128B slabs of 64 rows x 128 B
+    assert p.numel() == 4 * 64 * 32
+    seen = torch.zeros(p.numel(), dtype=torch.bool)
+    for tap in range(4):
+        for n in (0, 1, 7, 8, 37, 63):
+            for k in (0, 3, 4, 17, 31):
+                off = tap * 2048 + (n >> 3) * 256 + (n & 7) * 32 + (((k >> 2) ^ (n & 7)) << 2) + (k & 3)
+                assert p[off] == wr[n, k, tap // 2, tap % 2]
+                seen[off] = True
+    assert seen.sum() == 4 * 6 * 5                                        # the sampled offsets are all distinct (a permutation)
+    assert torch.equal(torch.sort(p).values, torch.sort(wr.permute(2, 3, 0, 1).reshape(-1)).values)
