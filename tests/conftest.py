@@ -45,3 +45,16 @@ class Golden(object):
 @pytest.fixture(scope="session")
 def golden():
     return Golden
+
+
+@pytest.fixture(autouse=True)
+def _fp32_library_math():
+    """Parity is judged against fp32 references: every test starts with TF32 off for cuDNN and cuBLAS (torch's default
+    allows it for convolutions), independent of test order.  The TF32 kernels (decoder tail, phase convolutions) are
+    selected by ``torch.backends.cudnn.allow_tf32``; their tests switch it on explicitly and this restores the state."""
+    import torch
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
