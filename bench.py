@@ -186,7 +186,8 @@ def main():
     model = build_model(device)
     # inputs "as loaded": [0,255] frames and radar points in frame coordinates; the prologue (shift, boxes, normalise,
     # pad), the empty-frame retry check and the SML input assembly all run inside the timed region
-    pipe = RadarDepthPipeline(model, response_thr=THR, chunk_points=2048, raw_inputs=True, retry_empty=True, sml_input=True)
+    pipe = RadarDepthPipeline(model, response_thr=THR, chunk_points=int(os.environ.get("RIDERS_CHUNK_POINTS", "2048")), raw_inputs=True,
+                              retry_empty=True, sml_input=True)
     batch = synth.chain_batch(rank * B, B, K_POINTS, H, W, PATCH)
     batch["images"] = np.rint(batch["images"] * 255.0).astype(np.float32)
     batch["points"] = (batch["points"] - np.array([PATCH[1] // 2, PATCH[0] // 2, 0], np.float32)).astype(np.float32)
