@@ -101,19 +101,68 @@ class ClockSampler(object):
                 "power_w_max": max(float(r[2]) for r in rows if r[2].replace(".", "").isdigit())}
 
 
-def cpu_frame_rate(seconds_budget, model_cpu=None, max_frames=4):
-    """The oracle port of the reference path on the host cores: frames/s over a bounded sample."""
+def cpu_frame_rate(seconds_budget, model_cpu=None, max_frames=4, global_alignment="st"):
+    """The oracle port of the reference path on the host cores: frames/s over a bounded sample.  Also returns the
+    reference outputs of those frames (the first frames of rank 0's batch) for the parity block."""
     from oracle import chain_ref
     from riders_b200 import synth
     model_cpu = model_cpu or build_model(torch.device("cpu"))
-    n, t0 = 0, time.perf_counter()
-    while n < max_frames:
-        chain_ref.chain_frame_ref(model_cpu, synth.chain_frame(n, K_POINTS, H, W, PATCH), THR)
-        n += 1
+    refs, t0 = [], time.perf_counter()
+    while len(refs) < max_frames:
+        refs.append(chain_ref.chain_frame_ref(model_cpu, synth.chain_frame(len(refs), K_POINTS, H, W, PATCH), THR,
+                                              want_conf=True, global_alignment=global_alignment))
         if time.perf_counter() - t0 > seconds_budget:
             break
     dt = time.perf_counter() - t0
-    return n / dt, n, dt
+    return len(refs) / dt, len(refs), dt, refs
+
+
+def parity_block(out, refs):
+    """GPU outputs of the benched configuration (exactly the flags that were timed) against the oracle port on the same
+    frames, at north_star's rules: confidences 1e-4 relative, select exact where the top-2 margin > 1e-6, scale / shift
+    1e-6 relative, scale map 1e-5 relative inside the hull and exactly the fill value outside."""
+    from oracle import confidence_reduce_ref as cr, interpolator_ref as ir
+    from riders_b200 import synth
+    res = {"frames": len(refs), "conf_max_rel_err": 0.0, "conf_fired_mismatch_frac": 0.0, "select_agree_frac_margin_gt_1e-6": 1.0,
+           "select_margin_gt_1e-6_frac": 0.0, "depth_max_rel_err": 0.0, "scale_rel_err": 0.0, "shift_rel_err": 0.0,
+           "int_depth_max_rel_err": 0.0, "scale_map_max_rel_err_inside": 0.0, "scale_map_outside_mismatch_px": 0,
+           "scale_map_masked_degenerate_frac": 0.0}
+    sel_ok, sel_n, px = 0, 0, 0
+    for b, ref in enumerate(refs):
+        r = out["response"][b].cpu().numpy()
+        d = out["depth"][b].cpu().numpy()
+        fired, fired_ref = r > 0, ref["response"] > 0
+        both = fired & fired_ref
+        res["conf_fired_mismatch_frac"] = max(res["conf_fired_mismatch_frac"], float((fired != fired_ref).mean()))
+        if both.any():
+            res["conf_max_rel_err"] = max(res["conf_max_rel_err"], float((np.abs(r[both] - ref["response"][both]) / ref["response"][both]).max()))
+            res["depth_max_rel_err"] = max(res["depth_max_rel_err"], float((np.abs(d[both] - ref["depth"][both]) / ref["depth"][both]).max()))
+        if "select" in out:
+            fr = synth.chain_frame(b, K_POINTS, H, W, PATCH)
+            margin = cr.top2_margin(ref["conf"], fr["points"], H, W, THR)
+            m = (margin > 1e-6) & fired_ref
+            sel_ok += int((out["select"][b].cpu().numpy()[m] == ref["select"][m]).sum())
+            sel_n += int(m.sum())
+            px += int(fired_ref.sum())
+        ss = out["scale_shift"][b].cpu().numpy()
+        res["scale_rel_err"] = max(res["scale_rel_err"], abs(ss[0] - ref["scale"]) / max(abs(ref["scale"]), 1e-30))
+        if ref["shift"] != 0.0:
+            res["shift_rel_err"] = max(res["shift_rel_err"], abs(ss[1] - ref["shift"]) / abs(ref["shift"]))
+        idp = out["int_depth"][b].cpu().numpy()
+        res["int_depth_max_rel_err"] = max(res["int_depth_max_rel_err"], float((np.abs(idp - ref["int_depth"]) / ref["int_depth"]).max()))
+        coords, _, _ = ir.extract_knots_ref(ref["int_depth"], ref["sparse_inv"], ref["valid"])
+        ok = ~ir.degenerate_pixel_mask(coords.T, H, W)
+        sm, smr = out["scale_map"][b].cpu().numpy(), ref["scale_map"]
+        res["scale_map_masked_degenerate_frac"] = max(res["scale_map_masked_degenerate_frac"], float(1.0 - ok.mean()))
+        res["scale_map_outside_mismatch_px"] += int(((sm == 1.0) != (smr == 1.0))[ok].sum())
+        res["scale_map_max_rel_err_inside"] = max(res["scale_map_max_rel_err_inside"], float((np.abs(sm - smr) / np.abs(smr))[ok].max()))
+    if sel_n:
+        res["select_agree_frac_margin_gt_1e-6"] = sel_ok / sel_n
+        res["select_margin_gt_1e-6_frac"] = sel_n / max(px, 1)
+    res["meets_north_star"] = bool(res["conf_max_rel_err"] <= 1e-4 and res["select_agree_frac_margin_gt_1e-6"] == 1.0 and
+                                   res["scale_rel_err"] <= 1e-6 and res["shift_rel_err"] <= 1e-6 and
+                                   res["scale_map_max_rel_err_inside"] <= 1e-5 and res["scale_map_outside_mismatch_px"] == 0)
+    return res
 
 
 def run_reference(args):
@@ -127,17 +176,18 @@ def run_reference(args):
     model = build_model(torch.device("cpu"))
     frames = [synth.chain_frame(i, K_POINTS, H, W, PATCH) for i in range(2)]
     for i in range(max(args.warmup, 0)):                      # bounded: warm-up on a K=64 slice of a frame
-        chain_ref.chain_frame_ref(model, synth.chain_frame(100 + i, 64, H, W, PATCH), THR)
+        chain_ref.chain_frame_ref(model, synth.chain_frame(100 + i, 64, H, W, PATCH), THR, global_alignment=args.align)
     steps = max(1, min(args.steps, 6))                           # one frame per step, <= ~1-2 min of CPU work
     t0 = time.perf_counter()
     for i in range(steps):
-        chain_ref.chain_frame_ref(model, frames[i % len(frames)], THR)
+        chain_ref.chain_frame_ref(model, frames[i % len(frames)], THR, global_alignment=args.align)
     dt = time.perf_counter() - t0
     v = steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(1, note="reference arm: one 640x512 frame (K=512) per step on the host cores"),
+            "config": workload_config(1, frames_per_gpu=1, align=args.align,
+                                      note="reference arm: one 640x512 frame (K=512) per step on the host cores"),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                              "sample": "%d steps x 1 frame (K=512) of the same synthetic workload; oracle port of "
                                        "forward_output + LSQ align + griddata-linear (CPU torch/torchvision/NumPy/SciPy)" % steps},
@@ -146,11 +196,229 @@ def run_reference(args):
     return 0
 
 
-def workload_config(n_gpus, note=None):
-    c = {"workload": "configs[1] RC-Net inference (run_rcnet_zju path) + SML front-end (LSQ align + scale-map "
-                     "interpolation): synthetic 640x512 thermal frames, 512 radar points/frame, thr 0.1",
-         "frames_per_gpu_per_step": FRAMES_PER_GPU, "radar_points_per_frame": K_POINTS, "patch": list(PATCH),
-         "global_frames_per_step": FRAMES_PER_GPU * n_gpus, "parallelism": "frame-sharded x%d (no data-path collective)" % n_gpus,
+def dtype_label(tf32):
+    """The arithmetic the timed step actually ran in (label it truthfully)."""
+    if tf32:
+        return ("tf32 (cuDNN backbone/decoder convolutions + fused decoder tail, torch's and the reference's GPU default) / "
+                "f32 (gather, LoFTR [fp16 hi/lo split, fp32-accurate], reduce, prologue) / f64 (alignment sums, barycentric fill)")
+    return "f32 (cuDNN fp32 convolutions, no TF32 anywhere) / f64 (alignment sums, barycentric fill)"
+
+
+def pin_rank_cores(local, world):
+    """N ranks share one host: give each rank its own slice of the cores so the Python launch threads and the pinned-memory
+    copies of different ranks do not migrate over each other."""
+    if world <= 1 or not hasattr(os, "sched_setaffinity"):
+        return
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(len(cores) // world, 1)
+        mine = cores[local * per:(local + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        torch.set_num_threads(max(1, min(per, 8)))
+    except OSError:
+        pass
+
+
+def run_eager(args):
+    """Same-box LIBRARY comparator: the reference's own formulation on the GPU with stock
+    library kernels only - torchvision roi_pool x5 (CUDA), the three einsums + nn.functional linears of LinearAttention /
+    LoFTREncoderLayer through cuBLAS, cuDNN convolutions in the reference's NCHW layout, and the literal (K, H', W') zero
+    canvases + torch.max + weighted mean of rcnet_main.py:460-485 - followed by the NumPy / SciPy alignment and
+    interpolation on the host, one frame per step like run_rcnet_zju.py.  None of this repo's kernels run here
+    (``oracle/rcnet_ref`` with device='cuda'; the model is the mirror's plain torch modules in NCHW, which take no fast path)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": "eager", "unavailable": "no CUDA device"}), flush=True)
+        return 0
+    from oracle import chain_ref, rcnet_ref
+    from riders_b200 import synth
+    dev = torch.device("cuda", 0)
+    if args.strict_fp32:
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    from riders_b200.rcnet.rcnet_model import RCNetModel
+    model = RCNetModel(device=torch.device("cpu"), **MODEL_ARGS)
+    model.eval()
+    model.device = dev
+    model.to(dev)                                            # NCHW, BatchNorm modules in place: plain torch everywhere
+    frames = [synth.chain_frame(i, K_POINTS, H, W, PATCH) for i in range(4)]
+
+    def one(fr, rcnet_only=False):
+        with torch.no_grad():
+            d, r, _ = rcnet_ref.forward_output_ref(model, torch.from_numpy(fr["image"])[None].to(dev), torch.from_numpy(fr["points"]).to(dev),
+                                                   [torch.from_numpy(fr["boxes"]).to(dev)], THR, literal=True)
+            d = d.cpu().numpy()                              # run_rcnet_zju.py:250
+        if not rcnet_only:
+            chain_ref.sml_front_end_ref(fr["mono"], fr["sparse"], global_alignment=args.align)
+        return d
+
+    for i in range(max(args.warmup, 2)):
+        one(frames[i % 4])
+    torch.cuda.synchronize()
+    steps = max(1, min(args.steps, 12))
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(frames[i % 4])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    for i in range(steps):
+        one(frames[i % 4], rcnet_only=True)
+    torch.cuda.synchronize()
+    dt_rc = time.perf_counter() - t1
+    v = steps / dt
+    print(json.dumps({"impl": "eager", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": args.warmup,
+                      "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": dtype_label(bool(torch.backends.cudnn.allow_tf32)).split(" / ")[0] + " (library kernels)", "data": "synthetic",
+                      "config": workload_config(1, frames_per_gpu=1, align=args.align, strict=args.strict_fp32,
+                                                note="library comparator: reference formulation with stock torch / torchvision CUDA kernels, "
+                                                     "one frame per step; alignment + griddata on the host as in the reference"),
+                      "rcnet_only_frames_per_s": steps / dt_rc, "rcnet_only_ms_per_frame": 1e3 * dt_rc / steps}), flush=True)
+    return 0
+
+
+def run_config1(args):
+    """BASELINE configs[0]: the val_zju.py SML front-end for ONE 640x512 frame with 200 radar points - global alignment,
+    knot extraction, Delaunay, barycentric fill, scale scaffold, SML input assembly - as latency per frame on one B200.
+    Device-resident inputs, (a) eager launches and (b) the same launches replayed from a CUDA graph (the inner loop is
+    launch-bound); e2e = NumPy in / NumPy out through the reference-facing classes.  The SML network itself cannot be built
+    offline (torch.hub encoder): attach any forward(x, d) module with RadarDepthPipeline(sml_model=...)."""
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --workload config1 needs a CUDA device")
+    from riders_b200 import ops, synth
+    from riders_b200.pipeline import RadarDepthPipeline
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    K1 = 200
+    fr = synth.chain_frame(0, K1, H, W, PATCH)
+    pipe = RadarDepthPipeline(None, global_alignment=args.align)
+    t = {k: torch.from_numpy(fr[k])[None].to(dev) for k in ("mono", "sparse", "image")}
+    rc_depth = t["sparse"].clone()                             # stand-in for the PNG run_rcnet_zju.py wrote: radar depths at the radar pixels
+
+    def step():
+        return pipe.sml_front_end(t["mono"], t["sparse"], rc_depth, t["image"], K1)
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    torch.cuda.synchronize()
+    steps = max(args.steps, 50)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2: flushed between timed iterations
+    evs = []
+    launches0 = ops.launch_count()
+    for _ in range(steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); out = step(); b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    launches = (ops.launch_count() - launches0) / steps
+    lat = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)
+    with ops.StageTimer() as timer:
+        for _ in range(steps):
+            flush.zero_()
+            step()
+    stages = {k: round(1e3 * ms / calls, 2) for k, (calls, ms, _) in timer.summary().items()}
+    # CUDA graph replay of the same launches
+    graph_us = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            gout = step()
+        g.replay()
+        torch.cuda.synchronize()
+        ge = []
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); g.replay(); b.record()
+            ge.append((a, b))
+        torch.cuda.synchronize()
+        graph_us = sorted(a.elapsed_time(b) * 1e3 for a, b in ge)[len(ge) // 2]
+        assert torch.equal(gout["scale_map"], out["scale_map"])
+    except Exception as e:                                                   # noqa: BLE001
+        graph_us = "unavailable: %s" % str(e)[:120]
+    # end to end through the reference-facing NumPy classes (host buffers in / out)
+    from riders_b200.modules.estimator import LeastSquaresEstimator, Optimizer
+    from riders_b200.modules.interpolator import Interpolator2D
+    from oracle import chain_ref
+    sparse_inv, valid = chain_ref.sparse_inverse_ref(fr["sparse"])
+
+    def host_step():
+        if args.align == "st":
+            ga = LeastSquaresEstimator(fr["mono"], sparse_inv, valid)
+            ga.compute_scale_and_shift(); ga.apply_scale_and_shift(); ga.clamp_min_max(clamp_min=0.1, clamp_max=255.0)
+        else:
+            ga = Optimizer(fr["mono"], sparse_inv, valid, "inv")
+            ga.optimize_scale(); ga.apply_scale(); ga.clamp_min_max(clamp_min=0.1, clamp_max=255.0)
+        int_depth = ga.output.astype(np.float32)
+        return Interpolator2D(int_depth, sparse_inv, valid).generate_interpolated_scale_map("linear")
+
+    for _ in range(3):
+        host_step()
+    t0 = time.perf_counter()
+    n_host = 20
+    for _ in range(n_host):
+        sm = host_step()
+    host_us = (time.perf_counter() - t0) / n_host * 1e6
+    # CPU reference of the same frame (LSQ / Brent + griddata), and parity of this run
+    t0 = time.perf_counter()
+    ref = chain_ref.sml_front_end_ref(fr["mono"], fr["sparse"], global_alignment=args.align)
+    cpu_us = (time.perf_counter() - t0) * 1e6
+    from oracle import interpolator_ref as ir
+    coords, _, _ = ir.extract_knots_ref(ref["int_depth"], ref["sparse_inv"], ref["valid"])
+    ok = ~ir.degenerate_pixel_mask(coords.T, H, W)
+    got = out["scale_map"][0].cpu().numpy()
+    ss = out["scale_shift"][0].cpu().numpy()
+    parity = {"scale_rel_err": abs(ss[0] - ref["scale"]) / abs(ref["scale"]),
+              "shift_rel_err": (abs(ss[1] - ref["shift"]) / abs(ref["shift"])) if ref["shift"] else 0.0,
+              "int_depth_bit_exact": bool(np.array_equal(out["int_depth"][0].cpu().numpy(), ref["int_depth"])),
+              "scale_map_max_rel_err_inside": float((np.abs(got - ref["scale_map"]) / np.abs(ref["scale_map"]))[ok].max()),
+              "scale_map_outside_mismatch_px": int(((got == 1.0) != (ref["scale_map"] == 1.0))[ok].sum()),
+              "host_class_path_equals_device_path": bool(np.array_equal(sm, got))}
+    med = lat[len(lat) // 2]
+    algorithmic = 4259840 * 2                                                # SURVEY 8(d): align 4.26 MB + interp 4.26 MB per frame
+    peaks = load_peaks()
+    print(json.dumps({"metric": "SML front-end latency @640x512, 200 radar points (configs[0])", "value": med, "unit": "us",
+                      "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": med * 1e-3, "higher_is_better": False,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32 maps / f64 sums + barycentric", "data": "synthetic",
+                      "config": {"workload": "configs[0] val_zju.py SML front-end: one 640x512 frame, 200 radar points: sparse inverse + "
+                                             "mask, %s align + clamp, knot extraction, Delaunay, barycentric fill, scale scaffold, SML input "
+                                             "assembly (352x288)" % ("LSQ" if args.align == "st" else "L1 Optimizer"),
+                                 "global_alignment": args.align, "l2": "256 MB flush between timed iterations"},
+                      "latency_us": {"p10": lat[len(lat) // 10], "median": med, "p90": lat[(9 * len(lat)) // 10], "cuda_graph_replay_median": graph_us},
+                      "stage_us": stages, "gpu_launches": launches,
+                      "e2e": {"value": host_us, "unit": "us", "note": "LeastSquaresEstimator/Optimizer + Interpolator2D classes, NumPy in / NumPy out",
+                              "h2d_bytes_per_step": int(3 * H * W * 4 + H * W), "d2h_bytes_per_step": int(2 * H * W * 4)},
+                      "roofline": {"kernel": "front-end (all launches)", "bound": "hbm", "achieved": algorithmic / (med * 1e-6) / 1e9, "peak": peaks["hbm"],
+                                   "unit": "GB/s", "frac": algorithmic / (med * 1e-6) / 1e9 / peaks["hbm"], "traffic": None,
+                                   "note": "one frame = 8.5 MB of algorithmic traffic = 1.3 us at the HBM peak: a single frame is latency-bound "
+                                           "by construction (SURVEY H7); the figure of merit is the latency"},
+                      "cpu_baseline": {"value": cpu_us, "unit": "us", "cores": os.cpu_count(), "kind": "port",
+                                       "sample": "the same frame through oracle.chain_ref.sml_front_end_ref (NumPy LSQ / SciPy Brent + SciPy griddata)"},
+                      "parity": parity}), flush=True)
+    return 0
+
+
+def run_train(args):
+    raise SystemExit("bench.py --workload train: see riders_b200/train.py (configs[3]); not built into this checkout yet")
+
+
+def workload_config(n_gpus, note=None, frames_per_gpu=FRAMES_PER_GPU, total=None, align="st", strict=False):
+    total = total if total is not None else frames_per_gpu * n_gpus
+    c = {"workload": "configs[1] RC-Net inference (run_rcnet_zju path) + SML front-end (%s + scale-map "
+                     "interpolation): synthetic 640x512 thermal frames, 512 radar points/frame, thr 0.1"
+                     % ("LSQ scale/shift align" if align == "st" else "L1 Optimizer scale align (the scripts' default)"),
+         "frames_per_gpu_per_step": frames_per_gpu, "radar_points_per_frame": K_POINTS, "patch": list(PATCH),
+         "global_frames_per_step": total, "parallelism": "frame-sharded x%d (no data-path collective)" % n_gpus,
+         "global_alignment": align, "strict_fp32": bool(strict),
          "inputs": "as loaded: [0,255] frames + radar points in frame coordinates; prologue (shift/boxes/normalise/pad), "
                    "empty-frame retry check, scale scaffold and SML input assembly (352x288) inside the timed region",
          "l2": "per-step working set (11.4 GB gathered features, 0.8 GB logits) >> 126 MB L2; no flush needed"}
@@ -164,13 +432,28 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager"])
+    ap.add_argument("--workload", default="chain", choices=["chain", "config1", "train"],
+                    help="chain: configs[1] (default); config1: one frame, 200 points, SML front-end latency; "
+                         "train: configs[3] RC-Net training step (bf16 autocast, gradient all-reduce)")
+    ap.add_argument("--strict-fp32", action="store_true",
+                    help="cuDNN / cuBLAS TF32 off and no TF32 decoder tail: every stage in fp32 (the 1e-4 parity configuration)")
+    ap.add_argument("--align", default="st", choices=["st", "s"],
+                    help="global alignment: st = least squares (north_star kernel 4), s = the scripts' default L1 Optimizer")
+    ap.add_argument("--global-frames", type=int, default=0,
+                    help="strong scaling (configs[2]): this many frames per step split over the ranks")
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--profile", action="store_true", help=argparse.SUPPRESS)   # under ncu: 1 warm-up, no e2e / cpu legs
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "eager":
+        return run_eager(args)
+    if args.workload == "config1":
+        return run_config1(args)
+    if args.workload == "train":
+        return run_train(args)
     args.warmup = 1 if args.profile else max(args.warmup, 3)
 
     if not torch.cuda.is_available():
@@ -180,15 +463,23 @@ def main():
     rank, world, local = rdist.init()
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
-    B = args.frames
+    pin_rank_cores(local, world)
+    strong = args.global_frames > 0
+    B = rdist.shard_frames(args.global_frames, rank, world)[1] - rdist.shard_frames(args.global_frames, rank, world)[0] \
+        if strong else args.frames
+    first_frame = rdist.shard_frames(args.global_frames, rank, world)[0] if strong else rank * B
     peaks = load_peaks()
+    if args.strict_fp32:
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    tf32 = bool(torch.backends.cudnn.allow_tf32)
 
     model = build_model(device)
     # inputs "as loaded": [0,255] frames and radar points in frame coordinates; the prologue (shift, boxes, normalise,
     # pad), the empty-frame retry check and the SML input assembly all run inside the timed region
     pipe = RadarDepthPipeline(model, response_thr=THR, chunk_points=int(os.environ.get("RIDERS_CHUNK_POINTS", "2048")), raw_inputs=True,
-                              retry_empty=True, sml_input=True)
-    batch = synth.chain_batch(rank * B, B, K_POINTS, H, W, PATCH)
+                              retry_empty=True, sml_input=True, global_alignment=args.align)
+    batch = synth.chain_batch(first_frame, B, K_POINTS, H, W, PATCH)
     batch["images"] = np.rint(batch["images"] * 255.0).astype(np.float32)
     batch["points"] = (batch["points"] - np.array([PATCH[1] // 2, PATCH[0] // 2, 0], np.float32)).astype(np.float32)
     host = {k: torch.from_numpy(batch[k]).pin_memory() for k in ("images", "points", "mono", "sparse")}
@@ -196,7 +487,14 @@ def main():
     offsets = batch["offsets"]
 
     def step_device():
-        return pipe.run_device(dev["images"], dev["points"], offsets, dev["mono"], dev["sparse"])
+        o = pipe.run_device(dev["images"], dev["points"], offsets, dev["mono"], dev["sparse"])
+        # the path's only collective, INSIDE the timed step: per-frame means of the result maps -> one all-reduce of 5 doubles
+        # over NCCL (asynchronous, no host sync); rank 0 divides after the timed region
+        o["metric_sums"] = rdist.all_reduce_sums_device(torch.stack([
+            o["depth"].double().mean(dim=(1, 2)).sum(), (o["response"] > 0).double().mean(dim=(1, 2)).sum(),
+            o["int_depth"].double().mean(dim=(1, 2)).sum(), o["scale_map"].double().mean(dim=(1, 2)).sum(),
+            torch.tensor(float(o["depth"].shape[0]), dtype=torch.float64, device=device)]))
+        return o
 
     sampler = ClockSampler(local) if rank == 0 else None        # started early: nvidia-smi needs ~0.5 s to deliver samples
     # cuDNN picks its convolution algorithms by timing them in the first call: run that one (untimed, not counted in W)
@@ -230,9 +528,9 @@ def main():
     stages = timer.summary()
 
     # the final metric reduction (the path's only collective): per-frame means of the three maps
-    sums = torch.stack([out["depth"].double().mean(dim=(1, 2)).sum(), (out["response"] > 0).double().mean(dim=(1, 2)).sum(),
-                        out["int_depth"].double().mean(dim=(1, 2)).sum(), out["scale_map"].double().mean(dim=(1, 2)).sum()])
-    means, n_frames = rdist.reduce_metric_sums(sums, B)
+    vec = out["metric_sums"].cpu()
+    n_frames = int(round(vec[-1].item()))
+    means = vec[:-1] / vec[-1]
     assert int(out["interp_status"].abs().sum().item()) == 0, "interpolation reported a failed frame"
 
     # ---------------------------------------------------------------- end to end (pinned host in / out)
@@ -270,6 +568,10 @@ def main():
     # Every ops.* wrapper reports the algorithmic bytes (flops for LoFTR) of its call next to the CUDA events that
     # bracket it.  The gather additionally reads each frame's feature maps once.
     TENSOR = {"loftr_transformer", "decoder_tail", "subpixel_conv"}
+    # the roofline object is for the dominant kernel among the SURVEY section-8 rows (the path this repo exists for);
+    # the decoder glue / tail around the cuDNN convolutions (out of scope as kernels) stay in `stages`
+    SECTION8 = {"roi_gather", "loftr_transformer", "confidence_reduce", "lsq_align", "l1_scale_align", "extract_knots",
+                "interp_triangulate", "interp_fill", "interp_linear"}
     stage_report = {}
     for name, (calls, ms, amount) in stages.items():
         bound = "tensor" if name in TENSOR else "hbm"
@@ -280,7 +582,7 @@ def main():
                               "work_per_step": amount / args.steps, "achieved": round(ach, 2),
                               "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac": round(ach / peaks[bound], 4)}
     ms_step = ms_total / args.steps
-    dom = max(stage_report, key=lambda k: stage_report[k]["ms_per_step"])
+    dom = max((k for k in stage_report if k in SECTION8), key=lambda k: stage_report[k]["ms_per_step"])
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
@@ -291,19 +593,20 @@ def main():
                 "frac": d["frac"], "traffic": traffic, "peak_source": peaks["source"],
                 "launches_per_step": d["calls_per_step"], "algorithmic_work_per_launch": d["work_per_step"] / max(d["calls_per_step"], 1),
                 "avg_launch_ms": d["ms_per_step"] / max(d["calls_per_step"], 1), "share_of_step": round(d["ms_per_step"] / ms_step, 4)}
-    if dom == "decoder_tail":
-        # the tail is a TF32 mma.sync kernel (N = 16 output channels): its FLOPs are held against the measured
-        # bf16 dense peak like every tensor-bound stage, of which that instruction reaches at most ~20 %
-        roofline["note"] = ("TF32 mma.sync (512 MAC/cycle/SM measured = 280 TFLOP/s = 0.20 of this peak); fused kernel: HBM traffic "
-                            "3.3 GB per launch instead of 15.7 GB for the three passes it replaces")
+    roofline["scope"] = "dominant kernel among the SURVEY section-8 rows; decoder glue / tail (out of scope as kernels) are in `stages`"
+    if dom == "loftr_transformer":
+        roofline["note"] = ("algorithmic fp32 FLOPs of the 16 layer calls against the measured bf16 dense peak; the fp32-accurate "
+                            "fp16 hi/lo operand split issues 3 MMAs per product, so tensor-pipe occupancy is ~3x this fraction")
 
     line = None
     if rank == 0:
-        line = {"metric": METRIC, "value": world * B * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+        total_frames = args.global_frames if strong else world * B
+        line = {"metric": METRIC, "value": total_frames * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(world), "clocks": clocks, "gpu_launches": int(launches),
-                "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": dtype_label(tf32), "data": "synthetic",
+                "config": workload_config(world, frames_per_gpu=B, total=total_frames, align=args.align, strict=args.strict_fp32),
+                "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": total_frames * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "roofline": roofline, "stages": stage_report,
                 "our_kernels_share_of_step": round(sum(s["ms_per_step"] for s in stage_report.values()) / ms_step, 4),
@@ -311,10 +614,18 @@ def main():
                             "mean_int_depth": means[2].item(), "mean_scale": means[3].item()},
                 "loftr_impl": os.environ.get("RIDERS_LOFTR_IMPL", "default")}
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, range(os.cpu_count() or 1)) if hasattr(os, "sched_setaffinity") else None
             torch.set_num_threads(os.cpu_count() or 1)
-            v, n, dt = cpu_frame_rate(12.0)
+            v, n, dt, refs = cpu_frame_rate(12.0, global_alignment=args.align)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": "%d frame(s) (K=512) of the same batch through the oracle port, %.1f s" % (n, dt)}
+            # parity of the configuration that was just timed (same model object, same flags), on the frames the CPU leg ran
+            pipe.return_select = True
+            pout = step_device()
+            torch.cuda.synchronize()
+            pipe.return_select = False
+            line["parity"] = parity_block(pout, refs)
+            line["parity"]["mode"] = dtype_label(tf32)
         print(json.dumps(line), flush=True)
     rdist.shutdown()
     return 0

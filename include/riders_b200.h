@@ -237,7 +237,8 @@ int riders_depth_metrics(const float* pred, const float* gt, int B, int H, int W
  *       (exact integer predicates) + per-pixel barycentric fill in fp64, `fill` outside the
  *       convex hull, float32 out (B,H,W).  Knots must be distinct pixels with 0 <= x,y < 8192.
  *       status (B) int32: 0 ok, RIDERS_EQHULL where SciPy would raise QhullError (the frame is
- *       then filled with `fill`), RIDERS_EINTERNAL if the edge pool overflowed.  Knots of frame b are knot_xy[b*max_knots .. +knot_count[b]).
+ *       then filled with `fill`), RIDERS_EINTERNAL if the edge pool overflowed or knot_count[b] > max_knots
+ *       (a truncated knot set is never triangulated: the frame is filled with `fill`).  Knots of frame b are knot_xy[b*max_knots .. +knot_count[b]).
  *       If tri_out != NULL it receives the triangles (B, 2*max_knots, 3) int32 (-1 padded) and
  *       tri_count (B).
  * ------------------------------------------------------------------------------------------ */

@@ -27,11 +27,19 @@ def sparse_inverse_ref(sparse_depth, min_depth=0.0, max_depth=100.0):
 
 
 def sml_front_end_ref(mono_pred, sparse_depth, min_depth=0.0, max_depth=100.0, clamp_min=0.1, clamp_max=255.0,
-                      acc_dtype=np.float64, interpolate=True):
+                      acc_dtype=np.float64, interpolate=True, global_alignment="st", mono_type="inv"):
     """Alignment + scale scaffold of one frame.  acc_dtype=float64 is 'the reference fed float64
-    inputs' (SURVEY H2); float32 the as-shipped behaviour."""
+    inputs' (SURVEY H2); float32 the as-shipped behaviour.  global_alignment 'st' = val_zju.py:146-155
+    (least squares), 's' = val_zju.py:156-167 (Optimizer: SciPy bounded Brent on the masked L1 objective,
+    fed float64 inputs; output = estimate * float32(scale), the numpy 1.23 casting of the pinned environment)."""
     sparse_inv, valid = sparse_inverse_ref(sparse_depth, min_depth, max_depth)
-    s, t = er.scale_shift_ls_ref(mono_pred, sparse_inv, valid, acc_dtype)
+    if global_alignment == "s":
+        s = er.optimize_scale_ref(np.asarray(mono_pred, np.float64), np.asarray(sparse_inv, np.float64), valid, mono_type)
+        t = 0.0
+    elif global_alignment == "st":
+        s, t = er.scale_shift_ls_ref(mono_pred, sparse_inv, valid, acc_dtype)
+    else:
+        raise NotImplementedError(global_alignment)
     int_depth = er.apply_clamp_ref(mono_pred, s, t, clamp_min, clamp_max)
     out = {"scale": float(s), "shift": float(t), "int_depth": int_depth, "valid": valid, "sparse_inv": sparse_inv}
     if interpolate:
@@ -47,7 +55,11 @@ def chain_frame_ref(model_cpu, frame, response_thr=0.1, patch=None, **kw):
     image = torch.from_numpy(frame["image"])[None]
     pts = torch.from_numpy(frame["points"])
     boxes = [torch.from_numpy(frame["boxes"])]
-    depth, response, select = forward_output_ref(model_cpu, image, pts, boxes, response_thr)
+    want_conf = kw.pop("want_conf", False)
+    res = forward_output_ref(model_cpu, image, pts, boxes, response_thr, want_conf=want_conf)
+    depth, response, select = res[:3]
     out = sml_front_end_ref(frame["mono"], frame["sparse"], **kw)
     out.update(depth=depth[0].numpy(), response=response[0].numpy(), select=select[0].numpy())
+    if want_conf:
+        out["conf"] = res[3]                       # (K, ph, pw) confidences, for the top-2 margin of the select rule
     return out

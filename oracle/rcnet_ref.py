@@ -65,7 +65,7 @@ def encoder_forward_ref(encoder, image, points, b_boxes):
     latent_h, latent_w = int(ph // 32.0), int(pw // 32.0)
     skip_scales = [1 / 2.0, 1 / 4.0, 1 / 8.0, 1 / 16.0, 1 / 32.0, 1 / 64.0, 1 / 128.0]
     latent_image, skips_image = enc.encoder_image(image)
-    boxes = [torch.as_tensor(b, dtype=torch.float32) for b in b_boxes]
+    boxes = [torch.as_tensor(b, dtype=torch.float32).to(image.device) for b in b_boxes]
     latent_pooled = torchvision.ops.roi_pool(latent_image, boxes, spatial_scale=1 / 32.0,
                                              output_size=(latent_h, latent_w))
     skips_pooled = [torchvision.ops.roi_pool(s, boxes, spatial_scale=skip_scales[i],
@@ -89,7 +89,7 @@ def model_forward_ref(model, image, points, b_boxes, return_logits=True):
 
 
 @torch.no_grad()
-def forward_output_ref(model, image, radar_points, bounding_boxes_list, response_thr=0.5, literal=False):
+def forward_output_ref(model, image, radar_points, bounding_boxes_list, response_thr=0.5, literal=False, want_conf=False):
     """CPU restatement of rcnet_main.py:435-487.  Returns depth (1,H,W), response (1,H,W), select (1,H,W)."""
     ph, pw = model.input_patch_size_image
     px, py = pw // 2, ph // 2
@@ -101,7 +101,7 @@ def forward_output_ref(model, image, radar_points, bounding_boxes_list, response
     if literal:
         tiles = []
         for crop, p in zip(conf, radar_points):
-            canvas = torch.zeros([1, padded.shape[-2], padded.shape[-1]])
+            canvas = torch.zeros([1, padded.shape[-2], padded.shape[-1]], device=conf.device)
             crop = torch.where(crop < response_thr, torch.zeros_like(crop), crop)
             x, y = int(p[0]), int(p[1])
             canvas[:, y - py:y + py, x - px:x + px] = crop
@@ -111,6 +111,10 @@ def forward_output_ref(model, image, radar_points, bounding_boxes_list, response
         depth = torch.sum(tiles * radar_points[:, 2].unsqueeze(1).unsqueeze(1), dim=0, keepdim=True) / \
             torch.sum(tiles, dim=0, keepdim=True)
         depth = torch.where(response == 0, torch.zeros_like(depth), depth)
+        if want_conf:
+            return depth, response, select, conf[:, 0].cpu().numpy()
         return depth, response, select
     d, r, s = confidence_reduce_ref(conf[:, 0].numpy(), radar_points.numpy(), H, W, response_thr)
+    if want_conf:
+        return torch.from_numpy(d)[None], torch.from_numpy(r)[None], torch.from_numpy(s)[None], conf[:, 0].numpy()
     return torch.from_numpy(d)[None], torch.from_numpy(r)[None], torch.from_numpy(s)[None]

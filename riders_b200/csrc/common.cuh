@@ -20,6 +20,18 @@ void count_launches(int n);                   // feeds riders_launch_count() (be
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Opt a kernel into `bytes` of dynamic shared memory on the CURRENT device.  The attribute is per device (and per
+// context), so the "already done" cache is indexed by device: a second GPU in the same process gets its own opt-in.
+template <typename Kernel>
+inline int ensure_dynamic_smem(Kernel kernel, size_t bytes, size_t (&cache)[64], const char* what) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (bytes <= cache[dev]) return RIDERS_OK;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return check_launch(what);
+    cache[dev] = bytes;
+    return RIDERS_OK;
+}
+
 __device__ __forceinline__ float ld_stream(const float* p) {
     // read-once data: bypass L1 allocation
     float v;

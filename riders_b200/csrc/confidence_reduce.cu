@@ -30,7 +30,7 @@ __device__ __forceinline__ float conf_value(float v, float thr) {
     // torch.sigmoid (rcnet_model.py:123): 1 / (1 + exp(-v)) with the SFU exp2 / reciprocal (relative
     // error ~2e-7, far inside the 1e-4 tolerance on confidences); strict < (rcnet_main.py:462).
     // A pixel the crop does not cover is loaded as 0 (confidences) / -inf (logits) -> contributes exactly 0.
-    if (LOGITS) v = __fdividef(1.0f, 1.0f + __expf(-v));
+    if (LOGITS) v = (1.0f / (1.0f + expf(-v)))   /* full-precision expf + IEEE division: a confidence within 1 ulp of the strict `< thr` cut must not flip */;
     return (v < thr) ? 0.0f : v;
 }
 

@@ -85,7 +85,7 @@ conv3x3_head_kernel(const float4* __restrict__ x, float* __restrict__ out, const
         const float t2 = __shfl_up_sync(0xffffffffu, d[2][0], 1) + d[2][1] + __shfl_down_sync(0xffffffffu, d[2][2], 1);   // -> row h-1
         acc_prev += t2;
         if (writes && h - 1 >= r0 && h - 1 < r1)
-            __stcs(o + (size_t)(h - 1) * W + col, P.sigmoid ? __fdividef(1.0f, 1.0f + __expf(-acc_prev)) : acc_prev);
+            __stcs(o + (size_t)(h - 1) * W + col, P.sigmoid ? (1.0f / (1.0f + expf(-acc_prev))) : acc_prev);
         acc_prev = acc_cur + t1;
         acc_cur = t0;
     }

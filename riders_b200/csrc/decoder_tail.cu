@@ -234,7 +234,7 @@ decoder_tail_kernel(const float4* __restrict__ y4, const float4* __restrict__ wb
                 float s = 0.f;
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) s += up[tap * UP + (tap / 3) * ZW + (tap % 3)];
-                __stcs(o + (size_t)(R0 + oy) * W + C0 + ox, P.sigmoid ? __fdividef(1.0f, 1.0f + __expf(-s)) : s);
+                __stcs(o + (size_t)(R0 + oy) * W + C0 + ox, P.sigmoid ? (1.0f / (1.0f + expf(-s))) : s);
             }
             ox += THREADS % TW; oy += THREADS / TW;
             if (ox >= TW) { ox -= TW; ++oy; }
@@ -308,12 +308,8 @@ extern "C" int riders_decoder_tail_nhwc(const float* y4, int taps, int N, int h,
     const int tiles_x = ceil_div(2 * w, tail::TW), tiles_y = ceil_div(2 * h, tail::TH);
     const long long blocks = (long long)N * tiles_x * tiles_y;
     RIDERS_REQUIRE(blocks < (1ll << 31), "decoder_tail: too many tiles for one launch");
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(tail::decoder_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tail::SMEM_BYTES) != cudaSuccess)
-            return check_launch("decoder_tail: shared memory attribute");
-        configured = true;
-    }
+    static size_t configured[64] = {0};
+    if (int rc_smem = ensure_dynamic_smem(tail::decoder_tail_kernel, (size_t)(tail::SMEM_BYTES), configured, "decoder_tail: shared memory attribute")) return rc_smem;
     count_launches(1);
     tail::decoder_tail_kernel<<<(unsigned)blocks, tail::THREADS, tail::SMEM_BYTES, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(y4), reinterpret_cast<const float4*>(wb_frag), out, P, h, w, tiles_x, tiles_y);

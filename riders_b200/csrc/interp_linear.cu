@@ -152,6 +152,11 @@ delaunay_kernel(const int32_t* __restrict__ knot_xy, const float* __restrict__ k
     const float* val = knot_val + (size_t)frame * max_knots;
 
     if (tid < 8) w.counters[tid] = 0;
+    if (knot_count[frame] > max_knots) {
+        // more valid pixels than the caller's capacity: never triangulate a truncated knot set silently
+        if (tid == 0) { status[frame] = RIDERS_EINTERNAL; if (tri_count) tri_count[frame] = 0; }
+        return;
+    }
     if (n < 3) {
         if (tid == 0) { status[frame] = RIDERS_EQHULL; if (tri_count) tri_count[frame] = 0; }
         return;
@@ -335,12 +340,8 @@ extern "C" int riders_interp_triangulate(const int32_t* knot_xy, const float* kn
     const SmemMesh S = smem_mesh_layout(max_knots, L);
     const int mesh_in_smem = S.total <= 200 * 1024 ? 1 : 0;               // ~680 knots; larger frames chase pointers in L2
     if (mesh_in_smem) {
-        static size_t configured = 0;
-        if (S.total > configured) {
-            if (cudaFuncSetAttribute(delaunay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total) != cudaSuccess)
-                return check_launch("interp_triangulate: smem attribute");
-            configured = S.total;
-        }
+        static size_t configured[64] = {0};
+        if (int rc_smem = ensure_dynamic_smem(delaunay_kernel, (size_t)(S.total), configured, "interp_triangulate: smem attribute")) return rc_smem;
     }
     count_launches(1);
     delaunay_kernel<<<B, DT_THREADS, mesh_in_smem ? S.total : 0, st>>>(knot_xy, knot_val, knot_count, max_knots, (uint8_t*)workspace, L,

@@ -796,12 +796,8 @@ int loftr_tc_pack(const riders_loftr_weights& w, int layer_slot, void* tc_ws, cu
 
 int loftr_tc_run(const float* x, const float* src, const riders_loftr_weights& w, int layer_slot,
                  int N, float attn_eps, float ln_eps, float* out, void* tc_ws, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(tc::loftr_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES) != cudaSuccess)
-            return check_launch("loftr(tcgen05): shared memory attribute");
-        configured = true;
-    }
+    static size_t configured[64] = {0};
+    if (int rc_smem = ensure_dynamic_smem(tc::loftr_layer_tc_kernel, (size_t)(tc::SMEM_BYTES), configured, "loftr(tcgen05): shared memory attribute")) return rc_smem;
     RIDERS_REQUIRE(out != x && out != src, "loftr(tcgen05): out must not alias an input");
     tc::LayerArgs P;
     P.x = x; P.src = src; P.out = out;
@@ -823,12 +819,8 @@ extern "C" int riders_debug_tc_gemm(const float* a, const float* b, float* d, in
     RIDERS_REQUIRE(a && b && d, "debug_tc_gemm: null pointer");
     RIDERS_REQUIRE((K == 64 || K == 128) && (terms == 1 || terms == 3), "debug_tc_gemm: K=%d terms=%d unsupported", K, terms);
     const int smem = 1024 + 2 * tc::OPER_BYTES;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(tc::tc_gemm_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-            return check_launch("debug_tc_gemm: shared memory attribute");
-        configured = true;
-    }
+    static size_t configured[64] = {0};
+    if (int rc_smem = ensure_dynamic_smem(tc::tc_gemm_selftest_kernel, (size_t)(smem), configured, "debug_tc_gemm: shared memory attribute")) return rc_smem;
     count_launches(1);
     tc::tc_gemm_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a, b, d, K, terms);
     return check_launch("debug_tc_gemm");
@@ -845,12 +837,8 @@ extern "C" int riders_debug_tc_mma_rate(int mode, int count, int ctas, long long
     const int nacc = (mode >> 4) & 15, n = 64 << (mode & 3);
     RIDERS_REQUIRE((mode & 3) < 3 && nacc >= 1 && nacc * n <= 512, "debug_tc_mma_rate: mode %d unsupported", mode);
     const int smem = 1024 + 6 * tc::SLAB;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(tc::tc_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-            return check_launch("debug_tc_mma_rate: shared memory attribute");
-        configured = true;
-    }
+    static size_t configured[64] = {0};
+    if (int rc_smem = ensure_dynamic_smem(tc::tc_mma_rate_kernel, (size_t)(smem), configured, "debug_tc_mma_rate: shared memory attribute")) return rc_smem;
     count_launches(1);
     tc::tc_mma_rate_kernel<<<ctas, 128, smem, (cudaStream_t)stream>>>(mode, count, device_cycles);
     return check_launch("debug_tc_mma_rate");

@@ -465,12 +465,8 @@ static int launch_tma_pack(TmaPack& P, int R, cudaStream_t st) {
         blocks += (long long)R * L.strips;
     }
     RIDERS_REQUIRE(blocks < (1ll << 31), "roi_gather: too many CTAs for one launch; chunk the RoIs");
-    static size_t configured = 0;
-    if (smem > configured) {
-        if (cudaFuncSetAttribute(roi_gather_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return check_launch("roi_gather: smem attribute");
-        configured = smem;
-    }
+    static size_t configured[64] = {0};
+    if (int rc_smem = ensure_dynamic_smem(roi_gather_tma_kernel, (size_t)(smem), configured, "roi_gather: smem attribute")) return rc_smem;
     count_launches(1);
     roi_gather_tma_kernel<<<(unsigned)blocks, TMA_THREADS, smem, st>>>(P);
     return RIDERS_OK;

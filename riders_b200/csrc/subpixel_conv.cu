@@ -171,12 +171,8 @@ extern "C" int riders_subpixel_conv_act_nhwc(const float* x, const float* bias_h
     const int row_tiles = ceil_div(h + 1, spc::TP);
     const long long blocks = (long long)N * row_tiles;
     RIDERS_REQUIRE(blocks < (1ll << 31), "subpixel_conv: too many tiles for one launch");
-    static size_t configured = 0;
-    if (configured < smem) {
-        if (cudaFuncSetAttribute(spc::subpixel_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return check_launch("subpixel_conv: shared memory attribute");
-        configured = smem;
-    }
+    static size_t configured[64] = {0};
+    if (int rc_smem = ensure_dynamic_smem(spc::subpixel_conv_kernel, (size_t)(smem), configured, "subpixel_conv: shared memory attribute")) return rc_smem;
     count_launches(1);
     spc::subpixel_conv_kernel<<<(unsigned)blocks, spc::THREADS, smem, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(w_frag), y4, P, h, w, row_tiles);

@@ -209,12 +209,8 @@ extern "C" int riders_subpixel_conv_tc_nhwc(const float* x, const float* w_pack,
     const long long tiles = (long long)N * P.pairs;
     RIDERS_REQUIRE(tiles < (1ll << 31), "subpixel_conv_tc: too many tiles for one launch");
     P.n_tiles = (int)tiles;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(spctc::subpixel_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, spctc::SMEM_BYTES) != cudaSuccess)
-            return check_launch("subpixel_conv_tc: shared memory attribute");
-        configured = true;
-    }
+    static size_t configured[64] = {0};
+    if (int rc_smem = ensure_dynamic_smem(spctc::subpixel_conv_tc_kernel, (size_t)(spctc::SMEM_BYTES), configured, "subpixel_conv_tc: shared memory attribute")) return rc_smem;
     const int grid = tiles < sm_count() ? (int)tiles : sm_count();
     count_launches(1);
     spctc::subpixel_conv_tc_kernel<<<grid, spctc::THREADS, spctc::SMEM_BYTES, (cudaStream_t)stream>>>(P);

@@ -96,6 +96,15 @@ def reduce_metric_sums(sums, n_frames):
     return means, int(round(total))
 
 
+def all_reduce_sums_device(vec):
+    """In-place SUM all-reduce of a small device (or CPU) tensor on the current stream, no host synchronisation: the per-step
+    form of ``reduce_metric_sums`` (the caller appends the frame count as the last element and divides when it finally
+    reads the vector).  A 1-process run returns ``vec`` untouched."""
+    if dist.is_initialized():
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+    return vec
+
+
 def max_over_ranks(value):
     """Max of a python float over ranks (device timings are reported as the slowest rank's)."""
     if not dist.is_initialized():

@@ -19,9 +19,13 @@ _NAMES = {
 
 
 def install(patch_rcnet_main=True):
-    """Returns the dict name -> module that was installed.  With ``patch_rcnet_main`` an already
-    imported (or importable) reference ``rcnet_main`` gets its ``forward_output`` replaced, so
-    ``rcnet_main.validate`` (RCNet/rcnet_main.py:558) uses the reduce kernel too."""
+    """Returns the dict name -> module that was installed.  With ``patch_rcnet_main`` the REFERENCE's own ``rcnet_main``
+    module (already imported, or importable from ``sys.path`` - the scripts run with ``RCNet/`` on the path) keeps all its
+    names (``train``, ``validate``, ``log_network_settings``, ``log_evaluation_results`` ... that
+    ``run_rcnet_zju.py:9`` / ``train_rcnet_zju.py`` import) and only gets its ``forward_output`` replaced, so
+    ``rcnet_main.validate`` (RCNet/rcnet_main.py:558) and the run scripts use the reduce kernel.  The module is never
+    swapped for the mirror; only when no reference ``rcnet_main`` can be imported at all does the name resolve to the
+    mirror (which then offers ``forward_output`` / ``forward_output_batched`` only)."""
     import importlib
     done = {}
     for alias, target in _NAMES.items():
@@ -31,10 +35,19 @@ def install(patch_rcnet_main=True):
     from .rcnet import rcnet_main as ours
     if patch_rcnet_main:
         ref = sys.modules.get("rcnet_main")
+        if ref is None:
+            try:
+                ref = importlib.import_module("rcnet_main")          # the reference's, found through the caller's sys.path
+            except Exception:                                         # not importable here (missing deps / not on the path)
+                ref = None
         if ref is not None and ref is not ours:
+            if not hasattr(ref, "_riders_reference_forward_output"):
+                ref._riders_reference_forward_output = getattr(ref, "forward_output", None)
             ref.forward_output = ours.forward_output
+            done["rcnet_main"] = ref
         else:
             sys.modules["rcnet_main"] = ours
+            done["rcnet_main"] = ours
         done["rcnet_main.forward_output"] = ours.forward_output
     return done
 
@@ -43,3 +56,9 @@ def uninstall():
     for alias, target in _NAMES.items():
         if sys.modules.get(alias) is sys.modules.get(target):
             del sys.modules[alias]
+    ref = sys.modules.get("rcnet_main")
+    if ref is not None and hasattr(ref, "_riders_reference_forward_output"):
+        ref.forward_output = ref._riders_reference_forward_output
+        del ref._riders_reference_forward_output
+    elif ref is not None and ref.__name__.startswith("riders_b200."):
+        del sys.modules["rcnet_main"]

@@ -71,9 +71,20 @@ def launch_count():
 
 
 def _need_cuda(*tensors):
+    """CUDA tensors only (no CPU fallback), all on the CURRENT device: the wrappers launch on
+    ``torch.cuda.current_stream()`` of the current device, so a tensor living on another GPU would be addressed from the
+    wrong context - refuse it loudly (wrap the call in ``with torch.cuda.device(t.device):``)."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise _lib.RidersError("riders_b200 ops need CUDA tensors (no CPU fallback); got device %s" % t.device)
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise _lib.RidersError("riders_b200 ops launch on the current device (cuda:%d) but got a tensor on %s; "
+                                   "use `with torch.cuda.device(tensor.device):`" % (cur, t.device))
 
 
 def _f32c(t):
@@ -645,13 +656,23 @@ def confidence_reduce(conf, points, frame_offsets, H, W, thr, logits=False, want
 # --------------------------------------------------------------------------------------------
 # A6/A7 alignment
 # --------------------------------------------------------------------------------------------
+def _binary_mask(mask):
+    """The reference multiplies by ``mask`` (modules/estimator.py:10-16), and every caller passes the boolean validity map
+    (val_zju.py:130-131,141).  The kernels take a 0/1 byte mask; a floating-point WEIGHT mask would be truncated to 0/1,
+    so it is refused instead of being silently changed."""
+    if mask.is_floating_point():
+        raise _lib.RidersError("alignment kernels take a boolean / integer 0-1 validity mask; floating-point weight masks "
+                               "are not supported (they would be truncated)")
+    mask = mask.contiguous()
+    return mask.view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8)
+
+
 def lsq_align(pred, target, mask, clamp_hi=None, clamp_lo=None, want_out=True):
     """pred/target (B,H,W) float32, mask (B,H,W) bool/uint8 (all CUDA).
     Returns sums (B,5) f64, scale_shift (B,2) f64, out (B,H,W) f32 | None."""
     _need_cuda(pred, target, mask)
     pred, target = _f32c(pred), _f32c(target)
-    mask = mask.contiguous()
-    mask = mask.view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8)
+    mask = _binary_mask(mask)
     B, H, W = pred.shape
     dev = pred.device
     L = _lib.lib()
@@ -673,8 +694,7 @@ def l1_scale_align(pred, target, mask, bounds=(0.01, 0.3), clamp_hi=None, clamp_
     nfev (B,) int32, out (B,H,W) f32 | None."""
     _need_cuda(pred, target, mask)
     pred, target = _f32c(pred), _f32c(target)
-    mask = mask.contiguous()
-    mask = mask.view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8)
+    mask = _binary_mask(mask)
     B, H, W = pred.shape
     dev = pred.device
     cap = int(max_valid) if max_valid else H * W

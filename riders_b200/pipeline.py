@@ -25,11 +25,28 @@ from .rcnet.rcnet_main import forward_output_batched
 class RadarDepthPipeline(object):
     def __init__(self, model, response_thr=0.1, min_depth=0.0, max_depth=100.0,
                  clamp_min=0.1, clamp_max=255.0, chunk_points=2048, max_knots=None,
-                 raw_inputs=False, retry_empty=False, sml_input=False, overlap_front_end=True):
+                 raw_inputs=False, retry_empty=False, sml_input=False, overlap_front_end=True,
+                 global_alignment='st', mono_type='inv', return_select=False, sml_model=None, host_keys=None):
         """raw_inputs: frames as loaded ([0,255]) and radar points in frame coordinates (the prologue kernel does the
         shift / boxes / normalisation / pad of run_rcnet_zju.py:214-240); retry_empty: the script's threshold-lowering
         retry for frames where nothing fires (:254-265); sml_input: also assemble the SML network's inputs (x, d) of
-        val_zju.py:181-196 (resize to 288-multiple-of-32, normalise, gray channel)."""
+        val_zju.py:181-196 (resize to 288-multiple-of-32, normalise, gray channel).
+        global_alignment: 'st' = least-squares scale + shift (val_zju.py:146-155), 's' = the scripts' default, the bounded-Brent
+        L1 scale of ``Optimizer`` (val_zju.py:156-167, bounds by ``mono_type`` 'inv' | 'pos').
+        sml_model: any ``nn.Module`` with ``forward(x, d)`` (the reference's MidasNet_small_videpth is not constructible
+        offline, modules/midas/blocks.py:44-51): when given it is fed the assembled inputs and its prediction is inverted and
+        bicubically resized to the frame like val_zju.py:198-210 (``out['sml_pred']``); without it the chain ends at the
+        network's inputs (``sml_x``, ``sml_d``).
+        host_keys: which results the host entry points copy back (default: the maps a caller consumes on the host; the SML
+        inputs stay on the device unless asked for)."""
+        if global_alignment not in ('st', 's'):
+            raise NotImplementedError(global_alignment)                 # val_zju.py:168-169
+        self.global_alignment, self.mono_type = global_alignment, mono_type
+        self.return_select = bool(return_select)
+        self.sml_model = sml_model
+        if sml_model is not None:
+            sml_input = True
+        self.host_keys = tuple(host_keys) if host_keys is not None else None
         self.raw_inputs, self.retry_empty, self.sml_input = bool(raw_inputs), bool(retry_empty), bool(sml_input)
         self.overlap_front_end = bool(overlap_front_end)
         self._side = None
@@ -43,6 +60,50 @@ class RadarDepthPipeline(object):
         self._pinned = {}
         self._copy_streams = None
         self._slot = 0
+
+    # ------------------------------------------------------------------------------ SML front-end
+    @torch.no_grad()
+    def align_and_interpolate(self, mono_pred, sparse_depth, max_knots):
+        """The RC-Net-independent half of the SML front-end for a batch of frames (BASELINE configs[0]): inverse sparse
+        depth + validity (val_zju.py:130-133), global alignment (:146-167), knot extraction + Delaunay + barycentric scale
+        map (modules/interpolator.py).  Knot capacity: the knots are the valid pixels of ``sparse_depth``; a frame with
+        more of them than ``max_knots`` is NOT truncated silently - its ``interp_status`` is RIDERS_EINTERNAL and its map
+        the fill value."""
+        valid = (sparse_depth < self.max_depth) & (sparse_depth > self.min_depth)
+        sparse_inv = torch.where(valid, 1.0 / sparse_depth, torch.zeros_like(sparse_depth))
+        if self.global_alignment == 'st':
+            _, scale_shift, int_depth = ops.lsq_align(mono_pred, sparse_inv, valid,
+                                                      clamp_hi=self.clamp_hi, clamp_lo=self.clamp_lo)
+        else:
+            bounds = (0.01, 0.3) if self.mono_type == 'inv' else (0.5, 1.6)               # modules/estimator.py:147-150
+            scale, _, _, int_depth = ops.l1_scale_align(mono_pred, sparse_inv, valid, bounds=bounds,
+                                                        clamp_hi=self.clamp_hi, clamp_lo=self.clamp_lo)
+            scale_shift = torch.stack([scale, torch.zeros_like(scale)], dim=1)
+        xy, scales, _, cnt = ops.extract_knots(int_depth, sparse_inv, valid, int(max_knots))
+        scale_map, status = ops.interp_linear(xy, scales, cnt, int_depth.shape[-2], int_depth.shape[-1], 1.0)
+        return {"valid": valid, "sparse_inv": sparse_inv, "scale_shift": scale_shift, "int_depth": int_depth,
+                "knot_count": cnt, "scale_map": scale_map, "interp_status": status}
+
+    @torch.no_grad()
+    def sml_front_end(self, mono_pred, sparse_depth, rcnet_depth, image, max_knots, image_hwc=False):
+        """BASELINE configs[0] on the device: everything val_zju.py does between the data loader and ScaleMapLearner.forward
+        (:130-196) for frames whose RC-Net quasi-dense depth ``rcnet_depth`` (B,H,W) is already known (the reference loads it
+        from the PNG run_rcnet_zju.py wrote).  Returns the front-end dict + ``int_scales``, ``sml_x``, ``sml_d`` (+ ``sml_pred``
+        with an attached ``sml_model``)."""
+        fe = self.align_and_interpolate(mono_pred, sparse_depth, max_knots)
+        fe["int_scales"], _, fe["scaffold_status"] = ops.scale_scaffold(fe["int_depth"], rcnet_depth, fe["sparse_inv"], fe["valid"],
+                                                                       self.min_depth, self.max_depth, png_quantize=True)
+        fe["sml_x"], fe["sml_d"] = ops.sml_input_assemble(fe["int_depth"], fe["int_scales"], image, image_hwc=image_hwc)
+        if self.sml_model is not None:
+            fe["sml_pred"] = self._run_sml(fe["sml_x"], fe["sml_d"], fe["int_depth"].shape[-2:])
+        return fe
+
+    def _run_sml(self, x, d, size):
+        # val_zju.py:198-210: ScaleMapLearner.forward(x, d) -> 1 / pred -> bicubic resize to the frame
+        pred = self.sml_model(x, d)
+        if pred.dim() == 3:
+            pred = pred[:, None]
+        return torch.nn.functional.interpolate(1.0 / pred, size=tuple(size), mode="bicubic", align_corners=False)[:, 0]
 
     # ------------------------------------------------------------------------------ device
     @torch.no_grad()
@@ -66,23 +127,20 @@ class RadarDepthPipeline(object):
         else:
             ctx = contextlib.nullcontext()
         with ctx:
-            # val_zju.py:130-133: valid = (d < max) * (d > min); d[~valid] = inf; d = 1/d  (-> 0 at invalid)
-            valid = (sparse_depth < self.max_depth) & (sparse_depth > self.min_depth)
-            sparse_inv = torch.where(valid, 1.0 / sparse_depth, torch.zeros_like(sparse_depth))
-            _, scale_shift, int_depth = ops.lsq_align(mono_pred, sparse_inv, valid,
-                                                      clamp_hi=self.clamp_hi, clamp_lo=self.clamp_lo)
             counts = [frame_offsets[i + 1] - frame_offsets[i] for i in range(len(frame_offsets) - 1)]
-            cap = self.max_knots or max(max(counts), 1)
-            xy, scales, _, cnt = ops.extract_knots(int_depth, sparse_inv, valid, cap)
-            scale_map, status = ops.interp_linear(xy, scales, cnt, int_depth.shape[-2], int_depth.shape[-1], 1.0)
+            fe = self.align_and_interpolate(mono_pred, sparse_depth, self.max_knots or max(max(counts, default=1), 1))
+            valid, sparse_inv, scale_shift, int_depth = fe["valid"], fe["sparse_inv"], fe["scale_shift"], fe["int_depth"]
+            cnt, scale_map, status = fe["knot_count"], fe["scale_map"], fe["interp_status"]
             if self.overlap_front_end:
                 join = torch.cuda.Event()
                 join.record(self._side)
                 for t in (valid, sparse_inv, scale_shift, int_depth, cnt, scale_map, status):
                     t.record_stream(main)
-        depth_q, response = forward_output_batched(self.model, images, radar_points, frame_offsets,
-                                                   self.response_thr, chunk_points=self.chunk_points,
-                                                   raw_inputs=self.raw_inputs, retry_empty=self.retry_empty)
+        fo = forward_output_batched(self.model, images, radar_points, frame_offsets,
+                                    self.response_thr, chunk_points=self.chunk_points,
+                                    raw_inputs=self.raw_inputs, retry_empty=self.retry_empty,
+                                    return_select=self.return_select)
+        depth_q, response = fo[0], fo[1]
         if self.overlap_front_end:
             main.wait_event(join)
         # val_zju.py:171-179 (interp='rcnet_*'): the scaffold the scripts actually feed to the SML network, with the
@@ -92,12 +150,22 @@ class RadarDepthPipeline(object):
         out = {"depth": depth_q, "response": response, "int_depth": int_depth, "scale_shift": scale_shift,
                "scale_map": scale_map, "interp_status": status, "knot_count": cnt,
                "int_scales": int_scales, "scaffold_status": scaffold_status}
+        if self.return_select:
+            out["select"] = fo[2]
         if self.sml_input:
             # val_zju.py:181-196: what ScaleMapLearner.forward(x, d) is fed
             img = sml_image if sml_image is not None else (images / 255.0 if self.raw_inputs else images)
             hwc = img.dim() == 4 and img.shape[-1] == 3 and img.shape[1] != 3
             out["sml_x"], out["sml_d"] = ops.sml_input_assemble(int_depth, int_scales, img, image_hwc=hwc)
+            if self.sml_model is not None:
+                out["sml_pred"] = self._run_sml(out["sml_x"], out["sml_d"], int_depth.shape[-2:])
         return out
+
+    def _host_keys(self):
+        if self.host_keys is not None:
+            return self.host_keys
+        keys = ("depth", "int_depth", "scale_map", "scale_shift", "interp_status")
+        return keys + (("sml_pred",) if self.sml_model is not None else ())
 
     # ------------------------------------------------------------------------------ host
     def _pin(self, name, shape, dtype):
@@ -123,8 +191,7 @@ class RadarDepthPipeline(object):
             dev.append(t.to(device, non_blocking=True))
         out = self.run_device(dev[0], dev[1], list(frame_offsets), dev[2], dev[3])
         host, d2h = {}, 0
-        for k in ("depth", "int_depth", "scale_map", "int_scales", "scale_shift", "interp_status") + \
-                ((("sml_x", "sml_d")) if self.sml_input else ()):
+        for k in self._host_keys():
             h = self._pin(k, out[k].shape, out[k].dtype)
             h.copy_(out[k], non_blocking=True)
             d2h += h.numel() * h.element_size()
@@ -168,8 +235,7 @@ class RadarDepthPipeline(object):
         main.wait_event(loaded)
         out = self.run_device(dev[0], dev[1], list(frame_offsets), dev[2], dev[3])
         # ---- results -> this slot's device staging buffers (on the compute stream), then device -> host on the copy stream
-        keys = ("depth", "int_depth", "scale_map", "int_scales", "scale_shift", "interp_status") + \
-            ((("sml_x", "sml_d")) if self.sml_input else ())
+        keys = self._host_keys()
         if slot["drained"] is not None:
             main.wait_event(slot["drained"])                     # the copy-out of the step that last used the staging buffers
         for k in keys:

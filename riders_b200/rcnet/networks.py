@@ -17,6 +17,7 @@ What is NOT torch here is the hot path inside ``RCNetEncoder.forward``: the five
 sm_100a gather kernel, and the LoFTR transformer (networks.py:444) runs through
 the fused layer kernels.  There is no CPU fallback for those two.
 """
+import functools
 import os
 
 import torch
@@ -46,7 +47,7 @@ def _act(name):
     if name is None or 'linear' in name:
         return None
     if 'leaky_relu' in name:
-        return lambda t: F.leaky_relu(t, _LEAK, inplace=True)
+        return functools.partial(F.leaky_relu, negative_slope=_LEAK, inplace=True)    # picklable / deep-copyable
     if 'relu' in name:
         return torch.relu
     if 'elu' in name:
@@ -172,7 +173,10 @@ class DecoderBlock(torch.nn.Module):
         if deconv_type != 'up':
             raise ValueError("only deconv_type='up' is used by RC-Net (rcnet_model.py:94)")
         self.skip_channels = cskip
-        self._w4 = self._w2 = self._wcol = self._wrow = None   # sub-pixel weights, built by fold_upsample_()
+        # sub-pixel weights, built by fold_upsample_(): non-persistent buffers, so .to(device) / .half() move them with the
+        # module while the state_dict keeps the reference's keys only
+        for name in ('_w4', '_w2', '_wcol', '_wrow'):
+            self.register_buffer(name, None, persistent=False)
         self.subpixel_taps = SUBPIXEL_TAPS          # 3: 3x3 phase kernels; 2: the equivalent 2x2 phase kernels (4/9 of the MACs)
         self._leaky = act is not None and 'leaky_relu' in act
         self.deconv = UpConv2d(cin, cout, init, act, use_batch_norm)
@@ -474,6 +478,7 @@ class MultiScaleDecoder(torch.nn.Module):
         """``head_sigmoid`` (inference fast path only; ignored otherwise - check ``self.last_head_sigmoid``): let the fused
         head kernel write torch.sigmoid(logits), so that the reduce kernel streams confidences."""
         self.last_head_sigmoid = False
+        self.last_used_tail = False                    # True when the TF32 fused tail ran (tests / bench label the mode by it)
         n = len(skips) - 1
         y, yp = x, None
         raw_bias = raw_slope = None                    # set when y is a RAW convolution output (see want_raw below)
@@ -520,6 +525,7 @@ class MultiScaleDecoder(torch.nn.Module):
             else:
                 y4 = F.conv2d(y, last._w2 if taps == 2 else last._w4, None, 1, 1)
             self.last_head_sigmoid = bool(head_sigmoid)
+            self.last_used_tail = True
             return [ops.decoder_tail(y4, last.deconv.conv.conv.bias, last.conv.conv.weight, last.conv.conv.bias, head.weight,
                                      _LEAK, taps=taps, sigmoid=head_sigmoid)]
         if (n != 0 and last.skip_channels == 0 and last.conv.fast_ok(y) and self.output0._act is None

@@ -89,6 +89,7 @@ class RCNetModel(object):
         """B200 extension, inference only: channels_last + BatchNorm folded into the convolutions.
         Results stay within the 1e-4 tolerance on confidences (float32 re-association only)."""
         self.eval()
+        self._optimized = True          # BatchNorm folded away, 4-channel stem: the state_dict no longer matches the reference's
         for net in (self.encoder, self.decoder):
             for mod in net.modules():
                 if isinstance(mod, networks.Conv2d):
@@ -113,7 +114,32 @@ class RCNetModel(object):
             enc.stem_pad_channels = 1
         return self
 
+    def log_summary(self, summary_writer, tag, step, image=None, output_response=None, output_label=None,
+                    output_depth=None, validity_map=None, ground_truth_label=None, ground_truth_depth=None,
+                    scalars={}, n_display=4):
+        """Same signature as rcnet_model.py:267-476 so ``rcnet_main.train`` (:398) and ``validate`` (:634) run unchanged on
+        the mirror.  Scalars and value histograms are logged; the colourised image panels of the reference need matplotlib
+        colour maps (utils/log_utils.py, SURVEY 2.1: logging is out of scope) and are skipped."""
+        if summary_writer is None:
+            return
+        with torch.no_grad():
+            for name, t in (('output_response', output_response), ('output_depth', output_depth),
+                            ('ground_truth_depth', ground_truth_depth)):
+                if t is not None and hasattr(summary_writer, 'add_histogram'):
+                    summary_writer.add_histogram('{}_{}_distro'.format(tag, name), t[0:n_display].detach().float().cpu(),
+                                                 global_step=step)
+            for name, value in scalars.items():
+                summary_writer.add_scalar('{}_{}'.format(tag, name), float(value), global_step=step)
+
+    def _refuse_if_optimized(self, what):
+        if getattr(self, '_optimized', False):
+            raise RuntimeError("RCNetModel.%s after optimize_for_inference(): the BatchNorm layers are folded into the "
+                               "convolutions and the stem has 4 input channels, so the state_dict does not have the "
+                               "reference's keys any more - %s BEFORE calling optimize_for_inference()" %
+                               (what, "restore the checkpoint" if what == "restore_model" else "save the model"))
+
     def save_model(self, checkpoint_path, step, optimizer):
+        self._refuse_if_optimized("save_model")
         torch.save({
             'train_step': step,
             'radarnet_optimizer_state_dict': optimizer.state_dict(),
@@ -122,6 +148,7 @@ class RCNetModel(object):
         }, checkpoint_path)
 
     def restore_model(self, checkpoint_path, optimizer=None):
+        self._refuse_if_optimized("restore_model")
         checkpoint = torch.load(checkpoint_path, map_location=self.device)
         self.encoder.load_state_dict(checkpoint['radarnet_encoder_state_dict'])
         self.decoder.load_state_dict(checkpoint['radarnet_decoder_state_dict'])

@@ -20,6 +20,45 @@ def test_install_registers_reference_module_names():
         sys.modules.pop("rcnet_main", None)
 
 
+def test_install_patches_the_reference_rcnet_main_in_place(tmp_path, monkeypatch):
+    """install() BEFORE the script imports rcnet_main (the natural order): the reference module found on sys.path keeps
+    its other names - run_rcnet_zju.py:9 imports forward_output, log_network_settings, log_evaluation_results - and only
+    forward_output is swapped; the mirror model offers log_summary for rcnet_main.train/validate."""
+    from riders_b200 import dropin
+    from riders_b200.rcnet import rcnet_main as ours
+    (tmp_path / "rcnet_main.py").write_text(
+        "from rcnet_model import RCNetModel\n"
+        "def forward_output(*a, **k):\n    return 'reference'\n"
+        "def log_network_settings(*a, **k):\n    return 'settings'\n"
+        "def log_evaluation_results(*a, **k):\n    return 'results'\n"
+        "def validate(model, *a, **k):\n    return model.log_summary(summary_writer=None, tag='eval', step=0)\n")
+    monkeypatch.syspath_prepend(str(tmp_path))
+    sys.modules.pop("rcnet_main", None)
+    dropin.install()
+    try:
+        from rcnet_main import forward_output, log_network_settings, log_evaluation_results       # run_rcnet_zju.py:9
+        import rcnet_main
+        assert forward_output is ours.forward_output and log_network_settings() == "settings" and log_evaluation_results() == "results"
+        assert rcnet_main.RCNetModel.__module__.startswith("riders_b200") and rcnet_main is not ours
+        m = rcnet_main.RCNetModel(3, 3, [64, 32], ["rcnet", "batch_norm"], [8, 16, 16, 16, 16], [8, 16, 16, 16, 16],
+                                  ["multiscale", "batch_norm"], [32, 16, 16, 8, 8], device=torch.device("cpu"))
+        assert rcnet_main.validate(m) is None                                                     # log_summary exists
+        dropin.uninstall()
+        assert rcnet_main.forward_output() == "reference"
+    finally:
+        dropin.uninstall()
+        sys.modules.pop("rcnet_main", None)
+
+
+def test_pipeline_rejects_unknown_alignment_and_handles_no_frames():
+    from riders_b200.pipeline import RadarDepthPipeline
+    import pytest
+    with pytest.raises(NotImplementedError):
+        RadarDepthPipeline(None, global_alignment="bogus")
+    p = RadarDepthPipeline(None, global_alignment="s", sml_model=torch.nn.Identity())
+    assert p.sml_input and p._host_keys()[-1] == "sml_pred"
+
+
 def test_mirror_keeps_reference_parameter_names_and_counts():
     from riders_b200.rcnet.rcnet_model import RCNetModel
     m = RCNetModel(3, 3, [240, 100], ["rcnet", "batch_norm"], [32, 64, 128, 128, 128], [32, 64, 128, 128, 128],

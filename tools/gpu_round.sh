@@ -20,6 +20,23 @@ for MODE in "$@"; do
     bench)
       timeout -s KILL 900 python bench.py --steps 5 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" | tee -a $OUT/status.txt
       tail -c 4000 $OUT/bench.json; tail -5 $OUT/bench.err ;;
+    benchstrict)
+      timeout -s KILL 900 python bench.py --steps 3 --warmup 3 --strict-fp32 > $OUT/bench_strict.json 2> $OUT/bench_strict.err; echo "bench-strict rc=$?" | tee -a $OUT/status.txt
+      tail -c 2500 $OUT/bench_strict.json; tail -5 $OUT/bench_strict.err ;;
+    benchs)
+      timeout -s KILL 900 python bench.py --steps 5 --warmup 3 --align s > $OUT/bench_align_s.json 2> $OUT/bench_align_s.err; echo "bench-align-s rc=$?" | tee -a $OUT/status.txt
+      tail -c 2500 $OUT/bench_align_s.json; tail -5 $OUT/bench_align_s.err ;;
+    config1)
+      timeout -s KILL 600 python bench.py --workload config1 > $OUT/bench_config1.json 2> $OUT/bench_config1.err; echo "config1 rc=$?" | tee -a $OUT/status.txt
+      cat $OUT/bench_config1.json; tail -5 $OUT/bench_config1.err
+      timeout -s KILL 600 python bench.py --workload config1 --align s > $OUT/bench_config1_s.json 2> $OUT/bench_config1_s.err; echo "config1-s rc=$?" | tee -a $OUT/status.txt
+      cat $OUT/bench_config1_s.json; tail -5 $OUT/bench_config1_s.err ;;
+    eager)
+      timeout -s KILL 900 python bench.py --impl eager --steps 8 --warmup 2 > $OUT/bench_eager.json 2> $OUT/bench_eager.err; echo "eager rc=$?" | tee -a $OUT/status.txt
+      cat $OUT/bench_eager.json; tail -5 $OUT/bench_eager.err ;;
+    train)
+      timeout -s KILL 900 python bench.py --workload train --steps 5 --warmup 3 > $OUT/bench_train.json 2> $OUT/bench_train.err; echo "train rc=$?" | tee -a $OUT/status.txt
+      cat $OUT/bench_train.json; tail -5 $OUT/bench_train.err ;;
     benchnotail)
       RIDERS_FUSED_TAIL=0 timeout -s KILL 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_notail.json 2> $OUT/bench_notail.err; echo "bench-notail rc=$?" | tee -a $OUT/status.txt
       tail -c 1500 $OUT/bench_notail.json ;;
