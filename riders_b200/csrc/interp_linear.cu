@@ -4,84 +4,51 @@
 //
 //   extract_knots_kernel : row-major scan of `valid` -> knot (x, y), scale = sparse/pred,
 //                          shift = sparse - pred            (interpolator.py:28-32)
-//   delaunay_kernel      : one CTA per frame.  Sort knots by (x, y) (bitonic, shared memory),
-//                          Guibas-Stolfi divide and conquer with exact integer predicates
-//                          (delaunay_core.cuh): the nodes of one recursion depth are merged
-//                          by independent threads, depth by depth; then emit triangle records.
-//   interp_fill_kernel   : 32x32 pixel tiles; each tile culls the frame's triangles by bounding
-//                          box, then every pixel evaluates exact integer edge functions (a pixel
-//                          on the hull boundary is inside, like SciPy's eps test) and the fp64
-//                          barycentric sum; no triangle -> `fill`.
+//   delaunay_star_kernel : ONE WARP PER KNOT builds that knot's Delaunay star (delaunay_star.cuh: exact int64 predicates,
+//                          symbolic perturbation for co-circular quads); candidates are visited outwards in knot index
+//                          (= row-major) order, 32 at a time against a read-only star, and the walk stops once the row
+//                          distance on both sides exceeds twice the largest circumradius of the closed star (no farther knot
+//                          can lie inside any of its circumcircles).  Every triangle is emitted once, by its lowest-index
+//                          knot.  The same launch writes the fill value over the output maps (the rasteriser overwrites the
+//                          covered pixels), and the last CTA of a frame publishes status / triangle count.
+//   raster_kernel        : scatter form of the barycentric fill: 8 triangles per CTA, the CTA's warps share the bounding-box
+//                          rows of each; a pixel is written iff its three exact integer edge functions are >= 0 (a pixel on
+//                          the hull boundary is inside, like SciPy's eps test).  Pixels on an edge or a knot are evaluated
+//                          from the edge's two knots in canonical order, so the two triangles sharing the edge write
+//                          identical bits (benign race, deterministic image).  value = (wa va + wb vb + wc vc) / (wa + wb + wc)
+//                          in fp64: exact at the knots.
 //
-// Roofline: the fill is HBM-write bound (4 B/pixel out); the triangulation is latency bound
-// (pointer chasing) and only amortises over a batch of frames - reported separately.
+// Round 1 ran a divide-and-conquer triangulation with ONE CTA per frame (0.24 ms for one 200-knot frame, 0.66 ms for 16
+// frames, a cliff past 680 knots) and a gather fill that tested ~15 bounding-box candidates per pixel; the star form uses
+// the whole GPU for a single frame and the scatter fill tests ~2 pixels per covered pixel.
+//
+// Roofline: algorithmic bytes are the 4 B/pixel of the output map (+ 12 B per knot); the launches write the map twice
+// (fill value, then the covered pixels) - 8 B/pixel of traffic.
 #include "common.cuh"
-#include "delaunay_core.cuh"
+#include "delaunay_star.cuh"
 #include "ordered_compact.cuh"
 
 namespace riders {
 
 using dt::Pt;
-using dt::Hull;
-using dt::Mesh;
-
-constexpr int DT_THREADS = 512;
 
 struct TriRec {            // 48 bytes
     int ax, ay, bx, by, cx, cy;
     float va, vb, vc;
-    int key_hi, key_lo;    // canonical order of the triangle (sorted knot ranks) for tie-breaking
-    int pad;
+    int ia, ib, ic;        // knot indices (row-major rank for extracted knots)
 };
 
-struct FrameWs {           // device-side view of one frame's workspace slice
-    unsigned long long* keys;
-    Pt* pts;
-    int* perm;
-    int* next;
-    int* org;
-    Hull* hulls;
-    int* counters;         // [0] fresh quads, [1] overflow, [2] triangles
-    TriRec* tris;
-};
+// per-frame counters in the workspace
+enum { CNT_TRIS = 0, CNT_OVERFLOW = 1, CNT_DONE = 2, CNT_STRIDE = 8 };
 
-struct WsLayout {
-    size_t keys, pts, perm, next, org, hulls, counters, tris, total;
-    int P, cap;
-};
+struct WsLayout { size_t counters, tris, total; };
 
-__host__ __device__ inline int next_pow2(int v) { int p = 2; while (p < v) p <<= 1; return p; }
-
-__host__ __device__ inline WsLayout ws_layout(int max_knots) {
+__host__ __device__ inline WsLayout ws_layout(int B, int max_knots) {
     WsLayout L;
-    L.P = next_pow2(max_knots < 2 ? 2 : max_knots);
-    L.cap = 8 * max_knots + 64;
-    size_t o = 0;
-    auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 255) & ~(size_t)255; return at; };
-    L.keys = take(sizeof(unsigned long long) * L.P);
-    L.pts = take(sizeof(Pt) * (size_t)(max_knots + 1));
-    L.perm = take(sizeof(int) * (size_t)(max_knots + 1));
-    L.next = take(sizeof(int) * 4 * (size_t)L.cap);
-    L.org = take(sizeof(int) * 4 * (size_t)L.cap);
-    L.hulls = take(sizeof(Hull) * 4 * (size_t)L.P);
-    L.counters = take(sizeof(int) * 8);
-    L.tris = take(sizeof(TriRec) * 2 * (size_t)(max_knots + 1));
-    L.total = o;
+    L.counters = 0;
+    L.tris = ((size_t)B * CNT_STRIDE * sizeof(int) + 255) & ~(size_t)255;
+    L.total = L.tris + (size_t)B * 2 * (size_t)max_knots * sizeof(TriRec);
     return L;
-}
-
-__device__ inline FrameWs frame_ws(uint8_t* base, const WsLayout& L, int frame) {
-    uint8_t* p = base + (size_t)frame * L.total;
-    FrameWs w;
-    w.keys = (unsigned long long*)(p + L.keys);
-    w.pts = (Pt*)(p + L.pts);
-    w.perm = (int*)(p + L.perm);
-    w.next = (int*)(p + L.next);
-    w.org = (int*)(p + L.org);
-    w.hulls = (Hull*)(p + L.hulls);
-    w.counters = (int*)(p + L.counters);
-    w.tris = (TriRec*)(p + L.tris);
-    return w;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -108,195 +75,200 @@ extract_knots_kernel(const float* __restrict__ pred, const float* __restrict__ s
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) knot_count[frame] = upto;
 }
 
-struct SmemMesh { size_t next, org, pts, perm, hulls, total; };
-
-__host__ __device__ inline SmemMesh smem_mesh_layout(int max_knots, const WsLayout& L) {
-    SmemMesh S;
-    size_t o = 0;
-    auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) & ~(size_t)15; return at; };
-    S.next = take(sizeof(int) * 4 * (size_t)L.cap);    // also holds the P sort keys (8 B each, P <= 2 * max_knots)
-    S.org = take(sizeof(int) * 4 * (size_t)L.cap);
-    S.pts = take(sizeof(Pt) * (size_t)(max_knots + 1));
-    S.perm = take(sizeof(int) * (size_t)(max_knots + 1));
-    S.hulls = take(sizeof(Hull) * 4 * (size_t)L.P);
-    S.total = o;
-    return S;
-}
-
 // ---------------------------------------------------------------------------------------------
-// triangulation: one CTA per frame
+// triangulation: one warp per knot
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(DT_THREADS)
-delaunay_kernel(const int32_t* __restrict__ knot_xy, const float* __restrict__ knot_val,
-                const int32_t* __restrict__ knot_count, int max_knots, uint8_t* ws_base, WsLayout L,
-                int32_t* __restrict__ status, int32_t* __restrict__ tri_out, int32_t* __restrict__ tri_count, int mesh_in_smem) {
-    extern __shared__ __align__(16) uint8_t dsm[];
-    __shared__ int s_counters[2];                       // [0] fresh quads, [1] overflow (shared-memory mesh only)
-    const int frame = blockIdx.x;
-    FrameWs w = frame_ws(ws_base, L, frame);
-    int* fresh = &w.counters[0];
-    int* overflow = &w.counters[1];
-    if (mesh_in_smem) {
-        // the pointer-chasing structures live in shared memory (~30-cycle instead of L2 latency per hop);
-        // only the triangle records and their count go to the global workspace for the fill kernel
-        const SmemMesh S = smem_mesh_layout(max_knots, L);
-        w.next = (int*)(dsm + S.next); w.org = (int*)(dsm + S.org);
-        w.keys = (unsigned long long*)(dsm + S.next);   // the sort finishes before the mesh is touched
-        w.pts = (Pt*)(dsm + S.pts); w.perm = (int*)(dsm + S.perm); w.hulls = (Hull*)(dsm + S.hulls);
-        fresh = &s_counters[0]; overflow = &s_counters[1];
-        if (threadIdx.x < 2) s_counters[threadIdx.x] = 0;
-    }
-    const int n = min(knot_count[frame], max_knots);
-    const int tid = threadIdx.x;
+constexpr int STAR_WARPS = 8;
+constexpr int STAR_THREADS = STAR_WARPS * 32;
+
+__global__ void __launch_bounds__(STAR_THREADS)
+delaunay_star_kernel(const int32_t* __restrict__ knot_xy, const float* __restrict__ knot_val,
+                     const int32_t* __restrict__ knot_count, int max_knots, uint8_t* ws_base, WsLayout L,
+                     int32_t* __restrict__ status, int32_t* __restrict__ tri_out, int32_t* __restrict__ tri_count,
+                     float* __restrict__ fill_out, float fill, int npx) {
+    extern __shared__ __align__(16) int s_pts[];                 // x | y << 16 of every knot of the frame
+    __shared__ star::Star s_star[STAR_WARPS][2];
+    __shared__ int s_unsorted;
+    const int frame = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int* counters = (int*)(ws_base + L.counters) + (size_t)frame * CNT_STRIDE;
+    TriRec* tris = (TriRec*)(ws_base + L.tris) + (size_t)frame * 2 * max_knots;
+    const int n_true = knot_count[frame];
+    const int n = (n_true >= 3 && n_true <= max_knots) ? n_true : 0;      // < 3: QhullError upstream; > capacity: reported, never truncated
     const int32_t* xy = knot_xy + (size_t)frame * max_knots * 2;
-    const float* val = knot_val + (size_t)frame * max_knots;
 
-    if (tid < 8) w.counters[tid] = 0;
-    if (knot_count[frame] > max_knots) {
-        // more valid pixels than the caller's capacity: never triangulate a truncated knot set silently
-        if (tid == 0) { status[frame] = RIDERS_EINTERNAL; if (tri_count) tri_count[frame] = 0; }
-        return;
+    // ---- the fill value over this CTA's slice of the map (the rasteriser overwrites the covered pixels) --------------
+    if (fill_out) {
+        float* o = fill_out + (size_t)frame * npx;
+        const int per = ((npx + (int)gridDim.x - 1) / (int)gridDim.x + 3) & ~3;
+        const int lo = blockIdx.x * per, hi = min(lo + per, npx);
+        if (((((uintptr_t)o) & 15) == 0) && (npx & 3) == 0) {
+            const float4 f4 = make_float4(fill, fill, fill, fill);
+            for (int i = lo + tid * 4; i < hi; i += STAR_THREADS * 4) *reinterpret_cast<float4*>(o + i) = f4;
+        } else {
+            for (int i = lo + tid; i < hi; i += STAR_THREADS) o[i] = fill;
+        }
     }
-    if (n < 3) {
-        if (tid == 0) { status[frame] = RIDERS_EQHULL; if (tri_count) tri_count[frame] = 0; }
-        return;
-    }
-    // ---- sort by (x, y): key = x:16 | y:16 | index:16 --------------------------------------
-    const int P = next_pow2(n);
-    for (int i = tid; i < P; i += DT_THREADS)
-        w.keys[i] = (i < n) ? (((unsigned long long)(unsigned)xy[2 * i] << 32) | ((unsigned long long)(unsigned)xy[2 * i + 1] << 16) | (unsigned)i)
-                            : ~0ull;
+    if (tid == 0) s_unsorted = 0;
     __syncthreads();
-    for (int k = 2; k <= P; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < P; i += DT_THREADS) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned long long a = w.keys[i], b = w.keys[ixj];
-                    const bool up = (i & k) == 0;
-                    if ((a > b) == up) { w.keys[i] = b; w.keys[ixj] = a; }
+    int unsorted = 0;
+    for (int i = tid; i < n; i += STAR_THREADS) {
+        const int x = xy[2 * i], y = xy[2 * i + 1];
+        s_pts[i] = (x & 0xffff) | (y << 16);
+        if (i > 0 && xy[2 * i - 1] > y) unsorted = 1;            // rows not ascending: the early exit below is off
+    }
+    if (unsorted) s_unsorted = 1;
+    __syncthreads();
+    const bool sorted = s_unsorted == 0;
+
+    const int p = blockIdx.x * STAR_WARPS + warp;
+    if (p < n) {
+        const int px = s_pts[p] & 0xffff, py = s_pts[p] >> 16;
+        int cur = 0;
+        if (lane == 0) s_star[warp][0].k = 0;
+        __syncwarp();
+        // candidates outwards from p in knot order: lane l of a batch looks at distance d = base + l/2 + 1 on side l & 1
+        const int dmax = max(p, n - 1 - p);
+        for (int base = 0; base < dmax; base += 16) {
+            const int d = base + (lane >> 1) + 1;
+            const int c = (lane & 1) ? p - d : p + d;
+            const bool ok = c >= 0 && c < n;
+            int ux = 0, uy = 0;
+            if (ok) { ux = (s_pts[c] & 0xffff) - px; uy = (s_pts[c] >> 16) - py; }
+            unsigned m = __ballot_sync(0xffffffffu, ok && star::accepts(s_star[warp][cur], p, ux, uy, c));
+            bool changed = false;
+            while (m) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
+                const int rx = __shfl_sync(0xffffffffu, ux, l), ry = __shfl_sync(0xffffffffu, uy, l), rc_id = __shfl_sync(0xffffffffu, c, l);
+                int rc = 0;
+                if (lane == 0) rc = star::insert(s_star[warp][cur], s_star[warp][cur ^ 1], p, rx, ry, rc_id);
+                rc = __shfl_sync(0xffffffffu, rc, 0);
+                if (rc < 0) { if (lane == 0) atomicExch(&counters[CNT_OVERFLOW], 1); }
+                else if (rc > 0) { cur ^= 1; changed = true; }
+                __syncwarp();
+            }
+            // ---- early exit: closed star and both row distances beyond twice the largest circumradius ----------------
+            if (sorted) {
+                const star::Star& s = s_star[warp][cur];
+                const int k = s.k;
+                if (k >= 3) {
+                    double r2max = 0.0;
+                    bool open = false;
+                    for (int j = lane; j < k; j += 32) {
+                        const int jn = j + 1 == k ? 0 : j + 1;
+                        const int ax = s.x[j], ay = s.y[j], bx = s.x[jn], by = s.y[jn];
+                        const int cr = star::cross2(ax, ay, bx, by);
+                        if (cr <= 0) { open = true; continue; }
+                        const double a2 = (double)(ax * ax + ay * ay), b2 = (double)(bx * bx + by * by);
+                        const double c2 = (double)((ax - bx) * (ax - bx) + (ay - by) * (ay - by));
+                        r2max = fmax(r2max, a2 * b2 * c2 / (4.0 * (double)cr * (double)cr));       // R^2 of triangle (p, a, b)
+                    }
+                    open = __any_sync(0xffffffffu, open);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) r2max = fmax(r2max, __shfl_xor_sync(0xffffffffu, r2max, o));
+                    if (!open) {
+                        const int nd = base + 17;                                  // next distance to look at
+                        const double lim = 4.0 * r2max * (1.0 + 1e-9);
+                        bool far_up = p + nd >= n, far_dn = p - nd < 0;
+                        if (!far_up) { const double dy = (double)((s_pts[p + nd] >> 16) - py); far_up = dy * dy > lim; }
+                        if (!far_dn) { const double dy = (double)((s_pts[p - nd] >> 16) - py); far_dn = dy * dy > lim; }
+                        if (far_up && far_dn) break;
+                    }
                 }
             }
-            __syncthreads();
+            (void)changed;
         }
-    for (int i = tid; i < n; i += DT_THREADS) {
-        const unsigned long long key = w.keys[i];
-        Pt p;
-        p.x = (int)(key >> 32); p.y = (int)((key >> 16) & 0xffff);
-        w.pts[i] = p;
-        w.perm[i] = (int)(key & 0xffff);
-    }
-    __syncthreads();
-
-    // ---- divide and conquer, deepest level first ----------------------------------------------
-    Mesh m;
-    m.next = w.next; m.org = w.org; m.fresh = fresh; m.capacity = L.cap; m.pts = w.pts; m.overflow = overflow;
-    const int D = dt::tree_depth(n);
-    for (int d = D; d >= 0; --d) {
-        for (int j = tid; j < (1 << d); j += DT_THREADS) dt::process_node(m, n, d, j, w.hulls);
-        __syncthreads();
-    }
-
-    // ---- triangle records ---------------------------------------------------------------------
-    const int quads = min(*fresh, L.cap);
-    for (int e2 = tid; e2 < 2 * quads; e2 += DT_THREADS) {
-        const int e = 4 * (e2 >> 1) + 2 * (e2 & 1);
-        int a, b, c;
-        if (!dt::left_triangle(m, e, a, b, c)) continue;
-        const int slot = atomicAdd(&w.counters[2], 1);
-        if (slot >= 2 * max_knots) continue;
-        TriRec t;
-        t.ax = w.pts[a].x; t.ay = w.pts[a].y; t.bx = w.pts[b].x; t.by = w.pts[b].y; t.cx = w.pts[c].x; t.cy = w.pts[c].y;
-        t.va = val[w.perm[a]]; t.vb = val[w.perm[b]]; t.vc = val[w.perm[c]];
-        int s0 = a, s1 = b, s2 = c, tmp;                       // sorted ranks -> canonical key
-        if (s0 > s1) { tmp = s0; s0 = s1; s1 = tmp; }
-        if (s1 > s2) { tmp = s1; s1 = s2; s2 = tmp; }
-        if (s0 > s1) { tmp = s0; s0 = s1; s1 = tmp; }
-        t.key_hi = s0; t.key_lo = (s1 << 16) | s2;
-        t.pad = 0;
-        w.tris[slot] = t;
-        if (tri_out) {
-            int32_t* o = tri_out + ((size_t)frame * 2 * max_knots + slot) * 3;
-            o[0] = w.perm[a]; o[1] = w.perm[b]; o[2] = w.perm[c];
+        // ---- every fan triangle (p, a, b) whose lowest knot index is p --------------------------------------------------
+        const star::Star& s = s_star[warp][cur];
+        const int k = s.k;
+        const float vp = knot_val[(size_t)frame * max_knots + p];
+        for (int j = lane; j < k && k >= 2; j += 32) {
+            const int jn = j + 1 == k ? 0 : j + 1;
+            if (star::cross2(s.x[j], s.y[j], s.x[jn], s.y[jn]) > 0 && p < s.id[j] && p < s.id[jn]) {
+                const int slot = atomicAdd(&counters[CNT_TRIS], 1);
+                if (slot < 2 * max_knots) {
+                    TriRec t;
+                    t.ax = px; t.ay = py; t.bx = px + s.x[j]; t.by = py + s.y[j]; t.cx = px + s.x[jn]; t.cy = py + s.y[jn];
+                    t.va = vp; t.vb = knot_val[(size_t)frame * max_knots + s.id[j]]; t.vc = knot_val[(size_t)frame * max_knots + s.id[jn]];
+                    t.ia = p; t.ib = s.id[j]; t.ic = s.id[jn];
+                    tris[slot] = t;
+                    if (tri_out) {
+                        int32_t* o = tri_out + ((size_t)frame * 2 * max_knots + slot) * 3;
+                        o[0] = p; o[1] = s.id[j]; o[2] = s.id[jn];
+                    }
+                } else {
+                    atomicExch(&counters[CNT_OVERFLOW], 1);
+                }
+            }
         }
     }
+    // ---- the last CTA of the frame publishes status and triangle count ---------------------------------------------------
     __syncthreads();
     if (tid == 0) {
-        const int nt = w.counters[2];
-        status[frame] = *overflow ? RIDERS_EINTERNAL : (nt == 0 ? RIDERS_EQHULL : RIDERS_OK);
-        if (tri_count) tri_count[frame] = nt;
+        __threadfence();
+        if (atomicAdd(&counters[CNT_DONE], 1) == (int)gridDim.x - 1) {
+            __threadfence();
+            const int nt = min(atomicAdd(&counters[CNT_TRIS], 0), 2 * max_knots);
+            const int ovf = atomicAdd(&counters[CNT_OVERFLOW], 0);
+            int st = RIDERS_OK;
+            if (n_true > max_knots || ovf) st = RIDERS_EINTERNAL;
+            else if (n_true < 3 || nt == 0) st = RIDERS_EQHULL;
+            status[frame] = st;
+            if (st != RIDERS_OK) counters[CNT_TRIS] = 0;          // the frame keeps the fill value
+            if (tri_count) tri_count[frame] = st == RIDERS_OK ? nt : 0;
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// fill
+// fill value (only when riders_interp_fill is called on its own) and the scatter rasteriser
 // ---------------------------------------------------------------------------------------------
-constexpr int FILL_THREADS = 256;
-constexpr int FT_W = 32, FT_H = 32, FILL_ROWS = FT_H / (FILL_THREADS / FT_W);   // 4 rows per thread
+__global__ void __launch_bounds__(256)
+fill_value_kernel(float* __restrict__ out, size_t total, float fill) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) out[i] = fill;
+}
 
-__global__ void __launch_bounds__(FILL_THREADS)
-interp_fill_kernel(uint8_t* ws_base, WsLayout L, int max_knots, int H, int W, float fill, float* __restrict__ out) {
-    __shared__ TriRec cand[FILL_THREADS];
-    __shared__ int warp_count[FILL_THREADS / 32];
-    __shared__ int n_cand;
-    const int frame = blockIdx.z;
-    const FrameWs w = frame_ws(ws_base, L, frame);
-    const int nt = min(w.counters[2], 2 * max_knots);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tx0 = blockIdx.x * FT_W, ty0 = blockIdx.y * FT_H;
-    const int px = tx0 + lane;
-    const int py0 = ty0 + warp;                                  // rows py0 + 8*m
+constexpr int RASTER_THREADS = 256;
+constexpr int RASTER_TRIS = 8;              // triangles per CTA; the 8 warps share each triangle's rows
 
-    float res[FILL_ROWS];
-    unsigned long long best[FILL_ROWS];
-#pragma unroll
-    for (int mI = 0; mI < FILL_ROWS; ++mI) { res[mI] = fill; best[mI] = ~0ull; }
+// value on the segment between knots (x0, y0, v0) and (x1, y1, v1) at pixel (px, py) of that segment, endpoints in
+// canonical (lexicographic) order so both triangles sharing the edge compute the same bits
+__device__ __forceinline__ float edge_value(int x0, int y0, float v0, int x1, int y1, float v1, int px, int py) {
+    if (x0 > x1 || (x0 == x1 && y0 > y1)) { int t = x0; x0 = x1; x1 = t; t = y0; y0 = y1; y1 = t; float f = v0; v0 = v1; v1 = f; }
+    int w0, w1;
+    if (x1 != x0) { w0 = x1 - px; w1 = px - x0; } else { w0 = y1 - py; w1 = py - y0; }
+    return (float)(((double)w0 * (double)v0 + (double)w1 * (double)v1) / (double)(w0 + w1));
+}
 
-    for (int base = 0; base < nt; base += FILL_THREADS) {
-        const int ti = base + tid;
-        bool hit = false;
-        TriRec t;
-        if (ti < nt) {
-            t = w.tris[ti];
-            const int x0 = min(t.ax, min(t.bx, t.cx)), x1 = max(t.ax, max(t.bx, t.cx));
-            const int y0 = min(t.ay, min(t.by, t.cy)), y1 = max(t.ay, max(t.by, t.cy));
-            hit = x0 < tx0 + FT_W && x1 >= tx0 && y0 < ty0 + FT_H && y1 >= ty0;
-        }
-        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) warp_count[warp] = __popc(ballot);
-        __syncthreads();
-        int offset = 0;
-#pragma unroll
-        for (int q = 0; q < FILL_THREADS / 32; ++q) offset += (q < warp) ? warp_count[q] : 0;
-        if (hit) cand[offset + __popc(ballot & ((1u << lane) - 1u))] = t;
-        if (tid == FILL_THREADS - 1) n_cand = offset + __popc(ballot);
-        __syncthreads();
-        const int n = n_cand;
-        for (int i = 0; i < n; ++i) {
-            const TriRec& c = cand[i];
-            const unsigned long long key = ((unsigned long long)(unsigned)c.key_hi << 32) | (unsigned)c.key_lo;
-            // edge functions are affine in the pixel row: evaluate at py0 and step by 8 rows
-            const int dxa = c.bx - px, dxb = c.cx - px, dxc = c.ax - px;
-#pragma unroll
-            for (int mI = 0; mI < FILL_ROWS; ++mI) {
-                const int py = py0 + 8 * mI;
-                const int wa = dxa * (c.cy - py) - (c.by - py) * dxb;     // orient(p, b, c)
-                const int wb = dxb * (c.ay - py) - (c.cy - py) * dxc;     // orient(p, c, a)
-                const int wc = dxc * (c.by - py) - (c.ay - py) * dxa;     // orient(p, a, b)
-                if ((wa | wb | wc) >= 0 && key < best[mI]) {
-                    const double det = (double)(wa + wb + wc);
-                    const double ca = (double)wa / det, cb = (double)wb / det, cc = (double)wc / det;
-                    res[mI] = (float)(ca * (double)c.va + cb * (double)c.vb + cc * (double)c.vc);
-                    best[mI] = key;
+__global__ void __launch_bounds__(RASTER_THREADS)
+raster_kernel(uint8_t* ws_base, WsLayout L, int max_knots, int H, int W, float* __restrict__ out) {
+    const int frame = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int* counters = (const int*)(ws_base + L.counters) + (size_t)frame * CNT_STRIDE;
+    const TriRec* tris = (const TriRec*)(ws_base + L.tris) + (size_t)frame * 2 * max_knots;
+    const int nt = min(counters[CNT_TRIS], 2 * max_knots);
+    float* o = out + (size_t)frame * H * W;
+    for (int ti = blockIdx.x * RASTER_TRIS; ti < min(nt, (int)(blockIdx.x + 1) * RASTER_TRIS); ++ti) {
+        const TriRec t = tris[ti];
+        const int x0 = max(min(t.ax, min(t.bx, t.cx)), 0), x1 = min(max(t.ax, max(t.bx, t.cx)), W - 1);
+        const int y0 = max(min(t.ay, min(t.by, t.cy)), 0), y1 = min(max(t.ay, max(t.by, t.cy)), H - 1);
+        for (int y = y0 + warp; y <= y1; y += RASTER_THREADS / 32) {
+            for (int xb = x0; xb <= x1; xb += 32) {
+                const int x = xb + lane;
+                // edge functions (the triangle is counter-clockwise): wa = orient(p, b, c), wb = orient(p, c, a), wc = orient(p, a, b)
+                const int dxa = t.bx - x, dxb = t.cx - x, dxc = t.ax - x;
+                const int wa = dxa * (t.cy - y) - (t.by - y) * dxb;
+                const int wb = dxb * (t.ay - y) - (t.cy - y) * dxc;
+                const int wc = dxc * (t.by - y) - (t.ay - y) * dxa;
+                if (x <= x1 && (wa | wb | wc) >= 0) {
+                    float v;
+                    if (wa == 0) v = edge_value(t.bx, t.by, t.vb, t.cx, t.cy, t.vc, x, y);           // on edge b-c (or at b / c)
+                    else if (wb == 0) v = edge_value(t.cx, t.cy, t.vc, t.ax, t.ay, t.va, x, y);
+                    else if (wc == 0) v = edge_value(t.ax, t.ay, t.va, t.bx, t.by, t.vb, x, y);
+                    else v = (float)(((double)wa * (double)t.va + (double)wb * (double)t.vb + (double)wc * (double)t.vc) /
+                                     (double)(wa + wb + wc));
+                    o[(size_t)y * W + x] = v;
                 }
             }
-        }
-    }
-    if (px < W) {
-#pragma unroll
-        for (int mI = 0; mI < FILL_ROWS; ++mI) {
-            const int py = py0 + 8 * mI;
-            if (py < H) out[((size_t)frame * H + py) * W + px] = res[mI];
         }
     }
 }
@@ -306,7 +278,7 @@ interp_fill_kernel(uint8_t* ws_base, WsLayout L, int max_knots, int H, int W, fl
 extern "C" size_t riders_interp_workspace_bytes(int B, int max_knots, int H, int W) {
     (void)H; (void)W;
     if (B <= 0 || max_knots <= 0) return 256;
-    return (size_t)B * riders::ws_layout(max_knots).total + 256;
+    return riders::ws_layout(B, max_knots).total + 256;
 }
 
 extern "C" int riders_extract_knots(const float* pred, const float* sparse, const uint8_t* valid,
@@ -325,9 +297,9 @@ extern "C" int riders_extract_knots(const float* pred, const float* sparse, cons
     return check_launch("extract_knots");
 }
 
-extern "C" int riders_interp_triangulate(const int32_t* knot_xy, const float* knot_val, const int32_t* knot_count,
-                                         int B, int max_knots, int32_t* status,
-                                         int32_t* tri_out, int32_t* tri_count, void* workspace, void* stream) {
+static int interp_triangulate_impl(const int32_t* knot_xy, const float* knot_val, const int32_t* knot_count,
+                                   int B, int max_knots, int32_t* status, int32_t* tri_out, int32_t* tri_count,
+                                   float* fill_out, float fill, int npx, void* workspace, void* stream) {
     using namespace riders;
     RIDERS_REQUIRE(B >= 0, "interp_triangulate: bad shape");
     RIDERS_REQUIRE(max_knots > 0 && max_knots <= 32768, "interp_triangulate: max_knots=%d out of range (1..32768)", max_knots);
@@ -336,38 +308,60 @@ extern "C" int riders_interp_triangulate(const int32_t* knot_xy, const float* kn
     RIDERS_REQUIRE(knot_xy && knot_val && knot_count && status && workspace, "interp_triangulate: null pointer");
     RIDERS_REQUIRE((((uintptr_t)workspace) & 255) == 0, "interp_triangulate: workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    const WsLayout L = ws_layout(max_knots);
-    const SmemMesh S = smem_mesh_layout(max_knots, L);
-    const int mesh_in_smem = S.total <= 200 * 1024 ? 1 : 0;               // ~680 knots; larger frames chase pointers in L2
-    if (mesh_in_smem) {
-        static size_t configured[64] = {0};
-        if (int rc_smem = ensure_dynamic_smem(delaunay_kernel, (size_t)(S.total), configured, "interp_triangulate: smem attribute")) return rc_smem;
-    }
+    const WsLayout L = ws_layout(B, max_knots);
+    if (cudaMemsetAsync((uint8_t*)workspace + L.counters, 0, (size_t)B * CNT_STRIDE * sizeof(int), st) != cudaSuccess)
+        return check_launch("interp_triangulate: counter reset");
+    const size_t smem = (size_t)max_knots * sizeof(int);
+    static size_t configured[64] = {0};
+    if (smem > 48 * 1024)
+        if (int rc_smem = ensure_dynamic_smem(delaunay_star_kernel, smem, configured, "interp_triangulate: smem attribute")) return rc_smem;
     count_launches(1);
-    delaunay_kernel<<<B, DT_THREADS, mesh_in_smem ? S.total : 0, st>>>(knot_xy, knot_val, knot_count, max_knots, (uint8_t*)workspace, L,
-                                                                       status, tri_out, tri_count, mesh_in_smem);
+    dim3 grid(ceil_div(max_knots, STAR_WARPS), B);
+    delaunay_star_kernel<<<grid, STAR_THREADS, smem, st>>>(knot_xy, knot_val, knot_count, max_knots, (uint8_t*)workspace, L,
+                                                           status, tri_out, tri_count, fill_out, fill, npx);
     return check_launch("interp_triangulate");
 }
 
-extern "C" int riders_interp_fill(int B, int max_knots, int H, int W, float fill, float* out, void* workspace, void* stream) {
+extern "C" int riders_interp_triangulate(const int32_t* knot_xy, const float* knot_val, const int32_t* knot_count,
+                                         int B, int max_knots, int32_t* status,
+                                         int32_t* tri_out, int32_t* tri_count, void* workspace, void* stream) {
+    return interp_triangulate_impl(knot_xy, knot_val, knot_count, B, max_knots, status, tri_out, tri_count, nullptr, 0.f, 0, workspace, stream);
+}
+
+static int interp_raster_impl(int B, int max_knots, int H, int W, float fill, bool prefill, float* out, void* workspace, void* stream) {
     using namespace riders;
     RIDERS_REQUIRE(B >= 0 && H > 0 && W > 0, "interp_fill: bad shape");
     RIDERS_REQUIRE(H <= 8192 && W <= 8192, "interp_fill: exact predicates need H, W <= 8192");
     RIDERS_REQUIRE(max_knots > 0 && max_knots <= 32768 && B <= 65535, "interp_fill: max_knots / B out of range");
     if (B == 0) return RIDERS_OK;
     RIDERS_REQUIRE(out && workspace, "interp_fill: null pointer");
-    const WsLayout L = ws_layout(max_knots);
-    dim3 grid(ceil_div(W, FT_W), ceil_div(H, FT_H), B);
+    cudaStream_t st = (cudaStream_t)stream;
+    const WsLayout L = ws_layout(B, max_knots);
+    if (prefill) {
+        count_launches(1);
+        const size_t total = (size_t)B * H * W;
+        fill_value_kernel<<<(unsigned)min((size_t)2048, (total + 1023) / 1024), 256, 0, st>>>(out, total, fill);
+    }
     count_launches(1);
-    interp_fill_kernel<<<grid, FILL_THREADS, 0, (cudaStream_t)stream>>>((uint8_t*)workspace, L, max_knots, H, W, fill, out);
+    dim3 grid(ceil_div(2 * max_knots, RASTER_TRIS), B);
+    raster_kernel<<<grid, RASTER_THREADS, 0, st>>>((uint8_t*)workspace, L, max_knots, H, W, out);
     return check_launch("interp_fill");
+}
+
+extern "C" int riders_interp_fill(int B, int max_knots, int H, int W, float fill, float* out, void* workspace, void* stream) {
+    return interp_raster_impl(B, max_knots, H, W, fill, true, out, workspace, stream);
 }
 
 extern "C" int riders_interp_linear(const int32_t* knot_xy, const float* knot_val, const int32_t* knot_count,
                                     int B, int max_knots, int H, int W, float fill,
                                     float* out, int32_t* status, int32_t* tri_out, int32_t* tri_count,
                                     void* workspace, void* stream) {
-    int rc = riders_interp_triangulate(knot_xy, knot_val, knot_count, B, max_knots, status, tri_out, tri_count, workspace, stream);
+    using namespace riders;
+    RIDERS_REQUIRE(B >= 0 && H > 0 && W > 0 && H <= 8192 && W <= 8192, "interp_linear: bad shape");
+    if (B == 0) return RIDERS_OK;
+    RIDERS_REQUIRE(out, "interp_linear: null pointer");
+    // two launches: stars (+ the fill value over the maps), then the rasteriser
+    int rc = interp_triangulate_impl(knot_xy, knot_val, knot_count, B, max_knots, status, tri_out, tri_count, out, fill, H * W, workspace, stream);
     if (rc != RIDERS_OK) return rc;
-    return riders_interp_fill(B, max_knots, H, W, fill, out, workspace, stream);
+    return interp_raster_impl(B, max_knots, H, W, fill, false, out, workspace, stream);
 }

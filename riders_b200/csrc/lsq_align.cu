@@ -10,9 +10,17 @@
 //   streams out = fl32(fl32(pred*s) + t) with the two clamps.  CTA 0 of each frame publishes
 //   sums / scale / shift.
 //
-// HBM roofline: 9 B/pixel read in pass 1 (mask-gated to >= 1 B/pixel), 4 B read + 4 B written
-// in pass 2 (the re-read of pred is an L2 hit for batches that fit the 126 MB L2).
+// One launch (lsq_fused_kernel, cooperative, persistent): both passes in ONE grid of co-resident CTAs with a grid-wide
+//   barrier in between - the default.  The same slices and the same summation order as the two-kernel form, so the
+//   results are bit-identical to it; what goes away is the second launch (at 16 frames the two dependent launches were
+//   launch-latency, not bandwidth: 40 us for 68 MB).  The two-kernel form stays as the route for stream capture /
+//   devices that refuse a cooperative launch.
+//
+// HBM roofline: algorithmic 13 B/pixel = pred + target (8) + mask (1) read, output (4) written.  Actual
+// traffic is lower: pass 1 reads the mask (1 B/pixel) and touches pred / target only in the 32-byte sectors that hold a
+// valid pixel; pass 2 reads pred once (4 B) and writes the output (4 B).
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace riders {
 
@@ -52,12 +60,9 @@ __device__ __forceinline__ void block_reduce5(Sums5& s, double (*sm)[5]) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(LSQ_THREADS)
-lsq_partial_kernel(const float* __restrict__ pred, const float* __restrict__ target,
-                   const uint8_t* __restrict__ mask, int npx, int ctas_per_frame,
-                   double* __restrict__ partial) {
-    __shared__ double sm[LSQ_THREADS / 32][5];
-    const int frame = blockIdx.y, cta = blockIdx.x;
+__device__ __forceinline__ void partial_slice(const float* __restrict__ pred, const float* __restrict__ target,
+                                              const uint8_t* __restrict__ mask, int npx, int ctas_per_frame,
+                                              double* __restrict__ partial, int frame, int cta, double (*sm)[5]) {
     const size_t fo = (size_t)frame * npx;
     const float* p = pred + fo;
     const float* t = target + fo;
@@ -95,16 +100,25 @@ lsq_partial_kernel(const float* __restrict__ pred, const float* __restrict__ tar
     block_reduce5(s, sm);
     if (threadIdx.x < 5)
         partial[((size_t)frame * ctas_per_frame + cta) * 5 + threadIdx.x] = sm[0][threadIdx.x];
+    __syncthreads();                                   // sm is reused by the next slice of a persistent CTA
 }
 
-__device__ __forceinline__ void solve_frame(const double* __restrict__ partial, int ctas_per_frame,
+__global__ void __launch_bounds__(LSQ_THREADS)
+lsq_partial_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                   const uint8_t* __restrict__ mask, int npx, int ctas_per_frame,
+                   double* __restrict__ partial) {
+    __shared__ double sm[LSQ_THREADS / 32][5];
+    partial_slice(pred, target, mask, npx, ctas_per_frame, partial, blockIdx.y, blockIdx.x, sm);
+}
+
+__device__ __forceinline__ void solve_frame(const double* partial, int ctas_per_frame,
                                             double* sm5, double* sm_ss) {
     // fixed-order sum of the per-CTA partials (identical in every CTA of the frame):
     // warp q adds sum q; lane l takes CTAs l, l+32, ... in order, then a fixed shuffle tree
     const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
     if (q < 5) {
         double a = 0.0;
-        for (int c = lane; c < ctas_per_frame; c += 32) a += partial[(size_t)c * 5 + q];
+        for (int c = lane; c < ctas_per_frame; c += 32) a += __ldcg(partial + (size_t)c * 5 + q);   // L2: written by other CTAs of this launch in the fused form
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
         if (lane == 0) sm5[q] = a;
@@ -124,14 +138,11 @@ __device__ __forceinline__ void solve_frame(const double* __restrict__ partial, 
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(LSQ_THREADS)
-lsq_apply_kernel(const float* __restrict__ pred, const double* __restrict__ partial,
-                 int npx, int ctas_per_frame,
-                 double* __restrict__ sums, double* __restrict__ scale_shift,
-                 float* __restrict__ out, float clamp_hi, float clamp_lo, int clamp_flags) {
-    __shared__ double sm5[5];
-    __shared__ double sm_ss[2];
-    const int frame = blockIdx.y, cta = blockIdx.x;
+__device__ __forceinline__ void apply_slice(const float* __restrict__ pred, const double* partial,
+                                            int npx, int ctas_per_frame,
+                                            double* __restrict__ sums, double* __restrict__ scale_shift,
+                                            float* __restrict__ out, float clamp_hi, float clamp_lo, int clamp_flags,
+                                            int frame, int cta, double* sm5, double* sm_ss) {
     solve_frame(partial + (size_t)frame * ctas_per_frame * 5, ctas_per_frame, sm5, sm_ss);
     if (cta == 0) {
         if (sums && threadIdx.x < 5) sums[frame * 5 + threadIdx.x] = sm5[threadIdx.x];
@@ -168,6 +179,51 @@ lsq_apply_kernel(const float* __restrict__ pred, const double* __restrict__ part
     }
 }
 
+__global__ void __launch_bounds__(LSQ_THREADS)
+lsq_apply_kernel(const float* __restrict__ pred, const double* __restrict__ partial,
+                 int npx, int ctas_per_frame,
+                 double* __restrict__ sums, double* __restrict__ scale_shift,
+                 float* __restrict__ out, float clamp_hi, float clamp_lo, int clamp_flags) {
+    __shared__ double sm5[5];
+    __shared__ double sm_ss[2];
+    apply_slice(pred, partial, npx, ctas_per_frame, sums, scale_shift, out, clamp_hi, clamp_lo, clamp_flags,
+                blockIdx.y, blockIdx.x, sm5, sm_ss);
+}
+
+// Both passes in one cooperative launch: every CTA walks the (frame, slice) items with the grid stride, the grid barrier
+// separates "all partials written" from "solve + apply".  Slices, thread -> pixel assignment and summation order are those
+// of the two kernels above, so the outputs are bit-identical to theirs on any grid size.
+__global__ void __launch_bounds__(LSQ_THREADS)
+lsq_fused_kernel(const float* __restrict__ pred, const float* __restrict__ target, const uint8_t* __restrict__ mask,
+                 int B, int npx, int ctas_per_frame, double* partial,
+                 double* __restrict__ sums, double* __restrict__ scale_shift,
+                 float* __restrict__ out, float clamp_hi, float clamp_lo, int clamp_flags) {
+    __shared__ double sm[LSQ_THREADS / 32][5];
+    __shared__ double sm5[5];
+    __shared__ double sm_ss[2];
+    const int items = B * ctas_per_frame;
+    for (int it = blockIdx.x; it < items; it += gridDim.x)
+        partial_slice(pred, target, mask, npx, ctas_per_frame, partial, it / ctas_per_frame, it % ctas_per_frame, sm);
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    if (out) {
+        for (int it = blockIdx.x; it < items; it += gridDim.x) {
+            apply_slice(pred, partial, npx, ctas_per_frame, sums, scale_shift, out, clamp_hi, clamp_lo, clamp_flags,
+                        it / ctas_per_frame, it % ctas_per_frame, sm5, sm_ss);
+            __syncthreads();                           // sm5 / sm_ss are rewritten by the next item
+        }
+    } else {
+        for (int frame = blockIdx.x; frame < B; frame += gridDim.x) {
+            apply_slice(pred, partial, npx, ctas_per_frame, sums, scale_shift, nullptr, clamp_hi, clamp_lo, clamp_flags,
+                        frame, 0, sm5, sm_ss);
+            __syncthreads();
+        }
+    }
+}
+
+static int g_lsq_mode = 1;                             // 1: one cooperative launch (default), 0: the two-kernel form
+void set_lsq_mode(int m) { g_lsq_mode = m; }
+
 }  // namespace riders
 
 extern "C" size_t riders_lsq_workspace_bytes(int B, int H, int W) {
@@ -190,6 +246,36 @@ extern "C" int riders_lsq_align(const float* pred, const float* target, const ui
     const int npx = H * W;
     const int ctas = ceil_div(npx, PX_PER_CTA);
     cudaStream_t st = (cudaStream_t)stream;
+    if (g_lsq_mode == 1) {
+        // co-resident capacity of this device for the fused kernel (cached per device)
+        static int capacity[64] = {0};
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+        if (!capacity[dev]) {
+            int per_sm = 0, coop = 0;
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+            if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lsq_fused_kernel, LSQ_THREADS, 0) == cudaSuccess && per_sm > 0)
+                capacity[dev] = per_sm * sm_count();
+            else
+                capacity[dev] = -1;
+            cudaGetLastError();
+        }
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cap);
+        if (capacity[dev] > 0 && cap == cudaStreamCaptureStatusNone) {
+            const int items = B * ctas;
+            int grid1 = items < capacity[dev] ? items : capacity[dev];
+            int npx_ = npx, ctas_ = ctas, B_ = B;
+            double* part = (double*)workspace;
+            void* args[] = {(void*)&pred, (void*)&target, (void*)&mask, (void*)&B_, (void*)&npx_, (void*)&ctas_, (void*)&part,
+                            (void*)&sums, (void*)&scale_shift, (void*)&out, (void*)&clamp_hi, (void*)&clamp_lo, (void*)&clamp_flags};
+            if (cudaLaunchCooperativeKernel((const void*)lsq_fused_kernel, dim3(grid1), dim3(LSQ_THREADS), args, 0, st) == cudaSuccess) {
+                count_launches(1);
+                return check_launch("lsq_align (fused)");
+            }
+            cudaGetLastError();                        // refused (e.g. MPS / partitioned device): take the two-kernel form
+        }
+    }
     dim3 grid(ctas, B);
     count_launches(2);
     lsq_partial_kernel<<<grid, LSQ_THREADS, 0, st>>>(pred, target, mask, npx, ctas, (double*)workspace);

@@ -65,6 +65,11 @@ class _span(object):
             _timer.spans.setdefault(self.name, []).append((self.a, b, self.work))
 
 
+def debug_set(key, value):
+    """Tuning / test knobs of the library (riders_debug_set): 'lsq_fused' 1|0, 'reduce_rows', 'gather_smem_kb', ..."""
+    _lib.check(_lib.lib().riders_debug_set(key.encode(), int(value)), "riders_debug_set")
+
+
 def launch_count():
     """Kernels launched by libriders_b200.so in this process so far (bench.py's gpu_launches)."""
     return int(_lib.lib().riders_launch_count())
@@ -681,7 +686,9 @@ def lsq_align(pred, target, mask, clamp_hi=None, clamp_lo=None, want_out=True):
     ss = torch.empty((B, 2), dtype=torch.float64, device=dev)
     out = torch.empty_like(pred) if want_out else None
     flags = (1 if clamp_hi is not None else 0) | (2 if clamp_lo is not None else 0)
-    with _span("lsq_align", B * H * W * (9 + (4 + 4 if want_out else 0))):
+    # algorithmic bytes: pred + target + mask read once (9 B/pixel) + the output written (4 B/pixel); the
+    # kernel's own second read of pred is traffic, not work
+    with _span("lsq_align", B * H * W * (9 + (4 if want_out else 0))):
         rc = L.riders_lsq_align(_ptr(pred), _ptr(target), _ptr(mask), B, H, W, _ptr(sums), _ptr(ss), _ptr(out),
                                 float(clamp_hi or 0.0), float(clamp_lo or 0.0), flags, _ptr(ws), _stream())
     _lib.check(rc, "riders_lsq_align")
@@ -705,7 +712,7 @@ def l1_scale_align(pred, target, mask, bounds=(0.01, 0.3), clamp_hi=None, clamp_
     nfev = torch.empty((B,), dtype=torch.int32, device=dev)
     out = torch.empty_like(pred) if want_out else None
     flags = (1 if clamp_hi is not None else 0) | (2 if clamp_lo is not None else 0)
-    with _span("l1_scale_align", B * H * W * (9 + (8 if want_out else 0))):
+    with _span("l1_scale_align", B * H * W * (9 + (4 if want_out else 0))):
         rc = L.riders_l1_scale_align(_ptr(pred), _ptr(target), _ptr(mask), B, H, W, cap,
                                      float(bounds[0]), float(bounds[1]), float(xatol), int(maxiter),
                                      _ptr(scale), _ptr(fval), _ptr(nfev), _ptr(out),
@@ -791,13 +798,11 @@ def interp_linear(knot_xy, knot_val, knot_count, H, W, fill=1.0, want_triangles=
     status = torch.zeros((B,), dtype=torch.int32, device=dev)
     tri = torch.full((B, 2 * max_knots, 3), -1, dtype=torch.int32, device=dev) if want_triangles else None
     tcount = torch.zeros((B,), dtype=torch.int32, device=dev) if want_triangles else None
-    with _span("interp_triangulate", B * max_knots * (12 + 2 * 48)):
-        rc = L.riders_interp_triangulate(_ptr(knot_xy), _ptr(knot_val), _ptr(knot_count), B, max_knots,
-                                         _ptr(status), _ptr(tri), _ptr(tcount), _ptr(ws), _stream())
-    _lib.check(rc, "riders_interp_triangulate")
-    with _span("interp_fill", B * H * W * 4 + B * 2 * max_knots * 48):
-        rc = L.riders_interp_fill(B, max_knots, H, W, float(fill), _ptr(out), _ptr(ws), _stream())
-    _lib.check(rc, "riders_interp_fill")
+    # one C call = two launches (stars + fill value, rasteriser); algorithmic bytes: the output map + 12 B per knot
+    with _span("interp_linear", B * H * W * 4 + B * max_knots * 12):
+        rc = L.riders_interp_linear(_ptr(knot_xy), _ptr(knot_val), _ptr(knot_count), B, max_knots, H, W, float(fill),
+                                    _ptr(out), _ptr(status), _ptr(tri), _ptr(tcount), _ptr(ws), _stream())
+    _lib.check(rc, "riders_interp_linear")
     if want_triangles:
         return out, status, tri, tcount
     return out, status

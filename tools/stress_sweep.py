@@ -54,8 +54,9 @@ def main():
                     out, status = ops.interp_linear(xy, val, cnt, H, W, 1.0)
             s = t.summary()
             assert int(status[0]) == 0
-            rec.update(triangulate_ms=round(s["interp_triangulate"][1] / 5, 4), fill_ms=round(s["interp_fill"][1] / 5, 4),
-                       fill_GBps=round((H * W * 4 + 2 * K * 48) / (s["interp_fill"][1] / 5) / 1e6, 1))
+            ims = s["interp_linear"][1] / 5          # stars + fill value + rasteriser (two launches)
+            rec.update(interp_ms=round(ims, 4), interp_GBps=round((H * W * 4 + 12 * K) / ims / 1e6, 1),
+                       interp_frac_hbm=round((H * W * 4 + 12 * K) / ims / 1e6 / HBM, 3))
             print(json.dumps(rec), flush=True)
 
 

@@ -9,13 +9,14 @@ import sys
 STAGE = {  # kernel substring -> bench stage (ops.StageTimer span name); calls per step divide the per-step sum
     "roi_gather": "roi_gather", "loftr_layer_tc": "loftr_transformer", "loftr_pack": "loftr_transformer",
     "confidence_reduce": "confidence_reduce", "lsq_": "lsq_align", "extract_knots": "extract_knots",
-    "delaunay": "interp_triangulate", "interp_fill": "interp_fill", "scaffold": "scale_scaffold",
+    "delaunay": "interp_linear", "raster_kernel": "interp_linear", "scaffold": "scale_scaffold", "l1_": "l1_scale_align",
+    "compact_valid": "l1_scale_align",
     "upsample_nearest": "upsample_nearest", "bias_act_nhwc": "bias_act", "bias_act_generic": "bias_act",
     "bias_leaky_concat": "leaky_concat", "leaky_concat_nhwc": "leaky_concat", "d2s_bias_act": "d2s_bias_act_concat",
     "conv3x3_head": "conv3x3_head", "decoder_tail": "decoder_tail", "bias_act_pad": "bias_act",
 }
 CALLS = {"roi_gather": 5, "loftr_transformer": 1, "confidence_reduce": 1, "lsq_align": 1, "extract_knots": 1,
-         "interp_triangulate": 1, "interp_fill": 1, "scale_scaffold": 1}
+         "interp_linear": 1, "l1_scale_align": 1, "scale_scaffold": 1}
 
 lines = [l for l in open(sys.argv[1]) if not l.startswith("==")]
 rows = collections.OrderedDict()
