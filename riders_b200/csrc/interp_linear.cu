@@ -251,15 +251,30 @@ raster_kernel(uint8_t* ws_base, WsLayout L, int max_knots, int H, int W, float* 
         const TriRec t = tris[ti];
         const int x0 = max(min(t.ax, min(t.bx, t.cx)), 0), x1 = min(max(t.ax, max(t.bx, t.cx)), W - 1);
         const int y0 = max(min(t.ay, min(t.by, t.cy)), 0), y1 = min(max(t.ay, max(t.by, t.cy)), H - 1);
+        // d(edge function)/dx per edge; for a wide bounding box (hull slivers) each row first gets its conservative x span
+        // from the three half-planes in float, so that the exact integer test below only visits chunks near the triangle
+        const int Aa = t.by - t.cy, Ab = t.cy - t.ay, Ac = t.ay - t.by;
+        const bool wide = (x1 - x0) >= 48;
         for (int y = y0 + warp; y <= y1; y += RASTER_THREADS / 32) {
-            for (int xb = x0; xb <= x1; xb += 32) {
+            int xs = x0, xe = x1;
+            if (wide) {
+                const float Ca = (float)(t.bx * (t.cy - y) - t.cx * (t.by - y));
+                const float Cb = (float)(t.cx * (t.ay - y) - t.ax * (t.cy - y));
+                const float Cc = (float)(t.ax * (t.by - y) - t.bx * (t.ay - y));
+                float lo = (float)x0, hi = (float)x1;
+                if (Aa > 0) lo = fmaxf(lo, -Ca / (float)Aa - 0.02f); else if (Aa < 0) hi = fminf(hi, Ca / (float)(-Aa) + 0.02f); else if (Ca < 0.f) continue;
+                if (Ab > 0) lo = fmaxf(lo, -Cb / (float)Ab - 0.02f); else if (Ab < 0) hi = fminf(hi, Cb / (float)(-Ab) + 0.02f); else if (Cb < 0.f) continue;
+                if (Ac > 0) lo = fmaxf(lo, -Cc / (float)Ac - 0.02f); else if (Ac < 0) hi = fminf(hi, Cc / (float)(-Ac) + 0.02f); else if (Cc < 0.f) continue;
+                xs = max(x0, (int)floorf(lo)); xe = min(x1, (int)ceilf(hi));
+            }
+            for (int xb = xs; xb <= xe; xb += 32) {
                 const int x = xb + lane;
                 // edge functions (the triangle is counter-clockwise): wa = orient(p, b, c), wb = orient(p, c, a), wc = orient(p, a, b)
                 const int dxa = t.bx - x, dxb = t.cx - x, dxc = t.ax - x;
                 const int wa = dxa * (t.cy - y) - (t.by - y) * dxb;
                 const int wb = dxb * (t.ay - y) - (t.cy - y) * dxc;
                 const int wc = dxc * (t.by - y) - (t.ay - y) * dxa;
-                if (x <= x1 && (wa | wb | wc) >= 0) {
+                if (x <= xe && (wa | wb | wc) >= 0) {
                     float v;
                     if (wa == 0) v = edge_value(t.bx, t.by, t.vb, t.cx, t.cy, t.vc, x, y);           // on edge b-c (or at b / c)
                     else if (wb == 0) v = edge_value(t.cx, t.cy, t.vc, t.ax, t.ay, t.va, x, y);

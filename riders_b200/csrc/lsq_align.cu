@@ -10,11 +10,10 @@
 //   streams out = fl32(fl32(pred*s) + t) with the two clamps.  CTA 0 of each frame publishes
 //   sums / scale / shift.
 //
-// One launch (lsq_fused_kernel, cooperative, persistent): both passes in ONE grid of co-resident CTAs with a grid-wide
-//   barrier in between - the default.  The same slices and the same summation order as the two-kernel form, so the
-//   results are bit-identical to it; what goes away is the second launch (at 16 frames the two dependent launches were
-//   launch-latency, not bandwidth: 40 us for 68 MB).  The two-kernel form stays as the route for stream capture /
-//   devices that refuse a cooperative launch.
+// Default: pass 2 is a programmatic dependent launch (lsq_apply_pdl_kernel) that loads its `pred` pixels while pass 1 still
+//   runs.  Also kept: lsq_fused_kernel, both passes in ONE cooperative grid with a grid-wide barrier (measured SLOWER at
+//   1 and 16 frames: the cooperative launch itself costs more than the second launch it saves - profiles/r02_microbench_*),
+//   and the two plain launches.  All three use the same slices and summation order: bit-identical results.
 //
 // HBM roofline: algorithmic 13 B/pixel = pred + target (8) + mask (1) read, output (4) written.  Actual
 // traffic is lower: pass 1 reads the mask (1 B/pixel) and touches pred / target only in the 32-byte sectors that hold a
@@ -108,6 +107,7 @@ lsq_partial_kernel(const float* __restrict__ pred, const float* __restrict__ tar
                    const uint8_t* __restrict__ mask, int npx, int ctas_per_frame,
                    double* __restrict__ partial) {
     __shared__ double sm[LSQ_THREADS / 32][5];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a programmatic dependent pass 2 may become resident now
     partial_slice(pred, target, mask, npx, ctas_per_frame, partial, blockIdx.y, blockIdx.x, sm);
 }
 
@@ -190,6 +190,68 @@ lsq_apply_kernel(const float* __restrict__ pred, const double* __restrict__ part
                 blockIdx.y, blockIdx.x, sm5, sm_ss);
 }
 
+// Pass 2 as a PROGRAMMATIC DEPENDENT LAUNCH (the default): launched with programmatic stream serialisation it becomes
+// resident while pass 1 is still running, loads its 16 pixels of `pred` per thread (they do not depend on pass 1), and only
+// then waits for pass 1's partials (griddepcontrol.wait) - the HBM read of pass 2 and the launch latency of the second kernel
+// hide under pass 1.  Same arithmetic as lsq_apply_kernel, bit for bit.
+__global__ void __launch_bounds__(LSQ_THREADS)
+lsq_apply_pdl_kernel(const float* __restrict__ pred, const double* partial,
+                     int npx, int ctas_per_frame,
+                     double* __restrict__ sums, double* __restrict__ scale_shift,
+                     float* __restrict__ out, float clamp_hi, float clamp_lo, int clamp_flags) {
+    __shared__ double sm5[5];
+    __shared__ double sm_ss[2];
+    const int frame = blockIdx.y, cta = blockIdx.x;
+    const size_t fo = (size_t)frame * npx;
+    const float* p = pred + fo;
+    float* o = out ? out + fo : nullptr;
+    const int begin = cta * PX_PER_CTA;
+    const int end = min(begin + PX_PER_CTA, npx);
+    const bool vec_ok = out && ((npx & 3) == 0) && ((((uintptr_t)p) & 15) == 0) && ((((uintptr_t)o) & 15) == 0);
+    float4 v[PX_PER_THREAD / 4];
+    if (out) {
+#pragma unroll
+        for (int it = 0; it < PX_PER_THREAD / 4; ++it) {
+            const int i = begin + (it * LSQ_THREADS + threadIdx.x) * 4;
+            v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (vec_ok) { if (i < end) v[it] = *reinterpret_cast<const float4*>(p + i); }
+            else {
+                if (i < end) v[it].x = p[i];
+                if (i + 1 < end) v[it].y = p[i + 1];
+                if (i + 2 < end) v[it].z = p[i + 2];
+                if (i + 3 < end) v[it].w = p[i + 3];
+            }
+        }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");            // pass 1 has completed and its partials are visible
+    solve_frame(partial + (size_t)frame * ctas_per_frame * 5, ctas_per_frame, sm5, sm_ss);
+    if (cta == 0) {
+        if (sums && threadIdx.x < 5) sums[frame * 5 + threadIdx.x] = sm5[threadIdx.x];
+        if (scale_shift && threadIdx.x < 2) scale_shift[frame * 2 + threadIdx.x] = sm_ss[threadIdx.x];
+    }
+    if (!out) return;
+    const float s = (float)sm_ss[0], t = (float)sm_ss[1];
+    const bool hi_on = clamp_flags & 1, lo_on = clamp_flags & 2;
+    auto f = [&](float x) {
+        float r = __fadd_rn(__fmul_rn(x, s), t);
+        if (hi_on && r > clamp_hi) r = clamp_hi;
+        if (lo_on && r < clamp_lo) r = clamp_lo;
+        return r;
+    };
+#pragma unroll
+    for (int it = 0; it < PX_PER_THREAD / 4; ++it) {
+        const int i = begin + (it * LSQ_THREADS + threadIdx.x) * 4;
+        if (vec_ok) {
+            if (i < end) *reinterpret_cast<float4*>(o + i) = make_float4(f(v[it].x), f(v[it].y), f(v[it].z), f(v[it].w));
+        } else {
+            if (i < end) o[i] = f(v[it].x);
+            if (i + 1 < end) o[i + 1] = f(v[it].y);
+            if (i + 2 < end) o[i + 2] = f(v[it].z);
+            if (i + 3 < end) o[i + 3] = f(v[it].w);
+        }
+    }
+}
+
 // Both passes in one cooperative launch: every CTA walks the (frame, slice) items with the grid stride, the grid barrier
 // separates "all partials written" from "solve + apply".  Slices, thread -> pixel assignment and summation order are those
 // of the two kernels above, so the outputs are bit-identical to theirs on any grid size.
@@ -221,7 +283,8 @@ lsq_fused_kernel(const float* __restrict__ pred, const float* __restrict__ targe
     }
 }
 
-static int g_lsq_mode = 1;                             // 1: one cooperative launch (default), 0: the two-kernel form
+static int g_lsq_mode = 2;                             // 2: two kernels, the second a programmatic dependent launch (default);
+                                                       // 1: one cooperative launch; 0: two plain kernels
 void set_lsq_mode(int m) { g_lsq_mode = m; }
 
 }  // namespace riders
@@ -280,6 +343,19 @@ extern "C" int riders_lsq_align(const float* pred, const float* target, const ui
     count_launches(2);
     lsq_partial_kernel<<<grid, LSQ_THREADS, 0, st>>>(pred, target, mask, npx, ctas, (double*)workspace);
     dim3 grid2(out ? ctas : 1, B);
+    if (g_lsq_mode == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid2; cfg.blockDim = dim3(LSQ_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        const double* part = (const double*)workspace;
+        if (cudaLaunchKernelEx(&cfg, lsq_apply_pdl_kernel, pred, part, npx, ctas, sums, scale_shift, out, clamp_hi, clamp_lo,
+                               clamp_flags) == cudaSuccess)
+            return check_launch("lsq_align (pdl)");
+        cudaGetLastError();                            // attribute refused: plain second launch below
+    }
     lsq_apply_kernel<<<grid2, LSQ_THREADS, 0, st>>>(pred, (const double*)workspace, npx, ctas, sums, scale_shift,
                                                     out, clamp_hi, clamp_lo, clamp_flags);
     return check_launch("lsq_align");

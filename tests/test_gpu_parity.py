@@ -343,26 +343,32 @@ def test_interpolator_class_and_qhull_errors(golden):
         Interpolator2D(np.ones((16, 16), np.float32), np.ones((16, 16), np.float32), valid).generate_interpolated_scale_map("linear")
 
 
-def test_lsq_one_launch_equals_the_two_kernel_form():
-    """riders_lsq_align's default is ONE cooperative launch (partials -> grid barrier -> solve + apply); it must be
-    bit-identical to the two-kernel form (same slices, same summation order) and cost one launch."""
+def test_lsq_launch_forms_are_bit_identical():
+    """riders_lsq_align has three launch forms - two plain kernels, one cooperative launch (partials -> grid barrier ->
+    solve + apply), and the default: pass 2 as a programmatic dependent launch that prefetches `pred` under pass 1.  Same
+    slices and summation order: bit-identical outputs."""
     B, Hh, Ww = 5, 512, 640
     ins = [synth.alignment_inputs(20 + b, 300 + 40 * b, Hh, Ww) for b in range(B)]
     p, t, m = (cu(np.stack([x[i] for x in ins])) for i in range(3))
     hi, lo = 10.0, float(np.float32(1 / 255.0))
+    res, launches = {}, {}
     try:
-        ops.debug_set("lsq_fused", 0)
-        n0 = ops.launch_count()
-        s2, ss2, o2 = ops.lsq_align(p, t, m, clamp_hi=hi, clamp_lo=lo)
-        n1 = ops.launch_count()
-        ops.debug_set("lsq_fused", 1)
-        s1, ss1, o1 = ops.lsq_align(p, t, m, clamp_hi=hi, clamp_lo=lo)
-        n2 = ops.launch_count()
-        _, ss1b, _ = ops.lsq_align(p, t, m, want_out=False)
+        for mode in (0, 1, 2):
+            ops.debug_set("lsq_fused", mode)
+            n0 = ops.launch_count()
+            res[mode] = ops.lsq_align(p, t, m, clamp_hi=hi, clamp_lo=lo)
+            launches[mode] = ops.launch_count() - n0
+            res[(mode, "noout")] = ops.lsq_align(p, t, m, want_out=False)[1]
+            res[(mode, "odd")] = ops.lsq_align(p[:, 1:, 3:], t[:, 1:, 3:], m[:, 1:, 3:], clamp_hi=hi, clamp_lo=lo)    # unaligned
     finally:
-        ops.debug_set("lsq_fused", 1)
-    assert (n1 - n0, n2 - n1) == (2, 1)
-    assert torch.equal(s1, s2) and torch.equal(ss1, ss2) and torch.equal(o1, o2) and torch.equal(ss1b, ss1)
+        ops.debug_set("lsq_fused", 2)
+    assert launches == {0: 2, 1: 1, 2: 2}
+    for mode in (1, 2):
+        for a, b in zip(res[mode], res[0]):
+            assert torch.equal(a, b)
+        assert torch.equal(res[(mode, "noout")], res[0][1])
+        for a, b in zip(res[(mode, "odd")], res[(0, "odd")]):
+            assert torch.equal(a, b)
 
 
 # ------------------------------------------------------------------------------------ whole chain

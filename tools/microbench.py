@@ -223,6 +223,48 @@ def bench_interp(B=64, K=512, H=512, W=640):
     report("extract_knots", ms, best, B * H * W * 9, B=B, K=K)
 
 
+def bench_frontend(H=512, W=640, K=512):
+    """The SML front-end kernels ALONE on an otherwise idle GPU (in the bench step they share the device with RC-Net), at the
+    batch sizes of configs[0] (1 frame), configs[1] (16) and 64: the three launch forms of the LSQ alignment, the L1 Optimizer,
+    knot extraction, and the two launches of the interpolation separately."""
+    import ctypes as C
+    from riders_b200 import _lib
+    L = _lib.lib()
+    for B in (1, 16, 64):
+        data = [synth.alignment_inputs(s, K, H, W) for s in range(4)]
+        rep = (B + 3) // 4
+        p = torch.from_numpy(np.stack([d[0] for d in data])).to(DEV).repeat(rep, 1, 1)[:B].contiguous()
+        t = torch.from_numpy(np.stack([d[1] for d in data])).to(DEV).repeat(rep, 1, 1)[:B].contiguous()
+        m = torch.from_numpy(np.stack([d[2] for d in data])).to(DEV).repeat(rep, 1, 1)[:B].contiguous()
+        nb = B * H * W * 13
+        for mode, name in ((0, "two_kernels"), (1, "cooperative_one_launch"), (2, "pdl")):
+            ops.debug_set("lsq_fused", mode)
+            ms, best = timeit(lambda: ops.lsq_align(p, t, m, 10.0, 1 / 255.0), iters=20)
+            report("lsq_align_" + name, ms, best, nb, B=B)
+        ops.debug_set("lsq_fused", 2)
+        ms, best = timeit(lambda: ops.l1_scale_align(p, t, m, clamp_hi=10.0, clamp_lo=1 / 255.0), iters=20)
+        report("l1_scale_align", ms, best, nb, B=B)
+        _, _, aligned = ops.lsq_align(p, t, m, 10.0, 1 / 255.0)
+        ms, best = timeit(lambda: ops.extract_knots(aligned, t, m, K), iters=20)
+        report("extract_knots", ms, best, B * (H * W + 20 * K), B=B, K=K)
+        xy, sc, _, cnt = ops.extract_knots(aligned, t, m, K)
+        ws = torch.empty(L.riders_interp_workspace_bytes(B, K, H, W), dtype=torch.uint8, device=DEV)
+        out = torch.empty((B, H, W), device=DEV)
+        status = torch.zeros(B, dtype=torch.int32, device=DEV)
+        vp = lambda x: C.c_void_p(x.data_ptr())
+        st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        ms, best = timeit(lambda: L.riders_interp_triangulate(vp(xy), vp(sc), vp(cnt), B, K, vp(status), None, None, vp(ws), st()), iters=20)
+        report("interp_stars (delaunay_star_kernel, no fill value)", ms, best, B * 12 * K, B=B, K=K)
+        ms, best = timeit(lambda: L.riders_interp_fill(B, K, H, W, 1.0, vp(out), vp(ws), st()), iters=20)
+        report("interp_fill (fill value + raster_kernel)", ms, best, B * H * W * 4, B=B, K=K)
+        ms, best = timeit(lambda: ops.interp_linear(xy, sc, cnt, H, W, 1.0), iters=20)
+        report("interp_linear (stars + fill value, raster)", ms, best, B * (H * W * 4 + 12 * K), B=B, K=K)
+        assert int(status.abs().sum()) == 0
+        depth = torch.where(m, 1.0 / t.clamp_min(1e-6), torch.zeros_like(t))
+        ms, best = timeit(lambda: ops.scale_scaffold(aligned, depth, t, m), iters=20)
+        report("scale_scaffold", ms, best, B * H * W * 25, B=B)
+
+
 def bench_membw(nbytes=4 << 30):
     """Direction-specific HBM rooflines on this box (library kernels, for reference next to MEASURED_PEAKS' copy figure):
     write-only (fill_), read-only (sum), copy."""
