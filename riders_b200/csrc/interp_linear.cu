@@ -15,8 +15,9 @@
 //                          rows of each; a pixel is written iff its three exact integer edge functions are >= 0 (a pixel on
 //                          the hull boundary is inside, like SciPy's eps test).  Pixels on an edge or a knot are evaluated
 //                          from the edge's two knots in canonical order, so the two triangles sharing the edge write
-//                          identical bits (benign race, deterministic image).  value = (wa va + wb vb + wc vc) / (wa + wb + wc)
-//                          in fp64: exact at the knots.
+//                          identical bits (benign race, deterministic image); that path is exact at the knots.  Interior
+//                          pixels evaluate the triangle's affine interpolant va + gx (x - ax) + gy (y - ay) in fp64 (the
+//                          barycentric sum written as a plane: two fused multiply-adds per pixel instead of a division).
 //
 // Round 1 ran a divide-and-conquer triangulation with ONE CTA per frame (0.24 ms for one 200-knot frame, 0.66 ms for 16
 // frames, a cliff past 680 knots) and a gather fill that tested ~15 bounding-box candidates per pixel; the star form uses
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(OC_THREADS)
 extract_knots_kernel(const float* __restrict__ pred, const float* __restrict__ sparse,
                      const uint8_t* __restrict__ valid, int H, int W, int max_knots,
                      int32_t* __restrict__ knot_xy, float* __restrict__ knot_scale,
-                     float* __restrict__ knot_shift, int32_t* __restrict__ knot_count) {
+                     float* __restrict__ knot_shift, int32_t* __restrict__ knot_count, unsigned* aggregates) {
     const int frame = blockIdx.y;
     const int npx = H * W;
     const size_t fo = (size_t)frame * npx;
@@ -71,7 +72,7 @@ extract_knots_kernel(const float* __restrict__ pred, const float* __restrict__ s
             knot_scale[ko + pos] = __fdiv_rn(s, p);          // interpolator.py:31
             knot_shift[ko + pos] = __fsub_rn(s, p);          // interpolator.py:32
         }
-    });
+    }, aggregates ? aggregates + (size_t)frame * gridDim.x : nullptr);
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) knot_count[frame] = upto;
 }
 
@@ -80,6 +81,89 @@ extract_knots_kernel(const float* __restrict__ pred, const float* __restrict__ s
 // ---------------------------------------------------------------------------------------------
 constexpr int STAR_WARPS = 8;
 constexpr int STAR_THREADS = STAR_WARPS * 32;
+constexpr int STAR_LANES = 32;              // device stars live in registers, one neighbour per lane: at most 32 neighbours
+                                            // (random knot sets stay below 20; more is reported as RIDERS_EINTERNAL)
+#define FULL 0xffffffffu
+
+// The warp-parallel form of star::accepts / star::insert (delaunay_star.cuh holds the scalar reference the host tests run):
+// lane j < k holds neighbour j (ex, ey relative to p, eid its knot index), counter-clockwise, cyclic.
+struct WarpStar {
+    int ex, ey, eid, k;
+
+    // every lane tests ITS OWN candidate (ux, uy, rid) against the read-only star
+    __device__ __forceinline__ bool accepts_each(int p, int ux, int uy, int rid) const {
+        if (k == 0) return true;
+        int ax = 0, ay = 0, aid = 0, bx = 0, by = 0, bid = 0;
+        bool found = false;
+        int cx = __shfl_sync(FULL, ex, 0), cy = __shfl_sync(FULL, ey, 0), cid = __shfl_sync(FULL, eid, 0);
+        for (int j = 0; j < k; ++j) {                               // uniform trip count: no divergence around the shuffles
+            const int jn = j + 1 == k ? 0 : j + 1;
+            const int nx = __shfl_sync(FULL, ex, jn), ny = __shfl_sync(FULL, ey, jn), nid = __shfl_sync(FULL, eid, jn);
+            if (!found && (k == 1 || star::in_wedge(cx, cy, nx, ny, ux, uy))) {
+                found = true; ax = cx; ay = cy; aid = cid; bx = nx; by = ny; bid = nid;
+            }
+            cx = nx; cy = ny; cid = nid;
+        }
+        if (star::cross2(ax, ay, ux, uy) == 0 && star::dot2(ax, ay, ux, uy) > 0)             // same ray: the nearer one only
+            return star::dot2(ux, uy, ux, uy) < star::dot2(ax, ay, ax, ay);
+        if (k == 1) return true;
+        if (star::cross2(ax, ay, bx, by) <= 0) return true;                                  // exterior wedge of a hull knot
+        return star::inside_sos(ax, ay, bx, by, ux, uy, rid, p, aid, bid);
+    }
+
+    __device__ __forceinline__ void get(int j, int& x, int& y, int& id) const {
+        x = __shfl_sync(FULL, ex, j); y = __shfl_sync(FULL, ey, j); id = __shfl_sync(FULL, eid, j);
+    }
+
+    // the whole warp inserts ONE candidate (warp-uniform arguments): 0 rejected, 1 inserted, -1 more than STAR_LANES neighbours
+    __device__ __forceinline__ int insert(int p, int ux, int uy, int rid, int lane) {
+        if (k == 0) { if (lane == 0) { ex = ux; ey = uy; eid = rid; } k = 1; return 1; }
+        int j = 0;
+        if (k >= 2) {
+            const int ln = lane + 1 == k ? 0 : lane + 1;
+            const int nx = __shfl_sync(FULL, ex, ln), ny = __shfl_sync(FULL, ey, ln);
+            const unsigned hit = __ballot_sync(FULL, lane < k && star::in_wedge(ex, ey, nx, ny, ux, uy));
+            j = hit ? __ffs(hit) - 1 : 0;
+        }
+        int ax, ay, aid;
+        get(j, ax, ay, aid);
+        const bool same_ray = star::cross2(ax, ay, ux, uy) == 0 && star::dot2(ax, ay, ux, uy) > 0;
+        if (same_ray) {
+            if (!(star::dot2(ux, uy, ux, uy) < star::dot2(ax, ay, ax, ay))) return 0;
+        } else if (k >= 2) {
+            int bx, by, bid;
+            get(j + 1 == k ? 0 : j + 1, bx, by, bid);
+            if (star::cross2(ax, ay, bx, by) > 0 && !star::inside_sos(ax, ay, bx, by, ux, uy, rid, p, aid, bid)) return 0;
+        }
+        int first = j + 1 == k ? 0 : j + 1;
+        int kept = same_ray ? k - 1 : k;
+        while (kept >= 2) {                                          // counter-clockwise side of the cavity
+            int bx, by, bid, cx, cy, cid;
+            get(first, bx, by, bid);
+            get(first + 1 == k ? 0 : first + 1, cx, cy, cid);
+            if (star::cross2(ux, uy, bx, by) <= 0 || star::cross2(bx, by, cx, cy) <= 0) break;
+            if (!star::inside_sos(bx, by, cx, cy, ux, uy, rid, cid, p, bid)) break;
+            first = first + 1 == k ? 0 : first + 1; --kept;
+        }
+        while (kept >= 2) {                                          // clockwise side
+            int a = first + kept - 1; if (a >= k) a -= k;
+            const int z = a == 0 ? k - 1 : a - 1;
+            int qx, qy, qid, zx, zy, zid;
+            get(a, qx, qy, qid);
+            get(z, zx, zy, zid);
+            if (star::cross2(qx, qy, ux, uy) <= 0 || star::cross2(zx, zy, qx, qy) <= 0) break;
+            if (!star::inside_sos(zx, zy, qx, qy, ux, uy, rid, zid, p, qid)) break;
+            --kept;
+        }
+        if (kept + 1 > STAR_LANES) return -1;
+        int src = first + lane - 1; if (src >= k) src -= k; if (src < 0) src = 0;         // new order: r, then the survivors
+        const int nx = __shfl_sync(FULL, ex, src), ny = __shfl_sync(FULL, ey, src), nid = __shfl_sync(FULL, eid, src);
+        if (lane == 0) { ex = ux; ey = uy; eid = rid; }
+        else if (lane <= kept) { ex = nx; ey = ny; eid = nid; }
+        k = kept + 1;
+        return 1;
+    }
+};
 
 __global__ void __launch_bounds__(STAR_THREADS)
 delaunay_star_kernel(const int32_t* __restrict__ knot_xy, const float* __restrict__ knot_val,
@@ -87,7 +171,6 @@ delaunay_star_kernel(const int32_t* __restrict__ knot_xy, const float* __restric
                      int32_t* __restrict__ status, int32_t* __restrict__ tri_out, int32_t* __restrict__ tri_count,
                      float* __restrict__ fill_out, float fill, int npx) {
     extern __shared__ __align__(16) int s_pts[];                 // x | y << 16 of every knot of the frame
-    __shared__ star::Star s_star[STAR_WARPS][2];
     __shared__ int s_unsorted;
     const int frame = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int* counters = (int*)(ws_base + L.counters) + (size_t)frame * CNT_STRIDE;
@@ -103,7 +186,7 @@ delaunay_star_kernel(const int32_t* __restrict__ knot_xy, const float* __restric
         const int lo = blockIdx.x * per, hi = min(lo + per, npx);
         if (((((uintptr_t)o) & 15) == 0) && (npx & 3) == 0) {
             const float4 f4 = make_float4(fill, fill, fill, fill);
-            for (int i = lo + tid * 4; i < hi; i += STAR_THREADS * 4) *reinterpret_cast<float4*>(o + i) = f4;
+            for (int i = lo + tid * 4; i < hi; i += STAR_THREADS * 4) __stcs(reinterpret_cast<float4*>(o + i), f4);
         } else {
             for (int i = lo + tid; i < hi; i += STAR_THREADS) o[i] = fill;
         }
@@ -123,9 +206,9 @@ delaunay_star_kernel(const int32_t* __restrict__ knot_xy, const float* __restric
     const int p = blockIdx.x * STAR_WARPS + warp;
     if (p < n) {
         const int px = s_pts[p] & 0xffff, py = s_pts[p] >> 16;
-        int cur = 0;
-        if (lane == 0) s_star[warp][0].k = 0;
-        __syncwarp();
+        WarpStar st;
+        st.ex = st.ey = st.eid = 0; st.k = 0;
+        float lim = -1.f;                                          // 4 R_max^2 of the closed star (< 0: open or not evaluated)
         // candidates outwards from p in knot order: lane l of a batch looks at distance d = base + l/2 + 1 on side l & 1
         const int dmax = max(p, n - 1 - p);
         for (int base = 0; base < dmax; base += 16) {
@@ -134,71 +217,65 @@ delaunay_star_kernel(const int32_t* __restrict__ knot_xy, const float* __restric
             const bool ok = c >= 0 && c < n;
             int ux = 0, uy = 0;
             if (ok) { ux = (s_pts[c] & 0xffff) - px; uy = (s_pts[c] >> 16) - py; }
-            unsigned m = __ballot_sync(0xffffffffu, ok && star::accepts(s_star[warp][cur], p, ux, uy, c));
+            const bool want = st.accepts_each(p, ux, uy, c);
+            unsigned m = __ballot_sync(FULL, ok && want);
             bool changed = false;
             while (m) {
                 const int l = __ffs(m) - 1;
                 m &= m - 1;
-                const int rx = __shfl_sync(0xffffffffu, ux, l), ry = __shfl_sync(0xffffffffu, uy, l), rc_id = __shfl_sync(0xffffffffu, c, l);
-                int rc = 0;
-                if (lane == 0) rc = star::insert(s_star[warp][cur], s_star[warp][cur ^ 1], p, rx, ry, rc_id);
-                rc = __shfl_sync(0xffffffffu, rc, 0);
+                const int rc = st.insert(p, __shfl_sync(FULL, ux, l), __shfl_sync(FULL, uy, l), __shfl_sync(FULL, c, l), lane);
                 if (rc < 0) { if (lane == 0) atomicExch(&counters[CNT_OVERFLOW], 1); }
-                else if (rc > 0) { cur ^= 1; changed = true; }
-                __syncwarp();
+                else if (rc > 0) changed = true;
             }
             // ---- early exit: closed star and both row distances beyond twice the largest circumradius ----------------
-            if (sorted) {
-                const star::Star& s = s_star[warp][cur];
-                const int k = s.k;
-                if (k >= 3) {
-                    double r2max = 0.0;
+            if (sorted && st.k >= 3) {
+                if (changed || lim < 0.f) {
+                    const int ln = lane + 1 == st.k ? 0 : lane + 1;
+                    const int nx = __shfl_sync(FULL, st.ex, ln), ny = __shfl_sync(FULL, st.ey, ln);
+                    float r2 = 0.f;
                     bool open = false;
-                    for (int j = lane; j < k; j += 32) {
-                        const int jn = j + 1 == k ? 0 : j + 1;
-                        const int ax = s.x[j], ay = s.y[j], bx = s.x[jn], by = s.y[jn];
-                        const int cr = star::cross2(ax, ay, bx, by);
-                        if (cr <= 0) { open = true; continue; }
-                        const double a2 = (double)(ax * ax + ay * ay), b2 = (double)(bx * bx + by * by);
-                        const double c2 = (double)((ax - bx) * (ax - bx) + (ay - by) * (ay - by));
-                        r2max = fmax(r2max, a2 * b2 * c2 / (4.0 * (double)cr * (double)cr));       // R^2 of triangle (p, a, b)
+                    if (lane < st.k) {
+                        const int cr = star::cross2(st.ex, st.ey, nx, ny);
+                        if (cr <= 0) open = true;
+                        else {
+                            const float a2 = (float)(st.ex * st.ex + st.ey * st.ey), b2 = (float)(nx * nx + ny * ny);
+                            const float c2 = (float)((st.ex - nx) * (st.ex - nx) + (st.ey - ny) * (st.ey - ny));
+                            r2 = a2 * b2 * (c2 / (4.0f * (float)cr * (float)cr));         // R^2 of fan triangle (p, e, next)
+                        }
                     }
-                    open = __any_sync(0xffffffffu, open);
+                    open = __any_sync(FULL, open);
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) r2max = fmax(r2max, __shfl_xor_sync(0xffffffffu, r2max, o));
-                    if (!open) {
-                        const int nd = base + 17;                                  // next distance to look at
-                        const double lim = 4.0 * r2max * (1.0 + 1e-9);
-                        bool far_up = p + nd >= n, far_dn = p - nd < 0;
-                        if (!far_up) { const double dy = (double)((s_pts[p + nd] >> 16) - py); far_up = dy * dy > lim; }
-                        if (!far_dn) { const double dy = (double)((s_pts[p - nd] >> 16) - py); far_dn = dy * dy > lim; }
-                        if (far_up && far_dn) break;
-                    }
+                    for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(FULL, r2, o));
+                    lim = open ? -1.f : 4.0f * r2 * 1.001f;          // float rounding is far inside the 0.1 % margin
+                }
+                if (lim >= 0.f) {
+                    const int nd = base + 17;                        // next distance to look at
+                    bool far_up = p + nd >= n, far_dn = p - nd < 0;
+                    if (!far_up) { const float dy = (float)((s_pts[p + nd] >> 16) - py); far_up = dy * dy > lim; }
+                    if (!far_dn) { const float dy = (float)((s_pts[p - nd] >> 16) - py); far_dn = dy * dy > lim; }
+                    if (far_up && far_dn) break;
                 }
             }
-            (void)changed;
         }
         // ---- every fan triangle (p, a, b) whose lowest knot index is p --------------------------------------------------
-        const star::Star& s = s_star[warp][cur];
-        const int k = s.k;
-        const float vp = knot_val[(size_t)frame * max_knots + p];
-        for (int j = lane; j < k && k >= 2; j += 32) {
-            const int jn = j + 1 == k ? 0 : j + 1;
-            if (star::cross2(s.x[j], s.y[j], s.x[jn], s.y[jn]) > 0 && p < s.id[j] && p < s.id[jn]) {
-                const int slot = atomicAdd(&counters[CNT_TRIS], 1);
-                if (slot < 2 * max_knots) {
-                    TriRec t;
-                    t.ax = px; t.ay = py; t.bx = px + s.x[j]; t.by = py + s.y[j]; t.cx = px + s.x[jn]; t.cy = py + s.y[jn];
-                    t.va = vp; t.vb = knot_val[(size_t)frame * max_knots + s.id[j]]; t.vc = knot_val[(size_t)frame * max_knots + s.id[jn]];
-                    t.ia = p; t.ib = s.id[j]; t.ic = s.id[jn];
-                    tris[slot] = t;
-                    if (tri_out) {
-                        int32_t* o = tri_out + ((size_t)frame * 2 * max_knots + slot) * 3;
-                        o[0] = p; o[1] = s.id[j]; o[2] = s.id[jn];
-                    }
-                } else {
-                    atomicExch(&counters[CNT_OVERFLOW], 1);
+        const int k = st.k;
+        const int ln = lane + 1 == k ? 0 : lane + 1;
+        const int nx = __shfl_sync(FULL, st.ex, ln), ny = __shfl_sync(FULL, st.ey, ln), nid = __shfl_sync(FULL, st.eid, ln);
+        if (lane < k && k >= 2 && star::cross2(st.ex, st.ey, nx, ny) > 0 && p < st.eid && p < nid) {
+            const int slot = atomicAdd(&counters[CNT_TRIS], 1);
+            if (slot < 2 * max_knots) {
+                const float* val = knot_val + (size_t)frame * max_knots;
+                TriRec t;
+                t.ax = px; t.ay = py; t.bx = px + st.ex; t.by = py + st.ey; t.cx = px + nx; t.cy = py + ny;
+                t.va = val[p]; t.vb = val[st.eid]; t.vc = val[nid];
+                t.ia = p; t.ib = st.eid; t.ic = nid;
+                tris[slot] = t;
+                if (tri_out) {
+                    int32_t* o = tri_out + ((size_t)frame * 2 * max_knots + slot) * 3;
+                    o[0] = p; o[1] = st.eid; o[2] = nid;
                 }
+            } else {
+                atomicExch(&counters[CNT_OVERFLOW], 1);
             }
         }
     }
@@ -251,37 +328,41 @@ raster_kernel(uint8_t* ws_base, WsLayout L, int max_knots, int H, int W, float* 
         const TriRec t = tris[ti];
         const int x0 = max(min(t.ax, min(t.bx, t.cx)), 0), x1 = min(max(t.ax, max(t.bx, t.cx)), W - 1);
         const int y0 = max(min(t.ay, min(t.by, t.cy)), 0), y1 = min(max(t.ay, max(t.by, t.cy)), H - 1);
-        // d(edge function)/dx per edge; for a wide bounding box (hull slivers) each row first gets its conservative x span
-        // from the three half-planes in float, so that the exact integer test below only visits chunks near the triangle
+        // edge functions (the triangle is counter-clockwise), affine in the pixel: w(x, y) = A x + C(y)
+        //   wa = orient(p, b, c), wb = orient(p, c, a), wc = orient(p, a, b);  wa + wb + wc = det = 2 * area
         const int Aa = t.by - t.cy, Ab = t.cy - t.ay, Ac = t.ay - t.by;
+        // the interpolant is affine too: v = va + gx (x - ax) + gy (y - ay), gradients in fp64 (same value as the barycentric sum)
+        const double det = (double)((t.bx - t.ax) * (t.cy - t.ay) - (t.by - t.ay) * (t.cx - t.ax));
+        const double dvb = (double)t.vb - (double)t.va, dvc = (double)t.vc - (double)t.va;
+        const double gx = (dvb * (double)(t.cy - t.ay) - dvc * (double)(t.by - t.ay)) / det;
+        const double gy = ((double)(t.bx - t.ax) * dvc - (double)(t.cx - t.ax) * dvb) / det;
+        // for a wide bounding box (hull slivers) each row first gets its conservative x span from the three half-planes in
+        // float, so that the exact integer test below only visits chunks near the triangle
         const bool wide = (x1 - x0) >= 48;
         for (int y = y0 + warp; y <= y1; y += RASTER_THREADS / 32) {
+            const int Ca = t.bx * (t.cy - y) - t.cx * (t.by - y);
+            const int Cb = t.cx * (t.ay - y) - t.ax * (t.cy - y);
+            const int Cc = t.ax * (t.by - y) - t.bx * (t.ay - y);
             int xs = x0, xe = x1;
             if (wide) {
-                const float Ca = (float)(t.bx * (t.cy - y) - t.cx * (t.by - y));
-                const float Cb = (float)(t.cx * (t.ay - y) - t.ax * (t.cy - y));
-                const float Cc = (float)(t.ax * (t.by - y) - t.bx * (t.ay - y));
                 float lo = (float)x0, hi = (float)x1;
-                if (Aa > 0) lo = fmaxf(lo, -Ca / (float)Aa - 0.02f); else if (Aa < 0) hi = fminf(hi, Ca / (float)(-Aa) + 0.02f); else if (Ca < 0.f) continue;
-                if (Ab > 0) lo = fmaxf(lo, -Cb / (float)Ab - 0.02f); else if (Ab < 0) hi = fminf(hi, Cb / (float)(-Ab) + 0.02f); else if (Cb < 0.f) continue;
-                if (Ac > 0) lo = fmaxf(lo, -Cc / (float)Ac - 0.02f); else if (Ac < 0) hi = fminf(hi, Cc / (float)(-Ac) + 0.02f); else if (Cc < 0.f) continue;
+                if (Aa > 0) lo = fmaxf(lo, -(float)Ca / (float)Aa - 0.02f); else if (Aa < 0) hi = fminf(hi, (float)Ca / (float)(-Aa) + 0.02f); else if (Ca < 0) continue;
+                if (Ab > 0) lo = fmaxf(lo, -(float)Cb / (float)Ab - 0.02f); else if (Ab < 0) hi = fminf(hi, (float)Cb / (float)(-Ab) + 0.02f); else if (Cb < 0) continue;
+                if (Ac > 0) lo = fmaxf(lo, -(float)Cc / (float)Ac - 0.02f); else if (Ac < 0) hi = fminf(hi, (float)Cc / (float)(-Ac) + 0.02f); else if (Cc < 0) continue;
                 xs = max(x0, (int)floorf(lo)); xe = min(x1, (int)ceilf(hi));
             }
+            const double vrow = fma(gy, (double)(y - t.ay), (double)t.va);
+            float* orow = o + (size_t)y * W;
             for (int xb = xs; xb <= xe; xb += 32) {
                 const int x = xb + lane;
-                // edge functions (the triangle is counter-clockwise): wa = orient(p, b, c), wb = orient(p, c, a), wc = orient(p, a, b)
-                const int dxa = t.bx - x, dxb = t.cx - x, dxc = t.ax - x;
-                const int wa = dxa * (t.cy - y) - (t.by - y) * dxb;
-                const int wb = dxb * (t.ay - y) - (t.cy - y) * dxc;
-                const int wc = dxc * (t.by - y) - (t.ay - y) * dxa;
+                const int wa = Aa * x + Ca, wb = Ab * x + Cb, wc = Ac * x + Cc;
                 if (x <= xe && (wa | wb | wc) >= 0) {
                     float v;
                     if (wa == 0) v = edge_value(t.bx, t.by, t.vb, t.cx, t.cy, t.vc, x, y);           // on edge b-c (or at b / c)
                     else if (wb == 0) v = edge_value(t.cx, t.cy, t.vc, t.ax, t.ay, t.va, x, y);
                     else if (wc == 0) v = edge_value(t.ax, t.ay, t.va, t.bx, t.by, t.vb, x, y);
-                    else v = (float)(((double)wa * (double)t.va + (double)wb * (double)t.vb + (double)wc * (double)t.vc) /
-                                     (double)(wa + wb + wc));
-                    o[(size_t)y * W + x] = v;
+                    else v = (float)fma(gx, (double)(x - t.ax), vrow);
+                    orow[x] = v;
                 }
             }
         }
@@ -307,8 +388,11 @@ extern "C" int riders_extract_knots(const float* pred, const float* sparse, cons
     RIDERS_REQUIRE(pred && sparse && valid && knot_xy && knot_scale && knot_shift && knot_count, "extract_knots: null pointer");
     count_launches(1);
     dim3 grid(ceil_div(H * W, OC_SLICE), B);
-    extract_knots_kernel<<<grid, OC_THREADS, 0, (cudaStream_t)stream>>>(pred, sparse, valid, H, W, max_knots,
-                                                                     knot_xy, knot_scale, knot_shift, knot_count);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned* agg = oc_scratch(B, grid.x, st);
+    extract_knots_kernel<<<grid, OC_THREADS, 0, st>>>(pred, sparse, valid, H, W, max_knots,
+                                                      knot_xy, knot_scale, knot_shift, knot_count, agg);
+    if (agg) cudaFreeAsync(agg, st);
     return check_launch("extract_knots");
 }
 

@@ -18,13 +18,13 @@ constexpr int BR_THREADS = 256;
 __global__ void __launch_bounds__(OC_THREADS)
 compact_valid_kernel(const float* __restrict__ pred, const float* __restrict__ target,
                      const uint8_t* __restrict__ valid, int npx, int cap,
-                     float2* __restrict__ pairs, int32_t* __restrict__ count) {
+                     float2* __restrict__ pairs, int32_t* __restrict__ count, unsigned* aggregates) {
     const int frame = blockIdx.y;
     const size_t fo = (size_t)frame * npx;
     float2* dst = pairs + (size_t)frame * cap;
     const int upto = ordered_compact_slice(valid + fo, npx, [&](int pos, int i) {
         if (pos < cap) dst[pos] = make_float2(pred[fo + i], target[fo + i]);
-    });
+    }, aggregates ? aggregates + (size_t)frame * gridDim.x : nullptr);
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) count[frame] = upto;
 }
 
@@ -167,7 +167,9 @@ extern "C" int riders_l1_scale_align(const float* pred, const float* target, con
     float2* pairs = (float2*)workspace;
     int32_t* count = (int32_t*)((uint8_t*)workspace + l1_pairs_bytes(B, max_valid));
     count_launches(out ? 3 : 2);
-    compact_valid_kernel<<<dim3(ceil_div(npx, OC_SLICE), B), OC_THREADS, 0, st>>>(pred, target, mask, npx, max_valid, pairs, count);
+    unsigned* agg = oc_scratch(B, ceil_div(npx, OC_SLICE), st);
+    compact_valid_kernel<<<dim3(ceil_div(npx, OC_SLICE), B), OC_THREADS, 0, st>>>(pred, target, mask, npx, max_valid, pairs, count, agg);
+    if (agg) cudaFreeAsync(agg, st);
     l1_brent_kernel<<<B, BR_THREADS, 0, st>>>(pairs, count, max_valid, lo, hi, xatol, maxiter, scale, fval, nfev);
     if (out) {
         dim3 grid(min(ceil_div(npx, 256 * 4), 1024), B);
