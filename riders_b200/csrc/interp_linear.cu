@@ -208,53 +208,82 @@ delaunay_star_kernel(const int32_t* __restrict__ knot_xy, const float* __restric
         const int px = s_pts[p] & 0xffff, py = s_pts[p] >> 16;
         WarpStar st;
         st.ex = st.ey = st.eid = 0; st.k = 0;
-        float lim = -1.f;                                          // 4 R_max^2 of the closed star (< 0: open or not evaluated)
-        // candidates outwards from p in knot order: lane l of a batch looks at distance d = base + l/2 + 1 on side l & 1
+        // Reach of the star = bounding box (relative to p) of the union of its fan circumcircles, in float with a margin:
+        // a knot outside every circumcircle and outside the exterior wedge cannot enter the star.  Knots are visited
+        // outwards in knot order, rows ascending, so a side (up / down) is finished once its next row is beyond the
+        // reach in y; batches with no knot inside the box are skipped.  An exterior wedge (hull knot) makes the sides it
+        // opens onto unbounded.
+        float bx0 = -3e38f, bx1 = 3e38f, by0 = -3e38f, by1 = 3e38f;
+        bool have_reach = false, open = false;
+        int oax = 0, oay = 0, obx = 0, oby = 0;                    // the exterior wedge [a, b) of a hull knot
+        bool up_done = false, dn_done = false;
         const int dmax = max(p, n - 1 - p);
         for (int base = 0; base < dmax; base += 16) {
+            // candidates: lane l looks at distance d = base + l/2 + 1 on side l & 1 (1 = up, towards lower indices)
             const int d = base + (lane >> 1) + 1;
-            const int c = (lane & 1) ? p - d : p + d;
-            const bool ok = c >= 0 && c < n;
+            const bool up = lane & 1;
+            const int c = up ? p - d : p + d;
+            bool ok = c >= 0 && c < n && !(up ? up_done : dn_done);
             int ux = 0, uy = 0;
             if (ok) { ux = (s_pts[c] & 0xffff) - px; uy = (s_pts[c] >> 16) - py; }
-            const bool want = st.accepts_each(p, ux, uy, c);
-            unsigned m = __ballot_sync(FULL, ok && want);
-            bool changed = false;
-            while (m) {
-                const int l = __ffs(m) - 1;
-                m &= m - 1;
-                const int rc = st.insert(p, __shfl_sync(FULL, ux, l), __shfl_sync(FULL, uy, l), __shfl_sync(FULL, c, l), lane);
-                if (rc < 0) { if (lane == 0) atomicExch(&counters[CNT_OVERFLOW], 1); }
-                else if (rc > 0) changed = true;
+            if (have_reach) {
+                const bool inside_box = (float)ux >= bx0 && (float)ux <= bx1 && (float)uy >= by0 && (float)uy <= by1;
+                ok = ok && (inside_box || (open && star::in_wedge(oax, oay, obx, oby, ux, uy)));
             }
-            // ---- early exit: closed star and both row distances beyond twice the largest circumradius ----------------
-            if (sorted && st.k >= 3) {
-                if (changed || lim < 0.f) {
-                    const int ln = lane + 1 == st.k ? 0 : lane + 1;
-                    const int nx = __shfl_sync(FULL, st.ex, ln), ny = __shfl_sync(FULL, st.ey, ln);
-                    float r2 = 0.f;
-                    bool open = false;
-                    if (lane < st.k) {
-                        const int cr = star::cross2(st.ex, st.ey, nx, ny);
-                        if (cr <= 0) open = true;
-                        else {
-                            const float a2 = (float)(st.ex * st.ex + st.ey * st.ey), b2 = (float)(nx * nx + ny * ny);
-                            const float c2 = (float)((st.ex - nx) * (st.ex - nx) + (st.ey - ny) * (st.ey - ny));
-                            r2 = a2 * b2 * (c2 / (4.0f * (float)cr * (float)cr));         // R^2 of fan triangle (p, e, next)
-                        }
+            bool changed = false;
+            if (__any_sync(FULL, ok)) {
+                const bool want = st.accepts_each(p, ux, uy, c);
+                unsigned m = __ballot_sync(FULL, ok && want);
+                while (m) {
+                    const int l = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int rc = st.insert(p, __shfl_sync(FULL, ux, l), __shfl_sync(FULL, uy, l), __shfl_sync(FULL, c, l), lane);
+                    if (rc < 0) { if (lane == 0) atomicExch(&counters[CNT_OVERFLOW], 1); }
+                    else if (rc > 0) changed = true;
+                }
+            }
+            if (st.k >= 2 && (changed || !have_reach)) {
+                const int ln = lane + 1 == st.k ? 0 : lane + 1;
+                const int nx = __shfl_sync(FULL, st.ex, ln), ny = __shfl_sync(FULL, st.ey, ln);
+                float x0 = 3e38f, x1 = -3e38f, y0 = 3e38f, y1 = -3e38f;
+                bool mine_open = false;
+                if (lane < st.k) {
+                    const int cr = star::cross2(st.ex, st.ey, nx, ny);
+                    if (cr <= 0) mine_open = true;
+                    else {
+                        const float a2 = (float)(st.ex * st.ex + st.ey * st.ey), b2 = (float)(nx * nx + ny * ny);
+                        const float inv = 0.5f / (float)cr;
+                        const float ccx = ((float)ny * a2 - (float)st.ey * b2) * inv, ccy = ((float)st.ex * b2 - (float)nx * a2) * inv;
+                        const float r = sqrtf(ccx * ccx + ccy * ccy) * 1.002f + 2.0f;    // float rounding stays far inside this margin
+                        x0 = ccx - r; x1 = ccx + r; y0 = ccy - r; y1 = ccy + r;
                     }
-                    open = __any_sync(FULL, open);
+                }
+                const unsigned om = __ballot_sync(FULL, mine_open);
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(FULL, r2, o));
-                    lim = open ? -1.f : 4.0f * r2 * 1.001f;          // float rounding is far inside the 0.1 % margin
+                for (int o = 16; o > 0; o >>= 1) {
+                    x0 = fminf(x0, __shfl_xor_sync(FULL, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(FULL, x1, o));
+                    y0 = fminf(y0, __shfl_xor_sync(FULL, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(FULL, y1, o));
                 }
-                if (lim >= 0.f) {
-                    const int nd = base + 17;                        // next distance to look at
-                    bool far_up = p + nd >= n, far_dn = p - nd < 0;
-                    if (!far_up) { const float dy = (float)((s_pts[p + nd] >> 16) - py); far_up = dy * dy > lim; }
-                    if (!far_dn) { const float dy = (float)((s_pts[p - nd] >> 16) - py); far_dn = dy * dy > lim; }
-                    if (far_up && far_dn) break;
+                bx0 = x0; bx1 = x1; by0 = y0; by1 = y1;
+                open = om != 0;
+                have_reach = __popc(om) <= 1;                      // two straight wedges (collinear star): no filter yet
+                if (open) {
+                    const int j = __ffs(om) - 1;
+                    oax = __shfl_sync(FULL, st.ex, j); oay = __shfl_sync(FULL, st.ey, j);
+                    obx = __shfl_sync(FULL, nx, j); oby = __shfl_sync(FULL, ny, j);
                 }
+            }
+            // ---- a side is finished when its next row lies beyond the reach (and the exterior wedge does not open onto it) ----
+            if (sorted && have_reach) {
+                const int nd = base + 17;                            // next distance to look at
+                bool open_dn = false, open_up = false;
+                if (open) {
+                    open_dn = oay > 0 || oby > 0 || star::in_wedge(oax, oay, obx, oby, 0, 1);
+                    open_up = oay < 0 || oby < 0 || star::in_wedge(oax, oay, obx, oby, 0, -1);
+                }
+                if (!dn_done) dn_done = p + nd >= n || (!open_dn && (float)((s_pts[p + nd] >> 16) - py) > by1);
+                if (!up_done) up_done = p - nd < 0 || (!open_up && (float)((s_pts[p - nd] >> 16) - py) < by0);
+                if (up_done && dn_done) break;
             }
         }
         // ---- every fan triangle (p, a, b) whose lowest knot index is p --------------------------------------------------
@@ -317,55 +346,79 @@ __device__ __forceinline__ float edge_value(int x0, int y0, float v0, int x1, in
     return (float)(((double)w0 * (double)v0 + (double)w1 * (double)v1) / (double)(w0 + w1));
 }
 
+// rows [y0 + row_first, y1] of triangle t with a row stride, executed by one warp
+__device__ __forceinline__ void raster_rows(const TriRec& t, int x0, int x1, int y0, int y1, int row_first, int row_step,
+                                            int lane, int W, float* __restrict__ o) {
+    // edge functions (the triangle is counter-clockwise), affine in the pixel: w(x, y) = A x + C(y)
+    //   wa = orient(p, b, c), wb = orient(p, c, a), wc = orient(p, a, b);  wa + wb + wc = det = 2 * area
+    const int Aa = t.by - t.cy, Ab = t.cy - t.ay, Ac = t.ay - t.by;
+    // the interpolant is affine too: v = va + gx (x - ax) + gy (y - ay), gradients in fp64 (same value as the barycentric sum)
+    const double det = (double)((t.bx - t.ax) * (t.cy - t.ay) - (t.by - t.ay) * (t.cx - t.ax));
+    const double dvb = (double)t.vb - (double)t.va, dvc = (double)t.vc - (double)t.va;
+    const double gx = (dvb * (double)(t.cy - t.ay) - dvc * (double)(t.by - t.ay)) / det;
+    const double gy = ((double)(t.bx - t.ax) * dvc - (double)(t.cx - t.ax) * dvb) / det;
+    // for a wide bounding box (hull slivers) each row first gets its conservative x span from the three half-planes in
+    // float, so that the exact integer test below only visits chunks near the triangle
+    const bool wide = (x1 - x0) >= 48;
+    for (int y = y0 + row_first; y <= y1; y += row_step) {
+        const int Ca = t.bx * (t.cy - y) - t.cx * (t.by - y);
+        const int Cb = t.cx * (t.ay - y) - t.ax * (t.cy - y);
+        const int Cc = t.ax * (t.by - y) - t.bx * (t.ay - y);
+        int xs = x0, xe = x1;
+        if (wide) {
+            float lo = (float)x0, hi = (float)x1;
+            if (Aa > 0) lo = fmaxf(lo, -(float)Ca / (float)Aa - 0.02f); else if (Aa < 0) hi = fminf(hi, (float)Ca / (float)(-Aa) + 0.02f); else if (Ca < 0) continue;
+            if (Ab > 0) lo = fmaxf(lo, -(float)Cb / (float)Ab - 0.02f); else if (Ab < 0) hi = fminf(hi, (float)Cb / (float)(-Ab) + 0.02f); else if (Cb < 0) continue;
+            if (Ac > 0) lo = fmaxf(lo, -(float)Cc / (float)Ac - 0.02f); else if (Ac < 0) hi = fminf(hi, (float)Cc / (float)(-Ac) + 0.02f); else if (Cc < 0) continue;
+            xs = max(x0, (int)floorf(lo)); xe = min(x1, (int)ceilf(hi));
+        }
+        const double vrow = fma(gy, (double)(y - t.ay), (double)t.va);
+        float* orow = o + (size_t)y * W;
+        for (int xb = xs; xb <= xe; xb += 32) {
+            const int x = xb + lane;
+            const int wa = Aa * x + Ca, wb = Ab * x + Cb, wc = Ac * x + Cc;
+            if (x <= xe && (wa | wb | wc) >= 0) {
+                float v;
+                if (wa == 0) v = edge_value(t.bx, t.by, t.vb, t.cx, t.cy, t.vc, x, y);           // on edge b-c (or at b / c)
+                else if (wb == 0) v = edge_value(t.cx, t.cy, t.vc, t.ax, t.ay, t.va, x, y);
+                else if (wc == 0) v = edge_value(t.ax, t.ay, t.va, t.bx, t.by, t.vb, x, y);
+                else v = (float)fma(gx, (double)(x - t.ax), vrow);
+                orow[x] = v;
+            }
+        }
+    }
+}
+
+// One triangle per warp; a triangle whose bounding box exceeds RASTER_BIG pixels is deferred and then rasterised by all the
+// warps of the CTA together (rows interleaved), so one hull sliver or a frame with three knots does not serialise on a warp.
+constexpr int RASTER_BIG = 4096;
+
 __global__ void __launch_bounds__(RASTER_THREADS)
 raster_kernel(uint8_t* ws_base, WsLayout L, int max_knots, int H, int W, float* __restrict__ out) {
+    __shared__ int s_big[RASTER_TRIS];
+    __shared__ int s_nbig;
     const int frame = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int* counters = (const int*)(ws_base + L.counters) + (size_t)frame * CNT_STRIDE;
     const TriRec* tris = (const TriRec*)(ws_base + L.tris) + (size_t)frame * 2 * max_knots;
     const int nt = min(counters[CNT_TRIS], 2 * max_knots);
+    if ((int)blockIdx.x * RASTER_TRIS >= nt) return;
     float* o = out + (size_t)frame * H * W;
-    for (int ti = blockIdx.x * RASTER_TRIS; ti < min(nt, (int)(blockIdx.x + 1) * RASTER_TRIS); ++ti) {
+    if (threadIdx.x == 0) s_nbig = 0;
+    __syncthreads();
+    const int ti = blockIdx.x * RASTER_TRIS + warp;
+    if (ti < nt) {
         const TriRec t = tris[ti];
         const int x0 = max(min(t.ax, min(t.bx, t.cx)), 0), x1 = min(max(t.ax, max(t.bx, t.cx)), W - 1);
         const int y0 = max(min(t.ay, min(t.by, t.cy)), 0), y1 = min(max(t.ay, max(t.by, t.cy)), H - 1);
-        // edge functions (the triangle is counter-clockwise), affine in the pixel: w(x, y) = A x + C(y)
-        //   wa = orient(p, b, c), wb = orient(p, c, a), wc = orient(p, a, b);  wa + wb + wc = det = 2 * area
-        const int Aa = t.by - t.cy, Ab = t.cy - t.ay, Ac = t.ay - t.by;
-        // the interpolant is affine too: v = va + gx (x - ax) + gy (y - ay), gradients in fp64 (same value as the barycentric sum)
-        const double det = (double)((t.bx - t.ax) * (t.cy - t.ay) - (t.by - t.ay) * (t.cx - t.ax));
-        const double dvb = (double)t.vb - (double)t.va, dvc = (double)t.vc - (double)t.va;
-        const double gx = (dvb * (double)(t.cy - t.ay) - dvc * (double)(t.by - t.ay)) / det;
-        const double gy = ((double)(t.bx - t.ax) * dvc - (double)(t.cx - t.ax) * dvb) / det;
-        // for a wide bounding box (hull slivers) each row first gets its conservative x span from the three half-planes in
-        // float, so that the exact integer test below only visits chunks near the triangle
-        const bool wide = (x1 - x0) >= 48;
-        for (int y = y0 + warp; y <= y1; y += RASTER_THREADS / 32) {
-            const int Ca = t.bx * (t.cy - y) - t.cx * (t.by - y);
-            const int Cb = t.cx * (t.ay - y) - t.ax * (t.cy - y);
-            const int Cc = t.ax * (t.by - y) - t.bx * (t.ay - y);
-            int xs = x0, xe = x1;
-            if (wide) {
-                float lo = (float)x0, hi = (float)x1;
-                if (Aa > 0) lo = fmaxf(lo, -(float)Ca / (float)Aa - 0.02f); else if (Aa < 0) hi = fminf(hi, (float)Ca / (float)(-Aa) + 0.02f); else if (Ca < 0) continue;
-                if (Ab > 0) lo = fmaxf(lo, -(float)Cb / (float)Ab - 0.02f); else if (Ab < 0) hi = fminf(hi, (float)Cb / (float)(-Ab) + 0.02f); else if (Cb < 0) continue;
-                if (Ac > 0) lo = fmaxf(lo, -(float)Cc / (float)Ac - 0.02f); else if (Ac < 0) hi = fminf(hi, (float)Cc / (float)(-Ac) + 0.02f); else if (Cc < 0) continue;
-                xs = max(x0, (int)floorf(lo)); xe = min(x1, (int)ceilf(hi));
-            }
-            const double vrow = fma(gy, (double)(y - t.ay), (double)t.va);
-            float* orow = o + (size_t)y * W;
-            for (int xb = xs; xb <= xe; xb += 32) {
-                const int x = xb + lane;
-                const int wa = Aa * x + Ca, wb = Ab * x + Cb, wc = Ac * x + Cc;
-                if (x <= xe && (wa | wb | wc) >= 0) {
-                    float v;
-                    if (wa == 0) v = edge_value(t.bx, t.by, t.vb, t.cx, t.cy, t.vc, x, y);           // on edge b-c (or at b / c)
-                    else if (wb == 0) v = edge_value(t.cx, t.cy, t.vc, t.ax, t.ay, t.va, x, y);
-                    else if (wc == 0) v = edge_value(t.ax, t.ay, t.va, t.bx, t.by, t.vb, x, y);
-                    else v = (float)fma(gx, (double)(x - t.ax), vrow);
-                    orow[x] = v;
-                }
-            }
-        }
+        if ((x1 - x0 + 1) * (y1 - y0 + 1) > RASTER_BIG) { if (lane == 0) s_big[atomicAdd(&s_nbig, 1)] = ti; }
+        else raster_rows(t, x0, x1, y0, y1, 0, 1, lane, W, o);
+    }
+    __syncthreads();
+    for (int b = 0; b < s_nbig; ++b) {
+        const TriRec t = tris[s_big[b]];
+        const int x0 = max(min(t.ax, min(t.bx, t.cx)), 0), x1 = min(max(t.ax, max(t.bx, t.cx)), W - 1);
+        const int y0 = max(min(t.ay, min(t.by, t.cy)), 0), y1 = min(max(t.ay, max(t.by, t.cy)), H - 1);
+        raster_rows(t, x0, x1, y0, y1, warp, RASTER_THREADS / 32, lane, W, o);
     }
 }
 

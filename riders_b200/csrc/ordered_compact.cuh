@@ -105,6 +105,19 @@ __device__ __forceinline__ int ordered_compact_slice(const uint8_t* __restrict__
 // Stream-ordered zeroed look-back scratch for one launch (frames x slices words); nullptr if the allocation is refused
 // (the kernels then take the scratch-free form).  Free with cudaFreeAsync on the same stream after the launch.
 inline unsigned* oc_scratch(int frames, int slices, cudaStream_t st) {
+    // keep freed blocks cached in the device's default pool (its default threshold of 0 returns them to the driver at every
+    // synchronisation, which made each cudaMallocAsync a 0.2 ms re-allocation)
+    static bool pool_set[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !pool_set[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = 64ull << 20;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+        pool_set[dev] = true;
+    }
     void* p = nullptr;
     const size_t bytes = (size_t)frames * slices * sizeof(unsigned);
     if (cudaMallocAsync(&p, bytes, st) != cudaSuccess) { cudaGetLastError(); return nullptr; }
