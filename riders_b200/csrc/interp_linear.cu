@@ -11,8 +11,8 @@
 //                          can lie inside any of its circumcircles).  Every triangle is emitted once, by its lowest-index
 //                          knot.  The same launch writes the fill value over the output maps (the rasteriser overwrites the
 //                          covered pixels), and the last CTA of a frame publishes status / triangle count.
-//   raster_kernel        : scatter form of the barycentric fill: 8 triangles per CTA, the CTA's warps share the bounding-box
-//                          rows of each; a pixel is written iff its three exact integer edge functions are >= 0 (a pixel on
+//   raster_kernel        : scatter form of the barycentric fill: 8 triangles per CTA, their bounding-box rows dealt
+//                          round-robin to the CTA's warps; a pixel is written iff its three exact integer edge functions are >= 0 (a pixel on
 //                          the hull boundary is inside, like SciPy's eps test).  Pixels on an edge or a knot are evaluated
 //                          from the edge's two knots in canonical order, so the two triangles sharing the edge write
 //                          identical bits (benign race, deterministic image); that path is exact at the knots.  Interior
@@ -232,14 +232,25 @@ delaunay_star_kernel(const int32_t* __restrict__ knot_xy, const float* __restric
             }
             bool changed = false;
             if (__any_sync(FULL, ok)) {
-                const bool want = st.accepts_each(p, ux, uy, c);
-                unsigned m = __ballot_sync(FULL, ok && want);
+                // Candidates of a batch are near p in knot order, not in space: inserting them in arrival order makes most of
+                // them transient neighbours (measured: 37 insertions per knot, 32 of them in the first batch).  Instead the
+                // nearest accepted candidate goes first and the others are re-tested against the star it changed.
+                unsigned m = __ballot_sync(FULL, ok && st.accepts_each(p, ux, uy, c));
+                const int d2 = ux * ux + uy * uy;
                 while (m) {
-                    const int l = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int rc = st.insert(p, __shfl_sync(FULL, ux, l), __shfl_sync(FULL, uy, l), __shfl_sync(FULL, c, l), lane);
+                    int best = (m >> lane) & 1 ? d2 : 0x7fffffff, who = lane;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const int ob = __shfl_xor_sync(FULL, best, o), ow = __shfl_xor_sync(FULL, who, o);
+                        if (ob < best || (ob == best && ow < who)) { best = ob; who = ow; }
+                    }
+                    m &= ~(1u << who);
+                    const int rc = st.insert(p, __shfl_sync(FULL, ux, who), __shfl_sync(FULL, uy, who), __shfl_sync(FULL, c, who), lane);
                     if (rc < 0) { if (lane == 0) atomicExch(&counters[CNT_OVERFLOW], 1); }
-                    else if (rc > 0) changed = true;
+                    else if (rc > 0) {
+                        changed = true;
+                        if (m) m &= __ballot_sync(FULL, st.accepts_each(p, ux, uy, c));
+                    }
                 }
             }
             if (st.k >= 2 && (changed || !have_reach)) {
@@ -346,33 +357,77 @@ __device__ __forceinline__ float edge_value(int x0, int y0, float v0, int x1, in
     return (float)(((double)w0 * (double)v0 + (double)w1 * (double)v1) / (double)(w0 + w1));
 }
 
-// rows [y0 + row_first, y1] of triangle t with a row stride, executed by one warp
-__device__ __forceinline__ void raster_rows(const TriRec& t, int x0, int x1, int y0, int y1, int row_first, int row_step,
-                                            int lane, int W, float* __restrict__ o) {
-    // edge functions (the triangle is counter-clockwise), affine in the pixel: w(x, y) = A x + C(y)
-    //   wa = orient(p, b, c), wb = orient(p, c, a), wc = orient(p, a, b);  wa + wb + wc = det = 2 * area
-    const int Aa = t.by - t.cy, Ab = t.cy - t.ay, Ac = t.ay - t.by;
-    // the interpolant is affine too: v = va + gx (x - ax) + gy (y - ay), gradients in fp64 (same value as the barycentric sum)
-    const double det = (double)((t.bx - t.ax) * (t.cy - t.ay) - (t.by - t.ay) * (t.cx - t.ax));
-    const double dvb = (double)t.vb - (double)t.va, dvc = (double)t.vc - (double)t.va;
-    const double gx = (dvb * (double)(t.cy - t.ay) - dvc * (double)(t.by - t.ay)) / det;
-    const double gy = ((double)(t.bx - t.ax) * dvc - (double)(t.cx - t.ax) * dvb) / det;
-    // for a wide bounding box (hull slivers) each row first gets its conservative x span from the three half-planes in
-    // float, so that the exact integer test below only visits chunks near the triangle
-    const bool wide = (x1 - x0) >= 48;
-    for (int y = y0 + row_first; y <= y1; y += row_step) {
+// per-triangle constants of the rasteriser, set up once by one warp and then shared by the CTA
+struct TriSetup {
+    int Aa, Ab, Ac;                 // d(edge function)/dx: wa = orient(p, b, c), wb = orient(p, c, a), wc = orient(p, a, b)
+    int ax, ay, bx, by, cx, cy;
+    int x0, x1, y0, rows;           // clipped bounding box
+    float va, vb, vc;
+    double gx, gy;                  // the affine interpolant v = va + gx (x - ax) + gy (y - ay) (= the barycentric sum)
+};
+
+// The CTA's RASTER_TRIS triangles are flattened into one list of bounding-box ROWS, dealt round-robin to the warps: the
+// work of a CTA is balanced whatever the triangle sizes (a hull sliver, or a frame with three knots, no longer serialises
+// on one warp).  A pixel is written iff its three exact integer edge functions are >= 0.
+__global__ void __launch_bounds__(RASTER_THREADS)
+raster_kernel(uint8_t* ws_base, WsLayout L, int max_knots, int H, int W, float* __restrict__ out) {
+    __shared__ TriSetup s_tri[RASTER_TRIS];
+    __shared__ int s_row0[RASTER_TRIS + 1];
+    const int frame = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int* counters = (const int*)(ws_base + L.counters) + (size_t)frame * CNT_STRIDE;
+    const TriRec* tris = (const TriRec*)(ws_base + L.tris) + (size_t)frame * 2 * max_knots;
+    const int nt = min(counters[CNT_TRIS], 2 * max_knots);
+    if ((int)blockIdx.x * RASTER_TRIS >= nt) return;
+    float* o = out + (size_t)frame * H * W;
+    const int ti = blockIdx.x * RASTER_TRIS + warp;
+    if (lane == 0) {
+        TriSetup u;
+        u.rows = 0;
+        if (ti < nt) {
+            const TriRec t = tris[ti];
+            u.ax = t.ax; u.ay = t.ay; u.bx = t.bx; u.by = t.by; u.cx = t.cx; u.cy = t.cy;
+            u.va = t.va; u.vb = t.vb; u.vc = t.vc;
+            u.Aa = t.by - t.cy; u.Ab = t.cy - t.ay; u.Ac = t.ay - t.by;
+            u.x0 = max(min(t.ax, min(t.bx, t.cx)), 0); u.x1 = min(max(t.ax, max(t.bx, t.cx)), W - 1);
+            u.y0 = max(min(t.ay, min(t.by, t.cy)), 0);
+            u.rows = min(max(t.ay, max(t.by, t.cy)), H - 1) - u.y0 + 1;
+            const double det = (double)((t.bx - t.ax) * (t.cy - t.ay) - (t.by - t.ay) * (t.cx - t.ax));
+            const double dvb = (double)t.vb - (double)t.va, dvc = (double)t.vc - (double)t.va;
+            u.gx = (dvb * (double)(t.cy - t.ay) - dvc * (double)(t.by - t.ay)) / det;
+            u.gy = ((double)(t.bx - t.ax) * dvc - (double)(t.cx - t.ax) * dvb) / det;
+        }
+        s_tri[warp] = u;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int i = 0; i < RASTER_TRIS; ++i) { s_row0[i] = acc; acc += s_tri[i].rows; }
+        s_row0[RASTER_TRIS] = acc;
+    }
+    __syncthreads();
+    const int total_rows = s_row0[RASTER_TRIS];
+    int cur = 0;
+    for (int r = warp; r < total_rows; r += RASTER_THREADS / 32) {
+        while (r >= s_row0[cur + 1]) ++cur;
+        const TriSetup& t = s_tri[cur];
+        const int y = t.y0 + (r - s_row0[cur]);
+        const int Aa = t.Aa, Ab = t.Ab, Ac = t.Ac;
         const int Ca = t.bx * (t.cy - y) - t.cx * (t.by - y);
         const int Cb = t.cx * (t.ay - y) - t.ax * (t.cy - y);
         const int Cc = t.ax * (t.by - y) - t.bx * (t.ay - y);
-        int xs = x0, xe = x1;
-        if (wide) {
-            float lo = (float)x0, hi = (float)x1;
+        int xs = t.x0, xe = t.x1;
+        if (xe - xs >= 48) {
+            // wide bounding box (hull slivers): the row's conservative x span from the three half-planes, in float; the exact
+            // integer test below then only visits the chunks near the triangle
+            float lo = (float)xs, hi = (float)xe;
             if (Aa > 0) lo = fmaxf(lo, -(float)Ca / (float)Aa - 0.02f); else if (Aa < 0) hi = fminf(hi, (float)Ca / (float)(-Aa) + 0.02f); else if (Ca < 0) continue;
             if (Ab > 0) lo = fmaxf(lo, -(float)Cb / (float)Ab - 0.02f); else if (Ab < 0) hi = fminf(hi, (float)Cb / (float)(-Ab) + 0.02f); else if (Cb < 0) continue;
             if (Ac > 0) lo = fmaxf(lo, -(float)Cc / (float)Ac - 0.02f); else if (Ac < 0) hi = fminf(hi, (float)Cc / (float)(-Ac) + 0.02f); else if (Cc < 0) continue;
-            xs = max(x0, (int)floorf(lo)); xe = min(x1, (int)ceilf(hi));
+            xs = max(xs, (int)floorf(lo)); xe = min(xe, (int)ceilf(hi));
         }
-        const double vrow = fma(gy, (double)(y - t.ay), (double)t.va);
+        const double vrow = fma(t.gy, (double)(y - t.ay), (double)t.va);
+        const double gx = t.gx;
+        const int ax = t.ax;
         float* orow = o + (size_t)y * W;
         for (int xb = xs; xb <= xe; xb += 32) {
             const int x = xb + lane;
@@ -382,43 +437,10 @@ __device__ __forceinline__ void raster_rows(const TriRec& t, int x0, int x1, int
                 if (wa == 0) v = edge_value(t.bx, t.by, t.vb, t.cx, t.cy, t.vc, x, y);           // on edge b-c (or at b / c)
                 else if (wb == 0) v = edge_value(t.cx, t.cy, t.vc, t.ax, t.ay, t.va, x, y);
                 else if (wc == 0) v = edge_value(t.ax, t.ay, t.va, t.bx, t.by, t.vb, x, y);
-                else v = (float)fma(gx, (double)(x - t.ax), vrow);
+                else v = (float)fma(gx, (double)(x - ax), vrow);
                 orow[x] = v;
             }
         }
-    }
-}
-
-// One triangle per warp; a triangle whose bounding box exceeds RASTER_BIG pixels is deferred and then rasterised by all the
-// warps of the CTA together (rows interleaved), so one hull sliver or a frame with three knots does not serialise on a warp.
-constexpr int RASTER_BIG = 4096;
-
-__global__ void __launch_bounds__(RASTER_THREADS)
-raster_kernel(uint8_t* ws_base, WsLayout L, int max_knots, int H, int W, float* __restrict__ out) {
-    __shared__ int s_big[RASTER_TRIS];
-    __shared__ int s_nbig;
-    const int frame = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int* counters = (const int*)(ws_base + L.counters) + (size_t)frame * CNT_STRIDE;
-    const TriRec* tris = (const TriRec*)(ws_base + L.tris) + (size_t)frame * 2 * max_knots;
-    const int nt = min(counters[CNT_TRIS], 2 * max_knots);
-    if ((int)blockIdx.x * RASTER_TRIS >= nt) return;
-    float* o = out + (size_t)frame * H * W;
-    if (threadIdx.x == 0) s_nbig = 0;
-    __syncthreads();
-    const int ti = blockIdx.x * RASTER_TRIS + warp;
-    if (ti < nt) {
-        const TriRec t = tris[ti];
-        const int x0 = max(min(t.ax, min(t.bx, t.cx)), 0), x1 = min(max(t.ax, max(t.bx, t.cx)), W - 1);
-        const int y0 = max(min(t.ay, min(t.by, t.cy)), 0), y1 = min(max(t.ay, max(t.by, t.cy)), H - 1);
-        if ((x1 - x0 + 1) * (y1 - y0 + 1) > RASTER_BIG) { if (lane == 0) s_big[atomicAdd(&s_nbig, 1)] = ti; }
-        else raster_rows(t, x0, x1, y0, y1, 0, 1, lane, W, o);
-    }
-    __syncthreads();
-    for (int b = 0; b < s_nbig; ++b) {
-        const TriRec t = tris[s_big[b]];
-        const int x0 = max(min(t.ax, min(t.bx, t.cx)), 0), x1 = min(max(t.ax, max(t.bx, t.cx)), W - 1);
-        const int y0 = max(min(t.ay, min(t.by, t.cy)), 0), y1 = min(max(t.ay, max(t.by, t.cy)), H - 1);
-        raster_rows(t, x0, x1, y0, y1, warp, RASTER_THREADS / 32, lane, W, o);
     }
 }
 
