@@ -235,7 +235,8 @@ delaunay_star_kernel(const int32_t* __restrict__ knot_xy, const float* __restric
                 // Candidates of a batch are near p in knot order, not in space: inserting them in arrival order makes most of
                 // them transient neighbours (measured: 37 insertions per knot, 32 of them in the first batch).  Instead the
                 // nearest accepted candidate goes first and the others are re-tested against the star it changed.
-                unsigned m = __ballot_sync(FULL, ok && st.accepts_each(p, ux, uy, c));
+                const bool want = st.accepts_each(p, ux, uy, c);          // every lane must call it: it shuffles (no `ok && ...` short-circuit)
+                unsigned m = __ballot_sync(FULL, ok && want);
                 const int d2 = ux * ux + uy * uy;
                 while (m) {
                     int best = (m >> lane) & 1 ? d2 : 0x7fffffff, who = lane;

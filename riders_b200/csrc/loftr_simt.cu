@@ -138,6 +138,8 @@ layer_norm_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
 
 struct SimtScratch { float *q, *k, *v, *msg, *m, *h, *ping0, *ping1; };
 
+constexpr int STATUS_FLOATS = 64;             // workspace status block (256 B): word 0 = fp16-range overflow flag of the tcgen05 path
+
 static size_t simt_scratch_floats(int N, int tokens, int C) {
     const size_t rows = (size_t)N * tokens;
     return rows * C * 7 + rows * 2 * C;     // q,k,v,msg,m,ping0,ping1 + h
@@ -174,8 +176,9 @@ static int loftr_layer_simt(const float* x, const float* src, const riders_loftr
 bool loftr_tc_built();
 size_t loftr_tc_workspace_bytes(int N, int tokens, int C);
 int loftr_tc_pack(const riders_loftr_weights& w, int layer_slot, void* tc_ws, cudaStream_t st);
-int loftr_tc_run(const float* x, const float* src, const riders_loftr_weights& w, int layer_slot,
-                 int N, float attn_eps, float ln_eps, float* out, void* tc_ws, cudaStream_t st);
+int loftr_tc_run_calls(int n_calls, const float* const* x, const float* const* src, float* const* out,
+                       const riders_loftr_weights* const* w, const int* slot,
+                       int N, float attn_eps, float ln_eps, void* tc_ws, int* overflow, cudaStream_t st);
 
 static int validate(const riders_loftr_weights* w, int N, int L, int S, int C, int nhead, int impl) {
     RIDERS_REQUIRE(N >= 0 && L > 0 && S > 0 && C > 0 && nhead > 0, "loftr: bad shape");
@@ -201,7 +204,7 @@ extern "C" size_t riders_loftr_workspace_bytes(int N, int tokens, int d_model, i
     if (N <= 0 || tokens <= 0 || d_model <= 0) return 256;
     size_t b = riders::simt_scratch_floats(N, tokens, d_model) * sizeof(float);
     if (impl == RIDERS_LOFTR_TCGEN05) b = riders::loftr_tc_workspace_bytes(N, tokens, d_model);
-    return b + 256;
+    return b + 256 + riders::STATUS_FLOATS * sizeof(float);
 }
 
 extern "C" int riders_loftr_layer_fwd(const float* x, const float* src, const riders_loftr_weights* w,
@@ -215,12 +218,15 @@ extern "C" int riders_loftr_layer_fwd(const float* x, const float* src, const ri
     RIDERS_REQUIRE(x && src && out && workspace, "loftr_layer: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     if (impl == RIDERS_LOFTR_TCGEN05) {
-        const size_t a = (size_t)N * (L > S ? L : S) * d_model;
-        void* tc_ws = (float*)workspace + 4 * a;
+        RIDERS_REQUIRE(out != x && out != src, "loftr_layer: out must not alias an input");
+        int* overflow = (int*)workspace;                      // status block: word 0 = fp16-range overflow flag
+        void* tc_ws = (float*)workspace + STATUS_FLOATS;
+        if (cudaMemsetAsync(overflow, 0, sizeof(int), st) != cudaSuccess) return check_launch("loftr_layer: status reset");
         if ((rc = loftr_tc_pack(*w, 0, tc_ws, st)) != RIDERS_OK) return rc;
-        return loftr_tc_run(x, src, *w, 0, N, attn_eps, ln_eps, out, tc_ws, st);
+        const int slot = 0;
+        return loftr_tc_run_calls(1, &x, &src, &out, &w, &slot, N, attn_eps, ln_eps, tc_ws, overflow, st);
     }
-    const SimtScratch s = carve((float*)workspace, N, L > S ? L : S, d_model);
+    const SimtScratch s = carve((float*)workspace + STATUS_FLOATS, N, L > S ? L : S, d_model);
     return loftr_layer_simt(x, src, *w, N, L, S, d_model, nhead, attn_eps, ln_eps, out, s, st);
 }
 
@@ -240,23 +246,38 @@ extern "C" int riders_loftr_transformer_fwd(const float* feat0, const float* fea
     RIDERS_REQUIRE(feat0 && feat1 && out0 && out1 && workspace, "loftr_transformer: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const int tokens = L > S ? L : S;
-    float* ws = (float*)workspace;
-    const SimtScratch s = carve(ws, N, tokens, d_model);
-    // Two ping-pong buffer pairs.  The layer at even distance from the end writes pair B, odd
-    // distance pair A, so the last layer can always write out0/out1 without reading them.
-    void* tc_ws = nullptr;
-    float *pa0, *pa1, *pb0, *pb1;
     if (impl == RIDERS_LOFTR_TCGEN05) {
-        const size_t a = (size_t)N * tokens * d_model;
-        pa0 = ws; pa1 = ws + a; pb0 = ws + 2 * a; pb1 = ws + 3 * a;
-        tc_ws = ws + 4 * a;
-        for (int i = 0; i < n_layers; ++i) {                 // split + swizzle every layer's weights once per call
+        // the whole transformer in ONE launch: every layer's weights split + swizzled once, then the list of 2 n_layers
+        // layer calls; a tile's tokens stay with its CTA through all of them (in place in out0 / out1 after their first use)
+        RIDERS_REQUIRE(2 * n_layers <= 16, "loftr_transformer(tcgen05): at most 8 layers (16 layer calls) per call");
+        RIDERS_REQUIRE(out0 != feat0 && out0 != feat1 && out1 != feat0 && out1 != feat1 && out0 != out1,
+                       "loftr_transformer: outputs must not alias the inputs");
+        int* overflow = (int*)workspace;
+        void* tc_ws = (float*)workspace + STATUS_FLOATS;
+        if (cudaMemsetAsync(overflow, 0, sizeof(int), st) != cudaSuccess) return check_launch("loftr_transformer: status reset");
+        const float* xs[16]; const float* ss[16]; float* os[16]; const riders_loftr_weights* ws_[16]; int slots[16];
+        const float* c0 = feat0;
+        const float* c1 = feat1;
+        int nc = 0;
+        for (int i = 0; i < n_layers; ++i) {
             int rc = loftr_tc_pack(layers[i], i, tc_ws, st);
             if (rc != RIDERS_OK) return rc;
+            if (layer_kind[i] == 0) {                   // 'self'  (linear_attention.py:175-177)
+                xs[nc] = c0; ss[nc] = c0; os[nc] = out0; ws_[nc] = &layers[i]; slots[nc++] = i;
+                xs[nc] = c1; ss[nc] = c1; os[nc] = out1; ws_[nc] = &layers[i]; slots[nc++] = i;
+            } else {                                    // 'cross' (linear_attention.py:178-180): the second call sees the new feat0
+                xs[nc] = c0; ss[nc] = c1; os[nc] = out0; ws_[nc] = &layers[i]; slots[nc++] = i;
+                xs[nc] = c1; ss[nc] = out0; os[nc] = out1; ws_[nc] = &layers[i]; slots[nc++] = i;
+            }
+            c0 = out0; c1 = out1;
         }
-    } else {
-        pa0 = s.ping0; pa1 = s.ping1; pb0 = out0; pb1 = out1;     // out buffers double as pair B
+        return loftr_tc_run_calls(nc, xs, ss, os, ws_, slots, N, attn_eps, ln_eps, tc_ws, overflow, st);
     }
+    float* ws = (float*)workspace + STATUS_FLOATS;
+    const SimtScratch s = carve(ws, N, tokens, d_model);
+    // SIMT path: two ping-pong buffer pairs.  The layer at even distance from the end writes pair B, odd
+    // distance pair A, so the last layer can always write out0/out1 without reading them.
+    float *pa0 = s.ping0, *pa1 = s.ping1, *pb0 = out0, *pb1 = out1;     // out buffers double as pair B
     const float* c0 = feat0;
     const float* c1 = feat1;
     for (int i = 0; i < n_layers; ++i) {
@@ -264,8 +285,6 @@ extern "C" int riders_loftr_transformer_fwd(const float* feat0, const float* fea
         float* n0 = (to_end == 0) ? out0 : ((to_end & 1) ? pa0 : pb0);
         float* n1 = (to_end == 0) ? out1 : ((to_end & 1) ? pa1 : pb1);
         auto run = [&](const float* xx, const float* ss, int Lx, int Ss, float* oo) -> int {
-            if (impl == RIDERS_LOFTR_TCGEN05)
-                return loftr_tc_run(xx, ss, layers[i], i, N, attn_eps, ln_eps, oo, tc_ws, st);
             return loftr_layer_simt(xx, ss, layers[i], N, Lx, Ss, d_model, nhead, attn_eps, ln_eps, oo, s, st);
         };
         int rc;

@@ -15,6 +15,17 @@
 // subnormal range) and every accumulator read-back multiplies by 2^-8.  Activations must stay
 // inside the fp16 range (|a| < 65504), the same constraint the reference's V/S scaling exists for.
 //
+// One launch runs the WHOLE transformer (RCNet/linear_attention.py:159-184): tokens of a radar point never interact with other
+// points, so a tile of 6 points walks through all 16 layer calls back to back inside one persistent CTA (tile-major order); its
+// tokens ping through the L2-resident output buffers, the 16 per-layer launches, their wave tails and 15/16 of the HBM token
+// traffic are gone.
+//
+// The linear attention itself (KV = K'^T V, normaliser, Q' KV: 2.5 % of the FLOPs but 40 % of the round-1 tile time on CUDA
+// cores) runs on the tensor cores too: q / k / v leave TMEM as fp16 hi/lo pairs, and each (point, head) pair is a handful of
+// warp-level mma.sync.m16n8k16 with the same 3-term split (KV^T = V^T K' accumulates in registers and IS the B fragment of
+// the Q' KV product; the normaliser rides along as an all-ones A row).  tcgen05 cannot take these: M = 21 tokens / 16 x 16
+// blocks per (point, head) against its M = 128 tile.
+//
 // Roles (576 threads): warp 0 streams the pre-split, pre-swizzled weight chunks (32 KB: hi|lo of
 // a 128 x 64 block) from L2 with cp.async.bulk through a 3-stage mbarrier ring; one elected lane of
 // warp 1 issues the MMAs (N = 128: an SS-mode MMA costs ~43 + N/2 cycles on this part, tools/mma_rate.py,
@@ -142,6 +153,10 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: 
 __device__ __forceinline__ uint32_t sw128(int row, int seg) {
     return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((seg ^ (row & 7)) << 4));
 }
+// fp16-range guard: the hi/lo split needs |a| <= 65504 (the fp32 reference has no such limit).  Every operand value passes
+// through split2, which records a violation (or a NaN) in `g_bad`; the kernel raises the caller's overflow flag and the host
+// re-runs the call on the fp32 SIMT kernels (rcnet/linear_attention.py).  One FSETP per value, folded into the compare chain.
+#define RANGE_CHECK(a, b) bad = bad || !(fabsf(a) <= 65504.0f) || !(fabsf(b) <= 65504.0f)
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
     const __half2 h = __floats2half2_rn(a, b);
     const float2 f = __half22float2(h);
@@ -150,8 +165,9 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 // split 8 consecutive K elements (col % 8 == 0) of row `row` into the hi / lo slabs of the operand at `base`
-__device__ __forceinline__ void split_store8(uint8_t* base, int row, int col, float4 a, float4 b) {
+__device__ __forceinline__ void split_store8(uint8_t* base, int row, int col, float4 a, float4 b, bool& bad) {
     const uint32_t off = (uint32_t)(col >> 6) * SLAB + sw128(row, (col & 63) >> 3);
+    RANGE_CHECK(a.x, a.y); RANGE_CHECK(a.z, a.w); RANGE_CHECK(b.x, b.y); RANGE_CHECK(b.z, b.w);
     uint4 hi, lo;
     split2(a.x, a.y, hi.x, lo.x); split2(a.z, a.w, hi.y, lo.y);
     split2(b.x, b.y, hi.z, lo.z); split2(b.z, b.w, hi.w, lo.w);
@@ -159,17 +175,8 @@ __device__ __forceinline__ void split_store8(uint8_t* base, int row, int col, fl
     *reinterpret_cast<uint4*>(base + 2 * SLAB + off) = lo;
 }
 
-// the same for 4 consecutive K elements (col % 4 == 0): 8-byte stores
-__device__ __forceinline__ void split_store4(uint8_t* base, int row, int col, float4 a) {
-    const uint32_t off = (uint32_t)(col >> 6) * SLAB + sw128(row, (col & 63) >> 3) + (uint32_t)((col & 7) >> 2) * 8u;
-    uint2 hi, lo;
-    split2(a.x, a.y, hi.x, lo.x); split2(a.z, a.w, hi.y, lo.y);
-    *reinterpret_cast<uint2*>(base + off) = hi;
-    *reinterpret_cast<uint2*>(base + 2 * SLAB + off) = lo;
-}
-
 // coalesced: epilogue warp `ew` (0..15) loads rows ew*8.. of a (rows x 128) fp32 tile and splits them into the operand
-__device__ __forceinline__ void load_tile_to_oper(uint8_t* base, const float* __restrict__ g, int valid_rows, int ew, int lane) {
+__device__ __forceinline__ void load_tile_to_oper(uint8_t* base, const float* g, int valid_rows, int ew, int lane, bool& bad) {
     float4 v[8];
     const int c8 = (lane & 15) * 8;
 #pragma unroll
@@ -177,14 +184,32 @@ __device__ __forceinline__ void load_tile_to_oper(uint8_t* base, const float* __
         const int row = ew * 8 + i * 2 + (lane >> 4);
         if (row < valid_rows) {
             const float4* src = reinterpret_cast<const float4*>(g + (size_t)row * CH + c8);
-            v[2 * i] = __ldg(src); v[2 * i + 1] = __ldg(src + 1);
+            v[2 * i] = __ldcg(src); v[2 * i + 1] = __ldcg(src + 1);     // L2: the tile itself may have written these rows in an earlier layer call
         } else {
             v[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f); v[2 * i + 1] = v[2 * i];
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) split_store8(base, ew * 8 + i * 2 + (lane >> 4), c8, v[2 * i], v[2 * i + 1]);
+    for (int i = 0; i < 4; ++i) split_store8(base, ew * 8 + i * 2 + (lane >> 4), c8, v[2 * i], v[2 * i + 1], bad);
 }
+
+// ------------------------------------------------------------------------------------ warp-level MMA (attention blocks)
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// D (16 x 8, fp32) += A (16 x 16, fp16, row) * B (16 x 8, fp16, col)
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// attention staging in the idle A operand: six arrays (Q' hi, Q' lo, K' hi, K' lo, V hi, V lo) of 128 token rows x 32 fp16 (one
+// quarter = 2 heads), rows 80 bytes apart so that the 8 rows of an ldmatrix tile (and the 8 lanes of a 16-byte store phase) fall
+// into distinct 16-byte bank groups
+constexpr int SROW = 80, SARR = 128 * SROW;
+static_assert(6 * SARR <= OPER_BYTES, "attention staging must fit the A operand");
 
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x + 1.0f : __expf(x); }   // elu(x) + 1 (SFU exp2, ~2 ulp)
 __device__ __forceinline__ float acc_f(uint32_t r) { return __uint_as_float(r) * W_UNSCALE; }  // accumulator read-back
@@ -213,21 +238,27 @@ __device__ __forceinline__ void publish(uint32_t bar) {
     mbar_arrive(bar);
 }
 
-struct LayerArgs {
-    const float* x; const float* src; float* out;
+constexpr int MAX_CALLS = 16;                   // layer calls per launch (RC-Net: 8 layers x 2 calls)
+struct CallArgs {
+    const float* x; const float* src; float* out;   // out may alias x (in place): every element is read and written by one thread
     const uint8_t* wpack;                       // NCHUNK x 16 KB, pre-split + pre-swizzled
     const float* ln1_g; const float* ln1_b; const float* ln2_g; const float* ln2_b;
+    int is_self;                                // src == x
+};
+struct LayerArgs {
+    CallArgs call[MAX_CALLS];
+    int n_calls;
     int N;                                      // radar points
     int n_tiles;
-    int is_self;                                // src == x
     float attn_eps, ln_eps;
     long long* trace;                           // optional phase timestamps (riders_debug_loftr_trace), else null
+    int* overflow;                              // set to 1 when an operand left the fp16 range (see RANGE_CHECK)
 };
 
 // trace layout per traced CTA (blockIdx.x == 0 or gridDim.x / 2): 128 slots; [0..63] epilogue thread, [64..127] MMA thread
-#define TRACE_E(k) do { if (P.trace && tr_on && lane == 0 && warp == 4 && tile == (int)blockIdx.x) P.trace[tr_base + (k)] = clock64(); } while (0)
-#define TRACE_M(k) do { if (P.trace && tr_on && lane == 0 && tile == (int)blockIdx.x) P.trace[tr_base + 64 + (k)] = clock64(); } while (0)
-#define TRACE_W(k) do { if (P.trace && tr_on && lane == 0 && tile == (int)blockIdx.x) P.trace[tr_base + 64 + (k)] = wsum; } while (0)
+#define TRACE_E(k) do { if (P.trace && tr_on && lane == 0 && warp == 4 && ci == 0 && tile == (int)blockIdx.x) P.trace[tr_base + (k)] = clock64(); } while (0)
+#define TRACE_M(k) do { if (P.trace && tr_on && lane == 0 && ci == 0 && tile == (int)blockIdx.x) P.trace[tr_base + 64 + (k)] = clock64(); } while (0)
+#define TRACE_W(k) do { if (P.trace && tr_on && lane == 0 && ci == 0 && tile == (int)blockIdx.x) P.trace[tr_base + 64 + (k)] = wsum; } while (0)
 
 // ------------------------------------------------------------------------------------ the fused layer
 __global__ void __launch_bounds__(THREADS, 1)
@@ -269,19 +300,19 @@ loftr_layer_tc_kernel(const LayerArgs P) {
         if (lane == 0) {
             uint32_t n = 0;
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x)
-                for (int c = 0; c < NCHUNK; ++c, ++n) {
-                    const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1;
-                    mbar_wait(bempty + 8 * s, ph ^ 1);
-                    mbar_expect_tx(bfull + 8 * s, CHUNK);
-                    bulk_g2s(smem_u32(b_base + s * CHUNK), P.wpack + (size_t)c * CHUNK, CHUNK, bfull + 8 * s);
-                }
+                for (int ci = 0; ci < P.n_calls; ++ci)
+                    for (int c = 0; c < NCHUNK; ++c, ++n) {
+                        const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1;
+                        mbar_wait(bempty + 8 * s, ph ^ 1);
+                        mbar_expect_tx(bfull + 8 * s, CHUNK);
+                        bulk_g2s(smem_u32(b_base + s * CHUNK), P.call[ci].wpack + (size_t)c * CHUNK, CHUNK, bfull + 8 * s);
+                    }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
         {
             uint32_t n = 0, aph = 0, vph = 0;
             const uint32_t xo = smem_u32(x_base), ao = smem_u32(a_base), b0 = smem_u32(b_base);
-            const uint32_t kv_src = P.is_self ? xo : ao;
             constexpr uint32_t IDESC = idesc_f16(128);
             long long wsum = 0;
             // one 128 x 128 weight block = 2 chunks (K halves): D[:, dcol .. dcol + 128) (+)= oper W^T
@@ -310,7 +341,9 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                     __syncwarp();
                 }
             };
-            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x)
+            for (int ci = 0; ci < P.n_calls; ++ci) {
+                const uint32_t kv_src = P.call[ci].is_self ? xo : ao;
                 // seg 0: q, k, v (-> attention can start), then mlp.0[: C, :C] on x
                 TRACE_M(0);
                 mbar_wait(a_ready, aph & 1); ++aph;
@@ -370,17 +403,23 @@ loftr_layer_tc_kernel(const LayerArgs P) {
         float* stage_f = reinterpret_cast<float*>(a_base);
         float* red = reinterpret_cast<float*>(x_base);   // LayerNorm partials (X is dead whenever a LayerNorm runs)
 
-        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        bool bad = false;                                // an operand value outside the fp16 range (RANGE_CHECK)
+        const int g8 = lane >> 2, t4 = lane & 3, r8 = lane & 7, tl = lane >> 3;      // mma.sync / ldmatrix lane coordinates
+        const uint32_t stage_u32 = smem_u32(a_base);
+
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x)
+        for (int ci = 0; ci < P.n_calls; ++ci) {
+            const CallArgs& A = P.call[ci];
             const int pts = min(PTS, P.N - tile * PTS);
             const int valid_rows = pts * TOK;
             const size_t g_row0 = (size_t)tile * ROWS;
-            const float* xg = P.x + g_row0 * CH;
-            const float* sg = P.src + g_row0 * CH;
+            const float* xg = A.x + g_row0 * CH;
+            const float* sg = A.src + g_row0 * CH;
 
             // ---- E0: X = x, A = src (cross) ---------------------------------------------------
             TRACE_E(0);
-            load_tile_to_oper(x_base, xg, valid_rows, ew, lane);
-            if (!P.is_self) load_tile_to_oper(a_base, sg, valid_rows, ew, lane);
+            load_tile_to_oper(x_base, xg, valid_rows, ew, lane, bad);
+            if (!A.is_self) load_tile_to_oper(a_base, sg, valid_rows, ew, lane, bad);
             publish(a_ready);
             TRACE_E(1);
 
@@ -391,23 +430,19 @@ loftr_layer_tc_kernel(const LayerArgs P) {
             tc_fence_after();
             TRACE_E(2);
             {
-                // One quarter (heads 2hq, 2hq+1 = 32 columns) at a time, staged in the idle A operand, fp32:
-                //   Qst | Kst | Vst [128][ST] with ST = 36 floats per row (144 B: the 8 lanes of a 128-bit store phase, one row
-                //   each, fall into distinct bank groups, so no XOR swizzle and every address below is base + immediate);
-                //   KV (16 x 16) and Ksum (16) of a (point, head) pair overwrite rows 0..15 / 16 of that pair's own K block
-                //   (21 rows x 16 columns) once its warp has consumed it.
-                // (1) every thread moves 8 columns of q, k, v of its row from TMEM (elu+1 on q and k);
-                // (2) warp w < 12 owns the (point, head) pair w: KV = K'^T V and Ksum, lane = (2 d, 4 v);
-                // (3) the same warp computes the 21 x 16 message block of its pair as a register-tiled product
-                //     Q' KV (lane = (3 rows, 4 v)): 4 shared-memory wavefronts per d instead of one KV broadcast per row.
-                constexpr int ST = 36;
-                float* Qst = stage_f;
-                float* Kst = stage_f + 128 * ST;
-                float* Vst = stage_f + 2 * 128 * ST;
-                float4 m[4][3];                          // [quarter][row of the lane's row group]: 4 v values each
+                // One quarter (heads 2 hq, 2 hq + 1 = 32 columns) at a time:
+                // (1) every thread moves 8 columns of q, k, v of its token row from TMEM, applies elu + 1 to q and k, splits
+                //     each value into fp16 hi / lo and stores 16-byte pieces into the six staging arrays;
+                // (2) warp w < 12 owns the (point, head) pair w and runs it on the tensor cores (mma.sync.m16n8k16, fp32
+                //     accumulate, 3-term split):  KV^T[v][d] = sum_s V[s][v] K'[s][d]  (A = V^T and B = K' both through
+                //     ldmatrix.trans; tokens 21..31 of the second k step are masked out of A) together with
+                //     Ksum[d] = sum_s K'[s][d] as an all-ones A;  the accumulator fragment of KV^T is exactly the B fragment
+                //     of  msg[l][v] = sum_d Q'[l][d] KV[d][v]  (rows = tokens, 2 m tiles), the normaliser Q' . Ksum is one
+                //     more n tile of the same product.  The message stays in registers (hi / lo halves) until the staging
+                //     is dead, then goes into the A operand for the merge projection.
+                uint32_t mh[4][6], ml[4][6];
                 const int pair = ew, p = pair >> 1, hl = pair & 1;
-                const int rg = lane >> 2, vq = lane & 3;
-                const bool worker = ew < 12;
+                const bool worker = ew < 12 && p < pts;
 #pragma unroll
                 for (int hq = 0; hq < 4; ++hq) {
                     {
@@ -418,95 +453,107 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                         tmem_wait_ld();
                         if (hq == 1) TRACE_E(20);
                         if (hq == 3) { tc_fence_before(); mbar_arrive(v_free); }    // D2 is free: mlp.0[C:, :C] may go
+                        uint4 h4, l4;
+                        uint8_t* srow = a_base + row * SROW + colq * 16;
+                        float f[8];
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            float4 qq, kk, vv;
-                            qq.x = elu1(acc_f(qr[4 * j + 0])); qq.y = elu1(acc_f(qr[4 * j + 1]));
-                            qq.z = elu1(acc_f(qr[4 * j + 2])); qq.w = elu1(acc_f(qr[4 * j + 3]));
-                            kk.x = elu1(acc_f(kr[4 * j + 0])); kk.y = elu1(acc_f(kr[4 * j + 1]));
-                            kk.z = elu1(acc_f(kr[4 * j + 2])); kk.w = elu1(acc_f(kr[4 * j + 3]));
-                            vv.x = acc_f(vr[4 * j + 0]); vv.y = acc_f(vr[4 * j + 1]);
-                            vv.z = acc_f(vr[4 * j + 2]); vv.w = acc_f(vr[4 * j + 3]);
-                            const int f4 = colq * 2 + j;
-                            reinterpret_cast<float4*>(Qst + row * ST)[f4] = qq;
-                            reinterpret_cast<float4*>(Kst + row * ST)[f4] = kk;
-                            reinterpret_cast<float4*>(Vst + row * ST)[f4] = vv;
-                        }
+                        for (int i = 0; i < 8; ++i) f[i] = elu1(acc_f(qr[i]));
+                        RANGE_CHECK(f[0], f[1]); RANGE_CHECK(f[2], f[3]); RANGE_CHECK(f[4], f[5]); RANGE_CHECK(f[6], f[7]);
+                        split2(f[0], f[1], h4.x, l4.x); split2(f[2], f[3], h4.y, l4.y); split2(f[4], f[5], h4.z, l4.z); split2(f[6], f[7], h4.w, l4.w);
+                        *reinterpret_cast<uint4*>(srow) = h4; *reinterpret_cast<uint4*>(srow + SARR) = l4;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) f[i] = elu1(acc_f(kr[i]));
+                        RANGE_CHECK(f[0], f[1]); RANGE_CHECK(f[2], f[3]); RANGE_CHECK(f[4], f[5]); RANGE_CHECK(f[6], f[7]);
+                        split2(f[0], f[1], h4.x, l4.x); split2(f[2], f[3], h4.y, l4.y); split2(f[4], f[5], h4.z, l4.z); split2(f[6], f[7], h4.w, l4.w);
+                        *reinterpret_cast<uint4*>(srow + 2 * SARR) = h4; *reinterpret_cast<uint4*>(srow + 3 * SARR) = l4;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) f[i] = acc_f(vr[i]);
+                        RANGE_CHECK(f[0], f[1]); RANGE_CHECK(f[2], f[3]); RANGE_CHECK(f[4], f[5]); RANGE_CHECK(f[6], f[7]);
+                        split2(f[0], f[1], h4.x, l4.x); split2(f[2], f[3], h4.y, l4.y); split2(f[4], f[5], h4.z, l4.z); split2(f[6], f[7], h4.w, l4.w);
+                        *reinterpret_cast<uint4*>(srow + 4 * SARR) = h4; *reinterpret_cast<uint4*>(srow + 5 * SARR) = l4;
                     }
                     if (hq == 1) TRACE_E(21);
                     epi_bar();
                     if (hq == 1) TRACE_E(22);
                     if (worker) {
-                        // (2) lane -> d = 2 dp, 2 dp + 1 and v = 4 vq .. 4 vq + 3
-                        const int dp = rg;
-                        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-                        float ks0 = 0.f, ks1 = 0.f;
-                        float* kblk = Kst + p * TOK * ST + hl * 16;               // this pair's K block: rows p*21 .. +20, 16 columns
-                        if (p < pts) {
-                            const float* kp = kblk + 2 * dp;
-                            const float* vp = Vst + p * TOK * ST + hl * 16 + 4 * vq;
+                        float kvt[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                        float ksm[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-                            for (int u = 0; u < TOK; ++u) {
-                                const float2 kk = *reinterpret_cast<const float2*>(kp + u * ST);
-                                const float4 vv = *reinterpret_cast<const float4*>(vp + u * ST);
-                                ks0 += kk.x; ks1 += kk.y;
-                                a0.x = fmaf(kk.x, vv.x, a0.x); a0.y = fmaf(kk.x, vv.y, a0.y);
-                                a0.z = fmaf(kk.x, vv.z, a0.z); a0.w = fmaf(kk.x, vv.w, a0.w);
-                                a1.x = fmaf(kk.y, vv.x, a1.x); a1.y = fmaf(kk.y, vv.y, a1.y);
-                                a1.z = fmaf(kk.y, vv.z, a1.z); a1.w = fmaf(kk.y, vv.w, a1.w);
+                        for (int ks = 0; ks < 2; ++ks) {
+                            // A = V^T: tile tl -> tokens ks*16 + 8*(tl>>1) .., value columns 8*(tl&1) ..
+                            const int rowA = min(p * TOK + ks * 16 + r8 + 8 * (tl >> 1), TILE_M - 1);
+                            const uint32_t aV = stage_u32 + 4 * SARR + rowA * SROW + (hl * 16 + 8 * (tl & 1)) * 2;
+                            uint32_t vh[4], vl[4], one[4] = {0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u};
+                            ldsm_x4_t(aV, vh); ldsm_x4_t(aV + SARR, vl);
+                            if (ks == 1) {                       // tokens 16 + 2 t4, 17 + 2 t4 in a0 / a1; 24.. in a2 / a3: keep < 21
+                                const uint32_t mk = t4 < 2 ? 0xffffffffu : (t4 == 2 ? 0x0000ffffu : 0u);
+                                vh[0] &= mk; vh[1] &= mk; vl[0] &= mk; vl[1] &= mk; one[0] &= mk; one[1] &= mk;
+                                vh[2] = vh[3] = vl[2] = vl[3] = one[2] = one[3] = 0u;
+                            }
+                            // B = K': tile tl -> tokens ks*16 + 8*(tl&1) .., d columns 8*(tl>>1) ..
+                            const int rowB = min(p * TOK + ks * 16 + r8 + 8 * (tl & 1), TILE_M - 1);
+                            const uint32_t aK = stage_u32 + 2 * SARR + rowB * SROW + (hl * 16 + 8 * (tl >> 1)) * 2;
+                            uint32_t kh[4], kl[4];
+                            ldsm_x4_t(aK, kh); ldsm_x4_t(aK + SARR, kl);
+#pragma unroll
+                            for (int nt = 0; nt < 2; ++nt) {
+                                mma16816(kvt[nt], vl, kh[2 * nt], kh[2 * nt + 1]);
+                                mma16816(kvt[nt], vh, kl[2 * nt], kl[2 * nt + 1]);
+                                mma16816(kvt[nt], vh, kh[2 * nt], kh[2 * nt + 1]);
+                                mma16816(ksm[nt], one, kl[2 * nt], kl[2 * nt + 1]);
+                                mma16816(ksm[nt], one, kh[2 * nt], kh[2 * nt + 1]);
                             }
                         }
-                        __syncwarp();                                             // every lane is done reading the K block
-                        *reinterpret_cast<float4*>(kblk + (2 * dp) * ST + 4 * vq) = a0;           // KV[d][v] -> row d of the block
-                        *reinterpret_cast<float4*>(kblk + (2 * dp + 1) * ST + 4 * vq) = a1;
-                        if (vq == 0) *reinterpret_cast<float2*>(kblk + 16 * ST + 2 * dp) = make_float2(ks0, ks1);   // Ksum -> row 16
-                        __syncwarp();
                         if (hq == 1) TRACE_E(23);
-                        // (3) lane -> rows 3 rg .. 3 rg + 2 of the point (rg < 7) and v = 4 vq .. 4 vq + 3
-                        float4 acc[3];
-                        float den[3] = {0.f, 0.f, 0.f};
+                        // KV^T accumulators -> B fragments of Q' KV: n tile nv holds v = 8 nv + g8, b0 = d 0..7, b1 = d 8..15
+                        uint32_t bh[2][2], bl[2][2], sh[2], sl[2];
+                        RANGE_CHECK(kvt[0][0], kvt[0][1]); RANGE_CHECK(kvt[1][0], kvt[1][1]); RANGE_CHECK(kvt[0][2], kvt[0][3]); RANGE_CHECK(kvt[1][2], kvt[1][3]);
+                        RANGE_CHECK(ksm[0][0], ksm[0][1]); RANGE_CHECK(ksm[1][0], ksm[1][1]);
+                        split2(kvt[0][0], kvt[0][1], bh[0][0], bl[0][0]); split2(kvt[1][0], kvt[1][1], bh[0][1], bl[0][1]);
+                        split2(kvt[0][2], kvt[0][3], bh[1][0], bl[1][0]); split2(kvt[1][2], kvt[1][3], bh[1][1], bl[1][1]);
+                        split2(ksm[0][0], ksm[0][1], sh[0], sl[0]); split2(ksm[1][0], ksm[1][1], sh[1], sl[1]);
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        const float* qp = Qst + (p * TOK + min(rg, 6) * 3) * ST + hl * 16;
-#pragma unroll
-                        for (int dq = 0; dq < 4; ++dq) {
-                            const float4 ksum = *reinterpret_cast<const float4*>(kblk + 16 * ST + 4 * dq);
-                            float4 qv[3];
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) {
-                                qv[i] = *reinterpret_cast<const float4*>(qp + i * ST + 4 * dq);
-                                den[i] = fmaf(qv[i].x, ksum.x, den[i]); den[i] = fmaf(qv[i].y, ksum.y, den[i]);
-                                den[i] = fmaf(qv[i].z, ksum.z, den[i]); den[i] = fmaf(qv[i].w, ksum.w, den[i]);
+                        for (int mt = 0; mt < 2; ++mt) {
+                            // A = Q': tile tl -> tokens mt*16 + 8*(tl&1) .., d columns 8*(tl>>1) ..
+                            const int rowQ = min(p * TOK + mt * 16 + r8 + 8 * (tl & 1), TILE_M - 1);
+                            const uint32_t aQ = stage_u32 + rowQ * SROW + (hl * 16 + 8 * (tl >> 1)) * 2;
+                            uint32_t qh[4], ql[4];
+                            ldsm_x4(aQ, qh); ldsm_x4(aQ + SARR, ql);
+                            float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f}, dn[4] = {0.f, 0.f, 0.f, 0.f};
+                            mma16816(o0, ql, bh[0][0], bh[0][1]); mma16816(o0, qh, bl[0][0], bl[0][1]); mma16816(o0, qh, bh[0][0], bh[0][1]);
+                            mma16816(o1, ql, bh[1][0], bh[1][1]); mma16816(o1, qh, bl[1][0], bl[1][1]); mma16816(o1, qh, bh[1][0], bh[1][1]);
+                            mma16816(dn, ql, sh[0], sh[1]); mma16816(dn, qh, sl[0], sl[1]); mma16816(dn, qh, sh[0], sh[1]);
+                            const float z0 = __fdividef(1.0f, dn[0] + P.attn_eps), z1 = __fdividef(1.0f, dn[2] + P.attn_eps);
+                            if (mt == 0) {                       // token rows g8 and g8 + 8
+                                RANGE_CHECK(o0[0] * z0, o0[1] * z0); RANGE_CHECK(o1[0] * z0, o1[1] * z0);
+                                RANGE_CHECK(o0[2] * z1, o0[3] * z1); RANGE_CHECK(o1[2] * z1, o1[3] * z1);
+                                split2(o0[0] * z0, o0[1] * z0, mh[hq][0], ml[hq][0]); split2(o1[0] * z0, o1[1] * z0, mh[hq][1], ml[hq][1]);
+                                split2(o0[2] * z1, o0[3] * z1, mh[hq][2], ml[hq][2]); split2(o1[2] * z1, o1[3] * z1, mh[hq][3], ml[hq][3]);
+                            } else {                             // token row 16 + g8 (valid for g8 < 5); rows 24.. do not exist
+                                RANGE_CHECK(o0[0] * z0, o0[1] * z0); RANGE_CHECK(o1[0] * z0, o1[1] * z0);
+                                split2(o0[0] * z0, o0[1] * z0, mh[hq][4], ml[hq][4]); split2(o1[0] * z0, o1[1] * z0, mh[hq][5], ml[hq][5]);
                             }
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float4 kv = *reinterpret_cast<const float4*>(kblk + (4 * dq + e) * ST + 4 * vq);
-#pragma unroll
-                                for (int i = 0; i < 3; ++i) {
-                                    const float q1 = e == 0 ? qv[i].x : e == 1 ? qv[i].y : e == 2 ? qv[i].z : qv[i].w;
-                                    acc[i].x = fmaf(q1, kv.x, acc[i].x); acc[i].y = fmaf(q1, kv.y, acc[i].y);
-                                    acc[i].z = fmaf(q1, kv.z, acc[i].z); acc[i].w = fmaf(q1, kv.w, acc[i].w);
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int i = 0; i < 3; ++i) {
-                            const float z = __fdividef(1.0f, den[i] + P.attn_eps);
-                            m[hq][i] = make_float4(acc[i].x * z, acc[i].y * z, acc[i].z * z, acc[i].w * z);
                         }
                     }
                     if (hq == 0) TRACE_E(3);
                     if (hq == 1) TRACE_E(24);
-                    epi_bar();                           // (2), (3) done reading: the next quarter may overwrite the staging
+                    epi_bar();                           // (2) done reading: the next quarter may overwrite the staging
                     if (hq == 1) TRACE_E(25);
                 }
                 // staging dead (barrier above): msg -> A operand, rows of point p, columns of head 2 hq + hl
-                if (worker && rg < 7) {
+                if (worker) {
 #pragma unroll
                     for (int hq = 0; hq < 4; ++hq)
 #pragma unroll
-                        for (int i = 0; i < 3; ++i)
-                            split_store4(a_base, p * TOK + rg * 3 + i, (2 * hq + hl) * 16 + 4 * vq, m[hq][i]);
+                        for (int sl6 = 0; sl6 < 6; ++sl6) {
+                            const int l = sl6 < 2 ? g8 : (sl6 < 4 ? g8 + 8 : g8 + 16);
+                            if (l < TOK) {
+                                const int rr = p * TOK + l, col = (2 * hq + hl) * 16 + (sl6 & 1) * 8 + 2 * t4;
+                                const uint32_t off = (uint32_t)(col >> 6) * SLAB + sw128(rr, (col & 63) >> 3) + (uint32_t)(col & 7) * 2u;
+                                *reinterpret_cast<uint32_t*>(a_base + off) = mh[hq][sl6];
+                                *reinterpret_cast<uint32_t*>(a_base + 2 * SLAB + off) = ml[hq][sl6];
+                            }
+                        }
                 }
             }
             publish(a_ready);
@@ -530,14 +577,14 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                     float y[8];
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const float4 g = __ldg(reinterpret_cast<const float4*>(P.ln1_g + col0) + 2 * j + e);
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(P.ln1_b + col0) + 2 * j + e);
+                        const float4 g = __ldg(reinterpret_cast<const float4*>(A.ln1_g + col0) + 2 * j + e);
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(A.ln1_b + col0) + 2 * j + e);
                         y[4 * e + 0] = (v[8 * j + 4 * e + 0] - mean) * rstd * g.x + b.x;
                         y[4 * e + 1] = (v[8 * j + 4 * e + 1] - mean) * rstd * g.y + b.y;
                         y[4 * e + 2] = (v[8 * j + 4 * e + 2] - mean) * rstd * g.z + b.z;
                         y[4 * e + 3] = (v[8 * j + 4 * e + 3] - mean) * rstd * g.w + b.w;
                     }
-                    split_store8(a_base, row, col0 + j * 8, make_float4(y[0], y[1], y[2], y[3]), make_float4(y[4], y[5], y[6], y[7]));
+                    split_store8(a_base, row, col0 + j * 8, make_float4(y[0], y[1], y[2], y[3]), make_float4(y[4], y[5], y[6], y[7]), bad);
                 }
             }
             publish(a_ready);
@@ -559,7 +606,7 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                                  make_float4(fmaxf(acc_f(hr[8 * j]), 0.f), fmaxf(acc_f(hr[8 * j + 1]), 0.f),
                                              fmaxf(acc_f(hr[8 * j + 2]), 0.f), fmaxf(acc_f(hr[8 * j + 3]), 0.f)),
                                  make_float4(fmaxf(acc_f(hr[8 * j + 4]), 0.f), fmaxf(acc_f(hr[8 * j + 5]), 0.f),
-                                             fmaxf(acc_f(hr[8 * j + 6]), 0.f), fmaxf(acc_f(hr[8 * j + 7]), 0.f)));
+                                             fmaxf(acc_f(hr[8 * j + 6]), 0.f), fmaxf(acc_f(hr[8 * j + 7]), 0.f)), bad);
             }
             publish(a_ready);
             TRACE_E(8);
@@ -580,8 +627,8 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                 // stage the normalised row (float4 index XOR (row & 31)) so the global traffic is coalesced
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 g = __ldg(reinterpret_cast<const float4*>(P.ln2_g + col0) + j);
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(P.ln2_b + col0) + j);
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(A.ln2_g + col0) + j);
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(A.ln2_b + col0) + j);
                     float4 y;
                     y.x = (v[4 * j + 0] - mean) * rstd * g.x + b.x;
                     y.y = (v[4 * j + 1] - mean) * rstd * g.y + b.y;
@@ -590,21 +637,22 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                     reinterpret_cast<float4*>(stage_f + row * CH)[(colq * 8 + j) ^ (row & 31)] = y;
                 }
                 epi_bar();
-                float* og = P.out + g_row0 * CH;
+                float* og = A.out + g_row0 * CH;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int r2 = ew * 8 + i;
                     if (r2 < valid_rows) {
                         const float4 y = reinterpret_cast<const float4*>(stage_f + r2 * CH)[lane ^ (r2 & 31)];
-                        const float4 xv = __ldg(reinterpret_cast<const float4*>(xg + (size_t)r2 * CH) + lane);
-                        reinterpret_cast<float4*>(og + (size_t)r2 * CH)[lane] = make_float4(xv.x + y.x, xv.y + y.y, xv.z + y.z, xv.w + y.w);
+                        const float4 xv = __ldcg(reinterpret_cast<const float4*>(xg + (size_t)r2 * CH) + lane);
+                        __stcg(reinterpret_cast<float4*>(og + (size_t)r2 * CH) + lane, make_float4(xv.x + y.x, xv.y + y.y, xv.z + y.z, xv.w + y.w));
                     }
                 }
-                epi_bar();                               // staging / partials reads done before the next tile's split stores
+                epi_bar();                               // staging / partials reads done (and this call's rows written) before the next call
             }
             TRACE_E(10);
             tc_fence_before();
         }
+        if (bad && P.overflow) atomicOr(P.overflow, 1);
     }
 
     tc_fence_before();
@@ -668,11 +716,12 @@ tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(128u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    bool bad = false;
     for (int c = 0; c < K; c += 8) {
         const float4* pa = reinterpret_cast<const float4*>(A + (size_t)row * K + c);
         const float4* pb = reinterpret_cast<const float4*>(B + (size_t)row * K + c);
-        split_store8(a_base, row, c, pa[0], pa[1]);
-        split_store8(b_base, row, c, pb[0], pb[1]);
+        split_store8(a_base, row, c, pa[0], pa[1], bad);
+        split_store8(b_base, row, c, pb[0], pb[1], bad);
     }
     fence_async_smem();
     tc_fence_before();
@@ -776,8 +825,9 @@ static long long* g_loftr_trace = nullptr;     // device buffer of 256 int64, se
 bool loftr_tc_built() { return true; }
 
 size_t loftr_tc_workspace_bytes(int N, int tokens, int C) {
-    // 4 ping-pong token buffers (transformer) + packed weights of up to MAX_LAYERS layers
-    return (size_t)N * tokens * C * 4 * sizeof(float) + (size_t)tc::MAX_LAYERS * tc::LAYER_PACK_BYTES + 1024;
+    // packed weights of up to MAX_LAYERS layers (the tokens live in the caller's output buffers)
+    (void)N; (void)tokens; (void)C;
+    return (size_t)tc::MAX_LAYERS * tc::LAYER_PACK_BYTES + 1024;
 }
 
 static uint8_t* pack_base(void* tc_ws) {
@@ -794,18 +844,29 @@ int loftr_tc_pack(const riders_loftr_weights& w, int layer_slot, void* tc_ws, cu
     return check_launch("loftr_pack_weights");
 }
 
-int loftr_tc_run(const float* x, const float* src, const riders_loftr_weights& w, int layer_slot,
-                 int N, float attn_eps, float ln_eps, float* out, void* tc_ws, cudaStream_t st) {
+// One launch for a list of layer calls (all of a transformer, or a single layer): call i reads x[i] / src[i], writes out[i]
+// (out[i] may alias x[i]) with the packed weights of layer slot[i].  `overflow` (device int, zeroed by the caller) is set when an
+// operand left the fp16 range.
+int loftr_tc_run_calls(int n_calls, const float* const* x, const float* const* src, float* const* out,
+                       const riders_loftr_weights* const* w, const int* slot,
+                       int N, float attn_eps, float ln_eps, void* tc_ws, int* overflow, cudaStream_t st) {
     static size_t configured[64] = {0};
     if (int rc_smem = ensure_dynamic_smem(tc::loftr_layer_tc_kernel, (size_t)(tc::SMEM_BYTES), configured, "loftr(tcgen05): shared memory attribute")) return rc_smem;
-    RIDERS_REQUIRE(out != x && out != src, "loftr(tcgen05): out must not alias an input");
+    RIDERS_REQUIRE(n_calls >= 1 && n_calls <= tc::MAX_CALLS, "loftr(tcgen05): 1..%d layer calls per launch (got %d)", tc::MAX_CALLS, n_calls);
     tc::LayerArgs P;
-    P.x = x; P.src = src; P.out = out;
-    P.wpack = pack_base(tc_ws) + (size_t)layer_slot * tc::LAYER_PACK_BYTES;
-    P.ln1_g = w.ln1_g; P.ln1_b = w.ln1_b; P.ln2_g = w.ln2_g; P.ln2_b = w.ln2_b;
-    P.N = N; P.n_tiles = ceil_div(N, tc::PTS); P.is_self = (x == src) ? 1 : 0;
+    for (int i = 0; i < n_calls; ++i) {
+        RIDERS_REQUIRE(out[i] != src[i] || x[i] == src[i], "loftr(tcgen05): out must not alias the source of a cross layer");
+        tc::CallArgs& A = P.call[i];
+        A.x = x[i]; A.src = src[i]; A.out = out[i];
+        A.wpack = pack_base(tc_ws) + (size_t)slot[i] * tc::LAYER_PACK_BYTES;
+        A.ln1_g = w[i]->ln1_g; A.ln1_b = w[i]->ln1_b; A.ln2_g = w[i]->ln2_g; A.ln2_b = w[i]->ln2_b;
+        A.is_self = (x[i] == src[i]) ? 1 : 0;
+    }
+    P.n_calls = n_calls;
+    P.N = N; P.n_tiles = ceil_div(N, tc::PTS);
     P.attn_eps = attn_eps; P.ln_eps = ln_eps;
     P.trace = g_loftr_trace;
+    P.overflow = overflow;
     const int grid = P.n_tiles < sm_count() ? P.n_tiles : sm_count();
     count_launches(1);
     tc::loftr_layer_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(P);

@@ -589,7 +589,21 @@ def _weights_struct(params, keep):
     return w
 
 
-def loftr_layer(x, source, params, nhead=8, impl=LOFTR_SIMT, attn_eps=1e-6, ln_eps=1e-5):
+class LoftrOverflow(object):
+    """fp16-range guard of the tcgen05 LoFTR path.  Its operands are fp16 hi/lo pairs, so every value must satisfy
+    |a| <= 65504 - a limit the fp32 reference does not have.  The kernel raises a device flag when a value leaves the range;
+    ``check()`` reads it (one D2H) and, if set, ``rerun()`` recomputes the call on the fp32 SIMT kernels.  ``loftr_layer`` /
+    ``loftr_transformer`` check immediately unless ``defer=True`` (the batched pipeline reads all flags at its own sync point)."""
+    pending = []
+
+    def __init__(self, flag, rerun):
+        self.flag, self.rerun = flag, rerun
+
+    def overflowed(self):
+        return bool(int(self.flag.item()))
+
+
+def loftr_layer(x, source, params, nhead=8, impl=LOFTR_SIMT, attn_eps=1e-6, ln_eps=1e-5, defer=False):
     _need_cuda(x, source)
     x, source = _f32c(x), _f32c(source)
     N, Lx, Cm = x.shape
@@ -602,11 +616,17 @@ def loftr_layer(x, source, params, nhead=8, impl=LOFTR_SIMT, attn_eps=1e-6, ln_e
     rc = L.riders_loftr_layer_fwd(_ptr(x), _ptr(source), C.byref(w), N, Lx, S, Cm, nhead,
                                   float(attn_eps), float(ln_eps), impl, _ptr(out), _ptr(ws), _stream())
     _lib.check(rc, "riders_loftr_layer_fwd")
+    if impl == LOFTR_TCGEN05 and N > 0:
+        guard = LoftrOverflow(ws[:4].view(torch.int32), lambda: loftr_layer(x, source, params, nhead, LOFTR_SIMT, attn_eps, ln_eps))
+        if defer:
+            LoftrOverflow.pending.append((guard, (out,)))
+        elif guard.overflowed():
+            return guard.rerun()
     return out
 
 
 def loftr_transformer(feat0, feat1, layer_params, layer_names, nhead=8, impl=LOFTR_SIMT,
-                      attn_eps=1e-6, ln_eps=1e-5):
+                      attn_eps=1e-6, ln_eps=1e-5, defer=False):
     """LocalFeatureTransformer.forward (RCNet/linear_attention.py:159-184) in one C call."""
     _need_cuda(feat0, feat1)
     feat0, feat1 = _f32c(feat0), _f32c(feat1)
@@ -629,7 +649,21 @@ def loftr_transformer(feat0, feat1, layer_params, layer_names, nhead=8, impl=LOF
                                             N, L0, S, Cm, nhead, float(attn_eps), float(ln_eps), impl,
                                             _ptr(out0), _ptr(out1), _ptr(ws), _stream())
     _lib.check(rc, "riders_loftr_transformer_fwd")
+    if impl == LOFTR_TCGEN05 and N > 0:
+        guard = LoftrOverflow(ws[:4].view(torch.int32),
+                              lambda: loftr_transformer(feat0, feat1, layer_params, layer_names, nhead, LOFTR_SIMT, attn_eps, ln_eps))
+        if defer:
+            LoftrOverflow.pending.append((guard, (out0, out1)))
+        elif guard.overflowed():
+            return guard.rerun()
     return out0, out1
+
+
+def loftr_overflow_pending():
+    """Read the overflow flags of every deferred tcgen05 LoFTR call since the last check (one 4-byte D2H each) and forget
+    them.  True = at least one call left the fp16 range: the caller recomputes with the SIMT kernels."""
+    pending, LoftrOverflow.pending = LoftrOverflow.pending, []
+    return any(guard.overflowed() for guard, _ in pending)
 
 
 # --------------------------------------------------------------------------------------------

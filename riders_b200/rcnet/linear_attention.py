@@ -7,8 +7,12 @@ Forward passes run on the sm_100a kernels:
   LinearAttention.forward          -> riders_linear_attention_fwd   (linear_attention.py:18-45)
   LoFTREncoderLayer.forward        -> riders_loftr_layer_fwd        (linear_attention.py:112-135)
   LocalFeatureTransformer.forward  -> riders_loftr_transformer_fwd  (linear_attention.py:159-184)
-``FullAttention`` (linear_attention.py:49-80) is never constructed by RC-Net
-(attention='linear', networks.py:378) and is not provided.
+``FullAttention`` (linear_attention.py:49-80) is never constructed by RC-Net (attention='linear', networks.py:378); it is
+provided as plain torch ops for API completeness.
+
+fp16-range guard: the tcgen05 path computes in fp16 hi/lo pairs (|value| <= 65504, a limit the fp32 reference does not have).
+The kernel flags a violation and the call is recomputed on the fp32 SIMT kernels - immediately here (one small D2H per call),
+or at the caller's own sync point when ``defer_overflow_check`` is set (``forward_output_batched``).
 """
 import copy
 import os
@@ -37,17 +41,34 @@ class LinearAttention(nn.Module):
         return ops.linear_attention(queries, keys, values, q_mask, kv_mask, self.eps)
 
 
+class FullAttention(nn.Module):
+    """linear_attention.py:49-80: softmax attention with the 1/sqrt(D) temperature (never constructed by RC-Net; torch ops)."""
+
+    def __init__(self, use_dropout=False, attention_dropout=0.1):
+        super().__init__()
+        self.use_dropout = use_dropout
+        self.dropout = nn.Dropout(attention_dropout)
+
+    def forward(self, queries, keys, values, q_mask=None, kv_mask=None):
+        QK = torch.einsum("nlhd,nshd->nlsh", queries, keys)
+        if kv_mask is not None:
+            QK.masked_fill_(~(q_mask[:, :, None, None] * kv_mask[:, None, :, None]).bool(), float('-inf'))
+        softmax_temp = 1. / queries.size(3) ** .5
+        A = torch.softmax(softmax_temp * QK, dim=2)
+        if self.use_dropout:
+            A = self.dropout(A)
+        return torch.einsum("nlsh,nshd->nlhd", A, values).contiguous()
+
+
 class LoFTREncoderLayer(nn.Module):
     def __init__(self, d_model, nhead, attention='linear'):
         super().__init__()
-        if attention != 'linear':
-            raise ValueError("only attention='linear' is provided (RC-Net never builds FullAttention)")
         self.dim = d_model // nhead
         self.nhead = nhead
         self.q_proj = nn.Linear(d_model, d_model, bias=False)
         self.k_proj = nn.Linear(d_model, d_model, bias=False)
         self.v_proj = nn.Linear(d_model, d_model, bias=False)
-        self.attention = LinearAttention()
+        self.attention = LinearAttention() if attention == 'linear' else FullAttention()
         self.merge = nn.Linear(d_model, d_model, bias=False)
         self.mlp = nn.Sequential(
             nn.Linear(d_model * 2, d_model * 2, bias=False),
@@ -85,11 +106,11 @@ class LoFTREncoderLayer(nn.Module):
 
     def forward(self, x, source, x_mask=None, source_mask=None):
         """x [N,L,C], source [N,S,C] -> [N,L,C]."""
-        if torch.is_grad_enabled() and x_mask is None and source_mask is None and \
+        if torch.is_grad_enabled() and x_mask is None and source_mask is None and isinstance(self.attention, LinearAttention) and \
                 (x.requires_grad or source.requires_grad or self.q_proj.weight.requires_grad):
             return self._forward_autograd(x, source)
-        if x_mask is not None or source_mask is not None:
-            # masked call (never issued by RC-Net, networks.py:444): compose from the kernels
+        if x_mask is not None or source_mask is not None or not isinstance(self.attention, LinearAttention):
+            # masked call / FullAttention (never issued by RC-Net, networks.py:444): compose from the kernels
             bs = x.size(0)
             q = self.q_proj(x).view(bs, -1, self.nhead, self.dim)
             k = self.k_proj(source).view(bs, -1, self.nhead, self.dim)
@@ -125,7 +146,7 @@ class LocalFeatureTransformer(nn.Module):
 
     def forward(self, feat0, feat1, mask0=None, mask1=None):
         assert self.d_model == feat0.size(2), "the feature number of src and transformer must be equal"
-        if mask0 is not None or mask1 is not None:
+        if mask0 is not None or mask1 is not None or self.attention != 'linear':
             for layer, name in zip(self.layers, self.layer_names):
                 if name == 'self':
                     feat0 = layer(feat0, feat0, mask0, mask0)
@@ -148,9 +169,11 @@ class LocalFeatureTransformer(nn.Module):
                 else:
                     raise KeyError
             return feat0, feat1
-        impl = default_impl()
+        impl = getattr(self, "force_impl", None)
+        impl = default_impl() if impl is None else impl
         if not self.layers[0]._supports(impl, feat0, feat1):
             impl = ops.LOFTR_SIMT
         return ops.loftr_transformer(feat0, feat1, [l.kernel_params() for l in self.layers],
                                      self.layer_names, self.nhead, impl,
-                                     self.layers[0].attention.eps, self.layers[0].norm1.eps)
+                                     self.layers[0].attention.eps, self.layers[0].norm1.eps,
+                                     defer=bool(getattr(self, "defer_overflow_check", False)))

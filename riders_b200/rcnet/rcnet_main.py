@@ -53,6 +53,39 @@ def forward_output(model, image, radar_points, bounding_boxes_list, response_thr
     return depth, response
 
 
+def _latent_to_maps(model, enc, dec, latent_image, skips_image, radar_points, rois, frame_offsets, H, W, ph, pw, response_thr,
+                    chunk_points, return_select):
+    """Latent path (1/32-level gather + point MLP + LoFTR) for every point of the batch at once, then the skip gather + decoder per
+    chunk of points and the reduce kernel.  Returns (reduce outputs, logits / confidences, is_logits)."""
+    images_device = radar_points.device
+    R = radar_points.shape[0]
+    logits = torch.empty((R, 1, ph, pw), device=images_device, dtype=torch.float32)
+    # latent path (1/32-level gather + point MLP + LoFTR) for every point of the batch at once: 1366 tiles of
+    # 6 points fill the 148 SMs in ~9 full waves; the skip gather + decoder run per chunk of points.
+    latent = enc.encode_latent(latent_image, radar_points, rois)
+    # each pooled skip is gathered straight into the concat buffer of the decoder block that consumes it
+    lead = dec.skip_lead_channels(len(skips_image)) if hasattr(dec, 'skip_lead_channels') else None
+    sigmoid_in_head = None if isinstance(dec, networks.MultiScaleDecoder) else False
+    for s in range(0, R, chunk_points):
+        e = min(R, s + chunk_points)
+        skips = enc.gather_skips(skips_image, rois[s:e], lead_channels=lead)
+        # the fused head kernel writes sigmoid(logit) directly when it runs (SFU work under an HBM-bound kernel), so the
+        # reduce streams confidences; otherwise the reduce applies the sigmoid itself
+        if sigmoid_in_head is None or sigmoid_in_head:
+            logits[s:e] = dec(x=latent[s:e], skips=skips, shape=(ph, pw), head_sigmoid=True)[-1]
+            done = bool(getattr(dec, 'last_head_sigmoid', False))
+            if sigmoid_in_head is None:
+                sigmoid_in_head = done
+            elif not done:
+                logits[s:e] = torch.sigmoid(logits[s:e])
+        else:
+            logits[s:e] = dec(x=latent[s:e], skips=skips, shape=(ph, pw))[-1]
+    is_logits = not sigmoid_in_head
+    out = list(ops.confidence_reduce(logits, radar_points, frame_offsets, H, W, response_thr, logits=is_logits,
+                                     want_select=return_select))
+    return out, logits, is_logits
+
+
 def forward_output_batched(model, images, radar_points, frame_offsets, response_thr=0.5,
                            chunk_points=1024, return_select=False, raw_inputs=False, retry_empty=False):
     """Many frames per call (BASELINE config 2/3).
@@ -84,30 +117,24 @@ def forward_output_batched(model, images, radar_points, frame_offsets, response_
         rois = torch.cat([frame_of[:, None], boxes], dim=1).contiguous()
     latent_image, skips_image = enc.encoder_image(padded)
     R = radar_points.shape[0]
-    logits = torch.empty((R, 1, ph, pw), device=images.device, dtype=torch.float32)
-    # latent path (1/32-level gather + point MLP + LoFTR) for every point of the batch at once: 1366 tiles of
-    # 6 points fill the 148 SMs in ~9 full waves; the skip gather + decoder run per chunk of points.
-    latent = enc.encode_latent(latent_image, radar_points, rois)
-    # each pooled skip is gathered straight into the concat buffer of the decoder block that consumes it
-    lead = dec.skip_lead_channels(len(skips_image)) if hasattr(dec, 'skip_lead_channels') else None
-    sigmoid_in_head = None if isinstance(dec, networks.MultiScaleDecoder) else False
-    for s in range(0, R, chunk_points):
-        e = min(R, s + chunk_points)
-        skips = enc.gather_skips(skips_image, rois[s:e], lead_channels=lead)
-        # the fused head kernel writes sigmoid(logit) directly when it runs (SFU work under an HBM-bound kernel), so the
-        # reduce streams confidences; otherwise the reduce applies the sigmoid itself
-        if sigmoid_in_head is None or sigmoid_in_head:
-            logits[s:e] = dec(x=latent[s:e], skips=skips, shape=(ph, pw), head_sigmoid=True)[-1]
-            done = bool(getattr(dec, 'last_head_sigmoid', False))
-            if sigmoid_in_head is None:
-                sigmoid_in_head = done
-            elif not done:
-                logits[s:e] = torch.sigmoid(logits[s:e])
-        else:
-            logits[s:e] = dec(x=latent[s:e], skips=skips, shape=(ph, pw))[-1]
-    is_logits = not sigmoid_in_head
-    out = list(ops.confidence_reduce(logits, radar_points, frame_offsets, H, W, response_thr, logits=is_logits,
-                                     want_select=return_select))
+    tf = getattr(enc, 'attention', None)
+    for attempt in (0, 1):
+        # The tcgen05 LoFTR path works in fp16 hi/lo pairs; a value beyond the fp16 range raises a device flag, which is read
+        # at this function's own sync point (no extra stall in the common case).  If it was raised, the latent path and
+        # everything after it are recomputed once with the fp32 SIMT kernels.
+        if tf is not None:
+            tf.defer_overflow_check = attempt == 0
+            tf.force_impl = ops.LOFTR_SIMT if attempt == 1 else None
+        try:
+            out, logits, is_logits = _latent_to_maps(model, enc, dec, latent_image, skips_image, radar_points, rois, frame_offsets,
+                                                     H, W, ph, pw, response_thr, chunk_points, return_select)
+        finally:
+            if tf is not None:
+                tf.defer_overflow_check = False
+                tf.force_impl = None
+        if attempt == 0 and ops.LoftrOverflow.pending and ops.loftr_overflow_pending():
+            continue
+        break
     if retry_empty:
         thr = float(response_thr)
         empty = (out[0].flatten(1).amax(dim=1) == 0).nonzero().flatten().tolist()          # D2H: the caller's np.sum(...) == 0

@@ -69,6 +69,67 @@ def test_loftr_tcgen05_layer_and_transformer_match_reference(golden):
     np.testing.assert_allclose(o1.cpu().numpy(), g["o1"], rtol=1e-4, atol=5e-5)
 
 
+def _random_layer(seed):
+    rng = np.random.default_rng(seed)
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    params = {}
+    for name, shape in (("q_proj.weight", (128, 128)), ("k_proj.weight", (128, 128)), ("v_proj.weight", (128, 128)),
+                        ("merge.weight", (128, 128)), ("mlp.0.weight", (256, 256)), ("mlp.2.weight", (128, 256))):
+        w = torch.empty(shape)
+        torch.nn.init.xavier_uniform_(w, generator=g)
+        params[name] = w.to(DEV)
+    for name in ("norm1", "norm2"):
+        params[name + ".weight"] = cu(rng.uniform(0.5, 1.5, 128).astype(np.float32))
+        params[name + ".bias"] = cu(rng.uniform(-0.2, 0.2, 128).astype(np.float32))
+    return params
+
+
+def test_loftr_tcgen05_fp16_range_guard():
+    """The tcgen05 path works in fp16 hi/lo pairs (|value| <= 65504); the fp32 reference has no such limit.  Tokens of
+    magnitude 1e5 must not yield silent Inf / NaN: the kernel raises its overflow flag and the call is recomputed on the
+    fp32 SIMT kernels (immediately, or at the caller's sync point in the deferred form)."""
+    params = _random_layer(3)
+    rng = np.random.default_rng(3)
+    big = cu((rng.standard_normal((13, 21, 128)) * 1e5).astype(np.float32))
+    ok = cu(rng.standard_normal((13, 21, 128)).astype(np.float32))
+    ref = ops.loftr_layer(big, big, params, impl=ops.LOFTR_SIMT)
+    got = ops.loftr_layer(big, big, params, impl=ops.LOFTR_TCGEN05)
+    assert torch.isfinite(got).all() and torch.equal(got, ref)
+    # one oversized token in an otherwise ordinary batch, cross layer
+    mixed = ok.clone()
+    mixed[7, 3, 5] = 3e5
+    got = ops.loftr_layer(ok, mixed, params, impl=ops.LOFTR_TCGEN05)
+    assert torch.equal(got, ops.loftr_layer(ok, mixed, params, impl=ops.LOFTR_SIMT))
+    # deferred form: the flag is read later, by the caller
+    assert not ops.LoftrOverflow.pending
+    ops.loftr_layer(ok, ok, params, impl=ops.LOFTR_TCGEN05, defer=True)
+    assert ops.LoftrOverflow.pending and not ops.loftr_overflow_pending()
+    ops.loftr_layer(big, big, params, impl=ops.LOFTR_TCGEN05, defer=True)
+    ops.loftr_transformer(ok, ok, [params, params], ["self", "cross"], impl=ops.LOFTR_TCGEN05, defer=True)
+    assert ops.loftr_overflow_pending() and not ops.LoftrOverflow.pending
+    # the whole transformer with oversized tokens
+    o0, o1 = ops.loftr_transformer(big, ok, [params, params], ["self", "cross"], impl=ops.LOFTR_TCGEN05)
+    r0, r1 = ops.loftr_transformer(big, ok, [params, params], ["self", "cross"], impl=ops.LOFTR_SIMT)
+    assert torch.equal(o0, r0) and torch.equal(o1, r1)
+
+
+def test_loftr_tcgen05_whole_transformer_is_one_launch():
+    """All 2 x n_layers layer calls of LocalFeatureTransformer.forward run inside ONE persistent kernel (+ one weight-pack
+    launch per layer): a tile's tokens stay with its CTA from the first layer call to the last."""
+    params = [_random_layer(10 + i) for i in range(8)]
+    rng = np.random.default_rng(5)
+    f0 = cu(rng.standard_normal((1000, 21, 128)).astype(np.float32))
+    f1 = cu(np.maximum(rng.standard_normal((1000, 21, 128)), 0).astype(np.float32))
+    n0 = ops.launch_count()
+    o0, o1 = ops.loftr_transformer(f0, f1, params, ["self", "cross"] * 4, impl=ops.LOFTR_TCGEN05)
+    assert ops.launch_count() - n0 == 8 + 1
+    r0, r1 = ops.loftr_transformer(f0, f1, params, ["self", "cross"] * 4, impl=ops.LOFTR_SIMT)
+    np.testing.assert_allclose(o0.cpu().numpy(), r0.cpu().numpy(), rtol=1e-4, atol=5e-5)
+    np.testing.assert_allclose(o1.cpu().numpy(), r1.cpu().numpy(), rtol=1e-4, atol=5e-5)
+    again = ops.loftr_transformer(f0, f1, params, ["self", "cross"] * 4, impl=ops.LOFTR_TCGEN05)
+    assert torch.equal(again[0], o0) and torch.equal(again[1], o1)                       # deterministic
+
+
 @pytest.mark.parametrize("N", [1, 5, 6, 7, 149 * 6 + 1])
 def test_loftr_tcgen05_ragged_tiles_vs_simt(N):
     # tile = 6 points: partial tiles, one tile, many tiles per CTA (> 148 tiles)

@@ -17,6 +17,10 @@ for MODE in "$@"; do
       tail -15 $OUT/pytest_gpu.log
       timeout -s KILL 300 python -c 'import __graft_entry__ as g; g.smoke()' > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/status.txt
       tail -3 $OUT/smoke.log ;;
+    testsel:*)
+      SEL=$(echo $MODE | cut -d: -f2-)
+      timeout -s KILL 420 python -m pytest tests -m gpu -x -q -k "$SEL" > $OUT/pytest_sel.log 2>&1; echo "pytest-sel($SEL) rc=$?" | tee -a $OUT/status.txt
+      tail -15 $OUT/pytest_sel.log ;;
     bench)
       timeout -s KILL 900 python bench.py --steps 5 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" | tee -a $OUT/status.txt
       tail -c 4000 $OUT/bench.json; tail -5 $OUT/bench.err ;;
