@@ -37,12 +37,12 @@
 //
 // TMEM columns (512): D0 [0,128) q -> merge -> mlp.2 | D1 [128,256) k | D2 [256,384) v -> h[:,128:]
 //                     D3 [384,512) h[:, :128]
-// The x half of mlp.0 (cat([x, message]) @ W1^T, linear_attention.py:132) does not depend on the
-// attention: its first 128 outputs are issued right behind q/k/v, the second 128 as soon as the
-// epilogue has drained v out of D2 - both run under the attention epilogue.
-// Shared memory: X operand (hi[2] | lo[2] slabs of 128 rows x 128 B) 64 KB, resident x (later
-// relu(h[:,128:]), LayerNorm partials) | A operand 64 KB (src / msg / m / relu(h[:, :128]), also
-// the attention staging - one quarter = 2 heads at a time - and the output staging) | 3 weight stages of 32 KB.
+// Shared memory: X operand (hi[2] | lo[2] slabs of 128 rows x 128 B) 64 KB: x for q/k/v, then the attention staging (one
+// quarter = 2 heads at a time), then x again (re-read from L2 while the merge projection runs) for its half of mlp.0, then
+// relu(h[:,128:]) | A operand 64 KB: src (cross), then the message - written by the attention warps quarter by quarter, never
+// held in registers -, m, relu(h[:, :128]) and the output staging | 3 weight stages of 32 KB | LayerNorm partials 2 KB.
+// The x half of mlp.0 (cat([x, message]) @ W1^T, linear_attention.py:132) does not depend on the attention: it is issued as
+// soon as x is back in X and runs under the merge read-back and LayerNorm 1.
 #include "common.cuh"
 #include <cuda_fp16.h>
 
@@ -61,7 +61,7 @@ constexpr int LAYER_PACK_BYTES = NCHUNK * CHUNK;               // 640 KB per lay
 constexpr int MAX_LAYERS = 16;
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = 64 + EPI_WARPS * 32;                   // warp 0 producer, warp 1 MMA, warps 2..17 epilogue
-constexpr int TAIL_BYTES = 128;                                // barriers + TMEM slot
+constexpr int TAIL_BYTES = 128 + 2048;                         // barriers + TMEM slot | LayerNorm partials (128 rows x 4 quarters)
 constexpr int SMEM_BYTES = 2 * OPER_BYTES + NSTAGE * CHUNK + TAIL_BYTES;   // 229504 of 232448; base must be 1024-aligned
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t D0 = 0, D1 = 128, D2 = 256, D3 = 384;
@@ -156,7 +156,7 @@ __device__ __forceinline__ uint32_t sw128(int row, int seg) {
 // fp16-range guard: the hi/lo split needs |a| <= 65504 (the fp32 reference has no such limit).  Every operand value passes
 // through split2, which records a violation (or a NaN) in `g_bad`; the kernel raises the caller's overflow flag and the host
 // re-runs the call on the fp32 SIMT kernels (rcnet/linear_attention.py).  One FSETP per value, folded into the compare chain.
-#define RANGE_CHECK(a, b) bad = bad || !(fabsf(a) <= 65504.0f) || !(fabsf(b) <= 65504.0f)
+#define RANGE_CHECK(a, b) bad = fmaxf(bad, fmaxf(fabsf(a), fabsf(b)))            /* running max |value|: one FMNMX each */
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
     const __half2 h = __floats2half2_rn(a, b);
     const float2 f = __half22float2(h);
@@ -165,7 +165,7 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 // split 8 consecutive K elements (col % 8 == 0) of row `row` into the hi / lo slabs of the operand at `base`
-__device__ __forceinline__ void split_store8(uint8_t* base, int row, int col, float4 a, float4 b, bool& bad) {
+__device__ __forceinline__ void split_store8(uint8_t* base, int row, int col, float4 a, float4 b, float& bad) {
     const uint32_t off = (uint32_t)(col >> 6) * SLAB + sw128(row, (col & 63) >> 3);
     RANGE_CHECK(a.x, a.y); RANGE_CHECK(a.z, a.w); RANGE_CHECK(b.x, b.y); RANGE_CHECK(b.z, b.w);
     uint4 hi, lo;
@@ -176,7 +176,7 @@ __device__ __forceinline__ void split_store8(uint8_t* base, int row, int col, fl
 }
 
 // coalesced: epilogue warp `ew` (0..15) loads rows ew*8.. of a (rows x 128) fp32 tile and splits them into the operand
-__device__ __forceinline__ void load_tile_to_oper(uint8_t* base, const float* g, int valid_rows, int ew, int lane, bool& bad) {
+__device__ __forceinline__ void load_tile_to_oper(uint8_t* base, const float* g, int valid_rows, int ew, int lane, float& bad) {
     float4 v[8];
     const int c8 = (lane & 15) * 8;
 #pragma unroll
@@ -209,13 +209,14 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 // quarter = 2 heads), rows 80 bytes apart so that the 8 rows of an ldmatrix tile (and the 8 lanes of a 16-byte store phase) fall
 // into distinct 16-byte bank groups
 constexpr int SROW = 80, SARR = 128 * SROW;
-static_assert(6 * SARR <= OPER_BYTES, "attention staging must fit the A operand");
+static_assert(6 * SARR <= OPER_BYTES, "attention staging must fit the X operand");
 
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x + 1.0f : __expf(x); }   // elu(x) + 1 (SFU exp2, ~2 ulp)
 __device__ __forceinline__ float acc_f(uint32_t r) { return __uint_as_float(r) * W_UNSCALE; }  // accumulator read-back
 
 // LayerNorm statistics of a 128-wide row held as 4 x 32 values by the four threads (column quarters) of the row:
-// partial sums go through shared memory and are added in a fixed order, so all four threads get identical bits.
+// partial sums go through shared memory (one 2 KB buffer, reused for the second pass) and are added in a fixed order, so
+// all four threads get identical bits.
 __device__ __forceinline__ void row_stats(const float (&v)[32], int row, int colq, float* red, float eps, float& mean, float& rstd) {
     float s = 0.f;
 #pragma unroll
@@ -226,9 +227,10 @@ __device__ __forceinline__ void row_stats(const float (&v)[32], int row, int col
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
-    red[512 + colq * 128 + row] = q;
+    epi_bar();                                           // every thread has read the sums
+    red[colq * 128 + row] = q;
     epi_bar();
-    rstd = 1.0f / sqrtf(((red[512 + row] + red[640 + row]) + (red[768 + row] + red[896 + row])) * (1.0f / CH) + eps);
+    rstd = 1.0f / sqrtf(((red[row] + red[128 + row]) + (red[256 + row] + red[384 + row])) * (1.0f / CH) + eps);
 }
 
 // signal "operand written (and my TMEM reads done)" to the MMA warp
@@ -273,7 +275,7 @@ loftr_layer_tc_kernel(const LayerArgs P) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
     const uint32_t bfull = smem_u32(bars), bempty = smem_u32(bars + NSTAGE);
     const uint32_t a_ready = smem_u32(bars + 2 * NSTAGE), d_ready = smem_u32(bars + 2 * NSTAGE + 1);
-    const uint32_t v_free = smem_u32(bars + 2 * NSTAGE + 2);
+    const uint32_t x_ready = smem_u32(bars + 2 * NSTAGE + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool tr_on = blockIdx.x == 0 || blockIdx.x == gridDim.x / 2;
@@ -283,7 +285,7 @@ loftr_layer_tc_kernel(const LayerArgs P) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(bfull + 8 * s, 1); mbar_init(bempty + 8 * s, 1); }
         mbar_init(a_ready, EPI_WARPS * 32);
         mbar_init(d_ready, 1);
-        mbar_init(v_free, EPI_WARPS * 32);
+        mbar_init(x_ready, EPI_WARPS * 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -344,7 +346,7 @@ loftr_layer_tc_kernel(const LayerArgs P) {
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x)
             for (int ci = 0; ci < P.n_calls; ++ci) {
                 const uint32_t kv_src = P.call[ci].is_self ? xo : ao;
-                // seg 0: q, k, v (-> attention can start), then mlp.0[: C, :C] on x
+                // seg 0: q, k, v (-> the attention can start)
                 TRACE_M(0);
                 mbar_wait(a_ready, aph & 1); ++aph;
                 tc_fence_after();
@@ -352,23 +354,23 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                 issue_block(xo, D0, 0, 0);
                 issue_block(kv_src, D1, 0, 0);
                 issue_block(kv_src, D2, 0, d_ready);
-                issue_block(xo, D3, 0, 0);
                 TRACE_M(2);
                 TRACE_W(3);
-                // seg 1: v drained from D2 -> mlp.0[C :, :C] on x
+                // seg 1: merge(msg)
                 TRACE_M(4);
-                mbar_wait(v_free, vph & 1); ++vph;
-                tc_fence_after();
-                TRACE_M(5); wsum = 0;
-                issue_block(xo, D2, 0, 0);
-                TRACE_M(6);
-                TRACE_W(7);
-                // seg 2: merge(msg)
-                TRACE_M(8);
                 mbar_wait(a_ready, aph & 1); ++aph;
                 tc_fence_after();
-                TRACE_M(9); wsum = 0;
+                TRACE_M(5); wsum = 0;
                 issue_block(ao, D0, 0, d_ready);
+                TRACE_M(6);
+                TRACE_W(7);
+                // seg 2: x is back in X -> its half of mlp.0 (runs under the merge read-back and LayerNorm 1)
+                TRACE_M(8);
+                mbar_wait(x_ready, vph & 1); ++vph;
+                tc_fence_after();
+                TRACE_M(9); wsum = 0;
+                issue_block(xo, D3, 0, 0);
+                issue_block(xo, D2, 0, 0);
                 TRACE_M(10);
                 TRACE_W(11);
                 // seg 3: mlp.0[:, C:] on m, accumulated onto the x halves
@@ -401,11 +403,11 @@ loftr_layer_tc_kernel(const LayerArgs P) {
         const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
         uint32_t dph = 0;
         float* stage_f = reinterpret_cast<float*>(a_base);
-        float* red = reinterpret_cast<float*>(x_base);   // LayerNorm partials (X is dead whenever a LayerNorm runs)
+        float* red = reinterpret_cast<float*>(bars) + 32;  // LayerNorm partials: 2 KB behind the barriers / TMEM slot
 
-        bool bad = false;                                // an operand value outside the fp16 range (RANGE_CHECK)
+        float bad = 0.f;                                 // running max |operand value| of the rows that exist (RANGE_CHECK)
         const int g8 = lane >> 2, t4 = lane & 3, r8 = lane & 7, tl = lane >> 3;      // mma.sync / ldmatrix lane coordinates
-        const uint32_t stage_u32 = smem_u32(a_base);
+        const uint32_t stage_u32 = smem_u32(x_base);     // attention staging lives in X (dead between the q/k/v MMAs and the x reload)
 
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x)
         for (int ci = 0; ci < P.n_calls; ++ci) {
@@ -438,9 +440,8 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                 //     ldmatrix.trans; tokens 21..31 of the second k step are masked out of A) together with
                 //     Ksum[d] = sum_s K'[s][d] as an all-ones A;  the accumulator fragment of KV^T is exactly the B fragment
                 //     of  msg[l][v] = sum_d Q'[l][d] KV[d][v]  (rows = tokens, 2 m tiles), the normaliser Q' . Ksum is one
-                //     more n tile of the same product.  The message stays in registers (hi / lo halves) until the staging
-                //     is dead, then goes into the A operand for the merge projection.
-                uint32_t mh[4][6], ml[4][6];
+                //     more n tile of the same product.  Each message block goes straight into the A operand (hi / lo, swizzled)
+                //     for the merge projection - the staging lives in X, so nothing is held back in registers.
                 const int pair = ew, p = pair >> 1, hl = pair & 1;
                 const bool worker = ew < 12 && p < pts;
 #pragma unroll
@@ -452,9 +453,8 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                         TMEM_LD8(trow + D2 + hq * 32 + colq * 8, vr);
                         tmem_wait_ld();
                         if (hq == 1) TRACE_E(20);
-                        if (hq == 3) { tc_fence_before(); mbar_arrive(v_free); }    // D2 is free: mlp.0[C:, :C] may go
                         uint4 h4, l4;
-                        uint8_t* srow = a_base + row * SROW + colq * 16;
+                        uint8_t* srow = x_base + row * SROW + colq * 16;
                         float f[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) f[i] = elu1(acc_f(qr[i]));
@@ -524,14 +524,29 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                             mma16816(o1, ql, bh[1][0], bh[1][1]); mma16816(o1, qh, bl[1][0], bl[1][1]); mma16816(o1, qh, bh[1][0], bh[1][1]);
                             mma16816(dn, ql, sh[0], sh[1]); mma16816(dn, qh, sl[0], sl[1]); mma16816(dn, qh, sh[0], sh[1]);
                             const float z0 = __fdividef(1.0f, dn[0] + P.attn_eps), z1 = __fdividef(1.0f, dn[2] + P.attn_eps);
-                            if (mt == 0) {                       // token rows g8 and g8 + 8
+                            // message block -> A operand (hi / lo, swizzled), token rows l0 = 16 mt + g8 and l0 + 8, columns of head
+                            // 2 hq + hl: two values (v = 8 nv + 2 t4, + 1) per 4-byte store; the 8 rows x 4 lanes of a warp hit 32 banks
+                            const int l0 = mt * 16 + g8;
+                            const int colb = (2 * hq + hl) * 16 + 2 * t4;
+                            if (l0 < TOK) {
+                                const int rr = p * TOK + l0;
+                                uint32_t h0, l0w, h1, l1w;
                                 RANGE_CHECK(o0[0] * z0, o0[1] * z0); RANGE_CHECK(o1[0] * z0, o1[1] * z0);
+                                split2(o0[0] * z0, o0[1] * z0, h0, l0w); split2(o1[0] * z0, o1[1] * z0, h1, l1w);
+                                const uint32_t off0 = (uint32_t)(colb >> 6) * SLAB + sw128(rr, (colb & 63) >> 3) + (uint32_t)(colb & 7) * 2u;
+                                const uint32_t off1 = (uint32_t)(colb >> 6) * SLAB + sw128(rr, ((colb + 8) & 63) >> 3) + (uint32_t)(colb & 7) * 2u;
+                                *reinterpret_cast<uint32_t*>(a_base + off0) = h0; *reinterpret_cast<uint32_t*>(a_base + 2 * SLAB + off0) = l0w;
+                                *reinterpret_cast<uint32_t*>(a_base + off1) = h1; *reinterpret_cast<uint32_t*>(a_base + 2 * SLAB + off1) = l1w;
+                            }
+                            if (l0 + 8 < TOK) {
+                                const int rr = p * TOK + l0 + 8;
+                                uint32_t h0, l0w, h1, l1w;
                                 RANGE_CHECK(o0[2] * z1, o0[3] * z1); RANGE_CHECK(o1[2] * z1, o1[3] * z1);
-                                split2(o0[0] * z0, o0[1] * z0, mh[hq][0], ml[hq][0]); split2(o1[0] * z0, o1[1] * z0, mh[hq][1], ml[hq][1]);
-                                split2(o0[2] * z1, o0[3] * z1, mh[hq][2], ml[hq][2]); split2(o1[2] * z1, o1[3] * z1, mh[hq][3], ml[hq][3]);
-                            } else {                             // token row 16 + g8 (valid for g8 < 5); rows 24.. do not exist
-                                RANGE_CHECK(o0[0] * z0, o0[1] * z0); RANGE_CHECK(o1[0] * z0, o1[1] * z0);
-                                split2(o0[0] * z0, o0[1] * z0, mh[hq][4], ml[hq][4]); split2(o1[0] * z0, o1[1] * z0, mh[hq][5], ml[hq][5]);
+                                split2(o0[2] * z1, o0[3] * z1, h0, l0w); split2(o1[2] * z1, o1[3] * z1, h1, l1w);
+                                const uint32_t off0 = (uint32_t)(colb >> 6) * SLAB + sw128(rr, (colb & 63) >> 3) + (uint32_t)(colb & 7) * 2u;
+                                const uint32_t off1 = (uint32_t)(colb >> 6) * SLAB + sw128(rr, ((colb + 8) & 63) >> 3) + (uint32_t)(colb & 7) * 2u;
+                                *reinterpret_cast<uint32_t*>(a_base + off0) = h0; *reinterpret_cast<uint32_t*>(a_base + 2 * SLAB + off0) = l0w;
+                                *reinterpret_cast<uint32_t*>(a_base + off1) = h1; *reinterpret_cast<uint32_t*>(a_base + 2 * SLAB + off1) = l1w;
                             }
                         }
                     }
@@ -540,24 +555,12 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                     epi_bar();                           // (2) done reading: the next quarter may overwrite the staging
                     if (hq == 1) TRACE_E(25);
                 }
-                // staging dead (barrier above): msg -> A operand, rows of point p, columns of head 2 hq + hl
-                if (worker) {
-#pragma unroll
-                    for (int hq = 0; hq < 4; ++hq)
-#pragma unroll
-                        for (int sl6 = 0; sl6 < 6; ++sl6) {
-                            const int l = sl6 < 2 ? g8 : (sl6 < 4 ? g8 + 8 : g8 + 16);
-                            if (l < TOK) {
-                                const int rr = p * TOK + l, col = (2 * hq + hl) * 16 + (sl6 & 1) * 8 + 2 * t4;
-                                const uint32_t off = (uint32_t)(col >> 6) * SLAB + sw128(rr, (col & 63) >> 3) + (uint32_t)(col & 7) * 2u;
-                                *reinterpret_cast<uint32_t*>(a_base + off) = mh[hq][sl6];
-                                *reinterpret_cast<uint32_t*>(a_base + 2 * SLAB + off) = ml[hq][sl6];
-                            }
-                        }
-                }
             }
-            publish(a_ready);
+            publish(a_ready);                            // the message is complete in A: merge may go
             TRACE_E(4);
+            // ---- x back into X (the staging is dead: barrier above) for its half of mlp.0; L2 hit, runs under the merge MMAs
+            load_tile_to_oper(x_base, xg, valid_rows, ew, lane, bad);
+            publish(x_ready);
 
             // ---- E2: m = LayerNorm1(merge(msg)) -> A ----------------------------------------
             mbar_wait(d_ready, dph & 1); ++dph;          // merge done (and with it both x halves of mlp.0: X is dead)
@@ -572,6 +575,7 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                 for (int i = 0; i < 32; ++i) v[i] = acc_f(r[i]);
                 float mean, rstd;
                 row_stats(v, row, colq, red, P.ln_eps, mean, rstd);
+                float rbad = 0.f;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float y[8];
@@ -584,8 +588,11 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                         y[4 * e + 2] = (v[8 * j + 4 * e + 2] - mean) * rstd * g.z + b.z;
                         y[4 * e + 3] = (v[8 * j + 4 * e + 3] - mean) * rstd * g.w + b.w;
                     }
-                    split_store8(a_base, row, col0 + j * 8, make_float4(y[0], y[1], y[2], y[3]), make_float4(y[4], y[5], y[6], y[7]), bad);
+                    split_store8(a_base, row, col0 + j * 8, make_float4(y[0], y[1], y[2], y[3]), make_float4(y[4], y[5], y[6], y[7]), rbad);
                 }
+                // rows beyond the tile's points (absent points of a ragged tile, the two pad rows) carry whatever the shared
+                // memory held: they never reach an output row and must not raise the range flag
+                if (row < valid_rows) bad = fmaxf(bad, rbad);
             }
             publish(a_ready);
             TRACE_E(6);
@@ -594,6 +601,7 @@ loftr_layer_tc_kernel(const LayerArgs P) {
             mbar_wait(d_ready, dph & 1); ++dph;
             tc_fence_after();
             TRACE_E(7);
+            float hbad = 0.f;
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 uint32_t hr[32];
@@ -606,8 +614,9 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                                  make_float4(fmaxf(acc_f(hr[8 * j]), 0.f), fmaxf(acc_f(hr[8 * j + 1]), 0.f),
                                              fmaxf(acc_f(hr[8 * j + 2]), 0.f), fmaxf(acc_f(hr[8 * j + 3]), 0.f)),
                                  make_float4(fmaxf(acc_f(hr[8 * j + 4]), 0.f), fmaxf(acc_f(hr[8 * j + 5]), 0.f),
-                                             fmaxf(acc_f(hr[8 * j + 6]), 0.f), fmaxf(acc_f(hr[8 * j + 7]), 0.f)), bad);
+                                             fmaxf(acc_f(hr[8 * j + 6]), 0.f), fmaxf(acc_f(hr[8 * j + 7]), 0.f)), hbad);
             }
+            if (row < valid_rows) bad = fmaxf(bad, hbad);
             publish(a_ready);
             TRACE_E(8);
 
@@ -652,7 +661,7 @@ loftr_layer_tc_kernel(const LayerArgs P) {
             TRACE_E(10);
             tc_fence_before();
         }
-        if (bad && P.overflow) atomicOr(P.overflow, 1);
+        if (!(bad <= 65504.0f) && P.overflow) atomicOr(P.overflow, 1);
     }
 
     tc_fence_before();
@@ -679,9 +688,9 @@ loftr_pack_weights_kernel(const PackArgs P) {
         case 0: W = P.wq; break;
         case 1: W = P.wk; break;
         case 2: W = P.wv; break;
-        case 3: W = P.w1; ld = 2 * CH; break;                    // mlp.0[:C, :C]   (x half of cat([x, message]))
-        case 4: W = P.w1; ld = 2 * CH; r0 = CH; break;           // mlp.0[C:, :C]
-        case 5: W = P.wm; break;
+        case 3: W = P.wm; break;
+        case 4: W = P.w1; ld = 2 * CH; break;                    // mlp.0[:C, :C]   (x half of cat([x, message]))
+        case 5: W = P.w1; ld = 2 * CH; r0 = CH; break;           // mlp.0[C:, :C]
         case 6: W = P.w1; ld = 2 * CH; c0 = CH; break;           // mlp.0[:C, C:]   (message half)
         case 7: W = P.w1; ld = 2 * CH; r0 = CH; c0 = CH; break;  // mlp.0[C:, C:]
         case 8: W = P.w2; ld = 2 * CH; break;                    // mlp.2[:, :C]
@@ -716,7 +725,7 @@ tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(128u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    bool bad = false;
+    float bad = 0.f;
     for (int c = 0; c < K; c += 8) {
         const float4* pa = reinterpret_cast<const float4*>(A + (size_t)row * K + c);
         const float4* pb = reinterpret_cast<const float4*>(B + (size_t)row * K + c);

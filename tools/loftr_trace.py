@@ -29,7 +29,8 @@ try:
     mhz = float(subprocess.check_output(["nvidia-smi", "--query-gpu=clocks.max.sm", "--format=csv,noheader,nounits"]).split()[0])
 except Exception:
     mhz = 1965.0
-E_NAMES = ["E0 start", "x (src) split done", "q/k/v ready", "attention half 0 done", "attention+msg split done", "merge ready",
+# round-2 kernel: seg 0 = q/k/v, seg 1 = merge, seg 2 = x half of mlp.0 (after the x reload), seg 3 = m half, seg 4 = mlp.2
+E_NAMES = ["E0 start", "x (src) split done", "q/k/v ready", "attention quarter 0 done", "attention done (msg in A)", "merge ready",
            "LN1 split done", "h ready", "relu(h) split done", "mlp2 ready", "LN2+store done"]
 for label, src in (("self", x), ("cross", s)):
     for _ in range(2):
@@ -56,7 +57,7 @@ for label, src in (("self", x), ("cross", s)):
             prev = e[k]
         q = e[20:26]
         if q[0]:
-            names = ["TMEM loads of q, k, v landed", "elu + staging stores", "barrier (all 16 warps staged)", "(2) KV + Ksum", "(3) Q.KV message", "barrier (staging free)"]
+            names = ["TMEM loads of q, k, v landed", "elu + hi/lo split + staging stores", "barrier (all 16 warps staged)", "KV^T + Ksum (mma.sync)", "Q.KV + normaliser + msg stores (mma.sync)", "barrier (staging free)"]
             print(" %s attention quarter 1 (us):  " % cta + "; ".join("%s %.2f" % (nm, (q[i] - (e[3] if i == 0 else q[i - 1])) / mhz) for i, nm in enumerate(names)))
         print(" %s MMA thread: segment [wait A, issue, of which waiting for weights]" % cta)
         for seg in range(5):
