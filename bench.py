@@ -408,7 +408,94 @@ def run_config1(args):
 
 
 def run_train(args):
-    raise SystemExit("bench.py --workload train: see riders_b200/train.py (configs[3]); not built into this checkout yet")
+    """BASELINE configs[3]: RC-Net training step (train_rcnet_zju path: 4 frames x 30 radar points per GPU, patch 240x100, masked
+    BCE, Adam) with the hand-written gather / LoFTR forward + backward kernels, bf16 autocast, and the gradient all-reduce over
+    NCCL at N GPUs.  value = training frames/s over all ranks (weak scaling: every rank has its own 4 frames); the all-reduce is
+    timed separately with CUDA events - it is the one collective that can limit this curve."""
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --workload train needs a CUDA device")
+    from riders_b200 import dist as rdist, ops, synth
+    from riders_b200.rcnet.rcnet_model import RCNetModel
+    from riders_b200.train import TrainStep
+    rank, world, local = rdist.init()
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    pin_rank_cores(local, world)
+    FR, KP = 4, 30                                            # train_rcnet_zju.py:28-30
+    bf16 = not args.strict_fp32
+    if args.strict_fp32:
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)                                      # identical initial weights on every rank (the all-reduce keeps them in step)
+    model = RCNetModel(device=torch.device("cpu"), **MODEL_ARGS)
+    model.device = device
+    model.to(device)
+    model.channels_last()
+    torch.backends.cudnn.benchmark = True
+    ts = TrainStep(model, bf16=bf16)
+    # synthetic batch: padded frames, pad-shifted points + boxes, lidar crops around every radar point (depth of a smooth scene)
+    rng = np.random.default_rng(1234 + rank)
+    frames = [synth.chain_frame(1000 * rank + i, KP, H, W, PATCH) for i in range(FR)]
+    img = np.stack([np.pad(f["image"], ((0, 0), (PATCH[0] // 2,) * 2, (PATCH[1] // 2,) * 2), mode="edge") for f in frames])
+    pts = np.concatenate([f["points"] for f in frames]).astype(np.float32)
+    gt = np.zeros((FR * KP, 1) + PATCH, np.float32)
+    for r in range(FR * KP):                                   # sparse lidar crop: 10 % of the pixels carry a depth near / far from z
+        keep = rng.uniform(size=PATCH) < 0.10
+        gt[r, 0] = np.where(keep, pts[r, 2] + rng.normal(0, 1.0, PATCH), 0).astype(np.float32).clip(0)
+    host = {"img": torch.from_numpy(img).pin_memory(), "pts": torch.from_numpy(pts).pin_memory(), "gt": torch.from_numpy(gt).pin_memory(),
+            "boxes": [torch.from_numpy(f["boxes"]).pin_memory() for f in frames]}
+    dev = {"img": host["img"].to(device).contiguous(memory_format=torch.channels_last), "pts": host["pts"].to(device),
+           "gt": host["gt"].to(device), "boxes": [b.to(device) for b in host["boxes"]]}
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        loss = ts.step(dev["img"], dev["pts"], dev["boxes"], dev["gt"])
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = ops.launch_count()
+    rdist.barrier(); torch.cuda.synchronize()
+    wall0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = ts.step(dev["img"], dev["pts"], dev["boxes"], dev["gt"], time_allreduce=True)
+    e1.record()
+    torch.cuda.synchronize(); rdist.barrier()
+    wall1 = time.time()
+    ms_total = rdist.max_over_ranks(e0.elapsed_time(e1))
+    launches = ops.launch_count() - launches0
+    ar_ms = sum(a.elapsed_time(b) for a, b in ts.allreduce_events) / max(len(ts.allreduce_events), 1) if ts.allreduce_events else 0.0
+    ar_ms = rdist.max_over_ranks(ar_ms)
+    clocks = sampler.stop(wall0, wall1) if sampler else None
+    # end to end: pinned host batch -> H2D -> step -> loss read on the host, every step
+    def e2e_step():
+        d = {"img": host["img"].to(device, non_blocking=True).contiguous(memory_format=torch.channels_last),
+             "pts": host["pts"].to(device, non_blocking=True), "gt": host["gt"].to(device, non_blocking=True),
+             "boxes": [b.to(device, non_blocking=True) for b in host["boxes"]]}
+        return float(ts.step(d["img"], d["pts"], d["boxes"], d["gt"]).item())
+    e2e_step()
+    rdist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        last = e2e_step()
+    torch.cuda.synchronize(); rdist.barrier()
+    e2e_ms = rdist.max_over_ranks((time.perf_counter() - t0) * 1e3)
+    h2d = sum(host[k].numel() * 4 for k in ("img", "pts", "gt")) + sum(b.numel() * 4 for b in host["boxes"])
+    n_param = sum(p.numel() for p in ts.params)
+    if rank == 0:
+        print(json.dumps({"metric": "RC-Net training frames/s @640x512 (configs[3]: 4 frames x 30 radar points per GPU)", "value": world * FR * args.steps / (ms_total * 1e-3),
+                          "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_total / args.steps,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "bf16 autocast (cuDNN convolutions, LoFTR tokens) / f32 master weights, loss, optimizer" if bf16 else "f32",
+                          "data": "synthetic",
+                          "config": {"workload": "configs[3] RC-Net training step (train_rcnet_zju path): forward with logits, masked BCE (pos_weight 2.5), "
+                                                 "backward, gradient all-reduce, Adam(2e-4)", "frames_per_gpu_per_step": FR, "radar_points_per_frame": KP,
+                                     "patch": list(PATCH), "parameters": n_param, "parallelism": "data parallel x%d, flat-bucket NCCL all-reduce of %.1f MB fp32 gradients" % (world, n_param * 4 / 1e6),
+                                     "l2": "activations of a step (GBs) >> 126 MB L2"},
+                          "clocks": clocks, "gpu_launches": int(launches), "loss": last,
+                          "allreduce": {"ms_per_step": ar_ms, "bytes": n_param * 4, "share_of_step": ar_ms / (ms_total / args.steps) if world > 1 else 0.0},
+                          "e2e": {"value": world * FR * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4}}), flush=True)
+    rdist.shutdown()
+    return 0
 
 
 def workload_config(n_gpus, note=None, frames_per_gpu=FRAMES_PER_GPU, total=None, align="st", strict=False):

@@ -127,6 +127,28 @@ int riders_loftr_layer_fwd(const float* x, const float* src, const riders_loftr_
                            float attn_eps, float ln_eps, int impl,
                            float* out, void* workspace, void* stream);
 
+/* A3, training path (BASELINE configs[3]; the reference differentiates this layer with torch autograd inside
+ * rcnet_main.train, RCNet/rcnet_main.py:342-358).
+ *   riders_loftr_layer_fwd_train: the same layer, keeping q, k, v, msg, merge output, m, pre-ReLU h and the mlp output in
+ *     `saved` (riders_loftr_saved_bytes, float32) for the backward.
+ *   riders_loftr_layer_bwd: given d_out, writes d_x (and d_src for a cross layer, x != src; for a self layer d_x carries both
+ *     paths and d_src is ignored) and ACCUMULATES the weight gradients into d_w (same struct, float32 buffers the caller zeroes).
+ *   dtype: RIDERS_DTYPE_F32 / RIDERS_DTYPE_BF16 for the token tensors crossing the ABI (x, src, out, d_out, d_x, d_src); weights,
+ *     weight gradients and `saved` are float32 (fp32 master weights, fp32 accumulation).  Deterministic (no atomics).
+ *   workspace: riders_loftr_train_workspace_bytes bytes, 256-byte aligned.                                                   */
+#define RIDERS_DTYPE_F32   0
+#define RIDERS_DTYPE_BF16  1
+size_t riders_loftr_saved_bytes(int N, int L, int S, int d_model);
+size_t riders_loftr_train_workspace_bytes(int N, int L, int S, int d_model);
+int riders_loftr_layer_fwd_train(const void* x, const void* src, const riders_loftr_weights* w,
+                                 int N, int L, int S, int d_model, int nhead, float attn_eps, float ln_eps, int dtype,
+                                 void* out, void* saved, void* workspace, void* stream);
+int riders_loftr_layer_bwd(const void* x, const void* src, const riders_loftr_weights* w, const void* saved,
+                           const void* d_out, int N, int L, int S, int d_model, int nhead,
+                           float attn_eps, float ln_eps, int dtype,
+                           void* d_x, void* d_src, const riders_loftr_weights* d_w,
+                           void* workspace, void* stream);
+
 /* A4  LocalFeatureTransformer.forward   RCNet/linear_attention.py:159-184
  *     layer_kind[i]: 0 = 'self' (f0=layer(f0,f0); f1=layer(f1,f1)), 1 = 'cross'
  *     (f0=layer(f0,f1); f1=layer(f1,f0_new)).  feat0 (N,L,C), feat1 (N,S,C) are not modified;

@@ -14,6 +14,7 @@ RIDERS_OK = 0
 RIDERS_EINVAL, RIDERS_ECUDA, RIDERS_ENODEVICE, RIDERS_EQHULL, RIDERS_EINTERNAL = -1, -2, -3, -4, -5
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 LOFTR_SIMT, LOFTR_TCGEN05 = 0, 1
+DTYPE_F32, DTYPE_BF16 = 0, 1
 MAX_LEVELS = 8
 
 vp, ci, cf, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
@@ -39,6 +40,11 @@ SIGNATURES = {
     "riders_loftr_layer_fwd": (ci, [vp, vp, C.POINTER(LoftrWeights), ci, ci, ci, ci, ci, cf, cf, ci, vp, vp, vp]),
     "riders_loftr_transformer_fwd": (ci, [vp, vp, C.POINTER(LoftrWeights), C.POINTER(ci), ci,
                                           ci, ci, ci, ci, ci, cf, cf, ci, vp, vp, vp, vp]),
+    "riders_loftr_saved_bytes": (sz, [ci, ci, ci, ci]),
+    "riders_loftr_train_workspace_bytes": (sz, [ci, ci, ci, ci]),
+    "riders_loftr_layer_fwd_train": (ci, [vp, vp, C.POINTER(LoftrWeights), ci, ci, ci, ci, ci, cf, cf, ci, vp, vp, vp, vp]),
+    "riders_loftr_layer_bwd": (ci, [vp, vp, C.POINTER(LoftrWeights), vp, vp, ci, ci, ci, ci, ci, cf, cf, ci,
+                                    vp, vp, C.POINTER(LoftrWeights), vp, vp]),
     "riders_confidence_reduce": (ci, [vp, ci, vp, vp, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp]),
     "riders_lsq_workspace_bytes": (sz, [ci, ci, ci]),
     "riders_lsq_align": (ci, [vp, vp, vp, ci, ci, ci, vp, vp, vp, cf, cf, ci, vp, vp]),

@@ -275,7 +275,7 @@ loftr_layer_tc_kernel(const LayerArgs P) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
     const uint32_t bfull = smem_u32(bars), bempty = smem_u32(bars + NSTAGE);
     const uint32_t a_ready = smem_u32(bars + 2 * NSTAGE), d_ready = smem_u32(bars + 2 * NSTAGE + 1);
-    const uint32_t x_ready = smem_u32(bars + 2 * NSTAGE + 2);
+    const uint32_t x_ready = smem_u32(bars + 2 * NSTAGE + 2), h_ready = smem_u32(bars + 2 * NSTAGE + 3);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool tr_on = blockIdx.x == 0 || blockIdx.x == gridDim.x / 2;
@@ -286,6 +286,7 @@ loftr_layer_tc_kernel(const LayerArgs P) {
         mbar_init(a_ready, EPI_WARPS * 32);
         mbar_init(d_ready, 1);
         mbar_init(x_ready, EPI_WARPS * 32);
+        mbar_init(h_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -378,17 +379,17 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                 mbar_wait(a_ready, aph & 1); ++aph;
                 tc_fence_after();
                 TRACE_M(13); wsum = 0;
-                issue_block(ao, D3, 1, 0);
+                issue_block(ao, D3, 1, h_ready);             // h[:, :C] complete (own barrier): its ReLU / re-split runs under the next block
                 issue_block(ao, D2, 1, d_ready);
                 TRACE_M(14);
                 TRACE_W(15);
-                // seg 4: mlp.2 on relu(h): [:, :C] from A, [:, C:] from X
+                // seg 4: mlp.2 on relu(h): [:, :C] from X, [:, C:] from A
                 TRACE_M(16);
                 mbar_wait(a_ready, aph & 1); ++aph;
                 tc_fence_after();
                 TRACE_M(17); wsum = 0;
-                issue_block(ao, D0, 0, 0);
-                issue_block(xo, D0, 1, d_ready);
+                issue_block(xo, D0, 0, 0);
+                issue_block(ao, D0, 1, d_ready);
                 TRACE_M(18);
                 TRACE_W(19);
             }
@@ -401,7 +402,7 @@ loftr_layer_tc_kernel(const LayerArgs P) {
         const int row = quad * 32 + lane;
         const int col0 = colq * 32;
         const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
-        uint32_t dph = 0;
+        uint32_t dph = 0, hph = 0;
         float* stage_f = reinterpret_cast<float*>(a_base);
         float* red = reinterpret_cast<float*>(bars) + 32;  // LayerNorm partials: 2 KB behind the barriers / TMEM slot
 
@@ -597,17 +598,18 @@ loftr_layer_tc_kernel(const LayerArgs P) {
             publish(a_ready);
             TRACE_E(6);
 
-            // ---- E3: relu(h[:, :C]) -> A, relu(h[:, C:]) -> X for mlp.2 -----------------------
-            mbar_wait(d_ready, dph & 1); ++dph;
-            tc_fence_after();
-            TRACE_E(7);
+            // ---- E3: relu(h[:, :C]) -> X (x is dead: its MMAs precede the m half in issue order), then relu(h[:, C:]) -> A (m dead)
             float hbad = 0.f;
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
+                // hf = 0: h[:, :C] in D3 (the second block still reads m from A); hf = 1: h[:, C:] in D2
+                if (hf == 0) { mbar_wait(h_ready, hph & 1); ++hph; } else { mbar_wait(d_ready, dph & 1); ++dph; }
+                tc_fence_after();
+                if (hf == 0) TRACE_E(7);
                 uint32_t hr[32];
                 TMEM_LD32(trow + (hf ? D2 : D3) + col0, hr);
                 tmem_wait_ld();
-                uint8_t* dst = hf ? x_base : a_base;
+                uint8_t* dst = hf ? a_base : x_base;
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     split_store8(dst, row, col0 + j * 8,

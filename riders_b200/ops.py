@@ -666,6 +666,63 @@ def loftr_overflow_pending():
     return any(guard.overflowed() for guard, _ in pending)
 
 
+_GRAD_FIELDS = ("wq", "wk", "wv", "wm", "w1", "w2", "ln1_g", "ln1_b", "ln2_g", "ln2_b")
+
+
+class LoftrLayerFunction(torch.autograd.Function):
+    """LoFTREncoderLayer with gradients (RC-Net training, RCNet/rcnet_main.py:342-358): forward = riders_loftr_layer_fwd_train
+    (keeps q, k, v, msg, the two pre-LayerNorm tensors, m and the pre-ReLU hidden layer), backward = riders_loftr_layer_bwd
+    (hand-derived, deterministic).  Tokens are float32 or bfloat16 (``x.dtype``), the ten parameters float32 master weights."""
+
+    @staticmethod
+    def forward(ctx, x, source, nhead, attn_eps, ln_eps, *params):
+        _need_cuda(x, source, *params)
+        dt = _lib.DTYPE_BF16 if x.dtype == torch.bfloat16 else _lib.DTYPE_F32
+        tdt = torch.bfloat16 if dt == _lib.DTYPE_BF16 else torch.float32
+        same = source is x
+        x = x.to(tdt).contiguous()
+        source = x if same else source.to(tdt).contiguous()
+        params = tuple(_f32c(p.detach()) for p in params)
+        N, Lx, Cm = x.shape
+        S = source.shape[1]
+        L = _lib.lib()
+        w = _lib.LoftrWeights(*[p.data_ptr() for p in params])
+        saved = torch.empty(L.riders_loftr_saved_bytes(N, Lx, S, Cm), dtype=torch.uint8, device=x.device)
+        ws = torch.empty(L.riders_loftr_train_workspace_bytes(N, Lx, S, Cm), dtype=torch.uint8, device=x.device)
+        out = torch.empty_like(x)
+        rc = L.riders_loftr_layer_fwd_train(_ptr(x), _ptr(source), C.byref(w), N, Lx, S, Cm, int(nhead), float(attn_eps),
+                                            float(ln_eps), dt, _ptr(out), _ptr(saved), _ptr(ws), _stream())
+        _lib.check(rc, "riders_loftr_layer_fwd_train")
+        ctx.save_for_backward(x, source, saved, *params)
+        ctx.meta = (int(nhead), float(attn_eps), float(ln_eps), dt, same)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, source, saved = ctx.saved_tensors[:3]
+        params = ctx.saved_tensors[3:]
+        nhead, attn_eps, ln_eps, dt, same = ctx.meta
+        N, Lx, Cm = x.shape
+        S = source.shape[1]
+        L = _lib.lib()
+        d_out = d_out.to(x.dtype).contiguous()
+        w = _lib.LoftrWeights(*[p.data_ptr() for p in params])
+        grads = [torch.zeros_like(p) for p in params]
+        dw = _lib.LoftrWeights(*[g.data_ptr() for g in grads])
+        d_x = torch.empty_like(x)
+        d_s = None if same else torch.empty_like(source)
+        ws = torch.empty(L.riders_loftr_train_workspace_bytes(N, Lx, S, Cm), dtype=torch.uint8, device=x.device)
+        rc = L.riders_loftr_layer_bwd(_ptr(x), _ptr(x if same else source), C.byref(w), _ptr(saved), _ptr(d_out), N, Lx, S, Cm, nhead,
+                                      attn_eps, ln_eps, dt, _ptr(d_x), _ptr(d_s), C.byref(dw), _ptr(ws), _stream())
+        _lib.check(rc, "riders_loftr_layer_bwd")
+        return (d_x, d_s, None, None, None) + tuple(grads)
+
+
+def loftr_layer_autograd(x, source, params, nhead=8, attn_eps=1e-6, ln_eps=1e-5):
+    """Differentiable LoFTREncoderLayer.forward; ``params`` = dict with the reference parameter names."""
+    return LoftrLayerFunction.apply(x, source, nhead, attn_eps, ln_eps, *[params[k] for k in _WEIGHT_ORDER])
+
+
 # --------------------------------------------------------------------------------------------
 # A5 reduce
 # --------------------------------------------------------------------------------------------

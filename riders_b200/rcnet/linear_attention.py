@@ -88,21 +88,16 @@ class LoFTREncoderLayer(nn.Module):
         return ops.loftr_impl_available(impl, x.shape[2], self.nhead, x.shape[1])
 
     def _forward_autograd(self, x, source):
-        """Training path (rcnet_main.py:342-358 needs gradients): the layer as differentiable torch ops on the
-        device, statement for statement linear_attention.py:112-135 / 18-45.  The fused kernels are inference-only."""
-        bs = x.size(0)
-        q = self.q_proj(x).view(bs, -1, self.nhead, self.dim)
-        k = self.k_proj(source).view(bs, -1, self.nhead, self.dim)
-        v = self.v_proj(source).view(bs, -1, self.nhead, self.dim)
-        Q, K = torch.nn.functional.elu(q) + 1, torch.nn.functional.elu(k) + 1
-        v_length = v.size(1)
-        v = v / v_length
-        KV = torch.einsum("nshd,nshv->nhdv", K, v)
-        Z = 1 / (torch.einsum("nlhd,nhd->nlh", Q, K.sum(dim=1)) + self.attention.eps)
-        message = (torch.einsum("nlhd,nhdv,nlh->nlhv", Q, KV, Z) * v_length).contiguous()
-        message = self.norm1(self.merge(message.view(bs, -1, self.nhead * self.dim)))
-        message = self.norm2(self.mlp(torch.cat([x, message], dim=2)))
-        return x + message
+        """Training path (rcnet_main.py:342-358 needs gradients): the hand-written forward / backward kernels behind
+        ``ops.LoftrLayerFunction`` (riders_loftr_layer_fwd_train / riders_loftr_layer_bwd).  Under bf16 autocast the
+        tokens are bfloat16, the parameters stay the float32 master weights."""
+        if torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16:
+            same = source is x
+            x = x.to(torch.bfloat16)
+            source = x if same else source.to(torch.bfloat16)
+        elif x.dtype != source.dtype:
+            source = source.to(x.dtype)
+        return ops.loftr_layer_autograd(x, source, self.kernel_params(), self.nhead, self.attention.eps, self.norm1.eps)
 
     def forward(self, x, source, x_mask=None, source_mask=None):
         """x [N,L,C], source [N,S,C] -> [N,L,C]."""

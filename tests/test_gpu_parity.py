@@ -988,6 +988,63 @@ def test_training_step_gradients_match_the_reference_path():
     assert checked > 50
 
 
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("cross", [False, True])
+def test_loftr_layer_backward_kernels_match_autograd(dtype, cross):
+    """riders_loftr_layer_fwd_train / riders_loftr_layer_bwd (ops.LoftrLayerFunction) at RC-Net's real layer shape (d_model
+    128, 8 heads, 21 tokens) against torch autograd through the reference formulation of the layer (oracle.rcnet_ref
+    .loftr_layer_torch, fp32): output, d_x, d_source and the gradients of all ten parameters.  float32 tokens: 2e-4 of each
+    gradient's scale (different summation order only); bfloat16 tokens (fp32 master weights and accumulation): 3e-2, the
+    bf16 mantissa (2^-8) through ~10 dependent roundings."""
+    from riders_b200.rcnet.linear_attention import LoFTREncoderLayer
+    torch.manual_seed(7)
+    N = 37
+    layer = LoFTREncoderLayer(128, 8).to(DEV)
+    for p_ in layer.parameters():
+        if p_.dim() > 1:
+            torch.nn.init.xavier_uniform_(p_)
+    with torch.no_grad():
+        layer.norm1.weight.uniform_(0.5, 1.5); layer.norm1.bias.uniform_(-0.2, 0.2)
+        layer.norm2.weight.uniform_(0.5, 1.5); layer.norm2.bias.uniform_(-0.2, 0.2)
+    x0 = torch.randn(N, 21, 128, device=DEV)
+    s0 = torch.randn(N, 21, 128, device=DEV) if cross else None
+    g = torch.randn(N, 21, 128, device=DEV)
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    # reference: fp32 autograd on the (dtype-rounded) inputs
+    xr = x0.to(tdt).float().requires_grad_(True)
+    sr = s0.to(tdt).float().requires_grad_(True) if cross else xr
+    ref = rcnet_ref.loftr_layer_torch(layer, xr, sr)
+    ref.backward(g.to(tdt).float())
+    ref_grads = {n: p_.grad.clone() for n, p_ in layer.named_parameters()}
+    ref_dx, ref_ds = xr.grad.clone(), (sr.grad.clone() if cross else None)
+    layer.zero_grad()
+    # kernels
+    xk = x0.to(tdt).requires_grad_(True)
+    sk = s0.to(tdt).requires_grad_(True) if cross else xk
+    out = ops.loftr_layer_autograd(xk, sk, layer.kernel_params(), 8, layer.attention.eps, layer.norm1.eps)
+    assert out.dtype == tdt
+    out.backward(g.to(tdt))
+    tol = 3e-2 if dtype == "bf16" else 2e-4
+
+    def close(a, b, name):
+        scale = float(b.abs().max()) + 1e-12
+        assert float((a.float() - b).abs().max()) <= tol * scale, (name, float((a.float() - b).abs().max()) / scale)
+
+    close(out.detach(), ref.detach(), "out")
+    close(xk.grad, ref_dx, "d_x")
+    if cross:
+        close(sk.grad, ref_ds, "d_source")
+    for n, p_ in layer.named_parameters():
+        assert p_.grad is not None and p_.grad.dtype == torch.float32, n
+        close(p_.grad, ref_grads[n], n)
+    # the module itself takes this path whenever gradients are required, and it is deterministic
+    layer.zero_grad()
+    x2 = x0.to(tdt).requires_grad_(True)
+    o2 = layer(x2, s0.to(tdt) if cross else x2)
+    o2.backward(g.to(tdt))
+    assert torch.equal(o2, out) and torch.equal(x2.grad, xk.grad)
+
+
 def test_gather_into_placed_concat_buffers_is_bit_exact_and_never_copied():
     """Skips gathered straight into the decoder's concat buffers (riders_roi_gather_fwd_placed) + the d2s / bias-leaky
     kernels that fill the leading channels == dense gather followed by the concat kernels, bit for bit."""

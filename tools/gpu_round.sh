@@ -39,7 +39,7 @@ for MODE in "$@"; do
       timeout -s KILL 900 python bench.py --impl eager --steps 8 --warmup 2 > $OUT/bench_eager.json 2> $OUT/bench_eager.err; echo "eager rc=$?" | tee -a $OUT/status.txt
       cat $OUT/bench_eager.json; tail -5 $OUT/bench_eager.err ;;
     train)
-      timeout -s KILL 900 python bench.py --workload train --steps 5 --warmup 3 > $OUT/bench_train.json 2> $OUT/bench_train.err; echo "train rc=$?" | tee -a $OUT/status.txt
+      timeout -s KILL 900 python bench.py --workload train --steps 10 --warmup 3 > $OUT/bench_train.json 2> $OUT/bench_train.err; echo "train rc=$?" | tee -a $OUT/status.txt
       cat $OUT/bench_train.json; tail -5 $OUT/bench_train.err ;;
     benchnotail)
       RIDERS_FUSED_TAIL=0 timeout -s KILL 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_notail.json 2> $OUT/bench_notail.err; echo "bench-notail rc=$?" | tee -a $OUT/status.txt
