@@ -679,7 +679,9 @@ class LoftrLayerFunction(torch.autograd.Function):
         _need_cuda(x, source, *params)
         dt = _lib.DTYPE_BF16 if x.dtype == torch.bfloat16 else _lib.DTYPE_F32
         tdt = torch.bfloat16 if dt == _lib.DTYPE_BF16 else torch.float32
-        same = source is x
+        # a self layer passes the same tensor twice; autograd hands the Function two distinct wrappers of it, so compare storage
+        same = source is x or (source.data_ptr() == x.data_ptr() and source.shape == x.shape and source.stride() == x.stride()
+                               and source.dtype == x.dtype)
         x = x.to(tdt).contiguous()
         source = x if same else source.to(tdt).contiguous()
         params = tuple(_f32c(p.detach()) for p in params)
