@@ -1011,16 +1011,16 @@ def test_loftr_layer_backward_kernels_match_autograd(dtype, cross):
     g = torch.randn(N, 21, 128, device=DEV)
     tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
     # reference: fp32 autograd on the (dtype-rounded) inputs
-    xr = x0.to(tdt).float().requires_grad_(True)
-    sr = s0.to(tdt).float().requires_grad_(True) if cross else xr
+    xr = x0.to(tdt).float().clone().requires_grad_(True)          # clone: .to() of a float32 tensor is the tensor itself
+    sr = s0.to(tdt).float().clone().requires_grad_(True) if cross else xr
     ref = rcnet_ref.loftr_layer_torch(layer, xr, sr)
     ref.backward(g.to(tdt).float())
     ref_grads = {n: p_.grad.clone() for n, p_ in layer.named_parameters()}
     ref_dx, ref_ds = xr.grad.clone(), (sr.grad.clone() if cross else None)
     layer.zero_grad()
     # kernels
-    xk = x0.to(tdt).requires_grad_(True)
-    sk = s0.to(tdt).requires_grad_(True) if cross else xk
+    xk = x0.to(tdt).clone().requires_grad_(True)
+    sk = s0.to(tdt).clone().requires_grad_(True) if cross else xk
     out = ops.loftr_layer_autograd(xk, sk, layer.kernel_params(), 8, layer.attention.eps, layer.norm1.eps)
     assert out.dtype == tdt
     out.backward(g.to(tdt))
@@ -1039,7 +1039,7 @@ def test_loftr_layer_backward_kernels_match_autograd(dtype, cross):
         close(p_.grad, ref_grads[n], n)
     # the module itself takes this path whenever gradients are required, and it is deterministic
     layer.zero_grad()
-    x2 = x0.to(tdt).requires_grad_(True)
+    x2 = x0.to(tdt).clone().requires_grad_(True)
     o2 = layer(x2, s0.to(tdt) if cross else x2)
     o2.backward(g.to(tdt))
     assert torch.equal(o2, out) and torch.equal(x2.grad, xk.grad)
