@@ -8,15 +8,16 @@
 //
 // HBM roofline: reads R*ph*pw*4 B of confidences + 12 B/point, writes 3 maps (12 B/pixel).
 //
-// Work decomposition: CTA = 32 x 32 pixel tile of one frame, 8 warps, each warp a 4-row x
-// 32-col strip, each thread 4 vertically stacked pixels (amortises the per-point address
-// math over 4 loads).  The CTA first compacts, in point order (so the float sums run in the
-// reference's k order and the first-max rule holds), the points whose crop overlaps the tile.
+// Work decomposition: CTA = TW x (8 * 32/TW * ROWS) pixel tile of one frame, 8 warps; a warp covers TW columns x 32/TW row
+// groups, each thread ROWS = 4 vertically stacked pixels (amortises the per-point address math over 4 loads).  TW = 32 is the
+// round-1 shape (32 x 32 tiles); TW = 16 (16 x 64 tiles, two row groups per warp) wastes fewer lanes on a 100-wide crop
+// that straddles the tiles ((100 + 16) / 100 = 1.16 lanes per useful lane instead of (100 + 32) / 100 = 1.32) and still reads
+// 64-byte row segments.  The CTA first compacts, in point order (so the float sums run in the reference's k order and the
+// first-max rule holds), the points whose crop overlaps the tile.
 #include "common.cuh"
 
 namespace riders {
 
-constexpr int TILE_W = 32;
 constexpr int CR_THREADS = 256;
 constexpr int CHUNK = 256;                 // candidate points examined per round
 constexpr int NC = 2;                      // candidates gathered per inner iteration (4 measured slower)
@@ -86,7 +87,7 @@ __device__ __forceinline__ void ld4_stream_if(const float* p, bool on, float (&v
 }
 
 // PW > 0: crop width fixed at compile time (RC-Net's 100): immediate row offsets, constant address math
-template <bool LOGITS, int ROWS, int PW>
+template <bool LOGITS, int ROWS, int PW, int TILE_W>
 __global__ void __launch_bounds__(CR_THREADS)
 confidence_reduce_kernel(const float* __restrict__ conf, const float* __restrict__ pts,
                          const int* __restrict__ frame_offsets,
@@ -94,7 +95,8 @@ confidence_reduce_kernel(const float* __restrict__ conf, const float* __restrict
                          float* __restrict__ depth, float* __restrict__ response,
                          int32_t* __restrict__ select) {
     const int pw = PW > 0 ? PW : pw_rt;
-    constexpr int TILE_H = (CR_THREADS / 32) * ROWS;
+    constexpr int GROUPS = 32 / TILE_W;                  // row groups per warp
+    constexpr int TILE_H = (CR_THREADS / 32) * GROUPS * ROWS;
     __shared__ Cand cand[CHUNK];
     __shared__ int warp_count[CR_THREADS / 32];
     __shared__ int n_cand;
@@ -105,8 +107,8 @@ confidence_reduce_kernel(const float* __restrict__ conf, const float* __restrict
     const int n_points = frame_offsets[frame + 1] - first_point;
     const size_t frame_px = (size_t)frame * H * W;
     const int tile_c = blockIdx.x * TILE_W, tile_r = blockIdx.y * TILE_H;
-    const int col = tile_c + lane;
-    const int row = tile_r + warp * ROWS;
+    const int col = tile_c + (lane % TILE_W);
+    const int row = tile_r + (warp * GROUPS + lane / TILE_W) * ROWS;
     const ptrdiff_t thr_off = (ptrdiff_t)row * pw + col;
 
     float best[ROWS], sc[ROWS], scz[ROWS];
@@ -151,11 +153,11 @@ confidence_reduce_kernel(const float* __restrict__ conf, const float* __restrict
             for (int u = 0; u < NC; ++u) {
                 const bool on = i + u < n;
                 q[u] = cand[on ? i + u : i];           // smem broadcast
-                const int i0 = row - q[u].r0;          // warp-uniform
+                const int i0 = row - q[u].r0;          // uniform per row group (per warp for TILE_W = 32)
                 const bool in_col = on && (unsigned)(col - q[u].c0) < (unsigned)pw;
                 const float* src = q[u].base + thr_off;
-                any[u] = on && i0 + ROWS > 0 && i0 < ph;
-                if (i0 >= 0 && i0 + ROWS <= ph) {      // the usual case: all ROWS rows inside the 240-row crop
+                any[u] = __any_sync(0xffffffffu, on && i0 + ROWS > 0 && i0 < ph);
+                if (__all_sync(0xffffffffu, i0 >= 0 && i0 + ROWS <= ph)) {      // the usual case: all rows inside the 240-row crop
                     if constexpr (PW > 0 && ROWS == 4) {
                         ld4_stream_if<LOGITS, PW>(src, in_col, v[u]);
                     } else {
@@ -170,7 +172,7 @@ confidence_reduce_kernel(const float* __restrict__ conf, const float* __restrict
             }
 #pragma unroll
             for (int u = 0; u < NC; ++u) {
-                if (!any[u]) continue;                 // warp-uniform: this warp's rows miss the crop
+                if (!any[u]) continue;                 // warp-uniform: none of this warp's rows meets the crop
 #pragma unroll
                 for (int m = 0; m < ROWS; ++m) {
                     const float x = conf_value<LOGITS>(v[u][m], thr);
@@ -197,16 +199,25 @@ confidence_reduce_kernel(const float* __restrict__ conf, const float* __restrict
 }
 
 static int g_reduce_rows = 4;
+static int g_reduce_tile_w = 16;
 void set_reduce_rows(int rows) { if (rows == 4 || rows == 8) g_reduce_rows = rows; }
+void set_reduce_tile_w(int w) { if (w == 16 || w == 32) g_reduce_tile_w = w; }
+
+template <bool LOGITS, int ROWS, int TW>
+static void launch_reduce_tw(const float* conf, const float* pts, const int* frame_offsets, int B, int H, int W, int ph, int pw,
+                             float thr, float* depth, float* response, int32_t* select, cudaStream_t st) {
+    dim3 grid(ceil_div(W, TW), ceil_div(H, (CR_THREADS / 32) * (32 / TW) * ROWS), B);
+    if (ROWS == 4 && pw == 100)                 // RC-Net's patch width (run_rcnet_zju.py:30)
+        confidence_reduce_kernel<LOGITS, ROWS, 100, TW><<<grid, CR_THREADS, 0, st>>>(conf, pts, frame_offsets, H, W, ph, pw, thr, depth, response, select);
+    else
+        confidence_reduce_kernel<LOGITS, ROWS, 0, TW><<<grid, CR_THREADS, 0, st>>>(conf, pts, frame_offsets, H, W, ph, pw, thr, depth, response, select);
+}
 
 template <bool LOGITS, int ROWS>
 static void launch_reduce(const float* conf, const float* pts, const int* frame_offsets, int B, int H, int W, int ph, int pw,
                           float thr, float* depth, float* response, int32_t* select, cudaStream_t st) {
-    dim3 grid(ceil_div(W, TILE_W), ceil_div(H, (CR_THREADS / 32) * ROWS), B);
-    if (ROWS == 4 && pw == 100)                 // RC-Net's patch width (run_rcnet_zju.py:30)
-        confidence_reduce_kernel<LOGITS, ROWS, 100><<<grid, CR_THREADS, 0, st>>>(conf, pts, frame_offsets, H, W, ph, pw, thr, depth, response, select);
-    else
-        confidence_reduce_kernel<LOGITS, ROWS, 0><<<grid, CR_THREADS, 0, st>>>(conf, pts, frame_offsets, H, W, ph, pw, thr, depth, response, select);
+    if (g_reduce_tile_w == 16 && ROWS == 4) launch_reduce_tw<LOGITS, ROWS, 16>(conf, pts, frame_offsets, B, H, W, ph, pw, thr, depth, response, select, st);
+    else launch_reduce_tw<LOGITS, ROWS, 32>(conf, pts, frame_offsets, B, H, W, ph, pw, thr, depth, response, select, st);
 }
 
 }  // namespace riders

@@ -47,6 +47,7 @@ extern "C" unsigned long long riders_launch_count(void) { return riders::g_launc
 extern "C" int riders_debug_set(const char* key, int value) {
     if (key && !strcmp(key, "gather_smem_kb")) { riders::set_gather_smem_budget(value); return RIDERS_OK; }
     if (key && !strcmp(key, "lsq_fused")) { riders::set_lsq_mode(value); return RIDERS_OK; }
+    if (key && !strcmp(key, "reduce_tile_w")) { riders::set_reduce_tile_w(value); return RIDERS_OK; }
     if (key && !strcmp(key, "reduce_rows")) { riders::set_reduce_rows(value); return RIDERS_OK; }
     riders::set_error("debug_set: unknown key '%s'", key ? key : "(null)");
     return RIDERS_EINVAL;

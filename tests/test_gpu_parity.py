@@ -126,6 +126,39 @@ def test_reduce_matches_golden(golden, tag):
     assert np.array_equal(sel, s0)                                            # and first-max everywhere else
 
 
+@pytest.mark.parametrize("K", [128, 4096])
+def test_stress_config_1280x1024_reduce_and_gather_vs_oracle(K):
+    """BASELINE configs[4] (1280x1024 frames, 128..4096 radar points): the reduce against the oracle (response and select
+    exact, depth 1e-5) and the five-level gather against the torchvision rules on the 1280x1024 pyramid (bit-exact), at the
+    two ends of the density sweep tools/stress_sweep.py times."""
+    H, W, patch = 1024, 1280, (240, 100)
+    pts, boxes = synth.radar_points(K, K, H, W, patch)
+    rng = np.random.default_rng(K)
+    conf = (1.0 / (1.0 + np.exp(-rng.normal(-1.5, 2.0, (K,) + patch)))).astype(np.float32)
+    d, r, s = ops.confidence_reduce(cu(conf), cu(pts), [0, K], H, W, 0.1)
+    d0, r0, s0 = cr.confidence_reduce_ref(conf, pts, H, W, 0.1)
+    assert np.array_equal(r[0].cpu().numpy(), r0) and np.array_equal(s[0].cpu().numpy(), s0)
+    np.testing.assert_allclose(d[0].cpu().numpy(), d0, rtol=1e-5, atol=0)
+    # gather on the pyramid of the padded 1264 x 1380 frame (ResNet strides 2..32), a subset of the points incl. the corners
+    Hp, Wp = H + patch[0], W + patch[1]
+    dims, h, w = [], Hp, Wp
+    for _ in range(5):
+        h, w = (h + 1) // 2, (w + 1) // 2
+        dims.append((h, w))
+    chans = [32, 64, 128, 128, 128]
+    scales, sizes = rr.rcnet_levels(patch)
+    sub = np.concatenate([np.arange(min(K, 24)), [K - 1]])
+    bx = boxes[sub].copy()
+    bx[0] = [0, 0, patch[1], patch[0]]                                   # top-left corner RoI (clipped by the map edge)
+    bx[1] = [Wp - patch[1], Hp - patch[0], Wp, Hp]                       # bottom-right corner
+    rois = rr.boxes_list_to_rois([bx])
+    feats = [rng.standard_normal((1, c, hh, ww)).astype(np.float32) for c, (hh, ww) in zip(chans, dims)]
+    got = ops.roi_gather([cu(f).contiguous(memory_format=torch.channels_last) for f in feats], cu(rois), scales, sizes,
+                         max_roi=(patch[1], patch[0]))
+    for f, sc, sz, g_ in zip(feats, scales, sizes, got):
+        assert np.array_equal(g_.cpu().numpy(), rr.roi_pool_torchvision(f, rois, sc, sz))
+
+
 def test_reduce_full_size_ragged_batch_and_logits():
     H, W, patch = 512, 640, (240, 100)
     Ks = [512, 1, 0, 300]

@@ -60,12 +60,16 @@ def bench_reduce(B=16, K=512, H=512, W=640, patch=(240, 100)):
     offs = torch.arange(0, B * K + 1, K, dtype=torch.int32, device=DEV)
     nbytes = B * (K * patch[0] * patch[1] * 4 + 12 * K + 3 * H * W * 4)
     from riders_b200 import _lib
-    for rows in (4, 8):
+    for rows, tw in ((4, 32), (8, 32), (4, 16)):
         _lib.lib().riders_debug_set(b"reduce_rows", rows)
+        _lib.lib().riders_debug_set(b"reduce_tile_w", tw)
         for logits in (False, True):
-            ms, best = timeit(lambda: ops.confidence_reduce(conf, pts, offs, H, W, 0.1, logits=logits))
-            report("confidence_reduce" + ("_logits" if logits else "") + "_rows%d" % rows, ms, best, nbytes, B=B, K=K)
+            for sel in (True, False):
+                nb = B * (K * patch[0] * patch[1] * 4 + 12 * K + (3 if sel else 2) * H * W * 4)
+                ms, best = timeit(lambda: ops.confidence_reduce(conf, pts, offs, H, W, 0.1, logits=logits, want_select=sel))
+                report("confidence_reduce" + ("_logits" if logits else "") + "_rows%d_tw%d_%dmaps" % (rows, tw, 3 if sel else 2), ms, best, nb, B=B, K=K)
     _lib.lib().riders_debug_set(b"reduce_rows", 4)
+    _lib.lib().riders_debug_set(b"reduce_tile_w", 16)
 
 
 def bench_lsq(B=64, H=512, W=640, K=512):
