@@ -269,6 +269,10 @@ int riders_extract_knots(const float* pred, const float* sparse, const uint8_t* 
                          int32_t* knot_xy, float* knot_scale, float* knot_shift, int32_t* knot_count,
                          void* stream);
 size_t riders_interp_workspace_bytes(int B, int max_knots, int H, int W);
+/* griddata(method='nearest') of the same call site (interpolate_knots passes any griddata method through): value of the nearest
+ * knot, exact integer distances, lowest knot index among equidistant ones; `fill` only for a frame without knots.            */
+int riders_interp_nearest(const int32_t* knot_xy, const float* knot_val, const int32_t* knot_count,
+                          int B, int max_knots, int H, int W, float fill, float* out, void* stream);
 int riders_interp_linear(const int32_t* knot_xy, const float* knot_val, const int32_t* knot_count,
                          int B, int max_knots, int H, int W, float fill,
                          float* out, int32_t* status,

@@ -56,6 +56,7 @@ SIGNATURES = {
     "riders_depth_metrics": (ci, [vp, vp, ci, ci, ci, cf, cf, vp, vp, vp]),
     "riders_extract_knots": (ci, [vp, vp, vp, ci, ci, ci, ci, vp, vp, vp, vp, vp]),
     "riders_interp_workspace_bytes": (sz, [ci, ci, ci, ci]),
+    "riders_interp_nearest": (ci, [vp, vp, vp, ci, ci, ci, ci, cf, vp, vp]),
     "riders_interp_triangulate": (ci, [vp, vp, vp, ci, ci, vp, vp, vp, vp, vp]),
     "riders_interp_fill": (ci, [ci, ci, ci, ci, cf, vp, vp, vp]),
     "riders_upsample_nearest_nhwc": (ci, [vp, ci, ci, ci, ci, ci, ci, vp, vp]),

@@ -445,7 +445,49 @@ raster_kernel(uint8_t* ws_base, WsLayout L, int max_knots, int H, int W, float* 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// griddata(method='nearest'): value of the nearest knot (exact integer distances; among equidistant knots the lowest index -
+// SciPy's cKDTree leaves that choice undefined).  Brute force over the frame's knots staged in shared memory: 640 x 512 pixels
+// x 512 knots = 168 M distance evaluations per frame.
+// ---------------------------------------------------------------------------------------------
+constexpr int NEAR_CHUNK = 1024;
+__global__ void __launch_bounds__(256)
+interp_nearest_kernel(const int32_t* __restrict__ knot_xy, const float* __restrict__ knot_val, const int32_t* __restrict__ knot_count,
+                      int max_knots, int H, int W, float fill, float* __restrict__ out) {
+    __shared__ int sx[NEAR_CHUNK], sy[NEAR_CHUNK];
+    const int frame = blockIdx.y;
+    const int n = min(knot_count[frame], max_knots);
+    const int px_i = blockIdx.x * 256 + threadIdx.x;
+    const int x = px_i % W, y = px_i / W;
+    int best = 0x7fffffff, arg = -1;
+    for (int base = 0; base < n; base += NEAR_CHUNK) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < min(NEAR_CHUNK, n - base); i += 256) {
+            sx[i] = knot_xy[((size_t)frame * max_knots + base + i) * 2];
+            sy[i] = knot_xy[((size_t)frame * max_knots + base + i) * 2 + 1];
+        }
+        __syncthreads();
+        const int m = min(NEAR_CHUNK, n - base);
+        for (int i = 0; i < m; ++i) {
+            const int dx = sx[i] - x, dy = sy[i] - y, d = dx * dx + dy * dy;
+            if (d < best) { best = d; arg = base + i; }
+        }
+    }
+    if (px_i < H * W) out[(size_t)frame * H * W + px_i] = arg >= 0 ? knot_val[(size_t)frame * max_knots + arg] : fill;
+}
+
 }  // namespace riders
+
+extern "C" int riders_interp_nearest(const int32_t* knot_xy, const float* knot_val, const int32_t* knot_count,
+                                     int B, int max_knots, int H, int W, float fill, float* out, void* stream) {
+    using namespace riders;
+    RIDERS_REQUIRE(B >= 0 && H > 0 && W > 0 && H <= 8192 && W <= 8192 && max_knots > 0 && B <= 65535, "interp_nearest: bad shape");
+    if (B == 0) return RIDERS_OK;
+    RIDERS_REQUIRE(knot_xy && knot_val && knot_count && out, "interp_nearest: null pointer");
+    count_launches(1);
+    interp_nearest_kernel<<<dim3(ceil_div(H * W, 256), B), 256, 0, (cudaStream_t)stream>>>(knot_xy, knot_val, knot_count, max_knots, H, W, fill, out);
+    return check_launch("interp_nearest");
+}
 
 extern "C" size_t riders_interp_workspace_bytes(int B, int max_knots, int H, int W) {
     (void)H; (void)W;

@@ -6,7 +6,9 @@ reference (one pinned H2D, the kernels, one D2H); torch CUDA tensors are accepte
 stay on the device.  The five normal-equation sums are accumulated in fp64 by a deterministic
 block tree (BASELINE north_star kernel 4), so ``scale``/``shift`` match the reference fed
 float64 inputs to ~1e-15 and the as-shipped float32 reference to its own rounding error.
-The RANSAC variant (estimator.py:32-87) is never called by the scripts and is not provided.
+The RANSAC variant (estimator.py:32-87, never called by the shipped scripts) is provided with the reference's own use of
+NumPy's global RNG: the valid (prediction, target) pairs are compacted on the device in ``np.where`` order, the 60 x 5-sample
+fits and inlier counts run over those few hundred pairs.
 """
 import numpy as np
 import torch
@@ -41,6 +43,38 @@ def compute_scale_and_shift_ls(prediction, target, mask):
     return np.float32(ss[0, 0]).reshape(()), np.float32(ss[0, 1]).reshape(())
 
 
+def compute_scale_and_shift_ransac(prediction, target, mask, num_iterations, sample_size, inlier_threshold,
+                                   inlier_ratio_threshold):
+    """estimator.py:32-87.  Same draws from ``np.random`` (one ``choice(valid_count, sample_size, replace=False)`` per
+    iteration), same update / early-exit rules; the sums run over the compacted valid pairs instead of the masked full maps
+    (the masked-out terms of the reference are exact zeros)."""
+    best_scale, best_shift, best_inlier_count = 0.0, 0.0, 0
+    p, t, m = _to_device(prediction, torch.float32), _to_device(target, torch.float32), _to_device(mask).bool()
+    pv, tv = p[m].cpu().numpy(), t[m].cpu().numpy()               # row-major order of the valid pixels = np.where(mask)
+    valid_count = pv.shape[0]
+    for _ in range(num_iterations):
+        if valid_count < sample_size:
+            break
+        indices = np.random.choice(valid_count, size=sample_size, replace=False)
+        ps, ts_ = pv[indices], tv[indices]
+        a_00, a_01, a_11 = np.sum(ps * ps), np.sum(ps), np.float32(sample_size)
+        b_0, b_1 = np.sum(ps * ts_), np.sum(ts_)
+        det = a_00 * a_11 - a_01 * a_01
+        x_0, x_1 = np.zeros_like(b_0), np.zeros_like(b_1)
+        if det > 0:
+            x_0 = (a_11 * b_0 - a_01 * b_1) / det
+            x_1 = (-a_01 * b_0 + a_00 * b_1) / det
+        residuals = np.abs(pv * x_0 + x_1 - tv)
+        inlier_count = np.sum(residuals < inlier_threshold)
+        if inlier_count > best_inlier_count:
+            best_scale, best_shift, best_inlier_count = x_0, x_1, inlier_count
+            if inlier_count / valid_count > inlier_ratio_threshold:
+                break
+    print('best_inlier_count: ', best_inlier_count)
+    print('inlier_ratio: ', best_inlier_count / valid_count if valid_count else float('nan'))
+    return best_scale, best_shift
+
+
 class LeastSquaresEstimator(object):
     def __init__(self, estimate, target, valid):
         self.estimate = estimate
@@ -60,6 +94,12 @@ class LeastSquaresEstimator(object):
                          _as3d(_to_device(self.target, torch.float32)),
                          _as3d(_to_device(self.valid)))
         return self._dev
+
+    def compute_scale_and_shift_ran(self, num_iterations=60, sample_size=5, inlier_threshold=0.02, inlier_ratio_threshold=0.8):
+        """estimator.py:101-106."""
+        self.scale, self.shift = compute_scale_and_shift_ransac(self.estimate, self.target, self.valid, num_iterations,
+                                                                sample_size, inlier_threshold, inlier_ratio_threshold)
+        self._applied = None
 
     def compute_scale_and_shift(self):
         # one pass pair on the device: sums -> solve -> unclamped output kept for apply_scale_and_shift()

@@ -3,10 +3,11 @@
 
 ``method='linear'`` - the only branch VI-Depth/RIDERS configure - runs on the device: knot
 extraction, exact-predicate Delaunay triangulation and the per-pixel barycentric fill (fp64
-math, float32 store, exactly ``fill_value=1.0`` outside the hull, like ``griddata``).  Other
-methods ('nearest', 'cubic') are SciPy features the reference never selects and raise
-``NotImplementedError``.  Where SciPy raises ``QhullError`` (fewer than 3 knots, all collinear)
-the same exception type is raised.
+math, float32 store, exactly ``fill_value=1.0`` outside the hull, like ``griddata``).
+``'nearest'`` runs on the device too (exact integer distances; SciPy's choice among equidistant
+knots is undefined, here the lowest knot index).  ``'cubic'`` (Clough-Tocher) is a SciPy feature
+the reference never selects and raises ``NotImplementedError``.  Where SciPy raises
+``QhullError`` (fewer than 3 knots, all collinear) the same exception type is raised.
 """
 import numpy as np
 import torch
@@ -40,8 +41,8 @@ def _raise_for_status(status):
 
 def interpolate_knots(map_size, knot_coords, knot_values, interpolate, fill_corners):
     """knot_coords (2,N) = (x row, y row); returns the float64 (H,W) map like griddata."""
-    if interpolate != 'linear':
-        raise NotImplementedError("only method='linear' is provided on the device path")
+    if interpolate not in ('linear', 'nearest'):
+        raise NotImplementedError("griddata method %r is not provided on the device path (linear, nearest)" % (interpolate,))
     coords = np.asarray(knot_coords)
     n = coords.shape[1]
     xy = _cuda(np.ascontiguousarray(coords.T.astype(np.int32))[None], torch.int32)
@@ -49,6 +50,8 @@ def interpolate_knots(map_size, knot_coords, knot_values, interpolate, fill_corn
     cnt = torch.tensor([n], dtype=torch.int32, device=xy.device)
     if n == 0:
         raise QhullError("QH6214 qhull input error: not enough points(0) to construct initial simplex")
+    if interpolate == 'nearest':
+        return ops.interp_nearest(xy, val, cnt, int(map_size[0]), int(map_size[1]), 1.0)[0].cpu().numpy().astype(np.float64)
     out, status = ops.interp_linear(xy, val, cnt, int(map_size[0]), int(map_size[1]), 1.0)
     _raise_for_status(status)
     return out[0].cpu().numpy().astype(np.float64)
@@ -79,8 +82,14 @@ class Interpolator2D(object):
         self.output = None
 
     def generate_interpolated_scale_map(self, interpolate_method, fill_corners=False):
-        if interpolate_method != 'linear':
-            raise NotImplementedError("only interpolate_method='linear' is provided on the device path")
+        if interpolate_method not in ('linear', 'nearest'):
+            raise NotImplementedError("griddata method %r is not provided on the device path (linear, nearest)" % (interpolate_method,))
+        if interpolate_method == 'nearest':
+            if self.num_knots == 0:
+                raise ValueError("griddata(method='nearest') needs at least one knot")
+            out = ops.interp_nearest(self._xy, self._scales, self._cnt, self.map_size[0], self.map_size[1], 1.0)
+            self.interpolated_scale_map = out[0].cpu().numpy().astype(np.float32)
+            return
         if self.num_knots == 0:
             raise QhullError("QH6214 qhull input error: not enough points(0) to construct initial simplex")
         out, status = ops.interp_linear(self._xy, self._scales, self._cnt, self.map_size[0], self.map_size[1], 1.0)

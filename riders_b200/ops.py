@@ -901,6 +901,21 @@ def interp_linear(knot_xy, knot_val, knot_count, H, W, fill=1.0, want_triangles=
     return out, status
 
 
+def interp_nearest(knot_xy, knot_val, knot_count, H, W, fill=1.0):
+    """griddata(method='nearest') on the device: (B,max_knots,2) int32 knots -> (B,H,W) float32."""
+    _need_cuda(knot_xy, knot_val, knot_count)
+    knot_xy = knot_xy.to(torch.int32).contiguous()
+    knot_val = _f32c(knot_val)
+    knot_count = knot_count.to(torch.int32).contiguous()
+    B, max_knots = knot_val.shape
+    out = torch.empty((B, H, W), dtype=torch.float32, device=knot_val.device)
+    with _span("interp_nearest", B * H * W * 4 + B * max_knots * 12):
+        rc = _lib.lib().riders_interp_nearest(_ptr(knot_xy), _ptr(knot_val), _ptr(knot_count), B, max_knots, H, W, float(fill),
+                                              _ptr(out), _stream())
+    _lib.check(rc, "riders_interp_nearest")
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # N4 prologue / N2 SML input assembly
 # --------------------------------------------------------------------------------------------

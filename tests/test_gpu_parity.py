@@ -404,6 +404,70 @@ def test_lsq_launch_forms_are_bit_identical():
             assert torch.equal(a, b)
 
 
+def test_interp_nearest_matches_griddata_where_the_nearest_knot_is_unique():
+    """Interpolator2D.generate_interpolated_scale_map('nearest') (griddata nearest = cKDTree query): identical wherever one
+    knot is strictly nearest; among equidistant knots SciPy's pick is undefined, so those pixels are only checked to carry
+    the value of ONE of the nearest knots."""
+    from scipy.interpolate import griddata
+    from riders_b200.modules.interpolator import Interpolator2D
+    H, W, K = 120, 160, 60
+    pred, target, mask = synth.alignment_inputs(5, K, H, W)
+    pred = (pred * np.float32(0.07) + np.float32(0.002)).astype(np.float32)
+    it = Interpolator2D(pred, target, mask)
+    it.generate_interpolated_scale_map('nearest')
+    got = it.interpolated_scale_map
+    ys, xs = np.nonzero(mask)
+    vals = (target[mask] / pred[mask]).astype(np.float32)
+    rows, cols = np.mgrid[0:H, 0:W]
+    ref = griddata(np.stack([xs, ys], 1), vals, (cols, rows), method='nearest').astype(np.float32)
+    d2 = (cols[..., None] - xs) ** 2 + (rows[..., None] - ys) ** 2
+    dmin = d2.min(-1)
+    unique = (d2 == dmin[..., None]).sum(-1) == 1
+    assert unique.mean() > 0.9 and np.array_equal(got[unique], ref[unique])
+    tie_ok = (np.abs(got[..., None] - vals) < 1e-12) & (d2 == dmin[..., None])
+    assert tie_ok.any(-1).all()
+    with pytest.raises(NotImplementedError):
+        it.generate_interpolated_scale_map('cubic')
+
+
+def test_ransac_estimator_follows_the_reference_draw_for_draw():
+    """LeastSquaresEstimator.compute_scale_and_shift_ran (estimator.py:32-87,101-106): with the same np.random seed the mirror
+    consumes the same draws and returns the reference's scale / shift (restated here on the full masked maps, as shipped)."""
+    from riders_b200.modules.estimator import LeastSquaresEstimator
+    pred, target, mask = synth.alignment_inputs(9, 200)
+    pred = pred.astype(np.float32)
+
+    def reference(num_iterations=60, sample_size=5, thr=0.02, ratio=0.8):
+        best = (0.0, 0.0, 0)
+        vi = np.where(mask)
+        n = len(vi[0])
+        for _ in range(num_iterations):
+            idx = np.random.choice(n, size=sample_size, replace=False)
+            ms = np.zeros_like(mask)
+            ms[vi[0][idx], vi[1][idx]] = 1
+            a00, a01, a11 = np.sum(ms * pred * pred), np.sum(ms * pred), np.sum(ms)
+            b0, b1 = np.sum(ms * pred * target), np.sum(ms * target)
+            det = a00 * a11 - a01 * a01
+            x0 = (a11 * b0 - a01 * b1) / det if det > 0 else 0.0
+            x1 = (-a01 * b0 + a00 * b1) / det if det > 0 else 0.0
+            res = np.abs(mask * pred * x0 + x1 - mask * target)[mask]
+            cnt = np.sum(res < thr)
+            if cnt > best[2]:
+                best = (x0, x1, cnt)
+                if cnt / n > ratio:
+                    break
+        return best
+
+    np.random.seed(4)
+    r0, r1, _ = reference()
+    np.random.seed(4)
+    est = LeastSquaresEstimator(pred, target, mask)
+    est.compute_scale_and_shift_ran()
+    np.testing.assert_allclose([est.scale, est.shift], [r0, r1], rtol=1e-4)
+    est.apply_scale_and_shift()
+    np.testing.assert_allclose(est.output, pred * np.float32(est.scale) + np.float32(est.shift), rtol=1e-6)
+
+
 # ------------------------------------------------------------------------------------ whole chain
 def _rand_model(device, patch, filt, dec, seed=0):
     from riders_b200.rcnet.rcnet_model import RCNetModel

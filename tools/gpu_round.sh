@@ -41,6 +41,22 @@ for MODE in "$@"; do
     train)
       timeout -s KILL 900 python bench.py --workload train --steps 10 --warmup 3 > $OUT/bench_train.json 2> $OUT/bench_train.err; echo "train rc=$?" | tee -a $OUT/status.txt
       cat $OUT/bench_train.json; tail -5 $OUT/bench_train.err ;;
+    strong64)
+      timeout -s KILL 900 python bench.py --global-frames 64 --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_strong64_1gpu.json 2> $OUT/bench_strong64_1gpu.err; echo "strong64 rc=$?" | tee -a $OUT/status.txt
+      tail -c 700 $OUT/bench_strong64_1gpu.json; tail -3 $OUT/bench_strong64_1gpu.err ;;
+    trainprof)
+      timeout -s KILL 600 python tools/train_profile.py > $OUT/train_profile.txt 2> $OUT/train_profile.err; echo "trainprof rc=$?" | tee -a $OUT/status.txt
+      head -32 $OUT/train_profile.txt; tail -3 $OUT/train_profile.err ;;
+    ncuall)
+      timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k "regex:loftr_layer_tc|lsq_|extract_knots|delaunay_star|raster_kernel|confidence_reduce|roi_gather_tma" -c 40 -f -o $OUT/prof_r02_hotpath \
+          python bench.py --steps 1 --profile > $OUT/ncu_all.log 2>&1; echo "ncu-all rc=$?" | tee -a $OUT/status.txt
+      ncu -i $OUT/prof_r02_hotpath.ncu-rep --page raw --csv > $OUT/prof_r02_hotpath_raw.csv 2>/dev/null
+      python tools/ncu_summary.py $OUT/prof_r02_hotpath_raw.csv > $OUT/ncu_summary_hotpath.txt 2>&1; head -60 $OUT/ncu_summary_hotpath.txt
+      timeout -s KILL 900 ncu --set full --clock-control none -k "regex:compact_valid|l1_brent|l1_apply" -c 6 -f -o $OUT/prof_r02_l1 \
+          python bench.py --steps 1 --profile --align s > $OUT/ncu_l1.log 2>&1; echo "ncu-l1 rc=$?" | tee -a $OUT/status.txt
+      ncu -i $OUT/prof_r02_l1.ncu-rep --page raw --csv > $OUT/prof_r02_l1_raw.csv 2>/dev/null
+      python tools/ncu_summary.py $OUT/prof_r02_l1_raw.csv > $OUT/ncu_summary_l1.txt 2>&1; head -40 $OUT/ncu_summary_l1.txt
+      for f in $OUT/prof_r02_hotpath.ncu-rep $OUT/prof_r02_l1.ncu-rep; do SZ=$(stat -c %s $f 2>/dev/null || echo 0); if [ "$SZ" -gt 30000000 ]; then rm -f $f; echo "dropped $f ($SZ bytes)"; fi; done ;;
     benchnotail)
       RIDERS_FUSED_TAIL=0 timeout -s KILL 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_notail.json 2> $OUT/bench_notail.err; echo "bench-notail rc=$?" | tee -a $OUT/status.txt
       tail -c 1500 $OUT/bench_notail.json ;;
