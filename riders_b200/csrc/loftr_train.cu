@@ -44,25 +44,48 @@ __device__ __forceinline__ void st_tok(void* p, size_t i, int dt, float v) {
 // ----------------------------------------------------------------------------------------------
 constexpr int TM = 64, TN = 64, TK = 16;
 
+// blockIdx.z = K split: this CTA covers k in [z * kchunk, min(K, (z + 1) * kchunk)).  With gridDim.z > 1 the tile goes to
+// part[z][M][N] (float32) and splitk_reduce_kernel adds the splits in index order (deterministic) into C.  The next K tile is
+// fetched into registers while the current one is multiplied (the K loop was global-load-latency bound: the weight-gradient
+// products have K = all tokens and only a handful of output tiles - 63 of the first 87 ms of a training step).
 __global__ void __launch_bounds__(256)
 gemm_kernel(const void* __restrict__ A, int lda, int ta, int dta, const void* __restrict__ B, int ldb, int tb, int dtb,
-            void* __restrict__ Cm, int ldc, int dtc, int M, int N, int K, int accumulate) {
+            void* __restrict__ Cm, int ldc, int dtc, int M, int N, int K, int accumulate, int kchunk, float* __restrict__ part) {
     __shared__ float As[TK][TM + 1];
     __shared__ float Bs[TK][TN + 1];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+    const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
     float acc[4][4] = {};
-    for (int k0 = 0; k0 < K; k0 += TK) {
-        for (int e = tid; e < TM * TK; e += 256) {
+    float ra[4], rb[4];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = tid + u * 256;
             // consecutive threads walk the contiguous dimension of each operand
             const int mi = ta ? e % TM : e / TK, ki = ta ? e / TM : e % TK;
             const int gm = m0 + mi, gk = k0 + ki;
-            As[ki][mi] = (gm < M && gk < K) ? ld_tok(A, ta ? (size_t)gk * lda + gm : (size_t)gm * lda + gk, dta) : 0.f;
+            ra[u] = (gm < M && gk < kend) ? ld_tok(A, ta ? (size_t)gk * lda + gm : (size_t)gm * lda + gk, dta) : 0.f;
             const int ni = tb ? e / TK : e % TN, kj = tb ? e % TK : e / TN;
             const int gn = n0 + ni, gk2 = k0 + kj;
-            Bs[kj][ni] = (gn < N && gk2 < K) ? ld_tok(B, tb ? (size_t)gn * ldb + gk2 : (size_t)gk2 * ldb + gn, dtb) : 0.f;
+            rb[u] = (gn < N && gk2 < kend) ? ld_tok(B, tb ? (size_t)gn * ldb + gk2 : (size_t)gk2 * ldb + gn, dtb) : 0.f;
         }
+    };
+    auto stash = [&]() {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = tid + u * 256;
+            const int mi = ta ? e % TM : e / TK, ki = ta ? e / TM : e % TK;
+            As[ki][mi] = ra[u];
+            const int ni = tb ? e / TK : e % TN, kj = tb ? e % TK : e / TN;
+            Bs[kj][ni] = rb[u];
+        }
+    };
+    fetch(kbeg);
+    for (int k0 = kbeg; k0 < kend; k0 += TK) {
+        stash();
         __syncthreads();
+        if (k0 + TK < kend) fetch(k0 + TK);
 #pragma unroll
         for (int kk = 0; kk < TK; ++kk) {
             float a[4], b[4];
@@ -83,16 +106,42 @@ gemm_kernel(const void* __restrict__ A, int lda, int ta, int dta, const void* __
         for (int j = 0; j < 4; ++j) {
             const int gn = n0 + tx * 4 + j;
             if (gn >= N) continue;
+            if (gridDim.z > 1) { part[((size_t)blockIdx.z * M + gm) * N + gn] = acc[i][j]; continue; }
             const size_t o = (size_t)gm * ldc + gn;
             st_tok(Cm, o, dtc, accumulate ? ld_tok(Cm, o, dtc) + acc[i][j] : acc[i][j]);
         }
     }
 }
 
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ part, int splits, void* __restrict__ Cm, int ldc, int dtc, int M, int N, int accumulate) {
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= M * N) return;
+    const int gm = e / N, gn = e % N;
+    float a = 0.f;
+    for (int z = 0; z < splits; ++z) a += part[(size_t)z * M * N + e];
+    const size_t o = (size_t)gm * ldc + gn;
+    st_tok(Cm, o, dtc, accumulate ? ld_tok(Cm, o, dtc) + a : a);
+}
+
+constexpr int SPLITK_CHUNK = 256, SPLITK_MAX = 64;
+static size_t splitk_floats(int C) { return (size_t)SPLITK_MAX * 2 * C * 2 * C; }
+
+// `part` (splitk_floats) enables the K split for products with few output tiles and a long K (the weight gradients)
 static void gemm(const void* A, int lda, bool ta, int dta, const void* B, int ldb, bool tb, int dtb, void* C, int ldc, int dtc,
-                 int M, int N, int K, bool accumulate, cudaStream_t st) {
-    count_launches(1);
-    gemm_kernel<<<dim3(ceil_div(M, TM), ceil_div(N, TN)), 256, 0, st>>>(A, lda, ta, dta, B, ldb, tb, dtb, C, ldc, dtc, M, N, K, accumulate);
+                 int M, int N, int K, bool accumulate, cudaStream_t st, float* part = nullptr) {
+    int splits = 1, kchunk = K;
+    if (part && K > 2 * SPLITK_CHUNK && ceil_div(M, TM) * ceil_div(N, TN) < 64) {
+        splits = ceil_div(K, SPLITK_CHUNK);
+        if (splits > SPLITK_MAX) splits = SPLITK_MAX;
+        kchunk = ceil_div(ceil_div(K, splits), TK) * TK;
+        splits = ceil_div(K, kchunk);
+    }
+    count_launches(splits > 1 ? 2 : 1);
+    gemm_kernel<<<dim3(ceil_div(M, TM), ceil_div(N, TN), splits), 256, 0, st>>>(A, lda, ta, dta, B, ldb, tb, dtb, C, ldc, dtc, M, N, K,
+                                                                                 accumulate, kchunk, part);
+    if (splits > 1)
+        splitk_reduce_kernel<<<ceil_div(M * N, 256), 256, 0, st>>>(part, splits, C, ldc, dtc, M, N, accumulate);
 }
 constexpr int F32 = RIDERS_DTYPE_F32;
 
@@ -273,7 +322,8 @@ extern "C" size_t riders_loftr_train_workspace_bytes(int N, int L, int S, int d_
     if (N <= 0) return 256;
     const size_t t = (size_t)N * (L > S ? L : S);
     // 2C-wide scratch (relu(h) / dh) + five C-wide scratch rows + LayerNorm partials
-    return (t * 2 * d_model * 2 + t * d_model * 6) * sizeof(float) + ((t + 7) / 8) * 2 * d_model * sizeof(float) + 1024;
+    return (t * 2 * d_model * 2 + t * d_model * 6) * sizeof(float) + ((t + 7) / 8) * 2 * d_model * sizeof(float) +
+           riders::train::splitk_floats(d_model) * sizeof(float) + 1024;
 }
 
 static int check_train(const riders_loftr_weights* w, int N, int L, int S, int C, int nhead, int dtype) {
@@ -343,7 +393,8 @@ extern "C" int riders_loftr_layer_bwd(const void* x, const void* src, const ride
     float* dk = p; p += T * C;
     float* dv = p; p += T * C;
     float* dxa = p; p += T * C;                          // float32 accumulator of dx
-    float* part = p;                                     // LayerNorm partials [ctas][2][C]
+    float* part = p; p += (size_t)((T + 7) / 8) * 2 * C;  // LayerNorm partials [ctas][2][C]
+    float* sk = p;                                       // split-K partials of the weight-gradient products
     const int lnc = ceil_div(Mx, 8);
     auto G = [](const float* q) { return const_cast<float*>(q); };
     const size_t ln_smem = (size_t)8 * 2 * C * sizeof(float);
@@ -353,25 +404,25 @@ extern "C" int riders_loftr_layer_bwd(const void* x, const void* src, const ride
     ln_bwd_reduce_kernel<<<ceil_div(2 * C, 256), 256, 0, st>>>(part, lnc, C, G(d_w->ln2_g), G(d_w->ln2_b));
     // ---- y2 = relu(h) W2^T
     relu_kernel<<<1024, 256, 0, st>>>(sv.h, hr, (size_t)Mx * 2 * C);
-    gemm(dy, C, true, F32, hr, 2 * C, false, F32, G(d_w->w2), 2 * C, F32, C, 2 * C, Mx, true, st);          // dW2 += dy2^T relu(h)
+    gemm(dy, C, true, F32, hr, 2 * C, false, F32, G(d_w->w2), 2 * C, F32, C, 2 * C, Mx, true, st, sk);          // dW2 += dy2^T relu(h)
     gemm(dy, C, false, F32, w->w2, 2 * C, false, F32, dh, 2 * C, F32, Mx, 2 * C, C, false, st);             // dh = dy2 W2
     relu_mask_kernel<<<1024, 256, 0, st>>>(sv.h, dh, (size_t)Mx * 2 * C);
     // ---- h = [x | m] W1^T
-    gemm(dh, 2 * C, true, F32, x, C, false, dtype, G(d_w->w1), 2 * C, F32, 2 * C, C, Mx, true, st);        // dW1[:, :C] += dh^T x
-    gemm(dh, 2 * C, true, F32, sv.m, C, false, F32, G(d_w->w1) + C, 2 * C, F32, 2 * C, C, Mx, true, st);   // dW1[:, C:] += dh^T m
+    gemm(dh, 2 * C, true, F32, x, C, false, dtype, G(d_w->w1), 2 * C, F32, 2 * C, C, Mx, true, st, sk);        // dW1[:, :C] += dh^T x
+    gemm(dh, 2 * C, true, F32, sv.m, C, false, F32, G(d_w->w1) + C, 2 * C, F32, 2 * C, C, Mx, true, st, sk);   // dW1[:, C:] += dh^T m
     gemm(dh, 2 * C, false, F32, w->w1, 2 * C, false, F32, dxa, C, F32, Mx, C, 2 * C, false, st);            // dx  = dh W1[:, :C]
     gemm(dh, 2 * C, false, F32, w->w1 + C, 2 * C, false, F32, dm, C, F32, Mx, C, 2 * C, false, st);         // dm  = dh W1[:, C:]
     // ---- m = LN1(y1), y1 = msg Wm^T
     ln_bwd_kernel<<<lnc, 256, ln_smem, st>>>(sv.y1, w->ln1_g, dm, F32, dy, part, Mx, C, ln_eps);
     ln_bwd_reduce_kernel<<<ceil_div(2 * C, 256), 256, 0, st>>>(part, lnc, C, G(d_w->ln1_g), G(d_w->ln1_b));
-    gemm(dy, C, true, F32, sv.msg, C, false, F32, G(d_w->wm), C, F32, C, C, Mx, true, st);                  // dWm += dy1^T msg
+    gemm(dy, C, true, F32, sv.msg, C, false, F32, G(d_w->wm), C, F32, C, C, Mx, true, st, sk);                  // dWm += dy1^T msg
     gemm(dy, C, false, F32, w->wm, C, false, F32, dm, C, F32, Mx, C, C, false, st);                         // dmsg = dy1 Wm
     // ---- attention
     attention_bwd_kernel<<<N * nhead, AB_THREADS, 0, st>>>(sv.q, sv.k, sv.v, sv.msg, dm, L, S, nhead, C / nhead, attn_eps, dq, dk, dv);
     // ---- q = x Wq^T, k = s Wk^T, v = s Wv^T
-    gemm(dq, C, true, F32, x, C, false, dtype, G(d_w->wq), C, F32, C, C, Mx, true, st);
-    gemm(dk, C, true, F32, src, C, false, dtype, G(d_w->wk), C, F32, C, C, Ms, true, st);
-    gemm(dv, C, true, F32, src, C, false, dtype, G(d_w->wv), C, F32, C, C, Ms, true, st);
+    gemm(dq, C, true, F32, x, C, false, dtype, G(d_w->wq), C, F32, C, C, Mx, true, st, sk);
+    gemm(dk, C, true, F32, src, C, false, dtype, G(d_w->wk), C, F32, C, C, Ms, true, st, sk);
+    gemm(dv, C, true, F32, src, C, false, dtype, G(d_w->wv), C, F32, C, C, Ms, true, st, sk);
     gemm(dq, C, false, F32, w->wq, C, false, F32, dxa, C, F32, Mx, C, C, true, st);                          // dx += dq Wq
     float* dsa = self ? dxa : dm;                                                                            // dmsg is dead
     gemm(dk, C, false, F32, w->wk, C, false, F32, dsa, C, F32, Ms, C, C, self, st);                          // ds (+)= dk Wk

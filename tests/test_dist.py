@@ -58,8 +58,22 @@ def _worker(rank, world, port, q):
     p = torch.nn.Parameter(torch.zeros(5))
     p.grad = torch.full((5,), float(r + 1))
     calls = rdist.allreduce_gradients([p])
+    # the per-step form used inside bench.py's timed loop: in-place sum of [metric sums ..., frame count]
+    vec = rdist.all_reduce_sums_device(torch.tensor([vals[b:e].sum(), float(e - b)], dtype=torch.float64))
+    assert abs(vec[0].item() / vec[1].item() - np.mean(vals)) < 1e-12
+    # two data-parallel training steps (riders_b200.train.TrainStep logic on a CPU stand-in model): identical weights on both
+    # ranks after the gradient all-reduce even though every rank sees different data
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(4, 1)
+    opt = torch.optim.Adam(lin.parameters(), lr=1e-2)
+    for step in range(2):
+        x = torch.full((3, 4), float(r + 1 + step))
+        opt.zero_grad()
+        lin(x).sum().backward()
+        rdist.allreduce_gradients(list(lin.parameters()))
+        opt.step()
     rdist.barrier()
-    q.put((r, means.tolist(), n, slow, total, p.grad.tolist(), calls))
+    q.put((r, means.tolist(), n, slow, total, p.grad.tolist(), calls, lin.weight.detach().flatten().tolist()))
     rdist.shutdown()
 
 
@@ -75,7 +89,8 @@ def test_two_rank_gloo_metric_reduction_and_gradients():
         p.join(timeout=60)
         assert p.exitcode == 0
     expect = np.mean(np.arange(7, dtype=np.float64) ** 2)
-    for r, means, n, slow, total, grad, calls in res:
+    for r, means, n, slow, total, grad, calls, w in res:
         assert n == 7 and abs(means[0] - expect) < 1e-12 and abs(means[1] - 1.0) < 1e-12
         assert slow == 11.0 and total == 2.0
         assert grad == [1.5] * 5 and calls == 1
+    assert res[0][7] == res[1][7]                                         # data-parallel replicas stay in lock step
