@@ -107,7 +107,10 @@ int riders_linear_attention_fwd(const float* q, const float* k, const float* v,
  *     impl: RIDERS_LOFTR_SIMT    fp32 FFMA kernels (any C%16==0), bit-for-bit fp32 semantics
  *           RIDERS_LOFTR_TCGEN05 fused tensor-core layer (C=128, nhead=8, L=S=21 tokens):
  *                                tcgen05.mma kind::f16 with a 2-term fp16 hi/lo operand split, 3 MMAs (fp32-accurate)
- *     workspace: riders_loftr_workspace_bytes(N, max(L,S), C, impl) bytes, 256-byte aligned.
+ *                                (attention blocks on mma.sync with the same split).  Operands must stay inside the fp16 range
+ *                                (|value| <= 65504): a violation sets word 0 of `workspace` (int32, reset by the call) to 1 and
+ *                                the caller recomputes with RIDERS_LOFTR_SIMT - never silent Inf / NaN.
+ *     workspace: riders_loftr_workspace_bytes(N, max(L,S), C, impl) bytes, 256-byte aligned; its first 256 bytes are a status block.
  * ------------------------------------------------------------------------------------------ */
 #define RIDERS_LOFTR_SIMT     0
 #define RIDERS_LOFTR_TCGEN05  1
@@ -152,7 +155,8 @@ int riders_loftr_layer_bwd(const void* x, const void* src, const riders_loftr_we
 /* A4  LocalFeatureTransformer.forward   RCNet/linear_attention.py:159-184
  *     layer_kind[i]: 0 = 'self' (f0=layer(f0,f0); f1=layer(f1,f1)), 1 = 'cross'
  *     (f0=layer(f0,f1); f1=layer(f1,f0_new)).  feat0 (N,L,C), feat1 (N,S,C) are not modified;
- *     results land in out0/out1 (may alias nothing else).  `layers` is a HOST array.           */
+ *     results land in out0/out1 (may alias nothing else).  `layers` is a HOST array.
+ *     RIDERS_LOFTR_TCGEN05 runs all 2 * n_layers layer calls in ONE persistent launch (n_layers <= 8).  */
 int riders_loftr_transformer_fwd(const float* feat0, const float* feat1,
                                  const riders_loftr_weights* layers, const int* layer_kind, int n_layers,
                                  int N, int L, int S, int d_model, int nhead,
