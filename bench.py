@@ -359,7 +359,9 @@ def run_config1(args):
             ga = Optimizer(fr["mono"], sparse_inv, valid, "inv")
             ga.optimize_scale(); ga.apply_scale(); ga.clamp_min_max(clamp_min=0.1, clamp_max=255.0)
         int_depth = ga.output.astype(np.float32)
-        return Interpolator2D(int_depth, sparse_inv, valid).generate_interpolated_scale_map("linear")
+        it = Interpolator2D(int_depth, sparse_inv, valid)
+        it.generate_interpolated_scale_map("linear")                         # modules/interpolator.py:43-50 stores, returns nothing
+        return it.interpolated_scale_map
 
     for _ in range(3):
         host_step()

@@ -61,7 +61,7 @@ constexpr int LAYER_PACK_BYTES = NCHUNK * CHUNK;               // 640 KB per lay
 constexpr int MAX_LAYERS = 16;
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = 64 + EPI_WARPS * 32;                   // warp 0 producer, warp 1 MMA, warps 2..17 epilogue
-constexpr int TAIL_BYTES = 128 + 2048;                         // barriers + TMEM slot | LayerNorm partials (128 rows x 4 quarters)
+constexpr int TAIL_BYTES = 128;                                // barriers + TMEM slot
 constexpr int SMEM_BYTES = 2 * OPER_BYTES + NSTAGE * CHUNK + TAIL_BYTES;   // 229504 of 232448; base must be 1024-aligned
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t D0 = 0, D1 = 128, D2 = 256, D3 = 384;
@@ -214,23 +214,26 @@ static_assert(6 * SARR <= OPER_BYTES, "attention staging must fit the X operand"
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x + 1.0f : __expf(x); }   // elu(x) + 1 (SFU exp2, ~2 ulp)
 __device__ __forceinline__ float acc_f(uint32_t r) { return __uint_as_float(r) * W_UNSCALE; }  // accumulator read-back
 
-// LayerNorm statistics of a 128-wide row held as 4 x 32 values by the four threads (column quarters) of the row:
-// partial sums go through shared memory (one 2 KB buffer, reused for the second pass) and are added in a fixed order, so
-// all four threads get identical bits.
-__device__ __forceinline__ void row_stats(const float (&v)[32], int row, int colq, float* red, float eps, float& mean, float& rstd) {
+// LayerNorm statistics of a 128-wide row held as 4 x 32 values by the four threads (column quarters) of the row, with ONE
+// exchange: every thread reduces its quarter to (mean_i, M2_i) locally, the four pairs meet in shared memory and are merged with
+// Chan's parallel formula  M2 = sum M2_i + 32 sum (mean_i - mean)^2  in a fixed order, so all four threads get identical bits and
+// there is no E[x^2] - mean^2 cancellation.  (Round 1 exchanged the sums and the squared deviations separately: two barriers more.)
+// `buf`: 128 x 4 float2 = 4 KB of the idle A operand.
+__device__ __forceinline__ void row_stats(const float (&v)[32], int row, int colq, float2* buf, float eps, float& mean, float& rstd) {
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) s += v[i];
-    red[colq * 128 + row] = s;
-    epi_bar();
-    mean = ((red[row] + red[128 + row]) + (red[256 + row] + red[384 + row])) * (1.0f / CH);
+    const float mi = s * (1.0f / 32.0f);
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
-    epi_bar();                                           // every thread has read the sums
-    red[colq * 128 + row] = q;
+    for (int i = 0; i < 32; ++i) { const float d = v[i] - mi; q = fmaf(d, d, q); }
+    buf[colq * 128 + row] = make_float2(mi, q);
     epi_bar();
-    rstd = 1.0f / sqrtf(((red[row] + red[128 + row]) + (red[256 + row] + red[384 + row])) * (1.0f / CH) + eps);
+    const float2 p0 = buf[row], p1 = buf[128 + row], p2 = buf[256 + row], p3 = buf[384 + row];
+    mean = ((p0.x + p1.x) + (p2.x + p3.x)) * 0.25f;
+    const float d0 = p0.x - mean, d1 = p1.x - mean, d2 = p2.x - mean, d3 = p3.x - mean;
+    const float m2 = ((p0.y + p1.y) + (p2.y + p3.y)) + 32.0f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
+    rstd = 1.0f / sqrtf(m2 * (1.0f / CH) + eps);
 }
 
 // signal "operand written (and my TMEM reads done)" to the MMA warp
@@ -403,8 +406,7 @@ loftr_layer_tc_kernel(const LayerArgs P) {
         const int col0 = colq * 32;
         const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
         uint32_t dph = 0, hph = 0;
-        float* stage_f = reinterpret_cast<float*>(a_base);
-        float* red = reinterpret_cast<float*>(bars) + 32;  // LayerNorm partials: 2 KB behind the barriers / TMEM slot
+        float2* red = reinterpret_cast<float2*>(a_base);  // LayerNorm partials: 4 KB of the A operand, dead whenever a LayerNorm runs
 
         float bad = 0.f;                                 // running max |operand value| of the rows that exist (RANGE_CHECK)
         const int g8 = lane >> 2, t4 = lane & 3, r8 = lane & 7, tl = lane >> 3;      // mma.sync / ldmatrix lane coordinates
@@ -576,6 +578,7 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                 for (int i = 0; i < 32; ++i) v[i] = acc_f(r[i]);
                 float mean, rstd;
                 row_stats(v, row, colq, red, P.ln_eps, mean, rstd);
+                epi_bar();                               // every thread has read the partials: m may overwrite them
                 float rbad = 0.f;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -635,30 +638,27 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                 for (int i = 0; i < 32; ++i) v[i] = acc_f(r[i]);
                 float mean, rstd;
                 row_stats(v, row, colq, red, P.ln_eps, mean, rstd);
-                // stage the normalised row (float4 index XOR (row & 31)) so the global traffic is coalesced
+                // every thread owns 32 consecutive columns (128 B) of its token row: residual read and result write go straight
+                // from / to global memory, 16 bytes at a time (the round-1 staging through shared memory cost two more barriers)
+                if (row < valid_rows) {
+                    const float4* xr = reinterpret_cast<const float4*>(xg + (size_t)row * CH + col0);
+                    float4* orow = reinterpret_cast<float4*>(A.out + (g_row0 + row) * CH + col0);
+                    float4 xv[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 g = __ldg(reinterpret_cast<const float4*>(A.ln2_g + col0) + j);
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(A.ln2_b + col0) + j);
-                    float4 y;
-                    y.x = (v[4 * j + 0] - mean) * rstd * g.x + b.x;
-                    y.y = (v[4 * j + 1] - mean) * rstd * g.y + b.y;
-                    y.z = (v[4 * j + 2] - mean) * rstd * g.z + b.z;
-                    y.w = (v[4 * j + 3] - mean) * rstd * g.w + b.w;
-                    reinterpret_cast<float4*>(stage_f + row * CH)[(colq * 8 + j) ^ (row & 31)] = y;
-                }
-                epi_bar();
-                float* og = A.out + g_row0 * CH;
+                    for (int j = 0; j < 8; ++j) xv[j] = __ldcg(xr + j);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r2 = ew * 8 + i;
-                    if (r2 < valid_rows) {
-                        const float4 y = reinterpret_cast<const float4*>(stage_f + r2 * CH)[lane ^ (r2 & 31)];
-                        const float4 xv = __ldcg(reinterpret_cast<const float4*>(xg + (size_t)r2 * CH) + lane);
-                        __stcg(reinterpret_cast<float4*>(og + (size_t)r2 * CH) + lane, make_float4(xv.x + y.x, xv.y + y.y, xv.z + y.z, xv.w + y.w));
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 g = __ldg(reinterpret_cast<const float4*>(A.ln2_g + col0) + j);
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(A.ln2_b + col0) + j);
+                        float4 y;
+                        y.x = xv[j].x + ((v[4 * j + 0] - mean) * rstd * g.x + b.x);
+                        y.y = xv[j].y + ((v[4 * j + 1] - mean) * rstd * g.y + b.y);
+                        y.z = xv[j].z + ((v[4 * j + 2] - mean) * rstd * g.z + b.z);
+                        y.w = xv[j].w + ((v[4 * j + 3] - mean) * rstd * g.w + b.w);
+                        __stcg(orow + j, y);
                     }
                 }
-                epi_bar();                               // staging / partials reads done (and this call's rows written) before the next call
+                epi_bar();                               // this call's rows are written (and the partials read) before the next call loads
             }
             TRACE_E(10);
             tc_fence_before();
