@@ -1,6 +1,6 @@
 // A6/A7: global scale/shift least squares + apply + clamp (modules/estimator.py:5-29,108-125).
 //
-// Pass 1 (lsq_partial_kernel): every CTA owns a fixed, contiguous PX_PER_CTA-pixel slice of one
+// Pass 1 (lsq_partial_kernel): every CTA owns a fixed, contiguous PX_PER_CTA-pixel (8192) slice of one
 //   frame, reads the mask first and touches pred/target only where the mask is set, accumulates
 //   the five normal-equation sums in fp64 and reduces them with a fixed shuffle/smem tree ->
 //   partial[frame][cta][5].  The slice size does not depend on the SM count, so the result is
@@ -23,9 +23,13 @@
 
 namespace riders {
 
+// 8192-pixel slices (256 threads x 32 pixels): a 640x512 frame is 40 slices, 16 frames are 640 CTAs = ONE wave of the 148 SMs at
+// <= 48 registers (round 1's 4096-pixel slices were 1280 CTAs = two waves for both passes; the slice size is a constant, so
+// results stay bit-reproducible on any device)
 constexpr int LSQ_THREADS = 256;
-constexpr int PX_PER_THREAD = 16;
-constexpr int PX_PER_CTA = LSQ_THREADS * PX_PER_THREAD;     // 4096
+constexpr int PX_PER_THREAD = 32;
+constexpr int PX_PER_CTA = LSQ_THREADS * PX_PER_THREAD;     // 8192
+constexpr int PDL_PREFETCH = 4;                             // float4 per thread loaded before the dependency wait (16 pixels)
 
 struct Sums5 { double v[5]; };
 
@@ -194,7 +198,7 @@ lsq_apply_kernel(const float* __restrict__ pred, const double* __restrict__ part
 // resident while pass 1 is still running, loads its 16 pixels of `pred` per thread (they do not depend on pass 1), and only
 // then waits for pass 1's partials (griddepcontrol.wait) - the HBM read of pass 2 and the launch latency of the second kernel
 // hide under pass 1.  Same arithmetic as lsq_apply_kernel, bit for bit.
-__global__ void __launch_bounds__(LSQ_THREADS)
+__global__ void __launch_bounds__(LSQ_THREADS, 5)
 lsq_apply_pdl_kernel(const float* __restrict__ pred, const double* partial,
                      int npx, int ctas_per_frame,
                      double* __restrict__ sums, double* __restrict__ scale_shift,
@@ -208,20 +212,22 @@ lsq_apply_pdl_kernel(const float* __restrict__ pred, const double* partial,
     const int begin = cta * PX_PER_CTA;
     const int end = min(begin + PX_PER_CTA, npx);
     const bool vec_ok = out && ((npx & 3) == 0) && ((((uintptr_t)p) & 15) == 0) && ((((uintptr_t)o) & 15) == 0);
-    float4 v[PX_PER_THREAD / 4];
+    auto load4 = [&](int it) {
+        const int i = begin + (it * LSQ_THREADS + threadIdx.x) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vec_ok) { if (i < end) v = *reinterpret_cast<const float4*>(p + i); }
+        else {
+            if (i < end) v.x = p[i];
+            if (i + 1 < end) v.y = p[i + 1];
+            if (i + 2 < end) v.z = p[i + 2];
+            if (i + 3 < end) v.w = p[i + 3];
+        }
+        return v;
+    };
+    float4 v[PDL_PREFETCH];
     if (out) {
 #pragma unroll
-        for (int it = 0; it < PX_PER_THREAD / 4; ++it) {
-            const int i = begin + (it * LSQ_THREADS + threadIdx.x) * 4;
-            v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (vec_ok) { if (i < end) v[it] = *reinterpret_cast<const float4*>(p + i); }
-            else {
-                if (i < end) v[it].x = p[i];
-                if (i + 1 < end) v[it].y = p[i + 1];
-                if (i + 2 < end) v[it].z = p[i + 2];
-                if (i + 3 < end) v[it].w = p[i + 3];
-            }
-        }
+        for (int it = 0; it < PDL_PREFETCH; ++it) v[it] = load4(it);
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");            // pass 1 has completed and its partials are visible
     solve_frame(partial + (size_t)frame * ctas_per_frame * 5, ctas_per_frame, sm5, sm_ss);
@@ -238,18 +244,24 @@ lsq_apply_pdl_kernel(const float* __restrict__ pred, const double* partial,
         if (lo_on && r < clamp_lo) r = clamp_lo;
         return r;
     };
-#pragma unroll
-    for (int it = 0; it < PX_PER_THREAD / 4; ++it) {
+    auto store4 = [&](int it, float4 x) {
         const int i = begin + (it * LSQ_THREADS + threadIdx.x) * 4;
         if (vec_ok) {
-            if (i < end) *reinterpret_cast<float4*>(o + i) = make_float4(f(v[it].x), f(v[it].y), f(v[it].z), f(v[it].w));
+            if (i < end) *reinterpret_cast<float4*>(o + i) = make_float4(f(x.x), f(x.y), f(x.z), f(x.w));
         } else {
-            if (i < end) o[i] = f(v[it].x);
-            if (i + 1 < end) o[i + 1] = f(v[it].y);
-            if (i + 2 < end) o[i + 2] = f(v[it].z);
-            if (i + 3 < end) o[i + 3] = f(v[it].w);
+            if (i < end) o[i] = f(x.x);
+            if (i + 1 < end) o[i + 1] = f(x.y);
+            if (i + 2 < end) o[i + 2] = f(x.z);
+            if (i + 3 < end) o[i + 3] = f(x.w);
         }
-    }
+    };
+    float4 w[PX_PER_THREAD / 4 - PDL_PREFETCH];
+#pragma unroll
+    for (int it = PDL_PREFETCH; it < PX_PER_THREAD / 4; ++it) w[it - PDL_PREFETCH] = load4(it);    // the rest streams while the first part is written
+#pragma unroll
+    for (int it = 0; it < PDL_PREFETCH; ++it) store4(it, v[it]);
+#pragma unroll
+    for (int it = PDL_PREFETCH; it < PX_PER_THREAD / 4; ++it) store4(it, w[it - PDL_PREFETCH]);
 }
 
 // Both passes in one cooperative launch: every CTA walks the (frame, slice) items with the grid stride, the grid barrier

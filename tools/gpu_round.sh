@@ -80,8 +80,8 @@ for MODE in "$@"; do
       cat $OUT/loftr_trace.txt ;;
     micro:*)
       WHICH=$(echo $MODE | cut -d: -f2 | tr ',' ' ')
-      timeout -s KILL 600 python tools/microbench.py $WHICH > $OUT/microbench_part.jsonl 2> $OUT/microbench_part.err; echo "microbench($WHICH) rc=$?" | tee -a $OUT/status.txt
-      cat $OUT/microbench_part.jsonl ;;
+      timeout -s KILL 600 python tools/microbench.py $WHICH > $OUT/microbench_$(echo $WHICH | tr " " "_").jsonl 2> $OUT/microbench_part.err; echo "microbench($WHICH) rc=$?" | tee -a $OUT/status.txt
+      cat $OUT/microbench_$(echo $WHICH | tr " " "_").jsonl ;;
     micro)
       timeout -s KILL 600 python tools/microbench.py > $OUT/microbench.jsonl 2> $OUT/microbench.err; echo "microbench rc=$?" | tee -a $OUT/status.txt
       cat $OUT/microbench.jsonl ;;
