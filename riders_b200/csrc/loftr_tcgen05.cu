@@ -176,8 +176,7 @@ __device__ __forceinline__ void split_store8(uint8_t* base, int row, int col, fl
 }
 
 // coalesced: epilogue warp `ew` (0..15) loads rows ew*8.. of a (rows x 128) fp32 tile and splits them into the operand
-__device__ __forceinline__ void load_tile_to_oper(uint8_t* base, const float* g, int valid_rows, int ew, int lane, float& bad) {
-    float4 v[8];
+__device__ __forceinline__ void load_tile_regs(float4 (&v)[8], const float* g, int valid_rows, int ew, int lane) {
     const int c8 = (lane & 15) * 8;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -189,8 +188,46 @@ __device__ __forceinline__ void load_tile_to_oper(uint8_t* base, const float* g,
             v[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f); v[2 * i + 1] = v[2 * i];
         }
     }
+}
+__device__ __forceinline__ void split_tile_regs(uint8_t* base, const float4 (&v)[8], int ew, int lane, float& bad) {
+    const int c8 = (lane & 15) * 8;
 #pragma unroll
     for (int i = 0; i < 4; ++i) split_store8(base, ew * 8 + i * 2 + (lane >> 4), c8, v[2 * i], v[2 * i + 1], bad);
+}
+// The same rows, asynchronously (LDGSTS) into a raw fp32 image of the tile (row stride 512 bytes; the whole X operand region):
+// issued while LayerNorm 2 of the previous call runs, consumed by the SAME thread (wait_group, then its own 16-byte pieces).
+__device__ __forceinline__ void prefetch_tile_async(uint8_t* raw, const float* g, int valid_rows, int ew, int lane) {
+    const int c8 = (lane & 15) * 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = ew * 8 + i * 2 + (lane >> 4);
+        if (row < valid_rows) {
+            const uint32_t dst = smem_u32(raw + ((size_t)row * CH + c8) * 4);
+            const float* src = g + (size_t)row * CH + c8;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 4) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void read_prefetched_tile(float4 (&v)[8], const uint8_t* raw, int valid_rows, int ew, int lane) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const int c8 = (lane & 15) * 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = ew * 8 + i * 2 + (lane >> 4);
+        if (row < valid_rows) {
+            const float4* src = reinterpret_cast<const float4*>(raw + ((size_t)row * CH + c8) * 4);
+            v[2 * i] = src[0]; v[2 * i + 1] = src[1];
+        } else {
+            v[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f); v[2 * i + 1] = v[2 * i];
+        }
+    }
+}
+__device__ __forceinline__ void load_tile_to_oper(uint8_t* base, const float* g, int valid_rows, int ew, int lane, float& bad) {
+    float4 v[8];
+    load_tile_regs(v, g, valid_rows, ew, lane);
+    split_tile_regs(base, v, ew, lane, bad);
 }
 
 // ------------------------------------------------------------------------------------ warp-level MMA (attention blocks)
@@ -237,10 +274,13 @@ __device__ __forceinline__ void row_stats(const float (&v)[32], int row, int col
 }
 
 // signal "operand written (and my TMEM reads done)" to the MMA warp
+// (every thread fences its own writes, the warp converges, one lane arrives: 16 arrivals per phase instead of 512 - the
+// arrivals are shared-memory atomics that serialise)
 __device__ __forceinline__ void publish(uint32_t bar) {
     fence_async_smem();
     tc_fence_before();
-    mbar_arrive(bar);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
 
 constexpr int MAX_CALLS = 16;                   // layer calls per launch (RC-Net: 8 layers x 2 calls)
@@ -261,9 +301,9 @@ struct LayerArgs {
 };
 
 // trace layout per traced CTA (blockIdx.x == 0 or gridDim.x / 2): 128 slots; [0..63] epilogue thread, [64..127] MMA thread
-#define TRACE_E(k) do { if (P.trace && tr_on && lane == 0 && warp == 4 && ci == 0 && tile == (int)blockIdx.x) P.trace[tr_base + (k)] = clock64(); } while (0)
-#define TRACE_M(k) do { if (P.trace && tr_on && lane == 0 && ci == 0 && tile == (int)blockIdx.x) P.trace[tr_base + 64 + (k)] = clock64(); } while (0)
-#define TRACE_W(k) do { if (P.trace && tr_on && lane == 0 && ci == 0 && tile == (int)blockIdx.x) P.trace[tr_base + 64 + (k)] = wsum; } while (0)
+#define TRACE_E(k) do { if (P.trace && tr_on && lane == 0 && warp == 4 && ci == 0 && tile == tr_tile) P.trace[tr_base + (k)] = clock64(); } while (0)
+#define TRACE_M(k) do { if (P.trace && tr_on && lane == 0 && ci == 0 && tile == tr_tile) P.trace[tr_base + 64 + (k)] = clock64(); } while (0)
+#define TRACE_W(k) do { if (P.trace && tr_on && lane == 0 && ci == 0 && tile == tr_tile) P.trace[tr_base + 64 + (k)] = wsum; } while (0)
 
 // ------------------------------------------------------------------------------------ the fused layer
 __global__ void __launch_bounds__(THREADS, 1)
@@ -279,17 +319,22 @@ loftr_layer_tc_kernel(const LayerArgs P) {
     const uint32_t bfull = smem_u32(bars), bempty = smem_u32(bars + NSTAGE);
     const uint32_t a_ready = smem_u32(bars + 2 * NSTAGE), d_ready = smem_u32(bars + 2 * NSTAGE + 1);
     const uint32_t x_ready = smem_u32(bars + 2 * NSTAGE + 2), h_ready = smem_u32(bars + 2 * NSTAGE + 3);
+    // one barrier per attention quarter (a phase per call each: the epilogue can never run two phases ahead of the MMA warp)
+    const uint32_t m_ready0 = smem_u32(bars + 10);
+    auto m_ready = [&](int q) { return m_ready0 + 8u * (uint32_t)(q + (q >> 1)); };       // slots 10, 11, 13, 14 (12 = TMEM slot)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool tr_on = blockIdx.x == 0 || blockIdx.x == gridDim.x / 2;
     const int tr_base = (blockIdx.x == 0 ? 0 : 128);
+    const int tr_tile = (int)(blockIdx.x + gridDim.x) < P.n_tiles ? (int)(blockIdx.x + gridDim.x) : (int)blockIdx.x;   // steady state if possible
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(bfull + 8 * s, 1); mbar_init(bempty + 8 * s, 1); }
-        mbar_init(a_ready, EPI_WARPS * 32);
+        mbar_init(a_ready, EPI_WARPS);
         mbar_init(d_ready, 1);
-        mbar_init(x_ready, EPI_WARPS * 32);
+        mbar_init(x_ready, EPI_WARPS);
         mbar_init(h_ready, 1);
+        for (int q = 0; q < 4; ++q) mbar_init(m_ready(q), EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -347,33 +392,77 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                     __syncwarp();
                 }
             };
+            // merge(msg), one attention quarter (2 heads = 32 message columns = 2 of the 8 k steps) at a time -> D3
+            uint32_t mph = 0;
+            auto issue_merge_quarter = [&](int hq) {
+                const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1;
+                mbar_wait(m_ready(hq), mph & 1);
+                if ((hq & 1) == 0) {
+                    const long long tw = P.trace ? clock64() : 0;
+                    mbar_wait(bfull + 8 * s, ph);
+                    if (P.trace) wsum += clock64() - tw;
+                }
+                tc_fence_after();
+                const int kb = hq >> 1;
+                const uint64_t ah = smem_desc(ao + kb * SLAB), al = smem_desc(ao + (2 + kb) * SLAB);
+                const uint64_t bh = smem_desc(b0 + s * CHUNK), bl = smem_desc(b0 + s * CHUNK + SLAB);
+                if (elect_one()) {
+#pragma unroll
+                    for (int k2 = 0; k2 < 2; ++k2) {
+                        const uint64_t adv = (uint64_t)((((hq & 1) << 1) + k2) * 2);
+                        umma_f16(tmem + D3, al + adv, bh + adv, IDESC, (uint32_t)(hq > 0 || k2 > 0));
+                        umma_f16(tmem + D3, ah + adv, bl + adv, IDESC, 1);
+                        umma_f16(tmem + D3, ah + adv, bh + adv, IDESC, 1);
+                    }
+                    if (hq & 1) umma_commit(bempty + 8 * s);
+                    if (hq == 3) umma_commit(d_ready);
+                }
+                __syncwarp();
+                if (hq & 1) ++n;
+            };
             for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x)
             for (int ci = 0; ci < P.n_calls; ++ci) {
-                const uint32_t kv_src = P.call[ci].is_self ? xo : ao;
-                // seg 0: q, k, v (-> the attention can start)
+                // a cross call whose source is the map the previous call of this tile just wrote finds it already split in X
+                // (written by that call's LayerNorm 2): then x goes to A and the operand roles of seg 0 are swapped
+                const bool handoff = ci > 0 && !P.call[ci].is_self && P.call[ci].src == P.call[ci - 1].out;
+                const uint32_t q_src = handoff ? ao : xo;
+                const uint32_t kv_src = (P.call[ci].is_self || handoff) ? xo : ao;
+                // seg 0: k, v, q (-> the attention can start).  After a hand-off the source is in X before this call begins: k and
+                // v go at once, q when x has arrived in A.
                 TRACE_M(0);
-                mbar_wait(a_ready, aph & 1); ++aph;
-                tc_fence_after();
-                TRACE_M(1); wsum = 0;
-                issue_block(xo, D0, 0, 0);
-                issue_block(kv_src, D1, 0, 0);
-                issue_block(kv_src, D2, 0, d_ready);
+                if (handoff) {
+                    mbar_wait(x_ready, vph & 1); ++vph;
+                    tc_fence_after();
+                    TRACE_M(1); wsum = 0;
+                    issue_block(kv_src, D1, 0, 0);
+                    issue_block(kv_src, D2, 0, 0);
+                    mbar_wait(a_ready, aph & 1); ++aph;
+                    tc_fence_after();
+                } else {
+                    mbar_wait(a_ready, aph & 1); ++aph;
+                    tc_fence_after();
+                    TRACE_M(1); wsum = 0;
+                    issue_block(kv_src, D1, 0, 0);
+                    issue_block(kv_src, D2, 0, 0);
+                }
+                issue_block(q_src, D0, 0, d_ready);
                 TRACE_M(2);
                 TRACE_W(3);
-                // seg 1: merge(msg)
+                // seg 1: merge(msg) -> D3, two k steps per finished attention quarter: only the last quarter's 6 MMAs are exposed
                 TRACE_M(4);
-                mbar_wait(a_ready, aph & 1); ++aph;
-                tc_fence_after();
-                TRACE_M(5); wsum = 0;
-                issue_block(ao, D0, 0, d_ready);
+                wsum = 0;
+                issue_merge_quarter(0); issue_merge_quarter(1); issue_merge_quarter(2);
+                TRACE_M(5);
+                issue_merge_quarter(3);
+                ++mph;
                 TRACE_M(6);
                 TRACE_W(7);
-                // seg 2: x is back in X -> its half of mlp.0 (runs under the merge read-back and LayerNorm 1)
+                // seg 2: x is back in X -> its half of mlp.0 (runs under the merge read-back and LayerNorm 1); k and v are dead
                 TRACE_M(8);
                 mbar_wait(x_ready, vph & 1); ++vph;
                 tc_fence_after();
                 TRACE_M(9); wsum = 0;
-                issue_block(xo, D3, 0, 0);
+                issue_block(xo, D1, 0, 0);
                 issue_block(xo, D2, 0, 0);
                 TRACE_M(10);
                 TRACE_W(11);
@@ -382,16 +471,18 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                 mbar_wait(a_ready, aph & 1); ++aph;
                 tc_fence_after();
                 TRACE_M(13); wsum = 0;
-                issue_block(ao, D3, 1, h_ready);             // h[:, :C] complete (own barrier): its ReLU / re-split runs under the next block
+                issue_block(ao, D1, 1, h_ready);             // h[:, :C] complete (own barrier): its ReLU / re-split runs under the next block
                 issue_block(ao, D2, 1, d_ready);
                 TRACE_M(14);
                 TRACE_W(15);
-                // seg 4: mlp.2 on relu(h): [:, :C] from X, [:, C:] from A
+                // seg 4: mlp.2 on relu(h): [:, :C] from X as soon as that half is split (x_ready), [:, C:] from A
                 TRACE_M(16);
-                mbar_wait(a_ready, aph & 1); ++aph;
+                mbar_wait(x_ready, vph & 1); ++vph;
                 tc_fence_after();
                 TRACE_M(17); wsum = 0;
                 issue_block(xo, D0, 0, 0);
+                mbar_wait(a_ready, aph & 1); ++aph;
+                tc_fence_after();
                 issue_block(ao, D0, 1, d_ready);
                 TRACE_M(18);
                 TRACE_W(19);
@@ -409,6 +500,7 @@ loftr_layer_tc_kernel(const LayerArgs P) {
         float2* red = reinterpret_cast<float2*>(a_base);  // LayerNorm partials: 4 KB of the A operand, dead whenever a LayerNorm runs
 
         float bad = 0.f;                                 // running max |operand value| of the rows that exist (RANGE_CHECK)
+        bool pre_valid = false;                          // this call's x rows are arriving in X as a raw fp32 image (prefetch_tile_async)
         const int g8 = lane >> 2, t4 = lane & 3, r8 = lane & 7, tl = lane >> 3;      // mma.sync / ldmatrix lane coordinates
         const uint32_t stage_u32 = smem_u32(x_base);     // attention staging lives in X (dead between the q/k/v MMAs and the x reload)
 
@@ -421,10 +513,23 @@ loftr_layer_tc_kernel(const LayerArgs P) {
             const float* xg = A.x + g_row0 * CH;
             const float* sg = A.src + g_row0 * CH;
 
-            // ---- E0: X = x, A = src (cross) ---------------------------------------------------
+            // ---- E0: X = x, A = src (cross); after a hand-off X already holds src and x goes to A ---------------
             TRACE_E(0);
-            load_tile_to_oper(x_base, xg, valid_rows, ew, lane, bad);
-            if (!A.is_self) load_tile_to_oper(a_base, sg, valid_rows, ew, lane, bad);
+            const bool handoff = ci > 0 && !A.is_self && A.src == P.call[ci - 1].out;      // same predicate as the MMA warp
+            if (handoff) {
+                publish(x_ready);                        // X = split(source), written by the previous call's LayerNorm 2: k and v may go
+                load_tile_to_oper(a_base, xg, valid_rows, ew, lane, bad);
+            } else {
+                if (pre_valid) {
+                    float4 v[8];
+                    read_prefetched_tile(v, x_base, valid_rows, ew, lane);
+                    epi_bar();                           // every thread holds its pieces: the split may overwrite the raw image
+                    split_tile_regs(x_base, v, ew, lane, bad);
+                } else {
+                    load_tile_to_oper(x_base, xg, valid_rows, ew, lane, bad);
+                }
+                if (!A.is_self) load_tile_to_oper(a_base, sg, valid_rows, ew, lane, bad);
+            }
             publish(a_ready);
             TRACE_E(1);
 
@@ -555,24 +660,26 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                     }
                     if (hq == 0) TRACE_E(3);
                     if (hq == 1) TRACE_E(24);
+                    fence_async_smem();                  // this quarter's message columns -> visible to the MMA (async proxy)
                     epi_bar();                           // (2) done reading: the next quarter may overwrite the staging
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive(m_ready(hq));   // (one lane per warp) the merge MMAs of these two k steps may go
                     if (hq == 1) TRACE_E(25);
                 }
             }
-            publish(a_ready);                            // the message is complete in A: merge may go
             TRACE_E(4);
             // ---- x back into X (the staging is dead: barrier above) for its half of mlp.0; L2 hit, runs under the merge MMAs
             load_tile_to_oper(x_base, xg, valid_rows, ew, lane, bad);
             publish(x_ready);
 
             // ---- E2: m = LayerNorm1(merge(msg)) -> A ----------------------------------------
-            mbar_wait(d_ready, dph & 1); ++dph;          // merge done (and with it both x halves of mlp.0: X is dead)
+            mbar_wait(d_ready, dph & 1); ++dph;          // merge done (D3)
             tc_fence_after();
             TRACE_E(5);
             {
                 uint32_t r[32];
                 float v[32];
-                TMEM_LD32(trow + D0 + col0, r);
+                TMEM_LD32(trow + D3 + col0, r);
                 tmem_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = acc_f(r[i]);
@@ -605,12 +712,12 @@ loftr_layer_tc_kernel(const LayerArgs P) {
             float hbad = 0.f;
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
-                // hf = 0: h[:, :C] in D3 (the second block still reads m from A); hf = 1: h[:, C:] in D2
+                // hf = 0: h[:, :C] in D1 (the second block still reads m from A); hf = 1: h[:, C:] in D2
                 if (hf == 0) { mbar_wait(h_ready, hph & 1); ++hph; } else { mbar_wait(d_ready, dph & 1); ++dph; }
                 tc_fence_after();
                 if (hf == 0) TRACE_E(7);
                 uint32_t hr[32];
-                TMEM_LD32(trow + (hf ? D2 : D3) + col0, hr);
+                TMEM_LD32(trow + (hf ? D2 : D1) + col0, hr);
                 tmem_wait_ld();
                 uint8_t* dst = hf ? a_base : x_base;
 #pragma unroll
@@ -620,15 +727,27 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                                              fmaxf(acc_f(hr[8 * j + 2]), 0.f), fmaxf(acc_f(hr[8 * j + 3]), 0.f)),
                                  make_float4(fmaxf(acc_f(hr[8 * j + 4]), 0.f), fmaxf(acc_f(hr[8 * j + 5]), 0.f),
                                              fmaxf(acc_f(hr[8 * j + 6]), 0.f), fmaxf(acc_f(hr[8 * j + 7]), 0.f)), hbad);
+                if (hf == 0) publish(x_ready);           // the first K half of mlp.2 goes while the second half is split
             }
             if (row < valid_rows) bad = fmaxf(bad, hbad);
             publish(a_ready);
             TRACE_E(8);
 
             // ---- E4: out = x + LayerNorm2(mlp(...)) -----------------------------------------
+            // what this thread does next: the following call of this tile, or call 0 of the CTA's next tile
+            const bool last_call = ci + 1 == P.n_calls;
+            const int n_tile = last_call ? tile + (int)gridDim.x : tile;
+            const CallArgs& NX = P.call[last_call ? 0 : ci + 1];
+            const bool has_next = n_tile < P.n_tiles;
+            const bool next_handoff = !last_call && !NX.is_self && NX.src == A.out;      // its source = the rows written below
             mbar_wait(d_ready, dph & 1); ++dph;
             tc_fence_after();
             TRACE_E(9);
+            // X is dead (mlp.2 complete).  Unless it is about to receive the next call's source, start fetching the next call's x
+            // into it now: rows this call does not write (the other map, or the next tile), ahead of this call's store burst
+            pre_valid = has_next && !next_handoff && NX.x != A.out;
+            if (pre_valid)
+                prefetch_tile_async(x_base, NX.x + (size_t)n_tile * ROWS * CH, min(PTS, P.N - n_tile * PTS) * TOK, ew, lane);
             {
                 uint32_t r[32];
                 float v[32];
@@ -653,15 +772,30 @@ loftr_layer_tc_kernel(const LayerArgs P) {
                     y.w = (v[4 * j + 3] - mean) * rstd * g.w + b.w;
                     reinterpret_cast<float4*>(stage_f + row * CH)[(colq * 8 + j) ^ (row & 31)] = y;
                 }
-                epi_bar();
+            }
+            epi_bar();
+            {
+                const float* stage_f = reinterpret_cast<const float*>(a_base);
                 float* og = A.out + g_row0 * CH;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int r2 = ew * 8 + i;
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (r2 < valid_rows) {
                         const float4 y = reinterpret_cast<const float4*>(stage_f + r2 * CH)[lane ^ (r2 & 31)];
                         const float4 xv = __ldcg(reinterpret_cast<const float4*>(xg + (size_t)r2 * CH) + lane);
-                        __stcg(reinterpret_cast<float4*>(og + (size_t)r2 * CH) + lane, make_float4(xv.x + y.x, xv.y + y.y, xv.z + y.z, xv.w + y.w));
+                        o = make_float4(xv.x + y.x, xv.y + y.y, xv.z + y.z, xv.w + y.w);
+                        __stcg(reinterpret_cast<float4*>(og + (size_t)r2 * CH) + lane, o);
+                    }
+                    if (next_handoff) {
+                        // these rows are the next call's source: split them into X right here (rows that do not exist: zeros)
+                        const int col = lane * 4;
+                        const uint32_t off = (uint32_t)(col >> 6) * SLAB + sw128(r2, (col & 63) >> 3) + (uint32_t)(col & 7) * 2u;
+                        RANGE_CHECK(o.x, o.y); RANGE_CHECK(o.z, o.w);
+                        uint2 hi, lo;
+                        split2(o.x, o.y, hi.x, lo.x); split2(o.z, o.w, hi.y, lo.y);
+                        *reinterpret_cast<uint2*>(x_base + off) = hi;
+                        *reinterpret_cast<uint2*>(x_base + 2 * SLAB + off) = lo;
                     }
                 }
                 epi_bar();                               // staging reads done (and this call's rows written) before the next call
@@ -693,9 +827,9 @@ loftr_pack_weights_kernel(const PackArgs P) {
     const int seg = t & 7, row = (t >> 3) & 127, c = t >> 10, blk = c >> 1, kb = c & 1;
     const float* W; int r0 = 0, c0 = 0, ld = CH;
     switch (blk) {
-        case 0: W = P.wq; break;
-        case 1: W = P.wk; break;
-        case 2: W = P.wv; break;
+        case 0: W = P.wk; break;                                 // k, v before q: after a hand-off their operand is ready first
+        case 1: W = P.wv; break;
+        case 2: W = P.wq; break;
         case 3: W = P.wm; break;
         case 4: W = P.w1; ld = 2 * CH; break;                    // mlp.0[:C, :C]   (x half of cat([x, message]))
         case 5: W = P.w1; ld = 2 * CH; r0 = CH; break;           // mlp.0[C:, :C]
