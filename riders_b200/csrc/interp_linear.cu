@@ -347,7 +347,8 @@ fill_value_kernel(float* __restrict__ out, size_t total, float fill) {
 }
 
 constexpr int RASTER_THREADS = 256;
-constexpr int RASTER_TRIS = 8;              // triangles per CTA; the 8 warps share each triangle's rows
+constexpr int RASTER_TRIS = 8;              // triangles per CTA
+constexpr int RASTER_WIDE = 64;             // bounding boxes wider than this (hull slivers) take the row path
 
 // value on the segment between knots (x0, y0, v0) and (x1, y1, v1) at pixel (px, py) of that segment, endpoints in
 // canonical (lexicographic) order so both triangles sharing the edge compute the same bits
@@ -358,21 +359,38 @@ __device__ __forceinline__ float edge_value(int x0, int y0, float v0, int x1, in
     return (float)(((double)w0 * (double)v0 + (double)w1 * (double)v1) / (double)(w0 + w1));
 }
 
-// per-triangle constants of the rasteriser, set up once by one warp and then shared by the CTA
-struct TriSetup {
-    int Aa, Ab, Ac;                 // d(edge function)/dx: wa = orient(p, b, c), wb = orient(p, c, a), wc = orient(p, a, b)
-    int ax, ay, bx, by, cx, cy;
-    int x0, x1, y0, rows;           // clipped bounding box
-    float va, vb, vc;
-    double gx, gy;                  // the affine interpolant v = va + gx (x - ax) + gy (y - ay) (= the barycentric sum)
+// per-triangle constants of the rasteriser, set up once by one thread and then shared by the CTA (16-byte groups: LDS.128).
+// Edge functions as planes: wa = orient(p, b, c) = Aa x + Ba y + Ca, wb = orient(p, c, a), wc = orient(p, a, b); all exact in
+// int32 (coordinates < 2^13).  The interpolant is the affine function v = va + gx (x - ax) + gy (y - ay) (= the barycentric sum).
+struct __align__(16) TriSetup {
+    int Aa, Ba, Ca, Ab;
+    int Bb, Cb, Ac, Bc;
+    int Cc, x0, y0, bw;             // clipped bounding box: origin and width
+    float inv_bw, va; int ax, ay;
+    double gx, gy;
+    int bx, by, cx, cy;
+    float vb, vc; int x1, rows;
 };
 
-// The CTA's RASTER_TRIS triangles are flattened into one list of bounding-box ROWS, dealt round-robin to the warps: the
-// work of a CTA is balanced whatever the triangle sizes (a hull sliver, or a frame with three knots, no longer serialises
-// on one warp).  A pixel is written iff its three exact integer edge functions are >= 0.
+__device__ __forceinline__ void shade_pixel(const TriSetup& t, int x, int y, int wa, int wb, int wc, float* __restrict__ o, int W) {
+    float v;
+    if (wa == 0) v = edge_value(t.bx, t.by, t.vb, t.cx, t.cy, t.vc, x, y);                       // on edge b-c (or at b / c)
+    else if (wb == 0) v = edge_value(t.cx, t.cy, t.vc, t.ax, t.ay, t.va, x, y);
+    else if (wc == 0) v = edge_value(t.ax, t.ay, t.va, t.bx, t.by, t.vb, x, y);
+    else v = (float)fma(t.gx, (double)(x - t.ax), fma(t.gy, (double)(y - t.ay), (double)t.va));
+    o[(size_t)y * W + x] = v;
+}
+
+// A pixel is written iff its three exact integer edge functions are >= 0.  The CTA's RASTER_TRIS triangles are flattened:
+//  * bounding boxes up to RASTER_WIDE pixels wide into one list of bounding-box PIXELS dealt to the 256 threads - every lane
+//    tests a pixel of some box (round 2's first version dealt box ROWS to warps: a 25-pixel-wide triangle used 12 of the 32
+//    lanes of every row and paid the row set-up 25 times);
+//  * wider ones (hull slivers, frames with a handful of knots) into a list of box rows dealt to the warps, each row clipped
+//    to its conservative span first, so a 600-pixel sliver costs its area and not its box.
 __global__ void __launch_bounds__(RASTER_THREADS)
 raster_kernel(uint8_t* ws_base, WsLayout L, int max_knots, int H, int W, float* __restrict__ out) {
     __shared__ TriSetup s_tri[RASTER_TRIS];
+    __shared__ int s_slot0[RASTER_TRIS + 1];
     __shared__ int s_row0[RASTER_TRIS + 1];
     const int frame = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int* counters = (const int*)(ws_base + L.counters) + (size_t)frame * CNT_STRIDE;
@@ -380,32 +398,60 @@ raster_kernel(uint8_t* ws_base, WsLayout L, int max_knots, int H, int W, float* 
     const int nt = min(counters[CNT_TRIS], 2 * max_knots);
     if ((int)blockIdx.x * RASTER_TRIS >= nt) return;
     float* o = out + (size_t)frame * H * W;
-    const int ti = blockIdx.x * RASTER_TRIS + warp;
-    if (lane == 0) {
-        TriSetup u;
-        u.rows = 0;
-        if (ti < nt) {
-            const TriRec t = tris[ti];
-            u.ax = t.ax; u.ay = t.ay; u.bx = t.bx; u.by = t.by; u.cx = t.cx; u.cy = t.cy;
-            u.va = t.va; u.vb = t.vb; u.vc = t.vc;
-            u.Aa = t.by - t.cy; u.Ab = t.cy - t.ay; u.Ac = t.ay - t.by;
-            u.x0 = max(min(t.ax, min(t.bx, t.cx)), 0); u.x1 = min(max(t.ax, max(t.bx, t.cx)), W - 1);
-            u.y0 = max(min(t.ay, min(t.by, t.cy)), 0);
-            u.rows = min(max(t.ay, max(t.by, t.cy)), H - 1) - u.y0 + 1;
-            const double det = (double)((t.bx - t.ax) * (t.cy - t.ay) - (t.by - t.ay) * (t.cx - t.ax));
-            const double dvb = (double)t.vb - (double)t.va, dvc = (double)t.vc - (double)t.va;
-            u.gx = (dvb * (double)(t.cy - t.ay) - dvc * (double)(t.by - t.ay)) / det;
-            u.gy = ((double)(t.bx - t.ax) * dvc - (double)(t.cx - t.ax) * dvb) / det;
+    if (warp == 0) {
+        const int ti = blockIdx.x * RASTER_TRIS + lane;
+        int slots = 0, wrows = 0;
+        if (lane < RASTER_TRIS) {
+            TriSetup u;
+            u.rows = 0; u.bw = 1; u.inv_bw = 1.f;
+            if (ti < nt) {
+                const TriRec t = tris[ti];
+                u.ax = t.ax; u.ay = t.ay; u.bx = t.bx; u.by = t.by; u.cx = t.cx; u.cy = t.cy;
+                u.va = t.va; u.vb = t.vb; u.vc = t.vc;
+                u.Aa = t.by - t.cy; u.Ba = t.cx - t.bx; u.Ca = t.bx * t.cy - t.cx * t.by;
+                u.Ab = t.cy - t.ay; u.Bb = t.ax - t.cx; u.Cb = t.cx * t.ay - t.ax * t.cy;
+                u.Ac = t.ay - t.by; u.Bc = t.bx - t.ax; u.Cc = t.ax * t.by - t.bx * t.ay;
+                u.x0 = max(min(t.ax, min(t.bx, t.cx)), 0); u.x1 = min(max(t.ax, max(t.bx, t.cx)), W - 1);
+                u.y0 = max(min(t.ay, min(t.by, t.cy)), 0);
+                u.rows = max(min(max(t.ay, max(t.by, t.cy)), H - 1) - u.y0 + 1, 0);
+                u.bw = max(u.x1 - u.x0 + 1, 1);
+                u.inv_bw = 1.0f / (float)u.bw;
+                const double det = (double)((t.bx - t.ax) * (t.cy - t.ay) - (t.by - t.ay) * (t.cx - t.ax));
+                const double dvb = (double)t.vb - (double)t.va, dvc = (double)t.vc - (double)t.va;
+                u.gx = (dvb * (double)(t.cy - t.ay) - dvc * (double)(t.by - t.ay)) / det;
+                u.gy = ((double)(t.bx - t.ax) * dvc - (double)(t.cx - t.ax) * dvb) / det;
+                if (u.bw <= RASTER_WIDE) slots = u.bw * u.rows; else wrows = u.rows;
+            }
+            s_tri[lane] = u;
         }
-        s_tri[warp] = u;
+        int ps = slots, pr = wrows;                      // inclusive scans over the first RASTER_TRIS lanes
+#pragma unroll
+        for (int d = 1; d < RASTER_TRIS; d <<= 1) {
+            const int a = __shfl_up_sync(FULL, ps, d), b2 = __shfl_up_sync(FULL, pr, d);
+            if (lane >= d) { ps += a; pr += b2; }
+        }
+        if (lane < RASTER_TRIS) { s_slot0[lane + 1] = ps; s_row0[lane + 1] = pr; }
+        if (lane == 0) { s_slot0[0] = 0; s_row0[0] = 0; }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int i = 0; i < RASTER_TRIS; ++i) { s_row0[i] = acc; acc += s_tri[i].rows; }
-        s_row0[RASTER_TRIS] = acc;
+    // ---- narrow boxes: one pixel of some box per thread and step ----------------------------------------------------------
+    const int total = s_slot0[RASTER_TRIS];
+    for (int s = threadIdx.x; s < total; s += RASTER_THREADS) {
+        int cur = 0;
+#pragma unroll
+        for (int step = RASTER_TRIS / 2; step > 0; step >>= 1)
+            if (s >= s_slot0[cur + step]) cur += step;
+        const TriSetup& t = s_tri[cur];
+        const int4 q0 = *reinterpret_cast<const int4*>(&t.Aa), q1 = *reinterpret_cast<const int4*>(&t.Bb), q2 = *reinterpret_cast<const int4*>(&t.Cc);
+        const int local = s - s_slot0[cur], bw = q2.w;
+        int r = (int)((float)local * t.inv_bw);          // local < 2^24: exact in float; the quotient is off by at most one
+        int c = local - r * bw;
+        if (c < 0) { --r; c += bw; } else if (c >= bw) { ++r; c -= bw; }
+        const int x = q2.y + c, y = q2.z + r;
+        const int wa = q0.x * x + q0.y * y + q0.z, wb = q0.w * x + q1.x * y + q1.y, wc = q1.z * x + q1.w * y + q2.x;
+        if ((wa | wb | wc) >= 0) shade_pixel(t, x, y, wa, wb, wc, o, W);
     }
-    __syncthreads();
+    // ---- wide boxes: their rows, dealt round-robin to the warps ------------------------------------------------------------
     const int total_rows = s_row0[RASTER_TRIS];
     int cur = 0;
     for (int r = warp; r < total_rows; r += RASTER_THREADS / 32) {
@@ -413,34 +459,18 @@ raster_kernel(uint8_t* ws_base, WsLayout L, int max_knots, int H, int W, float* 
         const TriSetup& t = s_tri[cur];
         const int y = t.y0 + (r - s_row0[cur]);
         const int Aa = t.Aa, Ab = t.Ab, Ac = t.Ac;
-        const int Ca = t.bx * (t.cy - y) - t.cx * (t.by - y);
-        const int Cb = t.cx * (t.ay - y) - t.ax * (t.cy - y);
-        const int Cc = t.ax * (t.by - y) - t.bx * (t.ay - y);
-        int xs = t.x0, xe = t.x1;
-        if (xe - xs >= 48) {
-            // wide bounding box (hull slivers): the row's conservative x span from the three half-planes, in float; the exact
-            // integer test below then only visits the chunks near the triangle
-            float lo = (float)xs, hi = (float)xe;
-            if (Aa > 0) lo = fmaxf(lo, -(float)Ca / (float)Aa - 0.02f); else if (Aa < 0) hi = fminf(hi, (float)Ca / (float)(-Aa) + 0.02f); else if (Ca < 0) continue;
-            if (Ab > 0) lo = fmaxf(lo, -(float)Cb / (float)Ab - 0.02f); else if (Ab < 0) hi = fminf(hi, (float)Cb / (float)(-Ab) + 0.02f); else if (Cb < 0) continue;
-            if (Ac > 0) lo = fmaxf(lo, -(float)Cc / (float)Ac - 0.02f); else if (Ac < 0) hi = fminf(hi, (float)Cc / (float)(-Ac) + 0.02f); else if (Cc < 0) continue;
-            xs = max(xs, (int)floorf(lo)); xe = min(xe, (int)ceilf(hi));
-        }
-        const double vrow = fma(t.gy, (double)(y - t.ay), (double)t.va);
-        const double gx = t.gx;
-        const int ax = t.ax;
-        float* orow = o + (size_t)y * W;
+        const int Ca = t.Ba * y + t.Ca, Cb = t.Bb * y + t.Cb, Cc = t.Bc * y + t.Cc;
+        // the row's conservative x span from the three half-planes, in float; the exact integer test below then only visits
+        // the chunks near the triangle
+        float lo = (float)t.x0, hi = (float)t.x1;
+        if (Aa > 0) lo = fmaxf(lo, -(float)Ca / (float)Aa - 0.02f); else if (Aa < 0) hi = fminf(hi, (float)Ca / (float)(-Aa) + 0.02f); else if (Ca < 0) continue;
+        if (Ab > 0) lo = fmaxf(lo, -(float)Cb / (float)Ab - 0.02f); else if (Ab < 0) hi = fminf(hi, (float)Cb / (float)(-Ab) + 0.02f); else if (Cb < 0) continue;
+        if (Ac > 0) lo = fmaxf(lo, -(float)Cc / (float)Ac - 0.02f); else if (Ac < 0) hi = fminf(hi, (float)Cc / (float)(-Ac) + 0.02f); else if (Cc < 0) continue;
+        const int xs = max(t.x0, (int)floorf(lo)), xe = min(t.x1, (int)ceilf(hi));
         for (int xb = xs; xb <= xe; xb += 32) {
             const int x = xb + lane;
             const int wa = Aa * x + Ca, wb = Ab * x + Cb, wc = Ac * x + Cc;
-            if (x <= xe && (wa | wb | wc) >= 0) {
-                float v;
-                if (wa == 0) v = edge_value(t.bx, t.by, t.vb, t.cx, t.cy, t.vc, x, y);           // on edge b-c (or at b / c)
-                else if (wb == 0) v = edge_value(t.cx, t.cy, t.vc, t.ax, t.ay, t.va, x, y);
-                else if (wc == 0) v = edge_value(t.ax, t.ay, t.va, t.bx, t.by, t.vb, x, y);
-                else v = (float)fma(gx, (double)(x - ax), vrow);
-                orow[x] = v;
-            }
+            if (x <= xe && (wa | wb | wc) >= 0) shade_pixel(t, x, y, wa, wb, wc, o, W);
         }
     }
 }
