@@ -40,7 +40,7 @@ struct TriRec {            // 48 bytes
 };
 
 // per-frame counters in the workspace
-enum { CNT_TRIS = 0, CNT_OVERFLOW = 1, CNT_DONE = 2, CNT_STRIDE = 8 };
+enum { CNT_TRIS = 0, CNT_OVERFLOW = 1, CNT_DONE = 2, CNT_NEXT = 3, CNT_STRIDE = 8 };
 
 struct WsLayout { size_t counters, tris, total; };
 
@@ -203,8 +203,14 @@ delaunay_star_kernel(const int32_t* __restrict__ knot_xy, const float* __restric
     __syncthreads();
     const bool sorted = s_unsorted == 0;
 
-    const int p = blockIdx.x * STAR_WARPS + warp;
-    if (p < n) {
+    // Stars are handed out dynamically (one atomic per star): a warp that drew a cheap interior knot takes the next one while
+    // a hull knot - whose exterior wedge keeps its scan open to the end of the list - is still running elsewhere.  (With one
+    // fixed star per warp the CTA waited for its slowest warp: ncu showed 4.2 barrier-stall cycles per issued instruction.)
+    for (;;) {
+        int p = 0;
+        if (lane == 0) p = atomicAdd(&counters[CNT_NEXT], 1);
+        p = __shfl_sync(FULL, p, 0);
+        if (p >= n) break;
         const int px = s_pts[p] & 0xffff, py = s_pts[p] >> 16;
         WarpStar st;
         st.ex = st.ey = st.eid = 0; st.k = 0;
@@ -350,13 +356,22 @@ constexpr int RASTER_THREADS = 256;
 constexpr int RASTER_TRIS = 8;              // triangles per CTA
 constexpr int RASTER_WIDE = 64;             // bounding boxes wider than this (hull slivers) take the row path
 
-// value on the segment between knots (x0, y0, v0) and (x1, y1, v1) at pixel (px, py) of that segment, endpoints in
-// canonical (lexicographic) order so both triangles sharing the edge compute the same bits
-__device__ __forceinline__ float edge_value(int x0, int y0, float v0, int x1, int y1, float v1, int px, int py) {
-    if (x0 > x1 || (x0 == x1 && y0 > y1)) { int t = x0; x0 = x1; x1 = t; t = y0; y0 = y1; y1 = t; float f = v0; v0 = v1; v1 = f; }
+// Pixels exactly ON an edge (or at a knot) belong to both triangles that share it: their value is computed from the edge alone, in
+// a canonical form - endpoints in lexicographic order, weights w0 = |p1 - p| and w1 = |p - p0| along the axis the edge advances on,
+// v = (w0 v0 + w1 v1) * (1 / (w0 + w1)) in double - so both triangles write the same bits whichever comes last.
+struct EdgeCanon { int x0, y0, x1, y1; float v0, v1; double inv_len; };
+__device__ __forceinline__ EdgeCanon canon_edge(int x0, int y0, float v0, int x1, int y1, float v1) {
+    EdgeCanon e;
+    const bool swap = x0 > x1 || (x0 == x1 && y0 > y1);
+    e.x0 = swap ? x1 : x0; e.y0 = swap ? y1 : y0; e.v0 = swap ? v1 : v0;
+    e.x1 = swap ? x0 : x1; e.y1 = swap ? y0 : y1; e.v1 = swap ? v0 : v1;
+    e.inv_len = 1.0 / (double)(e.x1 != e.x0 ? e.x1 - e.x0 : e.y1 - e.y0);
+    return e;
+}
+__device__ __forceinline__ float edge_value(int x0, int y0, float v0, int x1, int y1, float v1, double inv_len, int px, int py) {
     int w0, w1;
     if (x1 != x0) { w0 = x1 - px; w1 = px - x0; } else { w0 = y1 - py; w1 = py - y0; }
-    return (float)(((double)w0 * (double)v0 + (double)w1 * (double)v1) / (double)(w0 + w1));
+    return (float)(fma((double)w0, (double)v0, (double)w1 * (double)v1) * inv_len);
 }
 
 // per-triangle constants of the rasteriser, set up once by one thread and then shared by the CTA (16-byte groups: LDS.128).
@@ -368,16 +383,18 @@ struct __align__(16) TriSetup {
     int Cc, x0, y0, bw;             // clipped bounding box: origin and width
     float inv_bw, va; int ax, ay;
     double gx, gy;
-    int bx, by, cx, cy;
-    float vb, vc; int x1, rows;
+    int x1, rows, pad0, pad1;
+    EdgeCanon ebc, eca, eab;        // the three edges in canonical form (pixels with wa == 0, wb == 0, wc == 0)
 };
 
 __device__ __forceinline__ void shade_pixel(const TriSetup& t, int x, int y, int wa, int wb, int wc, float* __restrict__ o, int W) {
     float v;
-    if (wa == 0) v = edge_value(t.bx, t.by, t.vb, t.cx, t.cy, t.vc, x, y);                       // on edge b-c (or at b / c)
-    else if (wb == 0) v = edge_value(t.cx, t.cy, t.vc, t.ax, t.ay, t.va, x, y);
-    else if (wc == 0) v = edge_value(t.ax, t.ay, t.va, t.bx, t.by, t.vb, x, y);
-    else v = (float)fma(t.gx, (double)(x - t.ax), fma(t.gy, (double)(y - t.ay), (double)t.va));
+    if (wa == 0 || wb == 0 || wc == 0) {                 // on an edge (or at a knot): one evaluation, whichever edge it is
+        const EdgeCanon& e = wa == 0 ? t.ebc : (wb == 0 ? t.eca : t.eab);
+        v = edge_value(e.x0, e.y0, e.v0, e.x1, e.y1, e.v1, e.inv_len, x, y);
+    } else {
+        v = (float)fma(t.gx, (double)(x - t.ax), fma(t.gy, (double)(y - t.ay), (double)t.va));
+    }
     o[(size_t)y * W + x] = v;
 }
 
@@ -387,7 +404,7 @@ __device__ __forceinline__ void shade_pixel(const TriSetup& t, int x, int y, int
 //    lanes of every row and paid the row set-up 25 times);
 //  * wider ones (hull slivers, frames with a handful of knots) into a list of box rows dealt to the warps, each row clipped
 //    to its conservative span first, so a 600-pixel sliver costs its area and not its box.
-__global__ void __launch_bounds__(RASTER_THREADS)
+__global__ void __launch_bounds__(RASTER_THREADS, 4)
 raster_kernel(uint8_t* ws_base, WsLayout L, int max_knots, int H, int W, float* __restrict__ out) {
     __shared__ TriSetup s_tri[RASTER_TRIS];
     __shared__ int s_slot0[RASTER_TRIS + 1];
@@ -403,11 +420,13 @@ raster_kernel(uint8_t* ws_base, WsLayout L, int max_knots, int H, int W, float* 
         int slots = 0, wrows = 0;
         if (lane < RASTER_TRIS) {
             TriSetup u;
-            u.rows = 0; u.bw = 1; u.inv_bw = 1.f;
+            u.rows = 0; u.bw = 1; u.inv_bw = 1.f; u.pad0 = u.pad1 = 0;
             if (ti < nt) {
                 const TriRec t = tris[ti];
-                u.ax = t.ax; u.ay = t.ay; u.bx = t.bx; u.by = t.by; u.cx = t.cx; u.cy = t.cy;
-                u.va = t.va; u.vb = t.vb; u.vc = t.vc;
+                u.ax = t.ax; u.ay = t.ay; u.va = t.va;
+                u.ebc = canon_edge(t.bx, t.by, t.vb, t.cx, t.cy, t.vc);
+                u.eca = canon_edge(t.cx, t.cy, t.vc, t.ax, t.ay, t.va);
+                u.eab = canon_edge(t.ax, t.ay, t.va, t.bx, t.by, t.vb);
                 u.Aa = t.by - t.cy; u.Ba = t.cx - t.bx; u.Ca = t.bx * t.cy - t.cx * t.by;
                 u.Ab = t.cy - t.ay; u.Bb = t.ax - t.cx; u.Cb = t.cx * t.ay - t.ax * t.cy;
                 u.Ac = t.ay - t.by; u.Bc = t.bx - t.ax; u.Cc = t.ax * t.by - t.bx * t.ay;
@@ -563,7 +582,21 @@ static int interp_triangulate_impl(const int32_t* knot_xy, const float* knot_val
     if (smem > 48 * 1024)
         if (int rc_smem = ensure_dynamic_smem(delaunay_star_kernel, smem, configured, "interp_triangulate: smem attribute")) return rc_smem;
     count_launches(1);
-    dim3 grid(ceil_div(max_knots, STAR_WARPS), B);
+    // CTAs per frame: the resident capacity of the device shared among the frames (one wave; the warps then draw stars until
+    // the frame's list is exhausted), at most one warp per knot
+    static int capacity[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (capacity[dev] == 0) {
+        int sms = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, delaunay_star_kernel, STAR_THREADS, smem);
+        capacity[dev] = max(sms * max(per_sm, 1), 1);
+        cudaGetLastError();
+    }
+    const int per_frame = min(max(capacity[dev] / B, 1), ceil_div(max_knots, STAR_WARPS));
+    dim3 grid(per_frame, B);
     delaunay_star_kernel<<<grid, STAR_THREADS, smem, st>>>(knot_xy, knot_val, knot_count, max_knots, (uint8_t*)workspace, L,
                                                            status, tri_out, tri_count, fill_out, fill, npx);
     return check_launch("interp_triangulate");
