@@ -42,30 +42,38 @@ __device__ __forceinline__ void st_tok(void* p, size_t i, int dt, float v) {
 // Every operand is float32 or bfloat16 (token tensors), accumulation in float32.  64 x 64 x 16 tiles, 4 x 4 outputs per thread,
 // fixed summation order.
 // ----------------------------------------------------------------------------------------------
-constexpr int TM = 64, TN = 64, TK = 16;
-
+constexpr int TM = 64, TN = 64, TK = 32;
 // blockIdx.z = K split: this CTA covers k in [z * kchunk, min(K, (z + 1) * kchunk)).  With gridDim.z > 1 the tile goes to
 // part[z][M][N] (float32) and splitk_reduce_kernel adds the splits in index order (deterministic) into C.  The next K tile is
 // fetched into registers while the current one is multiplied (the K loop was global-load-latency bound: the weight-gradient
 // products have K = all tokens and only a handful of output tiles - 63 of the first 87 ms of a training step).
+// TMv = 32 halves the tile height for products that would otherwise leave SMs idle (2520 tokens x 128 columns = 80 tiles of
+// 64 x 64 on 148 SMs); TK = 32 halves the number of load -> barrier -> multiply rounds of the latency-bound K loop.
+template <int TMv>
 __global__ void __launch_bounds__(256)
 gemm_kernel(const void* __restrict__ A, int lda, int ta, int dta, const void* __restrict__ B, int ldb, int tb, int dtb,
             void* __restrict__ Cm, int ldc, int dtc, int M, int N, int K, int accumulate, int kchunk, float* __restrict__ part) {
-    __shared__ float As[TK][TM + 1];
+    constexpr int RM = TMv / 16;                         // output rows per thread
+    constexpr int UA = TMv * TK / 256, UB = TN * TK / 256;
+    __shared__ float As[TK][TMv + 1];
     __shared__ float Bs[TK][TN + 1];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+    const int m0 = blockIdx.x * TMv, n0 = blockIdx.y * TN;
     const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
-    float acc[4][4] = {};
-    float ra[4], rb[4];
+    float acc[RM][4] = {};
+    float ra[UA], rb[UB];
     auto fetch = [&](int k0) {
+        // consecutive threads walk the contiguous dimension of each operand
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < UA; ++u) {
             const int e = tid + u * 256;
-            // consecutive threads walk the contiguous dimension of each operand
-            const int mi = ta ? e % TM : e / TK, ki = ta ? e / TM : e % TK;
+            const int mi = ta ? e % TMv : e / TK, ki = ta ? e / TMv : e % TK;
             const int gm = m0 + mi, gk = k0 + ki;
             ra[u] = (gm < M && gk < kend) ? ld_tok(A, ta ? (size_t)gk * lda + gm : (size_t)gm * lda + gk, dta) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const int e = tid + u * 256;
             const int ni = tb ? e / TK : e % TN, kj = tb ? e % TK : e / TN;
             const int gn = n0 + ni, gk2 = k0 + kj;
             rb[u] = (gn < N && gk2 < kend) ? ld_tok(B, tb ? (size_t)gn * ldb + gk2 : (size_t)gk2 * ldb + gn, dtb) : 0.f;
@@ -73,10 +81,14 @@ gemm_kernel(const void* __restrict__ A, int lda, int ta, int dta, const void* __
     };
     auto stash = [&]() {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < UA; ++u) {
             const int e = tid + u * 256;
-            const int mi = ta ? e % TM : e / TK, ki = ta ? e / TM : e % TK;
+            const int mi = ta ? e % TMv : e / TK, ki = ta ? e / TMv : e % TK;
             As[ki][mi] = ra[u];
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const int e = tid + u * 256;
             const int ni = tb ? e / TK : e % TN, kj = tb ? e % TK : e / TN;
             Bs[kj][ni] = rb[u];
         }
@@ -88,19 +100,21 @@ gemm_kernel(const void* __restrict__ A, int lda, int ta, int dta, const void* __
         if (k0 + TK < kend) fetch(k0 + TK);
 #pragma unroll
         for (int kk = 0; kk < TK; ++kk) {
-            float a[4], b[4];
+            float a[RM], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+            for (int i = 0; i < RM; ++i) a[i] = As[kk][ty * RM + i];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < RM; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int gm = m0 + ty * 4 + i;
+    for (int i = 0; i < RM; ++i) {
+        const int gm = m0 + ty * RM + i;
         if (gm >= M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -138,8 +152,12 @@ static void gemm(const void* A, int lda, bool ta, int dta, const void* B, int ld
         splits = ceil_div(K, kchunk);
     }
     count_launches(splits > 1 ? 2 : 1);
-    gemm_kernel<<<dim3(ceil_div(M, TM), ceil_div(N, TN), splits), 256, 0, st>>>(A, lda, ta, dta, B, ldb, tb, dtb, C, ldc, dtc, M, N, K,
-                                                                                 accumulate, kchunk, part);
+    if (ceil_div(M, TM) * ceil_div(N, TN) * splits < 148)        // would leave SMs idle: half-height tiles
+        gemm_kernel<32><<<dim3(ceil_div(M, 32), ceil_div(N, TN), splits), 256, 0, st>>>(A, lda, ta, dta, B, ldb, tb, dtb, C, ldc, dtc, M, N, K,
+                                                                                        accumulate, kchunk, part);
+    else
+        gemm_kernel<TM><<<dim3(ceil_div(M, TM), ceil_div(N, TN), splits), 256, 0, st>>>(A, lda, ta, dta, B, ldb, tb, dtb, C, ldc, dtc, M, N, K,
+                                                                                        accumulate, kchunk, part);
     if (splits > 1)
         splitk_reduce_kernel<<<ceil_div(M * N, 256), 256, 0, st>>>(part, splits, C, ldc, dtc, M, N, accumulate);
 }

@@ -347,41 +347,87 @@ struct GatherBwdLevel {
     float scale;
 };
 
+// One thread per feature element sums, in RoI order (deterministic, no atomics), the gradients of the bins whose argmax is that
+// element.  The CTA first compacts - in order - the RoIs of its frame whose row range meets the rows its 256 consecutive elements
+// cover (axis arithmetic done once per RoI and CTA, kept in shared memory), so a thread visits a handful of candidates instead of
+// re-deriving the bin geometry of every RoI of the batch (the first version: 37 us per RoI, 15 % of the training step).
+struct BwdCand { int b, ys, yext, xs, xext, r; float ybin, xbin; };
+constexpr int BWD_CHUNK = GEN_THREADS;
+
 template <bool NHWC>
 __global__ void __launch_bounds__(GEN_THREADS)
 roi_gather_bwd_kernel(const GatherBwdLevel L, const float* __restrict__ rois, int R, int B) {
+    __shared__ BwdCand s_c[BWD_CHUNK];
+    __shared__ int s_warp[GEN_THREADS / 32];
     const long long n = (long long)B * L.C * L.H * L.W;
-    const long long e0 = (long long)blockIdx.x * GEN_THREADS + threadIdx.x;
-    if (e0 >= n) return;
-    long long e = e0;
+    const long long first = (long long)blockIdx.x * GEN_THREADS;
+    const long long e0 = first + threadIdx.x;
+    const bool active = e0 < n;
+    long long e = active ? e0 : n - 1;
     int b, c, h, w;
     if (NHWC) { c = (int)(e % L.C); e /= L.C; w = (int)(e % L.W); e /= L.W; h = (int)(e % L.H); b = (int)(e / L.H); }
     else      { w = (int)(e % L.W); e /= L.W; h = (int)(e % L.H); e /= L.H; c = (int)(e % L.C); b = (int)(e / L.C); }
     const int me = h * L.W + w;
+    // rows covered by this CTA (when all its elements lie in one H x W plane: one frame for NHWC, one (frame, channel) for NCHW)
+    const long long last = min(first + GEN_THREADS - 1, n - 1);
+    const long long plane = NHWC ? (long long)L.H * L.W * L.C : (long long)L.H * L.W;
+    const long long row_len = NHWC ? (long long)L.W * L.C : (long long)L.W;
+    const bool one_plane = first / plane == last / plane;
+    const int h_lo = (int)((first % plane) / row_len), h_hi = (int)((last % plane) / row_len);
+    const int b_lo = (int)(first / ((long long)L.C * L.H * L.W)), b_hi = (int)(last / ((long long)L.C * L.H * L.W));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float acc = 0.f;
-    for (int r = 0; r < R; ++r) {
-        const float* roi = rois + (size_t)r * 5;
-        if ((int)roi[0] != b) continue;
-        const RoiAxis ax = roi_axis(roi[1], roi[3], L.scale, L.ow);
-        const RoiAxis ay = roi_axis(roi[2], roi[4], L.scale, L.oh);
-        const int hr = h - ay.start, wr = w - ax.start;
-        if (hr < 0 || wr < 0 || hr > ay.extent || wr > ax.extent) continue;
-        const int ie = (int)((float)hr / ay.bin), je = (int)((float)wr / ax.bin);
-        for (int i = max(ie - 2, 0); i <= min(ie + 2, L.oh - 1); ++i) {
-            int h0, h1;
-            roi_bin_range(ay, i, L.H, h0, h1);
-            if (h < h0 || h >= h1) continue;
-            for (int j = max(je - 2, 0); j <= min(je + 2, L.ow - 1); ++j) {
-                int w0, w1;
-                roi_bin_range(ax, j, L.W, w0, w1);
-                if (w < w0 || w >= w1) continue;
-                const size_t o = NHWC ? ((((size_t)r * L.oh + i) * L.ow + j) * L.C + c)
-                                      : ((((size_t)r * L.C + c) * L.oh + i) * L.ow + j);
-                if (L.argmax[o] == me) acc += L.grad_out[o];
+    for (int r0 = 0; r0 < R; r0 += BWD_CHUNK) {
+        // ---- ordered compaction of the chunk's RoIs that can touch this CTA ------------------------------------------------
+        const int r = r0 + threadIdx.x;
+        bool keep = false;
+        BwdCand cd;
+        if (r < R) {
+            const float* roi = rois + (size_t)r * 5;
+            cd.b = (int)roi[0]; cd.r = r;
+            const RoiAxis ax = roi_axis(roi[1], roi[3], L.scale, L.ow);
+            const RoiAxis ay = roi_axis(roi[2], roi[4], L.scale, L.oh);
+            cd.ys = ay.start; cd.yext = ay.extent; cd.ybin = ay.bin;
+            cd.xs = ax.start; cd.xext = ax.extent; cd.xbin = ax.bin;
+            keep = cd.b >= b_lo && cd.b <= b_hi && (!one_plane || (cd.ys <= h_hi && cd.ys + cd.yext >= h_lo));
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int off = 0, total = 0;
+#pragma unroll
+        for (int i = 0; i < GEN_THREADS / 32; ++i) { const int v = s_warp[i]; if (i < warp) off += v; total += v; }
+        if (keep) s_c[off + __popc(m & ((1u << lane) - 1))] = cd;
+        __syncthreads();
+        // ---- this element against the candidates, in RoI order --------------------------------------------------------------
+        if (active) {
+            for (int k = 0; k < total; ++k) {
+                const BwdCand q = s_c[k];
+                if (q.b != b) continue;
+                const int hr = h - q.ys, wr = w - q.xs;
+                if (hr < 0 || wr < 0 || hr > q.yext || wr > q.xext) continue;
+                RoiAxis ax, ay;
+                ax.start = q.xs; ax.extent = q.xext; ax.bin = q.xbin;
+                ay.start = q.ys; ay.extent = q.yext; ay.bin = q.ybin;
+                const int ie = (int)((float)hr / ay.bin), je = (int)((float)wr / ax.bin);
+                for (int i = max(ie - 2, 0); i <= min(ie + 2, L.oh - 1); ++i) {
+                    int h0, h1;
+                    roi_bin_range(ay, i, L.H, h0, h1);
+                    if (h < h0 || h >= h1) continue;
+                    for (int j = max(je - 2, 0); j <= min(je + 2, L.ow - 1); ++j) {
+                        int w0, w1;
+                        roi_bin_range(ax, j, L.W, w0, w1);
+                        if (w < w0 || w >= w1) continue;
+                        const size_t o = NHWC ? ((((size_t)q.r * L.oh + i) * L.ow + j) * L.C + c)
+                                              : ((((size_t)q.r * L.C + c) * L.oh + i) * L.ow + j);
+                        if (L.argmax[o] == me) acc += L.grad_out[o];
+                    }
+                }
             }
         }
+        __syncthreads();                                 // the list is rewritten by the next chunk
     }
-    L.grad_feat[e0] += acc;
+    if (active) L.grad_feat[e0] += acc;
 }
 
 // ---------------------------------------------------------------------------------------------
