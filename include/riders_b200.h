@@ -353,6 +353,15 @@ int riders_decoder_tail_nhwc(const float* y4, int taps, int N, int h, int w,
                              const float* bias_a_host, const float* wb_frag, const float* bias_b_host,
                              const float* wh_host, float slope, int apply_sigmoid,
                              float* out, void* stream);
+/* The same fused tail on the 5th-generation tensor cores (tcgen05.mma kind::f16, accumulators in TMEM), streaming down strips
+ * of the map row by row (csrc/decoder_tail_tc.cu): operands are fp16 (11-bit significand like TF32) with fp32 accumulation.
+ * w_pack: DEVICE, 6144 bytes of fp16 built by ops._tail_tc_weights: for every horizontal tap dx the K-major no-swizzle B image
+ * [dx][row group n/8][K chunk c/8][n%8][c%8] of Wb stacked over its three kernel rows (n = 16 ky + co, 48 rows), then of Wh
+ * (n = ky, 16 rows of which 3 are used).  status: DEVICE int32 or NULL; bit 0 is OR-ed in when a staged value left the fp16
+ * range (|v| > 65504 or NaN) - the result is then invalid and the caller re-runs riders_decoder_tail_nhwc.              */
+int riders_decoder_tail_tc_nhwc(const float* y4, int taps, int N, int h, int w,
+                                const float* bias_a_host, const void* w_pack, const float* bias_b_host,
+                                float slope, int apply_sigmoid, float* out, int* status, void* stream);
 /* Sub-pixel phase convolution of the last decoder block in its 2x2-tap form (32 -> 4 x 16 channels), TF32, with the bias
  * + LeakyReLU of the convolution that produced x fused into the operand load (deconv1.conv -> deconv0.deconv of
  * MultiScaleDecoder, RCNet/networks.py:678-779): y4 (N, 64, h+1, w+1) = conv2x2(act(x + bias), W2, padding 1), x (N, 32, h, w)

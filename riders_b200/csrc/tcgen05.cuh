@@ -62,6 +62,40 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
+// fp16 operands, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// instruction descriptor: D fp32, A / B fp16 (format 0), both K-major, M = 128; N in bits 17..22
+constexpr uint32_t idesc_f16(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
+// K-major operand WITHOUT swizzle (the "interleaved" canonical layout ((8, m), (T, 2)) : ((16 B, SBO), (1, LBO))): a core matrix
+// is 8 rows x 16 bytes stored contiguously (rows 16 B apart), `sbo` bytes between 8-row groups, `lbo` bytes between the two
+// 16-byte K chunks of one 32-byte K step.  The start address only needs 16-byte alignment, so an operand can begin at ANY row
+// of a row-contiguous plane - what lets a convolution tap be a shifted view of one staged tile.
+__device__ __forceinline__ uint64_t smem_desc_nosw(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem_addr, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem_addr), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t tmem, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(cols) : "memory");
+}
+#define TMEM_LD16(taddr, r)                                                                                     \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                      \
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                              \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),   \
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),     \
+                   "=r"(r[15])                                                                                  \
+                 : "r"(taddr))
+#define TMEM_LD1(taddr, r) asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr))
+
 #define TMEM_LD32(taddr, r)                                                                                     \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                      \
                  "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"                                      \

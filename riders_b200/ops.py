@@ -518,6 +518,80 @@ def decoder_tail(y4, bias_a, weight_b, bias_b, weight_head, slope=0.2, taps=3, s
     return out
 
 
+_TAILTC_CACHE = {}
+
+
+def _tail_tc_weights(weight_b, weight_head):
+    """(16,16,3,3) + (1,16,3,3) -> the 6144-byte fp16 B-operand image of riders_decoder_tail_tc_nhwc: per horizontal tap dx a
+    K-major, unswizzled matrix [row group n // 8][K chunk c // 8][n % 8][c % 8]; rows n = 16 ky + co of Wb (48), then rows
+    n = ky of Wh (16, 3 used).  Cached per version of both parameters."""
+    def make():
+        dev = weight_b.device
+        wb, wh = weight_b.detach().float(), weight_head.detach().float()
+        dx = torch.arange(3, device=dev).view(3, 1, 1, 1, 1)
+        kc = torch.arange(2, device=dev).view(1, 1, 2, 1, 1)
+        nr = torch.arange(8, device=dev).view(1, 1, 1, 8, 1)
+        ke = torch.arange(8, device=dev).view(1, 1, 1, 1, 8)
+        n = torch.arange(6, device=dev).view(1, 6, 1, 1, 1) * 8 + nr
+        b = wb[n % 16, kc * 8 + ke, n // 16, dx]                                   # (3, 6, 2, 8, 8)
+        n = torch.arange(2, device=dev).view(1, 2, 1, 1, 1) * 8 + nr
+        hd = torch.where(n < 3, wh[0, kc * 8 + ke, n.clamp(max=2), dx], torch.zeros((), device=dev))    # (3, 2, 2, 8, 8)
+        return torch.cat([b.reshape(-1), hd.reshape(-1)]).to(torch.float16).contiguous()
+    ent = _TAILTC_CACHE.get(id(weight_b))
+    if (ent is not None and ent[0]() is weight_b and ent[1]() is weight_head
+            and ent[2] == (weight_b._version, weight_b.data_ptr(), weight_head._version, weight_head.data_ptr())):
+        return ent[3]
+    if len(_TAILTC_CACHE) > 64:
+        _TAILTC_CACHE.clear()
+    val = make()
+    _TAILTC_CACHE[id(weight_b)] = (weakref.ref(weight_b), weakref.ref(weight_head),
+                                   (weight_b._version, weight_b.data_ptr(), weight_head._version, weight_head.data_ptr()), val)
+    return val
+
+
+TAIL_MMA_SYNC, TAIL_TCGEN05 = 0, 1
+
+
+class TailOverflow(object):
+    """fp16-range guard of the tcgen05 decoder tail (``decoder_tail(impl=TAIL_TCGEN05)``): the kernel ORs 1 into ``flag`` when
+    a staged activation left the fp16 range; the caller then re-runs the TF32 mma.sync kernel.  Same protocol as
+    ``LoftrOverflow``: checked immediately, or collected in ``LoftrOverflow.pending`` with ``defer=True``."""
+
+    def __init__(self, flag, rerun):
+        self.flag, self.rerun = flag, rerun
+
+    def overflowed(self):
+        return bool(int(self.flag.item()))
+
+
+def decoder_tail_tc(y4, bias_a, weight_b, bias_b, weight_head, slope=0.2, taps=3, sigmoid=False, defer=False):
+    """``decoder_tail`` on tcgen05 / TMEM (fp16 operands, fp32 accumulation, csrc/decoder_tail_tc.cu).  A value outside the
+    fp16 range makes the call fall back to the TF32 mma.sync kernel (immediately, or at the caller's sync point with
+    ``defer=True``: the guard is appended to ``LoftrOverflow.pending``)."""
+    _need_cuda(y4, weight_b)
+    t = 1 if taps == 2 else 0
+    N, C4 = y4.shape[:2]
+    h, w = y4.shape[2] - t, y4.shape[3] - t
+    if not (_is_channels_last(y4) and y4.dtype == torch.float32 and C4 == 64 and tuple(weight_b.shape) == (16, 16, 3, 3)
+            and tuple(weight_head.shape) == (1, 16, 3, 3) and h > 0 and w > 0):
+        raise _lib.RidersError("decoder_tail_tc: needs a channels_last float32 (N,64,h,w) map, a (16,16,3,3) and a (1,16,3,3) weight")
+    pack = _tail_tc_weights(weight_b, weight_head)
+    ha, hb = _host_floats(bias_a), _host_floats(bias_b)
+    out = torch.empty((N, 1, 2 * h, 2 * w), device=y4.device, dtype=torch.float32)
+    flag = torch.zeros(1, dtype=torch.int32, device=y4.device)
+    with _span("decoder_tail", N * 4 * h * w * (16 * 16 * 9 + 16 * 9) * 2):
+        rc = _lib.lib().riders_decoder_tail_tc_nhwc(_ptr(y4), int(taps), N, h, w, _ptr(ha), _ptr(pack), _ptr(hb),
+                                                    float(slope), 1 if sigmoid else 0, _ptr(out), _ptr(flag), _stream())
+    _lib.check(rc, "riders_decoder_tail_tc_nhwc")
+    if N > 0:
+        guard = TailOverflow(flag, lambda: decoder_tail(y4, bias_a, weight_b, bias_b, weight_head, slope, taps, sigmoid))
+        if defer:
+            LoftrOverflow.pending.append((guard, (out,)))
+        elif guard.overflowed():
+            return guard.rerun()
+    return out
+
+
 def leaky_concat(a, b, slope=0.2, act_on_a=True, bias=None):
     """cat([leaky_relu(a [+ bias]), b], dim=1) for channels-last float32 CUDA maps in one pass (bit-exact)."""
     if bias is not None:

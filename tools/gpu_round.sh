@@ -12,6 +12,9 @@ for MODE in "$@"; do
       timeout -s KILL 240 python -m pytest tests/test_gpu_tcgen05.py -m gpu -q > $OUT/pytest_tc.log 2>&1; RC=$?; echo "tc rc=$RC" | tee -a $OUT/status.txt
       tail -40 $OUT/pytest_tc.log
       if [ $RC -ne 0 ]; then export RIDERS_LOFTR_IMPL=simt; echo "tcgen05 tests failed -> remaining modes run with RIDERS_LOFTR_IMPL=simt"; fi ;;
+    tailtc)
+      timeout -s KILL 150 python tools/tail_tc_check.py > $OUT/tail_tc_check.txt 2>&1; echo "tailtc rc=$?" | tee -a $OUT/status.txt
+      tail -40 $OUT/tail_tc_check.txt ;;
     test)
       timeout -s KILL 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/status.txt
       tail -15 $OUT/pytest_gpu.log

@@ -143,6 +143,9 @@ def bench_tail(R=2048):
         nbytes = (y4.numel() + R * 24000) * 4
         ms, best = timeit(lambda: ops.decoder_tail(y4, ba, wb, bb, wh, 0.2, taps=taps, sigmoid=True), iters=5)
         report("decoder_tail_taps%d" % taps, ms, best, nbytes, flops=flops, R=R)
+        ms, best = timeit(lambda: ops.decoder_tail_tc(y4, ba, wb, bb, wh, 0.2, taps=taps, sigmoid=True, defer=True), iters=5)
+        ops.LoftrOverflow.pending.clear()
+        report("decoder_tail_tcgen05_taps%d" % taps, ms, best, nbytes, flops=flops, R=R)
 
         def separate():
             z = ops.d2s_bias_act_concat(y4, ba, None, 0.2, taps=taps)

@@ -1,0 +1,52 @@
+"""First-light check of the tcgen05 decoder tail (riders_decoder_tail_tc_nhwc) against torch convolutions of the fp16-rounded
+operands, with an error map summary (which rows / columns / points are off) - run under a hard timeout on a GPU box."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from riders_b200 import ops  # noqa: E402
+
+F = torch.nn.functional
+DEV = torch.device("cuda:0")
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def h16(x):
+    return x.half().float()
+
+
+def case(N, h, w, taps, seed=0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    t = 1 if taps == 2 else 0
+    y4 = torch.randn((N, 64, h + t, w + t), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    ba, bb = torch.randn(16, device=DEV, generator=g) * 0.3, torch.randn(16, device=DEV, generator=g) * 0.3
+    wb = torch.randn((16, 16, 3, 3), device=DEV, generator=g) * 0.15
+    wh = torch.randn((1, 16, 3, 3), device=DEV, generator=g) * 0.2
+    y = ops.d2s_bias_act_concat(y4, ba, None, 0.2, taps=taps).contiguous()
+    z = F.leaky_relu(F.conv2d(h16(y), h16(wb), None, 1, 1) + bb.view(1, -1, 1, 1), 0.2)
+    ref = F.conv2d(h16(z), h16(wh), None, 1, 1)
+    ref32 = F.conv2d(F.leaky_relu(F.conv2d(y, wb, bb, 1, 1), 0.2), wh, None, 1, 1)
+    got = ops.decoder_tail_tc(y4, ba, wb, bb, wh, 0.2, taps=taps)
+    torch.cuda.synchronize()
+    scale = float(ref32.abs().max())
+    err = (got - ref).abs()
+    bad = err > 1e-3 * scale
+    print("N=%d h=%d w=%d taps=%d: scale %.3f  max err %.3e (vs fp16-operand ref)  %.3e (vs fp32)  bad fraction %.4f" %
+          (N, h, w, taps, scale, float(err.max()), float((got - ref32).abs().max()), float(bad.float().mean())), flush=True)
+    if bool(bad.any()):
+        rows = bad.any(dim=3).any(dim=1).any(dim=0).nonzero().flatten().tolist()
+        cols = bad.any(dim=2).any(dim=1).any(dim=0).nonzero().flatten().tolist()
+        pts = bad.flatten(1).any(dim=1).nonzero().flatten().tolist()
+        print("   bad rows", rows[:40], "... cols", cols[:40], "... points", pts[:10], flush=True)
+        print("   got[0,0,:4,:6]\n", got[0, 0, :4, :6].cpu().numpy(), "\n   ref\n", ref[0, 0, :4, :6].cpu().numpy(), flush=True)
+    return not bool(bad.any())
+
+
+if __name__ == "__main__":
+    ok = True
+    for N, h, w, taps in ((1, 8, 5, 3), (3, 7, 9, 2), (2, 13, 30, 3), (3, 120, 50, 2), (2, 40, 70, 3), (40, 120, 50, 2)):
+        ok = case(N, h, w, taps) and ok
+    print("ALL OK" if ok else "MISMATCH", flush=True)
