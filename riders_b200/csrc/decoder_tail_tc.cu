@@ -27,9 +27,9 @@
 // every staged value passes a running max and a value outside the fp16 range raises `status` (the host then re-runs the
 // mma.sync TF32 kernel, ops.decoder_tail).
 //
-// Warp roles (13 warps, 2 CTAs per SM, 256 TMEM columns each): 0-3 stage y rows (global -> bias + LeakyReLU -> fp16 -> ring),
-// 4-7 z epilogue (TMEM -> bias + LeakyReLU + image mask -> fp16 -> z ring), 8-11 head epilogue (TMEM -> sum -> sigmoid ->
-// global), 12: one elected lane issues every MMA.  All hand-offs are mbarriers; TMEM and shared-memory rings are freed by
+// Warp roles (17 warps, 2 CTAs per SM, 256 TMEM columns each): 0-7 stage y rows (global -> bias + LeakyReLU -> fp16 -> ring),
+// 8-11 z epilogue (TMEM -> bias + LeakyReLU + image mask -> fp16 -> z ring), 12-15 head epilogue (TMEM -> sum -> sigmoid ->
+// global), 16: one elected lane issues every MMA.  All hand-offs are mbarriers; TMEM and shared-memory rings are freed by
 // tcgen05.commit (operands) or by the reading warps (accumulators).
 #include "common.cuh"
 #include "tcgen05.cuh"
@@ -43,18 +43,16 @@ constexpr int TC = 124;                              // output columns per strip
 constexpr int NPOS = 136;                            // pixels per operand plane (128 + 2 read by the shifted views, padded)
 constexpr int PLANE = NPOS * 16;                     // 2176 B: 8 fp16 channels of one row
 constexpr int SLOT = 2 * PLANE;                      // 4352 B: one staged row (16 channels)
-constexpr int NYS = 6, NZS = 4;                      // y / z operand ring slots
+constexpr int NYS = 8, NZS = 6;                      // y / z operand ring slots
 constexpr int ZR = 12;                               // z accumulator ring: 16 TMEM columns each
 constexpr int NDH = 4;                               // head accumulator ring: 16 TMEM columns each
 constexpr int LAG = 3;                               // the head of z row q is issued after the convolution of y row q + 2 + LAG
 constexpr uint32_t TMEM_COLS = 256, DH_COL0 = 16 * ZR;
-constexpr int LOADER_WARPS = 4, W_MMA = 12, THREADS = 13 * 32;
+constexpr int LOADER_WARPS = 8, W_EPI1 = 8, W_EPI2 = 12, W_MMA = 16, THREADS = 17 * 32;
 constexpr int WB_BYTES = 3 * 48 * 32, WH_BYTES = 3 * 16 * 32, W_BYTES = WB_BYTES + WH_BYTES;      // 4608 + 1536
 constexpr int B_YFULL = 0, B_YFREE = B_YFULL + NYS, B_ZFULL = B_YFREE + NYS, B_ZFREE = B_ZFULL + NZS, B_AFULL = B_ZFREE + NZS,
               B_AFREE = B_AFULL + ZR, B_HFULL = B_AFREE + ZR, B_HFREE = B_HFULL + NDH, NBARS = B_HFREE + NDH;
-constexpr int RAWD = 6;                              // raw y4 rows in flight per CTA (cp.async ring, 8 KB each)
-constexpr int RAW_BYTES = RAWD * 4 * 128 * 16;
-constexpr int SMEM_BYTES = (NYS + NZS) * SLOT + RAW_BYTES + W_BYTES + NBARS * 8 + 16;              // 99184
+constexpr int SMEM_BYTES = (NYS + NZS) * SLOT + W_BYTES + NBARS * 8 + 16;
 static_assert(TC + 4 <= 128 && 16 * ZR + 16 * NDH <= (int)TMEM_COLS, "strip / TMEM budget");
 
 struct Params {
@@ -67,10 +65,13 @@ struct Params {
     int tiles_x, row_splits, rows_per;
 };
 
-__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
-    const __half2 v = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<const uint32_t*>(&v);
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<const uint32_t*>(&v); }
+__device__ __forceinline__ __half2 bits_h2(uint32_t v) { return *reinterpret_cast<const __half2*>(&v); }
 
 __global__ void __launch_bounds__(THREADS, 2)
 decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ wpack, float* __restrict__ out,
@@ -78,8 +79,7 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* ys = smem;                                   // [NYS][2][NPOS] x 16 B
     uint8_t* zs = ys + NYS * SLOT;                        // [NZS][2][NPOS] x 16 B
-    uint8_t* raw = zs + NZS * SLOT;                       // [RAWD][4 passes][128 loader threads] x 16 B of y4 as fetched
-    uint8_t* ws = raw + RAW_BYTES;                        // packed Wb, Wh
+    uint8_t* ws = zs + NZS * SLOT;                        // packed Wb, Wh
     const uint32_t bars = smem_u32(ws + W_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ws + W_BYTES + NBARS * 8);
     auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
@@ -111,86 +111,107 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    float amax = 0.f;                                     // running max of |staged value| (fp16 range guard)
+    if (warp >= W_EPI1 && warp < W_EPI2) {                // z accumulators start from zero (their readers keep them so)
+        for (int i = 0; i < ZR; ++i) tmem_zero16(tmem + ((uint32_t)((warp - W_EPI1) * 32) << 16) + 16 * i);
+        tc_fence_before();
+    }
+    __syncthreads();
+    tc_fence_after();
+    __half2 amax2 = __float2half2_rn(0.f);                // running max of |staged fp16 value| (range guard: inf = overflow)
 
     if (warp < LOADER_WARPS) {
         // ===================== y rows: depth-to-space + bias_a + LeakyReLU -> fp16 -> ring =====================
         // lane = (quarter of the 16 channels, pixel of an 8-pixel group): the four quarter-lanes of a pixel read its 64 bytes,
-        // the warp's store covers 8 pixels x 2 planes (256 B, two conflict-free wavefronts)
+        // the warp's store covers 8 pixels x 2 planes (256 B, two conflict-free wavefronts).  8 warps x 8 pixels x 2 passes.
         const int q = lane >> 3, l8 = lane & 7;
         const float4 ba = make_float4(P.bias_a[4 * q + 0], P.bias_a[4 * q + 1], P.bias_a[4 * q + 2], P.bias_a[4 * q + 3]);
         const int pt = P.t, hq = P.h + pt, wq = P.w + pt;
         const int xw = min(TC, W - C0) + 4;               // y positions of this strip that can be non-zero
-        const int x0 = warp * 8 + l8;                     // position in pass 0; + 32 per pass
+        const int x0 = warp * 8 + l8;                     // position in pass 0; + 64 in pass 1
         const int X0 = C0 - 2 + x0;
-        const int b = X0 & 1;                             // column phase: fixed per thread (a pass advances 32 columns)
+        const int b = X0 & 1;                             // column phase: fixed per thread (a pass advances 64 columns)
         // float4 offset of (Y, X) = [((Y >> 1) + a pt) wq + (X >> 1) + b pt] * 16 + (2 a + b) * 4 + q
         const float4* src = y4 + (size_t)n * hq * wq * 16 + q + b * 4;
+        const bool ok0 = (unsigned)X0 < (unsigned)W && x0 < xw, ok1 = (unsigned)(X0 + 64) < (unsigned)W && x0 + 64 < xw;
+        const float4* src0 = src + ((X0 >> 1) + b * pt) * 16;                    // column part of the two passes
+        const float4* src1 = src + (((X0 + 64) >> 1) + b * pt) * 16;
         uint8_t* dst0 = ys + (q >> 1) * PLANE + (q & 1) * 8 + x0 * 16;
-        // The raw rows are prefetched RAWD - 1 rows ahead with cp.async (no registers held while in flight); every thread reads
-        // back only the 16-byte pieces it fetched itself, so cp.async.wait_group is the only synchronisation needed.
-        const uint32_t raw0 = smem_u32(raw) + tid * 16;
-        unsigned colmask = 0;
-#pragma unroll
-        for (int p = 0; p < 4; ++p)
-            colmask |= ((unsigned)(X0 + 32 * p) < (unsigned)W && x0 + 32 * p < xw ? 1u : 0u) << p;
-        auto issue_row = [&](int iy) {
+        // Rows go global -> registers -> operand ring (a staging copy in shared memory costs more shared-memory bandwidth than
+        // the MMAs themselves: the kernel is bound by that pipe).  Two rows are in flight per thread (three register buffers,
+        // the loop is unrolled by three so that they stay registers) and a bulk L2 prefetch runs PF rows ahead, so the loads in
+        // flight only have to cover the L2 latency.
+        const size_t img = (size_t)n * hq * wq * 16;
+        const int lc0 = max((C0 - 2) >> 1, 0), lc1 = min(((C0 - 2 + xw - 1) >> 1) + pt, wq - 1);      // low-resolution columns used
+        auto prefetch_row = [&](int Y) {                  // the low-resolution row behind output rows Y (and its sibling)
+            if ((unsigned)Y >= (unsigned)H) return;
+            const int L = (Y >> 1) + (Y & 1) * pt;
+            const float4* g = y4 + img + ((size_t)L * wq + lc0) * 16;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"((lc1 - lc0 + 1) * 256) : "memory");
+        };
+        constexpr int PF = 10;
+        if (tid == 0)
+            for (int Y = zlo - 1; Y < zlo - 1 + PF; ++Y)
+                if (Y == zlo - 1 || (Y & 1) == pt) prefetch_row(Y);              // each low-resolution row once
+        auto load_row = [&](int iy, float4 (&v)[2]) {
             const int Y = zlo - 1 + iy, a = Y & 1;
             const bool row_ok = (unsigned)Y < (unsigned)H;
-            const float4* rp = src + (row_ok ? (size_t)(((Y >> 1) + a * pt) * wq) * 16 + a * 8 : 0);
-            const uint32_t d = raw0 + (iy % RAWD) * (4 * 128 * 16);
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                const bool ok = row_ok && ((colmask >> p) & 1);
-                const float4* g = ok ? rp + (((X0 + 32 * p) >> 1) + b * pt) * 16 : y4;         // zero-filled when !ok (src size 0)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d + p * (128 * 16)), "l"(g), "r"(ok ? 16 : 0) : "memory");
-            }
+            const size_t ro = row_ok ? (size_t)(((Y >> 1) + a * pt) * wq) * 16 + a * 8 : 0;
+            v[0] = row_ok && ok0 ? __ldcs(src0 + ro) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[1] = row_ok && ok1 ? __ldcs(src1 + ro) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tid == 0 && ((Y + PF) & 1) == pt) prefetch_row(Y + PF);
         };
-        for (int j = 0; j < RAWD - 1; ++j) {
-            if (j < ny) issue_row(j);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-        for (int iy = 0; iy < ny; ++iy) {
-            if (iy + RAWD - 1 < ny) issue_row(iy + RAWD - 1);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group %0;" ::"n"(RAWD - 1) : "memory");
+        int sl = 0, ph = 1;                               // operand slot and its free phase
+        auto stage_row = [&](int iy, const float4 (&v)[2]) {
             const bool row_ok = (unsigned)(zlo - 1 + iy) < (unsigned)H;
-            const float4* rsl = reinterpret_cast<const float4*>(raw + (iy % RAWD) * (4 * 128 * 16)) + tid;
-            float4 cur[4];
-#pragma unroll
-            for (int p = 0; p < 4; ++p) cur[p] = rsl[p * 128];
-            const int sl = iy % NYS;
-            mbar_wait(bar(B_YFREE + sl), ((iy / NYS) & 1) ^ 1);
+            mbar_wait_parked(bar(B_YFREE + sl), ph);
             uint8_t* dst = dst0 + sl * SLOT;
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                float4 x = cur[p];
+            for (int p = 0; p < 2; ++p) {
+                float4 x = v[p];
                 x.x += ba.x; x.y += ba.y; x.z += ba.z; x.w += ba.w;
                 x.x = fmaxf(x.x, x.x * slope); x.y = fmaxf(x.y, x.y * slope);      // LeakyReLU, 0 <= slope <= 1
                 x.z = fmaxf(x.z, x.z * slope); x.w = fmaxf(x.w, x.w * slope);
-                const bool ok = row_ok && ((colmask >> p) & 1);
-                if (ok) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
+                const bool ok = row_ok && (p ? ok1 : ok0);
+                const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
                 uint2 o;
-                o.x = ok ? pack_h2(x.x, x.y) : 0u;        // zero outside the image: the convolution pads the ACTIVATED map
-                o.y = ok ? pack_h2(x.z, x.w) : 0u;
-                *reinterpret_cast<uint2*>(dst + p * 32 * 16) = o;
+                o.x = ok ? h2_bits(h0) : 0u;              // zero outside the image: the convolution pads the ACTIVATED map
+                o.y = ok ? h2_bits(h1) : 0u;
+                amax2 = __hmax2_nan(amax2, __hmax2_nan(__habs2(bits_h2(o.x)), __habs2(bits_h2(o.y))));
+                *reinterpret_cast<uint2*>(dst + p * 64 * 16) = o;
             }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(B_YFULL + sl));
+            if (++sl == NYS) { sl = 0; ph ^= 1; }
+        };
+        float4 r0[2], r1[2], r2[2];
+        load_row(0, r0);
+        if (1 < ny) load_row(1, r1);
+        for (int iy = 0; iy < ny; iy += 3) {
+            if (iy + 2 < ny) load_row(iy + 2, r2);
+            stage_row(iy, r0);
+            if (iy + 1 < ny) {
+                if (iy + 3 < ny) load_row(iy + 3, r0);
+                stage_row(iy + 1, r1);
+            }
+            if (iy + 2 < ny) {
+                if (iy + 4 < ny) load_row(iy + 4, r1);
+                stage_row(iy + 2, r2);
+            }
         }
-    } else if (warp < 8) {
+    } else if (warp < W_EPI2) {
         // ===================== z epilogue: TMEM -> bias_b + LeakyReLU + image mask -> fp16 -> z ring =====================
-        const int lg = warp - 4, x = lg * 32 + lane;      // TMEM lane = z position; image column C0 - 1 + x
+        const int lg = warp - W_EPI1, x = lg * 32 + lane; // TMEM lane = z position; image column C0 - 1 + x
         const bool colok = (unsigned)(C0 - 1 + x) < (unsigned)W;
         const uint32_t trow = tmem + ((uint32_t)(lg * 32) << 16);
+        int st = 0, stph = 0, zsl = 0, zph = 1;
         for (int rz = 0; rz < nz; ++rz) {
-            const int st = rz % ZR;
-            mbar_wait(bar(B_AFULL + st), (rz / ZR) & 1);
+            mbar_wait_parked(bar(B_AFULL + st), stph);
             tc_fence_after();
             uint32_t r[16];
             TMEM_LD16(trow + 16 * (ZR - 1 - st), r);
             tmem_wait_ld();
+            tmem_zero16(trow + 16 * (ZR - 1 - st));       // the next tenant's MMAs all accumulate
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(B_AFREE + st));
@@ -199,91 +220,126 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
             for (int c = 0; c < 16; c += 2) {
                 float v0 = __uint_as_float(r[c]) + P.bias_b[c], v1 = __uint_as_float(r[c + 1]) + P.bias_b[c + 1];
                 v0 = fmaxf(v0, v0 * slope); v1 = fmaxf(v1, v1 * slope);
-                amax = fmaxf(amax, fmaxf(fabsf(v0), fabsf(v1)));
-                hv[c >> 1] = colok ? pack_h2(v0, v1) : 0u;                   // the head's zero padding outside the image
+                const __half2 hh = __floats2half2_rn(v0, v1);
+                amax2 = __hmax2_nan(amax2, __habs2(hh));
+                hv[c >> 1] = colok ? h2_bits(hh) : 0u;                       // the head's zero padding outside the image
             }
-            const int zsl = rz % NZS;
-            mbar_wait(bar(B_ZFREE + zsl), ((rz / NZS) & 1) ^ 1);
+            mbar_wait_parked(bar(B_ZFREE + zsl), zph);
             uint8_t* dst = zs + zsl * SLOT + x * 16;
             *reinterpret_cast<uint4*>(dst) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
             *reinterpret_cast<uint4*>(dst + PLANE) = make_uint4(hv[4], hv[5], hv[6], hv[7]);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(B_ZFULL + zsl));
+            if (++st == ZR) { st = 0; stph ^= 1; }
+            if (++zsl == NZS) { zsl = 0; zph ^= 1; }
         }
-    } else if (warp < 12) {
+    } else if (warp < W_MMA) {
         // ===================== head epilogue: logits[o] = Dh[o-1][0] + Dh[o][1] + Dh[o+1][2] =====================
-        const int lg = warp - 8, x = lg * 32 + lane;      // TMEM lane = output position; image column C0 + x
+        const int lg = warp - W_EPI2, x = lg * 32 + lane; // TMEM lane = output position; image column C0 + x
         const bool ok = x < TC && C0 + x < W;
         const uint32_t trow = tmem + ((uint32_t)(lg * 32) << 16) + DH_COL0;
-        float* op = out + (size_t)n * H * W + (ok ? C0 + x : 0);
-        for (int o = R0; o < R1; ++o) {
-            const int hq = min(o + 1, zhi) - zlo;
-            mbar_wait(bar(B_HFULL + hq % NDH), (hq / NDH) & 1);
+        float* op = out + (size_t)n * H * W + (size_t)R0 * W + (ok ? C0 + x : 0);
+        static_assert(NDH == 4, "head ring indices are masked");
+        for (int q = R0 - zlo; q < R1 - zlo; ++q, op += W) {               // q = o - zlo: z row of the output row, 0 <= q < nz
+            const int hq = min(q + 1, nz - 1);
+            mbar_wait_parked(bar(B_HFULL + (hq & 3)), (hq >> 2) & 1);
             tc_fence_after();
             uint32_t v0 = 0u, v1 = 0u, v2 = 0u;
-            const int q = o - zlo;                        // 0 <= q < nz
-            if (q >= 1) TMEM_LD1(trow + 16 * ((q - 1) % NDH) + 0, v0);
-            TMEM_LD1(trow + 16 * (q % NDH) + 1, v1);
-            if (q + 1 < nz) TMEM_LD1(trow + 16 * ((q + 1) % NDH) + 2, v2);
+            if (q >= 1) TMEM_LD1(trow + 16 * ((q - 1) & 3) + 0, v0);
+            TMEM_LD1(trow + 16 * (q & 3) + 1, v1);
+            if (q + 1 < nz) TMEM_LD1(trow + 16 * ((q + 1) & 3) + 2, v2);
             tmem_wait_ld();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0 && q >= 1) mbar_arrive(bar(B_HFREE + (q - 1) % NDH));
-            const float s = (__uint_as_float(v0) + __uint_as_float(v1)) + __uint_as_float(v2);
-            if (ok) __stcs(op + (size_t)o * W, P.sigmoid ? (1.0f / (1.0f + expf(-s))) : s);
+            if (lane == 0 && q >= 1) mbar_arrive(bar(B_HFREE + ((q - 1) & 3)));
+            const float sum = (__uint_as_float(v0) + __uint_as_float(v1)) + __uint_as_float(v2);
+            if (ok) __stcs(op, P.sigmoid ? (1.0f / (1.0f + expf(-sum))) : sum);
         }
     } else {
-        // ===================== MMA issuer =====================
-        if (elect_one()) {
-            const uint32_t ya = smem_u32(ys), za = smem_u32(zs), wa = smem_u32(ws);
-            constexpr uint32_t I16 = idesc_f16(16), I32 = idesc_f16(32), I48 = idesc_f16(48);
-            auto adesc = [&](uint32_t slot, int dx) { return smem_desc_nosw(slot + 16u * dx, PLANE, 128); };
-            auto bdesc = [&](int dx, int block) { return smem_desc_nosw(wa + dx * 1536 + block * 512, 128, 256); };
-            auto hdesc = [&](int dx) { return smem_desc_nosw(wa + WB_BYTES + dx * 512, 128, 256); };
-            for (int t = 0; t < ny + LAG; ++t) {
-                if (t < ny) {
-                    // y row t: kernel row dy' of the 3x3 accumulates into z row t - dy' (relative); the first contribution to
-                    // z row t (dy' = 0, dx = 0) overwrites its accumulator, whose previous tenant must have been read
-                    const int ysl = t % NYS;
-                    mbar_wait(bar(B_YFULL + ysl), (t / NYS) & 1);
-                    if (t < nz) mbar_wait(bar(B_AFREE + t % ZR), ((t / ZR) & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t a0 = ya + ysl * SLOT;
-                    const int s0 = t % ZR;
-                    if (t >= 2 && t < nz && s0 >= 2) {
-                        const uint32_t c0 = tmem + 16 * (ZR - 1 - s0);            // accumulators of z rows t, t-1, t-2: adjacent
-                        umma_f16(c0, adesc(a0, 0), bdesc(0, 0), I16, 0);
-                        umma_f16(c0 + 16, adesc(a0, 0), bdesc(0, 1), I32, 1);
-                        umma_f16(c0, adesc(a0, 1), bdesc(1, 0), I48, 1);
-                        umma_f16(c0, adesc(a0, 2), bdesc(2, 0), I48, 1);
-                    } else {
+        // ===================== MMA issuer: the whole warp runs the (warp-uniform) control flow, one elected lane issues ======
+        const uint32_t ya = smem_u32(ys), za = smem_u32(zs), wa = smem_u32(ws);
+        constexpr uint32_t I16 = idesc_f16(16), I32 = idesc_f16(32), I48 = idesc_f16(48);
+        // descriptors differ only in their start-address field (units of 16 B): + SLOT / 16 per ring slot, + 1 per pixel of
+        // horizontal shift; B: + 96 per tap dx (1536 B), + 32 per kernel row (512 B)
+        const uint64_t yd0 = smem_desc_nosw(ya, PLANE, 128), zd0 = smem_desc_nosw(za, PLANE, 128);
+        const uint64_t bd0 = smem_desc_nosw(wa, 128, 256), hd0 = smem_desc_nosw(wa + WB_BYTES, 128, 256);
+        int ysl = 0, yph = 0, zr = 0, zrph = 1;           // y operand slot / phase, accumulator slot of z row t / its free phase
+        int hzs = 0, hzph = 0, hds = 0, hdph = 1;         // z operand slot / phase, head accumulator slot / its free phase
+        for (int t = 0; t < ny + LAG; ++t) {
+            if (t < ny) {
+                // y row t: kernel row dy' of the 3x3 accumulates into z row t - dy' (relative); the accumulator of z row t must
+                // have been read (and zeroed) by the epilogue of its previous tenant
+                mbar_wait_parked(bar(B_YFULL + ysl), yph);
+                if (t < nz) mbar_wait_parked(bar(B_AFREE + zr), zrph);
+                tc_fence_after();
+                const uint64_t ad = yd0 + (uint64_t)(ysl * (SLOT / 16));
+                const int zr2 = zr >= 2 ? zr - 2 : zr + ZR - 2;                    // accumulator slot of z row t - 2
+                if (t >= 2 && t < nz) {
+                    // all three kernel rows have a target: their accumulators (z rows t, t-1, t-2) are adjacent columns unless
+                    // the ring wraps between them
+                    if (elect_one()) {
+                        if (zr >= 2) {
+                            const uint32_t c0 = tmem + 16 * (ZR - 1 - zr);
+#pragma unroll
+                            for (int dx = 0; dx < 3; ++dx) umma_f16(c0, ad + dx, bd0 + 96 * dx, I48, 1);
+                        } else if (zr == 1) {               // rows t, t-1 -> columns 160..191, row t-2 -> column 0
+#pragma unroll
+                            for (int dx = 0; dx < 3; ++dx) {
+                                umma_f16(tmem + 16 * (ZR - 2), ad + dx, bd0 + 96 * dx, I32, 1);
+                                umma_f16(tmem, ad + dx, bd0 + 96 * dx + 64, I16, 1);
+                            }
+                        } else {                            // row t -> column 176, rows t-1, t-2 -> columns 0..31
+#pragma unroll
+                            for (int dx = 0; dx < 3; ++dx) {
+                                umma_f16(tmem + 16 * (ZR - 1), ad + dx, bd0 + 96 * dx, I16, 1);
+                                umma_f16(tmem, ad + dx, bd0 + 96 * dx + 32, I32, 1);
+                            }
+                        }
+                        umma_commit(bar(B_YFREE + ysl));
+                        umma_commit(bar(B_AFULL + zr2));                           // z row t - 2 has its three kernel rows
+                    }
+                } else {
+                    if (elect_one()) {
                         for (int b = 0; b < 3; ++b) {
                             const int rzb = t - b;
                             if (rzb < 0 || rzb >= nz) continue;
-                            const uint32_t cb = tmem + 16 * (ZR - 1 - rzb % ZR);
-                            for (int dx = 0; dx < 3; ++dx) umma_f16(cb, adesc(a0, dx), bdesc(dx, b), I16, (b == 0 && dx == 0) ? 0u : 1u);
+                            const int zb = zr >= b ? zr - b : zr + ZR - b;
+                            const uint32_t cb = tmem + 16 * (ZR - 1 - zb);
+                            for (int dx = 0; dx < 3; ++dx) umma_f16(cb, ad + dx, bd0 + (uint64_t)(96 * dx + 32 * b), I16, 1);
                         }
+                        umma_commit(bar(B_YFREE + ysl));
+                        if (t >= 2) umma_commit(bar(B_AFULL + zr2));
                     }
-                    umma_commit(bar(B_YFREE + ysl));
-                    if (t >= 2) umma_commit(bar(B_AFULL + (t - 2) % ZR));         // z row t - 2 has its three kernel rows
                 }
-                const int hz = t - 2 - LAG;
-                if (hz >= 0 && hz < nz) {
-                    const int zsl = hz % NZS, ds = hz % NDH;
-                    mbar_wait(bar(B_ZFULL + zsl), (hz / NZS) & 1);
-                    mbar_wait(bar(B_HFREE + ds), ((hz / NDH) & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t a0 = za + zsl * SLOT, d = tmem + DH_COL0 + 16 * ds;
-                    for (int dx = 0; dx < 3; ++dx) umma_f16(d, adesc(a0, dx), hdesc(dx), I16, dx > 0 ? 1u : 0u);
-                    umma_commit(bar(B_ZFREE + zsl));
-                    umma_commit(bar(B_HFULL + ds));
+                __syncwarp();
+                if (++ysl == NYS) { ysl = 0; yph ^= 1; }
+                if (++zr == ZR) { zr = 0; zrph ^= 1; }
+            }
+            const int hz = t - 2 - LAG;
+            if (hz >= 0 && hz < nz) {
+                mbar_wait_parked(bar(B_ZFULL + hzs), hzph);
+                mbar_wait_parked(bar(B_HFREE + hds), hdph);
+                tc_fence_after();
+                const uint64_t ad = zd0 + (uint64_t)(hzs * (SLOT / 16));
+                const uint32_t d = tmem + DH_COL0 + 16 * hds;
+                if (elect_one()) {
+                    umma_f16(d, ad, hd0, I16, 0);
+                    umma_f16(d, ad + 1, hd0 + 32, I16, 1);
+                    umma_f16(d, ad + 2, hd0 + 64, I16, 1);
+                    umma_commit(bar(B_ZFREE + hzs));
+                    umma_commit(bar(B_HFULL + hds));
                 }
+                __syncwarp();
+                if (++hzs == NZS) { hzs = 0; hzph ^= 1; }
+                if (++hds == NDH) { hds = 0; hdph ^= 1; }
             }
         }
-        __syncwarp();
     }
-    if (status && !(amax <= 65504.f)) atomicOr(status, 1);                        // also catches NaN
+    {
+        const float2 m = __half22float2(amax2);
+        if (status && !(fmaxf(m.x, m.y) <= 65504.f)) atomicOr(status, 1);         // inf: overflow; also catches NaN
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == W_MMA) tmem_dealloc(tmem, TMEM_COLS);

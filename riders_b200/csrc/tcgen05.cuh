@@ -29,6 +29,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     } while (!done);
 }
+// the same wait for warps that may sit on the barrier for a long time: the suspend-time hint lets the hardware park the warp
+// (woken by the phase completion) instead of returning to the polling loop every few dozen cycles - in a warp-specialised
+// kernel the polling loops of the idle roles otherwise eat the issue slots of the busy ones
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
+    } while (!done);
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
