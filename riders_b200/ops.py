@@ -737,7 +737,12 @@ def loftr_overflow_pending():
     """Read the overflow flags of every deferred tcgen05 LoFTR call since the last check (one 4-byte D2H each) and forget
     them.  True = at least one call left the fp16 range: the caller recomputes with the SIMT kernels."""
     pending, LoftrOverflow.pending = LoftrOverflow.pending, []
-    return any(guard.overflowed() for guard, _ in pending)
+    if not pending:
+        return False
+    if len(pending) == 1:
+        return pending[0][0].overflowed()
+    flags = torch.stack([guard.flag.reshape(-1)[0] for guard, _ in pending])           # one kernel + one D2H for all of them
+    return bool(int((flags != 0).any().item()))
 
 
 _GRAD_FIELDS = ("wq", "wk", "wv", "wm", "w1", "w2", "ln1_g", "ln1_b", "ln2_g", "ln2_b")

@@ -447,6 +447,11 @@ class MultiScaleDecoder(torch.nn.Module):
             setattr(self, 'deconv%d' % i, None)
         self.output0 = Conv2d(cin, output_channels, 3, 1, weight_initializer, output_func, False)
         self.fused_tail = os.environ.get('RIDERS_FUSED_TAIL', '1') != '0'      # ops.decoder_tail where TF32 is allowed
+        # which kernel runs the fused tail: 'tcgen05' (decoder_tail_tc.cu: tcgen05.mma / TMEM, fp16 operands; a value outside the
+        # fp16 range raises a device flag and the caller re-runs the mma.sync kernel) or 'mma_sync' (decoder_tail.cu, TF32)
+        self.tail_impl = os.environ.get('RIDERS_TAIL_IMPL', 'tcgen05')
+        self.force_tail_impl = None                     # set by forward_output_batched for its re-run after a range violation
+        self.defer_tail_check = False                   # True: the range flag is read at the caller's own sync point
         self.subconv_tc = os.environ.get('RIDERS_SUBCONV_TC', '0') != '0'      # ops.subpixel_conv_tc instead of cuDNN's 2x2 convolution: opt-in (both sit at the HBM bound of this write-heavy shape, cuDNN 10-15 % ahead)
         self.fused_sub = os.environ.get('RIDERS_FUSED_SUBCONV', '0') != '0'    # ops.subpixel_conv_act in front of it: opt-in, measured no faster than bias_act + cuDNN
 
@@ -526,6 +531,11 @@ class MultiScaleDecoder(torch.nn.Module):
                 y4 = F.conv2d(y, last._w2 if taps == 2 else last._w4, None, 1, 1)
             self.last_head_sigmoid = bool(head_sigmoid)
             self.last_used_tail = True
+            impl = self.force_tail_impl or self.tail_impl
+            self.last_tail_impl = impl
+            if impl == 'tcgen05':
+                return [ops.decoder_tail_tc(y4, last.deconv.conv.conv.bias, last.conv.conv.weight, last.conv.conv.bias,
+                                            head.weight, _LEAK, taps=taps, sigmoid=head_sigmoid, defer=self.defer_tail_check)]
             return [ops.decoder_tail(y4, last.deconv.conv.conv.bias, last.conv.conv.weight, last.conv.conv.bias, head.weight,
                                      _LEAK, taps=taps, sigmoid=head_sigmoid)]
         if (n != 0 and last.skip_channels == 0 and last.conv.fast_ok(y) and self.output0._act is None

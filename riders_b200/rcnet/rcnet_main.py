@@ -125,6 +125,9 @@ def forward_output_batched(model, images, radar_points, frame_offsets, response_
         if tf is not None:
             tf.defer_overflow_check = attempt == 0
             tf.force_impl = ops.LOFTR_SIMT if attempt == 1 else None
+        if hasattr(dec, 'defer_tail_check'):             # the tcgen05 decoder tail has the same guard (fp16 operands)
+            dec.defer_tail_check = attempt == 0
+            dec.force_tail_impl = 'mma_sync' if attempt == 1 else None
         try:
             out, logits, is_logits = _latent_to_maps(model, enc, dec, latent_image, skips_image, radar_points, rois, frame_offsets,
                                                      H, W, ph, pw, response_thr, chunk_points, return_select)
@@ -132,6 +135,9 @@ def forward_output_batched(model, images, radar_points, frame_offsets, response_
             if tf is not None:
                 tf.defer_overflow_check = False
                 tf.force_impl = None
+            if hasattr(dec, 'defer_tail_check'):
+                dec.defer_tail_check = False
+                dec.force_tail_impl = None
         if attempt == 0 and ops.LoftrOverflow.pending and ops.loftr_overflow_pending():
             continue
         break

@@ -1,6 +1,8 @@
 """Parity of the CUDA path (through the C ABI) with the CPU oracle and the reference-generated
 golden fixtures.  Integer / selection work must be bit-exact; floating point within the
 tolerances of BASELINE.json's north_star, written next to each assert."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -950,6 +952,70 @@ def test_decoder_tail_matches_the_three_passes(hw, taps):
     np.testing.assert_allclose(sg.cpu().numpy(), torch.sigmoid(got).cpu().numpy(), rtol=2e-6, atol=1e-7)
 
 
+def _fp16(x):
+    return x.half().float()
+
+
+@pytest.mark.parametrize("taps", [2, 3])
+@pytest.mark.parametrize("hw,N", [((120, 50), 3), ((7, 9), 2), ((13, 30), 5), ((2, 3), 1), ((40, 70), 2), ((120, 50), 40), ((9, 130), 1)])
+def test_decoder_tail_tcgen05_matches_fp16_operand_convolutions(hw, N, taps):
+    """ops.decoder_tail_tc (tcgen05.mma kind::f16, accumulators in TMEM, streaming row pipeline): fp16 operands (11-bit
+    significand, like TF32) with fp32 accumulation.  Against fp32 convolutions of the fp16-ROUNDED operands (the kernel's own
+    rounding points: y, Wb, z, Wh) only values whose z sits on an fp16 rounding boundary move (by one fp16 ulp of a product);
+    against the pure fp32 passes it is within fp16 / TF32 operand accuracy.  Shapes: RC-Net's 240 x 100, tiny maps, several
+    column strips (2 w > 124), rows split over CTAs (few points), many strips per SM (N = 40); deterministic."""
+    F = torch.nn.functional
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device=DEV).manual_seed(hw[0] * 7 + taps + N)
+    (h, w), t = hw, (1 if taps == 2 else 0)
+    y4 = torch.randn((N, 64, h + t, w + t), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    ba, bb = torch.randn(16, device=DEV, generator=g) * 0.3, torch.randn(16, device=DEV, generator=g) * 0.3
+    wb = torch.randn((16, 16, 3, 3), device=DEV, generator=g) * 0.15
+    wh = torch.randn((1, 16, 3, 3), device=DEV, generator=g) * 0.2
+    y = ops.d2s_bias_act_concat(y4, ba, None, 0.2, taps=taps).contiguous()           # bit-exact pass (tested above)
+    ref32 = F.conv2d(F.leaky_relu(F.conv2d(y, wb, bb, 1, 1), 0.2), wh, None, 1, 1)
+    zh = F.leaky_relu(F.conv2d(_fp16(y), _fp16(wb), None, 1, 1) + bb.view(1, -1, 1, 1), 0.2)
+    refh = F.conv2d(_fp16(zh), _fp16(wh), None, 1, 1)
+    got = ops.decoder_tail_tc(y4, ba, wb, bb, wh, 0.2, taps=taps)
+    sg = ops.decoder_tail_tc(y4, ba, wb, bb, wh, 0.2, taps=taps, sigmoid=True)
+    assert got.shape == ref32.shape
+    scale = float(ref32.abs().max())
+    err = (got - refh).abs()
+    assert float(err.mean()) < 4e-6 * scale and float(err.max()) < 5e-4 * scale
+    assert float((err > 2e-5 * scale).float().mean()) < 0.05
+    assert float((got - ref32).abs().max()) < 2e-3 * scale
+    np.testing.assert_allclose(sg.cpu().numpy(), torch.sigmoid(got).cpu().numpy(), rtol=2e-6, atol=1e-7)
+    assert torch.equal(got, ops.decoder_tail_tc(y4, ba, wb, bb, wh, 0.2, taps=taps))
+    # the two tail kernels agree to operand accuracy (TF32 and fp16 keep the same number of significand bits)
+    assert float((got - ops.decoder_tail(y4, ba, wb, bb, wh, 0.2, taps=taps)).abs().max()) < 2e-3 * scale
+
+
+def test_decoder_tail_tcgen05_fp16_range_guard():
+    """Activations beyond the fp16 range (a limit neither the fp32 reference nor the TF32 kernel has) raise the device flag of
+    riders_decoder_tail_tc_nhwc: ops.decoder_tail_tc then returns the mma.sync TF32 kernel's result (bit-identical to calling
+    it), immediately or - with defer=True - once the caller has read the pending flags."""
+    g = torch.Generator(device=DEV).manual_seed(3)
+    y4 = torch.randn((2, 64, 13, 10), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    ba, bb = torch.randn(16, device=DEV, generator=g) * 0.3, torch.randn(16, device=DEV, generator=g) * 0.3
+    wb = torch.randn((16, 16, 3, 3), device=DEV, generator=g) * 0.15
+    wh = torch.randn((1, 16, 3, 3), device=DEV, generator=g) * 0.2
+    ok = ops.decoder_tail_tc(y4, ba, wb, bb, wh, 0.2, taps=2)
+    assert torch.isfinite(ok).all()
+    big = y4.clone()
+    big[1, 5, 4, 3] = 1.0e5                                              # one activation out of range
+    ref = ops.decoder_tail(big, ba, wb, bb, wh, 0.2, taps=2)
+    assert torch.equal(ops.decoder_tail_tc(big, ba, wb, bb, wh, 0.2, taps=2), ref)
+    zbig, wbp = y4.clone(), wb.abs()                                     # y in range, z = conv(y) beyond it
+    zbig[0, :, 3:6, 2:5] = 3.0e4
+    refz = ops.decoder_tail(zbig, ba, wbp, bb, wh, 0.2, taps=2)
+    assert torch.equal(ops.decoder_tail_tc(zbig, ba, wbp, bb, wh, 0.2, taps=2), refz)
+    ops.LoftrOverflow.pending.clear()
+    ops.decoder_tail_tc(y4, ba, wb, bb, wh, 0.2, taps=2, defer=True)
+    assert len(ops.LoftrOverflow.pending) == 1 and not ops.loftr_overflow_pending()
+    ops.decoder_tail_tc(big, ba, wb, bb, wh, 0.2, taps=2, defer=True)
+    assert ops.loftr_overflow_pending() and not ops.LoftrOverflow.pending
+
+
 @pytest.mark.parametrize("hw", [(120, 50), (7, 9), (13, 30)])
 def test_subpixel_conv_act_matches_torch(hw):
     """ops.subpixel_conv_act (mma.sync): conv2x2(act(x + bias), W2, padding 1) on the TF32 tensor cores == fp32 convolution
@@ -1015,9 +1081,12 @@ def test_decoder_uses_the_fused_tail_only_where_tf32_is_allowed(monkeypatch):
             if isinstance(m, networks.DecoderBlock):
                 m.fold_upsample_()
         calls, subs, tcs = [], [], []
-        real, real_sub, real_tc = ops.decoder_tail, ops.subpixel_conv_act, ops.subpixel_conv_tc
+        real, real_sub, real_tc, real_tail_tc = ops.decoder_tail, ops.subpixel_conv_act, ops.subpixel_conv_tc, ops.decoder_tail_tc
+        tail_tcs = []
         monkeypatch.setattr(ops, "subpixel_conv_tc", lambda *a, **k: (tcs.append(1), real_tc(*a, **k))[1])
         monkeypatch.setattr(ops, "decoder_tail", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+        monkeypatch.setattr(ops, "decoder_tail_tc", lambda *a, **k: (calls.append(1), tail_tcs.append(1), real_tail_tc(*a, **k))[2])
+        assert dec.tail_impl == os.environ.get("RIDERS_TAIL_IMPL", "tcgen05")
         monkeypatch.setattr(ops, "subpixel_conv_act", lambda *a, **k: (subs.append(1), real_sub(*a, **k))[1])
         torch.backends.cudnn.allow_tf32 = False
         ref = dec(x, skips, shape=(240, 100))[-1]
@@ -1034,14 +1103,18 @@ def test_decoder_uses_the_fused_tail_only_where_tf32_is_allowed(monkeypatch):
             dec.subconv_tc = False
             got3 = dec(x, skips, shape=(240, 100))[-1]                # cuDNN phase convolution + tail
             assert len(calls) == 3 and len(subs) == 1 and len(tcs) == 1
-            calls.pop()
+            n_tc = len(tail_tcs)
+            dec.tail_impl = "mma_sync" if dec.tail_impl == "tcgen05" else "tcgen05"       # the other tail kernel
+            got4 = dec(x, skips, shape=(240, 100))[-1]
+            assert len(calls) == 4 and len(tail_tcs) == n_tc + (dec.tail_impl == "tcgen05") and dec.last_tail_impl == dec.tail_impl
+            calls.pop(); calls.pop()
             dec.fused_tail = False
             sep = dec(x, skips, shape=(240, 100))[-1]                 # the separate passes
             assert len(calls) == 2 and len(subs) == 1
         finally:
             torch.backends.cudnn.allow_tf32 = False
     scale = float(ref.abs().max())
-    for t in (got, got2, got3, sep):
+    for t in (got, got2, got3, got4, sep):
         assert float((t - ref).abs().max()) < 5e-3 * scale
     assert float((got - sep).abs().max()) < 5e-3 * scale
 
