@@ -362,6 +362,17 @@ int riders_decoder_tail_nhwc(const float* y4, int taps, int N, int h, int w,
 int riders_decoder_tail_tc_nhwc(const float* y4, int taps, int N, int h, int w,
                                 const float* bias_a_host, const void* w_pack, const float* bias_b_host,
                                 float slope, int apply_sigmoid, float* out, int* status, void* stream);
+/* The two kernels back to back without the float y4 map between them: riders_subpixel_conv_tc_half_nhwc is the tcgen05 phase
+ * convolution (riders_subpixel_conv_tc_nhwc) whose epilogue finishes the up-convolution - depth-to-space, + bias_host (16, or
+ * NULL), LeakyReLU(slope), fp16 - and writes yh [N][2h][2][2w][8] fp16: per output row two planes of 8 channels, the image of
+ * the tail's MMA operand; riders_decoder_tail_tc_half_nhwc is the tcgen05 tail reading that map (its rows are bulk-copied
+ * straight into the operand ring).  Halves the bytes of the interface (32 instead of 64 B per pixel, written once and read
+ * once) and takes the staging arithmetic out of the tail.  Same rounding points as riders_decoder_tail_tc_nhwc fed by a TF32
+ * phase convolution.  status as above (both kernels raise the same flag).                                               */
+int riders_subpixel_conv_tc_half_nhwc(const float* x, const float* w_pack, int N, int h, int w, const float* bias_host,
+                                      float slope, void* yh, int* status, void* stream);
+int riders_decoder_tail_tc_half_nhwc(const void* yh, int N, int h, int w, const void* w_pack, const float* bias_b_host,
+                                     float slope, int apply_sigmoid, float* out, int* status, void* stream);
 /* Sub-pixel phase convolution of the last decoder block in its 2x2-tap form (32 -> 4 x 16 channels), TF32, with the bias
  * + LeakyReLU of the convolution that produced x fused into the operand load (deconv1.conv -> deconv0.deconv of
  * MultiScaleDecoder, RCNet/networks.py:678-779): y4 (N, 64, h+1, w+1) = conv2x2(act(x + bias), W2, padding 1), x (N, 32, h, w)

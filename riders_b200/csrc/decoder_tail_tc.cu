@@ -48,11 +48,18 @@ constexpr int ZR = 12;                               // z accumulator ring: 16 T
 constexpr int NDH = 4;                               // head accumulator ring: 16 TMEM columns each
 constexpr int LAG = 3;                               // the head of z row q is issued after the convolution of y row q + 2 + LAG
 constexpr uint32_t TMEM_COLS = 256, DH_COL0 = 16 * ZR;
-constexpr int LOADER_WARPS = 8, W_EPI1 = 8, W_EPI2 = 12, W_MMA = 16, THREADS = 17 * 32;
 constexpr int WB_BYTES = 3 * 48 * 32, WH_BYTES = 3 * 16 * 32, W_BYTES = WB_BYTES + WH_BYTES;      // 4608 + 1536
 constexpr int B_YFULL = 0, B_YFREE = B_YFULL + NYS, B_ZFULL = B_YFREE + NYS, B_ZFREE = B_ZFULL + NZS, B_AFULL = B_ZFREE + NZS,
               B_AFREE = B_AFULL + ZR, B_HFULL = B_AFREE + ZR, B_HFREE = B_HFULL + NDH, NBARS = B_HFREE + NDH;
-constexpr int SMEM_BYTES = (NYS + NZS) * SLOT + W_BYTES + NBARS * 8 + 16;
+// Warp roles.  Float input (y4 from a library convolution): warps 0-7 stage, 8-11 / 12-15 epilogues, 16 issues the MMAs.
+// fp16 input (the finished map of riders_subpixel_conv_tc_half_nhwc): nothing to compute while staging - lane 0 of warp 0
+// bulk-copies rows straight into the operand ring, warp 1 issues the MMAs, warps 4-7 / 8-11 are the epilogues.
+template <bool HALF_IN> struct Roles {
+    static constexpr int LOADER_WARPS = HALF_IN ? 1 : 8, W_EPI1 = HALF_IN ? 4 : 8, W_EPI2 = W_EPI1 + 4, W_MMA = HALF_IN ? 1 : 16;
+    static constexpr int THREADS = HALF_IN ? 12 * 32 : 17 * 32;
+    static constexpr int YSLOTS = NYS + (HALF_IN ? 1 : 0);          // + a slot that stays zero: the rows outside the image
+    static constexpr int SMEM_BYTES = (YSLOTS + NZS) * SLOT + W_BYTES + NBARS * 8 + 16;
+};
 static_assert(TC + 4 <= 128 && 16 * ZR + 16 * NDH <= (int)TMEM_COLS, "strip / TMEM budget");
 
 struct Params {
@@ -73,12 +80,15 @@ __device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
 __device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<const uint32_t*>(&v); }
 __device__ __forceinline__ __half2 bits_h2(uint32_t v) { return *reinterpret_cast<const __half2*>(&v); }
 
-__global__ void __launch_bounds__(THREADS, 2)
+template <bool HALF_IN>
+__global__ void __launch_bounds__(Roles<HALF_IN>::THREADS, 2)
 decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ wpack, float* __restrict__ out,
                        int* __restrict__ status, const __grid_constant__ Params P) {
+    constexpr int LOADER_WARPS = Roles<HALF_IN>::LOADER_WARPS, W_EPI1 = Roles<HALF_IN>::W_EPI1, W_EPI2 = Roles<HALF_IN>::W_EPI2,
+                  W_MMA = Roles<HALF_IN>::W_MMA, THREADS = Roles<HALF_IN>::THREADS, YSLOTS = Roles<HALF_IN>::YSLOTS;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* ys = smem;                                   // [NYS][2][NPOS] x 16 B
-    uint8_t* zs = ys + NYS * SLOT;                        // [NZS][2][NPOS] x 16 B
+    uint8_t* ys = smem;                                   // [YSLOTS][2][NPOS] x 16 B
+    uint8_t* zs = ys + YSLOTS * SLOT;                     // [NZS][2][NPOS] x 16 B
     uint8_t* ws = zs + NZS * SLOT;                        // packed Wb, Wh
     const uint32_t bars = smem_u32(ws + W_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ws + W_BYTES + NBARS * 8);
@@ -96,10 +106,10 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
     const int nz = zhi - zlo + 1, ny = nz + 2;                             // y rows zlo - 1 .. zhi + 1
     const float slope = P.slope;
 
-    for (int i = tid; i < (NYS + NZS) * SLOT / 16; i += THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < (YSLOTS + NZS) * SLOT / 16; i += THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = tid; i < W_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(ws)[i] = __ldg(wpack + i);
     if (tid == 0) {
-        for (int i = 0; i < NYS; ++i) { mbar_init(bar(B_YFULL + i), LOADER_WARPS); mbar_init(bar(B_YFREE + i), 1); }
+        for (int i = 0; i < NYS; ++i) { mbar_init(bar(B_YFULL + i), HALF_IN ? 1 : LOADER_WARPS); mbar_init(bar(B_YFREE + i), 1); }
         for (int i = 0; i < NZS; ++i) { mbar_init(bar(B_ZFULL + i), 4); mbar_init(bar(B_ZFREE + i), 1); }
         for (int i = 0; i < ZR; ++i)  { mbar_init(bar(B_AFULL + i), 1); mbar_init(bar(B_AFREE + i), 4); }
         for (int i = 0; i < NDH; ++i) { mbar_init(bar(B_HFULL + i), 1); mbar_init(bar(B_HFREE + i), 4); }
@@ -119,7 +129,27 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
     tc_fence_after();
     __half2 amax2 = __float2half2_rn(0.f);                // running max of |staged fp16 value| (range guard: inf = overflow)
 
-    if (warp < LOADER_WARPS) {
+    if (HALF_IN && warp == 0) {
+        // ===================== y rows (fp16 input): one bulk copy per plane straight into the operand ring =====================
+        if (lane == 0) {
+            const __half* yh = reinterpret_cast<const __half*>(y4);
+            const int xs = max(C0 - 2, 0), xe = min(W, C0 + TC + 2);              // image columns of this strip (with the halo)
+            const uint32_t bytes = (uint32_t)(xe - xs) * 16, dpos = (uint32_t)(xs - (C0 - 2)) * 16;
+            const __half* src = yh + ((size_t)n * H * 2 * W + xs) * 8;
+            int sl = 0, ph = 1;
+            for (int iy = 0; iy < ny; ++iy) {
+                const int Y = zlo - 1 + iy;
+                if ((unsigned)Y >= (unsigned)H) continue;                          // the MMA reads the zero slot for those
+                mbar_wait_sleep(bar(B_YFREE + sl), ph, 100);
+                mbar_expect_tx(bar(B_YFULL + sl), 2 * bytes);
+                const uint32_t dst = smem_u32(ys + sl * SLOT) + dpos;
+                const __half* g = src + (size_t)Y * 2 * W * 8;
+                bulk_g2s(dst, g, bytes, bar(B_YFULL + sl));
+                bulk_g2s(dst + PLANE, g + (size_t)W * 8, bytes, bar(B_YFULL + sl));
+                if (++sl == NYS) { sl = 0; ph ^= 1; }
+            }
+        }
+    } else if (!HALF_IN && warp < LOADER_WARPS) {
         // ===================== y rows: depth-to-space + bias_a + LeakyReLU -> fp16 -> ring =====================
         // lane = (quarter of the 16 channels, pixel of an 8-pixel group): the four quarter-lanes of a pixel read its 64 bytes,
         // the warp's store covers 8 pixels x 2 planes (256 B, two conflict-free wavefronts).  8 warps x 8 pixels x 2 passes.
@@ -152,18 +182,23 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
         if (tid == 0)
             for (int Y = zlo - 1; Y < zlo - 1 + PF; ++Y)
                 if (Y == zlo - 1 || (Y & 1) == pt) prefetch_row(Y);              // each low-resolution row once
-        auto load_row = [&](int iy, float4 (&v)[2]) {
-            const int Y = zlo - 1 + iy, a = Y & 1;
-            const bool row_ok = (unsigned)Y < (unsigned)H;
-            const size_t ro = row_ok ? (size_t)(((Y >> 1) + a * pt) * wq) * 16 + a * 8 : 0;
+        // row part of the address, kept incrementally: from an even row to the next one the phase advances by 8 float4 (and the
+        // low-resolution row by pt), from an odd one the phase goes back and the low-resolution row advances by 1 - pt
+        const int d_even = pt * wq * 16 + 8, d_odd = (1 - pt) * wq * 16 - 8;
+        int Yl = zlo - 1;                                  // row the next load_row call fetches
+        int ro = (((Yl >> 1) + (Yl & 1) * pt) * wq) * 16 + (Yl & 1) * 8;      // (consistent for Yl = -1 too; never dereferenced then)
+        auto load_row = [&](float4 (&v)[2]) {
+            const bool row_ok = (unsigned)Yl < (unsigned)H;
             v[0] = row_ok && ok0 ? __ldcs(src0 + ro) : make_float4(0.f, 0.f, 0.f, 0.f);
             v[1] = row_ok && ok1 ? __ldcs(src1 + ro) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tid == 0 && ((Y + PF) & 1) == pt) prefetch_row(Y + PF);
+            if (tid == 0 && ((Yl + PF) & 1) == pt) prefetch_row(Yl + PF);
+            ro += (Yl & 1) ? d_odd : d_even;
+            ++Yl;
         };
         int sl = 0, ph = 1;                               // operand slot and its free phase
         auto stage_row = [&](int iy, const float4 (&v)[2]) {
             const bool row_ok = (unsigned)(zlo - 1 + iy) < (unsigned)H;
-            mbar_wait_parked(bar(B_YFREE + sl), ph);
+            mbar_wait_sleep(bar(B_YFREE + sl), ph, 200);
             uint8_t* dst = dst0 + sl * SLOT;
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
@@ -185,28 +220,28 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
             if (++sl == NYS) { sl = 0; ph ^= 1; }
         };
         float4 r0[2], r1[2], r2[2];
-        load_row(0, r0);
-        if (1 < ny) load_row(1, r1);
+        load_row(r0);
+        if (1 < ny) load_row(r1);
         for (int iy = 0; iy < ny; iy += 3) {
-            if (iy + 2 < ny) load_row(iy + 2, r2);
+            if (iy + 2 < ny) load_row(r2);
             stage_row(iy, r0);
             if (iy + 1 < ny) {
-                if (iy + 3 < ny) load_row(iy + 3, r0);
+                if (iy + 3 < ny) load_row(r0);
                 stage_row(iy + 1, r1);
             }
             if (iy + 2 < ny) {
-                if (iy + 4 < ny) load_row(iy + 4, r1);
+                if (iy + 4 < ny) load_row(r1);
                 stage_row(iy + 2, r2);
             }
         }
-    } else if (warp < W_EPI2) {
+    } else if (warp >= W_EPI1 && warp < W_EPI2) {
         // ===================== z epilogue: TMEM -> bias_b + LeakyReLU + image mask -> fp16 -> z ring =====================
         const int lg = warp - W_EPI1, x = lg * 32 + lane; // TMEM lane = z position; image column C0 - 1 + x
         const bool colok = (unsigned)(C0 - 1 + x) < (unsigned)W;
         const uint32_t trow = tmem + ((uint32_t)(lg * 32) << 16);
         int st = 0, stph = 0, zsl = 0, zph = 1;
         for (int rz = 0; rz < nz; ++rz) {
-            mbar_wait_parked(bar(B_AFULL + st), stph);
+            mbar_wait_sleep(bar(B_AFULL + st), stph, 100);
             tc_fence_after();
             uint32_t r[16];
             TMEM_LD16(trow + 16 * (ZR - 1 - st), r);
@@ -224,7 +259,7 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
                 amax2 = __hmax2_nan(amax2, __habs2(hh));
                 hv[c >> 1] = colok ? h2_bits(hh) : 0u;                       // the head's zero padding outside the image
             }
-            mbar_wait_parked(bar(B_ZFREE + zsl), zph);
+            mbar_wait_sleep(bar(B_ZFREE + zsl), zph, 100);
             uint8_t* dst = zs + zsl * SLOT + x * 16;
             *reinterpret_cast<uint4*>(dst) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
             *reinterpret_cast<uint4*>(dst + PLANE) = make_uint4(hv[4], hv[5], hv[6], hv[7]);
@@ -234,7 +269,7 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
             if (++st == ZR) { st = 0; stph ^= 1; }
             if (++zsl == NZS) { zsl = 0; zph ^= 1; }
         }
-    } else if (warp < W_MMA) {
+    } else if (warp >= W_EPI2 && warp < W_EPI2 + 4) {
         // ===================== head epilogue: logits[o] = Dh[o-1][0] + Dh[o][1] + Dh[o+1][2] =====================
         const int lg = warp - W_EPI2, x = lg * 32 + lane; // TMEM lane = output position; image column C0 + x
         const bool ok = x < TC && C0 + x < W;
@@ -243,7 +278,7 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
         static_assert(NDH == 4, "head ring indices are masked");
         for (int q = R0 - zlo; q < R1 - zlo; ++q, op += W) {               // q = o - zlo: z row of the output row, 0 <= q < nz
             const int hq = min(q + 1, nz - 1);
-            mbar_wait_parked(bar(B_HFULL + (hq & 3)), (hq >> 2) & 1);
+            mbar_wait_sleep(bar(B_HFULL + (hq & 3)), (hq >> 2) & 1, 100);
             tc_fence_after();
             uint32_t v0 = 0u, v1 = 0u, v2 = 0u;
             if (q >= 1) TMEM_LD1(trow + 16 * ((q - 1) & 3) + 0, v0);
@@ -256,7 +291,7 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
             const float sum = (__uint_as_float(v0) + __uint_as_float(v1)) + __uint_as_float(v2);
             if (ok) __stcs(op, P.sigmoid ? (1.0f / (1.0f + expf(-sum))) : sum);
         }
-    } else {
+    } else if (warp == W_MMA) {
         // ===================== MMA issuer: the whole warp runs the (warp-uniform) control flow, one elected lane issues ======
         const uint32_t ya = smem_u32(ys), za = smem_u32(zs), wa = smem_u32(ws);
         constexpr uint32_t I16 = idesc_f16(16), I32 = idesc_f16(32), I48 = idesc_f16(48);
@@ -270,10 +305,11 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
             if (t < ny) {
                 // y row t: kernel row dy' of the 3x3 accumulates into z row t - dy' (relative); the accumulator of z row t must
                 // have been read (and zeroed) by the epilogue of its previous tenant
-                mbar_wait_parked(bar(B_YFULL + ysl), yph);
-                if (t < nz) mbar_wait_parked(bar(B_AFREE + zr), zrph);
+                const bool yring = !HALF_IN || (unsigned)(zlo - 1 + t) < (unsigned)H;      // fp16 input: rows outside = the zero slot
+                if (yring) mbar_wait(bar(B_YFULL + ysl), yph);
+                if (t < nz) mbar_wait(bar(B_AFREE + zr), zrph);
                 tc_fence_after();
-                const uint64_t ad = yd0 + (uint64_t)(ysl * (SLOT / 16));
+                const uint64_t ad = yd0 + (uint64_t)((yring ? ysl : NYS) * (SLOT / 16));
                 const int zr2 = zr >= 2 ? zr - 2 : zr + ZR - 2;                    // accumulator slot of z row t - 2
                 if (t >= 2 && t < nz) {
                     // all three kernel rows have a target: their accumulators (z rows t, t-1, t-2) are adjacent columns unless
@@ -296,7 +332,7 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
                                 umma_f16(tmem, ad + dx, bd0 + 96 * dx + 32, I32, 1);
                             }
                         }
-                        umma_commit(bar(B_YFREE + ysl));
+                        if (yring) umma_commit(bar(B_YFREE + ysl));
                         umma_commit(bar(B_AFULL + zr2));                           // z row t - 2 has its three kernel rows
                     }
                 } else {
@@ -308,18 +344,18 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
                             const uint32_t cb = tmem + 16 * (ZR - 1 - zb);
                             for (int dx = 0; dx < 3; ++dx) umma_f16(cb, ad + dx, bd0 + (uint64_t)(96 * dx + 32 * b), I16, 1);
                         }
-                        umma_commit(bar(B_YFREE + ysl));
+                        if (yring) umma_commit(bar(B_YFREE + ysl));
                         if (t >= 2) umma_commit(bar(B_AFULL + zr2));
                     }
                 }
                 __syncwarp();
-                if (++ysl == NYS) { ysl = 0; yph ^= 1; }
+                if (yring && ++ysl == NYS) { ysl = 0; yph ^= 1; }
                 if (++zr == ZR) { zr = 0; zrph ^= 1; }
             }
             const int hz = t - 2 - LAG;
             if (hz >= 0 && hz < nz) {
-                mbar_wait_parked(bar(B_ZFULL + hzs), hzph);
-                mbar_wait_parked(bar(B_HFREE + hds), hdph);
+                mbar_wait(bar(B_ZFULL + hzs), hzph);
+                mbar_wait(bar(B_HFREE + hds), hdph);
                 tc_fence_after();
                 const uint64_t ad = zd0 + (uint64_t)(hzs * (SLOT / 16));
                 const uint32_t d = tmem + DH_COL0 + 16 * hds;
@@ -348,16 +384,16 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
 }  // namespace tailtc
 }  // namespace riders
 
-extern "C" int riders_decoder_tail_tc_nhwc(const float* y4, int taps, int N, int h, int w, const float* bias_a_host,
-                                           const void* w_pack, const float* bias_b_host, float slope, int apply_sigmoid,
-                                           float* out, int* status, void* stream) {
+static int decoder_tail_tc_launch(const void* in, bool half_in, int taps, int N, int h, int w, const float* bias_a_host,
+                                  const void* w_pack, const float* bias_b_host, float slope, int apply_sigmoid,
+                                  float* out, int* status, void* stream) {
     using namespace riders;
     RIDERS_REQUIRE(N >= 0 && h > 0 && w > 0, "decoder_tail_tc: bad shape");
     RIDERS_REQUIRE(taps == 2 || taps == 3, "decoder_tail_tc: taps must be 2 or 3 (got %d)", taps);
     RIDERS_REQUIRE(slope >= 0.f && slope <= 1.f, "decoder_tail_tc: LeakyReLU slope must be in [0, 1] (got %g)", (double)slope);
     if (N == 0) return RIDERS_OK;
-    RIDERS_REQUIRE(y4 && w_pack && out, "decoder_tail_tc: null pointer");
-    RIDERS_REQUIRE(((((uintptr_t)y4) | ((uintptr_t)w_pack)) & 15) == 0, "decoder_tail_tc: y4 / w_pack must be 16-byte aligned");
+    RIDERS_REQUIRE(in && w_pack && out, "decoder_tail_tc: null pointer");
+    RIDERS_REQUIRE(((((uintptr_t)in) | ((uintptr_t)w_pack)) & 15) == 0, "decoder_tail_tc: input / w_pack must be 16-byte aligned");
     tailtc::Params P;
     for (int c = 0; c < 16; ++c) {
         P.bias_a[c] = bias_a_host ? bias_a_host[c] : 0.f;
@@ -379,10 +415,28 @@ extern "C" int riders_decoder_tail_tc_nhwc(const float* y4, int taps, int N, int
     P.row_splits = ceil_div(H, P.rows_per);
     const long long blocks = strips * P.row_splits;
     RIDERS_REQUIRE(blocks < (1ll << 31), "decoder_tail_tc: too many strips for one launch");
-    static size_t configured[64] = {0};
-    if (int rc_smem = ensure_dynamic_smem(tailtc::decoder_tail_tc_kernel, (size_t)(tailtc::SMEM_BYTES), configured, "decoder_tail_tc: shared memory attribute")) return rc_smem;
     count_launches(1);
-    tailtc::decoder_tail_tc_kernel<<<(unsigned)blocks, tailtc::THREADS, tailtc::SMEM_BYTES, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(y4), reinterpret_cast<const uint4*>(w_pack), out, status, P);
+    if (half_in) {
+        static size_t configured[64] = {0};
+        if (int rc_smem = ensure_dynamic_smem(tailtc::decoder_tail_tc_kernel<true>, (size_t)(tailtc::Roles<true>::SMEM_BYTES), configured, "decoder_tail_tc: shared memory attribute")) return rc_smem;
+        tailtc::decoder_tail_tc_kernel<true><<<(unsigned)blocks, tailtc::Roles<true>::THREADS, tailtc::Roles<true>::SMEM_BYTES, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4*>(in), reinterpret_cast<const uint4*>(w_pack), out, status, P);
+    } else {
+        static size_t configured[64] = {0};
+        if (int rc_smem = ensure_dynamic_smem(tailtc::decoder_tail_tc_kernel<false>, (size_t)(tailtc::Roles<false>::SMEM_BYTES), configured, "decoder_tail_tc: shared memory attribute")) return rc_smem;
+        tailtc::decoder_tail_tc_kernel<false><<<(unsigned)blocks, tailtc::Roles<false>::THREADS, tailtc::Roles<false>::SMEM_BYTES, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4*>(in), reinterpret_cast<const uint4*>(w_pack), out, status, P);
+    }
     return check_launch("decoder_tail_tc_nhwc");
+}
+
+extern "C" int riders_decoder_tail_tc_nhwc(const float* y4, int taps, int N, int h, int w, const float* bias_a_host,
+                                           const void* w_pack, const float* bias_b_host, float slope, int apply_sigmoid,
+                                           float* out, int* status, void* stream) {
+    return decoder_tail_tc_launch(y4, false, taps, N, h, w, bias_a_host, w_pack, bias_b_host, slope, apply_sigmoid, out, status, stream);
+}
+
+extern "C" int riders_decoder_tail_tc_half_nhwc(const void* yh, int N, int h, int w, const void* w_pack, const float* bias_b_host,
+                                                float slope, int apply_sigmoid, float* out, int* status, void* stream) {
+    return decoder_tail_tc_launch(yh, true, 3, N, h, w, nullptr, w_pack, bias_b_host, slope, apply_sigmoid, out, status, stream);
 }

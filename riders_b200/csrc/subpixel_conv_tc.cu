@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "tcgen05.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 namespace riders {
 namespace spctc {
@@ -39,9 +40,20 @@ struct Params {
     const uint4* w_pack;
     float* y4;
     int h, w, pairs, n_tiles;
+    // HALF variant: the epilogue finishes the up-convolution - depth-to-space, + bias, LeakyReLU, fp16 - and writes the map the
+    // tcgen05 decoder tail stages as its MMA operand: yh [N][2h][2 planes of 8 channels][2w][8] fp16 (a row = two contiguous
+    // planes = what one bulk copy moves into an operand ring slot)
+    __half* yh;
+    int* status;             // bit 0 raised when a value leaves the fp16 range
+    float bias[16];
+    float slope;
 };
+constexpr int THREADS_HALF = 320;                     // + a second group of read-back warps (one per accumulator)
 
-__global__ void __launch_bounds__(THREADS, 1)
+__device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<const uint32_t*>(&v); }
+
+template <bool HALF>
+__global__ void __launch_bounds__(HALF ? THREADS_HALF : THREADS, 1)
 subpixel_conv_tc_kernel(const __grid_constant__ Params P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -63,7 +75,7 @@ subpixel_conv_tc_kernel(const __grid_constant__ Params P) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < 4 * B_SLAB / 16; i += THREADS) reinterpret_cast<uint4*>(b_base)[i] = __ldg(P.w_pack + i);
+    for (int i = tid; i < 4 * B_SLAB / 16; i += (HALF ? THREADS_HALF : THREADS)) reinterpret_cast<uint4*>(b_base)[i] = __ldg(P.w_pack + i);
     fence_async_smem();                                            // B was written through the generic proxy, UMMA reads it through the async one
     tc_fence_before();
     __syncthreads();
@@ -113,6 +125,75 @@ subpixel_conv_tc_kernel(const __grid_constant__ Params P) {
                 umma_commit(dfull + 8 * d);                        // ... and the accumulator is complete
             }
             __syncwarp();
+        }
+    } else if (HALF) {
+        // ===================== read-back + finish (HALF): two groups of four warps, group g drains accumulator g ==============
+        const int quad = warp & 3, grp = (warp - 2) >> 2;
+        const int row = quad * 32 + lane;                          // slab row = TMEM lane
+        const int r2 = row >= ROW_SLOT ? 1 : 0, J = row - r2 * ROW_SLOT;          // y4 row p + r2, y4 column J
+        const int H = 2 * P.h, W = 2 * P.w;
+        const int leader = 64 + grp * 128;                         // first thread of the group
+        const uint32_t ROWB = (uint32_t)W * 32;                    // bytes of one output row (2 planes x W x 16 B)
+        uint8_t* stage = o_base + grp * OUT_STAGE;                 // [4 output rows][2 planes][W][16 B] <= 14 KB
+        __half2 amax2 = __float2half2_rn(0.f);
+        const float slope = P.slope;
+        uint32_t k = 0;
+        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++k) {
+            if ((int)(k & 1) != grp) continue;
+            const uint32_t ph = (k >> 1) & 1;
+            const int n = tile / P.pairs, p = (tile - n * P.pairs) * 2;
+            mbar_wait(dfull + 8 * grp, ph);
+            tc_fence_after();
+            uint32_t r0[32], r1[32];
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + grp * NOUT;
+            TMEM_LD32(taddr, r0);
+            TMEM_LD32(taddr + 32, r1);
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(dempty + 8 * grp);
+            if (tid == leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the stores that read this buffer are done
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+            // phase (a, b) of y4 position (I, J) is output pixel (2 I - a, 2 J - b); local output row lr = Y - (2 p - 1)
+            const int I = p + r2;
+            if (I <= P.h && J <= P.w) {
+#pragma unroll
+                for (int ab = 0; ab < 4; ++ab) {
+                    const int a = ab >> 1, b = ab & 1;
+                    const int Y = 2 * I - a, X = 2 * J - b;
+                    if ((unsigned)Y < (unsigned)H && (unsigned)X < (unsigned)W) {
+                        const uint32_t* v = ab < 2 ? r0 + 16 * ab : r1 + 16 * (ab - 2);
+                        uint32_t hv[8];
+#pragma unroll
+                        for (int c = 0; c < 16; c += 2) {
+                            float v0 = __uint_as_float(v[c]) + P.bias[c], v1 = __uint_as_float(v[c + 1]) + P.bias[c + 1];
+                            v0 = fmaxf(v0, v0 * slope); v1 = fmaxf(v1, v1 * slope);
+                            const __half2 hh = __floats2half2_rn(v0, v1);
+                            amax2 = __hmax2_nan(amax2, __habs2(hh));
+                            hv[c >> 1] = h2_bits(hh);
+                        }
+                        uint8_t* d = stage + (uint32_t)(2 * r2 - a + 1) * ROWB + (uint32_t)X * 16;
+                        *reinterpret_cast<uint4*>(d) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+                        *reinterpret_cast<uint4*>(d + (uint32_t)W * 16) = make_uint4(hv[4], hv[5], hv[6], hv[7]);
+                    }
+                }
+            }
+            fence_async_smem();
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+            if (tid == leader) {
+                for (int lr = 0; lr < 4; ++lr) {
+                    const int Y = 2 * p - 1 + lr;
+                    if ((unsigned)Y >= (unsigned)H) continue;
+                    __half* gdst = P.yh + ((size_t)n * H + Y) * (size_t)W * 16;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(gdst), "r"(smem_u32(stage + lr * ROWB)), "r"(ROWB) : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        if (tid == leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        {
+            const float2 m = __half22float2(amax2);
+            if (P.status && !(fmaxf(m.x, m.y) <= 65504.f)) atomicOr(P.status, 1);
         }
     } else {
         // ===================== read-back warps: TMEM lane quadrant = warp % 4 =====================
@@ -184,13 +265,14 @@ static EncodeTiledFn get_encode_fn() {
 }  // namespace spctc
 }  // namespace riders
 
-extern "C" int riders_subpixel_conv_tc_nhwc(const float* x, const float* w_pack, int N, int h, int w, float* y4, void* stream) {
+static int subpixel_conv_tc_launch(const float* x, const float* w_pack, int N, int h, int w, float* y4, __half* yh,
+                                   const float* bias_host, float slope, int* status, void* stream) {
     using namespace riders;
     RIDERS_REQUIRE(N >= 0 && h > 0 && w > 0, "subpixel_conv_tc: bad shape");
     RIDERS_REQUIRE(w + 1 <= spctc::ROW_SLOT, "subpixel_conv_tc: at most %d columns (got w = %d)", spctc::ROW_SLOT - 1, w);
     if (N == 0) return RIDERS_OK;
-    RIDERS_REQUIRE(x && w_pack && y4, "subpixel_conv_tc: null pointer");
-    RIDERS_REQUIRE(((((uintptr_t)x) | ((uintptr_t)w_pack) | ((uintptr_t)y4)) & 15) == 0, "subpixel_conv_tc: 16-byte alignment");
+    RIDERS_REQUIRE(x && w_pack && (y4 || yh), "subpixel_conv_tc: null pointer");
+    RIDERS_REQUIRE(((((uintptr_t)x) | ((uintptr_t)w_pack) | ((uintptr_t)y4) | ((uintptr_t)yh)) & 15) == 0, "subpixel_conv_tc: 16-byte alignment");
     spctc::EncodeTiledFn enc = spctc::get_encode_fn();
     if (!enc) { set_error("subpixel_conv_tc: cuTensorMapEncodeTiled unavailable"); return RIDERS_ECUDA; }
     spctc::Params P;
@@ -204,15 +286,37 @@ extern "C" int riders_subpixel_conv_tc_nhwc(const float* x, const float* w_pack,
     if (cr != CUDA_SUCCESS) { set_error("subpixel_conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr); return RIDERS_ECUDA; }
     P.w_pack = reinterpret_cast<const uint4*>(w_pack);
     P.y4 = y4;
+    P.yh = yh;
+    P.status = status;
+    for (int c = 0; c < 16; ++c) P.bias[c] = bias_host ? bias_host[c] : 0.f;
+    P.slope = slope;
     P.h = h; P.w = w;
     P.pairs = (h + 2) / 2;
     const long long tiles = (long long)N * P.pairs;
     RIDERS_REQUIRE(tiles < (1ll << 31), "subpixel_conv_tc: too many tiles for one launch");
     P.n_tiles = (int)tiles;
-    static size_t configured[64] = {0};
-    if (int rc_smem = ensure_dynamic_smem(spctc::subpixel_conv_tc_kernel, (size_t)(spctc::SMEM_BYTES), configured, "subpixel_conv_tc: shared memory attribute")) return rc_smem;
     const int grid = tiles < sm_count() ? (int)tiles : sm_count();
     count_launches(1);
-    spctc::subpixel_conv_tc_kernel<<<grid, spctc::THREADS, spctc::SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    if (yh) {
+        static size_t configured[64] = {0};
+        if (int rc_smem = ensure_dynamic_smem(spctc::subpixel_conv_tc_kernel<true>, (size_t)(spctc::SMEM_BYTES), configured, "subpixel_conv_tc: shared memory attribute")) return rc_smem;
+        spctc::subpixel_conv_tc_kernel<true><<<grid, spctc::THREADS_HALF, spctc::SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    } else {
+        static size_t configured[64] = {0};
+        if (int rc_smem = ensure_dynamic_smem(spctc::subpixel_conv_tc_kernel<false>, (size_t)(spctc::SMEM_BYTES), configured, "subpixel_conv_tc: shared memory attribute")) return rc_smem;
+        spctc::subpixel_conv_tc_kernel<false><<<grid, spctc::THREADS, spctc::SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    }
     return check_launch("subpixel_conv_tc_nhwc");
+}
+
+extern "C" int riders_subpixel_conv_tc_nhwc(const float* x, const float* w_pack, int N, int h, int w, float* y4, void* stream) {
+    RIDERS_REQUIRE(y4 || N == 0, "subpixel_conv_tc: null pointer");
+    return subpixel_conv_tc_launch(x, w_pack, N, h, w, y4, nullptr, nullptr, 1.f, nullptr, stream);
+}
+
+extern "C" int riders_subpixel_conv_tc_half_nhwc(const float* x, const float* w_pack, int N, int h, int w, const float* bias_host,
+                                                 float slope, void* yh, int* status, void* stream) {
+    RIDERS_REQUIRE(yh || N == 0, "subpixel_conv_tc_half: null pointer");
+    RIDERS_REQUIRE(slope >= 0.f && slope <= 1.f, "subpixel_conv_tc_half: LeakyReLU slope must be in [0, 1] (got %g)", (double)slope);
+    return subpixel_conv_tc_launch(x, w_pack, N, h, w, nullptr, reinterpret_cast<__half*>(yh), bias_host, slope, status, stream);
 }

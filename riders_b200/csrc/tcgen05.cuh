@@ -43,6 +43,21 @@ __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) 
             "}\n" : "=r"(done) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
     } while (!done);
 }
+// wait with an explicit sleep between polls, for the roles of a pipeline that run ahead of its bottleneck stage: their wake-up
+// latency is absorbed by the rings, their polling would cost the busy warps issue slots
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        asm volatile("nanosleep.u32 %0;" ::"r"(ns) : "memory");
+    }
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");

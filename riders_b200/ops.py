@@ -592,6 +592,61 @@ def decoder_tail_tc(y4, bias_a, weight_b, bias_b, weight_head, slope=0.2, taps=3
     return out
 
 
+def subpixel_conv_tc_half(x, w2, bias, slope=0.2, flag=None):
+    """The last block's up-convolution finished in one kernel (tcgen05 phase convolution + depth-to-space + bias + LeakyReLU
+    + fp16): x (N,32,h,w) channels_last, activated -> yh (N, 2h, 2, 2w, 8) float16, the operand image ``decoder_tail_tc_half``
+    reads.  ``flag``: int32 device scalar receiving the fp16-range violation bit (created when None).  Returns (yh, flag)."""
+    _need_cuda(x, w2)
+    N, Cc, h, w = x.shape
+    if not (_is_channels_last(x) and x.dtype == torch.float32 and Cc == 32 and tuple(w2.shape) == (64, 32, 2, 2) and w <= 54):
+        raise _lib.RidersError("subpixel_conv_tc_half: needs a channels_last float32 (N,32,h,w<=54) map and (64,32,2,2) kernels")
+    yh = torch.empty((N, 2 * h, 2, 2 * w, 8), device=x.device, dtype=torch.float16)
+    if flag is None:
+        flag = torch.zeros(1, dtype=torch.int32, device=x.device)
+    with _span("subpixel_conv", N * (h + 1) * (w + 1) * 128 * 64 * 2):
+        rc = _lib.lib().riders_subpixel_conv_tc_half_nhwc(_ptr(x), _ptr(_subpixel_tc_weights(w2)), N, h, w, _ptr(_host_floats(bias)),
+                                                          float(slope), _ptr(yh), _ptr(flag), _stream())
+    _lib.check(rc, "riders_subpixel_conv_tc_half_nhwc")
+    return yh, flag
+
+
+def decoder_tail_tc_half(yh, weight_b, bias_b, weight_head, slope=0.2, sigmoid=False, flag=None):
+    """The tcgen05 decoder tail on the fp16 operand map of ``subpixel_conv_tc_half``: logits (N,1,2h,2w), flag."""
+    _need_cuda(yh, weight_b)
+    if not (yh.dim() == 5 and yh.dtype == torch.float16 and yh.is_contiguous() and yh.shape[2] == 2 and yh.shape[4] == 8
+            and yh.shape[1] % 2 == 0 and yh.shape[3] % 2 == 0 and tuple(weight_b.shape) == (16, 16, 3, 3)
+            and tuple(weight_head.shape) == (1, 16, 3, 3)):
+        raise _lib.RidersError("decoder_tail_tc_half: needs a contiguous float16 (N,2h,2,2w,8) map, a (16,16,3,3) and a (1,16,3,3) weight")
+    N, H, _, W, _ = yh.shape
+    out = torch.empty((N, 1, H, W), device=yh.device, dtype=torch.float32)
+    if flag is None:
+        flag = torch.zeros(1, dtype=torch.int32, device=yh.device)
+    with _span("decoder_tail", N * H * W * (16 * 16 * 9 + 16 * 9) * 2):
+        rc = _lib.lib().riders_decoder_tail_tc_half_nhwc(_ptr(yh), N, H // 2, W // 2, _ptr(_tail_tc_weights(weight_b, weight_head)),
+                                                         _ptr(_host_floats(bias_b)), float(slope), 1 if sigmoid else 0, _ptr(out),
+                                                         _ptr(flag), _stream())
+    _lib.check(rc, "riders_decoder_tail_tc_half_nhwc")
+    return out, flag
+
+
+def decoder_upconv_tail_tc(x, w2, bias_a, weight_b, bias_b, weight_head, slope=0.2, sigmoid=False, defer=False):
+    """Last decoder block + head from the 32-channel map ``x`` (N,32,h,w) on: ``subpixel_conv_tc_half`` -> ``decoder_tail_tc_half``
+    (both tcgen05 / TMEM, fp16 map between them).  One fp16-range flag for both; when raised the result comes from the TF32
+    flow (cuDNN phase convolution + mma.sync tail) - immediately, or at the caller's sync point with ``defer=True``."""
+    yh, flag = subpixel_conv_tc_half(x, w2, bias_a, slope)
+    out, _ = decoder_tail_tc_half(yh, weight_b, bias_b, weight_head, slope, sigmoid, flag=flag)
+    if x.shape[0] > 0:
+        def rerun():
+            y4 = torch.nn.functional.conv2d(x, w2, None, 1, 1)
+            return decoder_tail(y4, bias_a, weight_b, bias_b, weight_head, slope, 2, sigmoid)
+        guard = TailOverflow(flag, rerun)
+        if defer:
+            LoftrOverflow.pending.append((guard, (out,)))
+        elif guard.overflowed():
+            return guard.rerun()
+    return out
+
+
 def leaky_concat(a, b, slope=0.2, act_on_a=True, bias=None):
     """cat([leaky_relu(a [+ bias]), b], dim=1) for channels-last float32 CUDA maps in one pass (bit-exact)."""
     if bias is not None:

@@ -450,6 +450,7 @@ class MultiScaleDecoder(torch.nn.Module):
         # which kernel runs the fused tail: 'tcgen05' (decoder_tail_tc.cu: tcgen05.mma / TMEM, fp16 operands; a value outside the
         # fp16 range raises a device flag and the caller re-runs the mma.sync kernel) or 'mma_sync' (decoder_tail.cu, TF32)
         self.tail_impl = os.environ.get('RIDERS_TAIL_IMPL', 'tcgen05')
+        self.tail_fp16_map = os.environ.get('RIDERS_TAIL_FP16_MAP', '1') != '0'   # tcgen05 phase convolution writes the tail's fp16 operand map
         self.force_tail_impl = None                     # set by forward_output_batched for its re-run after a range violation
         self.defer_tail_check = False                   # True: the range flag is read at the caller's own sync point
         self.subconv_tc = os.environ.get('RIDERS_SUBCONV_TC', '0') != '0'      # ops.subpixel_conv_tc instead of cuDNN's 2x2 convolution: opt-in (both sit at the HBM bound of this write-heavy shape, cuDNN 10-15 % ahead)
@@ -522,6 +523,16 @@ class MultiScaleDecoder(torch.nn.Module):
             # TF32 flow (torch's default): the whole tail - depth-to-space + bias + LeakyReLU, the block's 16 -> 16
             # convolution, bias + LeakyReLU, the 16 -> 1 head - in ONE kernel fed by the sub-pixel phase convolution
             taps = 2 if (last.subpixel_taps == 2 and last._w2 is not None) else 3
+            impl = self.force_tail_impl or self.tail_impl
+            if (impl == 'tcgen05' and self.tail_fp16_map and raw_slope is None and taps == 2 and y.shape[1] == 32
+                    and tuple(last._w2.shape) == (64, 32, 2, 2) and y.shape[3] <= 54 and ops._is_channels_last(y)):
+                # the up-convolution finished by the tcgen05 phase convolution itself (fp16 operand map), then the tcgen05 tail
+                self.last_head_sigmoid = bool(head_sigmoid)
+                self.last_used_tail = True
+                self.last_tail_impl = 'tcgen05+fp16map'
+                return [ops.decoder_upconv_tail_tc(y, last._w2, last.deconv.conv.conv.bias, last.conv.conv.weight,
+                                                   last.conv.conv.bias, head.weight, _LEAK, sigmoid=head_sigmoid,
+                                                   defer=self.defer_tail_check)]
             if raw_slope is not None:
                 y4 = ops.subpixel_conv_act(y, raw_bias, raw_slope, last._w2)          # previous block's bias + LeakyReLU fused in
             elif (self.subconv_tc and taps == 2 and tuple(last._w2.shape) == (64, 32, 2, 2) and y.shape[3] <= 54
@@ -531,7 +542,6 @@ class MultiScaleDecoder(torch.nn.Module):
                 y4 = F.conv2d(y, last._w2 if taps == 2 else last._w4, None, 1, 1)
             self.last_head_sigmoid = bool(head_sigmoid)
             self.last_used_tail = True
-            impl = self.force_tail_impl or self.tail_impl
             self.last_tail_impl = impl
             if impl == 'tcgen05':
                 return [ops.decoder_tail_tc(y4, last.deconv.conv.conv.bias, last.conv.conv.weight, last.conv.conv.bias,

@@ -147,6 +147,23 @@ def bench_tail(R=2048):
         ops.LoftrOverflow.pending.clear()
         report("decoder_tail_tcgen05_taps%d" % taps, ms, best, nbytes, flops=flops, R=R)
 
+        if taps == 2:
+            x32 = torch.randn((R, 32, 120, 50), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+            w2 = torch.randn((64, 32, 2, 2), device=DEV, generator=g) * 0.1
+            ms, best = timeit(lambda: F.conv2d(x32, w2, None, 1, 1), iters=5)
+            report("phase_conv_cudnn_tf32", ms, best, x32.numel() * 4 + y4.numel() * 4, R=R)
+            ms, best = timeit(lambda: ops.subpixel_conv_tc_half(x32, w2, ba, 0.2), iters=5)
+            report("phase_conv_tcgen05_fp16_map", ms, best, x32.numel() * 4 + R * 24000 * 32, R=R)
+            yh, _ = ops.subpixel_conv_tc_half(x32, w2, ba, 0.2)
+            ms, best = timeit(lambda: ops.decoder_tail_tc_half(yh, wb, bb, wh, 0.2, sigmoid=True), iters=5)
+            report("decoder_tail_tcgen05_fp16_map", ms, best, R * 24000 * 36, flops=flops, R=R)
+            ms, best = timeit(lambda: ops.decoder_upconv_tail_tc(x32, w2, ba, wb, bb, wh, 0.2, sigmoid=True, defer=True), iters=5)
+            ops.LoftrOverflow.pending.clear()
+            report("upconv_tail_tcgen05_fp16_map (both kernels)", ms, best, x32.numel() * 4 + R * 24000 * 4, flops=flops, R=R)
+            ms, best = timeit(lambda: ops.decoder_tail_tc(F.conv2d(x32, w2, None, 1, 1), ba, wb, bb, wh, 0.2, taps=2, sigmoid=True, defer=True), iters=5)
+            ops.LoftrOverflow.pending.clear()
+            report("cudnn_phase_conv + decoder_tail_tcgen05", ms, best, x32.numel() * 4 + R * 24000 * 4, flops=flops, R=R)
+
         def separate():
             z = ops.d2s_bias_act_concat(y4, ba, None, 0.2, taps=taps)
             return ops.conv3x3_head(F.conv2d(z, wb, None, 1, 1), bb, 0.2, wh, sigmoid=True)

@@ -45,8 +45,42 @@ def case(N, h, w, taps, seed=0):
     return not bool(bad.any())
 
 
+def case_half(N, h, w, seed=0):
+    """fp16-map path: tcgen05 phase convolution finishing the up-convolution (yh) + tcgen05 tail reading it."""
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    x = torch.randn((N, 32, h, w), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    w2 = torch.randn((64, 32, 2, 2), device=DEV, generator=g) * 0.1
+    ba, bb = torch.randn(16, device=DEV, generator=g) * 0.3, torch.randn(16, device=DEV, generator=g) * 0.3
+    wb = torch.randn((16, 16, 3, 3), device=DEV, generator=g) * 0.15
+    wh = torch.randn((1, 16, 3, 3), device=DEV, generator=g) * 0.2
+    xt = (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)                     # the tensor core truncates to TF32
+    w2t = ((w2.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    y4 = F.conv2d(xt, w2t, None, 1, 1).contiguous(memory_format=torch.channels_last)
+    y = ops.d2s_bias_act_concat(y4, ba, None, 0.2, taps=2).contiguous()                       # (N,16,2h,2w)
+    yh, flag = ops.subpixel_conv_tc_half(x, w2, ba, 0.2)
+    torch.cuda.synchronize()
+    yref = y.view(N, 2, 8, 2 * h, 2 * w).permute(0, 3, 1, 4, 2)                               # [n][Y][plane][X][k]
+    ey = (yh.float() - yref).abs()
+    print("half N=%d h=%d w=%d: yh max err %.3e (scale %.2f), flag %d" % (N, h, w, float(ey.max()), float(yref.abs().max()), int(flag.item())), flush=True)
+    z = F.leaky_relu(F.conv2d(h16(y), h16(wb), None, 1, 1) + bb.view(1, -1, 1, 1), 0.2)
+    ref = F.conv2d(h16(z), h16(wh), None, 1, 1)
+    got = ops.decoder_upconv_tail_tc(x, w2, ba, wb, bb, wh, 0.2)
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    err = (got - ref).abs()
+    bad = err > 2e-3 * scale
+    print("   logits scale %.3f  max err %.3e  bad fraction %.4f" % (scale, float(err.max()), float(bad.float().mean())), flush=True)
+    if bool(bad.any()):
+        rows = bad.any(dim=3).any(dim=1).any(dim=0).nonzero().flatten().tolist()
+        cols = bad.any(dim=2).any(dim=1).any(dim=0).nonzero().flatten().tolist()
+        print("   bad rows", rows[:40], "... cols", cols[:40], flush=True)
+    return (not bool(bad.any())) and float(ey.max()) < 4e-3 * float(yref.abs().max())
+
+
 if __name__ == "__main__":
     ok = True
     for N, h, w, taps in ((1, 8, 5, 3), (3, 7, 9, 2), (2, 13, 30, 3), (3, 120, 50, 2), (2, 40, 70, 3), (40, 120, 50, 2)):
         ok = case(N, h, w, taps) and ok
+    for N, h, w in ((1, 8, 5), (3, 7, 9), (2, 13, 30), (3, 120, 50), (40, 120, 50)):
+        ok = case_half(N, h, w) and ok
     print("ALL OK" if ok else "MISMATCH", flush=True)
