@@ -46,7 +46,6 @@ constexpr int SLOT = 2 * PLANE;                      // 4352 B: one staged row (
 constexpr int NYS = 8, NZS = 6;                      // y / z operand ring slots
 constexpr int ZR = 12;                               // z accumulator ring: 16 TMEM columns each
 constexpr int NDH = 4;                               // head accumulator ring: 16 TMEM columns each
-constexpr int LAG = 3;                               // the head of z row q is issued after the convolution of y row q + 2 + LAG
 constexpr uint32_t TMEM_COLS = 256, DH_COL0 = 16 * ZR;
 constexpr int WB_BYTES = 3 * 48 * 32, WH_BYTES = 3 * 16 * 32, W_BYTES = WB_BYTES + WH_BYTES;      // 4608 + 1536
 constexpr int B_YFULL = 0, B_YFREE = B_YFULL + NYS, B_ZFULL = B_YFREE + NYS, B_ZFREE = B_ZFULL + NZS, B_AFULL = B_ZFREE + NZS,
@@ -55,8 +54,12 @@ constexpr int B_YFULL = 0, B_YFREE = B_YFULL + NYS, B_ZFULL = B_YFREE + NYS, B_Z
 // fp16 input (the finished map of riders_subpixel_conv_tc_half_nhwc): nothing to compute while staging - lane 0 of warp 0
 // bulk-copies rows straight into the operand ring, warp 1 issues the MMAs, warps 4-7 / 8-11 are the epilogues.
 template <bool HALF_IN> struct Roles {
-    static constexpr int LOADER_WARPS = HALF_IN ? 1 : 8, W_EPI1 = HALF_IN ? 4 : 8, W_EPI2 = W_EPI1 + 4, W_MMA = HALF_IN ? 1 : 16;
-    static constexpr int THREADS = HALF_IN ? 12 * 32 : 17 * 32;
+    // z epilogue groups (four warps each, alternating z rows): a row's epilogue is one serial chain of TMEM / shared-memory
+    // round trips per warp, so with the staging arithmetic gone (fp16 input) ONE group is the slowest stage of the pipeline
+    static constexpr int EPI1_GROUPS = HALF_IN ? 2 : 1;
+    static constexpr int LOADER_WARPS = HALF_IN ? 1 : 8, W_EPI1 = HALF_IN ? 4 : 8, W_EPI2 = W_EPI1 + 4 * EPI1_GROUPS, W_MMA = HALF_IN ? 1 : 16;
+    static constexpr int W_MMA_HEAD = HALF_IN ? 2 : 17;             // the head's MMAs have their own issuing warp (see there)
+    static constexpr int THREADS = HALF_IN ? 16 * 32 : 18 * 32;
     static constexpr int YSLOTS = NYS + (HALF_IN ? 1 : 0);          // + a slot that stays zero: the rows outside the image
     static constexpr int SMEM_BYTES = (YSLOTS + NZS) * SLOT + W_BYTES + NBARS * 8 + 16;
 };
@@ -70,6 +73,7 @@ struct Params {
     int t;                   // 0: y4 from the 3x3 phase kernels (h, w); 1: from the 2x2 phase kernels, (h + 1, w + 1)
     int h, w;
     int tiles_x, row_splits, rows_per;
+    int dbg;                 // timing experiments only (riders_debug_set("tail_tc_dbg")): 1 = one head MMA, 2 = one convolution MMA per row
 };
 
 __device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
@@ -84,6 +88,7 @@ template <bool HALF_IN>
 __global__ void __launch_bounds__(Roles<HALF_IN>::THREADS, 2)
 decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ wpack, float* __restrict__ out,
                        int* __restrict__ status, const __grid_constant__ Params P) {
+    constexpr int EPI1_GROUPS = Roles<HALF_IN>::EPI1_GROUPS, W_MMA_HEAD = Roles<HALF_IN>::W_MMA_HEAD;
     constexpr int LOADER_WARPS = Roles<HALF_IN>::LOADER_WARPS, W_EPI1 = Roles<HALF_IN>::W_EPI1, W_EPI2 = Roles<HALF_IN>::W_EPI2,
                   W_MMA = Roles<HALF_IN>::W_MMA, THREADS = Roles<HALF_IN>::THREADS, YSLOTS = Roles<HALF_IN>::YSLOTS;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -121,7 +126,7 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    if (warp >= W_EPI1 && warp < W_EPI2) {                // z accumulators start from zero (their readers keep them so)
+    if (warp >= W_EPI1 && warp < W_EPI1 + 4) {            // z accumulators start from zero (their readers keep them so)
         for (int i = 0; i < ZR; ++i) tmem_zero16(tmem + ((uint32_t)((warp - W_EPI1) * 32) << 16) + 16 * i);
         tc_fence_before();
     }
@@ -236,11 +241,12 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
         }
     } else if (warp >= W_EPI1 && warp < W_EPI2) {
         // ===================== z epilogue: TMEM -> bias_b + LeakyReLU + image mask -> fp16 -> z ring =====================
-        const int lg = warp - W_EPI1, x = lg * 32 + lane; // TMEM lane = z position; image column C0 - 1 + x
+        static_assert(ZR % EPI1_GROUPS == 0 && NZS % EPI1_GROUPS == 0, "a group keeps the parity of its ring slots");
+        const int lg = (warp - W_EPI1) & 3, grp = (warp - W_EPI1) >> 2, x = lg * 32 + lane;   // TMEM lane = z position; image column C0 - 1 + x
         const bool colok = (unsigned)(C0 - 1 + x) < (unsigned)W;
         const uint32_t trow = tmem + ((uint32_t)(lg * 32) << 16);
-        int st = 0, stph = 0, zsl = 0, zph = 1;
-        for (int rz = 0; rz < nz; ++rz) {
+        int st = grp, stph = 0, zsl = grp, zph = 1;       // group g takes z rows g, g + EPI1_GROUPS, ...
+        for (int rz = grp; rz < nz; rz += EPI1_GROUPS) {
             mbar_wait_sleep(bar(B_AFULL + st), stph, 100);
             tc_fence_after();
             uint32_t r[16];
@@ -266,8 +272,8 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(B_ZFULL + zsl));
-            if (++st == ZR) { st = 0; stph ^= 1; }
-            if (++zsl == NZS) { zsl = 0; zph ^= 1; }
+            if ((st += EPI1_GROUPS) >= ZR) { st -= ZR; stph ^= 1; }
+            if ((zsl += EPI1_GROUPS) >= NZS) { zsl -= NZS; zph ^= 1; }
         }
     } else if (warp >= W_EPI2 && warp < W_EPI2 + 4) {
         // ===================== head epilogue: logits[o] = Dh[o-1][0] + Dh[o][1] + Dh[o+1][2] =====================
@@ -293,16 +299,14 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
         }
     } else if (warp == W_MMA) {
         // ===================== MMA issuer: the whole warp runs the (warp-uniform) control flow, one elected lane issues ======
-        const uint32_t ya = smem_u32(ys), za = smem_u32(zs), wa = smem_u32(ws);
+        const uint32_t ya = smem_u32(ys), wa = smem_u32(ws);
         constexpr uint32_t I16 = idesc_f16(16), I32 = idesc_f16(32), I48 = idesc_f16(48);
         // descriptors differ only in their start-address field (units of 16 B): + SLOT / 16 per ring slot, + 1 per pixel of
         // horizontal shift; B: + 96 per tap dx (1536 B), + 32 per kernel row (512 B)
-        const uint64_t yd0 = smem_desc_nosw(ya, PLANE, 128), zd0 = smem_desc_nosw(za, PLANE, 128);
-        const uint64_t bd0 = smem_desc_nosw(wa, 128, 256), hd0 = smem_desc_nosw(wa + WB_BYTES, 128, 256);
+        const uint64_t yd0 = smem_desc_nosw(ya, PLANE, 128), bd0 = smem_desc_nosw(wa, 128, 256);
         int ysl = 0, yph = 0, zr = 0, zrph = 1;           // y operand slot / phase, accumulator slot of z row t / its free phase
-        int hzs = 0, hzph = 0, hds = 0, hdph = 1;         // z operand slot / phase, head accumulator slot / its free phase
-        for (int t = 0; t < ny + LAG; ++t) {
-            if (t < ny) {
+        for (int t = 0; t < ny; ++t) {
+            {
                 // y row t: kernel row dy' of the 3x3 accumulates into z row t - dy' (relative); the accumulator of z row t must
                 // have been read (and zeroed) by the epilogue of its previous tenant
                 const bool yring = !HALF_IN || (unsigned)(zlo - 1 + t) < (unsigned)H;      // fp16 input: rows outside = the zero slot
@@ -318,7 +322,8 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
                         if (zr >= 2) {
                             const uint32_t c0 = tmem + 16 * (ZR - 1 - zr);
 #pragma unroll
-                            for (int dx = 0; dx < 3; ++dx) umma_f16(c0, ad + dx, bd0 + 96 * dx, I48, 1);
+                            for (int dx = 0; dx < 3; ++dx)
+                                if (dx == 0 || !(P.dbg & 2)) umma_f16(c0, ad + dx, bd0 + 96 * dx, I48, 1);
                         } else if (zr == 1) {               // rows t, t-1 -> columns 160..191, row t-2 -> column 0
 #pragma unroll
                             for (int dx = 0; dx < 3; ++dx) {
@@ -352,24 +357,33 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
                 if (yring && ++ysl == NYS) { ysl = 0; yph ^= 1; }
                 if (++zr == ZR) { zr = 0; zrph ^= 1; }
             }
-            const int hz = t - 2 - LAG;
-            if (hz >= 0 && hz < nz) {
-                mbar_wait(bar(B_ZFULL + hzs), hzph);
-                mbar_wait(bar(B_HFREE + hds), hdph);
-                tc_fence_after();
-                const uint64_t ad = zd0 + (uint64_t)(hzs * (SLOT / 16));
-                const uint32_t d = tmem + DH_COL0 + 16 * hds;
-                if (elect_one()) {
-                    umma_f16(d, ad, hd0, I16, 0);
+        }
+    } else if (warp == W_MMA_HEAD) {
+        // ===================== MMA issuer of the head: its own warp.  One warp issuing both convolutions was the slowest
+        // stage of the pipeline (~170 instructions of dependent barrier / descriptor arithmetic per row); the two streams
+        // are independent (tcgen05.commit tracks the MMAs of the issuing thread) ======
+        const uint32_t za = smem_u32(zs), wa = smem_u32(ws);
+        constexpr uint32_t I16 = idesc_f16(16);
+        const uint64_t zd0 = smem_desc_nosw(za, PLANE, 128), hd0 = smem_desc_nosw(wa + WB_BYTES, 128, 256);
+        int hzs = 0, hzph = 0, hds = 0, hdph = 1;         // z operand slot / phase, head accumulator slot / its free phase
+        for (int hz = 0; hz < nz; ++hz) {
+            mbar_wait(bar(B_ZFULL + hzs), hzph);
+            mbar_wait(bar(B_HFREE + hds), hdph);
+            tc_fence_after();
+            const uint64_t ad = zd0 + (uint64_t)(hzs * (SLOT / 16));
+            const uint32_t d = tmem + DH_COL0 + 16 * hds;
+            if (elect_one()) {
+                umma_f16(d, ad, hd0, I16, 0);
+                if (!(P.dbg & 1)) {
                     umma_f16(d, ad + 1, hd0 + 32, I16, 1);
                     umma_f16(d, ad + 2, hd0 + 64, I16, 1);
-                    umma_commit(bar(B_ZFREE + hzs));
-                    umma_commit(bar(B_HFULL + hds));
                 }
-                __syncwarp();
-                if (++hzs == NZS) { hzs = 0; hzph ^= 1; }
-                if (++hds == NDH) { hds = 0; hdph ^= 1; }
+                umma_commit(bar(B_ZFREE + hzs));
+                umma_commit(bar(B_HFULL + hds));
             }
+            __syncwarp();
+            if (++hzs == NZS) { hzs = 0; hzph ^= 1; }
+            if (++hds == NDH) { hds = 0; hdph ^= 1; }
         }
     }
     {
@@ -381,7 +395,9 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
     if (warp == W_MMA) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+static int g_dbg = 0;
 }  // namespace tailtc
+void set_tail_tc_dbg(int v) { tailtc::g_dbg = v; }
 }  // namespace riders
 
 static int decoder_tail_tc_launch(const void* in, bool half_in, int taps, int N, int h, int w, const float* bias_a_host,
@@ -403,6 +419,7 @@ static int decoder_tail_tc_launch(const void* in, bool half_in, int taps, int N,
     P.sigmoid = apply_sigmoid ? 1 : 0;
     P.t = taps == 2 ? 1 : 0;
     P.h = h; P.w = w;
+    P.dbg = tailtc::g_dbg;
     const int H = 2 * h, W = 2 * w;
     P.tiles_x = ceil_div(W, tailtc::TC);
     // a strip is a whole column of the map unless that leaves SMs idle (few points): then the rows are split too

@@ -46,6 +46,7 @@ extern "C" int riders_abi_version(void) { return 2; }
 extern "C" unsigned long long riders_launch_count(void) { return riders::g_launches.load(std::memory_order_relaxed); }
 extern "C" int riders_debug_set(const char* key, int value) {
     if (key && !strcmp(key, "gather_smem_kb")) { riders::set_gather_smem_budget(value); return RIDERS_OK; }
+    if (key && !strcmp(key, "tail_tc_dbg")) { riders::set_tail_tc_dbg(value); return RIDERS_OK; }
     if (key && !strcmp(key, "lsq_fused")) { riders::set_lsq_mode(value); return RIDERS_OK; }
     if (key && !strcmp(key, "reduce_tile_w")) { riders::set_reduce_tile_w(value); return RIDERS_OK; }
     if (key && !strcmp(key, "reduce_rows")) { riders::set_reduce_rows(value); return RIDERS_OK; }
