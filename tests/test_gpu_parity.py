@@ -990,6 +990,55 @@ def test_decoder_tail_tcgen05_matches_fp16_operand_convolutions(hw, N, taps):
     assert float((got - ops.decoder_tail(y4, ba, wb, bb, wh, 0.2, taps=taps)).abs().max()) < 2e-3 * scale
 
 
+@pytest.mark.parametrize("hw,N", [((120, 50), 3), ((7, 9), 2), ((13, 30), 5), ((2, 3), 1), ((120, 50), 40), ((31, 54), 2)])
+def test_upconv_and_tail_on_tcgen05_through_the_fp16_operand_map(hw, N):
+    """ops.subpixel_conv_tc_half (tcgen05 phase convolution whose epilogue finishes the up-convolution: depth-to-space + bias +
+    LeakyReLU + fp16, written as the tail's operand image) and ops.decoder_tail_tc_half (rows bulk-copied into the operand
+    ring).  The map equals fp16(act(d2s(conv2x2(TF32-truncated x, TF32-rounded W2)) + bias)) up to the fp32 summation order
+    (one fp16 ulp where the sum sits on a rounding boundary); the logits follow the same reference as the float-input tail."""
+    F = torch.nn.functional
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device=DEV).manual_seed(hw[0] + 3 * N)
+    h, w = hw
+    x = torch.randn((N, 32, h, w), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    w2 = torch.randn((64, 32, 2, 2), device=DEV, generator=g) * 0.1
+    ba, bb = torch.randn(16, device=DEV, generator=g) * 0.3, torch.randn(16, device=DEV, generator=g) * 0.3
+    wb = torch.randn((16, 16, 3, 3), device=DEV, generator=g) * 0.15
+    wh = torch.randn((1, 16, 3, 3), device=DEV, generator=g) * 0.2
+    x_trunc = (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+    y4 = F.conv2d(x_trunc, _tf32_rna(w2), None, 1, 1).contiguous(memory_format=torch.channels_last)
+    y = ops.d2s_bias_act_concat(y4, ba, None, 0.2, taps=2).contiguous()
+    yh, flag = ops.subpixel_conv_tc_half(x, w2, ba, 0.2)
+    assert yh.shape == (N, 2 * h, 2, 2 * w, 8) and yh.dtype == torch.float16 and int(flag.item()) == 0
+    yref = y.view(N, 2, 8, 2 * h, 2 * w).permute(0, 3, 1, 4, 2)                      # [n][Y][plane][X][k]
+    ysc = float(yref.abs().max())
+    ey = (yh.float() - yref).abs()
+    assert float(ey.max()) <= 2.0 ** -10 * ysc and float((ey > 2.0 ** -11 * yref.abs() + 1e-7).float().mean()) < 0.02
+    y16 = yh.float().permute(0, 2, 4, 1, 3).reshape(N, 16, 2 * h, 2 * w)           # the map the tail really reads
+    zh = F.leaky_relu(F.conv2d(y16, _fp16(wb), None, 1, 1) + bb.view(1, -1, 1, 1), 0.2)
+    refh = F.conv2d(_fp16(zh), _fp16(wh), None, 1, 1)
+    ref32 = F.conv2d(F.leaky_relu(F.conv2d(y, wb, bb, 1, 1), 0.2), wh, None, 1, 1)
+    out, _ = ops.decoder_tail_tc_half(yh, wb, bb, wh, 0.2, flag=flag)
+    got = ops.decoder_upconv_tail_tc(x, w2, ba, wb, bb, wh, 0.2)
+    assert torch.equal(out, got) and int(flag.item()) == 0
+    scale = float(ref32.abs().max())
+    err = (got - refh).abs()
+    assert float(err.mean()) < 4e-6 * scale and float(err.max()) < 5e-4 * scale
+    assert float((err > 2e-5 * scale).float().mean()) < 0.05
+    # against the library flow it replaces (cuDNN fp32 phase convolution + the three fp32 passes): operand accuracy
+    y32 = ops.d2s_bias_act_concat(F.conv2d(x, w2, None, 1, 1).contiguous(memory_format=torch.channels_last), ba, None, 0.2, taps=2)
+    full32 = F.conv2d(F.leaky_relu(F.conv2d(y32.contiguous(), wb, bb, 1, 1), 0.2), wh, None, 1, 1)
+    assert float((got - full32).abs().max()) < 3e-3 * float(full32.abs().max())
+    sg = ops.decoder_upconv_tail_tc(x, w2, ba, wb, bb, wh, 0.2, sigmoid=True)
+    np.testing.assert_allclose(sg.cpu().numpy(), torch.sigmoid(got).cpu().numpy(), rtol=2e-6, atol=1e-7)
+    # range guard: an activation beyond fp16 -> the TF32 library flow answers
+    xb = x.clone()
+    xb[0, :, 0, 0] = 3.0e5
+    refb = ops.decoder_tail(F.conv2d(xb, w2, None, 1, 1), ba, wb, bb, wh, 0.2, taps=2)
+    torch.backends.cudnn.allow_tf32 = False
+    assert torch.equal(ops.decoder_upconv_tail_tc(xb, w2, ba, wb, bb, wh, 0.2), refb)
+
+
 def test_decoder_tail_tcgen05_fp16_range_guard():
     """Activations beyond the fp16 range (a limit neither the fp32 reference nor the TF32 kernel has) raise the device flag of
     riders_decoder_tail_tc_nhwc: ops.decoder_tail_tc then returns the mma.sync TF32 kernel's result (bit-identical to calling
@@ -1093,6 +1142,12 @@ def test_decoder_uses_the_fused_tail_only_where_tf32_is_allowed(monkeypatch):
         assert not calls and not subs
         torch.backends.cudnn.allow_tf32 = True
         try:
+            dec.tail_fp16_map = True                                  # default: tcgen05 phase convolution -> fp16 operand map -> tcgen05 tail
+            if dec.tail_impl == "tcgen05":
+                got5 = dec(x, skips, shape=(240, 100))[-1]
+                assert dec.last_tail_impl == "tcgen05+fp16map" and dec.last_used_tail and not calls and not tcs
+                assert float((got5 - ref).abs().max()) < 5e-3 * float(ref.abs().max())
+            dec.tail_fp16_map = False                                 # the float y4 interface (RIDERS_TAIL_FP16_MAP=0)
             dec.fused_sub = True                                      # opt-in (RIDERS_FUSED_SUBCONV=1)
             got = dec(x, skips, shape=(240, 100))[-1]                 # mma.sync phase convolution (+ fused activation) + tail
             assert len(calls) == 1 and len(subs) == 1 and not tcs
