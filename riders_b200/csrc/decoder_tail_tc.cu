@@ -27,10 +27,10 @@
 // every staged value passes a running max and a value outside the fp16 range raises `status` (the host then re-runs the
 // mma.sync TF32 kernel, ops.decoder_tail).
 //
-// Warp roles (17 warps, 2 CTAs per SM, 256 TMEM columns each): 0-7 stage y rows (global -> bias + LeakyReLU -> fp16 -> ring),
-// 8-11 z epilogue (TMEM -> bias + LeakyReLU + image mask -> fp16 -> z ring), 12-15 head epilogue (TMEM -> sum -> sigmoid ->
-// global), 16: one elected lane issues every MMA.  All hand-offs are mbarriers; TMEM and shared-memory rings are freed by
-// tcgen05.commit (operands) or by the reading warps (accumulators).
+// Warp roles (2 CTAs per SM, 256 TMEM columns each; see Roles below): staging warps (float input: global -> bias + LeakyReLU ->
+// fp16 -> ring; fp16 input: one lane bulk-copies rows), z epilogue groups (TMEM -> bias + LeakyReLU + image mask -> fp16 -> z
+// ring), head epilogue groups (TMEM -> sum -> sigmoid -> global), one MMA-issuing warp per convolution.  All hand-offs are
+// mbarriers; TMEM and shared-memory rings are freed by tcgen05.commit (operands) or by the reading warps (accumulators).
 #include "common.cuh"
 #include "tcgen05.cuh"
 #include <cuda_fp16.h>
@@ -57,9 +57,12 @@ template <bool HALF_IN> struct Roles {
     // z epilogue groups (four warps each, alternating z rows): a row's epilogue is one serial chain of TMEM / shared-memory
     // round trips per warp, so with the staging arithmetic gone (fp16 input) ONE group is the slowest stage of the pipeline
     static constexpr int EPI1_GROUPS = HALF_IN ? 2 : 1;
+    // head epilogue groups: two were built and measured NO faster (0.79 vs 0.76 ms) - by then the shared-memory pipe (tensor-core
+    // operand reads: 3.5 + 3 MMAs x ~40 wavefronts per row and CTA) is ~85 % busy, which no amount of warps changes
+    static constexpr int EPI2_GROUPS = 1;
     static constexpr int LOADER_WARPS = HALF_IN ? 1 : 8, W_EPI1 = HALF_IN ? 4 : 8, W_EPI2 = W_EPI1 + 4 * EPI1_GROUPS, W_MMA = HALF_IN ? 1 : 16;
     static constexpr int W_MMA_HEAD = HALF_IN ? 2 : 17;             // the head's MMAs have their own issuing warp (see there)
-    static constexpr int THREADS = HALF_IN ? 16 * 32 : 18 * 32;
+    static constexpr int THREADS = HALF_IN ? (4 + 4 * EPI1_GROUPS + 4 * EPI2_GROUPS) * 32 : 18 * 32;
     static constexpr int YSLOTS = NYS + (HALF_IN ? 1 : 0);          // + a slot that stays zero: the rows outside the image
     static constexpr int SMEM_BYTES = (YSLOTS + NZS) * SLOT + W_BYTES + NBARS * 8 + 16;
 };
@@ -88,7 +91,7 @@ template <bool HALF_IN>
 __global__ void __launch_bounds__(Roles<HALF_IN>::THREADS, 2)
 decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ wpack, float* __restrict__ out,
                        int* __restrict__ status, const __grid_constant__ Params P) {
-    constexpr int EPI1_GROUPS = Roles<HALF_IN>::EPI1_GROUPS, W_MMA_HEAD = Roles<HALF_IN>::W_MMA_HEAD;
+    constexpr int EPI1_GROUPS = Roles<HALF_IN>::EPI1_GROUPS, EPI2_GROUPS = Roles<HALF_IN>::EPI2_GROUPS, W_MMA_HEAD = Roles<HALF_IN>::W_MMA_HEAD;
     constexpr int LOADER_WARPS = Roles<HALF_IN>::LOADER_WARPS, W_EPI1 = Roles<HALF_IN>::W_EPI1, W_EPI2 = Roles<HALF_IN>::W_EPI2,
                   W_MMA = Roles<HALF_IN>::W_MMA, THREADS = Roles<HALF_IN>::THREADS, YSLOTS = Roles<HALF_IN>::YSLOTS;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -117,7 +120,7 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
         for (int i = 0; i < NYS; ++i) { mbar_init(bar(B_YFULL + i), HALF_IN ? 1 : LOADER_WARPS); mbar_init(bar(B_YFREE + i), 1); }
         for (int i = 0; i < NZS; ++i) { mbar_init(bar(B_ZFULL + i), 4); mbar_init(bar(B_ZFREE + i), 1); }
         for (int i = 0; i < ZR; ++i)  { mbar_init(bar(B_AFULL + i), 1); mbar_init(bar(B_AFREE + i), 4); }
-        for (int i = 0; i < NDH; ++i) { mbar_init(bar(B_HFULL + i), 1); mbar_init(bar(B_HFREE + i), 4); }
+        for (int i = 0; i < NDH; ++i) { mbar_init(bar(B_HFULL + i), 1); mbar_init(bar(B_HFREE + i), EPI2_GROUPS == 1 ? 4 : 12); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -275,14 +278,23 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
             if ((st += EPI1_GROUPS) >= ZR) { st -= ZR; stph ^= 1; }
             if ((zsl += EPI1_GROUPS) >= NZS) { zsl -= NZS; zph ^= 1; }
         }
-    } else if (warp >= W_EPI2 && warp < W_EPI2 + 4) {
+    } else if (warp >= W_EPI2 && warp < W_EPI2 + 4 * EPI2_GROUPS) {
         // ===================== head epilogue: logits[o] = Dh[o-1][0] + Dh[o][1] + Dh[o+1][2] =====================
-        const int lg = warp - W_EPI2, x = lg * 32 + lane; // TMEM lane = output position; image column C0 + x
+        // One group: rows in order, Dh[q-1] is free once row q has been read.  Two groups (alternating rows, running concurrently):
+        // an accumulator is free when ALL its reader rows have arrived (3 rows x 4 warps = 12); the readers that do not exist at
+        // the top of the strip are arrived for up front.
+        const int lg = (warp - W_EPI2) & 3, grp = (warp - W_EPI2) >> 2, x = lg * 32 + lane;   // TMEM lane = output position; image column C0 + x
         const bool ok = x < TC && C0 + x < W;
         const uint32_t trow = tmem + ((uint32_t)(lg * 32) << 16) + DH_COL0;
-        float* op = out + (size_t)n * H * W + (size_t)R0 * W + (ok ? C0 + x : 0);
         static_assert(NDH == 4, "head ring indices are masked");
-        for (int q = R0 - zlo; q < R1 - zlo; ++q, op += W) {               // q = o - zlo: z row of the output row, 0 <= q < nz
+        const int q0 = R0 - zlo, q1 = R1 - zlo;           // q = o - zlo: z row of the output row, 0 <= q < nz
+        if (EPI2_GROUPS > 1 && grp == 0 && lane == 0) {
+            for (int j = 0; j < 2 && j < nz; ++j)
+                for (int r = j - 1; r <= j + 1; ++r)
+                    if (r < q0) mbar_arrive(bar(B_HFREE + (j & 3)));
+        }
+        float* op = out + (size_t)n * H * W + (size_t)(R0 + grp) * W + (ok ? C0 + x : 0);
+        for (int q = q0 + grp; q < q1; q += EPI2_GROUPS, op += EPI2_GROUPS * W) {
             const int hq = min(q + 1, nz - 1);
             mbar_wait_sleep(bar(B_HFULL + (hq & 3)), (hq >> 2) & 1, 100);
             tc_fence_after();
@@ -293,7 +305,13 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
             tmem_wait_ld();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0 && q >= 1) mbar_arrive(bar(B_HFREE + ((q - 1) & 3)));
+            if (lane == 0) {
+                if (q >= 1) mbar_arrive(bar(B_HFREE + ((q - 1) & 3)));
+                if (EPI2_GROUPS > 1) {
+                    mbar_arrive(bar(B_HFREE + (q & 3)));
+                    if (q + 1 < nz) mbar_arrive(bar(B_HFREE + ((q + 1) & 3)));
+                }
+            }
             const float sum = (__uint_as_float(v0) + __uint_as_float(v1)) + __uint_as_float(v2);
             if (ok) __stcs(op, P.sigmoid ? (1.0f / (1.0f + expf(-sum))) : sum);
         }

@@ -109,3 +109,59 @@ def test_subpixel_fragments_and_tcgen05_slabs():
                 seen[off] = True
     assert seen.sum() == 4 * 6 * 5                                        # the sampled offsets are all distinct (a permutation)
     assert torch.equal(torch.sort(p).values, torch.sort(wr.permute(2, 3, 0, 1).reshape(-1)).values)
+
+
+def test_tcgen05_tail_weight_pack_is_the_unswizzled_k_major_image():
+    """ops._tail_tc_weights: the 6144-byte fp16 B-operand image of riders_decoder_tail_tc_nhwc.  Emulate what the tensor core
+    computes from it - D[m][n] = sum_k A[m][k] B[n][k] with B read through the unswizzled K-major descriptor (core matrix =
+    8 rows x 16 bytes, 256 B between 8-row groups, 128 B between the two K chunks) and A = the rows of an operand row slot
+    shifted by dx pixels - and check that accumulating the N blocks into z rows r+1, r, r-1 IS the 3x3 convolution (and the
+    head's N = 16 image its three kernel rows)."""
+    torch.manual_seed(7)
+    wb, wh = torch.randn(16, 16, 3, 3) * 0.2, torch.randn(1, 16, 3, 3) * 0.2
+    pack = ops._tail_tc_weights(wb, wh)
+    assert pack.dtype == torch.float16 and pack.numel() * 2 == 6144
+    raw = pack.numpy()
+
+    def b_matrix(byte0, rows):                       # rows x 16 matrix as the descriptor (LBO 128, SBO 256) addresses it
+        m = np.zeros((rows, 16), np.float32)
+        for n in range(rows):
+            for k in range(16):
+                off = byte0 + (n // 8) * 256 + (k // 8) * 128 + (n % 8) * 16 + (k % 8) * 2
+                m[n, k] = raw[off // 2]
+        return m
+    H, W = 6, 9
+    y = torch.randn(1, 16, H, W).half().float()
+    wbh, whh = wb.half().float(), wh.half().float()
+    ref_z = F.conv2d(y, wbh, None, 1, 1)[0]                                    # (16, H, W)
+    ypad = F.pad(y, (1, 1, 0, 0))[0].permute(1, 2, 0).numpy()                 # (H, W + 2, 16): column x + dx of the padded row
+    z = np.zeros((H, W, 16), np.float32)
+    for r in range(H):                                                         # y row r feeds z rows r + 1 - dy'
+        for dx in range(3):
+            B = b_matrix(dx * 1536, 48)                                        # n = 16 dy' + co
+            D = ypad[r, dx:dx + W, :] @ B.T                                    # (W, 48)
+            for dyp in range(3):
+                q = r + 1 - dyp
+                if 0 <= q < H:
+                    z[q] += D[:, 16 * dyp:16 * dyp + 16]
+    np.testing.assert_allclose(z.transpose(2, 0, 1), ref_z.numpy(), rtol=1e-5, atol=1e-5)
+    zt = torch.randn(1, 16, H, W).half().float()
+    ref_o = F.conv2d(zt, whh, None, 1, 1)[0, 0]
+    zpad = F.pad(zt, (1, 1, 0, 0))[0].permute(1, 2, 0).numpy()
+    Dh = np.zeros((H, W, 16), np.float32)
+    for q in range(H):
+        for dx in range(3):
+            Dh[q] += zpad[q, dx:dx + W, :] @ b_matrix(4608 + dx * 512, 16).T
+    assert not Dh[:, :, 3:].any()                                              # rows 3..15 of the head image are zero
+    out = np.zeros((H, W), np.float32)
+    for o in range(H):                                                         # logits[o] = Dh[o-1][0] + Dh[o][1] + Dh[o+1][2]
+        for dyp in range(3):
+            q = o - 1 + dyp
+            if 0 <= q < H:
+                out[o] += Dh[q, :, dyp]
+    np.testing.assert_allclose(out, ref_o.numpy(), rtol=1e-5, atol=1e-5)
+    assert ops._tail_tc_weights(wb, wh) is pack                                # cached per parameter version
+    wh.data.mul_(2.0)
+    wh._version                                                                 # (in-place edits bump the version)
+    wh.mul_(1.0)
+    assert ops._tail_tc_weights(wb, wh) is not pack
