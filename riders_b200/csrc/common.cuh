@@ -13,7 +13,7 @@ int  check_launch(const char* what);          // cudaGetLastError -> RIDERS_* co
 int  sm_count();
 void set_reduce_rows(int rows);
 void set_reduce_tile_w(int w);               // confidence_reduce.cu: 16 (default) or 32 pixel wide tiles              // confidence_reduce.cu tuning knob (4 or 8 rows per thread)
-void set_lsq_mode(int mode);                 // lsq_align.cu: 1 = one cooperative launch (default), 0 = two kernels
+void set_lsq_mode(int mode);                 // lsq_align.cu: 2 = PDL (default), 3 = one launch + flag barrier, 1 = cooperative, 0 = two kernels
 void set_gather_smem_budget(int kb);         // roi_gather.cu tuning knob (riders_debug_set)
 void set_tail_tc_dbg(int v);                 // decoder_tail_tc.cu timing experiments
 void count_launches(int n);                   // feeds riders_launch_count() (bench.py's gpu_launches)

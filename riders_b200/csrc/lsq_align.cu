@@ -11,7 +11,9 @@
 //   sums / scale / shift.
 //
 // Default: pass 2 is a programmatic dependent launch (lsq_apply_pdl_kernel) that loads its `pred` pixels while pass 1 still
-//   runs.  Also kept: lsq_fused_kernel, both passes in ONE cooperative grid with a grid-wide barrier (measured SLOWER at
+//   runs.  Also kept (mode 3): lsq_single_kernel - ONE ordinary launch with a per-frame flag barrier between the passes;
+//   measured SLOWER than the PDL pair (26.6 vs 21.5 us at 16 frames, 80 vs 54 us at 64: the waiting CTAs hold the SM slots the
+//   not-yet-started CTAs of later frames need, profiles/r02_microbench_frontend.jsonl).  Also kept: lsq_fused_kernel, both passes in ONE cooperative grid with a grid-wide barrier (measured SLOWER at
 //   1 and 16 frames: the cooperative launch itself costs more than the second launch it saves - profiles/r02_microbench_*),
 //   and the two plain launches.  All three use the same slices and summation order: bit-identical results.
 //
@@ -20,6 +22,7 @@
 // valid pixel; pass 2 reads pred once (4 B) and writes the output (4 B).
 #include "common.cuh"
 #include <cooperative_groups.h>
+#include <atomic>
 
 namespace riders {
 
@@ -101,8 +104,10 @@ __device__ __forceinline__ void partial_slice(const float* __restrict__ pred, co
         }
     }
     block_reduce5(s, sm);
-    if (threadIdx.x < 5)
+    if (threadIdx.x < 5) {
         partial[((size_t)frame * ctas_per_frame + cta) * 5 + threadIdx.x] = sm[0][threadIdx.x];
+        __threadfence();                               // device-visible before anything this CTA signals after the barrier below
+    }
     __syncthreads();                                   // sm is reused by the next slice of a persistent CTA
 }
 
@@ -264,6 +269,94 @@ lsq_apply_pdl_kernel(const float* __restrict__ pred, const double* partial,
     for (int it = PDL_PREFETCH; it < PX_PER_THREAD / 4; ++it) store4(it, w[it - PDL_PREFETCH]);
 }
 
+// Both passes in ONE ordinary launch (mode 3): the grid of pass 1, a per-frame flag barrier, then solve + apply.  A frame's CTAs
+// only wait for the CTAs of the SAME frame: every CTA publishes its partial sums followed by a flag word carrying this call's
+// nonce (st.release; the workspace needs no zeroing - stale memory cannot hold the nonce), polls the flags of its frame
+// (ld.acquire), and goes on.  No second launch, no programmatic dependency, no cooperative-launch cost (but see the
+// measurement in the file header: it loses to the PDL pair); `pred` is prefetched
+// before the wait like the PDL form does.  Deadlock-free as long as one frame's CTAs fit the device together (the host
+// checks; CTAs are dispatched frame by frame, earlier frames never wait for later ones).  Same slices, thread -> pixel
+// assignment and summation order as the other forms: bit-identical results.
+__global__ void __launch_bounds__(LSQ_THREADS, 5)
+lsq_single_kernel(const float* __restrict__ pred, const float* __restrict__ target, const uint8_t* __restrict__ mask,
+                  int npx, int ctas_per_frame, double* partial, unsigned long long* flags, unsigned long long nonce,
+                  double* __restrict__ sums, double* __restrict__ scale_shift,
+                  float* __restrict__ out, float clamp_hi, float clamp_lo, int clamp_flags) {
+    __shared__ double sm[LSQ_THREADS / 32][5];
+    __shared__ double sm5[5];
+    __shared__ double sm_ss[2];
+    const int frame = blockIdx.y, cta = blockIdx.x;
+    const size_t fo = (size_t)frame * npx;
+    const float* p = pred + fo;
+    float* o = out ? out + fo : nullptr;
+    const int begin = cta * PX_PER_CTA;
+    const int end = min(begin + PX_PER_CTA, npx);
+    const bool vec_ok = out && ((npx & 3) == 0) && ((((uintptr_t)p) & 15) == 0) && ((((uintptr_t)o) & 15) == 0);
+    auto load4 = [&](int it) {
+        const int i = begin + (it * LSQ_THREADS + threadIdx.x) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vec_ok) { if (i < end) v = *reinterpret_cast<const float4*>(p + i); }
+        else {
+            if (i < end) v.x = p[i];
+            if (i + 1 < end) v.y = p[i + 1];
+            if (i + 2 < end) v.z = p[i + 2];
+            if (i + 3 < end) v.w = p[i + 3];
+        }
+        return v;
+    };
+    float4 v[PDL_PREFETCH];
+    if (out) {
+#pragma unroll
+        for (int it = 0; it < PDL_PREFETCH; ++it) v[it] = load4(it);
+    }
+    partial_slice(pred, target, mask, npx, ctas_per_frame, partial, frame, cta, sm);
+    unsigned long long* fl = flags + (size_t)frame * ctas_per_frame;
+    if (threadIdx.x == 0) {
+        __threadfence();                                           // the five partial sums (written by threads 0..4) before the flag
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(fl + cta), "l"(nonce) : "memory");
+    }
+    if (!out && cta != 0) return;                                  // sums / scale only: one CTA per frame finishes the job
+    for (int c = threadIdx.x; c < ctas_per_frame; c += LSQ_THREADS) {
+        unsigned long long f;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(fl + c) : "memory");
+        } while (f != nonce);
+    }
+    __syncthreads();
+    solve_frame(partial + (size_t)frame * ctas_per_frame * 5, ctas_per_frame, sm5, sm_ss);
+    if (cta == 0) {
+        if (sums && threadIdx.x < 5) sums[frame * 5 + threadIdx.x] = sm5[threadIdx.x];
+        if (scale_shift && threadIdx.x < 2) scale_shift[frame * 2 + threadIdx.x] = sm_ss[threadIdx.x];
+    }
+    if (!out) return;
+    const float sc = (float)sm_ss[0], sh = (float)sm_ss[1];
+    const bool hi_on = clamp_flags & 1, lo_on = clamp_flags & 2;
+    auto f = [&](float x) {
+        float r = __fadd_rn(__fmul_rn(x, sc), sh);
+        if (hi_on && r > clamp_hi) r = clamp_hi;
+        if (lo_on && r < clamp_lo) r = clamp_lo;
+        return r;
+    };
+    auto store4 = [&](int it, float4 x) {
+        const int i = begin + (it * LSQ_THREADS + threadIdx.x) * 4;
+        if (vec_ok) {
+            if (i < end) *reinterpret_cast<float4*>(o + i) = make_float4(f(x.x), f(x.y), f(x.z), f(x.w));
+        } else {
+            if (i < end) o[i] = f(x.x);
+            if (i + 1 < end) o[i + 1] = f(x.y);
+            if (i + 2 < end) o[i + 2] = f(x.z);
+            if (i + 3 < end) o[i + 3] = f(x.w);
+        }
+    };
+    float4 w[PX_PER_THREAD / 4 - PDL_PREFETCH];
+#pragma unroll
+    for (int it = PDL_PREFETCH; it < PX_PER_THREAD / 4; ++it) w[it - PDL_PREFETCH] = load4(it);    // the rest streams while the first part is written
+#pragma unroll
+    for (int it = 0; it < PDL_PREFETCH; ++it) store4(it, v[it]);
+#pragma unroll
+    for (int it = PDL_PREFETCH; it < PX_PER_THREAD / 4; ++it) store4(it, w[it - PDL_PREFETCH]);
+}
+
 // Both passes in one cooperative launch: every CTA walks the (frame, slice) items with the grid stride, the grid barrier
 // separates "all partials written" from "solve + apply".  Slices, thread -> pixel assignment and summation order are those
 // of the two kernels above, so the outputs are bit-identical to theirs on any grid size.
@@ -296,6 +389,7 @@ lsq_fused_kernel(const float* __restrict__ pred, const float* __restrict__ targe
 }
 
 static int g_lsq_mode = 2;                             // 2: two kernels, the second a programmatic dependent launch (default);
+                                                       // 3: ONE ordinary launch with a per-frame flag barrier (measured slower);
                                                        // 1: one cooperative launch; 0: two plain kernels
 void set_lsq_mode(int m) { g_lsq_mode = m; }
 
@@ -304,7 +398,7 @@ void set_lsq_mode(int m) { g_lsq_mode = m; }
 extern "C" size_t riders_lsq_workspace_bytes(int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
     const size_t ctas = (size_t)riders::ceil_div(H * W, riders::PX_PER_CTA);
-    return (size_t)B * ctas * 5 * sizeof(double);
+    return (size_t)B * ctas * (5 * sizeof(double) + sizeof(unsigned long long));        // partial sums + the flag words of mode 3
 }
 
 extern "C" int riders_lsq_align(const float* pred, const float* target, const uint8_t* mask,
@@ -352,10 +446,37 @@ extern "C" int riders_lsq_align(const float* pred, const float* target, const ui
         }
     }
     dim3 grid(ctas, B);
+    if (g_lsq_mode == 3) {
+        // one frame's CTAs must be able to be resident together (they wait for each other): cached per device
+        static int capacity[64] = {0};
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+        if (!capacity[dev]) {
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lsq_single_kernel, LSQ_THREADS, 0) == cudaSuccess && per_sm > 0)
+                capacity[dev] = per_sm * sm_count();
+            else
+                capacity[dev] = -1;
+            cudaGetLastError();
+        }
+        // a captured graph would replay the same nonce on the same workspace: capture takes the two-kernel form
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cap);
+        if (capacity[dev] > 0 && ctas <= capacity[dev] / 4 && cap == cudaStreamCaptureStatusNone) {
+            static std::atomic<unsigned long long> nonce{0x9E3779B97F4A7C15ull ^ (unsigned long long)(uintptr_t)&capacity};
+            const unsigned long long my = nonce.fetch_add(0x9E3779B97F4A7C15ull, std::memory_order_relaxed) | 1ull;
+            double* part = (double*)workspace;
+            unsigned long long* flags = (unsigned long long*)(part + (size_t)B * ctas * 5);
+            count_launches(1);
+            lsq_single_kernel<<<grid, LSQ_THREADS, 0, st>>>(pred, target, mask, npx, ctas, part, flags, my, sums, scale_shift, out,
+                                                            clamp_hi, clamp_lo, clamp_flags);
+            return check_launch("lsq_align (single launch)");
+        }
+    }
     count_launches(2);
     lsq_partial_kernel<<<grid, LSQ_THREADS, 0, st>>>(pred, target, mask, npx, ctas, (double*)workspace);
     dim3 grid2(out ? ctas : 1, B);
-    if (g_lsq_mode == 2) {
+    if (g_lsq_mode >= 2) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid2; cfg.blockDim = dim3(LSQ_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
         cudaLaunchAttribute attr[1];

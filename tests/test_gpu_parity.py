@@ -379,26 +379,32 @@ def test_interpolator_class_and_qhull_errors(golden):
 
 
 def test_lsq_launch_forms_are_bit_identical():
-    """riders_lsq_align has three launch forms - two plain kernels, one cooperative launch (partials -> grid barrier ->
-    solve + apply), and the default: pass 2 as a programmatic dependent launch that prefetches `pred` under pass 1.  Same
-    slices and summation order: bit-identical outputs."""
+    """riders_lsq_align has four launch forms - two plain kernels, one cooperative launch (partials -> grid barrier ->
+    solve + apply), ONE ordinary launch with a per-frame flag barrier (nonce-tagged flags, no zeroed scratch), and the
+    default: pass 2 as a programmatic dependent launch that prefetches `pred` under pass 1.  Same slices and summation
+    order: bit-identical outputs."""
     B, Hh, Ww = 5, 512, 640
     ins = [synth.alignment_inputs(20 + b, 300 + 40 * b, Hh, Ww) for b in range(B)]
     p, t, m = (cu(np.stack([x[i] for x in ins])) for i in range(3))
     hi, lo = 10.0, float(np.float32(1 / 255.0))
     res, launches = {}, {}
     try:
-        for mode in (0, 1, 2):
+        for mode in (0, 1, 2, 3):
             ops.debug_set("lsq_fused", mode)
             n0 = ops.launch_count()
             res[mode] = ops.lsq_align(p, t, m, clamp_hi=hi, clamp_lo=lo)
             launches[mode] = ops.launch_count() - n0
             res[(mode, "noout")] = ops.lsq_align(p, t, m, want_out=False)[1]
             res[(mode, "odd")] = ops.lsq_align(p[:, 1:, 3:], t[:, 1:, 3:], m[:, 1:, 3:], clamp_hi=hi, clamp_lo=lo)    # unaligned
+            if mode == 3:                                                  # same workspace pattern twice in a row: the nonce changes
+                again = ops.lsq_align(p * 1.5, t, m, clamp_hi=hi, clamp_lo=lo)
+                ops.debug_set("lsq_fused", 0)
+                for a, b in zip(again, ops.lsq_align(p * 1.5, t, m, clamp_hi=hi, clamp_lo=lo)):
+                    assert torch.equal(a, b)
     finally:
         ops.debug_set("lsq_fused", 2)
-    assert launches == {0: 2, 1: 1, 2: 2}
-    for mode in (1, 2):
+    assert launches == {0: 2, 1: 1, 2: 2, 3: 1}
+    for mode in (1, 2, 3):
         for a, b in zip(res[mode], res[0]):
             assert torch.equal(a, b)
         assert torch.equal(res[(mode, "noout")], res[0][1])

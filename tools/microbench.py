@@ -261,7 +261,7 @@ def bench_frontend(H=512, W=640, K=512):
         t = torch.from_numpy(np.stack([d[1] for d in data])).to(DEV).repeat(rep, 1, 1)[:B].contiguous()
         m = torch.from_numpy(np.stack([d[2] for d in data])).to(DEV).repeat(rep, 1, 1)[:B].contiguous()
         nb = B * H * W * 13
-        for mode, name in ((0, "two_kernels"), (1, "cooperative_one_launch"), (2, "pdl")):
+        for mode, name in ((0, "two_kernels"), (1, "cooperative_one_launch"), (2, "pdl"), (3, "single_launch_flag_barrier")):
             ops.debug_set("lsq_fused", mode)
             ms, best = timeit(lambda: ops.lsq_align(p, t, m, 10.0, 1 / 255.0), iters=20)
             report("lsq_align_" + name, ms, best, nb, B=B)
