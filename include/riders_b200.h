@@ -373,6 +373,16 @@ int riders_subpixel_conv_tc_half_nhwc(const float* x, const float* w_pack, int N
                                       float slope, void* yh, int* status, void* stream);
 int riders_decoder_tail_tc_half_nhwc(const void* yh, int N, int h, int w, const void* w_pack, const float* bias_b_host,
                                      float slope, int apply_sigmoid, float* out, int* status, void* stream);
+/* The whole up-convolution of the last decoder block from the RAW output of the convolution in front of it (csrc/upconv_tc.cu):
+ *   yh = fp16(act(depth_to_space(conv2x2(act_p(x + bias_p), W2, padding 1)) + bias_a)),   x (N, 32, h, w <= 54) channels-last fp32,
+ * act_p = LeakyReLU(slope_p) (slope_p = 1 and bias_p_host = NULL: x is already activated), yh in the layout of
+ * riders_subpixel_conv_tc_half_nhwc.  tcgen05.mma kind::f16, operands staged once (global -> registers -> fp16 planes), the four
+ * taps are shifted views of the staged rows.  w_pack: DEVICE, 16 KB of fp16: for tap t = 2u + v and K half kh the K-major
+ * unswizzled image [t][kh][n / 8][k / 8][n % 8][k % 8] of W2[n][16 kh + k][u][v] (ops._upconv_tc_weights).  bias_p_host (32),
+ * bias_a_host (16): HOST memory or NULL.  status as for riders_decoder_tail_tc_nhwc.                                          */
+int riders_upconv_tc_half_nhwc(const float* x, const float* bias_p_host, float slope_p, const void* w_pack,
+                               int N, int h, int w, const float* bias_a_host, float slope, void* yh,
+                               int* status, void* stream);
 /* Sub-pixel phase convolution of the last decoder block in its 2x2-tap form (32 -> 4 x 16 channels), TF32, with the bias
  * + LeakyReLU of the convolution that produced x fused into the operand load (deconv1.conv -> deconv0.deconv of
  * MultiScaleDecoder, RCNet/networks.py:678-779): y4 (N, 64, h+1, w+1) = conv2x2(act(x + bias), W2, padding 1), x (N, 32, h, w)

@@ -1,0 +1,287 @@
+// The last decoder block's up-convolution in ONE kernel, from the RAW output of the convolution in front of it to the fp16
+// operand map of the tcgen05 decoder tail (MultiScaleDecoder deconv1.conv -> deconv0.deconv, RCNet/networks.py:678-779,
+// utils/net_utils.py:474-569; phase algebra in upsample.cu):
+//
+//     xa = LeakyReLU(x + bias_p)                       the previous convolution's bias + activation (x: its raw output, 32 ch)
+//     y4 = conv2x2(xa, W2, padding 1)                  sub-pixel form of resize x2 + 3x3 convolution: 4 phases x 16 channels
+//     y  = LeakyReLU(depth_to_space(y4) + bias_a)      -> fp16, written as yh [N][2h][2 planes][2w][8]
+//
+// It replaces three passes of the library flow (bias_act over the 32-channel map: 1.6 GB read + 1.6 GB written per 2048 points;
+// the phase convolution; the depth-to-space / bias / activation pass) and improves on riders_subpixel_conv_tc_half_nhwc, whose
+// TMA-fed TF32 MMAs read the activated fp32 map: that kernel loads every input row four times (one shifted copy per tap) and is
+// bound by the shared-memory pipe.  Here the rows go global -> registers (+ bias, LeakyReLU, fp16) -> shared memory ONCE, in the
+// unswizzled K-major plane layout of decoder_tail_tc.cu: pixel p of a staged row at byte 16 p of each 8-channel plane, rows 56
+// pixels apart.  An unswizzled operand descriptor may start at any 16-byte boundary, so all four taps are shifted views of the
+// same staged rows: tap (u, v) of the y4 row pair (I, I + 1) is the M = 128 operand starting at row I - 1 + u, pixel v
+// (positions 0..55 of the pair's first row, 56..111 of its second).  Per pair: 8 tcgen05.mma kind::f16 (4 taps x 2 halves of the
+// 32 input channels, M 128, N 64, K 16) into one of four 64-column TMEM accumulators; two groups of four warps finish the pairs
+// alternately (TMEM -> depth-to-space, + bias_a, LeakyReLU, fp16 -> staging -> one bulk store per finished output row).
+//
+// A CTA streams down one radar point's map in batches of 8 y4 rows (9 input rows, double-buffered); persistent over the points.
+// fp16 operands (11-bit significand, like the TF32 of the flow this replaces), fp32 accumulation; every staged / written value
+// passes a running |max| and a value outside the fp16 range raises `status` (the host then answers from the TF32 library flow).
+#include "common.cuh"
+#include "tcgen05.cuh"
+#include <cuda_fp16.h>
+
+namespace riders {
+namespace upconv {
+using namespace tcg;
+
+constexpr int CIN = 32, NOUT = 64;
+constexpr int PITCH = 56;                             // positions per staged input row: 1 + w + 1 <= 56
+constexpr int BROWS = 8, XROWS = BROWS + 1;           // y4 rows / input rows per batch
+constexpr int PLANE_POS = 528;                        // positions per plane: 9 x 56 + the reach of the last M = 128 view (7 * 56 + 1 + 127)
+constexpr int PLANE = PLANE_POS * 16;                 // 8448 B (a multiple of 128)
+constexpr int BATCH_BYTES = 4 * PLANE;                // four planes of 8 channels
+constexpr int NBUF = 2, NACC = 4;
+constexpr int W_BYTES = 8 * NOUT * 32;                // 4 taps x 2 K halves x (64 rows x 16 fp16) = 16 KB
+constexpr int STAGE_BYTES = 4 * 2 * 110 * 16;         // epilogue staging: 4 output rows x 2 planes x W <= 110 pixels x 16 B
+constexpr int LOADER_WARPS = 8, W_MMA = 8, W_EPI = 12, EPI_GROUPS = 2, THREADS = (W_EPI + 4 * EPI_GROUPS) * 32;   // warps 9..11 idle
+constexpr int B_BFULL = 0, B_BFREE = B_BFULL + NBUF, B_DFULL = B_BFREE + NBUF, B_DFREE = B_DFULL + NACC, NBARS = B_DFREE + NACC;
+constexpr int SMEM_BYTES = NBUF * BATCH_BYTES + W_BYTES + EPI_GROUPS * STAGE_BYTES + NBARS * 8 + 16;
+constexpr uint32_t TMEM_COLS = NACC * NOUT;           // 256
+
+struct Params {
+    const float4* x;          // (N, h, w, 32) fp32, raw output of the previous convolution
+    const uint4* w_pack;
+    __half* yh;               // [N][2h][2][2w][8]
+    int* status;
+    float bias_p[CIN];        // the previous convolution's bias (zeros if none)
+    float slope_p;            // its LeakyReLU slope (1 = identity: x is already activated)
+    float bias_a[16];
+    float slope;
+    int N, h, w;
+};
+
+__device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<const uint32_t*>(&v); }
+
+__global__ void __launch_bounds__(THREADS, 1)
+upconv_tc_kernel(const __grid_constant__ Params P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* xb = smem;                                   // [NBUF][4 planes][PLANE_POS] x 16 B
+    uint8_t* ws = xb + NBUF * BATCH_BYTES;                // packed W2
+    uint8_t* stg = ws + W_BYTES;                          // [EPI_GROUPS][4 rows][2 planes][W] x 16 B
+    const uint32_t bars = smem_u32(stg + EPI_GROUPS * STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg + EPI_GROUPS * STAGE_BYTES + NBARS * 8);
+    auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int h = P.h, w = P.w, H = 2 * h, W = 2 * w;
+    const int nbatch = (h + 1 + BROWS - 1) / BROWS;       // y4 has h + 1 rows
+
+    for (int i = tid; i < NBUF * BATCH_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(xb)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < W_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(ws)[i] = __ldg(P.w_pack + i);
+    if (tid == 0) {
+        for (int i = 0; i < NBUF; ++i) { mbar_init(bar(B_BFULL + i), LOADER_WARPS); mbar_init(bar(B_BFREE + i), 1); }
+        for (int i = 0; i < NACC; ++i) { mbar_init(bar(B_DFULL + i), 1); mbar_init(bar(B_DFREE + i), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    __half2 amax2 = __float2half2_rn(0.f);
+
+    if (warp < LOADER_WARPS) {
+        // ===================== input rows: global -> + bias_p, LeakyReLU -> fp16 -> plane layout =====================
+        // thread = (pixel, 8-channel chunk): a warp reads 8 pixels x 128 B (contiguous) and stores 8 pixels x 4 planes
+        const int px = tid >> 2, ch = tid & 3;
+        const bool active = px < w;
+        float bp[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bp[e] = P.bias_p[ch * 8 + e];
+        const float sp = P.slope_p;
+        uint32_t nb = 0;                                   // batches staged so far (ring position)
+        for (int n = blockIdx.x; n < P.N; n += gridDim.x) {
+            const float4* xn = P.x + ((size_t)n * h * w + px) * 8 + ch * 2;
+            for (int bi = 0; bi < nbatch; ++bi, ++nb) {
+                const int buf = nb % NBUF;
+                const int i0 = bi * BROWS - 1;             // first input row of the batch (row -1 = the padding)
+                if (lane == 0 && warp == 0) {              // L2 prefetch of the next batch's rows (contiguous in memory)
+                    const int r0 = max(i0 + BROWS, 0), r1 = min(i0 + BROWS + XROWS, h);
+                    if (bi + 1 < nbatch && r1 > r0)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+                                     ::"l"(P.x + ((size_t)n * h + r0) * w * 8), "r"((r1 - r0) * w * 128) : "memory");
+                }
+                mbar_wait_sleep(bar(B_BFREE + buf), ((nb / NBUF) & 1) ^ 1, 100);
+                uint8_t* dst = xb + buf * BATCH_BYTES + ch * PLANE + (1 + px) * 16;
+                // three rows in flight
+                float4 v[3][2];
+                auto load = [&](int r, float4 (&t)[2]) {
+                    const int row = i0 + r;
+                    if (active && (unsigned)row < (unsigned)h) {
+                        const float4* g = xn + (size_t)row * w * 8;
+                        t[0] = __ldcs(g); t[1] = __ldcs(g + 1);
+                    } else {
+                        t[0] = make_float4(0.f, 0.f, 0.f, 0.f); t[1] = t[0];
+                    }
+                };
+                auto stage = [&](int r, const float4 (&t)[2]) {
+                    const bool ok = active && (unsigned)(i0 + r) < (unsigned)h;
+                    const float a[8] = {t[0].x, t[0].y, t[0].z, t[0].w, t[1].x, t[1].y, t[1].z, t[1].w};
+                    uint32_t hv[4];
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        float v0 = a[e] + bp[e], v1 = a[e + 1] + bp[e + 1];
+                        v0 = fmaxf(v0, v0 * sp); v1 = fmaxf(v1, v1 * sp);
+                        const __half2 hh = __floats2half2_rn(v0, v1);
+                        hv[e >> 1] = ok ? h2_bits(hh) : 0u;               // zero rows / columns: the convolution pads the ACTIVATED map
+                        if (ok) amax2 = __hmax2_nan(amax2, __habs2(hh));
+                    }
+                    if (active) *reinterpret_cast<uint4*>(dst + r * PITCH * 16) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+                };
+                load(0, v[0]); load(1, v[1]);
+#pragma unroll
+                for (int r = 0; r < XROWS; ++r) {
+                    if (r + 2 < XROWS) load(r + 2, v[(r + 2) % 3]);
+                    stage(r, v[r % 3]);
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(B_BFULL + buf));
+            }
+        }
+    } else if (warp == W_MMA) {
+        // ===================== MMA issuer =====================
+        const uint32_t xa = smem_u32(xb), wa = smem_u32(ws);
+        constexpr uint32_t IDESC = idesc_f16(NOUT);
+        const uint64_t bd0 = smem_desc_nosw(wa, 128, 256);
+        uint32_t nb = 0, np = 0;                           // batches / pairs issued so far
+        for (int n = blockIdx.x; n < P.N; n += gridDim.x) {
+            for (int bi = 0; bi < nbatch; ++bi, ++nb) {
+                const int buf = nb % NBUF;
+                mbar_wait(bar(B_BFULL + buf), (nb / NBUF) & 1);
+                const uint64_t ad0 = smem_desc_nosw(xa + buf * BATCH_BYTES, PLANE, 128);
+                const int npairs = min(BROWS / 2, (h + 1 - bi * BROWS + 1) / 2);
+                for (int k = 0; k < npairs; ++k, ++np) {
+                    const int acc = np % NACC;
+                    mbar_wait(bar(B_DFREE + acc), ((np / NACC) & 1) ^ 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const int u = t >> 1, v = t & 1;
+#pragma unroll
+                            for (int kh = 0; kh < 2; ++kh)
+                                umma_f16(tmem + acc * NOUT,
+                                         ad0 + (uint64_t)(kh * 2 * (PLANE / 16) + (2 * k + u) * PITCH + v),
+                                         bd0 + (uint64_t)((t * 2 + kh) * (NOUT * 32 / 16)), IDESC, (t | kh) ? 1u : 0u);
+                        }
+                        umma_commit(bar(B_DFULL + acc));
+                        if (k == npairs - 1) umma_commit(bar(B_BFREE + buf));
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp >= W_EPI) {
+        // ===================== finish: TMEM -> depth-to-space + bias_a + LeakyReLU -> fp16 -> staging -> bulk stores =====
+        const int quad = warp & 3, grp = (warp - W_EPI) >> 2;
+        const int row = quad * 32 + lane;                          // TMEM lane = position in the pair
+        const int r2 = row >= PITCH ? 1 : 0, J = row - r2 * PITCH; // y4 row of the pair, y4 column
+        const int leader = (W_EPI + 4 * grp) * 32;
+        const uint32_t ROWB = (uint32_t)W * 32;                    // bytes of one output row (2 planes x W x 16 B)
+        uint8_t* stage = stg + grp * STAGE_BYTES;
+        const float slope = P.slope;
+        uint32_t np = 0;
+        for (int n = blockIdx.x; n < P.N; n += gridDim.x) {
+            for (int bi = 0; bi < nbatch; ++bi) {
+                const int npairs = min(BROWS / 2, (h + 1 - bi * BROWS + 1) / 2);
+                for (int k = 0; k < npairs; ++k, ++np) {
+                    if ((int)(np % EPI_GROUPS) != grp) continue;
+                    const int acc = np % NACC;
+                    const int p = bi * BROWS + 2 * k;              // first y4 row of the pair
+                    mbar_wait_sleep(bar(B_DFULL + acc), (np / NACC) & 1, 100);
+                    tc_fence_after();
+                    uint32_t r0[32], r1[32];
+                    const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc * NOUT;
+                    TMEM_LD32(taddr, r0);
+                    TMEM_LD32(taddr + 32, r1);
+                    tmem_wait_ld();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(B_DFREE + acc));
+                    if (tid == leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the stores that read this buffer are done
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                    // phase (a, b) of y4 position (I, J) is output pixel (2 I - a, 2 J - b); local output row lr = Y - (2 p - 1)
+                    const int I = p + r2;
+                    if (row < 2 * PITCH && I <= h && J <= w) {
+#pragma unroll
+                        for (int ab = 0; ab < 4; ++ab) {
+                            const int a = ab >> 1, b = ab & 1;
+                            const int Y = 2 * I - a, X = 2 * J - b;
+                            if ((unsigned)Y < (unsigned)H && (unsigned)X < (unsigned)W) {
+                                const uint32_t* v = ab < 2 ? r0 + 16 * ab : r1 + 16 * (ab - 2);
+                                uint32_t hv[8];
+#pragma unroll
+                                for (int c = 0; c < 16; c += 2) {
+                                    float v0 = __uint_as_float(v[c]) + P.bias_a[c], v1 = __uint_as_float(v[c + 1]) + P.bias_a[c + 1];
+                                    v0 = fmaxf(v0, v0 * slope); v1 = fmaxf(v1, v1 * slope);
+                                    const __half2 hh = __floats2half2_rn(v0, v1);
+                                    amax2 = __hmax2_nan(amax2, __habs2(hh));
+                                    hv[c >> 1] = h2_bits(hh);
+                                }
+                                uint8_t* d = stage + (uint32_t)(2 * r2 - a + 1) * ROWB + (uint32_t)X * 16;
+                                *reinterpret_cast<uint4*>(d) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+                                *reinterpret_cast<uint4*>(d + (uint32_t)W * 16) = make_uint4(hv[4], hv[5], hv[6], hv[7]);
+                            }
+                        }
+                    }
+                    fence_async_smem();
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                    if (tid == leader) {
+                        for (int lr = 0; lr < 4; ++lr) {
+                            const int Y = 2 * p - 1 + lr;
+                            if ((unsigned)Y >= (unsigned)H) continue;
+                            __half* gdst = P.yh + ((size_t)n * H + Y) * (size_t)W * 16;
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                         ::"l"(gdst), "r"(smem_u32(stage + lr * ROWB)), "r"(ROWB) : "memory");
+                        }
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            }
+        }
+        if (tid == leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    {
+        const float2 m = __half22float2(amax2);
+        if (P.status && !(fmaxf(m.x, m.y) <= 65504.f)) atomicOr(P.status, 1);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_MMA) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+}  // namespace upconv
+}  // namespace riders
+
+extern "C" int riders_upconv_tc_half_nhwc(const float* x, const float* bias_p_host, float slope_p, const void* w_pack,
+                                          int N, int h, int w, const float* bias_a_host, float slope, void* yh,
+                                          int* status, void* stream) {
+    using namespace riders;
+    RIDERS_REQUIRE(N >= 0 && h > 0 && w > 0, "upconv_tc: bad shape");
+    RIDERS_REQUIRE(w + 2 <= upconv::PITCH, "upconv_tc: at most %d columns (got w = %d)", upconv::PITCH - 2, w);
+    RIDERS_REQUIRE(slope >= 0.f && slope <= 1.f && slope_p >= 0.f && slope_p <= 1.f, "upconv_tc: LeakyReLU slopes must be in [0, 1]");
+    if (N == 0) return RIDERS_OK;
+    RIDERS_REQUIRE(x && w_pack && yh, "upconv_tc: null pointer");
+    RIDERS_REQUIRE(((((uintptr_t)x) | ((uintptr_t)w_pack) | ((uintptr_t)yh)) & 15) == 0, "upconv_tc: 16-byte alignment");
+    upconv::Params P;
+    P.x = reinterpret_cast<const float4*>(x);
+    P.w_pack = reinterpret_cast<const uint4*>(w_pack);
+    P.yh = reinterpret_cast<__half*>(yh);
+    P.status = status;
+    for (int c = 0; c < upconv::CIN; ++c) P.bias_p[c] = bias_p_host ? bias_p_host[c] : 0.f;
+    P.slope_p = slope_p;
+    for (int c = 0; c < 16; ++c) P.bias_a[c] = bias_a_host ? bias_a_host[c] : 0.f;
+    P.slope = slope;
+    P.N = N; P.h = h; P.w = w;
+    static size_t configured[64] = {0};
+    if (int rc_smem = ensure_dynamic_smem(upconv::upconv_tc_kernel, (size_t)(upconv::SMEM_BYTES), configured, "upconv_tc: shared memory attribute")) return rc_smem;
+    const int grid = N < sm_count() ? N : sm_count();
+    count_launches(1);
+    upconv::upconv_tc_kernel<<<grid, upconv::THREADS, upconv::SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    return check_launch("upconv_tc_half_nhwc");
+}

@@ -610,6 +610,43 @@ def subpixel_conv_tc_half(x, w2, bias, slope=0.2, flag=None):
     return yh, flag
 
 
+def _upconv_tc_weights(w2):
+    """(64,32,2,2) 2x2-tap phase kernels -> the 16 KB fp16 B-operand image of riders_upconv_tc_half_nhwc: for tap t = 2u + v and
+    K half kh a K-major unswizzled 64 x 16 matrix [n // 8][k // 8][n % 8][k % 8] of W2[n][16 kh + k][u][v]; cached per version."""
+    def make():
+        dev = w2.device
+        t = torch.arange(4, device=dev).view(4, 1, 1, 1, 1, 1)
+        kh = torch.arange(2, device=dev).view(1, 2, 1, 1, 1, 1)
+        ng = torch.arange(8, device=dev).view(1, 1, 8, 1, 1, 1)
+        kc = torch.arange(2, device=dev).view(1, 1, 1, 2, 1, 1)
+        nr = torch.arange(8, device=dev).view(1, 1, 1, 1, 8, 1)
+        ke = torch.arange(8, device=dev).view(1, 1, 1, 1, 1, 8)
+        return w2.detach().float()[ng * 8 + nr, kh * 16 + kc * 8 + ke, t // 2, t % 2].reshape(-1).to(torch.float16).contiguous()
+    return _cached(_UPCONV_CACHE, w2, make)          # (its own cache: _FRAG_CACHE holds the mma.sync fragments of the same w2)
+
+
+_UPCONV_CACHE = {}
+
+
+def upconv_tc_half(x, bias_p, slope_p, w2, bias_a, slope=0.2, flag=None):
+    """The last block's up-convolution from the RAW output ``x`` (N,32,h,w<=54, channels_last) of the convolution in front of it:
+    act_p(x + bias_p) -> tcgen05 phase convolution -> depth-to-space + bias_a + LeakyReLU -> fp16 operand map (N,2h,2,2w,8).
+    ``bias_p=None, slope_p=1``: x is already activated.  Returns (yh, flag)."""
+    _need_cuda(x, w2)
+    N, Cc, h, w = x.shape
+    if not (_is_channels_last(x) and x.dtype == torch.float32 and Cc == 32 and tuple(w2.shape) == (64, 32, 2, 2) and w <= 54):
+        raise _lib.RidersError("upconv_tc_half: needs a channels_last float32 (N,32,h,w<=54) map and (64,32,2,2) kernels")
+    yh = torch.empty((N, 2 * h, 2, 2 * w, 8), device=x.device, dtype=torch.float16)
+    if flag is None:
+        flag = torch.zeros(1, dtype=torch.int32, device=x.device)
+    # algorithmic bytes: the 32-channel map in, the fp16 map out
+    with _span("upconv", x.numel() * 4 + yh.numel() * 2):
+        rc = _lib.lib().riders_upconv_tc_half_nhwc(_ptr(x), _ptr(_host_floats(bias_p)), float(slope_p), _ptr(_upconv_tc_weights(w2)),
+                                                   N, h, w, _ptr(_host_floats(bias_a)), float(slope), _ptr(yh), _ptr(flag), _stream())
+    _lib.check(rc, "riders_upconv_tc_half_nhwc")
+    return yh, flag
+
+
 def decoder_tail_tc_half(yh, weight_b, bias_b, weight_head, slope=0.2, sigmoid=False, flag=None):
     """The tcgen05 decoder tail on the fp16 operand map of ``subpixel_conv_tc_half``: logits (N,1,2h,2w), flag."""
     _need_cuda(yh, weight_b)
@@ -629,15 +666,25 @@ def decoder_tail_tc_half(yh, weight_b, bias_b, weight_head, slope=0.2, sigmoid=F
     return out, flag
 
 
-def decoder_upconv_tail_tc(x, w2, bias_a, weight_b, bias_b, weight_head, slope=0.2, sigmoid=False, defer=False):
-    """Last decoder block + head from the 32-channel map ``x`` (N,32,h,w) on: ``subpixel_conv_tc_half`` -> ``decoder_tail_tc_half``
-    (both tcgen05 / TMEM, fp16 map between them).  One fp16-range flag for both; when raised the result comes from the TF32
-    flow (cuDNN phase convolution + mma.sync tail) - immediately, or at the caller's sync point with ``defer=True``."""
-    yh, flag = subpixel_conv_tc_half(x, w2, bias_a, slope)
+def decoder_upconv_tail_tc(x, w2, bias_a, weight_b, bias_b, weight_head, slope=0.2, sigmoid=False, defer=False,
+                           bias_p=None, slope_p=1.0, producer="upconv"):
+    """Last decoder block + head from the 32-channel map ``x`` (N,32,h,w) on: up-convolution kernel -> ``decoder_tail_tc_half``
+    (both tcgen05 / TMEM, fp16 map between them).  ``producer``: 'upconv' (``upconv_tc_half``: operands staged once, takes the RAW
+    output of the previous convolution with its ``bias_p`` / ``slope_p``) or 'tma' (``subpixel_conv_tc_half``: TMA-fed TF32 MMAs on an
+    activated map).  One fp16-range flag for both kernels; when raised the result comes from the TF32 flow (cuDNN phase
+    convolution + mma.sync tail) - immediately, or at the caller's sync point with ``defer=True``."""
+    def activated():
+        if bias_p is None and float(slope_p) == 1.0:
+            return x
+        return torch.nn.functional.leaky_relu(x if bias_p is None else x + bias_p.view(1, -1, 1, 1), float(slope_p))
+    if producer == "upconv":
+        yh, flag = upconv_tc_half(x, bias_p, slope_p, w2, bias_a, slope)
+    else:
+        yh, flag = subpixel_conv_tc_half(activated(), w2, bias_a, slope)
     out, _ = decoder_tail_tc_half(yh, weight_b, bias_b, weight_head, slope, sigmoid, flag=flag)
     if x.shape[0] > 0:
         def rerun():
-            y4 = torch.nn.functional.conv2d(x, w2, None, 1, 1)
+            y4 = torch.nn.functional.conv2d(activated(), w2, None, 1, 1)
             return decoder_tail(y4, bias_a, weight_b, bias_b, weight_head, slope, 2, sigmoid)
         guard = TailOverflow(flag, rerun)
         if defer:

@@ -451,6 +451,7 @@ class MultiScaleDecoder(torch.nn.Module):
         # fp16 range raises a device flag and the caller re-runs the mma.sync kernel) or 'mma_sync' (decoder_tail.cu, TF32)
         self.tail_impl = os.environ.get('RIDERS_TAIL_IMPL', 'tcgen05')
         self.tail_fp16_map = os.environ.get('RIDERS_TAIL_FP16_MAP', '1') != '0'   # tcgen05 phase convolution writes the tail's fp16 operand map
+        self.tail_upconv = os.environ.get('RIDERS_TAIL_UPCONV', '1') != '0'       # csrc/upconv_tc.cu (else the TMA-fed phase convolution)
         self.force_tail_impl = None                     # set by forward_output_batched for its re-run after a range violation
         self.defer_tail_check = False                   # True: the range flag is read at the caller's own sync point
         self.subconv_tc = os.environ.get('RIDERS_SUBCONV_TC', '0') != '0'      # ops.subpixel_conv_tc instead of cuDNN's 2x2 convolution: opt-in (both sit at the HBM bound of this write-heavy shape, cuDNN 10-15 % ahead)
@@ -474,6 +475,14 @@ class MultiScaleDecoder(torch.nn.Module):
         return (self.fused_sub and self.fused_tail and torch.backends.cudnn.allow_tf32 and not torch.is_grad_enabled()
                 and shape is not None and last.subpixel_taps == 2 and last._w2 is not None
                 and tuple(last._w2.shape) == (64, 32, 2, 2) and last.skip_channels == 0)
+
+    def _upconv_ok(self, last, shape):
+        """May the block in front of the last one hand over its raw convolution output to ``ops.upconv_tc_half`` (the tcgen05
+        up-convolution kernel applies that block's bias + LeakyReLU while it stages its operand)?"""
+        return ((self.force_tail_impl or self.tail_impl) == 'tcgen05' and self.tail_fp16_map and self.tail_upconv
+                and self.fused_tail and torch.backends.cudnn.allow_tf32 and not torch.is_grad_enabled() and shape is not None
+                and last.subpixel_taps == 2 and last._w2 is not None and tuple(last._w2.shape) == (64, 32, 2, 2)
+                and last.skip_channels == 0)
 
     def skip_lead_channels(self, n_skips):
         """Output channels of the up-convolution in front of each skip (skips[i] feeds block ``_order[n_skips-1-i]``,
@@ -502,7 +511,8 @@ class MultiScaleDecoder(torch.nn.Module):
             # the block in front of the fused tail hands over its RAW convolution output: its bias + LeakyReLU are applied
             # by the tail's own phase-convolution kernel while it stages its operand (ops.subpixel_conv_act)
             want_raw = (i == len(self._order) - 2 and pad_out is None and getattr(self, name).conv._fused_slope is not None
-                        and self._sub_ok(getattr(self, self._order[-1]), shape))
+                        and (self._sub_ok(getattr(self, self._order[-1]), shape)
+                             or self._upconv_ok(getattr(self, self._order[-1]), shape)))
             out = getattr(self, name)(y, skips[n], xp=yp, pad_out=pad_out, raw=want_raw)
             if want_raw:
                 y, raw_bias, raw_slope = out
@@ -524,15 +534,20 @@ class MultiScaleDecoder(torch.nn.Module):
             # convolution, bias + LeakyReLU, the 16 -> 1 head - in ONE kernel fed by the sub-pixel phase convolution
             taps = 2 if (last.subpixel_taps == 2 and last._w2 is not None) else 3
             impl = self.force_tail_impl or self.tail_impl
-            if (impl == 'tcgen05' and self.tail_fp16_map and raw_slope is None and taps == 2 and y.shape[1] == 32
-                    and tuple(last._w2.shape) == (64, 32, 2, 2) and y.shape[3] <= 54 and ops._is_channels_last(y)):
-                # the up-convolution finished by the tcgen05 phase convolution itself (fp16 operand map), then the tcgen05 tail
+            if (impl == 'tcgen05' and self.tail_fp16_map and taps == 2 and y.shape[1] == 32
+                    and tuple(last._w2.shape) == (64, 32, 2, 2) and y.shape[3] <= 54 and ops._is_channels_last(y)
+                    and (raw_slope is None or self.tail_upconv)):
+                # the up-convolution in one tcgen05 kernel that writes the tail's fp16 operand map, then the tcgen05 tail.
+                # 'upconv': operands staged once, the previous block's bias + LeakyReLU applied on the way (y may be raw);
+                # 'tma': the round-2 TMA-fed TF32 phase convolution with the finishing epilogue (RIDERS_TAIL_UPCONV=0)
                 self.last_head_sigmoid = bool(head_sigmoid)
                 self.last_used_tail = True
                 self.last_tail_impl = 'tcgen05+fp16map'
                 return [ops.decoder_upconv_tail_tc(y, last._w2, last.deconv.conv.conv.bias, last.conv.conv.weight,
                                                    last.conv.conv.bias, head.weight, _LEAK, sigmoid=head_sigmoid,
-                                                   defer=self.defer_tail_check)]
+                                                   defer=self.defer_tail_check, bias_p=raw_bias,
+                                                   slope_p=1.0 if raw_slope is None else raw_slope,
+                                                   producer='upconv' if self.tail_upconv else 'tma')]
             if raw_slope is not None:
                 y4 = ops.subpixel_conv_act(y, raw_bias, raw_slope, last._w2)          # previous block's bias + LeakyReLU fused in
             elif (self.subconv_tc and taps == 2 and tuple(last._w2.shape) == (64, 32, 2, 2) and y.shape[3] <= 54

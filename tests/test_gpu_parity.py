@@ -1025,7 +1025,7 @@ def test_upconv_and_tail_on_tcgen05_through_the_fp16_operand_map(hw, N):
     refh = F.conv2d(_fp16(zh), _fp16(wh), None, 1, 1)
     ref32 = F.conv2d(F.leaky_relu(F.conv2d(y, wb, bb, 1, 1), 0.2), wh, None, 1, 1)
     out, _ = ops.decoder_tail_tc_half(yh, wb, bb, wh, 0.2, flag=flag)
-    got = ops.decoder_upconv_tail_tc(x, w2, ba, wb, bb, wh, 0.2)
+    got = ops.decoder_upconv_tail_tc(x, w2, ba, wb, bb, wh, 0.2, producer="tma")
     assert torch.equal(out, got) and int(flag.item()) == 0
     scale = float(ref32.abs().max())
     err = (got - refh).abs()
@@ -1035,14 +1035,58 @@ def test_upconv_and_tail_on_tcgen05_through_the_fp16_operand_map(hw, N):
     y32 = ops.d2s_bias_act_concat(F.conv2d(x, w2, None, 1, 1).contiguous(memory_format=torch.channels_last), ba, None, 0.2, taps=2)
     full32 = F.conv2d(F.leaky_relu(F.conv2d(y32.contiguous(), wb, bb, 1, 1), 0.2), wh, None, 1, 1)
     assert float((got - full32).abs().max()) < 3e-3 * float(full32.abs().max())
-    sg = ops.decoder_upconv_tail_tc(x, w2, ba, wb, bb, wh, 0.2, sigmoid=True)
+    sg = ops.decoder_upconv_tail_tc(x, w2, ba, wb, bb, wh, 0.2, sigmoid=True, producer="tma")
     np.testing.assert_allclose(sg.cpu().numpy(), torch.sigmoid(got).cpu().numpy(), rtol=2e-6, atol=1e-7)
     # range guard: an activation beyond fp16 -> the TF32 library flow answers
     xb = x.clone()
     xb[0, :, 0, 0] = 3.0e5
     refb = ops.decoder_tail(F.conv2d(xb, w2, None, 1, 1), ba, wb, bb, wh, 0.2, taps=2)
     torch.backends.cudnn.allow_tf32 = False
-    assert torch.equal(ops.decoder_upconv_tail_tc(xb, w2, ba, wb, bb, wh, 0.2), refb)
+    assert torch.equal(ops.decoder_upconv_tail_tc(xb, w2, ba, wb, bb, wh, 0.2, producer="tma"), refb)
+
+
+@pytest.mark.parametrize("hw,N,raw", [((120, 50), 3, True), ((7, 9), 2, False), ((13, 30), 5, True), ((2, 3), 1, True),
+                                      ((120, 50), 200, True), ((31, 54), 2, True), ((9, 8), 160, False)])
+def test_upconv_tcgen05_from_the_raw_map_to_the_fp16_operand_map(hw, N, raw):
+    """ops.upconv_tc_half (csrc/upconv_tc.cu): previous bias + LeakyReLU, 2x2-tap phase convolution on tcgen05 (fp16 operands staged
+    once, taps as shifted views), depth-to-space + bias + LeakyReLU + fp16.  Against torch on the fp16-rounded operands the map
+    differs by at most one fp16 rounding; through the tail it matches the library flow to operand accuracy; several points per
+    persistent CTA (N = 200 / 160), partial batches and pairs (h + 1 not a multiple of 8), w at the limit (54)."""
+    F = torch.nn.functional
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device=DEV).manual_seed(hw[0] + 3 * N)
+    h, w = hw
+    x = torch.randn((N, 32, h, w), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    w2 = torch.randn((64, 32, 2, 2), device=DEV, generator=g) * 0.1
+    bp = torch.randn(32, device=DEV, generator=g) * 0.3 if raw else None
+    sp = 0.2 if raw else 1.0
+    ba, bb = torch.randn(16, device=DEV, generator=g) * 0.3, torch.randn(16, device=DEV, generator=g) * 0.3
+    wb = torch.randn((16, 16, 3, 3), device=DEV, generator=g) * 0.15
+    wh = torch.randn((1, 16, 3, 3), device=DEV, generator=g) * 0.2
+    xa = F.leaky_relu(x + bp.view(1, -1, 1, 1), sp) if raw else x
+    y4 = F.conv2d(_fp16(xa), _fp16(w2), None, 1, 1).contiguous(memory_format=torch.channels_last)
+    y = ops.d2s_bias_act_concat(y4, ba, None, 0.2, taps=2).contiguous()
+    yref = y.view(N, 2, 8, 2 * h, 2 * w).permute(0, 3, 1, 4, 2)                      # [n][Y][plane][X][k]
+    yh, flag = ops.upconv_tc_half(x, bp, sp, w2, ba, 0.2)
+    assert yh.shape == (N, 2 * h, 2, 2 * w, 8) and yh.dtype == torch.float16 and int(flag.item()) == 0
+    ysc = float(yref.abs().max())
+    ey = (yh.float() - yref).abs()
+    assert float(ey.max()) <= 2.0 ** -10 * ysc and float((ey > 2.0 ** -11 * yref.abs() + 1e-7).float().mean()) < 0.02
+    assert torch.equal(yh, ops.upconv_tc_half(x, bp, sp, w2, ba, 0.2)[0])            # deterministic
+    # through the tail, against the library flow it replaces (fp32 activation pass, phase convolution, three passes)
+    got = ops.decoder_upconv_tail_tc(x, w2, ba, wb, bb, wh, 0.2, bias_p=bp, slope_p=sp)
+    assert torch.equal(got, ops.decoder_tail_tc_half(yh, wb, bb, wh, 0.2)[0])
+    y32 = ops.d2s_bias_act_concat(F.conv2d(xa, w2, None, 1, 1).contiguous(memory_format=torch.channels_last), ba, None, 0.2, taps=2)
+    full32 = F.conv2d(F.leaky_relu(F.conv2d(y32.contiguous(), wb, bb, 1, 1), 0.2), wh, None, 1, 1)
+    assert float((got - full32).abs().max()) < 3e-3 * float(full32.abs().max())
+    other = ops.decoder_upconv_tail_tc(x, w2, ba, wb, bb, wh, 0.2, bias_p=bp, slope_p=sp, producer="tma")
+    assert float((got - other).abs().max()) < 3e-3 * float(full32.abs().max())      # the TMA-fed TF32 producer agrees
+    # range guard: an activation beyond fp16 -> the TF32 library flow answers
+    xb = x.clone()
+    xb[0, :, 0, 0] = 3.0e5
+    xab = F.leaky_relu(xb + bp.view(1, -1, 1, 1), sp) if raw else xb
+    refb = ops.decoder_tail(F.conv2d(xab, w2, None, 1, 1), ba, wb, bb, wh, 0.2, taps=2)
+    assert torch.equal(ops.decoder_upconv_tail_tc(xb, w2, ba, wb, bb, wh, 0.2, bias_p=bp, slope_p=sp), refb)
 
 
 def test_decoder_tail_tcgen05_fp16_range_guard():
@@ -1175,8 +1219,9 @@ def test_decoder_uses_the_fused_tail_only_where_tf32_is_allowed(monkeypatch):
         finally:
             torch.backends.cudnn.allow_tf32 = False
     scale = float(ref.abs().max())
-    for t in (got, got2, got3, got4, sep):
-        assert float((t - ref).abs().max()) < 5e-3 * scale
+    for name, t in (("mma.sync phase conv + tail", got), ("tcgen05 phase conv + tail", got2), ("cuDNN phase conv + tail", got3),
+                    ("other tail kernel", got4), ("separate passes", sep)):
+        assert float((t - ref).abs().max()) < 5e-3 * scale, name
     assert float((got - sep).abs().max()) < 5e-3 * scale
 
 

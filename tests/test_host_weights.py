@@ -165,3 +165,35 @@ def test_tcgen05_tail_weight_pack_is_the_unswizzled_k_major_image():
     wh._version                                                                 # (in-place edits bump the version)
     wh.mul_(1.0)
     assert ops._tail_tc_weights(wb, wh) is not pack
+
+
+def test_upconv_weight_pack_and_its_cache():
+    """ops._upconv_tc_weights: K-major unswizzled fp16 image [tap 2u+v][K half][n // 8][k // 8][n % 8][k % 8] of W2[n][16 kh + k][u][v];
+    the phase convolution it encodes (every tap a shifted view of the padded row) equals conv2d(x, W2, padding 1); and the pack
+    does not share a cache slot with the mma.sync fragments of the same parameter."""
+    torch.manual_seed(11)
+    w2 = torch.randn(64, 32, 2, 2) * 0.2
+    pack = ops._upconv_tc_weights(w2)
+    assert pack.dtype == torch.float16 and pack.numel() * 2 == 16384
+    raw = pack.numpy()
+
+    def b_matrix(t, kh):
+        m = np.zeros((64, 16), np.float32)
+        for n in range(64):
+            for k in range(16):
+                off = (t * 2 + kh) * 2048 + (n // 8) * 256 + (k // 8) * 128 + (n % 8) * 16 + (k % 8) * 2
+                m[n, k] = raw[off // 2]
+        return m
+    h, w = 3, 5
+    x = torch.randn(1, 32, h, w).half().float()
+    ref = F.conv2d(x, w2.half().float(), None, 1, 1)[0]                        # (64, h + 1, w + 1)
+    xp = F.pad(x, (1, 1, 1, 1))[0].permute(1, 2, 0).numpy()                    # staged rows: row i + 1, position j + 1
+    out = np.zeros((h + 1, w + 1, 64), np.float32)
+    for I in range(h + 1):
+        for t in range(4):
+            u, v = t // 2, t % 2
+            for kh in range(2):
+                out[I] += xp[I + u, v:v + w + 1, 16 * kh:16 * kh + 16] @ b_matrix(t, kh).T
+    np.testing.assert_allclose(out.transpose(2, 0, 1), ref.numpy(), rtol=1e-5, atol=1e-5)
+    frag = ops._subpixel_weight_fragments(w2)
+    assert frag.dtype == torch.float32 and ops._upconv_tc_weights(w2) is pack and ops._subpixel_weight_fragments(w2) is frag

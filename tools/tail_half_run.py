@@ -16,7 +16,10 @@ w2 = torch.randn((64, 32, 2, 2), device=DEV, generator=g) * 0.1
 ba, bb = torch.randn(16, device=DEV, generator=g) * 0.1, torch.randn(16, device=DEV, generator=g) * 0.1
 wb = torch.randn((16, 16, 3, 3), device=DEV, generator=g) * 0.1
 wh = torch.randn((1, 16, 3, 3), device=DEV, generator=g) * 0.1
+bp = torch.randn(32, device=DEV, generator=g) * 0.1
 for name, fn in (("phase convolution -> fp16 map", lambda: ops.subpixel_conv_tc_half(x32, w2, ba, 0.2)),
+                 ("raw map -> upconv -> fp16 map", lambda: ops.upconv_tc_half(x32, bp, 0.2, w2, ba, 0.2)),
+                 ("bias_act of the 32-channel map", lambda: ops.bias_act_(x32, bp, 0.2)),
                  ("tail on the fp16 map", None)):
     if fn is None:
         yh, _ = ops.subpixel_conv_tc_half(x32, w2, ba, 0.2)

@@ -77,10 +77,40 @@ def case_half(N, h, w, seed=0):
     return (not bool(bad.any())) and float(ey.max()) < 4e-3 * float(yref.abs().max())
 
 
+def case_upconv(N, h, w, seed=0, raw=True):
+    """upconv_tc_half: raw 32-channel map (+ previous bias / LeakyReLU) -> fp16 operand map, against torch on fp16-rounded operands."""
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    x = torch.randn((N, 32, h, w), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    w2 = torch.randn((64, 32, 2, 2), device=DEV, generator=g) * 0.1
+    bp = torch.randn(32, device=DEV, generator=g) * 0.3 if raw else None
+    sp = 0.2 if raw else 1.0
+    ba = torch.randn(16, device=DEV, generator=g) * 0.3
+    xa = F.leaky_relu(x + bp.view(1, -1, 1, 1), sp) if raw else x
+    y4 = F.conv2d(h16(xa), h16(w2), None, 1, 1).contiguous(memory_format=torch.channels_last)
+    y = ops.d2s_bias_act_concat(y4, ba, None, 0.2, taps=2).contiguous()
+    yref = y.view(N, 2, 8, 2 * h, 2 * w).permute(0, 3, 1, 4, 2)
+    yh, flag = ops.upconv_tc_half(x, bp, sp, w2, ba, 0.2)
+    torch.cuda.synchronize()
+    ey = (yh.float() - yref).abs()
+    sc = float(yref.abs().max())
+    bad = ey > 2.5e-3 * sc
+    print("upconv N=%d h=%d w=%d raw=%d: yh max err %.3e (scale %.2f) bad fraction %.5f flag %d" %
+          (N, h, w, raw, float(ey.max()), sc, float(bad.float().mean()), int(flag.item())), flush=True)
+    if bool(bad.any()):
+        idx = bad.nonzero()[:8].tolist()
+        print("   first bad [n, Y, plane, X, k]:", idx, flush=True)
+        rows = bad.any(dim=4).any(dim=3).any(dim=2).any(dim=0).nonzero().flatten().tolist()
+        cols = bad.any(dim=4).any(dim=2).any(dim=1).any(dim=0).nonzero().flatten().tolist()
+        print("   bad rows", rows[:40], "cols", cols[:40], flush=True)
+    return not bool(bad.any())
+
+
 if __name__ == "__main__":
     ok = True
     for N, h, w, taps in ((1, 8, 5, 3), (3, 7, 9, 2), (2, 13, 30, 3), (3, 120, 50, 2), (2, 40, 70, 3), (40, 120, 50, 2)):
         ok = case(N, h, w, taps) and ok
     for N, h, w in ((1, 8, 5), (3, 7, 9), (2, 13, 30), (3, 120, 50), (40, 120, 50)):
         ok = case_half(N, h, w) and ok
+    for N, h, w, raw in ((1, 8, 5, True), (3, 7, 9, False), (2, 13, 30, True), (3, 120, 50, True), (200, 120, 50, True), (2, 31, 54, True)):
+        ok = case_upconv(N, h, w, raw=raw) and ok
     print("ALL OK" if ok else "MISMATCH", flush=True)
