@@ -383,6 +383,15 @@ int riders_decoder_tail_tc_half_nhwc(const void* yh, int N, int h, int w, const 
 int riders_upconv_tc_half_nhwc(const float* x, const float* bias_p_host, float slope_p, const void* w_pack,
                                int N, int h, int w, const float* bias_a_host, float slope, void* yh,
                                int* status, void* stream);
+/* The same kernel one level up (deconv1 of RC-Net's decoder: 64 -> 32 channels, 60 x 25 -> 120 x 50), float32 out:
+ *   out[n][2h][2w][0..32) = act(depth_to_space(conv2x2(act_p(x + bias_p), W2 (128,64,2,2), padding 1)) + bias_a),
+ * x (N, 64, h, w <= 26) channels-last fp32; out: channels-last float32 with a pixel stride of ctot >= 32 channels - the block's
+ * concat buffer, whose channels [32, ctot) already hold the skip (placed there by the gather).  Replaces the library phase
+ * convolution and the depth-to-space / bias / LeakyReLU / concat pass of that block.  w_pack: 64 KB, layout as above with
+ * n < 128 and four K steps per tap.  status: raised when a staged input value leaves the fp16 range.                        */
+int riders_upconv_tc_f32_nhwc(const float* x, const float* bias_p_host, float slope_p, const void* w_pack,
+                              int N, int h, int w, const float* bias_a_host, float slope, float* out, int ctot,
+                              int* status, void* stream);
 /* Sub-pixel phase convolution of the last decoder block in its 2x2-tap form (32 -> 4 x 16 channels), TF32, with the bias
  * + LeakyReLU of the convolution that produced x fused into the operand load (deconv1.conv -> deconv0.deconv of
  * MultiScaleDecoder, RCNet/networks.py:678-779): y4 (N, 64, h+1, w+1) = conv2x2(act(x + bias), W2, padding 1), x (N, 32, h, w)

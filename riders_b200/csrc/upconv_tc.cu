@@ -28,38 +28,56 @@ namespace riders {
 namespace upconv {
 using namespace tcg;
 
-constexpr int CIN = 32, NOUT = 64;
-constexpr int PITCH = 56;                             // positions per staged input row: 1 + w + 1 <= 56
 constexpr int BROWS = 8, XROWS = BROWS + 1;           // y4 rows / input rows per batch
-constexpr int PLANE_POS = 528;                        // positions per plane: 9 x 56 + the reach of the last M = 128 view (7 * 56 + 1 + 127)
-constexpr int PLANE = PLANE_POS * 16;                 // 8448 B (a multiple of 128)
-constexpr int BATCH_BYTES = 4 * PLANE;                // four planes of 8 channels
 constexpr int NBUF = 2, NACC = 4;
-constexpr int W_BYTES = 8 * NOUT * 32;                // 4 taps x 2 K halves x (64 rows x 16 fp16) = 16 KB
-constexpr int STAGE_BYTES = 4 * 2 * 110 * 16;         // epilogue staging: 4 output rows x 2 planes x W <= 110 pixels x 16 B
 constexpr int LOADER_WARPS = 8, W_MMA = 8, W_EPI = 12, EPI_GROUPS = 2, THREADS = (W_EPI + 4 * EPI_GROUPS) * 32;   // warps 9..11 idle
 constexpr int B_BFULL = 0, B_BFREE = B_BFULL + NBUF, B_DFULL = B_BFREE + NBUF, B_DFREE = B_DFULL + NACC, NBARS = B_DFREE + NACC;
-constexpr int SMEM_BYTES = NBUF * BATCH_BYTES + W_BYTES + EPI_GROUPS * STAGE_BYTES + NBARS * 8 + 16;
-constexpr uint32_t TMEM_COLS = NACC * NOUT;           // 256
+
+// Two instances.  <32, 16, 56, true>: the LAST block (deconv0), two y4 rows of <= 55 positions per M = 128 tile, fp16 operand
+// map out (the tail's input).  <64, 32, 28, false>: the block before it (deconv1: 60 x 25 -> 120 x 50), four y4 rows of <= 27
+// positions per tile, float32 channels-last out, written into the first COUT channels of the block's concat buffer (the skip
+// is already in place behind them) - there it replaces the library phase convolution AND the depth-to-space pass.
+template <int CIN_, int COUT_, int PITCH_, bool HALF_OUT_> struct Cfg {
+    static constexpr int CIN = CIN_, COUT = COUT_, NOUT = 4 * COUT_, PITCH = PITCH_;
+    static constexpr bool HALF_OUT = HALF_OUT_;
+    static constexpr int RPT = 112 / PITCH;                               // y4 rows per M = 128 tile
+    static constexpr int NPLANES = CIN / 8, KSTEPS = CIN / 16;
+    static constexpr int PLANE_POS = (((BROWS - RPT + 1) * PITCH + 1 + 128) + 7) / 8 * 8;   // staged rows + the reach of the last view
+    static constexpr int PLANE = PLANE_POS * 16;
+    static constexpr int BATCH_BYTES = NPLANES * PLANE;
+    static constexpr int W_BYTES = 4 * KSTEPS * NOUT * 32;                // 4 taps x K steps x (NOUT rows x 16 fp16)
+    static constexpr int STAGE_BYTES = HALF_OUT ? 2 * RPT * 2 * 2 * (PITCH - 1) * 16 : 0;   // 2 RPT output rows x 2 planes x W pixels x 16 B
+    static constexpr int SMEM_BYTES = NBUF * BATCH_BYTES + W_BYTES + EPI_GROUPS * STAGE_BYTES + NBARS * 8 + 16;
+    static constexpr uint32_t TMEM_COLS = NACC * NOUT;
+    static_assert(BROWS % RPT == 0 && RPT * PITCH <= 128 && XROWS * PITCH <= PLANE_POS && NPLANES * (PITCH - 2) <= LOADER_WARPS * 32,
+                  "tile geometry");
+    static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
+};
 
 struct Params {
-    const float4* x;          // (N, h, w, 32) fp32, raw output of the previous convolution
+    const float4* x;          // (N, h, w, CIN) fp32, raw output of the previous convolution
     const uint4* w_pack;
-    __half* yh;               // [N][2h][2][2w][8]
+    __half* yh;               // HALF_OUT: [N][2h][2][2w][8]
+    float* out;               // !HALF_OUT: (N, 2h, 2w, ctot) float32, channels [0, COUT) written
+    int ctot;
     int* status;
-    float bias_p[CIN];        // the previous convolution's bias (zeros if none)
+    float bias_p[64];         // the previous convolution's bias (zeros if none)
     float slope_p;            // its LeakyReLU slope (1 = identity: x is already activated)
-    float bias_a[16];
+    float bias_a[32];
     float slope;
     int N, h, w;
 };
 
 __device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<const uint32_t*>(&v); }
 
+template <class C>
 __global__ void __launch_bounds__(THREADS, 1)
 upconv_tc_kernel(const __grid_constant__ Params P) {
+    constexpr int CIN = C::CIN, NOUT = C::NOUT, PITCH = C::PITCH, RPT = C::RPT, NPLANES = C::NPLANES, KSTEPS = C::KSTEPS;
+    constexpr int PLANE = C::PLANE, BATCH_BYTES = C::BATCH_BYTES, W_BYTES = C::W_BYTES, STAGE_BYTES = C::STAGE_BYTES;
+    constexpr uint32_t TMEM_COLS = C::TMEM_COLS;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* xb = smem;                                   // [NBUF][4 planes][PLANE_POS] x 16 B
+    uint8_t* xb = smem;                                   // [NBUF][NPLANES][PLANE_POS] x 16 B
     uint8_t* ws = xb + NBUF * BATCH_BYTES;                // packed W2
     uint8_t* stg = ws + W_BYTES;                          // [EPI_GROUPS][4 rows][2 planes][W] x 16 B
     const uint32_t bars = smem_u32(stg + EPI_GROUPS * STAGE_BYTES);
@@ -87,7 +105,7 @@ upconv_tc_kernel(const __grid_constant__ Params P) {
     if (warp < LOADER_WARPS) {
         // ===================== input rows: global -> + bias_p, LeakyReLU -> fp16 -> plane layout =====================
         // thread = (pixel, 8-channel chunk): a warp reads 8 pixels x 128 B (contiguous) and stores 8 pixels x 4 planes
-        const int px = tid >> 2, ch = tid & 3;
+        const int px = tid / NPLANES, ch = tid % NPLANES;
         const bool active = px < w;
         float bp[8];
 #pragma unroll
@@ -95,7 +113,7 @@ upconv_tc_kernel(const __grid_constant__ Params P) {
         const float sp = P.slope_p;
         uint32_t nb = 0;                                   // batches staged so far (ring position)
         for (int n = blockIdx.x; n < P.N; n += gridDim.x) {
-            const float4* xn = P.x + ((size_t)n * h * w + px) * 8 + ch * 2;
+            const float4* xn = P.x + ((size_t)n * h * w + px) * (CIN / 4) + ch * 2;
             for (int bi = 0; bi < nbatch; ++bi, ++nb) {
                 const int buf = nb % NBUF;
                 const int i0 = bi * BROWS - 1;             // first input row of the batch (row -1 = the padding)
@@ -103,7 +121,7 @@ upconv_tc_kernel(const __grid_constant__ Params P) {
                     const int r0 = max(i0 + BROWS, 0), r1 = min(i0 + BROWS + XROWS, h);
                     if (bi + 1 < nbatch && r1 > r0)
                         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
-                                     ::"l"(P.x + ((size_t)n * h + r0) * w * 8), "r"((r1 - r0) * w * 128) : "memory");
+                                     ::"l"(P.x + ((size_t)n * h + r0) * w * (CIN / 4)), "r"((r1 - r0) * w * CIN * 4) : "memory");
                 }
                 mbar_wait_sleep(bar(B_BFREE + buf), ((nb / NBUF) & 1) ^ 1, 100);
                 uint8_t* dst = xb + buf * BATCH_BYTES + ch * PLANE + (1 + px) * 16;
@@ -112,7 +130,7 @@ upconv_tc_kernel(const __grid_constant__ Params P) {
                 auto load = [&](int r, float4 (&t)[2]) {
                     const int row = i0 + r;
                     if (active && (unsigned)row < (unsigned)h) {
-                        const float4* g = xn + (size_t)row * w * 8;
+                        const float4* g = xn + (size_t)row * w * (CIN / 4);
                         t[0] = __ldcs(g); t[1] = __ldcs(g + 1);
                     } else {
                         t[0] = make_float4(0.f, 0.f, 0.f, 0.f); t[1] = t[0];
@@ -154,7 +172,7 @@ upconv_tc_kernel(const __grid_constant__ Params P) {
                 const int buf = nb % NBUF;
                 mbar_wait(bar(B_BFULL + buf), (nb / NBUF) & 1);
                 const uint64_t ad0 = smem_desc_nosw(xa + buf * BATCH_BYTES, PLANE, 128);
-                const int npairs = min(BROWS / 2, (h + 1 - bi * BROWS + 1) / 2);
+                const int npairs = min(BROWS / RPT, (h + 1 - bi * BROWS + RPT - 1) / RPT);   // tiles of RPT y4 rows in this batch
                 for (int k = 0; k < npairs; ++k, ++np) {
                     const int acc = np % NACC;
                     mbar_wait(bar(B_DFREE + acc), ((np / NACC) & 1) ^ 1);
@@ -164,10 +182,10 @@ upconv_tc_kernel(const __grid_constant__ Params P) {
                         for (int t = 0; t < 4; ++t) {
                             const int u = t >> 1, v = t & 1;
 #pragma unroll
-                            for (int kh = 0; kh < 2; ++kh)
+                            for (int kh = 0; kh < KSTEPS; ++kh)
                                 umma_f16(tmem + acc * NOUT,
-                                         ad0 + (uint64_t)(kh * 2 * (PLANE / 16) + (2 * k + u) * PITCH + v),
-                                         bd0 + (uint64_t)((t * 2 + kh) * (NOUT * 32 / 16)), IDESC, (t | kh) ? 1u : 0u);
+                                         ad0 + (uint64_t)(kh * 2 * (PLANE / 16) + (RPT * k + u) * PITCH + v),
+                                         bd0 + (uint64_t)((t * KSTEPS + kh) * (NOUT * 32 / 16)), IDESC, (t | kh) ? 1u : 0u);
                         }
                         umma_commit(bar(B_DFULL + acc));
                         if (k == npairs - 1) umma_commit(bar(B_BFREE + buf));
@@ -179,72 +197,104 @@ upconv_tc_kernel(const __grid_constant__ Params P) {
     } else if (warp >= W_EPI) {
         // ===================== finish: TMEM -> depth-to-space + bias_a + LeakyReLU -> fp16 -> staging -> bulk stores =====
         const int quad = warp & 3, grp = (warp - W_EPI) >> 2;
-        const int row = quad * 32 + lane;                          // TMEM lane = position in the pair
-        const int r2 = row >= PITCH ? 1 : 0, J = row - r2 * PITCH; // y4 row of the pair, y4 column
+        const int row = quad * 32 + lane;                          // TMEM lane = position in the tile
+        const int r2 = row / PITCH, J = row - r2 * PITCH;          // y4 row of the tile, y4 column
         const int leader = (W_EPI + 4 * grp) * 32;
-        const uint32_t ROWB = (uint32_t)W * 32;                    // bytes of one output row (2 planes x W x 16 B)
+        const uint32_t ROWB = (uint32_t)W * 32;                    // HALF_OUT: bytes of one output row (2 planes x W x 16 B)
         uint8_t* stage = stg + grp * STAGE_BYTES;
         const float slope = P.slope;
         uint32_t np = 0;
         for (int n = blockIdx.x; n < P.N; n += gridDim.x) {
             for (int bi = 0; bi < nbatch; ++bi) {
-                const int npairs = min(BROWS / 2, (h + 1 - bi * BROWS + 1) / 2);
+                const int npairs = min(BROWS / RPT, (h + 1 - bi * BROWS + RPT - 1) / RPT);
                 for (int k = 0; k < npairs; ++k, ++np) {
                     if ((int)(np % EPI_GROUPS) != grp) continue;
                     const int acc = np % NACC;
-                    const int p = bi * BROWS + 2 * k;              // first y4 row of the pair
+                    const int p = bi * BROWS + RPT * k;            // first y4 row of the tile
+                    const int I = p + r2;
+                    const bool lane_ok = row < RPT * PITCH && I <= h && J <= w;
                     mbar_wait_sleep(bar(B_DFULL + acc), (np / NACC) & 1, 100);
                     tc_fence_after();
-                    uint32_t r0[32], r1[32];
                     const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc * NOUT;
-                    TMEM_LD32(taddr, r0);
-                    TMEM_LD32(taddr + 32, r1);
-                    tmem_wait_ld();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar(B_DFREE + acc));
-                    if (tid == leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the stores that read this buffer are done
-                    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-                    // phase (a, b) of y4 position (I, J) is output pixel (2 I - a, 2 J - b); local output row lr = Y - (2 p - 1)
-                    const int I = p + r2;
-                    if (row < 2 * PITCH && I <= h && J <= w) {
+                    if constexpr (C::HALF_OUT) {
+                        uint32_t r0[32], r1[32];
+                        TMEM_LD32(taddr, r0);
+                        TMEM_LD32(taddr + 32, r1);
+                        tmem_wait_ld();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar(B_DFREE + acc));
+                        if (tid == leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the stores that read this buffer are done
+                        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                        // phase (a, b) of y4 position (I, J) is output pixel (2 I - a, 2 J - b); local output row lr = Y - (2 p - 1)
+                        if (lane_ok) {
 #pragma unroll
-                        for (int ab = 0; ab < 4; ++ab) {
-                            const int a = ab >> 1, b = ab & 1;
-                            const int Y = 2 * I - a, X = 2 * J - b;
-                            if ((unsigned)Y < (unsigned)H && (unsigned)X < (unsigned)W) {
-                                const uint32_t* v = ab < 2 ? r0 + 16 * ab : r1 + 16 * (ab - 2);
-                                uint32_t hv[8];
+                            for (int ab = 0; ab < 4; ++ab) {
+                                const int a = ab >> 1, b = ab & 1;
+                                const int Y = 2 * I - a, X = 2 * J - b;
+                                if ((unsigned)Y < (unsigned)H && (unsigned)X < (unsigned)W) {
+                                    const uint32_t* v = ab < 2 ? r0 + 16 * ab : r1 + 16 * (ab - 2);
+                                    uint32_t hv[8];
 #pragma unroll
-                                for (int c = 0; c < 16; c += 2) {
-                                    float v0 = __uint_as_float(v[c]) + P.bias_a[c], v1 = __uint_as_float(v[c + 1]) + P.bias_a[c + 1];
-                                    v0 = fmaxf(v0, v0 * slope); v1 = fmaxf(v1, v1 * slope);
-                                    const __half2 hh = __floats2half2_rn(v0, v1);
-                                    amax2 = __hmax2_nan(amax2, __habs2(hh));
-                                    hv[c >> 1] = h2_bits(hh);
+                                    for (int c = 0; c < 16; c += 2) {
+                                        float v0 = __uint_as_float(v[c]) + P.bias_a[c], v1 = __uint_as_float(v[c + 1]) + P.bias_a[c + 1];
+                                        v0 = fmaxf(v0, v0 * slope); v1 = fmaxf(v1, v1 * slope);
+                                        const __half2 hh = __floats2half2_rn(v0, v1);
+                                        amax2 = __hmax2_nan(amax2, __habs2(hh));
+                                        hv[c >> 1] = h2_bits(hh);
+                                    }
+                                    uint8_t* d = stage + (uint32_t)(2 * r2 - a + 1) * ROWB + (uint32_t)X * 16;
+                                    *reinterpret_cast<uint4*>(d) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+                                    *reinterpret_cast<uint4*>(d + (uint32_t)W * 16) = make_uint4(hv[4], hv[5], hv[6], hv[7]);
                                 }
-                                uint8_t* d = stage + (uint32_t)(2 * r2 - a + 1) * ROWB + (uint32_t)X * 16;
-                                *reinterpret_cast<uint4*>(d) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
-                                *reinterpret_cast<uint4*>(d + (uint32_t)W * 16) = make_uint4(hv[4], hv[5], hv[6], hv[7]);
                             }
                         }
-                    }
-                    fence_async_smem();
-                    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-                    if (tid == leader) {
-                        for (int lr = 0; lr < 4; ++lr) {
-                            const int Y = 2 * p - 1 + lr;
-                            if ((unsigned)Y >= (unsigned)H) continue;
-                            __half* gdst = P.yh + ((size_t)n * H + Y) * (size_t)W * 16;
-                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                         ::"l"(gdst), "r"(smem_u32(stage + lr * ROWB)), "r"(ROWB) : "memory");
+                        fence_async_smem();
+                        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                        if (tid == leader) {
+                            for (int lr = 0; lr < 2 * RPT; ++lr) {
+                                const int Y = 2 * p - 1 + lr;
+                                if ((unsigned)Y >= (unsigned)H) continue;
+                                __half* gdst = P.yh + ((size_t)n * H + Y) * (size_t)W * 16;
+                                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                             ::"l"(gdst), "r"(smem_u32(stage + lr * ROWB)), "r"(ROWB) : "memory");
+                            }
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    } else {
+                        // float32 channels-last out: phase ab = 32 accumulator columns = the COUT channels of output pixel
+                        // (2 I - a, 2 J - b): + bias_a, LeakyReLU, eight 16-byte stores (the pixel's 128 contiguous bytes)
+                        static_assert(C::HALF_OUT || C::COUT == 32, "float32 epilogue: one TMEM_LD32 per phase");
+#pragma unroll
+                        for (int ab = 0; ab < 4; ++ab) {
+                            uint32_t r[32];
+                            TMEM_LD32(taddr + 32 * ab, r);
+                            tmem_wait_ld();
+                            if (ab == 3) {
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(bar(B_DFREE + acc));
+                            }
+                            const int a = ab >> 1, b = ab & 1;
+                            const int Y = 2 * I - a, X = 2 * J - b;
+                            if (lane_ok && (unsigned)Y < (unsigned)H && (unsigned)X < (unsigned)W) {
+                                float4* o = reinterpret_cast<float4*>(P.out + (((size_t)n * H + Y) * W + X) * (size_t)P.ctot);
+#pragma unroll
+                                for (int c = 0; c < 32; c += 4) {
+                                    float4 q;
+                                    q.x = __uint_as_float(r[c]) + P.bias_a[c];         q.y = __uint_as_float(r[c + 1]) + P.bias_a[c + 1];
+                                    q.z = __uint_as_float(r[c + 2]) + P.bias_a[c + 2]; q.w = __uint_as_float(r[c + 3]) + P.bias_a[c + 3];
+                                    q.x = fmaxf(q.x, q.x * slope); q.y = fmaxf(q.y, q.y * slope);
+                                    q.z = fmaxf(q.z, q.z * slope); q.w = fmaxf(q.w, q.w * slope);
+                                    o[c >> 2] = q;
+                                }
+                            }
+                        }
                     }
                 }
             }
         }
-        if (tid == leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (C::HALF_OUT && tid == leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     {
         const float2 m = __half22float2(amax2);
@@ -258,30 +308,60 @@ upconv_tc_kernel(const __grid_constant__ Params P) {
 }  // namespace upconv
 }  // namespace riders
 
+template <class C>
+static int upconv_launch(const riders::upconv::Params& P, cudaStream_t st, const char* what) {
+    using namespace riders;
+    static size_t configured[64] = {0};
+    if (int rc_smem = ensure_dynamic_smem(upconv::upconv_tc_kernel<C>, (size_t)(C::SMEM_BYTES), configured, "upconv_tc: shared memory attribute")) return rc_smem;
+    const int grid = P.N < sm_count() ? P.N : sm_count();
+    count_launches(1);
+    upconv::upconv_tc_kernel<C><<<grid, upconv::THREADS, C::SMEM_BYTES, st>>>(P);
+    return check_launch(what);
+}
+
+static int upconv_fill(riders::upconv::Params& P, const float* x, const float* bias_p_host, float slope_p, const void* w_pack,
+                       int N, int h, int w, const float* bias_a_host, float slope, int cin, int cout, int pitch) {
+    using namespace riders;
+    RIDERS_REQUIRE(N >= 0 && h > 0 && w > 0, "upconv_tc: bad shape");
+    RIDERS_REQUIRE(w + 2 <= pitch, "upconv_tc: at most %d columns (got w = %d)", pitch - 2, w);
+    RIDERS_REQUIRE(slope >= 0.f && slope <= 1.f && slope_p >= 0.f && slope_p <= 1.f, "upconv_tc: LeakyReLU slopes must be in [0, 1]");
+    P.x = reinterpret_cast<const float4*>(x);
+    P.w_pack = reinterpret_cast<const uint4*>(w_pack);
+    P.yh = nullptr; P.out = nullptr; P.ctot = 0; P.status = nullptr;
+    for (int c = 0; c < 64; ++c) P.bias_p[c] = (bias_p_host && c < cin) ? bias_p_host[c] : 0.f;
+    P.slope_p = slope_p;
+    for (int c = 0; c < 32; ++c) P.bias_a[c] = (bias_a_host && c < cout) ? bias_a_host[c] : 0.f;
+    P.slope = slope;
+    P.N = N; P.h = h; P.w = w;
+    return RIDERS_OK;
+}
+
 extern "C" int riders_upconv_tc_half_nhwc(const float* x, const float* bias_p_host, float slope_p, const void* w_pack,
                                           int N, int h, int w, const float* bias_a_host, float slope, void* yh,
                                           int* status, void* stream) {
     using namespace riders;
-    RIDERS_REQUIRE(N >= 0 && h > 0 && w > 0, "upconv_tc: bad shape");
-    RIDERS_REQUIRE(w + 2 <= upconv::PITCH, "upconv_tc: at most %d columns (got w = %d)", upconv::PITCH - 2, w);
-    RIDERS_REQUIRE(slope >= 0.f && slope <= 1.f && slope_p >= 0.f && slope_p <= 1.f, "upconv_tc: LeakyReLU slopes must be in [0, 1]");
+    upconv::Params P;
+    if (int rc = upconv_fill(P, x, bias_p_host, slope_p, w_pack, N, h, w, bias_a_host, slope, 32, 16, 56)) return rc;
     if (N == 0) return RIDERS_OK;
     RIDERS_REQUIRE(x && w_pack && yh, "upconv_tc: null pointer");
     RIDERS_REQUIRE(((((uintptr_t)x) | ((uintptr_t)w_pack) | ((uintptr_t)yh)) & 15) == 0, "upconv_tc: 16-byte alignment");
-    upconv::Params P;
-    P.x = reinterpret_cast<const float4*>(x);
-    P.w_pack = reinterpret_cast<const uint4*>(w_pack);
     P.yh = reinterpret_cast<__half*>(yh);
     P.status = status;
-    for (int c = 0; c < upconv::CIN; ++c) P.bias_p[c] = bias_p_host ? bias_p_host[c] : 0.f;
-    P.slope_p = slope_p;
-    for (int c = 0; c < 16; ++c) P.bias_a[c] = bias_a_host ? bias_a_host[c] : 0.f;
-    P.slope = slope;
-    P.N = N; P.h = h; P.w = w;
-    static size_t configured[64] = {0};
-    if (int rc_smem = ensure_dynamic_smem(upconv::upconv_tc_kernel, (size_t)(upconv::SMEM_BYTES), configured, "upconv_tc: shared memory attribute")) return rc_smem;
-    const int grid = N < sm_count() ? N : sm_count();
-    count_launches(1);
-    upconv::upconv_tc_kernel<<<grid, upconv::THREADS, upconv::SMEM_BYTES, (cudaStream_t)stream>>>(P);
-    return check_launch("upconv_tc_half_nhwc");
+    return upconv_launch<upconv::Cfg<32, 16, 56, true>>(P, (cudaStream_t)stream, "upconv_tc_half_nhwc");
+}
+
+extern "C" int riders_upconv_tc_f32_nhwc(const float* x, const float* bias_p_host, float slope_p, const void* w_pack,
+                                         int N, int h, int w, const float* bias_a_host, float slope, float* out, int ctot,
+                                         int* status, void* stream) {
+    using namespace riders;
+    upconv::Params P;
+    if (int rc = upconv_fill(P, x, bias_p_host, slope_p, w_pack, N, h, w, bias_a_host, slope, 64, 32, 28)) return rc;
+    RIDERS_REQUIRE(ctot >= 32 && ctot % 4 == 0, "upconv_tc_f32: the output pixel stride must be >= 32 channels and a multiple of 4 (got %d)", ctot);
+    if (N == 0) return RIDERS_OK;
+    RIDERS_REQUIRE(x && w_pack && out, "upconv_tc: null pointer");
+    RIDERS_REQUIRE(((((uintptr_t)x) | ((uintptr_t)w_pack) | ((uintptr_t)out)) & 15) == 0, "upconv_tc: 16-byte alignment");
+    P.out = out;
+    P.ctot = ctot;
+    P.status = status;
+    return upconv_launch<upconv::Cfg<64, 32, 28, false>>(P, (cudaStream_t)stream, "upconv_tc_f32_nhwc");
 }

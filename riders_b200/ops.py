@@ -611,13 +611,14 @@ def subpixel_conv_tc_half(x, w2, bias, slope=0.2, flag=None):
 
 
 def _upconv_tc_weights(w2):
-    """(64,32,2,2) 2x2-tap phase kernels -> the 16 KB fp16 B-operand image of riders_upconv_tc_half_nhwc: for tap t = 2u + v and
-    K half kh a K-major unswizzled 64 x 16 matrix [n // 8][k // 8][n % 8][k % 8] of W2[n][16 kh + k][u][v]; cached per version."""
+    """(4 Cout, Cin, 2, 2) 2x2-tap phase kernels -> the fp16 B-operand image of riders_upconv_tc_*_nhwc: for tap t = 2u + v and K
+    step kh (16 input channels) a K-major unswizzled (4 Cout) x 16 matrix [n // 8][k // 8][n % 8][k % 8] of W2[n][16 kh + k][u][v]
+    ((64,32,2,2): 16 KB; (128,64,2,2): 64 KB); cached per version."""
     def make():
         dev = w2.device
         t = torch.arange(4, device=dev).view(4, 1, 1, 1, 1, 1)
-        kh = torch.arange(2, device=dev).view(1, 2, 1, 1, 1, 1)
-        ng = torch.arange(8, device=dev).view(1, 1, 8, 1, 1, 1)
+        kh = torch.arange(w2.shape[1] // 16, device=dev).view(1, -1, 1, 1, 1, 1)
+        ng = torch.arange(w2.shape[0] // 8, device=dev).view(1, 1, -1, 1, 1, 1)
         kc = torch.arange(2, device=dev).view(1, 1, 1, 2, 1, 1)
         nr = torch.arange(8, device=dev).view(1, 1, 1, 1, 8, 1)
         ke = torch.arange(8, device=dev).view(1, 1, 1, 1, 1, 8)
@@ -645,6 +646,35 @@ def upconv_tc_half(x, bias_p, slope_p, w2, bias_a, slope=0.2, flag=None):
                                                    N, h, w, _ptr(_host_floats(bias_a)), float(slope), _ptr(yh), _ptr(flag), _stream())
     _lib.check(rc, "riders_upconv_tc_half_nhwc")
     return yh, flag
+
+
+def upconv_tc_f32(x, bias_p, slope_p, w2, bias_a, slope=0.2, skip=None, flag=None):
+    """deconv1 of RC-Net's decoder (64 -> 32 channels) as ONE tcgen05 kernel: act_p(x + bias_p) -> 2x2-tap phase convolution ->
+    depth-to-space + bias_a + LeakyReLU, float32, written into the leading 32 channels of the block's concat buffer.
+    x (N,64,h,w<=26) channels_last; ``skip``: None, or a skip placed by ``placed_skip_buffers`` (its parent buffer is the
+    destination), or any (N,Cs,2h,2w) map (copied behind the result).  Returns (z (N, 32 + Cs, 2h, 2w) channels_last, flag)."""
+    _need_cuda(x, w2)
+    N, Cc, h, w = x.shape
+    if not (_is_channels_last(x) and x.dtype == torch.float32 and Cc == 64 and tuple(w2.shape) == (128, 64, 2, 2) and w <= 26):
+        raise _lib.RidersError("upconv_tc_f32: needs a channels_last float32 (N,64,h,w<=26) map and (128,64,2,2) kernels")
+    parent = placed_parent(skip, 32) if skip is not None else None
+    if parent is None:
+        Cs = 0 if skip is None else skip.shape[1]
+        if Cs % 4:
+            raise _lib.RidersError("upconv_tc_f32: the skip needs a multiple of 4 channels")
+        parent = torch.empty((N, 32 + Cs, 2 * h, 2 * w), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+        if Cs:
+            parent[:, 32:].copy_(skip)
+    if tuple(parent.shape[2:]) != (2 * h, 2 * w) or parent.shape[0] != N:
+        raise _lib.RidersError("upconv_tc_f32: the skip does not match the up-sampled map")
+    if flag is None:
+        flag = torch.zeros(1, dtype=torch.int32, device=x.device)
+    with _span("upconv", x.numel() * 4 + N * 4 * h * w * 32 * 4):
+        rc = _lib.lib().riders_upconv_tc_f32_nhwc(_ptr(x), _ptr(_host_floats(bias_p)), float(slope_p), _ptr(_upconv_tc_weights(w2)),
+                                                  N, h, w, _ptr(_host_floats(bias_a)), float(slope), _ptr(parent), parent.shape[1],
+                                                  _ptr(flag), _stream())
+    _lib.check(rc, "riders_upconv_tc_f32_nhwc")
+    return parent, flag
 
 
 def decoder_tail_tc_half(yh, weight_b, bias_b, weight_head, slope=0.2, sigmoid=False, flag=None):

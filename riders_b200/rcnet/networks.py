@@ -179,6 +179,9 @@ class DecoderBlock(torch.nn.Module):
             self.register_buffer(name, None, persistent=False)
         self.subpixel_taps = SUBPIXEL_TAPS          # 3: 3x3 phase kernels; 2: the equivalent 2x2 phase kernels (4/9 of the MACs)
         self._leaky = act is not None and 'leaky_relu' in act
+        # set by MultiScaleDecoder.forward: may this block's up-convolution run as ONE tcgen05 kernel (ops.upconv_tc_f32, 64 -> 32
+        # channels only), and is its fp16-range flag collected for the caller's sync point instead of being read here
+        self.upconv_tc, self.upconv_defer, self.last_used_upconv_tc = False, False, False
         self.deconv = UpConv2d(cin, cout, init, act, use_batch_norm)
         self.conv = Conv2d(cskip + cout, cout, 3, 1, init, act, use_batch_norm)
 
@@ -233,6 +236,19 @@ class DecoderBlock(torch.nn.Module):
                 and (skip is None or (skip_cl and skip.shape[1] % 4 == 0))):
             # exact 2x block: sub-pixel convolution on the low-resolution map (the resized map never exists),
             # then depth-to-space + bias + LeakyReLU (+ skip concat) in one pass
+            if (self.upconv_tc and taps == 2 and tuple(wsub.shape) == (128, 64, 2, 2) and x.shape[3] <= 26
+                    and torch.backends.cudnn.allow_tf32 and not torch.is_grad_enabled() and ops._is_channels_last(x)):
+                # TF32 flow, 64 -> 32 channels (RC-Net's deconv1): phase convolution + depth-to-space + bias + LeakyReLU + concat
+                # in ONE tcgen05 kernel (csrc/upconv_tc.cu); fp16 operands, the range flag joins the caller's pending guards
+                z, flag = ops.upconv_tc_f32(x, None, 1.0, wsub, up.conv.bias, _LEAK, skip if self.skip_channels > 0 else None)
+                self.last_used_upconv_tc = True
+                if self.upconv_defer:
+                    ops.LoftrOverflow.pending.append((ops.TailOverflow(flag, None), (z,)))
+                elif int(flag.item()):                                 # a value left the fp16 range: the library passes answer
+                    self.last_used_upconv_tc = False
+                    y4 = F.conv2d(x, wsub, None, 1, 1)
+                    z = ops.d2s_bias_act_concat(y4, up.conv.bias, skip if self.skip_channels > 0 else None, _LEAK, taps=taps)
+                return self._tail(z, raw, pad_out)
             y4 = F.conv2d(x, wsub, None, 1, 1)
             z = ops.d2s_bias_act_concat(y4, up.conv.bias, skip if self.skip_channels > 0 else None, _LEAK, taps=taps)
             return self._tail(z, raw, pad_out)
@@ -452,6 +468,7 @@ class MultiScaleDecoder(torch.nn.Module):
         self.tail_impl = os.environ.get('RIDERS_TAIL_IMPL', 'tcgen05')
         self.tail_fp16_map = os.environ.get('RIDERS_TAIL_FP16_MAP', '1') != '0'   # tcgen05 phase convolution writes the tail's fp16 operand map
         self.tail_upconv = os.environ.get('RIDERS_TAIL_UPCONV', '1') != '0'       # csrc/upconv_tc.cu (else the TMA-fed phase convolution)
+        self.tail_upconv_l1 = os.environ.get('RIDERS_UPCONV_L1', '1') != '0'      # the same kernel for the 64 -> 32 block in front of it
         self.force_tail_impl = None                     # set by forward_output_batched for its re-run after a range violation
         self.defer_tail_check = False                   # True: the range flag is read at the caller's own sync point
         self.subconv_tc = os.environ.get('RIDERS_SUBCONV_TC', '0') != '0'      # ops.subpixel_conv_tc instead of cuDNN's 2x2 convolution: opt-in (both sit at the HBM bound of this write-heavy shape, cuDNN 10-15 % ahead)
@@ -497,6 +514,10 @@ class MultiScaleDecoder(torch.nn.Module):
         n = len(skips) - 1
         y, yp = x, None
         raw_bias = raw_slope = None                    # set when y is a RAW convolution output (see want_raw below)
+        for name in self._order:
+            blk = getattr(self, name)
+            blk.upconv_tc = (self.tail_upconv_l1 and self.fused_tail and (self.force_tail_impl or self.tail_impl) == 'tcgen05')
+            blk.upconv_defer = self.defer_tail_check
         for i, name in enumerate(self._order[:-1]):
             # target of the NEXT block: when it is 2n+1 along one axis, this block's bias + activation pass writes the
             # replicate-padded operand of that block's sub-pixel convolution directly (DecoderBlock.forward, pad_out)

@@ -1089,6 +1089,49 @@ def test_upconv_tcgen05_from_the_raw_map_to_the_fp16_operand_map(hw, N, raw):
     assert torch.equal(ops.decoder_upconv_tail_tc(xb, w2, ba, wb, bb, wh, 0.2, bias_p=bp, slope_p=sp), refb)
 
 
+@pytest.mark.parametrize("hw,N,Cs,raw,placed", [((60, 25), 3, 32, False, True), ((8, 5), 1, 32, False, False), ((7, 9), 3, 0, True, False),
+                                                ((13, 26), 2, 8, True, False), ((60, 25), 300, 32, False, True)])
+def test_upconv_tcgen05_float_output_for_the_64_to_32_block(hw, N, Cs, raw, placed):
+    """ops.upconv_tc_f32 (csrc/upconv_tc.cu, the 64 -> 32 channel instance: RC-Net's deconv1): phase convolution on tcgen05 +
+    depth-to-space + bias + LeakyReLU written as float32 into the leading channels of the concat buffer, the skip behind them
+    untouched (placed) or copied.  Against the library passes on fp16-rounded operands: fp32 summation order only; against
+    the pure fp32 passes: operand accuracy.  Several points per persistent CTA (N = 300), w at the limit (26)."""
+    F = torch.nn.functional
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device=DEV).manual_seed(hw[0] + 5 * N)
+    h, w = hw
+    x = torch.randn((N, 64, h, w), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    w2 = torch.randn((128, 64, 2, 2), device=DEV, generator=g) * 0.08
+    bp = torch.randn(64, device=DEV, generator=g) * 0.3 if raw else None
+    sp = 0.2 if raw else 1.0
+    ba = torch.randn(32, device=DEV, generator=g) * 0.3
+    if placed:
+        parent = torch.randn((N, 32 + Cs, 2 * h, 2 * w), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+        skip = parent[:, 32:]
+        assert ops.placed_parent(skip, 32) is not None
+        skip_ref = skip.clone()
+    else:
+        skip = torch.randn((N, Cs, 2 * h, 2 * w), device=DEV, generator=g).contiguous(memory_format=torch.channels_last) if Cs else None
+        skip_ref = skip
+    xa = F.leaky_relu(x + bp.view(1, -1, 1, 1), sp) if raw else x
+    y4 = F.conv2d(_fp16(xa), _fp16(w2), None, 1, 1).contiguous(memory_format=torch.channels_last)
+    ref = ops.d2s_bias_act_concat(y4, ba, skip_ref, 0.2, taps=2)
+    ref32 = ops.d2s_bias_act_concat(F.conv2d(xa, w2, None, 1, 1).contiguous(memory_format=torch.channels_last), ba, skip_ref, 0.2, taps=2)
+    got, flag = ops.upconv_tc_f32(x, bp, sp, w2, ba, 0.2, skip)
+    assert got.shape == ref.shape and ops._is_channels_last(got) and int(flag.item()) == 0
+    if placed:
+        assert got.data_ptr() == parent.data_ptr()
+    sc = float(ref[:, :32].abs().max())
+    np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=2e-5 * sc)
+    if Cs:
+        assert torch.equal(got[:, 32:], skip_ref)
+    assert float((got - ref32).abs().max()) < 3e-3 * sc
+    assert torch.equal(got, ops.upconv_tc_f32(x, bp, sp, w2, ba, 0.2, skip)[0])
+    xb = x.clone()
+    xb[0, 3, 0, 0] = 1.0e6
+    assert int(ops.upconv_tc_f32(xb, bp, sp, w2, ba, 0.2, skip)[1].item()) == 1            # staged value beyond the fp16 range
+
+
 def test_decoder_tail_tcgen05_fp16_range_guard():
     """Activations beyond the fp16 range (a limit neither the fp32 reference nor the TF32 kernel has) raise the device flag of
     riders_decoder_tail_tc_nhwc: ops.decoder_tail_tc then returns the mma.sync TF32 kernel's result (bit-identical to calling

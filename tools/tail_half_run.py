@@ -9,6 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from riders_b200 import ops  # noqa: E402
 
 DEV = torch.device("cuda:0")
+torch.backends.cudnn.benchmark = True
 g = torch.Generator(device=DEV).manual_seed(0)
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 x32 = torch.randn((R, 32, 120, 50), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
@@ -17,9 +18,21 @@ ba, bb = torch.randn(16, device=DEV, generator=g) * 0.1, torch.randn(16, device=
 wb = torch.randn((16, 16, 3, 3), device=DEV, generator=g) * 0.1
 wh = torch.randn((1, 16, 3, 3), device=DEV, generator=g) * 0.1
 bp = torch.randn(32, device=DEV, generator=g) * 0.1
+x64 = torch.randn((R, 64, 60, 25), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+w64 = torch.randn((128, 64, 2, 2), device=DEV, generator=g) * 0.1
+b32 = torch.randn(32, device=DEV, generator=g) * 0.1
+cat64 = torch.randn((R, 64, 120, 50), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+skip32 = cat64[:, 32:]
+
+
+def lib_l1():
+    y4 = torch.nn.functional.conv2d(x64, w64, None, 1, 1)
+    return ops.d2s_bias_act_concat(y4, b32, skip32, 0.2, taps=2)
 for name, fn in (("phase convolution -> fp16 map", lambda: ops.subpixel_conv_tc_half(x32, w2, ba, 0.2)),
                  ("raw map -> upconv -> fp16 map", lambda: ops.upconv_tc_half(x32, bp, 0.2, w2, ba, 0.2)),
                  ("bias_act of the 32-channel map", lambda: ops.bias_act_(x32, bp, 0.2)),
+                 ("deconv1: cuDNN phase conv + d2s", lib_l1),
+                 ("deconv1: upconv_tc_f32", lambda: ops.upconv_tc_f32(x64, None, 1.0, w64, b32, 0.2, skip32)),
                  ("tail on the fp16 map", None)):
     if fn is None:
         yh, _ = ops.subpixel_conv_tc_half(x32, w2, ba, 0.2)

@@ -105,6 +105,34 @@ def case_upconv(N, h, w, seed=0, raw=True):
     return not bool(bad.any())
 
 
+def case_upconv_f32(N, h, w, Cs=32, raw=False, seed=0):
+    """upconv_tc_f32 (64 -> 32 channels, float32 into the concat buffer) against torch on fp16-rounded operands."""
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    x = torch.randn((N, 64, h, w), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    w2 = torch.randn((128, 64, 2, 2), device=DEV, generator=g) * 0.08
+    bp = torch.randn(64, device=DEV, generator=g) * 0.3 if raw else None
+    sp = 0.2 if raw else 1.0
+    ba = torch.randn(32, device=DEV, generator=g) * 0.3
+    skip = torch.randn((N, Cs, 2 * h, 2 * w), device=DEV, generator=g).contiguous(memory_format=torch.channels_last) if Cs else None
+    xa = F.leaky_relu(x + bp.view(1, -1, 1, 1), sp) if raw else x
+    y4 = F.conv2d(h16(xa), h16(w2), None, 1, 1).contiguous(memory_format=torch.channels_last)
+    ref = ops.d2s_bias_act_concat(y4, ba, skip, 0.2, taps=2)
+    got, flag = ops.upconv_tc_f32(x, bp, sp, w2, ba, 0.2, skip)
+    torch.cuda.synchronize()
+    err = (got - ref).abs()
+    sc = float(ref[:, :32].abs().max())
+    bad = err > 1e-4 * sc
+    print("upconv_f32 N=%d h=%d w=%d Cs=%d raw=%d: max err %.3e (scale %.2f) bad fraction %.5f flag %d shape %s" %
+          (N, h, w, Cs, raw, float(err.max()), sc, float(bad.float().mean()), int(flag.item()), tuple(got.shape)), flush=True)
+    if bool(bad.any()):
+        print("   first bad [n, c, Y, X]:", bad.nonzero()[:8].tolist(), flush=True)
+        rows = bad.any(dim=3).any(dim=1).any(dim=0).nonzero().flatten().tolist()
+        cols = bad.any(dim=2).any(dim=1).any(dim=0).nonzero().flatten().tolist()
+        chans = bad.any(dim=3).any(dim=2).any(dim=0).nonzero().flatten().tolist()
+        print("   bad rows", rows[:40], "cols", cols[:40], "channels", chans[:40], flush=True)
+    return not bool(bad.any())
+
+
 if __name__ == "__main__":
     ok = True
     for N, h, w, taps in ((1, 8, 5, 3), (3, 7, 9, 2), (2, 13, 30, 3), (3, 120, 50, 2), (2, 40, 70, 3), (40, 120, 50, 2)):
@@ -113,4 +141,6 @@ if __name__ == "__main__":
         ok = case_half(N, h, w) and ok
     for N, h, w, raw in ((1, 8, 5, True), (3, 7, 9, False), (2, 13, 30, True), (3, 120, 50, True), (200, 120, 50, True), (2, 31, 54, True)):
         ok = case_upconv(N, h, w, raw=raw) and ok
+    for N, h, w, Cs, raw in ((1, 8, 5, 32, False), (3, 7, 9, 0, True), (2, 13, 26, 8, True), (3, 60, 25, 32, False), (300, 60, 25, 32, False)):
+        ok = case_upconv_f32(N, h, w, Cs, raw) and ok
     print("ALL OK" if ok else "MISMATCH", flush=True)
