@@ -111,55 +111,64 @@ upconv_tc_kernel(const __grid_constant__ Params P) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) bp[e] = P.bias_p[ch * 8 + e];
         const float sp = P.slope_p;
-        uint32_t nb = 0;                                   // batches staged so far (ring position)
-        for (int n = blockIdx.x; n < P.N; n += gridDim.x) {
+        // (point, batch) items of this CTA in order; item it = point blockIdx.x + (it / nbatch) gridDim.x, batch it % nbatch
+        const int my_points = (P.N - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int items = my_points * nbatch;
+        auto prefetch_item = [&](int it) {                 // the batch's input rows are contiguous in memory: one bulk L2 prefetch
+            if (it >= items) return;
+            const int n = blockIdx.x + (it / nbatch) * gridDim.x, bi = it % nbatch;
+            const int r0 = max(bi * BROWS - 1, 0), r1 = min(bi * BROWS - 1 + XROWS, h);
+            if (r1 > r0)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+                             ::"l"(P.x + ((size_t)n * h + r0) * w * (CIN / 4)), "r"((r1 - r0) * w * CIN * 4) : "memory");
+        };
+        constexpr int PFD = 3;                             // prefetch distance in batches
+        if (tid == 0)
+            for (int it = 0; it < PFD; ++it) prefetch_item(it);
+        constexpr int DEPTH = 4;                           // input rows in flight per thread (registers)
+        for (int it = 0; it < items; ++it) {
+            const int n = blockIdx.x + (it / nbatch) * gridDim.x, bi = it % nbatch;
             const float4* xn = P.x + ((size_t)n * h * w + px) * (CIN / 4) + ch * 2;
-            for (int bi = 0; bi < nbatch; ++bi, ++nb) {
-                const int buf = nb % NBUF;
-                const int i0 = bi * BROWS - 1;             // first input row of the batch (row -1 = the padding)
-                if (lane == 0 && warp == 0) {              // L2 prefetch of the next batch's rows (contiguous in memory)
-                    const int r0 = max(i0 + BROWS, 0), r1 = min(i0 + BROWS + XROWS, h);
-                    if (bi + 1 < nbatch && r1 > r0)
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
-                                     ::"l"(P.x + ((size_t)n * h + r0) * w * (CIN / 4)), "r"((r1 - r0) * w * CIN * 4) : "memory");
+            const int buf = it % NBUF;
+            const int i0 = bi * BROWS - 1;                 // first input row of the batch (row -1 = the padding)
+            if (tid == 0) prefetch_item(it + PFD);
+            uint8_t* dst = xb + buf * BATCH_BYTES + ch * PLANE + (1 + px) * 16;
+            float4 v[DEPTH][2];
+            auto load = [&](int r, float4 (&t)[2]) {
+                const int row = i0 + r;
+                if (active && (unsigned)row < (unsigned)h) {
+                    const float4* g = xn + (size_t)row * w * (CIN / 4);
+                    t[0] = __ldcs(g); t[1] = __ldcs(g + 1);
+                } else {
+                    t[0] = make_float4(0.f, 0.f, 0.f, 0.f); t[1] = t[0];
                 }
-                mbar_wait_sleep(bar(B_BFREE + buf), ((nb / NBUF) & 1) ^ 1, 100);
-                uint8_t* dst = xb + buf * BATCH_BYTES + ch * PLANE + (1 + px) * 16;
-                // three rows in flight
-                float4 v[3][2];
-                auto load = [&](int r, float4 (&t)[2]) {
-                    const int row = i0 + r;
-                    if (active && (unsigned)row < (unsigned)h) {
-                        const float4* g = xn + (size_t)row * w * (CIN / 4);
-                        t[0] = __ldcs(g); t[1] = __ldcs(g + 1);
-                    } else {
-                        t[0] = make_float4(0.f, 0.f, 0.f, 0.f); t[1] = t[0];
-                    }
-                };
-                auto stage = [&](int r, const float4 (&t)[2]) {
-                    const bool ok = active && (unsigned)(i0 + r) < (unsigned)h;
-                    const float a[8] = {t[0].x, t[0].y, t[0].z, t[0].w, t[1].x, t[1].y, t[1].z, t[1].w};
-                    uint32_t hv[4];
+            };
+            auto stage = [&](int r, const float4 (&t)[2]) {
+                const bool ok = active && (unsigned)(i0 + r) < (unsigned)h;
+                const float a[8] = {t[0].x, t[0].y, t[0].z, t[0].w, t[1].x, t[1].y, t[1].z, t[1].w};
+                uint32_t hv[4];
 #pragma unroll
-                    for (int e = 0; e < 8; e += 2) {
-                        float v0 = a[e] + bp[e], v1 = a[e + 1] + bp[e + 1];
-                        v0 = fmaxf(v0, v0 * sp); v1 = fmaxf(v1, v1 * sp);
-                        const __half2 hh = __floats2half2_rn(v0, v1);
-                        hv[e >> 1] = ok ? h2_bits(hh) : 0u;               // zero rows / columns: the convolution pads the ACTIVATED map
-                        if (ok) amax2 = __hmax2_nan(amax2, __habs2(hh));
-                    }
-                    if (active) *reinterpret_cast<uint4*>(dst + r * PITCH * 16) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
-                };
-                load(0, v[0]); load(1, v[1]);
-#pragma unroll
-                for (int r = 0; r < XROWS; ++r) {
-                    if (r + 2 < XROWS) load(r + 2, v[(r + 2) % 3]);
-                    stage(r, v[r % 3]);
+                for (int e = 0; e < 8; e += 2) {
+                    float v0 = a[e] + bp[e], v1 = a[e + 1] + bp[e + 1];
+                    v0 = fmaxf(v0, v0 * sp); v1 = fmaxf(v1, v1 * sp);
+                    const __half2 hh = __floats2half2_rn(v0, v1);
+                    hv[e >> 1] = ok ? h2_bits(hh) : 0u;               // zero rows / columns: the convolution pads the ACTIVATED map
+                    if (ok) amax2 = __hmax2_nan(amax2, __habs2(hh));
                 }
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(B_BFULL + buf));
+                if (active) *reinterpret_cast<uint4*>(dst + r * PITCH * 16) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+            };
+            // the first rows are requested BEFORE the wait for the buffer (they only need registers)
+#pragma unroll
+            for (int r = 0; r < DEPTH - 1; ++r) load(r, v[r]);
+            mbar_wait_sleep(bar(B_BFREE + buf), ((it / NBUF) & 1) ^ 1, 100);
+#pragma unroll
+            for (int r = 0; r < XROWS; ++r) {
+                if (r + DEPTH - 1 < XROWS) load(r + DEPTH - 1, v[(r + DEPTH - 1) % DEPTH]);
+                stage(r, v[r % DEPTH]);
             }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(B_BFULL + buf));
         }
     } else if (warp == W_MMA) {
         // ===================== MMA issuer =====================
