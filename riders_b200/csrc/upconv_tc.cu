@@ -46,7 +46,9 @@ template <int CIN_, int COUT_, int PITCH_, bool HALF_OUT_> struct Cfg {
     static constexpr int PLANE = PLANE_POS * 16;
     static constexpr int BATCH_BYTES = NPLANES * PLANE;
     static constexpr int W_BYTES = 4 * KSTEPS * NOUT * 32;                // 4 taps x K steps x (NOUT rows x 16 fp16)
-    static constexpr int STAGE_BYTES = HALF_OUT ? 2 * RPT * 2 * 2 * (PITCH - 1) * 16 : 0;   // 2 RPT output rows x 2 planes x W pixels x 16 B
+    // epilogue staging per group.  fp16 out: 2 RPT output rows x 2 planes x W pixels x 16 B (bulk-stored row by row);
+    // float out: per warp 32 pixels x 128 B (+ 16 B pad) for the transposing store
+    static constexpr int STAGE_BYTES = HALF_OUT ? 2 * RPT * 2 * 2 * (PITCH - 1) * 16 : 4 * 32 * 144;
     static constexpr int SMEM_BYTES = NBUF * BATCH_BYTES + W_BYTES + EPI_GROUPS * STAGE_BYTES + NBARS * 8 + 16;
     static constexpr uint32_t TMEM_COLS = NACC * NOUT;
     static_assert(BROWS % RPT == 0 && RPT * PITCH <= 128 && XROWS * PITCH <= PLANE_POS && NPLANES * (PITCH - 2) <= LOADER_WARPS * 32,
@@ -274,6 +276,10 @@ upconv_tc_kernel(const __grid_constant__ Params P) {
                         // float32 channels-last out: phase ab = 32 accumulator columns = the COUT channels of output pixel
                         // (2 I - a, 2 J - b): + bias_a, LeakyReLU, eight 16-byte stores (the pixel's 128 contiguous bytes)
                         static_assert(C::HALF_OUT || C::COUT == 32, "float32 epilogue: one TMEM_LD32 per phase");
+                        // The pixels of a warp's lanes are 512 B apart in memory; storing them lane by lane is 32 partial sectors per
+                        // instruction.  Each lane parks its pixel in a per-warp staging row, then the warp writes 4 whole pixels per
+                        // instruction (8 lanes x 16 B = one pixel's 128 contiguous bytes), addresses passed by shuffle.
+                        uint8_t* wst = stage + (warp & 3) * (32 * 144);
 #pragma unroll
                         for (int ab = 0; ab < 4; ++ab) {
                             uint32_t r[32];
@@ -286,17 +292,25 @@ upconv_tc_kernel(const __grid_constant__ Params P) {
                             }
                             const int a = ab >> 1, b = ab & 1;
                             const int Y = 2 * I - a, X = 2 * J - b;
-                            if (lane_ok && (unsigned)Y < (unsigned)H && (unsigned)X < (unsigned)W) {
-                                float4* o = reinterpret_cast<float4*>(P.out + (((size_t)n * H + Y) * W + X) * (size_t)P.ctot);
+                            const bool ok = lane_ok && (unsigned)Y < (unsigned)H && (unsigned)X < (unsigned)W;
+                            const unsigned long long gp = ok ? (unsigned long long)(P.out + (((size_t)n * H + Y) * W + X) * (size_t)P.ctot) : 0ull;
+                            __syncwarp();                                  // the previous phase has been read out of the staging rows
 #pragma unroll
-                                for (int c = 0; c < 32; c += 4) {
-                                    float4 q;
-                                    q.x = __uint_as_float(r[c]) + P.bias_a[c];         q.y = __uint_as_float(r[c + 1]) + P.bias_a[c + 1];
-                                    q.z = __uint_as_float(r[c + 2]) + P.bias_a[c + 2]; q.w = __uint_as_float(r[c + 3]) + P.bias_a[c + 3];
-                                    q.x = fmaxf(q.x, q.x * slope); q.y = fmaxf(q.y, q.y * slope);
-                                    q.z = fmaxf(q.z, q.z * slope); q.w = fmaxf(q.w, q.w * slope);
-                                    o[c >> 2] = q;
-                                }
+                            for (int c = 0; c < 32; c += 4) {
+                                float4 q;
+                                q.x = __uint_as_float(r[c]) + P.bias_a[c];         q.y = __uint_as_float(r[c + 1]) + P.bias_a[c + 1];
+                                q.z = __uint_as_float(r[c + 2]) + P.bias_a[c + 2]; q.w = __uint_as_float(r[c + 3]) + P.bias_a[c + 3];
+                                q.x = fmaxf(q.x, q.x * slope); q.y = fmaxf(q.y, q.y * slope);
+                                q.z = fmaxf(q.z, q.z * slope); q.w = fmaxf(q.w, q.w * slope);
+                                *reinterpret_cast<float4*>(wst + lane * 144 + c * 4) = q;
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) {
+                                const int src = it * 4 + (lane >> 3);
+                                const unsigned long long g = __shfl_sync(0xffffffffu, gp, src);
+                                const float4 q = *reinterpret_cast<const float4*>(wst + src * 144 + (lane & 7) * 16);
+                                if (g) reinterpret_cast<float4*>(g)[lane & 7] = q;
                             }
                         }
                     }
