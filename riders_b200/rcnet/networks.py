@@ -218,9 +218,18 @@ class DecoderBlock(torch.nn.Module):
             return yp[:, :, pad_out[0]:, pad_out[1]:], yp
         return self.conv(z)
 
-    def forward(self, x, skip=None, shape=None, raw=False, xp=None, pad_out=None):
+    def upconv_tc_ok(self, x_shape, target):
+        """Will ``forward`` run this block's up-convolution as ONE tcgen05 kernel (ops.upconv_tc_f32) for an input of ``x_shape``
+        and the target size ``target``?  (64 -> 32 channels, exact 2x, inference, TF32 flow; decided by MultiScaleDecoder.)"""
+        return (self.upconv_tc and self.subpixel_taps == 2 and self._w2 is not None and tuple(self._w2.shape) == (128, 64, 2, 2)
+                and x_shape[1] == 64 and x_shape[3] <= 26 and tuple(target) == (2 * x_shape[2], 2 * x_shape[3])
+                and torch.backends.cudnn.allow_tf32 and not torch.is_grad_enabled())
+
+    def forward(self, x, skip=None, shape=None, raw=False, xp=None, pad_out=None, x_act=None):
         """``raw=True`` (inference fast path only): return (conv output without bias/activation, bias, slope)
         of the block's last convolution so that the decoder head can fuse them.
+        ``x_act=(bias, slope)``: ``x`` is the RAW output of the previous block's convolution (its bias + LeakyReLU are applied by
+        ops.upconv_tc_f32 while it stages its operand, or here in one pass when that kernel does not take this call).
         ``pad_out=(sy, sx)`` (fast path only, ignored otherwise): the NEXT block's target is 2n+1 along one axis, so return
         ``(y, y_padded)`` with ``y = y_padded[:, :, sy:, sx:]``; ``xp``: that padded map handed to the next block."""
         if skip is not None:
@@ -230,23 +239,35 @@ class DecoderBlock(torch.nn.Module):
         up = self.deconv.conv
         taps = 2 if (self.subpixel_taps == 2 and self._w2 is not None) else 3
         wsub = self._w2 if taps == 2 else self._w4
+        use_upconv = (self.upconv_tc_ok(x.shape, shape) and ops._is_channels_last(x) and x.is_cuda and x.dtype == torch.float32
+                      and (skip is None or skip.shape[1] % 4 == 0))
+
+        def activate(t):
+            if x_act is None or (x_act[0] is None and float(x_act[1]) == 1.0):
+                return t
+            if ops._is_channels_last(t) and t.is_cuda:
+                return ops.bias_act_(t, x_act[0], x_act[1])
+            return F.leaky_relu(t if x_act[0] is None else t + x_act[0].view(1, -1, 1, 1), float(x_act[1]))
+        if x_act is not None and not use_upconv:
+            x, x_act = activate(x), None
         # a skip gathered straight into this block's concat buffer (ops.placed_skip_buffers) counts as channels-last
         skip_cl = skip is not None and (ops._is_channels_last(skip) or ops.placed_parent(skip, up.conv.out_channels) is not None)
         if (self._w4 is not None and tuple(shape) == (2 * x.shape[2], 2 * x.shape[3]) and up.fast_ok(x)
                 and (skip is None or (skip_cl and skip.shape[1] % 4 == 0))):
             # exact 2x block: sub-pixel convolution on the low-resolution map (the resized map never exists),
             # then depth-to-space + bias + LeakyReLU (+ skip concat) in one pass
-            if (self.upconv_tc and taps == 2 and tuple(wsub.shape) == (128, 64, 2, 2) and x.shape[3] <= 26
-                    and torch.backends.cudnn.allow_tf32 and not torch.is_grad_enabled() and ops._is_channels_last(x)):
-                # TF32 flow, 64 -> 32 channels (RC-Net's deconv1): phase convolution + depth-to-space + bias + LeakyReLU + concat
-                # in ONE tcgen05 kernel (csrc/upconv_tc.cu); fp16 operands, the range flag joins the caller's pending guards
-                z, flag = ops.upconv_tc_f32(x, None, 1.0, wsub, up.conv.bias, _LEAK, skip if self.skip_channels > 0 else None)
+            if use_upconv:
+                # TF32 flow, 64 -> 32 channels (RC-Net's deconv1): (previous bias + LeakyReLU +) phase convolution + depth-to-space
+                # + bias + LeakyReLU + concat in ONE tcgen05 kernel (csrc/upconv_tc.cu); fp16 operands, the range flag joins
+                # the caller's pending guards
+                xb, xs = (None, 1.0) if x_act is None else x_act
+                z, flag = ops.upconv_tc_f32(x, xb, xs, wsub, up.conv.bias, _LEAK, skip if self.skip_channels > 0 else None)
                 self.last_used_upconv_tc = True
                 if self.upconv_defer:
                     ops.LoftrOverflow.pending.append((ops.TailOverflow(flag, None), (z,)))
                 elif int(flag.item()):                                 # a value left the fp16 range: the library passes answer
                     self.last_used_upconv_tc = False
-                    y4 = F.conv2d(x, wsub, None, 1, 1)
+                    y4 = F.conv2d(activate(x), wsub, None, 1, 1)
                     z = ops.d2s_bias_act_concat(y4, up.conv.bias, skip if self.skip_channels > 0 else None, _LEAK, taps=taps)
                 return self._tail(z, raw, pad_out)
             y4 = F.conv2d(x, wsub, None, 1, 1)
@@ -534,7 +555,14 @@ class MultiScaleDecoder(torch.nn.Module):
             want_raw = (i == len(self._order) - 2 and pad_out is None and getattr(self, name).conv._fused_slope is not None
                         and (self._sub_ok(getattr(self, self._order[-1]), shape)
                              or self._upconv_ok(getattr(self, self._order[-1]), shape)))
-            out = getattr(self, name)(y, skips[n], xp=yp, pad_out=pad_out, raw=want_raw)
+            # ... and so does the block in front of a block whose up-convolution runs as ops.upconv_tc_f32
+            if (not want_raw and i < len(self._order) - 2 and pad_out is None and tgt is not None
+                    and getattr(self, name).conv._fused_slope is not None and 0.0 <= getattr(self, name).conv._fused_slope <= 1.0
+                    and nxt.upconv_tc_ok((y.shape[0], getattr(self, name).conv.conv.out_channels, cur[0], cur[1]), tgt)):
+                want_raw = True
+            x_act = None if raw_slope is None else (raw_bias, raw_slope)
+            out = getattr(self, name)(y, skips[n], xp=yp, pad_out=pad_out, raw=want_raw, x_act=x_act)
+            raw_bias = raw_slope = None
             if want_raw:
                 y, raw_bias, raw_slope = out
                 yp = None
