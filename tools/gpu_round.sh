@@ -51,7 +51,7 @@ for MODE in "$@"; do
       timeout -s KILL 600 python tools/train_profile.py > $OUT/train_profile.txt 2> $OUT/train_profile.err; echo "trainprof rc=$?" | tee -a $OUT/status.txt
       head -32 $OUT/train_profile.txt; tail -3 $OUT/train_profile.err ;;
     ncuall)
-      timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k "regex:loftr_layer_tc|lsq_|extract_knots|delaunay_star|raster_kernel|confidence_reduce|roi_gather_tma|decoder_tail_tc|subpixel_conv_tc" -c 48 -f -o $OUT/prof_r02_hotpath \
+      timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k "regex:loftr_layer_tc|lsq_|extract_knots|delaunay_star|raster_kernel|confidence_reduce|roi_gather_tma|decoder_tail_tc|upconv_tc" -c 48 -f -o $OUT/prof_r02_hotpath \
           python bench.py --steps 1 --profile > $OUT/ncu_all.log 2>&1; echo "ncu-all rc=$?" | tee -a $OUT/status.txt
       ncu -i $OUT/prof_r02_hotpath.ncu-rep --page raw --csv > $OUT/prof_r02_hotpath_raw.csv 2>/dev/null
       python tools/ncu_summary.py $OUT/prof_r02_hotpath_raw.csv > $OUT/ncu_summary_hotpath.txt 2>&1; head -60 $OUT/ncu_summary_hotpath.txt

@@ -27,7 +27,8 @@ for name, us in rows:
     agg[short] = (c + 1, t + us)
 total = sum(t for _, t in agg.values())
 print("launches %d   total %.1f us" % (len(rows), total))
-ours = sum(t for k, (c, t) in agg.items() if "riders" in k or k.startswith(("tail::", "tc::")))   # ncu drops the outer namespace of nested ones
+OURS = ("tail::", "tc::", "tailtc::", "upconv::", "spctc::", "train::")                  # ncu drops the outer namespace of nested ones
+ours = sum(t for k, (c, t) in agg.items() if "riders" in k or any(ns in k for ns in OURS))
 print("our kernels (namespace riders): %.1f us = %.1f %% of device time" % (ours, 100 * ours / max(total, 1e-9)))
 print("%-92s %7s %12s %7s" % ("kernel", "count", "total_us", "share"))
 for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
