@@ -94,7 +94,7 @@ for MODE in "$@"; do
       python tools/summarize_launches.py $OUT/launches.csv prologue_flag > $OUT/launches_summary.txt 2>&1; head -40 $OUT/launches_summary.txt
       gzip -f $OUT/launches.csv ;;
     traffic)
-      timeout -s KILL 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k 'regex:roi_gather|loftr_|confidence_reduce|lsq_|extract_knots|delaunay|interp_fill|scaffold|upsample_nearest|bias_act|leaky_concat|d2s_|conv3x3_head|metrics_|l1_|decoder_tail|subpixel_conv|prologue' --csv --log-file $OUT/launches_traffic.csv \
+      timeout -s KILL 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k 'regex:roi_gather|loftr_|confidence_reduce|lsq_|extract_knots|delaunay|interp_fill|scaffold|upsample_nearest|bias_act|leaky_concat|d2s_|conv3x3_head|metrics_|l1_|decoder_tail|subpixel_conv|upconv_tc|prologue' --csv --log-file $OUT/launches_traffic.csv \
           python bench.py --steps 1 --profile > $OUT/bench_under_ncu_traffic.log 2>&1; echo "ncu-traffic rc=$?" | tee -a $OUT/status.txt
       python tools/traffic_from_ncu.py $OUT/launches_traffic.csv > $OUT/traffic.json 2> $OUT/traffic.err; cat $OUT/traffic.json; tail -3 $OUT/traffic.err
       gzip -f $OUT/launches_traffic.csv ;;

@@ -13,7 +13,8 @@ STAGE = {  # kernel substring -> bench stage (ops.StageTimer span name); calls p
     "compact_valid": "l1_scale_align",
     "upsample_nearest": "upsample_nearest", "bias_act_nhwc": "bias_act", "bias_act_generic": "bias_act",
     "bias_leaky_concat": "leaky_concat", "leaky_concat_nhwc": "leaky_concat", "d2s_bias_act": "d2s_bias_act_concat",
-    "conv3x3_head": "conv3x3_head", "decoder_tail": "decoder_tail", "bias_act_pad": "bias_act",
+    "conv3x3_head": "conv3x3_head", "decoder_tail": "decoder_tail", "bias_act_pad": "bias_act", "upconv_tc": "upconv",
+    "subpixel_conv": "subpixel_conv",
 }
 CALLS = {"roi_gather": 5, "loftr_transformer": 1, "confidence_reduce": 1, "lsq_align": 1, "extract_knots": 1,
          "interp_linear": 1, "l1_scale_align": 1, "scale_scaffold": 1}
