@@ -392,6 +392,14 @@ int riders_upconv_tc_half_nhwc(const float* x, const float* bias_p_host, float s
 int riders_upconv_tc_f32_nhwc(const float* x, const float* bias_p_host, float slope_p, const void* w_pack,
                               int N, int h, int w, const float* bias_a_host, float slope, float* out, int ctot,
                               int* status, void* stream);
+/* The 3x3 convolution between those two blocks (deconv1.conv of RC-Net's decoder: 64 -> 32 channels at 120 x 50, stride 1,
+ * padding 1) on the same kernel template: out (N, h, w, ctot >= 32) float32 = act(conv3x3(act_p(x + bias_p), W) + bias) with
+ * slope = 1 and bias_host = NULL for the RAW output (what riders_upconv_tc_half_nhwc takes).  x (N, 64, h, w <= 54) channels-last
+ * fp32; w_pack: 36 KB fp16, [tap 3 ky + kx][K step][n / 8][k / 8][n % 8][k % 8] of W[n][16 kh + k][ky][kx]
+ * (ops._conv3x3_tc_weights).  status: raised when a staged input value leaves the fp16 range.                                  */
+int riders_conv3x3_tc_f32_nhwc(const float* x, const float* bias_p_host, float slope_p, const void* w_pack,
+                               int N, int h, int w, const float* bias_host, float slope, float* out, int ctot,
+                               int* status, void* stream);
 /* Sub-pixel phase convolution of the last decoder block in its 2x2-tap form (32 -> 4 x 16 channels), TF32, with the bias
  * + LeakyReLU of the convolution that produced x fused into the operand load (deconv1.conv -> deconv0.deconv of
  * MultiScaleDecoder, RCNet/networks.py:678-779): y4 (N, 64, h+1, w+1) = conv2x2(act(x + bias), W2, padding 1), x (N, 32, h, w)

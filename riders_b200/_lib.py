@@ -78,6 +78,7 @@ SIGNATURES = {
     "riders_decoder_tail_tc_half_nhwc": (ci, [vp, ci, ci, ci, vp, vp, cf, ci, vp, vp, vp]),
     "riders_upconv_tc_half_nhwc": (ci, [vp, vp, cf, vp, ci, ci, ci, vp, cf, vp, vp, vp]),
     "riders_upconv_tc_f32_nhwc": (ci, [vp, vp, cf, vp, ci, ci, ci, vp, cf, vp, ci, vp, vp]),
+    "riders_conv3x3_tc_f32_nhwc": (ci, [vp, vp, cf, vp, ci, ci, ci, vp, cf, vp, ci, vp, vp]),
     "riders_subpixel_conv_act_nhwc": (ci, [vp, vp, cf, vp, ci, ci, ci, vp, vp]),
     "riders_subpixel_conv_tc_nhwc": (ci, [vp, vp, ci, ci, ci, vp, vp]),
     "riders_subpixel_conv_smem_bytes": (C.c_size_t, [ci]),

@@ -28,7 +28,7 @@ namespace riders {
 namespace upconv {
 using namespace tcg;
 
-constexpr int BROWS = 8, XROWS = BROWS + 1;           // y4 rows / input rows per batch
+constexpr int BROWS = 8;                              // output (y4) rows per batch
 constexpr int NBUF = 2, NACC = 4;
 constexpr int LOADER_WARPS = 8, W_MMA = 8, W_EPI = 12, EPI_GROUPS = 2, THREADS = (W_EPI + 4 * EPI_GROUPS) * 32;   // warps 9..11 idle
 constexpr int B_BFULL = 0, B_BFREE = B_BFULL + NBUF, B_DFULL = B_BFREE + NBUF, B_DFREE = B_DFULL + NACC, NBARS = B_DFREE + NACC;
@@ -37,23 +37,29 @@ constexpr int B_BFULL = 0, B_BFREE = B_BFULL + NBUF, B_DFULL = B_BFREE + NBUF, B
 // map out (the tail's input).  <64, 32, 28, false>: the block before it (deconv1: 60 x 25 -> 120 x 50), four y4 rows of <= 27
 // positions per tile, float32 channels-last out, written into the first COUT channels of the block's concat buffer (the skip
 // is already in place behind them) - there it replaces the library phase convolution AND the depth-to-space pass.
-template <int CIN_, int COUT_, int PITCH_, bool HALF_OUT_> struct Cfg {
-    static constexpr int CIN = CIN_, COUT = COUT_, NOUT = 4 * COUT_, PITCH = PITCH_;
-    static constexpr bool HALF_OUT = HALF_OUT_;
-    static constexpr int RPT = 112 / PITCH;                               // y4 rows per M = 128 tile
+// <64, 32, 56, false, K3 = true>: the 3x3 convolution between the two (deconv1.conv, 64 -> 32 channels at 120 x 50), the largest
+// library convolution of the step: same staging and views with nine taps ((dy, dx) = a row and a pixel shift), one output
+// row pair per tile, N = 32, raw float32 out (its consumer - the first instance - applies the bias and the activation).
+template <int CIN_, int COUT_, int PITCH_, bool HALF_OUT_, bool K3_ = false> struct Cfg {
+    static constexpr int CIN = CIN_, COUT = COUT_, PITCH = PITCH_;
+    static constexpr bool HALF_OUT = HALF_OUT_, K3 = K3_;
+    static constexpr int NOUT = K3 ? COUT_ : 4 * COUT_;                   // 3x3: plain output channels; 2x2: four phases
+    static constexpr int TAPS = K3 ? 9 : 4, TAPW = K3 ? 3 : 2;            // taps, taps per kernel row
+    static constexpr int XROWS = BROWS + TAPW - 1;                        // input rows staged per batch of BROWS output (y4) rows
+    static constexpr int RPT = 112 / PITCH;                               // output (y4) rows per M = 128 tile
     static constexpr int NPLANES = CIN / 8, KSTEPS = CIN / 16;
-    static constexpr int PLANE_POS = (((BROWS - RPT + 1) * PITCH + 1 + 128) + 7) / 8 * 8;   // staged rows + the reach of the last view
+    static constexpr int PLANE_POS = (((BROWS - RPT + TAPW - 1) * PITCH + (TAPW - 1) + 128) + 7) / 8 * 8;   // staged rows + the reach of the last view
     static constexpr int PLANE = PLANE_POS * 16;
     static constexpr int BATCH_BYTES = NPLANES * PLANE;
-    static constexpr int W_BYTES = 4 * KSTEPS * NOUT * 32;                // 4 taps x K steps x (NOUT rows x 16 fp16)
+    static constexpr int W_BYTES = TAPS * KSTEPS * NOUT * 32;             // taps x K steps x (NOUT rows x 16 fp16)
     // epilogue staging per group.  fp16 out: 2 RPT output rows x 2 planes x W pixels x 16 B (bulk-stored row by row);
     // float out: per warp 32 pixels x 128 B (+ 16 B pad) for the transposing store
     static constexpr int STAGE_BYTES = HALF_OUT ? 2 * RPT * 2 * 2 * (PITCH - 1) * 16 : 4 * 32 * 144;
     static constexpr int SMEM_BYTES = NBUF * BATCH_BYTES + W_BYTES + EPI_GROUPS * STAGE_BYTES + NBARS * 8 + 16;
     static constexpr uint32_t TMEM_COLS = NACC * NOUT;
-    static_assert(BROWS % RPT == 0 && RPT * PITCH <= 128 && XROWS * PITCH <= PLANE_POS && NPLANES * (PITCH - 2) <= LOADER_WARPS * 32,
+    static_assert(BROWS % RPT == 0 && RPT * PITCH <= 128 && XROWS * PITCH <= PLANE_POS && NPLANES * (PITCH - 2) <= 2 * LOADER_WARPS * 32,
                   "tile geometry");
-    static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
+    static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
 };
 
 struct Params {
@@ -77,6 +83,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 upconv_tc_kernel(const __grid_constant__ Params P) {
     constexpr int CIN = C::CIN, NOUT = C::NOUT, PITCH = C::PITCH, RPT = C::RPT, NPLANES = C::NPLANES, KSTEPS = C::KSTEPS;
     constexpr int PLANE = C::PLANE, BATCH_BYTES = C::BATCH_BYTES, W_BYTES = C::W_BYTES, STAGE_BYTES = C::STAGE_BYTES;
+    constexpr int XROWS = C::XROWS, TAPS = C::TAPS, TAPW = C::TAPW;
+    constexpr bool K3 = C::K3;
     constexpr uint32_t TMEM_COLS = C::TMEM_COLS;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* xb = smem;                                   // [NBUF][NPLANES][PLANE_POS] x 16 B
@@ -87,7 +95,8 @@ upconv_tc_kernel(const __grid_constant__ Params P) {
     auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h = P.h, w = P.w, H = 2 * h, W = 2 * w;
-    const int nbatch = (h + 1 + BROWS - 1) / BROWS;       // y4 has h + 1 rows
+    const int orows = K3 ? h : h + 1;                     // output rows of the GEMM: y4 has h + 1 rows, the 3x3 output h
+    const int nbatch = (orows + BROWS - 1) / BROWS;
 
     for (int i = tid; i < NBUF * BATCH_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(xb)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = tid; i < W_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(ws)[i] = __ldg(P.w_pack + i);
@@ -107,8 +116,9 @@ upconv_tc_kernel(const __grid_constant__ Params P) {
     if (warp < LOADER_WARPS) {
         // ===================== input rows: global -> + bias_p, LeakyReLU -> fp16 -> plane layout =====================
         // thread = (pixel, 8-channel chunk): a warp reads 8 pixels x 128 B (contiguous) and stores 8 pixels x 4 planes
+        // (wide 64-channel rows - 54 pixels x 8 chunks - take two passes per thread)
+        constexpr int PASSES = (NPLANES * (PITCH - 2) + LOADER_WARPS * 32 - 1) / (LOADER_WARPS * 32), PXSTEP = LOADER_WARPS * 32 / NPLANES;
         const int px = tid / NPLANES, ch = tid % NPLANES;
-        const bool active = px < w;
         float bp[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) bp[e] = P.bias_p[ch * 8 + e];
@@ -127,7 +137,7 @@ upconv_tc_kernel(const __grid_constant__ Params P) {
         constexpr int PFD = 3;                             // prefetch distance in batches
         if (tid == 0)
             for (int it = 0; it < PFD; ++it) prefetch_item(it);
-        constexpr int DEPTH = 4;                           // input rows in flight per thread (registers)
+        constexpr int DEPTH = PASSES == 1 ? 4 : 3;         // input rows in flight per thread (registers)
         for (int it = 0; it < items; ++it) {
             const int n = blockIdx.x + (it / nbatch) * gridDim.x, bi = it % nbatch;
             const float4* xn = P.x + ((size_t)n * h * w + px) * (CIN / 4) + ch * 2;
@@ -135,29 +145,36 @@ upconv_tc_kernel(const __grid_constant__ Params P) {
             const int i0 = bi * BROWS - 1;                 // first input row of the batch (row -1 = the padding)
             if (tid == 0) prefetch_item(it + PFD);
             uint8_t* dst = xb + buf * BATCH_BYTES + ch * PLANE + (1 + px) * 16;
-            float4 v[DEPTH][2];
-            auto load = [&](int r, float4 (&t)[2]) {
+            float4 v[DEPTH][2 * PASSES];
+            auto load = [&](int r, float4 (&t)[2 * PASSES]) {
                 const int row = i0 + r;
-                if (active && (unsigned)row < (unsigned)h) {
-                    const float4* g = xn + (size_t)row * w * (CIN / 4);
-                    t[0] = __ldcs(g); t[1] = __ldcs(g + 1);
-                } else {
-                    t[0] = make_float4(0.f, 0.f, 0.f, 0.f); t[1] = t[0];
+#pragma unroll
+                for (int q = 0; q < PASSES; ++q) {
+                    if (px + q * PXSTEP < w && (unsigned)row < (unsigned)h) {
+                        const float4* g = xn + ((size_t)row * w + q * PXSTEP) * (CIN / 4);
+                        t[2 * q] = __ldcs(g); t[2 * q + 1] = __ldcs(g + 1);
+                    } else {
+                        t[2 * q] = make_float4(0.f, 0.f, 0.f, 0.f); t[2 * q + 1] = t[2 * q];
+                    }
                 }
             };
-            auto stage = [&](int r, const float4 (&t)[2]) {
-                const bool ok = active && (unsigned)(i0 + r) < (unsigned)h;
-                const float a[8] = {t[0].x, t[0].y, t[0].z, t[0].w, t[1].x, t[1].y, t[1].z, t[1].w};
-                uint32_t hv[4];
+            auto stage = [&](int r, const float4 (&t)[2 * PASSES]) {
 #pragma unroll
-                for (int e = 0; e < 8; e += 2) {
-                    float v0 = a[e] + bp[e], v1 = a[e + 1] + bp[e + 1];
-                    v0 = fmaxf(v0, v0 * sp); v1 = fmaxf(v1, v1 * sp);
-                    const __half2 hh = __floats2half2_rn(v0, v1);
-                    hv[e >> 1] = ok ? h2_bits(hh) : 0u;               // zero rows / columns: the convolution pads the ACTIVATED map
-                    if (ok) amax2 = __hmax2_nan(amax2, __habs2(hh));
+                for (int q = 0; q < PASSES; ++q) {
+                    const bool active = px + q * PXSTEP < w;
+                    const bool ok = active && (unsigned)(i0 + r) < (unsigned)h;
+                    const float a[8] = {t[2 * q].x, t[2 * q].y, t[2 * q].z, t[2 * q].w, t[2 * q + 1].x, t[2 * q + 1].y, t[2 * q + 1].z, t[2 * q + 1].w};
+                    uint32_t hv[4];
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        float v0 = a[e] + bp[e], v1 = a[e + 1] + bp[e + 1];
+                        v0 = fmaxf(v0, v0 * sp); v1 = fmaxf(v1, v1 * sp);
+                        const __half2 hh = __floats2half2_rn(v0, v1);
+                        hv[e >> 1] = ok ? h2_bits(hh) : 0u;           // zero rows / columns: the convolution pads the ACTIVATED map
+                        if (ok) amax2 = __hmax2_nan(amax2, __habs2(hh));
+                    }
+                    if (active) *reinterpret_cast<uint4*>(dst + (r * PITCH + q * PXSTEP) * 16) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
                 }
-                if (active) *reinterpret_cast<uint4*>(dst + r * PITCH * 16) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
             };
             // the first rows are requested BEFORE the wait for the buffer (they only need registers)
 #pragma unroll
@@ -183,15 +200,15 @@ upconv_tc_kernel(const __grid_constant__ Params P) {
                 const int buf = nb % NBUF;
                 mbar_wait(bar(B_BFULL + buf), (nb / NBUF) & 1);
                 const uint64_t ad0 = smem_desc_nosw(xa + buf * BATCH_BYTES, PLANE, 128);
-                const int npairs = min(BROWS / RPT, (h + 1 - bi * BROWS + RPT - 1) / RPT);   // tiles of RPT y4 rows in this batch
+                const int npairs = min(BROWS / RPT, (orows - bi * BROWS + RPT - 1) / RPT);   // tiles of RPT y4 rows in this batch
                 for (int k = 0; k < npairs; ++k, ++np) {
                     const int acc = np % NACC;
                     mbar_wait(bar(B_DFREE + acc), ((np / NACC) & 1) ^ 1);
                     tc_fence_after();
                     if (elect_one()) {
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const int u = t >> 1, v = t & 1;
+                        for (int t = 0; t < TAPS; ++t) {
+                            const int u = t / TAPW, v = t % TAPW;
 #pragma unroll
                             for (int kh = 0; kh < KSTEPS; ++kh)
                                 umma_f16(tmem + acc * NOUT,
@@ -217,13 +234,13 @@ upconv_tc_kernel(const __grid_constant__ Params P) {
         uint32_t np = 0;
         for (int n = blockIdx.x; n < P.N; n += gridDim.x) {
             for (int bi = 0; bi < nbatch; ++bi) {
-                const int npairs = min(BROWS / RPT, (h + 1 - bi * BROWS + RPT - 1) / RPT);
+                const int npairs = min(BROWS / RPT, (orows - bi * BROWS + RPT - 1) / RPT);
                 for (int k = 0; k < npairs; ++k, ++np) {
                     if ((int)(np % EPI_GROUPS) != grp) continue;
                     const int acc = np % NACC;
                     const int p = bi * BROWS + RPT * k;            // first y4 row of the tile
                     const int I = p + r2;
-                    const bool lane_ok = row < RPT * PITCH && I <= h && J <= w;
+                    const bool lane_ok = row < RPT * PITCH && (K3 ? (I < h && J < w) : (I <= h && J <= w));
                     mbar_wait_sleep(bar(B_DFULL + acc), (np / NACC) & 1, 100);
                     tc_fence_after();
                     const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc * NOUT;
@@ -280,20 +297,22 @@ upconv_tc_kernel(const __grid_constant__ Params P) {
                         // instruction.  Each lane parks its pixel in a per-warp staging row, then the warp writes 4 whole pixels per
                         // instruction (8 lanes x 16 B = one pixel's 128 contiguous bytes), addresses passed by shuffle.
                         uint8_t* wst = stage + (warp & 3) * (32 * 144);
+                        constexpr int NPH = K3 ? 1 : 4;                    // phases per accumulator (3x3: the tile's pixels themselves)
 #pragma unroll
-                        for (int ab = 0; ab < 4; ++ab) {
+                        for (int ab = 0; ab < NPH; ++ab) {
                             uint32_t r[32];
                             TMEM_LD32(taddr + 32 * ab, r);
                             tmem_wait_ld();
-                            if (ab == 3) {
+                            if (ab == NPH - 1) {
                                 tc_fence_before();
                                 __syncwarp();
                                 if (lane == 0) mbar_arrive(bar(B_DFREE + acc));
                             }
                             const int a = ab >> 1, b = ab & 1;
-                            const int Y = 2 * I - a, X = 2 * J - b;
-                            const bool ok = lane_ok && (unsigned)Y < (unsigned)H && (unsigned)X < (unsigned)W;
-                            const unsigned long long gp = ok ? (unsigned long long)(P.out + (((size_t)n * H + Y) * W + X) * (size_t)P.ctot) : 0ull;
+                            const int Y = K3 ? I : 2 * I - a, X = K3 ? J : 2 * J - b;
+                            const int OH = K3 ? h : H, OW = K3 ? w : W;
+                            const bool ok = lane_ok && (unsigned)Y < (unsigned)OH && (unsigned)X < (unsigned)OW;
+                            const unsigned long long gp = ok ? (unsigned long long)(P.out + (((size_t)n * OH + Y) * OW + X) * (size_t)P.ctot) : 0ull;
                             __syncwarp();                                  // the previous phase has been read out of the staging rows
 #pragma unroll
                             for (int c = 0; c < 32; c += 4) {
@@ -387,4 +406,20 @@ extern "C" int riders_upconv_tc_f32_nhwc(const float* x, const float* bias_p_hos
     P.ctot = ctot;
     P.status = status;
     return upconv_launch<upconv::Cfg<64, 32, 28, false>>(P, (cudaStream_t)stream, "upconv_tc_f32_nhwc");
+}
+
+extern "C" int riders_conv3x3_tc_f32_nhwc(const float* x, const float* bias_p_host, float slope_p, const void* w_pack,
+                                          int N, int h, int w, const float* bias_host, float slope, float* out, int ctot,
+                                          int* status, void* stream) {
+    using namespace riders;
+    upconv::Params P;
+    if (int rc = upconv_fill(P, x, bias_p_host, slope_p, w_pack, N, h, w, bias_host, slope, 64, 32, 56)) return rc;
+    RIDERS_REQUIRE(ctot >= 32 && ctot % 4 == 0, "conv3x3_tc_f32: the output pixel stride must be >= 32 channels and a multiple of 4 (got %d)", ctot);
+    if (N == 0) return RIDERS_OK;
+    RIDERS_REQUIRE(x && w_pack && out, "conv3x3_tc: null pointer");
+    RIDERS_REQUIRE(((((uintptr_t)x) | ((uintptr_t)w_pack) | ((uintptr_t)out)) & 15) == 0, "conv3x3_tc: 16-byte alignment");
+    P.out = out;
+    P.ctot = ctot;
+    P.status = status;
+    return upconv_launch<upconv::Cfg<64, 32, 56, false, true>>(P, (cudaStream_t)stream, "conv3x3_tc_f32_nhwc");
 }

@@ -677,6 +677,42 @@ def upconv_tc_f32(x, bias_p, slope_p, w2, bias_a, slope=0.2, skip=None, flag=Non
     return parent, flag
 
 
+_CONV3_CACHE = {}
+
+
+def _conv3x3_tc_weights(weight):
+    """(32,64,3,3) convolution weight -> the 36 KB fp16 B-operand image of riders_conv3x3_tc_f32_nhwc: for tap t = 3 ky + kx and K
+    step kh a K-major unswizzled 32 x 16 matrix [n // 8][k // 8][n % 8][k % 8] of W[n][16 kh + k][ky][kx]; cached per version."""
+    def make():
+        dev = weight.device
+        t = torch.arange(9, device=dev).view(9, 1, 1, 1, 1, 1)
+        kh = torch.arange(weight.shape[1] // 16, device=dev).view(1, -1, 1, 1, 1, 1)
+        ng = torch.arange(weight.shape[0] // 8, device=dev).view(1, 1, -1, 1, 1, 1)
+        kc = torch.arange(2, device=dev).view(1, 1, 1, 2, 1, 1)
+        nr = torch.arange(8, device=dev).view(1, 1, 1, 1, 8, 1)
+        ke = torch.arange(8, device=dev).view(1, 1, 1, 1, 1, 8)
+        return weight.detach().float()[ng * 8 + nr, kh * 16 + kc * 8 + ke, t // 3, t % 3].reshape(-1).to(torch.float16).contiguous()
+    return _cached(_CONV3_CACHE, weight, make)
+
+
+def conv3x3_tc_f32(x, weight, bias_p=None, slope_p=1.0, bias=None, slope=1.0, flag=None):
+    """3x3 convolution (stride 1, padding 1) 64 -> 32 channels on tcgen05 (fp16 operands staged once, nine taps as shifted views
+    of the staged rows, fp32 accumulation): out = act(conv(act_p(x + bias_p), weight) + bias), float32 channels_last; with the
+    defaults the RAW convolution output of an activated map.  x (N,64,H,W<=54) channels_last.  Returns (out, flag)."""
+    _need_cuda(x, weight)
+    N, Cc, H, W = x.shape
+    if not (_is_channels_last(x) and x.dtype == torch.float32 and Cc == 64 and tuple(weight.shape) == (32, 64, 3, 3) and W <= 54):
+        raise _lib.RidersError("conv3x3_tc_f32: needs a channels_last float32 (N,64,H,W<=54) map and a (32,64,3,3) weight")
+    out = torch.empty((N, 32, H, W), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+    if flag is None:
+        flag = torch.zeros(1, dtype=torch.int32, device=x.device)
+    with _span("conv3x3_tc", N * H * W * 64 * 32 * 9 * 2):
+        rc = _lib.lib().riders_conv3x3_tc_f32_nhwc(_ptr(x), _ptr(_host_floats(bias_p)), float(slope_p), _ptr(_conv3x3_tc_weights(weight)),
+                                                   N, H, W, _ptr(_host_floats(bias)), float(slope), _ptr(out), 32, _ptr(flag), _stream())
+    _lib.check(rc, "riders_conv3x3_tc_f32_nhwc")
+    return out, flag
+
+
 def decoder_tail_tc_half(yh, weight_b, bias_b, weight_head, slope=0.2, sigmoid=False, flag=None):
     """The tcgen05 decoder tail on the fp16 operand map of ``subpixel_conv_tc_half``: logits (N,1,2h,2w), flag."""
     _need_cuda(yh, weight_b)

@@ -1132,6 +1132,28 @@ def test_upconv_tcgen05_float_output_for_the_64_to_32_block(hw, N, Cs, raw, plac
     assert int(ops.upconv_tc_f32(xb, bp, sp, w2, ba, 0.2, skip)[1].item()) == 1            # staged value beyond the fp16 range
 
 
+@pytest.mark.parametrize("hw,N", [((120, 50), 3), ((8, 5), 1), ((13, 54), 2), ((120, 50), 300)])
+def test_conv3x3_tcgen05_instance_matches_torch(hw, N):
+    """ops.conv3x3_tc_f32: the 3x3 / nine-tap instance of the up-convolution kernel template (64 -> 32 channels, raw float32
+    out).  Not on the chain - it measures 1.56 ms against cuDNN's 1.23 ms per 2048 points (36 MMAs of N = 32 per tile re-read
+    the A operand) - but it is exported and therefore tested: fp32 summation order against torch on fp16-rounded operands."""
+    F = torch.nn.functional
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device=DEV).manual_seed(hw[0] + N)
+    h, w = hw
+    x = torch.randn((N, 64, h, w), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    wt = torch.randn((32, 64, 3, 3), device=DEV, generator=g) * 0.05
+    ref = F.conv2d(_fp16(x), _fp16(wt), None, 1, 1)
+    got, flag = ops.conv3x3_tc_f32(x, wt)
+    assert got.shape == ref.shape and ops._is_channels_last(got) and int(flag.item()) == 0
+    sc = float(ref.abs().max())
+    np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=3e-5 * sc)
+    assert float((got - F.conv2d(x, wt, None, 1, 1)).abs().max()) < 3e-3 * sc
+    b = torch.randn(32, device=DEV, generator=g) * 0.3
+    act, _ = ops.conv3x3_tc_f32(x, wt, bias=b, slope=0.2)
+    np.testing.assert_allclose(act.cpu().numpy(), F.leaky_relu(ref + b.view(1, -1, 1, 1), 0.2).cpu().numpy(), rtol=1e-5, atol=3e-5 * sc)
+
+
 def test_decoder_tail_tcgen05_fp16_range_guard():
     """Activations beyond the fp16 range (a limit neither the fp32 reference nor the TF32 kernel has) raise the device flag of
     riders_decoder_tail_tc_nhwc: ops.decoder_tail_tc then returns the mma.sync TF32 kernel's result (bit-identical to calling

@@ -23,6 +23,8 @@ w64 = torch.randn((128, 64, 2, 2), device=DEV, generator=g) * 0.1
 b32 = torch.randn(32, device=DEV, generator=g) * 0.1
 cat64 = torch.randn((R, 64, 120, 50), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
 skip32 = cat64[:, 32:]
+w3 = (torch.randn((32, 64, 3, 3), device=DEV, generator=g) * 0.05).contiguous(memory_format=torch.channels_last)
+torch.backends.cudnn.allow_tf32 = True
 
 
 def lib_l1():
@@ -33,6 +35,8 @@ for name, fn in (("phase convolution -> fp16 map", lambda: ops.subpixel_conv_tc_
                  ("bias_act of the 32-channel map", lambda: ops.bias_act_(x32, bp, 0.2)),
                  ("deconv1: cuDNN phase conv + d2s", lib_l1),
                  ("deconv1: upconv_tc_f32", lambda: ops.upconv_tc_f32(x64, None, 1.0, w64, b32, 0.2, skip32)),
+                 ("deconv1.conv 3x3 64->32: cuDNN TF32", lambda: torch.nn.functional.conv2d(cat64, w3, None, 1, 1)),
+                 ("deconv1.conv 3x3 64->32: tcgen05", lambda: ops.conv3x3_tc_f32(cat64, w3)),
                  ("tail on the fp16 map", None)):
     if fn is None:
         yh, _ = ops.subpixel_conv_tc_half(x32, w2, ba, 0.2)

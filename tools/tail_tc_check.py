@@ -133,6 +133,26 @@ def case_upconv_f32(N, h, w, Cs=32, raw=False, seed=0):
     return not bool(bad.any())
 
 
+def case_conv3(N, h, w, seed=0):
+    """conv3x3_tc_f32 (64 -> 32, raw output) against torch on fp16-rounded operands."""
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    x = torch.randn((N, 64, h, w), device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+    wt = torch.randn((32, 64, 3, 3), device=DEV, generator=g) * 0.05
+    ref = F.conv2d(h16(x), h16(wt), None, 1, 1)
+    got, flag = ops.conv3x3_tc_f32(x, wt)
+    torch.cuda.synchronize()
+    err = (got - ref).abs()
+    sc = float(ref.abs().max())
+    bad = err > 1e-4 * sc
+    print("conv3x3 N=%d h=%d w=%d: max err %.3e (scale %.2f) bad fraction %.5f flag %d" % (N, h, w, float(err.max()), sc, float(bad.float().mean()), int(flag.item())), flush=True)
+    if bool(bad.any()):
+        print("   first bad [n, c, Y, X]:", bad.nonzero()[:8].tolist(), flush=True)
+        rows = bad.any(dim=3).any(dim=1).any(dim=0).nonzero().flatten().tolist()
+        cols = bad.any(dim=2).any(dim=1).any(dim=0).nonzero().flatten().tolist()
+        print("   bad rows", rows[:40], "cols", cols[:40], flush=True)
+    return not bool(bad.any())
+
+
 if __name__ == "__main__":
     ok = True
     for N, h, w, taps in ((1, 8, 5, 3), (3, 7, 9, 2), (2, 13, 30, 3), (3, 120, 50, 2), (2, 40, 70, 3), (40, 120, 50, 2)):
@@ -143,4 +163,6 @@ if __name__ == "__main__":
         ok = case_upconv(N, h, w, raw=raw) and ok
     for N, h, w, Cs, raw in ((1, 8, 5, 32, False), (3, 7, 9, 0, True), (2, 13, 26, 8, True), (3, 60, 25, 32, False), (300, 60, 25, 32, False)):
         ok = case_upconv_f32(N, h, w, Cs, raw) and ok
+    for N, h, w in ((1, 8, 5), (3, 7, 9), (2, 13, 54), (3, 120, 50), (300, 120, 50)):
+        ok = case_conv3(N, h, w) and ok
     print("ALL OK" if ok else "MISMATCH", flush=True)
