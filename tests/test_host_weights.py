@@ -197,3 +197,32 @@ def test_upconv_weight_pack_and_its_cache():
     np.testing.assert_allclose(out.transpose(2, 0, 1), ref.numpy(), rtol=1e-5, atol=1e-5)
     frag = ops._subpixel_weight_fragments(w2)
     assert frag.dtype == torch.float32 and ops._upconv_tc_weights(w2) is pack and ops._subpixel_weight_fragments(w2) is frag
+
+
+def test_conv3x3_weight_pack_emulates_the_nine_tap_views():
+    """ops._conv3x3_tc_weights: [tap 3 ky + kx][K step][n // 8][k // 8][n % 8][k % 8] fp16; summing, over the nine taps and four K
+    steps, the products of the (row + ky, pixel + kx) views of the zero-padded map with these matrices is conv2d(x, W, padding 1)."""
+    torch.manual_seed(5)
+    wt = torch.randn(32, 64, 3, 3) * 0.1
+    pack = ops._conv3x3_tc_weights(wt)
+    assert pack.dtype == torch.float16 and pack.numel() * 2 == 9 * 4 * 32 * 32
+    raw = pack.numpy()
+
+    def b_matrix(t, kh):
+        m = np.zeros((32, 16), np.float32)
+        for n in range(32):
+            for k in range(16):
+                off = (t * 4 + kh) * 1024 + (n // 8) * 256 + (k // 8) * 128 + (n % 8) * 16 + (k % 8) * 2
+                m[n, k] = raw[off // 2]
+        return m
+    h, w = 4, 6
+    x = torch.randn(1, 64, h, w).half().float()
+    ref = F.conv2d(x, wt.half().float(), None, 1, 1)[0]
+    xp = F.pad(x, (1, 1, 1, 1))[0].permute(1, 2, 0).numpy()                    # staged rows: row i + 1, position j + 1
+    out = np.zeros((h, w, 32), np.float32)
+    for I in range(h):
+        for t in range(9):
+            ky, kx = t // 3, t % 3
+            for kh in range(4):
+                out[I] += xp[I + ky, kx:kx + w, 16 * kh:16 * kh + 16] @ b_matrix(t, kh).T
+    np.testing.assert_allclose(out.transpose(2, 0, 1), ref.numpy(), rtol=1e-5, atol=1e-5)
