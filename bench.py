@@ -202,8 +202,11 @@ def dtype_label(tf32):
         tail = os.environ.get("RIDERS_TAIL_IMPL", "tcgen05")
         fp16map = tail == "tcgen05" and os.environ.get("RIDERS_TAIL_FP16_MAP", "1") != "0"
         return ("tf32 (cuDNN backbone/decoder convolutions, torch's and the reference's GPU default) + "
-                + ("last up-convolution (TF32 tcgen05.mma) and fused decoder tail (tcgen05.mma, fp16 operands / fp32 accumulation: the "
-                   "same 11-bit significand as TF32, range-guarded) with an fp16 map between them" if fp16map else
+                + (("last two up-convolutions and fused decoder tail on tcgen05.mma with fp16 operands / fp32 accumulation (the same 11-bit "
+                    "significand as TF32, range-guarded; fp16 map between the last up-convolution and the tail)"
+                    if os.environ.get("RIDERS_TAIL_UPCONV", "1") != "0" else
+                    "last up-convolution (TF32 tcgen05.mma) and fused decoder tail (tcgen05.mma, fp16 operands / fp32 accumulation: the "
+                    "same 11-bit significand as TF32, range-guarded) with an fp16 map between them") if fp16map else
                    "fused decoder tail on tcgen05 with fp16 operands / fp32 accumulation (same 11-bit significand as TF32, range-guarded)"
                    if tail == "tcgen05" else "fused decoder tail on TF32 mma.sync") + " / "
                 "f32 (gather, LoFTR [fp16 hi/lo split, fp32-accurate], reduce, prologue) / f64 (alignment sums, barycentric fill)")
