@@ -87,7 +87,9 @@ __device__ __forceinline__ void ld4_stream_if(const float* p, bool on, float (&v
 }
 
 // PW > 0: crop width fixed at compile time (RC-Net's 100): immediate row offsets, constant address math
-template <bool LOGITS, int ROWS, int PW, int TILE_W>
+// SELECT = false (no `select` map asked for): the running maximum is one FMNMX instead of compare + two selects - the kernel is
+// issue-bound, and that is 2 of ~14 instructions per loaded confidence
+template <bool LOGITS, int ROWS, int PW, int TILE_W, bool SELECT>
 __global__ void __launch_bounds__(CR_THREADS)
 confidence_reduce_kernel(const float* __restrict__ conf, const float* __restrict__ pts,
                          const int* __restrict__ frame_offsets,
@@ -175,10 +177,22 @@ confidence_reduce_kernel(const float* __restrict__ conf, const float* __restrict
                 if (!any[u]) continue;                 // warp-uniform: none of this warp's rows meets the crop
 #pragma unroll
                 for (int m = 0; m < ROWS; ++m) {
-                    const float x = conf_value<LOGITS>(v[u][m], thr);
-                    if (x > best[m]) { best[m] = x; arg[m] = q[u].k; }          // first max wins
-                    sc[m] = __fadd_rn(sc[m], x);
-                    scz[m] = __fadd_rn(scz[m], __fmul_rn(x, q[u].z));           // (tile*z) then sum, rcnet_main.py:478
+                    if (SELECT) {
+                        const float x = conf_value<LOGITS>(v[u][m], thr);
+                        if (x > best[m]) { best[m] = x; arg[m] = q[u].k; }      // first max wins
+                        sc[m] = __fadd_rn(sc[m], x);
+                        scz[m] = __fadd_rn(scz[m], __fmul_rn(x, q[u].z));       // (tile*z) then sum, rcnet_main.py:478
+                    } else {
+                        // the same arithmetic under one predicate: a confidence below the cut contributes exactly 0 (adding +0
+                        // changes nothing), so the three updates are simply skipped - one select less per confidence
+                        float x = v[u][m];
+                        if (LOGITS) x = 1.0f / (1.0f + expf(-x));
+                        if (!(x < thr)) {
+                            best[m] = fmaxf(best[m], x);                        // same value (x >= 0, a NaN never replaces it)
+                            sc[m] = __fadd_rn(sc[m], x);
+                            scz[m] = __fadd_rn(scz[m], __fmul_rn(x, q[u].z));
+                        }
+                    }
                 }
             }
         }
@@ -192,7 +206,7 @@ confidence_reduce_kernel(const float* __restrict__ conf, const float* __restrict
                 const size_t o = frame_px + (size_t)r * W + col;
                 response[o] = best[m];
                 depth[o] = (best[m] == 0.0f) ? 0.0f : __fdiv_rn(scz[m], sc[m]);
-                if (select) select[o] = arg[m];
+                if (SELECT) select[o] = arg[m];
             }
         }
     }
@@ -207,10 +221,13 @@ template <bool LOGITS, int ROWS, int TW>
 static void launch_reduce_tw(const float* conf, const float* pts, const int* frame_offsets, int B, int H, int W, int ph, int pw,
                              float thr, float* depth, float* response, int32_t* select, cudaStream_t st) {
     dim3 grid(ceil_div(W, TW), ceil_div(H, (CR_THREADS / 32) * (32 / TW) * ROWS), B);
-    if (ROWS == 4 && pw == 100)                 // RC-Net's patch width (run_rcnet_zju.py:30)
-        confidence_reduce_kernel<LOGITS, ROWS, 100, TW><<<grid, CR_THREADS, 0, st>>>(conf, pts, frame_offsets, H, W, ph, pw, thr, depth, response, select);
-    else
-        confidence_reduce_kernel<LOGITS, ROWS, 0, TW><<<grid, CR_THREADS, 0, st>>>(conf, pts, frame_offsets, H, W, ph, pw, thr, depth, response, select);
+    if (ROWS == 4 && pw == 100) {               // RC-Net's patch width (run_rcnet_zju.py:30)
+        if (select) confidence_reduce_kernel<LOGITS, ROWS, 100, TW, true><<<grid, CR_THREADS, 0, st>>>(conf, pts, frame_offsets, H, W, ph, pw, thr, depth, response, select);
+        else confidence_reduce_kernel<LOGITS, ROWS, 100, TW, false><<<grid, CR_THREADS, 0, st>>>(conf, pts, frame_offsets, H, W, ph, pw, thr, depth, response, select);
+    } else {
+        if (select) confidence_reduce_kernel<LOGITS, ROWS, 0, TW, true><<<grid, CR_THREADS, 0, st>>>(conf, pts, frame_offsets, H, W, ph, pw, thr, depth, response, select);
+        else confidence_reduce_kernel<LOGITS, ROWS, 0, TW, false><<<grid, CR_THREADS, 0, st>>>(conf, pts, frame_offsets, H, W, ph, pw, thr, depth, response, select);
+    }
 }
 
 template <bool LOGITS, int ROWS>
