@@ -48,7 +48,11 @@ template <int CIN_, int COUT_, int PITCH_, bool HALF_OUT_, bool K3_ = false> str
     static constexpr int XROWS = BROWS + TAPW - 1;                        // input rows staged per batch of BROWS output (y4) rows
     static constexpr int RPT = 112 / PITCH;                               // output (y4) rows per M = 128 tile
     static constexpr int NPLANES = CIN / 8, KSTEPS = CIN / 16;
-    static constexpr int PLANE_POS = (((BROWS - RPT + TAPW - 1) * PITCH + (TAPW - 1) + 128) + 7) / 8 * 8;   // staged rows + the reach of the last view
+    // staged rows + the reach of the last view.  The staging stores are 16 bytes per lane, processed a quarter warp at a time:
+    // its 8 lanes are 1 pixel x 8 planes (CIN 64) or 2 adjacent pixels x 4 planes (CIN 32), so the plane stride is made 16 /
+    // 32 bytes mod 128 - the 8 lanes then fall into 8 different 16-byte bank groups (a stride of 0 mod 128 was an 8- / 4-way
+    // conflict on every store: ncu counted 3x the ideal shared-memory wavefronts)
+    static constexpr int PLANE_POS = (((BROWS - RPT + TAPW - 1) * PITCH + (TAPW - 1) + 128) + 7) / 8 * 8 + (CIN / 8 == 8 ? 1 : 2);
     static constexpr int PLANE = PLANE_POS * 16;
     static constexpr int BATCH_BYTES = NPLANES * PLANE;
     static constexpr int W_BYTES = TAPS * KSTEPS * NOUT * 32;             // taps x K steps x (NOUT rows x 16 fp16)

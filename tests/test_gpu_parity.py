@@ -1135,7 +1135,7 @@ def test_upconv_tcgen05_float_output_for_the_64_to_32_block(hw, N, Cs, raw, plac
 @pytest.mark.parametrize("hw,N", [((120, 50), 3), ((8, 5), 1), ((13, 54), 2), ((120, 50), 300)])
 def test_conv3x3_tcgen05_instance_matches_torch(hw, N):
     """ops.conv3x3_tc_f32: the 3x3 / nine-tap instance of the up-convolution kernel template (64 -> 32 channels, raw float32
-    out).  Not on the chain - it measures 1.56 ms against cuDNN's 1.23 ms per 2048 points (36 MMAs of N = 32 per tile re-read
+    out).  Not on the chain - it measures 1.43 ms against cuDNN's 1.21 ms per 2048 points (36 MMAs of N = 32 per tile re-read
     the A operand) - but it is exported and therefore tested: fp32 summation order against torch on fp16-rounded operands."""
     F = torch.nn.functional
     torch.backends.cudnn.allow_tf32 = False
