@@ -6,9 +6,10 @@
 //     logits = conv3x3(z; Wh)        [-> sigmoid]              output0, 16 -> 1, no bias
 //
 // as a streaming pipeline: a CTA owns a strip of one radar point's map (all 240 rows x up to 124 columns) and walks down it
-// row by row; y and z rows live in small shared-memory rings, nothing but y4 (64 B per output pixel) is read and nothing but
-// the logits (4 B) is written, and no row is ever computed twice (the mma.sync kernel recomputes a 2-pixel halo per 12 x 50
-// tile: +44 % work).
+// row by row; y and z rows live in small shared-memory rings, nothing but the input map is read (the fp16 operand map of
+// upconv_tc.cu / subpixel_conv_tc.cu: 32 B per output pixel, its rows bulk-copied straight into the y ring; or a float y4 from a
+// library phase convolution: 64 B, staged through registers) and nothing but the logits (4 B) is written, and no row is ever
+// computed twice (the mma.sync kernel recomputes a 2-pixel halo per 12 x 50 tile: +44 % work).
 //
 // Both convolutions are implicit GEMMs whose A operand is a SHIFTED VIEW of a staged row:
 //   * an operand row slot holds 128 (+2) consecutive pixels of one image row as two planes of 16-byte chunks (8 fp16 channels
@@ -18,9 +19,9 @@
 //     K = 16 input channels, no im2col, no copies;
 //   * the vertical taps ride in N: for y row r the B operand of tap dx stacks the three kernel rows, N = 3 x 16 output channels,
 //     and the three 16-column blocks of D accumulate into the TMEM accumulators of z rows r+1, r, r-1 (a ring of twelve
-//     16-column accumulators laid out so that the three targets are adjacent columns).  One z row costs 3-4 MMAs
-//     (128 x 48 x 16) instead of the 9 x 2 x 8 mma.sync.m16n8k8 per 16 pixels of the legacy kernel, and its epilogue reads 16
-//     finished columns;
+//     16-column accumulators laid out so that the three targets are adjacent columns; every MMA accumulates, the epilogue
+//     zeroes an accumulator right after reading it).  One z row costs 3 MMAs (128 x 48 x 16; 6 where the ring wraps) instead of
+//     the 9 x 2 x 8 mma.sync.m16n8k8 per 16 pixels of the legacy kernel, and its epilogue reads 16 finished columns;
 //   * the 16 -> 1 head is the same construction with N = 16 (columns 0..2 = the head's three kernel rows): three MMAs per z row,
 //     logits[o] = Dh[o-1][0] + Dh[o][1] + Dh[o+1][2] read back one column each.
 // Operands are fp16 (11-bit significand, the same as the TF32 the cuDNN flow and decoder_tail.cu use) with fp32 accumulation;
