@@ -64,6 +64,40 @@ prologue_pad_kernel(const float* __restrict__ image, int B, int C, int H, int W,
     }
 }
 
+// The same pass for the usual case - 3 channels, channels-last out - without per-element 64-bit index arithmetic: blockIdx =
+// (column block, padded row, frame), thread = padded pixel: three plane reads that are coalesced over the warp (the element-wise
+// form read the three planes interleaved lane by lane) and one contiguous 12-byte store per thread.  Same arithmetic, bit for bit.
+__global__ void __launch_bounds__(PR_THREADS)
+prologue_pad3_nhwc_kernel(const float* __restrict__ image, int H, int W, int px, int py, const int32_t* __restrict__ flags,
+                          float* __restrict__ out) {
+    const int Hp = H + 2 * py, Wp = W + 2 * px;
+    const int xx = blockIdx.x * PR_THREADS + threadIdx.x, yy = blockIdx.y, b = blockIdx.z;
+    if (xx >= Wp) return;
+    const int sx = min(max(xx - px, 0), W - 1), sy = min(max(yy - py, 0), H - 1);
+    const float* src = image + ((size_t)b * 3 * H + sy) * W + sx;
+    const size_t plane = (size_t)H * W;
+    float v0 = __ldg(src), v1 = __ldg(src + plane), v2 = __ldg(src + 2 * plane);
+    if (flags[b]) { v0 = (float)(int)v0; v1 = (float)(int)v1; v2 = (float)(int)v2; }      // Tensor.int(): truncation toward zero
+    float* o = out + (((size_t)b * Hp + yy) * Wp + xx) * 3;
+    o[0] = __fdiv_rn(v0, 255.0f); o[1] = __fdiv_rn(v1, 255.0f); o[2] = __fdiv_rn(v2, 255.0f);
+}
+
+// points / RoI rows alone (the pixel part of prologue_pad_kernel is taken by prologue_pad3_nhwc_kernel)
+__global__ void __launch_bounds__(PR_THREADS)
+prologue_points_kernel(int B, int px, int py, const float* __restrict__ points, const int32_t* __restrict__ frame_offsets, int R,
+                       float* __restrict__ points_out, float* __restrict__ rois) {
+    const long long tid = (long long)blockIdx.x * PR_THREADS + threadIdx.x;
+    if (tid >= R) return;
+    const float x = __fadd_rn(points[tid * 3 + 0], (float)px), y = __fadd_rn(points[tid * 3 + 1], (float)py);
+    points_out[tid * 3 + 0] = x; points_out[tid * 3 + 1] = y; points_out[tid * 3 + 2] = points[tid * 3 + 2];
+    int lo = 0, hi = B;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (frame_offsets[mid] <= (int)tid) lo = mid; else hi = mid; }
+    float* r = rois + tid * 5;
+    r[0] = (float)lo;
+    r[1] = __fsub_rn(x, (float)px); r[2] = __fsub_rn(y, (float)py);
+    r[3] = __fadd_rn(x, (float)px); r[4] = __fadd_rn(y, (float)py);
+}
+
 __global__ void __launch_bounds__(PR_THREADS)
 sml_input_kernel(const float* __restrict__ int_depth, const float* __restrict__ int_scales, const float* __restrict__ image,
                  int hwc, int B, int H, int W, int oh, int ow, double ify, double ifx,
@@ -112,7 +146,14 @@ extern "C" int riders_rcnet_prologue(const float* image, int B, int C, int H, in
     const long long cap = (long long)sm_count() * 16, need = ((long long)R + PR_THREADS - 1) / PR_THREADS;
     if (blocks > cap) blocks = cap;
     if (blocks < need) blocks = need;
-    if (out_layout == RIDERS_LAYOUT_NHWC)
+    if (out_layout == RIDERS_LAYOUT_NHWC && C == 3 && H + 2 * pad_y <= 65535 && B <= 65535) {
+        if (R > 0) {
+            count_launches(1);
+            prologue_points_kernel<<<(unsigned)need, PR_THREADS, 0, st>>>(B, pad_x, pad_y, points, frame_offsets, R, points_shifted, rois);
+        }
+        prologue_pad3_nhwc_kernel<<<dim3(ceil_div(W + 2 * pad_x, PR_THREADS), H + 2 * pad_y, B), PR_THREADS, 0, st>>>(
+            image, H, W, pad_x, pad_y, frame_flags, padded);
+    } else if (out_layout == RIDERS_LAYOUT_NHWC)
         prologue_pad_kernel<true><<<(unsigned)blocks, PR_THREADS, 0, st>>>(image, B, C, H, W, pad_x, pad_y, frame_flags, points,
                                                                         frame_offsets, R, padded, points_shifted, rois);
     else
