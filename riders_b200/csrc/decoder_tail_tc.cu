@@ -287,30 +287,29 @@ decoder_tail_tc_kernel(const float4* __restrict__ y4, const uint4* __restrict__ 
         const int lg = (warp - W_EPI2) & 3, grp = (warp - W_EPI2) >> 2, x = lg * 32 + lane;   // TMEM lane = output position; image column C0 + x
         const bool ok = x < TC && C0 + x < W;
         const uint32_t trow = tmem + ((uint32_t)(lg * 32) << 16) + DH_COL0;
-        static_assert(NDH == 4, "head ring indices are masked");
         const int q0 = R0 - zlo, q1 = R1 - zlo;           // q = o - zlo: z row of the output row, 0 <= q < nz
         if (EPI2_GROUPS > 1 && grp == 0 && lane == 0) {
             for (int j = 0; j < 2 && j < nz; ++j)
                 for (int r = j - 1; r <= j + 1; ++r)
-                    if (r < q0) mbar_arrive(bar(B_HFREE + (j & 3)));
+                    if (r < q0) mbar_arrive(bar(B_HFREE + j % NDH));
         }
         float* op = out + (size_t)n * H * W + (size_t)(R0 + grp) * W + (ok ? C0 + x : 0);
         for (int q = q0 + grp; q < q1; q += EPI2_GROUPS, op += EPI2_GROUPS * W) {
             const int hq = min(q + 1, nz - 1);
-            mbar_wait_sleep(bar(B_HFULL + (hq & 3)), (hq >> 2) & 1, 100);
+            mbar_wait_sleep(bar(B_HFULL + hq % NDH), (hq / NDH) & 1, 100);
             tc_fence_after();
             uint32_t v0 = 0u, v1 = 0u, v2 = 0u;
-            if (q >= 1) TMEM_LD1(trow + 16 * ((q - 1) & 3) + 0, v0);
-            TMEM_LD1(trow + 16 * (q & 3) + 1, v1);
-            if (q + 1 < nz) TMEM_LD1(trow + 16 * ((q + 1) & 3) + 2, v2);
+            if (q >= 1) TMEM_LD1(trow + 16 * ((q - 1) % NDH) + 0, v0);
+            TMEM_LD1(trow + 16 * (q % NDH) + 1, v1);
+            if (q + 1 < nz) TMEM_LD1(trow + 16 * ((q + 1) % NDH) + 2, v2);
             tmem_wait_ld();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (q >= 1) mbar_arrive(bar(B_HFREE + ((q - 1) & 3)));
+                if (q >= 1) mbar_arrive(bar(B_HFREE + (q - 1) % NDH));
                 if (EPI2_GROUPS > 1) {
-                    mbar_arrive(bar(B_HFREE + (q & 3)));
-                    if (q + 1 < nz) mbar_arrive(bar(B_HFREE + ((q + 1) & 3)));
+                    mbar_arrive(bar(B_HFREE + q % NDH));
+                    if (q + 1 < nz) mbar_arrive(bar(B_HFREE + (q + 1) % NDH));
                 }
             }
             const float sum = (__uint_as_float(v0) + __uint_as_float(v1)) + __uint_as_float(v2);
