@@ -226,3 +226,22 @@ def test_conv3x3_weight_pack_emulates_the_nine_tap_views():
             for kh in range(4):
                 out[I] += xp[I + ky, kx:kx + w, 16 * kh:16 * kh + 16] @ b_matrix(t, kh).T
     np.testing.assert_allclose(out.transpose(2, 0, 1), ref.numpy(), rtol=1e-5, atol=1e-5)
+
+
+def test_decoder_block_takes_a_raw_input_with_its_activation():
+    """DecoderBlock.forward(x_act=(bias, slope)): ``x`` is the RAW output of the previous block's convolution (the hand-over
+    ops.upconv_tc_f32 uses on the GPU); when that kernel does not take the call the block applies bias + LeakyReLU itself -
+    on the CPU that is the only path: same result as feeding the activated map."""
+    torch.manual_seed(9)
+    blk = networks.DecoderBlock(8, 4, 4, 'kaiming_uniform', 'leaky_relu', False).eval()
+    x = torch.randn(2, 8, 5, 7)
+    skip = torch.randn(2, 4, 10, 14)
+    b = torch.randn(8) * 0.3
+    with torch.no_grad():
+        ref = blk(F.leaky_relu(x + b.view(1, -1, 1, 1), 0.2), skip)
+        got = blk(x, skip, x_act=(b, 0.2))
+        same = blk(x, skip, x_act=(None, 1.0))
+        plain = blk(x, skip)
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=1e-6, atol=1e-6)
+    assert torch.equal(same, plain) and not blk.upconv_tc and not blk.last_used_upconv_tc
+    assert not blk.upconv_tc_ok(x.shape, (10, 14))
